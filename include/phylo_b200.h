@@ -1,0 +1,178 @@
+/*
+ * phylo_b200 — C ABI of the B200-native phylogenetic-likelihood hot path.
+ *
+ * This is the drop-in boundary for ONE path of biocaml/phylogenetics (OCaml):
+ * Felsenstein pruning over a rooted tree with the reference's underflow
+ * rescaling, and the per-branch transition matrices P(t) = exp(Qt).
+ * The reference has no FFI of its own; the entry points below
+ * are what OCaml C stubs over Bigarray buffers bind (see INTEGRATION.md and
+ * ocaml/phylo_b200_stubs.c).  Plain C: pointers and sizes only.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   Phylo_ctmc.pruning                     lib/phylo_ctmc.mli:55-61   (lib/phylo_ctmc.ml:83-98)
+ *   Phylo_ctmc.conditional_likelihoods     lib/phylo_ctmc.mli:68-73   (lib/phylo_ctmc.ml:100-120)
+ *   Phylo_ctmc.Missing_values/Ambiguous    lib/phylo_ctmc.ml:145-172, :280-302
+ *   Felsenstein.Make(..).felsenstein       lib/felsenstein.mli:11-48  (lib/felsenstein.ml:22-78)
+ *   Site_evolution_model.S.transition_probability_matrix
+ *                                          lib/site_evolution_model.mli:7-14 (.ml:27-51)
+ *   Rate_matrix.transition_probability_matrix  lib/rate_matrix.mli:73-76 (.ml:132-138)
+ *   Mutsel.transition_probability_matrix   lib/mutsel.mli:59 (.ml:96-97)
+ *   Matrix.expm                            lib/linear_algebra.ml:308-404
+ *
+ * Conventions
+ *   - All matrices cross this ABI COLUMN-MAJOR, element (i,j) at [j*n + i], the
+ *     layout of the reference's Lacaml/Bigarray `mat` (lib/linear_algebra.ml:151-152).
+ *     P(i,j) = Prob(child state j | parent state i): rows sum to 1.
+ *   - Every function returns PB_OK (0) or a negative pb_status; the message is
+ *     available from pb_last_error().  Nothing aborts, exits or throws across
+ *     the ABI.  An OCaml wrapper maps PB_ERR_INVALID_ARG to Invalid_argument and
+ *     the rest to Failure (the reference's conventions).
+ *   - One context = one caller thread.  Device work is enqueued on the context's
+ *     CUDA stream; the blocking entry points synchronise that stream only.
+ *   - There is no CPU fallback: every compute entry point fails with
+ *     PB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PHYLO_B200_H
+#define PHYLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+typedef enum {
+    PB_OK = 0,
+    PB_ERR_INVALID_ARG = -1,   /* -> OCaml Invalid_argument */
+    PB_ERR_CUDA = -2,          /* CUDA runtime / no device */
+    PB_ERR_STATE = -3,         /* call order: something required was not set */
+    PB_ERR_NOMEM = -4,
+    PB_ERR_NCCL = -5,
+    PB_ERR_NUMERIC = -6        /* e.g. rate matrix not reversible for the eigen path */
+} pb_status;
+
+/* pb_create flags */
+#define PB_FLAG_KEEP_CLV      0x1u  /* level-scheduled path; every node's conditional-likelihood
+                                       array stays resident (pb_get_clv, partial re-evaluation) */
+#define PB_FLAG_LEVEL_KERNELS 0x2u  /* force the level-scheduled path even when the fused
+                                       site-resident kernel applies (buffers are recycled) */
+
+/* Root / rescaling conventions (pb_set_mode) */
+#define PB_MODE_PHYLO_CTMC   0  /* SV.shift threshold 1e-6, root product with pi is shifted
+                                   (lib/phylo_ctmc.ml:33,97) */
+#define PB_MODE_FELSENSTEIN  1  /* shift_normal threshold 1e-7, no shift after x pi
+                                   (lib/felsenstein.ml:47-48,64) */
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* nstates 2..64, ncat >= 1 (1 = the reference; >1 = rate-category mixture),
+ * nsites >= 1 columns held by THIS context (a site shard when multi-GPU),
+ * ntaxa = rows of the tip matrix.  Returns NULL on failure (pb_last_error(NULL)). */
+pb_ctx *pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, unsigned flags);
+void pb_destroy(pb_ctx *ctx);
+/* ctx may be NULL: last error of a failed pb_create on this thread. */
+const char *pb_last_error(const pb_ctx *ctx);
+/* Enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of
+ * the context's own.  NULL restores the private stream. */
+int pb_set_stream(pb_ctx *ctx, void *cuda_stream);
+int pb_set_mode(pb_ctx *ctx, int mode);
+/* Explicit threshold / root-shift, overriding pb_set_mode. */
+int pb_set_rescaling(pb_ctx *ctx, double threshold, int shift_at_root);
+
+/* ---- inputs ----------------------------------------------------------- */
+
+/* Rooted tree of arbitrary arity >= 1 (Tree.t, lib/tree.ml:3-13) flattened by the
+ * caller: node v's children are child_idx[child_ptr[v] .. child_ptr[v+1]) IN THE
+ * REFERENCE'S BRANCH ORDER (the left fold of lib/phylo_ctmc.ml:94-95 follows it);
+ * leaves have no children and tip_row[v] = their row in the tip matrix (else -1).
+ * branch_len[v] is the length of the branch above v (ignored for the root; may
+ * be NULL when matrices are supplied with pb_set_pmatrices).  Branch "b" is
+ * identified everywhere by the node id at its lower end. */
+int pb_set_tree(pb_ctx *ctx, int nnodes, int root, const int32_t *child_ptr,
+                const int32_t *child_idx, const int32_t *tip_row, const double *branch_len);
+int pb_set_branch_lengths(pb_ctx *ctx, const double *branch_len /* [nnodes] */);
+
+/* Observed states, one byte per (taxon, site): states[row*ld + site] in 0..nstates-1
+ * (`leaf_state`, lib/phylo_ctmc.mli:58; evaluated eagerly by the caller).  Host memory. */
+int pb_set_tips(pb_ctx *ctx, const uint8_t *states, int64_t ld);
+/* Same, from a device pointer (copied device-to-device on the context's stream). */
+int pb_set_tips_device(pb_ctx *ctx, const uint8_t *d_states, int64_t ld);
+/* State SETS per (taxon, site): bit i set = state i compatible (Ambiguous.leaf_indicator,
+ * lib/phylo_ctmc.ml:234-242); 0 = missing observation (Missing_values: leaf_state = None). */
+int pb_set_tip_masks(pb_ctx *ctx, const uint64_t *masks, int64_t ld);
+
+int pb_set_root_frequencies(pb_ctx *ctx, const double *pi /* [nstates] */);
+/* Rate categories: branch lengths are multiplied by rates[k]; site likelihood =
+ * sum_k weights[k] * L_k.  (Extension: the reference has no rate heterogeneity.) */
+int pb_set_categories(pb_ctx *ctx, const double *rates, const double *weights /* [ncat] */);
+
+/* P(t) = U diag(exp(t*lambda)) Uinv  — the decomposition Site_evolution_model.Make_diag
+ * stages once (lib/site_evolution_model.ml:43-47), e.g. JC69/K80 reductions (:57-73,:97-117).
+ * P matrices are rebuilt ON DEVICE for every branch x category in one launch. */
+int pb_set_eigensystem(pb_ctx *ctx, const double *U, const double *lambda, const double *Uinv);
+/* Reversible rate matrix Q with stationary distribution pi: the library
+ * symmetrises (S = D^1/2 Q D^-1/2, D = diag pi), diagonalises S on the host (one n x n
+ * Jacobi, cf. Matrix.diagonalize lib/linear_algebra.ml:238-241) and installs the
+ * eigensystem.  PB_ERR_NUMERIC if pi_i q_ij != pi_j q_ji. */
+int pb_set_rate_matrix(pb_ctx *ctx, const double *Q, const double *pi);
+/* General (possibly non-reversible) rate matrix: P(t) = expm(t*r_k*Q) for every branch x
+ * category by a batched Pade-13 scaling-and-squaring kernel (Matrix.expm,
+ * lib/linear_algebra.ml:308-404; callers lib/site_evolution_model.ml:31-32, lib/mutsel.ml:96-97). */
+int pb_set_rate_matrix_general(pb_ctx *ctx, const double *Q);
+/* Caller-built matrices ([`Mat p] of lib/phylo_ctmc.ml:4-8): P[(k*nnodes + v)*n*n ...],
+ * column-major each, for category k and the branch above node v (root's is ignored). */
+int pb_set_pmatrices(pb_ctx *ctx, const double *P);
+
+/* ---- evaluation ------------------------------------------------------- */
+
+/* Sum over sites of the log-likelihood (Felsenstein.felsenstein / sum of
+ * Phylo_ctmc.pruning) and, when per_site != NULL, each site's value [nsites].
+ * Blocking; results are host memory. */
+int pb_loglik(pb_ctx *ctx, double *total, double *per_site);
+/* Non-blocking half: enqueue P(t) + pruning + root reduction on the stream. */
+int pb_loglik_enqueue(pb_ctx *ctx);
+/* Blocking half: wait for the stream and fetch.  per_site may be NULL. */
+int pb_loglik_fetch(pb_ctx *ctx, double *total, double *per_site);
+/* Device pointers of the last evaluation's results (valid until the next call):
+ * total (1 double) and per-site log-likelihoods [nsites]. */
+int pb_result_device_ptrs(pb_ctx *ctx, const double **d_total, const double **d_per_site);
+
+/* Conditional-likelihood array of one node (needs PB_FLAG_KEEP_CLV and a prior
+ * evaluation): v[site*nstates + i] and carry[site] for category cat, i.e. the
+ * shifted_vector SV (v, carry) of lib/phylo_ctmc.ml:26 per site.  For a leaf the
+ * indicator vector with carry 0. */
+int pb_get_clv(pb_ctx *ctx, int node, int cat, double *v, double *carry);
+/* Copy out the matrices in use: P[(k*nnodes + v)*n*n ...] column-major. */
+int pb_get_pmatrices(pb_ctx *ctx, double *P);
+
+/* How many kernels of this library the context has launched so far. */
+int64_t pb_kernel_launches(const pb_ctx *ctx);
+/* Which pruning path the next pb_loglik takes: "fused4", "level4", "level_dense", ... */
+const char *pb_path_name(const pb_ctx *ctx);
+
+/* ---- stand-alone P(t) producers (no context) -------------------------- */
+
+/* out[m] = U diag(exp(t[m]*lambda)) Uinv for m < count, one launch on `device`.
+ * Site_evolution_model.Make_diag.transition_probability_matrix (.ml:43-47). */
+int pb_transition_matrices_eigen(int device, int n, int count, const double *U,
+                                 const double *lambda, const double *Uinv,
+                                 const double *t, double *out);
+/* out[m] = expm(t[m] * Q), batched Pade on `device`.
+ * Rate_matrix.transition_probability_matrix ~tau ~rates (lib/rate_matrix.ml:132-138). */
+int pb_transition_matrices_expm(int device, int n, int count, const double *Q,
+                                const double *t, double *out);
+
+/* ---- host-side helpers (no GPU; exposed for callers without LAPACK) ---- */
+
+/* Eigen-decomposition of a reversible Q as used by pb_set_rate_matrix. */
+int pb_host_reversible_eigensystem(int n, const double *Q, const double *pi,
+                                   double *U, double *lambda, double *Uinv);
+
+const char *pb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLO_B200_H */

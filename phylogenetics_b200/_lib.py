@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI (include/phylo_b200.h).
+
+The shared library is built in-tree (``python -m phylogenetics_b200.build``) and
+loaded from this directory.  There is no fallback: if the library is missing the
+import fails, and every compute entry point fails when no B200 is present.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphylo_b200.so")
+
+PB_OK = 0
+PB_ERR_INVALID_ARG = -1
+PB_ERR_CUDA = -2
+PB_ERR_STATE = -3
+PB_ERR_NOMEM = -4
+PB_ERR_NCCL = -5
+PB_ERR_NUMERIC = -6
+
+PB_FLAG_KEEP_CLV = 0x1
+PB_FLAG_LEVEL_KERNELS = 0x2
+PB_MODE_PHYLO_CTMC = 0
+PB_MODE_FELSENSTEIN = 1
+
+# Every symbol include/phylo_b200.h declares (tests check the .so exports them all).
+EXPORTS = [
+    "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_set_mode", "pb_set_rescaling",
+    "pb_set_tree", "pb_set_branch_lengths", "pb_set_tips", "pb_set_tips_device", "pb_set_tip_masks",
+    "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
+    "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_enqueue",
+    "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_get_pmatrices",
+    "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
+    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
+]
+
+
+class PhyloB200Error(RuntimeError):
+    """Failure reported by the native library (maps to OCaml Failure)."""
+
+    def __init__(self, code, message):
+        super().__init__("phylo_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class PhyloB200InvalidArgument(PhyloB200Error, ValueError):
+    """PB_ERR_INVALID_ARG (maps to OCaml Invalid_argument)."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "phylogenetics_b200: %s is missing. Build it with `python -m phylogenetics_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    sig = {
+        "pb_create": (vp, [ci, ci, ci, i64, ci, ctypes.c_uint]),
+        "pb_destroy": (None, [vp]),
+        "pb_last_error": (ctypes.c_char_p, [vp]),
+        "pb_set_stream": (ci, [vp, vp]),
+        "pb_set_mode": (ci, [vp, ci]),
+        "pb_set_rescaling": (ci, [vp, dbl, ci]),
+        "pb_set_tree": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+        "pb_set_branch_lengths": (ci, [vp, vp]),
+        "pb_set_tips": (ci, [vp, vp, i64]),
+        "pb_set_tips_device": (ci, [vp, vp, i64]),
+        "pb_set_tip_masks": (ci, [vp, vp, i64]),
+        "pb_set_root_frequencies": (ci, [vp, vp]),
+        "pb_set_categories": (ci, [vp, vp, vp]),
+        "pb_set_eigensystem": (ci, [vp, vp, vp, vp]),
+        "pb_set_rate_matrix": (ci, [vp, vp, vp]),
+        "pb_set_rate_matrix_general": (ci, [vp, vp]),
+        "pb_set_pmatrices": (ci, [vp, vp]),
+        "pb_loglik": (ci, [vp, vp, vp]),
+        "pb_loglik_enqueue": (ci, [vp]),
+        "pb_loglik_fetch": (ci, [vp, vp, vp]),
+        "pb_result_device_ptrs": (ci, [vp, vp, vp]),
+        "pb_get_clv": (ci, [vp, ci, ci, vp, vp]),
+        "pb_get_pmatrices": (ci, [vp, vp]),
+        "pb_kernel_launches": (i64, [vp]),
+        "pb_path_name": (ctypes.c_char_p, [vp]),
+        "pb_transition_matrices_eigen": (ci, [ci, ci, ci, vp, vp, vp, vp, vp]),
+        "pb_transition_matrices_expm": (ci, [ci, ci, ci, vp, vp, vp]),
+        "pb_host_reversible_eigensystem": (ci, [ci, vp, vp, vp, vp, vp]),
+        "pb_version": (ctypes.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
+lib = _load()
+
+
+def check(rc, ctx=None):
+    """Raise on a negative status, with the library's message."""
+    if rc == PB_OK:
+        return
+    msg = lib.pb_last_error(ctx)
+    msg = msg.decode() if msg else ""
+    if rc == PB_ERR_INVALID_ARG:
+        raise PhyloB200InvalidArgument(rc, msg)
+    raise PhyloB200Error(rc, msg)

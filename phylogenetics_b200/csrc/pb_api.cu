@@ -1,0 +1,899 @@
+// C-ABI implementation of include/phylo_b200.h: context, tree compiler, launches.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/phylo_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pb_kernels.cuh"
+#include "pb_kernels_dmma.cuh"
+#include "pb_kernels_expm.cuh"
+#include "pb_host_linalg.h"
+
+using pbk::FusedOp;
+using pbk::LevelChild;
+using pbk::LevelNode;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum PSource { PSRC_NONE = 0, PSRC_EIGEN = 1, PSRC_DIRECT = 2, PSRC_EXPM = 3 };
+enum Path { PATH_FUSED4 = 0, PATH_LEVEL4 = 1, PATH_LEVEL_DENSE = 2, PATH_LEVEL_DMMA = 3 };
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= count && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) count = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct pb_ctx {
+    int device = 0, n = 0, ncat = 1, ntaxa = 0;
+    int64_t nsites = 0, spad = 0;
+    unsigned flags = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double threshold = 1e-6;
+    int shift_at_root = 1;
+    mutable std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // tree
+    int nnodes = 0, root = -1;
+    std::vector<int> child_ptr, child_idx, tip_row, parent;
+    std::vector<double> branch_len;
+    bool have_tree = false, have_blen = false;
+
+    // compiled schedules
+    std::vector<LevelNode> lv_nodes;
+    std::vector<LevelChild> lv_children;
+    std::vector<int> lv_first;          // first LevelNode of every level (+ end)
+    std::vector<int> slot_of_node;      // CLV slot of every internal node (level path)
+    int nslots = 0, max_arity = 0;
+    std::vector<FusedOp> fprog;
+    int fstack = 0;
+    DevBuf<LevelNode> d_lv_nodes;
+    DevBuf<LevelChild> d_lv_children;
+    DevBuf<FusedOp> d_fprog;
+
+    // inputs
+    DevBuf<uint8_t> d_tips;
+    DevBuf<uint64_t> d_masks;
+    bool have_tips = false, have_masks = false;
+    DevBuf<double> d_pi, d_rates, d_weights, d_blen;
+    bool have_pi = false;
+    std::vector<double> h_rates, h_weights;
+    DevBuf<double> d_U, d_lambda, d_Uinv, d_Q;
+    DevBuf<double> d_P;
+    int psrc = PSRC_NONE;
+    bool p_dirty = true;
+
+    // work + outputs
+    DevBuf<double> d_pool, d_site_cat, d_per_site, d_partials, d_total;
+    int64_t slot_stride = 0;
+    double* h_total = nullptr;   // pinned
+    bool evaluated = false;
+};
+
+namespace {
+
+int fail(pb_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(pb_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, PB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PB_CUDA(c, call)                                         \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// Column-major (ABI) -> row-major (device) for a batch of n x n matrices.
+void to_row_major(int n, size_t count, const double* in, double* out)
+{
+    for (size_t m = 0; m < count; m++)
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) out[m * n * n + i * n + j] = in[m * n * n + j * n + i];
+}
+
+int path_of(const pb_ctx* c)
+{
+    const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0 || c->have_masks;
+    if (c->n == 4) {
+        if (!level && c->have_tree) {
+            const size_t need = (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 5 * 128 * 8 +
+                                c->fprog.size() * sizeof(FusedOp);
+            if (need <= c->smem_optin) return PATH_FUSED4;
+        }
+        return PATH_LEVEL4;
+    }
+    if (!c->have_masks && pbk::dmma_supported(c->n)) return PATH_LEVEL_DMMA;
+    return PATH_LEVEL_DENSE;
+}
+
+// ---- tree compiler ------------------------------------------------------
+int compile_tree(pb_ctx* c)
+{
+    const int nn = c->nnodes;
+    // post-order by explicit stack (trees can be caterpillars: no recursion)
+    std::vector<int> order;
+    order.reserve(nn);
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({c->root, c->child_ptr[c->root]});
+        while (!st.empty()) {
+            auto& top = st.back();
+            if (top.second < c->child_ptr[top.first + 1]) {
+                const int ch = c->child_idx[top.second++];
+                st.push_back({ch, c->child_ptr[ch]});
+            } else {
+                order.push_back(top.first);
+                st.pop_back();
+            }
+        }
+    }
+    if ((int)order.size() != nn) return fail(c, PB_ERR_INVALID_ARG, "tree: not every node is reachable from the root");
+
+    std::vector<int> level(nn, 0), su(nn, 0);
+    c->max_arity = 0;
+    for (int v : order) {
+        const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
+        if (c0 == c1) continue;
+        c->max_arity = std::max(c->max_arity, c1 - c0);
+        int lv = 0;
+        for (int k = c0; k < c1; k++) lv = std::max(lv, level[c->child_idx[k]]);
+        level[v] = lv + 1;
+        // stack need of the accumulator machine (Sethi-Ullman style)
+        if (c1 - c0 == 2) {
+            const int a = c->child_idx[c0], b = c->child_idx[c0 + 1];
+            const bool ia = c->child_ptr[a] != c->child_ptr[a + 1], ib = c->child_ptr[b] != c->child_ptr[b + 1];
+            if (ia && ib) su[v] = std::max(std::max(su[a], su[b]), std::min(su[a], su[b]) + 1);
+            else su[v] = ia ? su[a] : (ib ? su[b] : 0);
+        } else {
+            int need = 0;
+            for (int k = c0; k < c1; k++) {
+                const int ch = c->child_idx[k];
+                const bool inner = c->child_ptr[ch] != c->child_ptr[ch + 1];
+                if (inner) need = std::max(need, su[ch] + (k > c0 ? 1 : 0));
+            }
+            su[v] = need;
+        }
+    }
+
+    // ---- level schedule + CLV slots
+    std::vector<int> internals;
+    for (int v : order) if (c->child_ptr[v] != c->child_ptr[v + 1]) internals.push_back(v);
+    std::stable_sort(internals.begin(), internals.end(), [&](int a, int b) { return level[a] < level[b]; });
+    c->lv_nodes.clear();
+    c->lv_children.clear();
+    c->lv_first.clear();
+    c->slot_of_node.assign(nn, -1);
+    const bool keep = (c->flags & PB_FLAG_KEEP_CLV) != 0;
+    std::vector<int> free_slots;
+    int nslots = 0;
+    size_t i = 0;
+    while (i < internals.size()) {
+        const int lv = level[internals[i]];
+        size_t j = i;
+        while (j < internals.size() && level[internals[j]] == lv) j++;
+        c->lv_first.push_back((int)c->lv_nodes.size());
+        for (size_t q = i; q < j; q++) {
+            const int v = internals[q];
+            int slot;
+            if (!keep && !free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
+            else slot = nslots++;
+            c->slot_of_node[v] = slot;
+        }
+        for (size_t q = i; q < j; q++) {
+            const int v = internals[q];
+            LevelNode nd;
+            nd.nchild = c->child_ptr[v + 1] - c->child_ptr[v];
+            nd.child_off = (int)c->lv_children.size();
+            nd.out_slot = c->slot_of_node[v];
+            nd.is_root = (v == c->root) ? 1 : 0;
+            for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; k++) {
+                const int ch = c->child_idx[k];
+                LevelChild cd;
+                cd.pad = 0;
+                cd.pnode = ch;
+                if (c->child_ptr[ch] == c->child_ptr[ch + 1]) { cd.kind = 0; cd.src = c->tip_row[ch]; }
+                else { cd.kind = 1; cd.src = c->slot_of_node[ch]; }
+                c->lv_children.push_back(cd);
+            }
+            c->lv_nodes.push_back(nd);
+        }
+        if (!keep)
+            for (size_t q = i; q < j; q++) {
+                const int v = internals[q];
+                for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; k++) {
+                    const int ch = c->child_idx[k];
+                    if (c->slot_of_node[ch] >= 0) free_slots.push_back(c->slot_of_node[ch]);
+                }
+            }
+        i = j;
+    }
+    c->lv_first.push_back((int)c->lv_nodes.size());
+    c->nslots = nslots;
+
+    // ---- fused accumulator/stack program (4-state path)
+    c->fprog.clear();
+    c->fstack = su[c->root];
+    {
+        auto is_inner = [&](int v) { return c->child_ptr[v] != c->child_ptr[v + 1]; };
+        auto op = [&](int code, int pA = 0, int rowA = 0, int pB = 0, int rowB = 0) {
+            FusedOp o{code, pA, rowA, pB, rowB, 0, 0, 0};
+            return o;
+        };
+        // work items: >= 0 visit node, < 0 emit the op stored in `pending`
+        struct Item { int node; FusedOp emit; bool is_emit; };
+        std::vector<Item> st;
+        st.push_back({c->root, {}, false});
+        while (!st.empty()) {
+            Item it = st.back();
+            st.pop_back();
+            if (it.is_emit) { c->fprog.push_back(it.emit); continue; }
+            const int v = it.node;
+            const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
+            std::vector<Item> seq;   // in execution order
+            if (c1 - c0 == 2) {
+                int a = c->child_idx[c0], b = c->child_idx[c0 + 1];
+                const bool ia = is_inner(a), ib = is_inner(b);
+                if (!ia && !ib) {
+                    seq.push_back({0, op(pbk::FOP_TIP_TIP, a, c->tip_row[a], b, c->tip_row[b]), true});
+                } else if (ia && ib) {
+                    if (su[b] > su[a]) std::swap(a, b);   // heavier first: exact, x*y and c1+c2 commute
+                    seq.push_back({a, {}, false});
+                    seq.push_back({0, op(pbk::FOP_APPLY, a), true});
+                    seq.push_back({0, op(pbk::FOP_PUSH), true});
+                    seq.push_back({b, {}, false});
+                    seq.push_back({0, op(pbk::FOP_APPLY, b), true});
+                    seq.push_back({0, op(pbk::FOP_POP_MUL), true});
+                } else {
+                    const int in = ia ? a : b, tp = ia ? b : a;
+                    seq.push_back({in, {}, false});
+                    seq.push_back({0, op(pbk::FOP_APPLY_MUL_TIP, in, 0, tp, c->tip_row[tp]), true});
+                }
+            } else {
+                for (int k = c0; k < c1; k++) {      // reference order (left fold)
+                    const int ch = c->child_idx[k];
+                    if (!is_inner(ch)) {
+                        seq.push_back({0, op(k == c0 ? pbk::FOP_TIP : pbk::FOP_MUL_TIP, ch, c->tip_row[ch]), true});
+                    } else {
+                        if (k > c0) seq.push_back({0, op(pbk::FOP_PUSH), true});
+                        seq.push_back({ch, {}, false});
+                        seq.push_back({0, op(pbk::FOP_APPLY, ch), true});
+                        if (k > c0) seq.push_back({0, op(pbk::FOP_POP_MUL), true});
+                    }
+                }
+            }
+            for (auto r = seq.rbegin(); r != seq.rend(); ++r) st.push_back(*r);
+        }
+        c->fprog.push_back(op(pbk::FOP_ROOT));
+    }
+
+    // upload
+    PB_CUDA(c, c->d_lv_nodes.ensure(c->lv_nodes.size()));
+    PB_CUDA(c, c->d_lv_children.ensure(c->lv_children.size()));
+    PB_CUDA(c, c->d_fprog.ensure(c->fprog.size()));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_lv_nodes.p, c->lv_nodes.data(), c->lv_nodes.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_lv_children.p, c->lv_children.data(), c->lv_children.size() * sizeof(LevelChild), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog.p, c->fprog.data(), c->fprog.size() * sizeof(FusedOp), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PB_OK;
+}
+
+// ---- P(t) ----------------------------------------------------------------
+int build_pmatrices(pb_ctx* c)
+{
+    if (c->psrc == PSRC_NONE) return fail(c, PB_ERR_STATE, "no transition model: call pb_set_eigensystem / pb_set_rate_matrix / pb_set_pmatrices");
+    if (c->psrc == PSRC_DIRECT || !c->p_dirty) return PB_OK;
+    if (!c->have_blen) return fail(c, PB_ERR_STATE, "branch lengths not set");
+    const int n = c->n;
+    PB_CUDA(c, c->d_P.ensure((size_t)c->ncat * c->nnodes * n * n));
+    if (c->psrc == PSRC_EIGEN) {
+        const size_t smem = (size_t)(n + 2 * n * n) * sizeof(double);
+        PB_CUDA(c, cudaFuncSetAttribute(pbk::pmat_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(c->nnodes, c->ncat);
+        pbk::pmat_eigen<<<grid, 256, smem, c->stream>>>(n, c->nnodes, c->root, c->d_U.p, c->d_lambda.p, c->d_Uinv.p,
+                                                        c->d_blen.p, c->d_rates.p, c->d_P.p);
+        c->launches++;
+    } else {
+        int rc = pbk::launch_expm_batched(n, c->nnodes, c->ncat, c->root, c->d_Q.p, c->d_blen.p, c->d_rates.p,
+                                          c->d_P.p, c->smem_optin, c->stream);
+        if (rc != 0) return fail(c, PB_ERR_CUDA, "expm kernel: not enough shared memory for this state count");
+        c->launches++;
+    }
+    PB_CUDA(c, cudaGetLastError());
+    c->p_dirty = false;
+    return PB_OK;
+}
+
+template <int N>
+int launch_level_dense(pb_ctx* c, int first, int count, int store_root)
+{
+    const size_t smem = (size_t)(N * N + N * 128) * sizeof(double);
+    PB_CUDA(c, cudaFuncSetAttribute(pbk::level_dense<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(c->spad / 128), count);
+    pbk::level_dense<N><<<grid, 128, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p,
+                                                        c->nnodes, c->ncat, c->d_tips.p, c->spad, c->d_pool.p,
+                                                        c->slot_stride, c->spad, c->d_pi.p, c->threshold,
+                                                        c->shift_at_root, c->d_site_cat.p, store_root);
+    c->launches++;
+    return PB_OK;
+}
+
+int run_pruning(pb_ctx* c)
+{
+    const int n = c->n;
+    const int path = path_of(c);
+    PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    if (path == PATH_FUSED4) {
+        constexpr int BLOCK = 128;
+        const size_t smem = (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 5 * BLOCK * 8 +
+                            c->fprog.size() * sizeof(FusedOp);
+        PB_CUDA(c, cudaFuncSetAttribute(pbk::fused4<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)(c->spad / BLOCK), c->ncat);
+        pbk::fused4<BLOCK><<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1),
+                                                             c->d_P.p, c->nnodes, c->d_tips.p, c->spad, c->d_pi.p,
+                                                             c->threshold, c->shift_at_root, c->d_site_cat.p, c->spad);
+        c->launches++;
+        PB_CUDA(c, cudaGetLastError());
+        return PB_OK;
+    }
+    // level-scheduled paths
+    c->slot_stride = (int64_t)c->ncat * (n + 1) * c->spad;
+    PB_CUDA(c, c->d_pool.ensure((size_t)c->nslots * c->slot_stride));
+    const int store_root = (c->flags & PB_FLAG_KEEP_CLV) ? 1 : 0;
+    for (size_t l = 0; l + 1 < c->lv_first.size(); l++) {
+        const int first = c->lv_first[l], count = c->lv_first[l + 1] - first;
+        if (path == PATH_LEVEL4) {
+            size_t smem = (size_t)c->max_arity * c->ncat * 16 * sizeof(double);
+            if (smem > 32768) smem = 0;
+            dim3 grid((unsigned)((c->spad / 2 + 255) / 256), count);
+            pbk::level4<<<grid, 256, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes,
+                                                        c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride,
+                                                        c->spad, c->d_pi.p, c->threshold, c->shift_at_root,
+                                                        c->d_site_cat.p, store_root);
+            c->launches++;
+        } else if (path == PATH_LEVEL_DMMA) {
+            int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
+                                            c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
+                                            c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root,
+                                            c->stream);
+            if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma launch configuration failed");
+            c->launches++;
+        } else {
+            int rc;
+            switch (n) {
+            case 2: rc = launch_level_dense<2>(c, first, count, store_root); break;
+            case 3: rc = launch_level_dense<3>(c, first, count, store_root); break;
+            case 5: rc = launch_level_dense<5>(c, first, count, store_root); break;
+            case 20: rc = launch_level_dense<20>(c, first, count, store_root); break;
+            case 61: rc = launch_level_dense<61>(c, first, count, store_root); break;
+            case 64: rc = launch_level_dense<64>(c, first, count, store_root); break;
+            default:
+                return fail(c, PB_ERR_INVALID_ARG, "nstates: compiled sizes are 2,3,4,5,20,61,64");
+            }
+            if (rc != PB_OK) return rc;
+        }
+    }
+    PB_CUDA(c, cudaGetLastError());
+    return PB_OK;
+}
+
+int run_root_reduction(pb_ctx* c)
+{
+    const int64_t blocks = (c->nsites + 255) / 256;
+    PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
+    PB_CUDA(c, c->d_partials.ensure((size_t)blocks));
+    PB_CUDA(c, c->d_total.ensure(1));
+    pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p, c->nsites,
+                                                               c->spad, c->d_per_site.p, c->d_partials.p);
+    pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, blocks, c->d_total.p);
+    c->launches += 2;
+    PB_CUDA(c, cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char* pb_version(void) { return "phylo_b200 0.1 (sm_100a)"; }
+
+const char* pb_last_error(const pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+pb_ctx* pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, unsigned flags)
+{
+    if (nstates < 2 || nstates > 64) { fail(nullptr, PB_ERR_INVALID_ARG, "nstates must be in 2..64"); return nullptr; }
+    if (ncat < 1 || ncat > 64) { fail(nullptr, PB_ERR_INVALID_ARG, "ncat must be in 1..64"); return nullptr; }
+    if (nsites < 1) { fail(nullptr, PB_ERR_INVALID_ARG, "nsites must be >= 1"); return nullptr; }
+    if (ntaxa < 1) { fail(nullptr, PB_ERR_INVALID_ARG, "ntaxa must be >= 1"); return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fail(nullptr, PB_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(nullptr, PB_ERR_INVALID_ARG, "device index out of range"); return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        cuda_fail(nullptr, e, "cudaSetDevice");
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        fail(nullptr, PB_ERR_CUDA, "device is not sm_100 (Blackwell B200): kernels are built for sm_100a only");
+        return nullptr;
+    }
+    pb_ctx* c = new pb_ctx();
+    c->device = device;
+    c->n = nstates;
+    c->ncat = ncat;
+    c->nsites = nsites;
+    c->ntaxa = ntaxa;
+    c->flags = flags;
+    c->spad = round_up(nsites, 512);
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->h_total, sizeof(double))) != cudaSuccess) {
+        cuda_fail(nullptr, e, "stream/pinned allocation");
+        delete c;
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    c->h_rates.assign(ncat, 1.0);
+    c->h_weights.assign(ncat, 1.0 / ncat);
+    if (c->d_rates.ensure(ncat) != cudaSuccess || c->d_weights.ensure(ncat) != cudaSuccess ||
+        cudaMemcpy(c->d_rates.p, c->h_rates.data(), ncat * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_weights.p, c->h_weights.data(), ncat * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(nullptr, PB_ERR_NOMEM, "device allocation failed");
+        pb_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void pb_destroy(pb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+    if (c->h_total) cudaFreeHost(c->h_total);
+    c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
+    c->d_tips.release(); c->d_masks.release(); c->d_pi.release(); c->d_rates.release(); c->d_weights.release();
+    c->d_blen.release(); c->d_U.release(); c->d_lambda.release(); c->d_Uinv.release(); c->d_Q.release();
+    c->d_P.release(); c->d_pool.release(); c->d_site_cat.release(); c->d_per_site.release();
+    c->d_partials.release(); c->d_total.release();
+    delete c;
+}
+
+#define PB_ENTER(c)                                                          \
+    if (!(c)) return PB_ERR_INVALID_ARG;                                     \
+    { cudaError_t e_ = cudaSetDevice((c)->device); if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); }
+
+int pb_set_stream(pb_ctx* c, void* s)
+{
+    PB_ENTER(c);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return PB_OK;
+}
+
+int pb_set_mode(pb_ctx* c, int mode)
+{
+    PB_ENTER(c);
+    if (mode == PB_MODE_PHYLO_CTMC) { c->threshold = 1e-6; c->shift_at_root = 1; }
+    else if (mode == PB_MODE_FELSENSTEIN) { c->threshold = 0.0000001; c->shift_at_root = 0; }
+    else return fail(c, PB_ERR_INVALID_ARG, "unknown mode");
+    return PB_OK;
+}
+
+int pb_set_rescaling(pb_ctx* c, double threshold, int shift_at_root)
+{
+    PB_ENTER(c);
+    c->threshold = threshold;
+    c->shift_at_root = shift_at_root ? 1 : 0;
+    return PB_OK;
+}
+
+int pb_set_tree(pb_ctx* c, int nnodes, int root, const int32_t* child_ptr, const int32_t* child_idx,
+                const int32_t* tip_row, const double* branch_len)
+{
+    PB_ENTER(c);
+    if (!child_ptr || !child_idx || !tip_row) return fail(c, PB_ERR_INVALID_ARG, "tree: null array");
+    if (nnodes < 2) return fail(c, PB_ERR_INVALID_ARG, "tree: needs at least one internal node and one leaf");
+    if (root < 0 || root >= nnodes) return fail(c, PB_ERR_INVALID_ARG, "tree: root out of range");
+    if (child_ptr[0] != 0) return fail(c, PB_ERR_INVALID_ARG, "tree: child_ptr[0] must be 0");
+    for (int v = 0; v < nnodes; v++)
+        if (child_ptr[v + 1] < child_ptr[v]) return fail(c, PB_ERR_INVALID_ARG, "tree: child_ptr must be non-decreasing");
+    const int nedges = child_ptr[nnodes];
+    if (nedges != nnodes - 1) return fail(c, PB_ERR_INVALID_ARG, "tree: a rooted tree over nnodes nodes has nnodes-1 branches");
+    std::vector<int> parent(nnodes, -1);
+    for (int v = 0; v < nnodes; v++)
+        for (int k = child_ptr[v]; k < child_ptr[v + 1]; k++) {
+            const int ch = child_idx[k];
+            if (ch < 0 || ch >= nnodes || ch == root) return fail(c, PB_ERR_INVALID_ARG, "tree: bad child index");
+            if (parent[ch] != -1) return fail(c, PB_ERR_INVALID_ARG, "tree: node has two parents");
+            parent[ch] = v;
+        }
+    if (child_ptr[root + 1] == child_ptr[root]) return fail(c, PB_ERR_INVALID_ARG, "tree: the root must be an internal node");
+    std::vector<char> seen(c->ntaxa, 0);
+    for (int v = 0; v < nnodes; v++) {
+        const bool leaf = child_ptr[v + 1] == child_ptr[v];
+        if (leaf) {
+            if (tip_row[v] < 0 || tip_row[v] >= c->ntaxa) return fail(c, PB_ERR_INVALID_ARG, "tree: leaf tip_row out of range");
+            seen[tip_row[v]] = 1;
+        }
+    }
+    c->nnodes = nnodes;
+    c->root = root;
+    c->child_ptr.assign(child_ptr, child_ptr + nnodes + 1);
+    c->child_idx.assign(child_idx, child_idx + nedges);
+    c->tip_row.assign(tip_row, tip_row + nnodes);
+    c->parent = parent;
+    c->have_tree = true;
+    c->have_blen = false;
+    c->p_dirty = true;
+    if (c->psrc == PSRC_DIRECT) c->psrc = PSRC_NONE;   // matrices belonged to the old tree
+    c->evaluated = false;
+    int rc = compile_tree(c);
+    if (rc != PB_OK) { c->have_tree = false; return rc; }
+    if (branch_len) return pb_set_branch_lengths(c, branch_len);
+    return PB_OK;
+}
+
+int pb_set_branch_lengths(pb_ctx* c, const double* bl)
+{
+    PB_ENTER(c);
+    if (!c->have_tree) return fail(c, PB_ERR_STATE, "set the tree first");
+    if (!bl) return fail(c, PB_ERR_INVALID_ARG, "branch_len is null");
+    for (int v = 0; v < c->nnodes; v++)
+        if (v != c->root && !(bl[v] >= 0.0)) return fail(c, PB_ERR_INVALID_ARG, "branch lengths must be >= 0");
+    c->branch_len.assign(bl, bl + c->nnodes);
+    c->branch_len[c->root] = 0.0;
+    PB_CUDA(c, c->d_blen.ensure(c->nnodes));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_blen.p, c->branch_len.data(), c->nnodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_blen = true;
+    c->p_dirty = true;
+    return PB_OK;
+}
+
+static int alloc_tips(pb_ctx* c)
+{
+    const size_t bytes = (size_t)c->ntaxa * c->spad;
+    const bool fresh = c->d_tips.count < bytes || !c->d_tips.p;
+    PB_CUDA(c, c->d_tips.ensure(bytes));
+    if (fresh) PB_CUDA(c, cudaMemsetAsync(c->d_tips.p, 0, bytes, c->stream));
+    return PB_OK;
+}
+
+int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
+{
+    PB_ENTER(c);
+    if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p, c->spad, states, ld, c->nsites, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
+    c->have_tips = true;
+    c->have_masks = false;
+    return PB_OK;
+}
+
+int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
+{
+    PB_ENTER(c);
+    if (!d_states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p, c->spad, d_states, ld, c->nsites, c->ntaxa, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_tips = true;
+    c->have_masks = false;
+    return PB_OK;
+}
+
+int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
+{
+    PB_ENTER(c);
+    (void)masks; (void)ld;
+    return fail(c, PB_ERR_STATE, "tip state-set masks (Missing_values / Ambiguous) are not built yet");
+}
+
+int pb_set_root_frequencies(pb_ctx* c, const double* pi)
+{
+    PB_ENTER(c);
+    if (!pi) return fail(c, PB_ERR_INVALID_ARG, "pi is null");
+    PB_CUDA(c, c->d_pi.ensure(c->n));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_pi.p, pi, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_pi = true;
+    return PB_OK;
+}
+
+int pb_set_categories(pb_ctx* c, const double* rates, const double* weights)
+{
+    PB_ENTER(c);
+    if (!rates || !weights) return fail(c, PB_ERR_INVALID_ARG, "categories: null pointer");
+    for (int k = 0; k < c->ncat; k++)
+        if (!(rates[k] >= 0.0) || !(weights[k] >= 0.0)) return fail(c, PB_ERR_INVALID_ARG, "category rates and weights must be >= 0");
+    c->h_rates.assign(rates, rates + c->ncat);
+    c->h_weights.assign(weights, weights + c->ncat);
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rates.p, c->h_rates.data(), c->ncat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_weights.p, c->h_weights.data(), c->ncat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->p_dirty = true;
+    return PB_OK;
+}
+
+int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const double* Uinv)
+{
+    PB_ENTER(c);
+    if (!U || !lambda || !Uinv) return fail(c, PB_ERR_INVALID_ARG, "eigensystem: null pointer");
+    const int n = c->n;
+    std::vector<double> ur((size_t)n * n), uir((size_t)n * n);
+    to_row_major(n, 1, U, ur.data());
+    to_row_major(n, 1, Uinv, uir.data());
+    PB_CUDA(c, c->d_U.ensure((size_t)n * n));
+    PB_CUDA(c, c->d_Uinv.ensure((size_t)n * n));
+    PB_CUDA(c, c->d_lambda.ensure(n));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_U.p, ur.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_Uinv.p, uir.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_lambda.p, lambda, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->psrc = PSRC_EIGEN;
+    c->p_dirty = true;
+    return PB_OK;
+}
+
+int pb_host_reversible_eigensystem(int n, const double* Q, const double* pi, double* U, double* lambda, double* Uinv)
+{
+    if (n < 1 || n > 64 || !Q || !pi || !U || !lambda || !Uinv) return PB_ERR_INVALID_ARG;
+    std::string why;
+    return pbh::reversible_eigensystem(n, Q, pi, U, lambda, Uinv, &why) ? PB_OK : PB_ERR_NUMERIC;
+}
+
+int pb_set_rate_matrix(pb_ctx* c, const double* Q, const double* pi)
+{
+    PB_ENTER(c);
+    if (!Q || !pi) return fail(c, PB_ERR_INVALID_ARG, "rate matrix: null pointer");
+    const int n = c->n;
+    std::vector<double> U((size_t)n * n), Ui((size_t)n * n), lam(n);
+    std::string why;
+    if (!pbh::reversible_eigensystem(n, Q, pi, U.data(), lam.data(), Ui.data(), &why))
+        return fail(c, PB_ERR_NUMERIC, "pb_set_rate_matrix: " + why);
+    return pb_set_eigensystem(c, U.data(), lam.data(), Ui.data());
+}
+
+int pb_set_rate_matrix_general(pb_ctx* c, const double* Q)
+{
+    PB_ENTER(c);
+    if (!Q) return fail(c, PB_ERR_INVALID_ARG, "rate matrix: null pointer");
+    const int n = c->n;
+    std::vector<double> qr((size_t)n * n);
+    to_row_major(n, 1, Q, qr.data());
+    PB_CUDA(c, c->d_Q.ensure((size_t)n * n));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_Q.p, qr.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->psrc = PSRC_EXPM;
+    c->p_dirty = true;
+    return PB_OK;
+}
+
+int pb_set_pmatrices(pb_ctx* c, const double* P)
+{
+    PB_ENTER(c);
+    if (!c->have_tree) return fail(c, PB_ERR_STATE, "set the tree first");
+    if (!P) return fail(c, PB_ERR_INVALID_ARG, "P is null");
+    const int n = c->n;
+    const size_t count = (size_t)c->ncat * c->nnodes;
+    std::vector<double> pr(count * n * n);
+    to_row_major(n, count, P, pr.data());
+    PB_CUDA(c, c->d_P.ensure(count * n * n));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_P.p, pr.data(), sizeof(double) * pr.size(), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->psrc = PSRC_DIRECT;
+    c->p_dirty = false;
+    return PB_OK;
+}
+
+int pb_loglik_enqueue(pb_ctx* c)
+{
+    PB_ENTER(c);
+    if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
+    if (!c->have_tips) return fail(c, PB_ERR_STATE, "tip states not set");
+    if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
+    int rc = build_pmatrices(c);
+    if (rc != PB_OK) return rc;
+    if ((rc = run_pruning(c)) != PB_OK) return rc;
+    if ((rc = run_root_reduction(c)) != PB_OK) return rc;
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->evaluated = true;
+    return PB_OK;
+}
+
+int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
+{
+    PB_ENTER(c);
+    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing enqueued");
+    if (per_site)
+        PB_CUDA(c, cudaMemcpyAsync(per_site, c->d_per_site.p, sizeof(double) * c->nsites, cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (total) *total = *c->h_total;
+    return PB_OK;
+}
+
+int pb_loglik(pb_ctx* c, double* total, double* per_site)
+{
+    int rc = pb_loglik_enqueue(c);
+    if (rc != PB_OK) return rc;
+    return pb_loglik_fetch(c, total, per_site);
+}
+
+int pb_result_device_ptrs(pb_ctx* c, const double** d_total, const double** d_per_site)
+{
+    PB_ENTER(c);
+    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (d_total) *d_total = c->d_total.p;
+    if (d_per_site) *d_per_site = c->d_per_site.p;
+    return PB_OK;
+}
+
+int pb_get_clv(pb_ctx* c, int node, int cat, double* v, double* carry)
+{
+    PB_ENTER(c);
+    if (!(c->flags & PB_FLAG_KEEP_CLV)) return fail(c, PB_ERR_STATE, "pb_get_clv needs PB_FLAG_KEEP_CLV");
+    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (node < 0 || node >= c->nnodes || cat < 0 || cat >= c->ncat || !v || !carry)
+        return fail(c, PB_ERR_INVALID_ARG, "pb_get_clv: bad node/category/pointer");
+    const int n = c->n;
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->child_ptr[node] == c->child_ptr[node + 1]) {      // leaf: indicator, carry 0
+        std::vector<uint8_t> row(c->nsites);
+        PB_CUDA(c, cudaMemcpy(row.data(), c->d_tips.p + (size_t)c->tip_row[node] * c->spad, c->nsites, cudaMemcpyDeviceToHost));
+        for (int64_t s = 0; s < c->nsites; s++) {
+            for (int i = 0; i < n; i++) v[s * n + i] = (i == row[s]) ? 1.0 : 0.0;
+            carry[s] = 0.0;
+        }
+        return PB_OK;
+    }
+    const int slot = c->slot_of_node[node];
+    std::vector<double> planes((size_t)(n + 1) * c->nsites);
+    const double* src = c->d_pool.p + (size_t)slot * c->slot_stride + (size_t)cat * (n + 1) * c->spad;
+    PB_CUDA(c, cudaMemcpy2D(planes.data(), c->nsites * sizeof(double), src, c->spad * sizeof(double),
+                            c->nsites * sizeof(double), n + 1, cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < c->nsites; s++) {
+        for (int i = 0; i < n; i++) v[s * n + i] = planes[(size_t)i * c->nsites + s];
+        carry[s] = planes[(size_t)n * c->nsites + s];
+    }
+    return PB_OK;
+}
+
+int pb_get_pmatrices(pb_ctx* c, double* P)
+{
+    PB_ENTER(c);
+    if (!P) return fail(c, PB_ERR_INVALID_ARG, "P is null");
+    if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
+    int rc = build_pmatrices(c);
+    if (rc != PB_OK) return rc;
+    const int n = c->n;
+    const size_t count = (size_t)c->ncat * c->nnodes;
+    std::vector<double> pr(count * n * n);
+    PB_CUDA(c, cudaMemcpyAsync(pr.data(), c->d_P.p, sizeof(double) * pr.size(), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    to_row_major(n, count, pr.data(), P);   // transpose is its own inverse
+    if (c->psrc != PSRC_DIRECT)
+        for (int k = 0; k < c->ncat; k++)   // the root has no branch: report identity
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) P[((size_t)k * c->nnodes + c->root) * n * n + j * n + i] = (i == j) ? 1.0 : 0.0;
+    return PB_OK;
+}
+
+int64_t pb_kernel_launches(const pb_ctx* c) { return c ? c->launches : 0; }
+
+const char* pb_path_name(const pb_ctx* c)
+{
+    if (!c) return "";
+    switch (path_of(c)) {
+    case PATH_FUSED4: return "fused4";
+    case PATH_LEVEL4: return "level4";
+    case PATH_LEVEL_DMMA: return "level_dmma";
+    default: return "level_dense";
+    }
+}
+
+static int standalone_setup(int device, int n, int count)
+{
+    if (n < 1 || n > 64 || count < 1) return fail(nullptr, PB_ERR_INVALID_ARG, "bad n or count");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, PB_ERR_CUDA, "no CUDA device (no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, PB_ERR_INVALID_ARG, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    return PB_OK;
+}
+
+int pb_transition_matrices_eigen(int device, int n, int count, const double* U, const double* lambda,
+                                 const double* Uinv, const double* t, double* out)
+{
+    int rc = standalone_setup(device, n, count);
+    if (rc != PB_OK) return rc;
+    if (!U || !lambda || !Uinv || !t || !out) return fail(nullptr, PB_ERR_INVALID_ARG, "null pointer");
+    std::vector<double> ur((size_t)n * n), uir((size_t)n * n), res((size_t)count * n * n);
+    to_row_major(n, 1, U, ur.data());
+    to_row_major(n, 1, Uinv, uir.data());
+    DevBuf<double> dU, dUi, dl, dt, dP;
+    pb_ctx* none = nullptr;
+    PB_CUDA(none, dU.ensure((size_t)n * n)); PB_CUDA(none, dUi.ensure((size_t)n * n)); PB_CUDA(none, dl.ensure(n));
+    PB_CUDA(none, dt.ensure(count)); PB_CUDA(none, dP.ensure((size_t)count * n * n));
+    PB_CUDA(none, cudaMemcpy(dU.p, ur.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    PB_CUDA(none, cudaMemcpy(dUi.p, uir.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    PB_CUDA(none, cudaMemcpy(dl.p, lambda, sizeof(double) * n, cudaMemcpyHostToDevice));
+    PB_CUDA(none, cudaMemcpy(dt.p, t, sizeof(double) * count, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)(n + 2 * n * n) * sizeof(double);
+    PB_CUDA(none, cudaFuncSetAttribute(pbk::pmat_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbk::pmat_eigen<<<dim3(count, 1), 256, smem>>>(n, count, -1, dU.p, dl.p, dUi.p, dt.p, nullptr, dP.p);
+    PB_CUDA(none, cudaGetLastError());
+    PB_CUDA(none, cudaMemcpy(res.data(), dP.p, sizeof(double) * res.size(), cudaMemcpyDeviceToHost));
+    to_row_major(n, count, res.data(), out);
+    dU.release(); dUi.release(); dl.release(); dt.release(); dP.release();
+    return PB_OK;
+}
+
+int pb_transition_matrices_expm(int device, int n, int count, const double* Q, const double* t, double* out)
+{
+    int rc = standalone_setup(device, n, count);
+    if (rc != PB_OK) return rc;
+    if (!Q || !t || !out) return fail(nullptr, PB_ERR_INVALID_ARG, "null pointer");
+    cudaDeviceProp prop;
+    pb_ctx* none = nullptr;
+    PB_CUDA(none, cudaGetDeviceProperties(&prop, device));
+    std::vector<double> qr((size_t)n * n), res((size_t)count * n * n);
+    to_row_major(n, 1, Q, qr.data());
+    DevBuf<double> dQ, dt, dP;
+    PB_CUDA(none, dQ.ensure((size_t)n * n)); PB_CUDA(none, dt.ensure(count)); PB_CUDA(none, dP.ensure((size_t)count * n * n));
+    PB_CUDA(none, cudaMemcpy(dQ.p, qr.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    PB_CUDA(none, cudaMemcpy(dt.p, t, sizeof(double) * count, cudaMemcpyHostToDevice));
+    if (pbk::launch_expm_batched(n, count, 1, -1, dQ.p, dt.p, nullptr, dP.p, prop.sharedMemPerBlockOptin, 0) != 0)
+        return fail(nullptr, PB_ERR_CUDA, "expm kernel: not enough shared memory for this state count");
+    PB_CUDA(none, cudaGetLastError());
+    PB_CUDA(none, cudaMemcpy(res.data(), dP.p, sizeof(double) * res.size(), cudaMemcpyDeviceToHost));
+    to_row_major(n, count, res.data(), out);
+    dQ.release(); dt.release(); dP.release();
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// Hand-written sm_100a kernels of the phylogenetic-likelihood hot path.
+//
+// Arithmetic is IEEE FP64 throughout.  Every kernel restates a piece of the
+// reference (biocaml/phylogenetics, paths relative to its checkout):
+//   K1 pmat_eigen        Site_evolution_model.Make_diag        lib/site_evolution_model.ml:43-47
+//   K2 level4/level_dense/fused4   Phylo_ctmc.pruning recursion lib/phylo_ctmc.ml:83-98
+//                        SV.mul + SV.shift rescaling           lib/phylo_ctmc.ml:33-40,76-78
+//   K3 root_combine/final_sum      Felsenstein.multisite sum   lib/felsenstein.ml:73-75
+//
+// Data layout in HBM:
+//   tips   uint8  [ntaxa][tips_ld]            site contiguous
+//   P      f64    [ncat][nnodes][n*n]         row-major (i = parent state, j = child state)
+//   CLV    f64    slot -> [ncat][n+1][spad]   plane-per-state, site contiguous; plane n = carry
+//   site_cat f64  [ncat][spad]                log-likelihood of every (category, site)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pbk {
+
+// --------------------------------------------------------------------------
+// Tree programs built on the host (pb_api.cu) and read, uniformly, by every thread.
+// --------------------------------------------------------------------------
+struct LevelChild {
+    int kind;    // 0 = tip (src = row of the tip matrix), 1 = inner node (src = CLV slot)
+    int src;
+    int pnode;   // node id at the lower end of the branch = index of its P matrix
+    int pad;
+};
+struct LevelNode {
+    int nchild;
+    int child_off;   // first entry in the LevelChild array
+    int out_slot;    // CLV slot written (ignored for the root unless KEEP_CLV)
+    int is_root;
+};
+
+enum FusedOpCode : int {
+    FOP_TIP_TIP = 0,   // ACC = shiftmul(col(pA, tip rowA), col(pB, tip rowB))
+    FOP_TIP = 1,       // ACC = col(pA, tip rowA), carry 0
+    FOP_APPLY = 2,     // ACC.v = P[pA] . ACC.v            (branch term of a finished subtree)
+    FOP_MUL_TIP = 3,   // ACC = shiftmul(ACC, col(pA, tip rowA))
+    FOP_PUSH = 4,      // stack[sp++] = ACC
+    FOP_POP_MUL = 5,   // ACC = shiftmul(stack[--sp], ACC)
+    FOP_APPLY_MUL_TIP = 6,  // ACC = shiftmul(P[pA].ACC, col(pB, tip rowB))
+    FOP_ROOT = 7       // x pi, optional shift, log(sum) + carry -> site_cat
+};
+struct FusedOp {
+    int code;
+    int pA, rowA;
+    int pB, rowB;
+    int pad0, pad1, pad2;
+};
+
+// --------------------------------------------------------------------------
+// K1: P[c][b] = U diag(exp(t_b r_c lambda)) Uinv for every branch x category, one launch.
+// Follows Make_diag (lib/site_evolution_model.ml:43-47): d = exp(t*lambda) elementwise,
+// then (U . diagm d) . Uinv with k accumulated in ascending order (dgemm).
+// grid = (nnodes, ncat); U and Uinv row-major here (converted at the ABI).
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pmat_eigen(int n, int nnodes, int skip_node, const double* __restrict__ U,
+           const double* __restrict__ lambda, const double* __restrict__ Uinv,
+           const double* __restrict__ blen, const double* __restrict__ rates,
+           double* __restrict__ P)
+{
+    extern __shared__ double sh[];
+    double* e = sh;              // [n]
+    double* ud = sh + n;         // [n*n]  U . diag(e), row-major
+    double* ui = ud + n * n;     // [n*n]  Uinv, row-major
+    const int b = blockIdx.x, c = blockIdx.y;
+    if (b == skip_node) return;
+    const double rate = rates ? rates[c] : 1.0;
+    const double t = blen[b] * rate;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) e[k] = exp(t * lambda[k]);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        ud[idx] = U[idx] * e[idx % n];
+        ui[idx] = Uinv[idx];
+    }
+    __syncthreads();
+    double* out = P + ((size_t)c * nnodes + b) * n * n;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        double acc = 0.0;
+        for (int k = 0; k < n; k++) acc = fma(ud[i * n + k], ui[k * n + j], acc);
+        out[idx] = acc;
+    }
+}
+
+// --------------------------------------------------------------------------
+// SV.shift (lib/phylo_ctmc.ml:33-40): keep when min v > threshold, otherwise
+// v := (1/max v) * v and carry += log(max v).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void shift4(double (&v)[4], double& carry, double thr)
+{
+    const double mn = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
+    if (!(mn > thr)) {
+        const double mx = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+        const double inv = 1.0 / mx;
+        v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
+        carry += log(mx);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void shiftN(double (&v)[N], double& carry, double thr)
+{
+    double mn = v[0], mx = v[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) { mn = fmin(mn, v[i]); mx = fmax(mx, v[i]); }
+    if (!(mn > thr)) {
+        const double inv = 1.0 / mx;
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = inv * v[i];
+        carry += log(mx);
+    }
+}
+
+// y = P x for a row-major 4x4 P (dgemv: j accumulated in ascending order).
+__device__ __forceinline__ void matvec4(const double* __restrict__ Pm, const double (&x)[4],
+                                        double (&y)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double a = Pm[i * 4 + 0] * x[0];
+        a = fma(Pm[i * 4 + 1], x[1], a);
+        a = fma(Pm[i * 4 + 2], x[2], a);
+        a = fma(Pm[i * 4 + 3], x[3], a);
+        y[i] = a;
+    }
+}
+
+// Root of Phylo_ctmc.pruning (lib/phylo_ctmc.ml:97-98) or of Felsenstein
+// (lib/felsenstein.ml:47-48, no shift): log(sum(v * pi)) + carry.
+__device__ __forceinline__ double root4(double (&v)[4], double carry, const double* __restrict__ pi,
+                                        double thr, int shift_at_root)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = v[i] * pi[i];
+    if (shift_at_root) shift4(v, carry, thr);
+    const double s = ((v[0] + v[1]) + v[2]) + v[3];
+    return log(s) + carry;
+}
+
+// --------------------------------------------------------------------------
+// K2 (level-scheduled, 4 states): one launch per tree level, blockIdx.y = node of the
+// level, each thread owns TWO adjacent sites (16-byte vector loads/stores on every
+// plane) and loops over the rate categories.  Children are folded left to right
+// exactly as List.reduce_exn ~f:SV.mul does (lib/phylo_ctmc.ml:91-95).
+// Algorithmic traffic per site.node: 8*C*5*(k_inner + 1) + k_tip bytes.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+level4(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children, int node_base,
+       const double* __restrict__ P, int nnodes, int ncat,
+       const uint8_t* __restrict__ tips, int64_t tips_ld,
+       double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+       const double* __restrict__ pi, double thr, int shift_at_root,
+       double* __restrict__ site_cat, int store_root)
+{
+    extern __shared__ double shP[];   // [nchild][ncat][16] when it fits, else unused
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    const bool staged = (size_t)nd.nchild * ncat * 16 * sizeof(double) <= 32768;
+    if (staged) {
+        for (int idx = threadIdx.x; idx < nd.nchild * ncat * 16; idx += blockDim.x) {
+            const int k = idx / (ncat * 16), r = idx - k * ncat * 16;
+            const int c = r / 16, e = r - c * 16;
+            shP[idx] = P[((size_t)c * nnodes + ch[k].pnode) * 16 + e];
+        }
+        __syncthreads();
+    }
+    const int64_t s0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (s0 >= spad) return;
+
+    for (int c = 0; c < ncat; c++) {
+        double va[4], vb[4], ca = 0.0, cb = 0.0;
+        for (int k = 0; k < nd.nchild; k++) {
+            const LevelChild cd = ch[k];
+            const double* Pm = staged ? (shP + ((size_t)k * ncat + c) * 16)
+                                      : (P + ((size_t)c * nnodes + cd.pnode) * 16);
+            double ta[4], tb[4], tca, tcb;
+            if (cd.kind == 0) {
+                const uchar2 st = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { ta[i] = Pm[i * 4 + st.x]; tb[i] = Pm[i * 4 + st.y]; }
+                tca = 0.0; tcb = 0.0;
+            } else {
+                const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * 5 * spad + s0;
+                double xa[4], xb[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double2 q = *reinterpret_cast<const double2*>(src + (int64_t)i * spad);
+                    xa[i] = q.x; xb[i] = q.y;
+                }
+                const double2 qc = *reinterpret_cast<const double2*>(src + 4 * spad);
+                tca = qc.x; tcb = qc.y;
+                matvec4(Pm, xa, ta);
+                matvec4(Pm, xb, tb);
+            }
+            if (k == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { va[i] = ta[i]; vb[i] = tb[i]; }
+                ca = tca; cb = tcb;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { va[i] = va[i] * ta[i]; vb[i] = vb[i] * tb[i]; }
+                ca = ca + tca; cb = cb + tcb;
+                shift4(va, ca, thr);
+                shift4(vb, cb, thr);
+            }
+        }
+        if (!nd.is_root || store_root) {
+            double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * 5 * spad + s0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<double2*>(dst + (int64_t)i * spad) = make_double2(va[i], vb[i]);
+            *reinterpret_cast<double2*>(dst + 4 * spad) = make_double2(ca, cb);
+        }
+        if (nd.is_root) {
+            const double la = root4(va, ca, pi, thr, shift_at_root);
+            const double lb = root4(vb, cb, pi, thr, shift_at_root);
+            *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0) = make_double2(la, lb);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// K2 (level-scheduled, N states, scalar DFMA version): one thread per site, the child's
+// CLV tile and its P matrix staged in shared memory, running product in registers.
+// Baseline and fallback for the tensor-core kernel (level_dmma, pb_kernels_dmma.cuh).
+// --------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128)
+level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children,
+            int node_base, const double* __restrict__ P, int nnodes, int ncat,
+            const uint8_t* __restrict__ tips, int64_t tips_ld,
+            double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+            const double* __restrict__ pi, double thr, int shift_at_root,
+            double* __restrict__ site_cat, int store_root)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                 // [N*N]
+    double* shX = sh + N * N;         // [N][128]
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    const int tid = threadIdx.x;
+    const int64_t s = (int64_t)blockIdx.x * 128 + tid;   // spad is a multiple of 128
+
+    for (int c = 0; c < ncat; c++) {
+        double acc[N];
+        double carry = 0.0;
+        for (int k = 0; k < nd.nchild; k++) {
+            const LevelChild cd = ch[k];
+            __syncthreads();
+            const double* Pg = P + ((size_t)c * nnodes + cd.pnode) * N * N;
+            for (int idx = tid; idx < N * N; idx += 128) shP[idx] = Pg[idx];
+            double tc = 0.0;
+            int st = 0;
+            if (cd.kind == 0) {
+                st = tips[(int64_t)cd.src * tips_ld + s];
+            } else {
+                const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (N + 1) * spad + s;
+#pragma unroll 4
+                for (int j = 0; j < N; j++) shX[j * 128 + tid] = src[(int64_t)j * spad];
+                tc = src[(int64_t)N * spad];
+            }
+            __syncthreads();
+            if (k == 0) carry = tc; else carry = carry + tc;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                double t;
+                if (cd.kind == 0) {
+                    t = shP[i * N + st];
+                } else {
+                    t = shP[i * N] * shX[tid];
+#pragma unroll 4
+                    for (int j = 1; j < N; j++) t = fma(shP[i * N + j], shX[j * 128 + tid], t);
+                }
+                acc[i] = (k == 0) ? t : acc[i] * t;
+            }
+            if (k > 0) shiftN<N>(acc, carry, thr);
+        }
+        if (!nd.is_root || store_root) {
+            double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * (N + 1) * spad + s;
+#pragma unroll
+            for (int i = 0; i < N; i++) dst[(int64_t)i * spad] = acc[i];
+            dst[(int64_t)N * spad] = carry;
+        }
+        if (nd.is_root) {
+#pragma unroll
+            for (int i = 0; i < N; i++) acc[i] = acc[i] * pi[i];
+            if (shift_at_root) shiftN<N>(acc, carry, thr);
+            double sum = acc[0];
+#pragma unroll
+            for (int i = 1; i < N; i++) sum += acc[i];
+            site_cat[(int64_t)c * spad + s] = log(sum) + carry;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// K2 (fused, 4 states): the whole post-order traversal of one (site, category) runs in
+// one thread; conditional likelihoods never leave the SM.  The tree is compiled on the
+// host into a short accumulator/stack program (heavier subtree first, so the stack depth
+// is <= log2(ntaxa)); every thread executes the same instruction stream.
+// HBM traffic: ntaxa bytes in, 8*C bytes out per site.  blockIdx.y = category.
+// --------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+fused4(const FusedOp* __restrict__ prog, int nops, int stack_depth,
+       const double* __restrict__ P, int nnodes,
+       const uint8_t* __restrict__ tips, int64_t tips_ld,
+       const double* __restrict__ pi, double thr, int shift_at_root,
+       double* __restrict__ site_cat, int64_t spad)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                                  // [nnodes][16] of this category
+    double* shS = sh + (size_t)nnodes * 16;            // [stack_depth][5][BLOCK]
+    FusedOp* shOps = reinterpret_cast<FusedOp*>(shS + (size_t)stack_depth * 5 * BLOCK);
+    const int c = blockIdx.y, tid = threadIdx.x;
+    {
+        const double* Pg = P + (size_t)c * nnodes * 16;
+        for (int idx = tid; idx < nnodes * 16; idx += BLOCK) shP[idx] = Pg[idx];
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
+        for (int idx = tid; idx < nops * 2; idx += BLOCK) dst[idx] = src[idx];
+    }
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * BLOCK + tid;   // spad is a multiple of BLOCK
+    double v[4] = {1.0, 1.0, 1.0, 1.0};
+    double carry = 0.0;
+    int sp = 0;
+    for (int ip = 0; ip < nops; ip++) {
+        const FusedOp op = shOps[ip];
+        switch (op.code) {
+        case FOP_TIP_TIP: {
+            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
+            const int sb = tips[(int64_t)op.rowB * tips_ld + s];
+            const double* pa = shP + op.pA * 16 + sa;
+            const double* pb = shP + op.pB * 16 + sb;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = pa[i * 4] * pb[i * 4];
+            carry = 0.0 + 0.0;
+            shift4(v, carry, thr);
+        } break;
+        case FOP_TIP: {
+            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
+            const double* pa = shP + op.pA * 16 + sa;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = pa[i * 4];
+            carry = 0.0;
+        } break;
+        case FOP_APPLY: {
+            double y[4];
+            matvec4(shP + op.pA * 16, v, y);
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = y[i];
+        } break;
+        case FOP_MUL_TIP: {
+            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
+            const double* pa = shP + op.pA * 16 + sa;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = v[i] * pa[i * 4];
+            carry = carry + 0.0;
+            shift4(v, carry, thr);
+        } break;
+        case FOP_APPLY_MUL_TIP: {
+            const int sb = tips[(int64_t)op.rowB * tips_ld + s];
+            double y[4];
+            matvec4(shP + op.pA * 16, v, y);
+            const double* pb = shP + op.pB * 16 + sb;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = y[i] * pb[i * 4];
+            carry = carry + 0.0;
+            shift4(v, carry, thr);
+        } break;
+        case FOP_PUSH: {
+            double* st = shS + (size_t)sp * 5 * BLOCK + tid;
+#pragma unroll
+            for (int i = 0; i < 4; i++) st[i * BLOCK] = v[i];
+            st[4 * BLOCK] = carry;
+            sp++;
+        } break;
+        case FOP_POP_MUL: {
+            sp--;
+            const double* st = shS + (size_t)sp * 5 * BLOCK + tid;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = st[i * BLOCK] * v[i];
+            carry = st[4 * BLOCK] + carry;
+            shift4(v, carry, thr);
+        } break;
+        case FOP_ROOT: {
+            site_cat[(int64_t)c * spad + s] = root4(v, carry, pi, thr, shift_at_root);
+        } break;
+        default: break;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// K3: per-site log-likelihood from the per-category values (log-sum-exp with the category
+// weights; identity for one category) and a deterministic two-stage sum of all sites.
+// Sites >= nsites (padding) contribute nothing.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double x, double* red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) red[w] = x;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256)
+root_combine(const double* __restrict__ site_cat, int ncat, const double* __restrict__ weights,
+             int64_t nsites, int64_t spad, double* __restrict__ per_site,
+             double* __restrict__ partials)
+{
+    __shared__ double red[8];
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double out = 0.0;
+    if (s < nsites) {
+        if (ncat == 1) {
+            out = site_cat[s];
+        } else {
+            double m = site_cat[s];
+            for (int c = 1; c < ncat; c++) m = fmax(m, site_cat[(int64_t)c * spad + s]);
+            if (m == -INFINITY) {
+                out = m;
+            } else {
+                double acc = 0.0;
+                for (int c = 0; c < ncat; c++)
+                    acc += weights[c] * exp(site_cat[(int64_t)c * spad + s] - m);
+                out = m + log(acc);
+            }
+        }
+        per_site[s] = out;
+    }
+    const double bs = block_sum_256(out, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+}
+
+__global__ void __launch_bounds__(256)
+final_sum(const double* __restrict__ partials, int64_t count, double* __restrict__ total)
+{
+    __shared__ double red[8];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < count; i += 256) acc += partials[i];
+    const double bs = block_sum_256(acc, red);
+    if (threadIdx.x == 0) *total = bs;
+}
+
+}  // namespace pbk

@@ -1,0 +1,208 @@
+"""Thin object wrapper over the C ABI context (include/phylo_b200.h).
+
+All arithmetic happens in libphylo_b200.so on the GPU.  numpy arrays are only
+the host buffers that cross the ABI (the role Bigarrays play for OCaml).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _colmajor(m):
+    """n x n matrix indexed [row, col] -> the ABI's column-major buffer."""
+    m = np.asarray(m, dtype=np.float64)
+    return np.ascontiguousarray(m.T)
+
+
+class LikelihoodContext:
+    """One pb_ctx: a (tree, alignment shard, model) evaluator on one GPU."""
+
+    def __init__(self, nstates, nsites, ntaxa, ncat=1, device=0, keep_clv=False, level_kernels=False):
+        flags = (_lib.PB_FLAG_KEEP_CLV if keep_clv else 0) | (_lib.PB_FLAG_LEVEL_KERNELS if level_kernels else 0)
+        self.nstates, self.nsites, self.ntaxa, self.ncat = int(nstates), int(nsites), int(ntaxa), int(ncat)
+        self._ctx = lib.pb_create(int(device), self.nstates, self.ncat, self.nsites, self.ntaxa, flags)
+        if not self._ctx:
+            msg = lib.pb_last_error(None).decode()
+            if "no CPU fallback" in msg or "sm_100" in msg or "CUDA" in msg:
+                raise _lib.PhyloB200Error(_lib.PB_ERR_CUDA, msg)
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, msg)
+        self.nnodes = 0
+        self.root = -1
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib.pb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        check(rc, self._ctx)
+
+    # -- configuration
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(lib.pb_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_mode(self, mode):
+        self._ck(lib.pb_set_mode(self._ctx, mode))
+
+    def set_rescaling(self, threshold, shift_at_root):
+        self._ck(lib.pb_set_rescaling(self._ctx, float(threshold), int(bool(shift_at_root))))
+
+    def set_tree(self, flat, branch_lengths=None):
+        """flat: tree.FlatTree (or any object with nnodes/root/child_ptr/child_idx/tip_row)."""
+        cp = np.ascontiguousarray(flat.child_ptr, dtype=np.int32)
+        ci = np.ascontiguousarray(flat.child_idx, dtype=np.int32)
+        tr = np.ascontiguousarray(flat.tip_row, dtype=np.int32)
+        bl = None if branch_lengths is None else _f64(branch_lengths)
+        if len(cp) != flat.nnodes + 1 or len(tr) != flat.nnodes:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tree arrays have the wrong length")
+        if bl is not None and len(bl) != flat.nnodes:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "branch_lengths must have nnodes entries")
+        self._ck(lib.pb_set_tree(self._ctx, int(flat.nnodes), int(flat.root), cp.ctypes.data, ci.ctypes.data,
+                                 tr.ctypes.data, None if bl is None else bl.ctypes.data))
+        self.nnodes, self.root = int(flat.nnodes), int(flat.root)
+
+    def set_branch_lengths(self, branch_lengths):
+        bl = _f64(branch_lengths)
+        if len(bl) != self.nnodes:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "branch_lengths must have nnodes entries")
+        self._ck(lib.pb_set_branch_lengths(self._ctx, bl.ctypes.data))
+
+    def set_tips(self, states):
+        """states: uint8 [ntaxa][>=nsites] host array (numpy, or a pinned torch tensor's numpy view)."""
+        states = np.asarray(states)
+        if states.dtype != np.uint8 or states.ndim != 2 or states.shape[0] != self.ntaxa \
+                or states.strides[1] != 1:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tips must be uint8 [ntaxa][nsites], site-contiguous")
+        self._ck(lib.pb_set_tips(self._ctx, states.ctypes.data, states.strides[0]))
+
+    def set_tips_ptr(self, host_ptr, ld):
+        self._ck(lib.pb_set_tips(self._ctx, ctypes.c_void_p(host_ptr), int(ld)))
+
+    def set_tips_device(self, device_ptr, ld):
+        self._ck(lib.pb_set_tips_device(self._ctx, ctypes.c_void_p(device_ptr), int(ld)))
+
+    def set_tip_masks(self, masks):
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        self._ck(lib.pb_set_tip_masks(self._ctx, masks.ctypes.data, masks.shape[1]))
+
+    def set_root_frequencies(self, pi):
+        pi = _f64(pi)
+        if len(pi) != self.nstates:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "pi must have nstates entries")
+        self._ck(lib.pb_set_root_frequencies(self._ctx, pi.ctypes.data))
+
+    def set_categories(self, rates, weights):
+        r, w = _f64(rates), _f64(weights)
+        if len(r) != self.ncat or len(w) != self.ncat:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "need ncat rates and weights")
+        self._ck(lib.pb_set_categories(self._ctx, r.ctypes.data, w.ctypes.data))
+
+    def set_eigensystem(self, U, lam, Uinv):
+        u, ui, l = _colmajor(U), _colmajor(Uinv), _f64(lam)
+        self._ck(lib.pb_set_eigensystem(self._ctx, u.ctypes.data, l.ctypes.data, ui.ctypes.data))
+
+    def set_rate_matrix(self, Q, pi):
+        q, p = _colmajor(Q), _f64(pi)
+        self._ck(lib.pb_set_rate_matrix(self._ctx, q.ctypes.data, p.ctypes.data))
+
+    def set_rate_matrix_general(self, Q):
+        q = _colmajor(Q)
+        self._ck(lib.pb_set_rate_matrix_general(self._ctx, q.ctypes.data))
+
+    def set_pmatrices(self, P):
+        """P: [ncat][nnodes][n][n] (or [nnodes][n][n] when ncat == 1), indexed [row, col]."""
+        P = np.asarray(P, dtype=np.float64).reshape(self.ncat, self.nnodes, self.nstates, self.nstates)
+        Pc = np.ascontiguousarray(np.swapaxes(P, 2, 3))
+        self._ck(lib.pb_set_pmatrices(self._ctx, Pc.ctypes.data))
+
+    # -- evaluation
+    def loglik(self, per_site=False):
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_loglik(self._ctx, ctypes.byref(total), None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
+    def enqueue(self):
+        self._ck(lib.pb_loglik_enqueue(self._ctx))
+
+    def fetch(self, per_site=False):
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_loglik_fetch(self._ctx, ctypes.byref(total), None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
+    def result_device_ptrs(self):
+        t, p = ctypes.c_void_p(), ctypes.c_void_p()
+        self._ck(lib.pb_result_device_ptrs(self._ctx, ctypes.byref(t), ctypes.byref(p)))
+        return t.value, p.value
+
+    def get_clv(self, node, cat=0):
+        v = np.empty((self.nsites, self.nstates))
+        c = np.empty(self.nsites)
+        self._ck(lib.pb_get_clv(self._ctx, int(node), int(cat), v.ctypes.data, c.ctypes.data))
+        return v, c
+
+    def get_pmatrices(self):
+        Pc = np.empty((self.ncat, self.nnodes, self.nstates, self.nstates))
+        self._ck(lib.pb_get_pmatrices(self._ctx, Pc.ctypes.data))
+        return np.ascontiguousarray(np.swapaxes(Pc, 2, 3))
+
+    @property
+    def kernel_launches(self):
+        return int(lib.pb_kernel_launches(self._ctx))
+
+    @property
+    def path_name(self):
+        return lib.pb_path_name(self._ctx).decode()
+
+
+def transition_matrices_eigen(U, lam, Uinv, ts, device=0):
+    """P(t) = U diag(exp(t lam)) Uinv for every t, one kernel launch (K1)."""
+    u, ui, l, t = _colmajor(U), _colmajor(Uinv), _f64(lam), _f64(np.atleast_1d(ts))
+    n = len(l)
+    out = np.empty((len(t), n, n))
+    check(lib.pb_transition_matrices_eigen(int(device), n, len(t), u.ctypes.data, l.ctypes.data,
+                                           ui.ctypes.data, t.ctypes.data, out.ctypes.data))
+    return np.ascontiguousarray(np.swapaxes(out, 1, 2))
+
+
+def transition_matrices_expm(Q, ts, device=0):
+    """P(t) = expm(t Q) for every t by the batched Pade kernel."""
+    q, t = _colmajor(Q), _f64(np.atleast_1d(ts))
+    n = q.shape[0]
+    out = np.empty((len(t), n, n))
+    check(lib.pb_transition_matrices_expm(int(device), n, len(t), q.ctypes.data, t.ctypes.data,
+                                          out.ctypes.data))
+    return np.ascontiguousarray(np.swapaxes(out, 1, 2))
+
+
+def host_reversible_eigensystem(Q, pi):
+    """(U, lambda, Uinv) with Q = U diag(lambda) Uinv — the host step of pb_set_rate_matrix."""
+    q, p = _colmajor(Q), _f64(pi)
+    n = len(p)
+    U, Ui, lam = np.empty((n, n)), np.empty((n, n)), np.empty(n)
+    rc = lib.pb_host_reversible_eigensystem(n, q.ctypes.data, p.ctypes.data, U.ctypes.data,
+                                            lam.ctypes.data, Ui.ctypes.data)
+    if rc != 0:
+        raise _lib.PhyloB200Error(rc, "rate matrix is not reversible with respect to pi")
+    return np.ascontiguousarray(U.T), lam, np.ascontiguousarray(Ui.T)

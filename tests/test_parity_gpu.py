@@ -1,0 +1,185 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Tolerances are the north star's: 1e-9 relative per site, 1e-10
+relative on the total (BASELINE.json)."""
+import math
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import c_oracle as C
+from phylogenetics_b200 import _lib
+from phylogenetics_b200.engine import LikelihoodContext
+
+pytestmark = pytest.mark.gpu
+
+PER_SITE_RTOL = 1e-9
+TOTAL_RTOL = 1e-10
+
+
+def oracle_per_site(case, P, mode=_lib.PB_MODE_PHYLO_CTMC):
+    thr, root_mode = (1e-6, 1) if mode == _lib.PB_MODE_PHYLO_CTMC else (1e-7, 0)
+    f = case.flat
+    return C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi, tips=case.tips,
+                     weights=case.weights, threshold=thr, root_mode=root_mode)
+
+
+def check(per_site, total, expect):
+    assert np.all(np.isfinite(per_site))
+    rel = np.abs(per_site - expect) / np.abs(expect)
+    assert rel.max() <= PER_SITE_RTOL, "per-site rel err %.3e" % rel.max()
+    truth = math.fsum(expect)
+    assert abs(total - truth) <= TOTAL_RTOL * abs(truth), "total rel err %.3e" % (abs(total - truth) / abs(truth))
+
+
+def run_ctx(case, source, level=False, keep=False, mode=_lib.PB_MODE_PHYLO_CTMC, P=None):
+    ctx = LikelihoodContext(case.n, case.nsites, case.flat.nleaves, ncat=case.ncat, level_kernels=level, keep_clv=keep)
+    ctx.set_tree(case.flat, case.bl)
+    ctx.set_mode(mode)
+    ctx.set_categories(case.rates, case.weights)
+    if source == "eigen":
+        ctx.set_rate_matrix(case.Q, case.pi)
+    elif source == "expm":
+        ctx.set_rate_matrix_general(case.Q)
+    else:
+        ctx.set_pmatrices(P)
+    ctx.set_tips(case.tips)
+    ctx.set_root_frequencies(case.pi)
+    return ctx
+
+
+CONFIGS = [
+    # name, model, ntaxa, nsites, ncat
+    ("c1_jc69_16x1000", "jc69", 16, 1000, 1),           # BASELINE configs[0]
+    ("k80_33x777", "k80", 33, 777, 1),                  # ragged site count
+    ("c2s_gtr_g4_128x4096", "gtr", 128, 4096, 4),       # configs[1] shape, fewer sites
+    ("c3s_wag_64x1500", "wag", 64, 1500, 1),            # configs[2] shape
+    ("c4s_mg94_32x700", "mg94", 32, 700, 1),            # configs[3] shape
+    ("c4s_mutsel_32x300", "mutsel", 32, 300, 1),
+]
+
+
+@pytest.mark.parametrize("name,model,ntaxa,nsites,ncat", CONFIGS)
+@pytest.mark.parametrize("level", [False, True])
+def test_same_matrices_parity(name, model, ntaxa, nsites, ncat, level):
+    """Identical P matrices fed to both sides ([`Mat p] route): pruning + rescaling + root only."""
+    case = cases.make_case(name, model, ntaxa, nsites, ncat=ncat, seed=zlib.crc32(name.encode()) % 1000)
+    P = case.host_P()
+    with run_ctx(case, "direct", level=level, P=P) as ctx:
+        total, per_site = ctx.loglik(per_site=True)
+        assert ctx.kernel_launches > 0
+    check(per_site, total, oracle_per_site(case, P))
+
+
+@pytest.mark.parametrize("name,model,ntaxa,nsites,ncat", CONFIGS)
+def test_eigen_pmatrices_parity(name, model, ntaxa, nsites, ncat):
+    """P(t) rebuilt on the device from the eigensystem (K1) vs the oracle's Pade expm restatement."""
+    from oracle import linalg_ref as la
+    case = cases.make_case(name, model, ntaxa, nsites, ncat=ncat, seed=zlib.crc32(name.encode()) % 1000)
+    f = case.flat
+    Pref = np.zeros((case.ncat, f.nnodes, case.n, case.n))
+    for k, r in enumerate(case.rates):
+        for v in range(f.nnodes):
+            if v != f.root:
+                Pref[k, v] = la.expm((case.bl[v] * r) * case.Q)
+    with run_ctx(case, "eigen") as ctx:
+        Pdev = ctx.get_pmatrices()
+        total, per_site = ctx.loglik(per_site=True)
+    mask = np.ones(f.nnodes, bool)
+    mask[f.root] = False
+    assert np.abs(Pdev[:, mask] - Pref[:, mask]).max() < 5e-14
+    check(per_site, total, oracle_per_site(case, Pref))
+
+
+def test_felsenstein_mode():
+    case = cases.make_case("fels", "k80", 40, 500, tree_kind="random")
+    P = case.host_P()
+    for level in (False, True):
+        with run_ctx(case, "direct", level=level, mode=_lib.PB_MODE_FELSENSTEIN, P=P) as ctx:
+            total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, oracle_per_site(case, P, _lib.PB_MODE_FELSENSTEIN))
+
+
+def test_conditional_likelihoods_match_oracle():
+    case = cases.make_case("clv", "gtr", 24, 64)
+    P = case.host_P()
+    f = case.flat
+    with run_ctx(case, "direct", keep=True, P=P) as ctx:
+        ctx.loglik()
+        for site in (0, 17, 63):
+            clv, car = C.conditional_likelihoods(4, f.root, f.child_ptr, f.child_idx, f.tip_row, P[0], site,
+                                                 tips=case.tips)
+            for v in range(f.nnodes):
+                gv, gc = ctx.get_clv(v)
+                np.testing.assert_allclose(gv[site], clv[v], rtol=1e-12, atol=0)
+                np.testing.assert_allclose(gc[site], car[v], rtol=1e-12, atol=1e-15)
+
+
+def test_kary_and_unary_nodes():
+    """Tree.t has arbitrary arity >= 1 (lib/tree.ml:3-8): left fold order over the children."""
+    from phylogenetics_b200 import tree as T, synthetic
+    rng = np.random.default_rng(5)
+    t = T.node(None, [
+        T.branch(0.11, T.leaf(0)),
+        T.branch(0.2, T.node(None, [T.branch(0.05, T.leaf(1)), T.branch(0.3, T.leaf(2)), T.branch(0.1, T.leaf(3)),
+                                    T.branch(0.4, T.node(None, [T.branch(0.2, T.leaf(4)), T.branch(0.15, T.leaf(5))]))])),
+        T.branch(0.07, T.node(None, [T.branch(0.3, T.node(None, [T.branch(0.1, T.leaf(6)), T.branch(0.2, T.leaf(7))]))])),
+        T.branch(0.25, T.node(None, [T.branch(0.2, T.node(None, [T.branch(0.3, T.leaf(8)), T.branch(0.1, T.leaf(9))])),
+                                     T.branch(0.1, T.node(None, [T.branch(0.2, T.leaf(10)), T.branch(0.6, T.leaf(11))])),
+                                     T.branch(0.3, T.leaf(12))])),
+    ])
+    flat = T.flatten(t)
+    bl = flat.branch_lengths(float)
+    Q, pi = synthetic.random_gtr(rng, 10.0)
+    P = synthetic.host_transition_matrices(Q, pi, bl)
+    tips = synthetic.simulate_alignment(rng, flat, P, pi, 333)
+    case = cases.Case("kary", flat, bl, Q, pi, tips)
+    for level in (False, True):
+        with run_ctx(case, "direct", level=level, P=P) as ctx:
+            total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, oracle_per_site(case, P))
+
+
+def test_deep_rescaling_long_branches():
+    """Caterpillar tree with long branches: rescaling fires at almost every node."""
+    from phylogenetics_b200 import tree as T, synthetic
+    rng = np.random.default_rng(11)
+    t = T.leaf(0)
+    for i in range(1, 200):
+        t = T.binary_node(None, T.branch(float(rng.uniform(0.5, 3.0)), t), T.branch(float(rng.uniform(0.5, 3.0)), T.leaf(i)))
+    flat = T.flatten(t)
+    bl = flat.branch_lengths(float)
+    Q, pi = synthetic.random_gtr(rng, 10.0)
+    P = synthetic.host_transition_matrices(Q, pi, bl)
+    tips = synthetic.simulate_alignment(rng, flat, P, pi, 257)
+    case = cases.Case("caterpillar", flat, bl, Q, pi, tips)
+    expect = oracle_per_site(case, P)
+    assert expect.min() < -250            # far below what unscaled doubles of 4^-200 could carry safely
+    for level in (False, True):
+        with run_ctx(case, "direct", level=level, P=P) as ctx:
+            total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, expect)
+
+
+def test_single_site_and_repeat_evaluation():
+    case = cases.make_case("one", "jc69", 5, 1)
+    P = case.host_P()
+    with run_ctx(case, "eigen") as ctx:
+        a = ctx.loglik()
+        b = ctx.loglik()
+        ctx.set_branch_lengths(case.bl * 1.5)
+        c = ctx.loglik()
+    assert a == b and a != c
+    check(np.array([a]), a, oracle_per_site(case, P))
+
+
+def test_errors_are_reported_not_thrown():
+    with LikelihoodContext(4, 10, 3) as ctx:
+        with pytest.raises(_lib.PhyloB200Error) as e:
+            ctx.loglik()
+        assert e.value.code == _lib.PB_ERR_STATE
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.set_mode(7)
+    with pytest.raises(_lib.PhyloB200InvalidArgument):
+        LikelihoodContext(1, 10, 3)
