@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: pruning site.node updates / second (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--sites S] [--config c2|c3|c4] [--path auto|level]
+
+A "step" is one full log-likelihood evaluation of one alignment (shard): P(t) for every
+branch x category, Felsenstein pruning over the whole tree, root reduction (and, for N > 1,
+the all-reduce of the scalar).  Workload at N = 1: BASELINE configs[1], GTR+Gamma4, 128 taxa,
+1M sites; for N > 1 every rank holds its own 1M-site shard (weak scaling, sites are
+independent).  One process per GPU under torchrun.
+
+The reference arm (--impl reference) times the CPU restatement of the reference's pruning
+(oracle/pruning_oracle.c, OpenMP over sites on all host cores) on a bounded sample of the
+same workload: the OCaml reference itself cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "pruning site-node updates/sec"
+UNIT = "site-node updates/s"
+
+CONFIGS = {
+    # name: (model, ntaxa, nsites, ncat, description)
+    "c2": ("gtr", 128, 1_000_000, 4, "GTR+Gamma4 DNA, 128-taxon birth-death tree, 1M sites"),
+    "c3": ("wag", 64, 200_000, 1, "WAG amino-acid 20-state, 64-taxon tree, 200k sites"),
+    "c4": ("mg94", 32, 100_000, 1, "MG94 codon 61-state, 32-taxon tree, 100k codons"),
+    "c1": ("jc69", 16, 1_000, 1, "JC69 DNA, 16-taxon tree, 1k sites"),
+}
+
+
+def algorithmic_bytes_per_site(n, ncat, ntaxa):
+    """B_site = 8*C*(n+1)*(2T-4) + T + 8 (level-scheduled model)."""
+    return 8 * ncat * (n + 1) * (2 * ntaxa - 4) + ntaxa + 8
+
+
+def algorithmic_flops_per_site(n, ncat, ntaxa):
+    """F_site = C*(2n^2*(T-2) + n*(T-1)) (tip children are look-ups)."""
+    return ncat * (2 * n * n * (ntaxa - 2) + n * (ntaxa - 1))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def build_case(cfg, nsites, seed):
+    import cases
+    model, ntaxa, _, ncat, _ = CONFIGS[cfg]
+    return cases.make_case(cfg, model, ntaxa, nsites, ncat=ncat, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[1]) for r in inside if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in inside:
+            for nm, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(inside[0][2]) if inside else None,
+                "samples": len(inside), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's pruning, all host cores, bounded sample."""
+    if rank != 0:
+        return
+    from oracle import c_oracle as C
+    cfg = args.config
+    model, ntaxa, full_sites, ncat, desc = CONFIGS[cfg]
+    cores = os.cpu_count() or 1
+    # size the per-step sample for roughly 3 s of CPU work per step
+    probe = build_case(cfg, 4096, seed=1)
+    P = probe.host_P()
+    f = probe.flat
+    t0 = time.perf_counter()
+    C.pruning(probe.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, probe.pi, tips=probe.tips,
+              weights=probe.weights, nthreads=cores)
+    per_site = (time.perf_counter() - t0) / 4096
+    budget = 180.0 / max(1, args.steps + args.warmup)
+    sample = int(min(full_sites, max(4096, min(3.0, budget) / per_site)))
+    case = build_case(cfg, sample, seed=2)
+    P = case.host_P()
+    f = case.flat
+
+    def step():
+        ps = C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi, tips=case.tips,
+                       weights=case.weights, nthreads=cores)
+        return C.sum_sequential(ps)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    ninternal = f.ninternal
+    value = sample * ninternal / dt
+    sample_desc = "%d of %d sites per step, same tree/model shape" % (sample, full_sites)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": sample_desc,
+                   "note": "CPU restatement of the reference algorithm (oracle/pruning_oracle.c, OpenMP over "
+                           "sites, P(t) precomputed per branch), not the OCaml/lacaml binary"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_block(cfg, seconds=12.0):
+    """Oracle port timed on this box's host cores on a bounded sample (rank 0, N = 1 only)."""
+    from oracle import c_oracle as C
+    cores = os.cpu_count() or 1
+    _, _, full_sites, _, _ = CONFIGS[cfg]
+    probe = build_case(cfg, 4096, seed=1)
+    P = probe.host_P()
+    f = probe.flat
+
+    def run(case, P):
+        t0 = time.perf_counter()
+        C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi, tips=case.tips,
+                  weights=case.weights, nthreads=cores)
+        return time.perf_counter() - t0
+    run(probe, P)
+    per_site = run(probe, P) / 4096
+    sample = int(min(full_sites, max(4096, seconds / per_site)))
+    case = build_case(cfg, sample, seed=2)
+    P = case.host_P()
+    f = case.flat
+    dt = run(case, P)
+    return {"value": sample * f.ninternal / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d sites, one pass (%.1f s), same tree/model shape; CPU restatement of the "
+                      "reference algorithm, not the OCaml binary" % (sample, full_sites, dt)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from phylogenetics_b200.engine import LikelihoodContext
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = args.config
+    model, ntaxa, full_sites, ncat, desc = CONFIGS[cfg]
+    nsites = args.sites or full_sites
+    case = build_case(cfg, nsites, seed=100 + rank)          # every rank simulates its own site shard
+    f = case.flat
+    n = case.n
+    ninternal = f.ninternal
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = LikelihoodContext(n, nsites, f.nleaves, ncat=ncat, device=local_rank, level_kernels=(args.path == "level"))
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_tree(f, case.bl)
+    ctx.set_categories(case.rates, case.weights)
+    ctx.set_rate_matrix(case.Q, case.pi)
+    ctx.set_root_frequencies(case.pi)
+    tips_pinned = torch.from_numpy(case.tips).pin_memory()
+    ctx.set_tips_ptr(tips_pinned.data_ptr(), nsites)
+    ctx.set_timing(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+
+    total_t = None
+
+    def step():
+        nonlocal total_t
+        ctx.enqueue()
+        if world > 1:
+            if total_t is None:
+                total_t = torch.as_tensor(ctx.total_as_cuda_array(), device="cuda")
+            dist.all_reduce(total_t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness gate on a slice of this rank's shard before timing anything
+    ctx.enqueue()
+    total0, per_site0 = ctx.fetch(per_site=True)
+    from oracle import c_oracle as C
+    Pdev = ctx.get_pmatrices()
+    chk = min(nsites, 20000)
+    expect = C.pruning(n, f.root, f.child_ptr, f.child_idx, f.tip_row, Pdev, case.pi,
+                       tips=np.ascontiguousarray(case.tips[:, :chk]), weights=case.weights)
+    rel = float(np.max(np.abs(per_site0[:chk] - expect) / np.abs(expect)))
+    if not rel < 1e-9:
+        raise SystemExit("parity gate failed: per-site rel err %.3e" % rel)
+    tot_rel = abs(total0 - float(np.sum(per_site0))) / abs(total0)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    prune_ms = []
+    barrier()
+    t_wall0 = time.time()
+    for a, b in ev:
+        flush.zero_()                    # L2 flush, outside the event pair
+        a.record(stream)
+        step()
+        b.record(stream)
+        b.synchronize()
+        prune_ms.append(ctx.get_timing())
+    barrier()
+    t_wall1 = time.time()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    launches = ctx.kernel_launches - launches0
+    t_local = sum(step_ms) / 1e3
+    t = torch.tensor([t_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # end-to-end through the public API with HOST buffers: H2D of the step's tips from pinned
+    # memory + evaluation + D2H of the total, every step.
+    e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(2):
+        ctx.set_tips_ptr(tips_pinned.data_ptr(), nsites)
+        ctx.loglik()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        ctx.set_tips_ptr(tips_pinned.data_ptr(), nsites)
+        tot = ctx.loglik()
+        if world > 1:
+            tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt)
+            tot = float(tt.item())
+    e1.record(stream)
+    barrier()
+    e2e_t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * nsites * ninternal * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        units = world * nsites * ninternal * args.steps
+        value = units / t_max
+        pm = np.array(prune_ms)                                    # [steps][3] ms
+        prune_avg_ms = float(pm[:, 1].mean())
+        nlaunch_prune = max(1, launches // args.steps - 3) if ctx.path_name != "fused4" else 1
+        bytes_eval = algorithmic_bytes_per_site(n, ncat, ntaxa) * nsites
+        flops_eval = algorithmic_flops_per_site(n, ncat, ntaxa) * nsites
+        achieved = bytes_eval / (prune_avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": "of " + peak_kind,
+                "kernel": ctx.path_name, "launches_per_step": nlaunch_prune,
+                "kernel_ms_per_step": prune_avg_ms,
+                "algorithmic_bytes_per_step": bytes_eval,
+                "fp64_tflops_achieved": flops_eval / (prune_avg_ms * 1e-3) / 1e12,
+                "note": ("fused4 keeps conditional likelihoods on chip: it moves ntaxa+8C bytes/site of HBM, "
+                         "so against the level-scheduled algorithmic bytes the fraction can exceed 1; its own "
+                         "bound is the FP64 pipe" if ctx.path_name == "fused4" else
+                         "level-scheduled: every inner CLV written once and read once")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + (" per GPU" if world > 1 else ""), "sites_per_gpu": nsites,
+                       "ntaxa": ntaxa, "nstates": n, "ncat": ncat, "internal_nodes": ninternal,
+                       "path": ctx.path_name, "l2": "flushed between steps (256 MiB memset outside the event pairs)",
+                       "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
+                       "parity_gate": {"per_site_max_rel_err": rel, "sites_checked": chk,
+                                       "total_vs_sum_of_sites_rel": tot_rel}},
+            "roofline": roof,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(case.tips.nbytes),
+                    "d2h_bytes_per_step": 8, "steps": e2e_steps,
+                    "note": "pb_set_tips from pinned host memory + pb_loglik (blocking, returns the total) per step"},
+            "gpu_launches": int(launches),
+            "phase_ms": {"pmat": float(pm[:, 0].mean()), "pruning": prune_avg_ms, "root": float(pm[:, 2].mean())},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(cfg)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--sites", type=int, default=0, help="override sites per GPU (testing)")
+    ap.add_argument("--path", default="auto", choices=["auto", "level"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,9 +74,10 @@ pb_ctx *pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, 
 void pb_destroy(pb_ctx *ctx);
 /* ctx may be NULL: last error of a failed pb_create on this thread. */
 const char *pb_last_error(const pb_ctx *ctx);
-/* Enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of
- * the context's own.  NULL restores the private stream. */
+/* Enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own non-blocking stream.  The handle 0 means the CUDA default stream. */
 int pb_set_stream(pb_ctx *ctx, void *cuda_stream);
+int pb_use_private_stream(pb_ctx *ctx);
 int pb_set_mode(pb_ctx *ctx, int mode);
 /* Explicit threshold / root-shift, overriding pb_set_mode. */
 int pb_set_rescaling(pb_ctx *ctx, double threshold, int shift_at_root);
@@ -146,6 +147,17 @@ int pb_result_device_ptrs(pb_ctx *ctx, const double **d_total, const double **d_
 int pb_get_clv(pb_ctx *ctx, int node, int cat, double *v, double *carry);
 /* Copy out the matrices in use: P[(k*nnodes + v)*n*n ...] column-major. */
 int pb_get_pmatrices(pb_ctx *ctx, double *P);
+
+/* Tunables (all optional): "fused_block" (128|256|512 threads), "fused_spt" (1|2 sites per
+ * thread), "fused_exact_log" (1: the fused kernel adds log(max v) at every rescaling like the
+ * reference's carry; 0 (default): it accumulates the product of the maxima and takes one log). */
+int pb_set_option(pb_ctx *ctx, const char *name, double value);
+
+/* Device timing of the phases of an evaluation, measured with CUDA events on the
+ * context's stream: ms[0] = P(t) construction, ms[1] = pruning kernels, ms[2] = root
+ * reduction of the LAST evaluation (pb_get_timing waits for it). */
+int pb_set_timing(pb_ctx *ctx, int on);
+int pb_get_timing(pb_ctx *ctx, double *ms /* [3] */);
 
 /* How many kernels of this library the context has launched so far. */
 int64_t pb_kernel_launches(const pb_ctx *ctx);

@@ -25,12 +25,12 @@ PB_MODE_FELSENSTEIN = 1
 
 # Every symbol include/phylo_b200.h declares (tests check the .so exports them all).
 EXPORTS = [
-    "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_set_mode", "pb_set_rescaling",
+    "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
     "pb_set_tree", "pb_set_branch_lengths", "pb_set_tips", "pb_set_tips_device", "pb_set_tip_masks",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_get_pmatrices",
-    "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
+    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
 ]
 
@@ -59,6 +59,7 @@ def _load():
         "pb_destroy": (None, [vp]),
         "pb_last_error": (ctypes.c_char_p, [vp]),
         "pb_set_stream": (ci, [vp, vp]),
+        "pb_use_private_stream": (ci, [vp]),
         "pb_set_mode": (ci, [vp, ci]),
         "pb_set_rescaling": (ci, [vp, dbl, ci]),
         "pb_set_tree": (ci, [vp, ci, ci, vp, vp, vp, vp]),
@@ -78,6 +79,9 @@ def _load():
         "pb_result_device_ptrs": (ci, [vp, vp, vp]),
         "pb_get_clv": (ci, [vp, ci, ci, vp, vp]),
         "pb_get_pmatrices": (ci, [vp, vp]),
+        "pb_set_option": (ci, [vp, ctypes.c_char_p, dbl]),
+        "pb_set_timing": (ci, [vp, ci]),
+        "pb_get_timing": (ci, [vp, vp]),
         "pb_kernel_launches": (i64, [vp]),
         "pb_path_name": (ctypes.c_char_p, [vp]),
         "pb_transition_matrices_eigen": (ci, [ci, ci, ci, vp, vp, vp, vp, vp]),

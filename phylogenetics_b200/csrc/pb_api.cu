@@ -10,11 +10,12 @@
 #include <vector>
 
 #include "pb_kernels.cuh"
+#include "pb_kernels_fused.cuh"
 #include "pb_kernels_dmma.cuh"
 #include "pb_kernels_expm.cuh"
 #include "pb_host_linalg.h"
 
-using pbk::FusedOp;
+using pbk::FusedOp2;
 using pbk::LevelChild;
 using pbk::LevelNode;
 
@@ -77,11 +78,17 @@ struct pb_ctx {
     std::vector<int> lv_first;          // first LevelNode of every level (+ end)
     std::vector<int> slot_of_node;      // CLV slot of every internal node (level path)
     int nslots = 0, max_arity = 0;
-    std::vector<FusedOp> fprog;
-    int fstack = 0;
+    std::vector<FusedOp2> fprog;
+    std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
+    int fstack = 0, fwords = 0;
+    int fused_block = 256, fused_spt = 2, fused_exact_log = 0;
     DevBuf<LevelNode> d_lv_nodes;
     DevBuf<LevelChild> d_lv_children;
-    DevBuf<FusedOp> d_fprog;
+    DevBuf<FusedOp2> d_fprog;
+    DevBuf<int> d_tip_order;
+    DevBuf<uint64_t> d_packed;
+    DevBuf<int> d_bad;
+    bool pack_dirty = true, tips_checked = false;
 
     // inputs
     DevBuf<uint8_t> d_tips;
@@ -98,8 +105,12 @@ struct pb_ctx {
     // work + outputs
     DevBuf<double> d_pool, d_site_cat, d_per_site, d_partials, d_total;
     int64_t slot_stride = 0;
-    double* h_total = nullptr;   // pinned
+    double* h_total = nullptr;   // pinned: [0] = total, [1] = bad-tip flag (as int)
     bool evaluated = false;
+
+    // optional per-phase device timing (pb_set_timing)
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -129,14 +140,18 @@ void to_row_major(int n, size_t count, const double* in, double* out)
             for (int j = 0; j < n; j++) out[m * n * n + i * n + j] = in[m * n * n + j * n + i];
 }
 
+size_t fused_smem_bytes(const pb_ctx* c)
+{
+    return (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * c->fused_block * c->fused_spt * 8 +
+           c->fprog.size() * sizeof(FusedOp2);
+}
+
 int path_of(const pb_ctx* c)
 {
     const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0 || c->have_masks;
     if (c->n == 4) {
         if (!level && c->have_tree) {
-            const size_t need = (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 5 * 128 * 8 +
-                                c->fprog.size() * sizeof(FusedOp);
-            if (need <= c->smem_optin) return PATH_FUSED4;
+            if (fused_smem_bytes(c) <= c->smem_optin && c->nnodes < 65536) return PATH_FUSED4;
         }
         return PATH_LEVEL4;
     }
@@ -250,21 +265,20 @@ int compile_tree(pb_ctx* c)
 
     // ---- fused accumulator/stack program (4-state path)
     c->fprog.clear();
+    c->tip_order.clear();
     c->fstack = su[c->root];
     {
         auto is_inner = [&](int v) { return c->child_ptr[v] != c->child_ptr[v + 1]; };
-        auto op = [&](int code, int pA = 0, int rowA = 0, int pB = 0, int rowB = 0) {
-            FusedOp o{code, pA, rowA, pB, rowB, 0, 0, 0};
-            return o;
-        };
-        // work items: >= 0 visit node, < 0 emit the op stored in `pending`
-        struct Item { int node; FusedOp emit; bool is_emit; };
+        // abstract ops first: code, pA (+tip A), pB (+tip B); tips get their packed position below
+        struct AOp { int code, pA, tipA, pB, tipB; };
+        std::vector<AOp> aops;
+        struct Item { int node; AOp emit; bool is_emit; };
         std::vector<Item> st;
         st.push_back({c->root, {}, false});
         while (!st.empty()) {
             Item it = st.back();
             st.pop_back();
-            if (it.is_emit) { c->fprog.push_back(it.emit); continue; }
+            if (it.is_emit) { aops.push_back(it.emit); continue; }
             const int v = it.node;
             const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
             std::vector<Item> seq;   // in execution order
@@ -272,37 +286,73 @@ int compile_tree(pb_ctx* c)
                 int a = c->child_idx[c0], b = c->child_idx[c0 + 1];
                 const bool ia = is_inner(a), ib = is_inner(b);
                 if (!ia && !ib) {
-                    seq.push_back({0, op(pbk::FOP_TIP_TIP, a, c->tip_row[a], b, c->tip_row[b]), true});
+                    seq.push_back({0, {pbk::FOP_TIP_TIP, a, a, b, b}, true});
                 } else if (ia && ib) {
-                    if (su[b] > su[a]) std::swap(a, b);   // heavier first: exact, x*y and c1+c2 commute
+                    if (su[b] > su[a]) std::swap(a, b);   // deeper first: exact, x*y and c1+c2 commute
                     seq.push_back({a, {}, false});
-                    seq.push_back({0, op(pbk::FOP_APPLY, a), true});
-                    seq.push_back({0, op(pbk::FOP_PUSH), true});
+                    seq.push_back({0, {pbk::FOP_APPLY, a, -1, 0, -1}, true});
+                    seq.push_back({0, {pbk::FOP_PUSH, 0, -1, 0, -1}, true});
                     seq.push_back({b, {}, false});
-                    seq.push_back({0, op(pbk::FOP_APPLY, b), true});
-                    seq.push_back({0, op(pbk::FOP_POP_MUL), true});
+                    seq.push_back({0, {pbk::FOP_APPLY, b, -1, 0, -1}, true});
+                    seq.push_back({0, {pbk::FOP_POP_MUL, 0, -1, 0, -1}, true});
                 } else {
                     const int in = ia ? a : b, tp = ia ? b : a;
                     seq.push_back({in, {}, false});
-                    seq.push_back({0, op(pbk::FOP_APPLY_MUL_TIP, in, 0, tp, c->tip_row[tp]), true});
+                    seq.push_back({0, {pbk::FOP_APPLY_MUL_TIP, in, -1, tp, tp}, true});
                 }
             } else {
                 for (int k = c0; k < c1; k++) {      // reference order (left fold)
                     const int ch = c->child_idx[k];
                     if (!is_inner(ch)) {
-                        seq.push_back({0, op(k == c0 ? pbk::FOP_TIP : pbk::FOP_MUL_TIP, ch, c->tip_row[ch]), true});
+                        seq.push_back({0, {k == c0 ? pbk::FOP_TIP : pbk::FOP_MUL_TIP, ch, ch, 0, -1}, true});
                     } else {
-                        if (k > c0) seq.push_back({0, op(pbk::FOP_PUSH), true});
+                        if (k > c0) seq.push_back({0, {pbk::FOP_PUSH, 0, -1, 0, -1}, true});
                         seq.push_back({ch, {}, false});
-                        seq.push_back({0, op(pbk::FOP_APPLY, ch), true});
-                        if (k > c0) seq.push_back({0, op(pbk::FOP_POP_MUL), true});
+                        seq.push_back({0, {pbk::FOP_APPLY, ch, -1, 0, -1}, true});
+                        if (k > c0) seq.push_back({0, {pbk::FOP_POP_MUL, 0, -1, 0, -1}, true});
                     }
                 }
             }
             for (auto r = seq.rbegin(); r != seq.rend(); ++r) st.push_back(*r);
         }
-        c->fprog.push_back(op(pbk::FOP_ROOT));
+        aops.push_back({pbk::FOP_ROOT, 0, -1, 0, -1});
+        // lower to FusedOp2: tips are consumed in program order, 32 per packed word
+        auto mk = [](int code, int pA, int shA, int pB, int shB) {
+            FusedOp2 o;
+            o.code = (uint8_t)code; o.shA = (uint8_t)shA; o.shB = (uint8_t)shB; o.pad = 0;
+            o.pA = (uint16_t)pA; o.pB = (uint16_t)pB;
+            return o;
+        };
+        int consumed = 0;
+        auto next_tip = [&](int leaf) {
+            if (consumed > 0 && consumed % 32 == 0) c->fprog.push_back(mk(pbk::FOP_LOADW, 0, 0, 0, 0));
+            c->tip_order.push_back(c->tip_row[leaf]);
+            return 2 * (consumed++ % 32);
+        };
+        for (const AOp& a : aops) {
+            if (a.code == pbk::FOP_TIP_TIP) {
+                if ((consumed + 1) % 32 == 0) {       // the pair straddles two words: TIP ; LOADW ; MUL_TIP (same arithmetic)
+                    const int sa = next_tip(a.tipA);
+                    c->fprog.push_back(mk(pbk::FOP_TIP, a.pA, sa, 0, 0));
+                    const int sb = next_tip(a.tipB);
+                    c->fprog.push_back(mk(pbk::FOP_MUL_TIP, a.pB, sb, 0, 0));
+                } else {
+                    const int sa = next_tip(a.tipA), sb = next_tip(a.tipB);
+                    c->fprog.push_back(mk(pbk::FOP_TIP_TIP, a.pA, sa, a.pB, sb));
+                }
+            } else if (a.code == pbk::FOP_TIP || a.code == pbk::FOP_MUL_TIP) {
+                const int sa = next_tip(a.tipA);
+                c->fprog.push_back(mk(a.code, a.pA, sa, 0, 0));
+            } else if (a.code == pbk::FOP_APPLY_MUL_TIP) {
+                const int sb = next_tip(a.tipB);
+                c->fprog.push_back(mk(a.code, a.pA, 0, a.pB, sb));
+            } else {
+                c->fprog.push_back(mk(a.code, a.pA, 0, 0, 0));
+            }
+        }
+        c->fwords = (consumed + 31) / 32;
     }
+    c->pack_dirty = true;
 
     // upload
     PB_CUDA(c, c->d_lv_nodes.ensure(c->lv_nodes.size()));
@@ -310,7 +360,9 @@ int compile_tree(pb_ctx* c)
     PB_CUDA(c, c->d_fprog.ensure(c->fprog.size()));
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_nodes.p, c->lv_nodes.data(), c->lv_nodes.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_children.p, c->lv_children.data(), c->lv_children.size() * sizeof(LevelChild), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog.p, c->fprog.data(), c->fprog.size() * sizeof(FusedOp), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog.p, c->fprog.data(), c->fprog.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, c->d_tip_order.ensure(c->tip_order.size()));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_tip_order.p, c->tip_order.data(), c->tip_order.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PB_OK;
 }
@@ -355,23 +407,71 @@ int launch_level_dense(pb_ctx* c, int first, int count, int store_root)
     return PB_OK;
 }
 
+template <int BLOCK, int SPT, bool EXACT>
+int launch_fused4_variant(pb_ctx* c)
+{
+    auto kern = pbk::fused4<BLOCK, SPT, EXACT>;
+    const size_t smem = fused_smem_bytes(c);
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+    if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4: kernel does not fit on an SM");
+    const int64_t ntiles = c->spad / (BLOCK * SPT);
+    int64_t gx = ((int64_t)c->sm_count * occ + c->ncat - 1) / c->ncat;
+    gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
+    dim3 grid((unsigned)gx, c->ncat);
+    kern<<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1), c->d_P.p,
+                                           c->nnodes, c->d_packed.p, c->spad, ntiles, c->d_pi.p, c->threshold,
+                                           c->shift_at_root, c->d_site_cat.p);
+    c->launches++;
+    return PB_OK;
+}
+
+int launch_fused4(pb_ctx* c)
+{
+    const int key = c->fused_block * 10 + c->fused_spt;
+    if (c->fused_exact_log) {
+        switch (key) {
+        case 1281: return launch_fused4_variant<128, 1, true>(c);
+        case 2561: return launch_fused4_variant<256, 1, true>(c);
+        case 2562: return launch_fused4_variant<256, 2, true>(c);
+        case 5121: return launch_fused4_variant<512, 1, true>(c);
+        default: return launch_fused4_variant<128, 2, true>(c);
+        }
+    }
+    switch (key) {
+    case 1281: return launch_fused4_variant<128, 1, false>(c);
+    case 2561: return launch_fused4_variant<256, 1, false>(c);
+    case 2562: return launch_fused4_variant<256, 2, false>(c);
+    case 5121: return launch_fused4_variant<512, 1, false>(c);
+    default: return launch_fused4_variant<128, 2, false>(c);
+    }
+}
+
 int run_pruning(pb_ctx* c)
 {
     const int n = c->n;
     const int path = path_of(c);
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
     if (path == PATH_FUSED4) {
-        constexpr int BLOCK = 128;
-        const size_t smem = (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 5 * BLOCK * 8 +
-                            c->fprog.size() * sizeof(FusedOp);
-        PB_CUDA(c, cudaFuncSetAttribute(pbk::fused4<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)(c->spad / BLOCK), c->ncat);
-        pbk::fused4<BLOCK><<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1),
-                                                             c->d_P.p, c->nnodes, c->d_tips.p, c->spad, c->d_pi.p,
-                                                             c->threshold, c->shift_at_root, c->d_site_cat.p, c->spad);
-        c->launches++;
+        if (c->pack_dirty) {
+            PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
+            pbk::pack_tips4<<<(unsigned)((c->spad + 255) / 256), 256, 0, c->stream>>>(
+                c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad,
+                c->d_bad.p);
+            c->launches++;
+            c->pack_dirty = false;
+            c->tips_checked = true;
+        }
+        int rc = launch_fused4(c);
+        if (rc != PB_OK) return rc;
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
+    }
+    if (!c->tips_checked) {
+        pbk::validate_tips<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_tips.p, (int64_t)c->ntaxa * c->spad, n, c->d_bad.p);
+        c->launches++;
+        c->tips_checked = true;
     }
     // level-scheduled paths
     c->slot_stride = (int64_t)c->ncat * (n + 1) * c->spad;
@@ -466,19 +566,28 @@ pb_ctx* pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, 
     c->nsites = nsites;
     c->ntaxa = ntaxa;
     c->flags = flags;
-    c->spad = round_up(nsites, 512);
+    c->spad = round_up(nsites, 1024);
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMallocHost(&c->h_total, sizeof(double))) != cudaSuccess) {
+        (e = cudaMallocHost(&c->h_total, 2 * sizeof(double))) != cudaSuccess) {
         cuda_fail(nullptr, e, "stream/pinned allocation");
         delete c;
         return nullptr;
     }
     c->stream = c->own_stream;
+    if (const char* v = getenv("PB_FUSED_VARIANT")) {     // e.g. "256x2": threads per block x sites per thread
+        int b = 0, q = 0;
+        if (sscanf(v, "%dx%d", &b, &q) == 2 && (b == 128 || b == 256 || b == 512) && (q == 1 || q == 2)) {
+            c->fused_block = b;
+            c->fused_spt = q;
+        }
+    }
+    if (const char* v = getenv("PB_FUSED_EXACT_LOG")) c->fused_exact_log = atoi(v) != 0;
     c->h_rates.assign(ncat, 1.0);
     c->h_weights.assign(ncat, 1.0 / ncat);
-    if (c->d_rates.ensure(ncat) != cudaSuccess || c->d_weights.ensure(ncat) != cudaSuccess ||
+    if (c->d_bad.ensure(1) != cudaSuccess || cudaMemset(c->d_bad.p, 0, sizeof(int)) != cudaSuccess ||
+        c->d_rates.ensure(ncat) != cudaSuccess || c->d_weights.ensure(ncat) != cudaSuccess ||
         cudaMemcpy(c->d_rates.p, c->h_rates.data(), ncat * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_weights.p, c->h_weights.data(), ncat * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
         fail(nullptr, PB_ERR_NOMEM, "device allocation failed");
@@ -494,6 +603,7 @@ void pb_destroy(pb_ctx* c)
     cudaSetDevice(c->device);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     if (c->h_total) cudaFreeHost(c->h_total);
+    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
     c->d_tips.release(); c->d_masks.release(); c->d_pi.release(); c->d_rates.release(); c->d_weights.release();
     c->d_blen.release(); c->d_U.release(); c->d_lambda.release(); c->d_Uinv.release(); c->d_Q.release();
@@ -509,7 +619,14 @@ void pb_destroy(pb_ctx* c)
 int pb_set_stream(pb_ctx* c, void* s)
 {
     PB_ENTER(c);
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;      // 0 is a valid handle: the CUDA default stream
+    return PB_OK;
+}
+
+int pb_use_private_stream(pb_ctx* c)
+{
+    PB_ENTER(c);
+    c->stream = c->own_stream;
     return PB_OK;
 }
 
@@ -609,8 +726,11 @@ int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p, c->spad, states, ld, c->nsites, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_tips = true;
     c->have_masks = false;
+    c->pack_dirty = true;
+    c->tips_checked = false;
     return PB_OK;
 }
 
@@ -621,8 +741,11 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p, c->spad, d_states, ld, c->nsites, c->ntaxa, cudaMemcpyDeviceToDevice, c->stream));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_tips = true;
     c->have_masks = false;
+    c->pack_dirty = true;
+    c->tips_checked = false;
     return PB_OK;
 }
 
@@ -736,11 +859,16 @@ int pb_loglik_enqueue(pb_ctx* c)
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
     if (!c->have_tips) return fail(c, PB_ERR_STATE, "tip states not set");
     if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     int rc = build_pmatrices(c);
     if (rc != PB_OK) return rc;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if ((rc = run_pruning(c)) != PB_OK) return rc;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     if ((rc = run_root_reduction(c)) != PB_OK) return rc;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->evaluated = true;
     return PB_OK;
 }
@@ -752,6 +880,8 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
     if (per_site)
         PB_CUDA(c, cudaMemcpyAsync(per_site, c->d_per_site.p, sizeof(double) * c->nsites, cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*reinterpret_cast<const int*>(c->h_total + 1) != 0)
+        return fail(c, PB_ERR_INVALID_ARG, "tip state out of range (>= nstates) in the alignment");
     if (total) *total = *c->h_total;
     return PB_OK;
 }
@@ -819,6 +949,49 @@ int pb_get_pmatrices(pb_ctx* c, double* P)
         for (int k = 0; k < c->ncat; k++)   // the root has no branch: report identity
             for (int i = 0; i < n; i++)
                 for (int j = 0; j < n; j++) P[((size_t)k * c->nnodes + c->root) * n * n + j * n + i] = (i == j) ? 1.0 : 0.0;
+    return PB_OK;
+}
+
+int pb_set_option(pb_ctx* c, const char* name, double value)
+{
+    PB_ENTER(c);
+    if (!name) return fail(c, PB_ERR_INVALID_ARG, "option name is null");
+    const std::string k(name);
+    const int iv = (int)value;
+    if (k == "fused_block") {
+        if (iv != 128 && iv != 256 && iv != 512) return fail(c, PB_ERR_INVALID_ARG, "fused_block must be 128, 256 or 512");
+        c->fused_block = iv;
+    } else if (k == "fused_spt") {
+        if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1 or 2");
+        c->fused_spt = iv;
+    } else if (k == "fused_exact_log") {
+        c->fused_exact_log = iv != 0;
+    } else {
+        return fail(c, PB_ERR_INVALID_ARG, "unknown option: " + k);
+    }
+    if (c->fused_block == 512 && c->fused_spt == 2) c->fused_spt = 1;
+    return PB_OK;
+}
+
+int pb_set_timing(pb_ctx* c, int on)
+{
+    PB_ENTER(c);
+    if (on && !c->ev[0])
+        for (int i = 0; i < 4; i++) PB_CUDA(c, cudaEventCreate(&c->ev[i]));
+    c->timing = on != 0;
+    return PB_OK;
+}
+
+int pb_get_timing(pb_ctx* c, double* ms)
+{
+    PB_ENTER(c);
+    if (!c->timing || !c->evaluated || !ms) return fail(c, PB_ERR_STATE, "timing is off or nothing was evaluated");
+    PB_CUDA(c, cudaEventSynchronize(c->ev[3]));
+    for (int i = 0; i < 3; i++) {
+        float t = 0.f;
+        PB_CUDA(c, cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]));
+        ms[i] = t;
+    }
     return PB_OK;
 }
 

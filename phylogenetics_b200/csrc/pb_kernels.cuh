@@ -44,12 +44,6 @@ enum FusedOpCode : int {
     FOP_APPLY_MUL_TIP = 6,  // ACC = shiftmul(P[pA].ACC, col(pB, tip rowB))
     FOP_ROOT = 7       // x pi, optional shift, log(sum) + carry -> site_cat
 };
-struct FusedOp {
-    int code;
-    int pA, rowA;
-    int pB, rowB;
-    int pad0, pad1, pad2;
-};
 
 // --------------------------------------------------------------------------
 // K1: P[c][b] = U diag(exp(t_b r_c lambda)) Uinv for every branch x category, one launch.
@@ -294,105 +288,6 @@ level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
 #pragma unroll
             for (int i = 1; i < N; i++) sum += acc[i];
             site_cat[(int64_t)c * spad + s] = log(sum) + carry;
-        }
-    }
-}
-
-// --------------------------------------------------------------------------
-// K2 (fused, 4 states): the whole post-order traversal of one (site, category) runs in
-// one thread; conditional likelihoods never leave the SM.  The tree is compiled on the
-// host into a short accumulator/stack program (heavier subtree first, so the stack depth
-// is <= log2(ntaxa)); every thread executes the same instruction stream.
-// HBM traffic: ntaxa bytes in, 8*C bytes out per site.  blockIdx.y = category.
-// --------------------------------------------------------------------------
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-fused4(const FusedOp* __restrict__ prog, int nops, int stack_depth,
-       const double* __restrict__ P, int nnodes,
-       const uint8_t* __restrict__ tips, int64_t tips_ld,
-       const double* __restrict__ pi, double thr, int shift_at_root,
-       double* __restrict__ site_cat, int64_t spad)
-{
-    extern __shared__ double sh[];
-    double* shP = sh;                                  // [nnodes][16] of this category
-    double* shS = sh + (size_t)nnodes * 16;            // [stack_depth][5][BLOCK]
-    FusedOp* shOps = reinterpret_cast<FusedOp*>(shS + (size_t)stack_depth * 5 * BLOCK);
-    const int c = blockIdx.y, tid = threadIdx.x;
-    {
-        const double* Pg = P + (size_t)c * nnodes * 16;
-        for (int idx = tid; idx < nnodes * 16; idx += BLOCK) shP[idx] = Pg[idx];
-        const int4* src = reinterpret_cast<const int4*>(prog);
-        int4* dst = reinterpret_cast<int4*>(shOps);
-        for (int idx = tid; idx < nops * 2; idx += BLOCK) dst[idx] = src[idx];
-    }
-    __syncthreads();
-    const int64_t s = (int64_t)blockIdx.x * BLOCK + tid;   // spad is a multiple of BLOCK
-    double v[4] = {1.0, 1.0, 1.0, 1.0};
-    double carry = 0.0;
-    int sp = 0;
-    for (int ip = 0; ip < nops; ip++) {
-        const FusedOp op = shOps[ip];
-        switch (op.code) {
-        case FOP_TIP_TIP: {
-            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
-            const int sb = tips[(int64_t)op.rowB * tips_ld + s];
-            const double* pa = shP + op.pA * 16 + sa;
-            const double* pb = shP + op.pB * 16 + sb;
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = pa[i * 4] * pb[i * 4];
-            carry = 0.0 + 0.0;
-            shift4(v, carry, thr);
-        } break;
-        case FOP_TIP: {
-            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
-            const double* pa = shP + op.pA * 16 + sa;
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = pa[i * 4];
-            carry = 0.0;
-        } break;
-        case FOP_APPLY: {
-            double y[4];
-            matvec4(shP + op.pA * 16, v, y);
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = y[i];
-        } break;
-        case FOP_MUL_TIP: {
-            const int sa = tips[(int64_t)op.rowA * tips_ld + s];
-            const double* pa = shP + op.pA * 16 + sa;
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = v[i] * pa[i * 4];
-            carry = carry + 0.0;
-            shift4(v, carry, thr);
-        } break;
-        case FOP_APPLY_MUL_TIP: {
-            const int sb = tips[(int64_t)op.rowB * tips_ld + s];
-            double y[4];
-            matvec4(shP + op.pA * 16, v, y);
-            const double* pb = shP + op.pB * 16 + sb;
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = y[i] * pb[i * 4];
-            carry = carry + 0.0;
-            shift4(v, carry, thr);
-        } break;
-        case FOP_PUSH: {
-            double* st = shS + (size_t)sp * 5 * BLOCK + tid;
-#pragma unroll
-            for (int i = 0; i < 4; i++) st[i * BLOCK] = v[i];
-            st[4 * BLOCK] = carry;
-            sp++;
-        } break;
-        case FOP_POP_MUL: {
-            sp--;
-            const double* st = shS + (size_t)sp * 5 * BLOCK + tid;
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = st[i * BLOCK] * v[i];
-            carry = st[4 * BLOCK] + carry;
-            shift4(v, carry, thr);
-        } break;
-        case FOP_ROOT: {
-            site_cat[(int64_t)c * spad + s] = root4(v, carry, pi, thr, shift_at_root);
-        } break;
-        default: break;
         }
     }
 }

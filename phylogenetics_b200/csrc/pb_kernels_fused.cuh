@@ -1,0 +1,249 @@
+// K2, fused site-resident form (4 states): the whole post-order traversal of one
+// (site, category) runs in one thread; conditional likelihoods never leave the SM.
+//
+// Restates Phylo_ctmc.pruning (lib/phylo_ctmc.ml:83-98) with SV.mul / SV.shift
+// (:33-40, :76-78).  The tree is compiled on the host (pb_api.cu) into a short
+// accumulator/stack program that every thread executes in lock step:
+//   * binary nodes evaluate their deeper subtree first (x*y and c1+c2 commute, so the
+//     result is bit-identical) which bounds the stack by log2(ntaxa);
+//   * nodes of arity >= 3 keep the reference's left-fold order.
+// Tip states are re-packed once per (alignment, tree) into 2-bit codes IN PROGRAM ORDER,
+// 32 tips per 64-bit word, word-major / site-contiguous: a thread streams its site's tips
+// with one coalesced 8-byte load per 32 tips, prefetched two words ahead.
+//
+// Rescaling: the rule (min v > threshold ? keep : v := (1/max v) v) and therefore every
+// vector are the reference's; the log-scale accumulator sums log(max v) over the rescaling
+// events of the whole traversal.  With EXACT_LOG it adds log(mx) at every event like the
+// reference's carry; otherwise it accumulates the product of the mx as (mantissa, binary
+// exponent) and takes one log at the root: the same real number, rounded differently
+// (<= ~1e-15 relative on the log-likelihood, inside the 1e-9 per-site tolerance).
+//
+// HBM traffic per site: ntaxa/4 bytes in, 8*C bytes out.  Bound: the FP64 pipe.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pb_kernels.cuh"
+
+namespace pbk {
+
+struct FusedOp2 {          // 8 bytes, read uniformly from shared memory
+    uint8_t code;          // FusedOpCode, or FOP_LOADW
+    uint8_t shA, shB;      // bit offset of tip A / B in the current packed word
+    uint8_t pad;
+    uint16_t pA, pB;       // node ids = indices of the P matrices
+};
+constexpr int FOP_LOADW = 8;   // advance the packed-tip window by one 64-bit word
+
+// Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
+// 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
+// Also flags any state >= 4.
+__global__ void __launch_bounds__(256)
+pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__ order, int ntips,
+           int nwords, uint64_t* __restrict__ packed, int64_t spad, int* __restrict__ bad_flag)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= spad) return;
+    int bad = 0;
+    for (int w = 0; w < nwords; w++) {
+        uint64_t word = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) {
+            const int k = w * 32 + j;
+            if (k < ntips) {
+                const unsigned st = tips[(int64_t)order[k] * ld + s];
+                bad |= (st > 3u);
+                word |= (uint64_t)(st & 3u) << (2 * j);
+            }
+        }
+        packed[(int64_t)w * spad + s] = word;
+    }
+    if (bad) atomicOr(bad_flag, 1);
+}
+
+// Flags tip states >= nstates (the level kernels index P with them).
+__global__ void __launch_bounds__(256)
+validate_tips(const uint8_t* __restrict__ tips, int64_t total, int nstates, int* __restrict__ bad_flag)
+{
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= (tips[i] >= nstates);
+    if (bad) atomicOr(bad_flag, 1);
+}
+
+template <bool EXACT_LOG>
+struct Scale {             // log-scale accumulator of one (site, category)
+    double m;              // EXACT_LOG: running sum of logs; else mantissa product in [2^-400, 1]
+    int e;
+    __device__ __forceinline__ void init() { m = EXACT_LOG ? 0.0 : 1.0; e = 0; }
+    __device__ __forceinline__ void add(double mx)
+    {
+        if (EXACT_LOG) {
+            m += log(mx);
+        } else {
+            m *= mx;
+            if (__double2hiint(m) < 0x26F00000) {      // m < 2^-400 (also catches 0 / negatives)
+                if (m > 0.0) { m *= 0x1p+400; e -= 400; }
+            }
+        }
+    }
+    __device__ __forceinline__ double value() const
+    {
+        return EXACT_LOG ? m : (log(m) + (double)e * 0.693147180559945309417232121458);
+    }
+};
+
+template <bool EXACT_LOG>
+__device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, double thr)
+{
+    const double mn = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
+    if (!(mn > thr)) {
+        const double mx = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+        const double inv = 1.0 / mx;
+        v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
+        sc.add(mx);
+    }
+}
+
+// Persistent kernel: grid = (blocks_x, ncat); each block stages the P matrices of its category
+// once and then loops over tiles of BLOCK*SPT sites.
+template <int BLOCK, int SPT, bool EXACT_LOG>
+__global__ void __launch_bounds__(BLOCK)
+fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
+       const double* __restrict__ P, int nnodes,
+       const uint64_t* __restrict__ packed, int64_t spad, int64_t ntiles,
+       const double* __restrict__ pi, double thr, int shift_at_root,
+       double* __restrict__ site_cat)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                                       // [nnodes][16] of this category
+    double* shS = sh + (size_t)nnodes * 16;                 // [stack_depth][4][BLOCK*SPT]
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shS + (size_t)stack_depth * 4 * BLOCK * SPT);
+    const int c = blockIdx.y, tid = threadIdx.x;
+    {
+        const double* Pg = P + (size_t)c * nnodes * 16;
+        for (int idx = tid; idx < nnodes * 16; idx += BLOCK) shP[idx] = Pg[idx];
+        const uint2* src = reinterpret_cast<const uint2*>(prog);
+        uint2* dst = reinterpret_cast<uint2*>(shOps);
+        for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
+    }
+    __syncthreads();
+    double pir[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) pir[i] = pi[i];
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t s0 = tile * (BLOCK * SPT) + tid;       // site of slot q: s0 + q*BLOCK
+        double v[SPT][4];
+        Scale<EXACT_LOG> sc[SPT];
+        uint64_t cur[SPT], nxt[SPT];
+        int word = 2;
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            sc[q].init();
+            cur[q] = packed[s0 + q * BLOCK];
+            nxt[q] = packed[spad + s0 + q * BLOCK];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[q][i] = 1.0;
+        }
+        int sp = 0;
+        for (int ip = 0; ip < nops; ip++) {
+            const FusedOp2 op = shOps[ip];
+            const double* PA = shP + (int)op.pA * 16;
+            const double* PB = shP + (int)op.pB * 16;
+            switch (op.code) {
+            case FOP_LOADW:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    cur[q] = nxt[q];
+                    nxt[q] = packed[(int64_t)word * spad + s0 + q * BLOCK];   // array is padded by 2 words
+                }
+                word++;
+                break;
+            case FOP_TIP_TIP:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sa = (int)(cur[q] >> op.shA) & 3, sb = (int)(cur[q] >> op.shB) & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa] * PB[i * 4 + sb];
+                    shift4s(v[q], sc[q], thr);
+                }
+                break;
+            case FOP_TIP:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sa = (int)(cur[q] >> op.shA) & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa];
+                }
+                break;
+            case FOP_APPLY: {
+                double pm[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4];
+                    matvec4(pm, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i];
+                }
+            } break;
+            case FOP_MUL_TIP:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sa = (int)(cur[q] >> op.shA) & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * PA[i * 4 + sa];
+                    shift4s(v[q], sc[q], thr);
+                }
+                break;
+            case FOP_APPLY_MUL_TIP: {
+                double pm[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sb = (int)(cur[q] >> op.shB) & 3;
+                    double y[4];
+                    matvec4(pm, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * PB[i * 4 + sb];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_PUSH: {
+                double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
+#pragma unroll
+                for (int q = 0; q < SPT; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                sp++;
+            } break;
+            case FOP_POP_MUL: {
+                sp--;
+                const double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = st[(i * SPT + q) * BLOCK] * v[q][i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_ROOT:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
+                    if (shift_at_root) shift4s(v[q], sc[q], thr);
+                    const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
+                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                }
+                break;
+            default: break;
+            }
+        }
+    }
+}
+
+}  // namespace pbk

@@ -59,7 +59,11 @@ class LikelihoodContext:
 
     # -- configuration
     def set_stream(self, cuda_stream_ptr):
-        self._ck(lib.pb_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_ptr or 0)))
+        """Enqueue on this cudaStream_t handle (0 = the CUDA default stream)."""
+        self._ck(lib.pb_set_stream(self._ctx, ctypes.c_void_p(int(cuda_stream_ptr))))
+
+    def use_private_stream(self):
+        self._ck(lib.pb_use_private_stream(self._ctx))
 
     def set_mode(self, mode):
         self._ck(lib.pb_set_mode(self._ctx, mode))
@@ -166,6 +170,27 @@ class LikelihoodContext:
         Pc = np.empty((self.ncat, self.nnodes, self.nstates, self.nstates))
         self._ck(lib.pb_get_pmatrices(self._ctx, Pc.ctypes.data))
         return np.ascontiguousarray(np.swapaxes(Pc, 2, 3))
+
+    def set_option(self, name, value):
+        self._ck(lib.pb_set_option(self._ctx, name.encode(), float(value)))
+
+    def set_timing(self, on=True):
+        self._ck(lib.pb_set_timing(self._ctx, int(bool(on))))
+
+    def get_timing(self):
+        """(pmat_ms, pruning_ms, root_ms) of the last evaluation, from CUDA events on the stream."""
+        ms = np.empty(3)
+        self._ck(lib.pb_get_timing(self._ctx, ms.ctypes.data))
+        return tuple(float(x) for x in ms)
+
+    def total_as_cuda_array(self):
+        """The device-resident total (1 double) as an object torch.as_tensor can wrap without a
+        copy (so a collective can reduce it in place)."""
+        ptr, _ = self.result_device_ptrs()
+
+        class _Total:
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return _Total()
 
     @property
     def kernel_launches(self):

@@ -183,3 +183,30 @@ def test_errors_are_reported_not_thrown():
             ctx.set_mode(7)
     with pytest.raises(_lib.PhyloB200InvalidArgument):
         LikelihoodContext(1, 10, 3)
+
+
+@pytest.mark.parametrize("block,spt,exact", [(128, 1, 0), (256, 1, 1), (512, 1, 0), (128, 2, 1), (256, 2, 0)])
+def test_fused_variants(block, spt, exact):
+    """Every compiled shape of the fused kernel, with the reference-style log carry and the
+    mantissa/exponent accumulator, on a tree deep enough to use the stack and >32 tips
+    (several packed words)."""
+    case = cases.make_case("fusedv", "gtr", 97, 3001, ncat=2, seed=3)
+    P = case.host_P()
+    with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("fused_block", block)
+        ctx.set_option("fused_spt", spt)
+        ctx.set_option("fused_exact_log", exact)
+        assert ctx.path_name == "fused4"
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P))
+
+
+def test_out_of_range_tip_state_is_an_error():
+    case = cases.make_case("bad", "jc69", 8, 100)
+    tips = case.tips.copy()
+    tips[3, 57] = 9
+    for level in (False, True):
+        with run_ctx(case, "eigen", level=level) as ctx:
+            ctx.set_tips(tips)
+            with pytest.raises(_lib.PhyloB200InvalidArgument):
+                ctx.loglik()
