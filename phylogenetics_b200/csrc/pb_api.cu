@@ -89,6 +89,7 @@ struct pb_ctx {
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
+    bool force_dense = false;           // option "dense_scalar": use the DFMA level kernel instead of DMMA
 
     // inputs
     DevBuf<uint8_t> d_tips;
@@ -155,7 +156,10 @@ int path_of(const pb_ctx* c)
         }
         return PATH_LEVEL4;
     }
-    if (!c->have_masks && pbk::dmma_supported(c->n)) return PATH_LEVEL_DMMA;
+    if (!c->have_masks && pbk::dmma_supported(c->n) && !c->force_dense) {
+        const int mp = (c->n + 15) / 16 * 16, ld = (c->n + 7) / 8 * 8 + 4;
+        if (((size_t)std::max(c->max_arity, 1) * mp * ld + mp) * sizeof(double) <= c->smem_optin) return PATH_LEVEL_DMMA;
+    }
     return PATH_LEVEL_DENSE;
 }
 
@@ -489,10 +493,10 @@ int run_pruning(pb_ctx* c)
                                                         c->d_site_cat.p, store_root);
             c->launches++;
         } else if (path == PATH_LEVEL_DMMA) {
-            int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
-                                            c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
-                                            c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root,
-                                            c->stream);
+            int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->max_arity,
+                                            c->d_P.p, c->nnodes, c->ncat, c->d_tips.p, c->spad, c->d_pool.p,
+                                            c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,
+                                            c->d_site_cat.p, store_root, c->sm_count, c->smem_optin, c->stream);
             if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma launch configuration failed");
             c->launches++;
         } else {
@@ -966,6 +970,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_spt = iv;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
+    } else if (k == "dense_scalar") {
+        c->force_dense = iv != 0;
     } else {
         return fail(c, PB_ERR_INVALID_ARG, "unknown option: " + k);
     }

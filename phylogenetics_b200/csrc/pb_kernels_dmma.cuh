@@ -1,15 +1,233 @@
-// FP64 tensor-core (mma.sync DMMA) level kernel for 20- and 61-state models.
+// K2, level-scheduled, dense alphabets (20 amino acids, 61 sense codons) on the FP64 tensor
+// cores: parent[i][site] = sum_j P[i][j] child[j][site] is a GEMM with M = parent states,
+// K = child states, N = sites, issued as mma.sync.aligned.m16n8k8 .f64 tiles (SASS: DMMA.16x8x8;
+// tcgen05.mma has no FP64 kind).  Measured on B200: m16n8k8 sustains 74 TFLOP/s, twice m8n8k4
+// and twice the DFMA pipe (profiles/fp64_peak_r01.json).
+//
+// Restates the node step of Phylo_ctmc.pruning (lib/phylo_ctmc.ml:91-95): one mat-vec per
+// inner child (a column look-up for a leaf child), children folded left to right with SV.mul,
+// i.e. element-wise product followed by SV.shift (:33-40, :76-78).
+//
+// One warp owns 8 adjacent sites (the N of the MMA) at a time:
+//   A fragments  <- the child's P, zero-padded to MP x KP, staged in shared memory
+//                   (row stride KP+4 doubles: conflict-free 8-byte fragment loads)
+//   B fragments  <- the child's CLV planes straight from HBM: 8 sites x 8 bytes = 64-byte
+//                   segments per state plane (two full sectors)
+//   C fragments  -> the node's CLV, rescaled in registers; min/max over states by
+//                   warp shuffles across the 8 row groups; stored as 16-byte pairs of sites.
 #pragma once
 #include "pb_kernels.cuh"
 
 namespace pbk {
 
-inline bool dmma_supported(int) { return false; }   // built in a later milestone
-
-inline int launch_level_dmma(int, const LevelNode*, const LevelChild*, int, int, const double*, int, int,
-                             const uint8_t*, int64_t, double*, int64_t, int64_t, const double*, double, int,
-                             double*, int, cudaStream_t)
+__device__ __forceinline__ void dmma_16x8x8(double (&c)[4], double a0, double a1, double a2, double a3,
+                                            double b0, double b1)
 {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+template <int N>
+struct DmmaShape {
+    static constexpr int MP = (N + 15) / 16 * 16;   // padded parent states
+    static constexpr int KP = (N + 7) / 8 * 8;      // padded child states
+    static constexpr int LD = KP + 4;               // smem row stride (doubles)
+    static constexpr int MT = MP / 16;
+    static constexpr int KS = KP / 8;
+};
+
+// SV.shift on a C-fragment tile: column j (j = 0, 1) of the thread's two sites; rows
+// mt*16 + g (+8).  All 8 row groups of a column take the same decision.
+template <int N>
+__device__ __forceinline__ void shift_frag(double (&out)[DmmaShape<N>::MT][4], double (&car)[2], int g, double thr)
+{
+    constexpr int MT = DmmaShape<N>::MT;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            if (mt * 16 + g < N) { mn = fmin(mn, out[mt][j]); mx = fmax(mx, out[mt][j]); }
+            if (mt * 16 + g + 8 < N) { mn = fmin(mn, out[mt][2 + j]); mx = fmax(mx, out[mt][2 + j]); }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (!(mn > thr)) {
+            const double inv = 1.0 / mx;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) { out[mt][j] = inv * out[mt][j]; out[mt][2 + j] = inv * out[mt][2 + j]; }
+            car[j] += log(mx);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children, int node_base,
+           const double* __restrict__ P, int nnodes, int ncat,
+           const uint8_t* __restrict__ tips, int64_t tips_ld,
+           double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+           const double* __restrict__ pi, double thr, int shift_at_root,
+           double* __restrict__ site_cat, int store_root, int tiles_per_block)
+{
+    using S = DmmaShape<N>;
+    constexpr int MP = S::MP, LD = S::LD, MT = S::MT, KS = S::KS;
+    extern __shared__ double sh[];           // [nchild][MP*LD] then pi[MP]
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    double* shPi = sh + (size_t)nd.nchild * MP * LD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int64_t ntiles = spad / 8;
+    const int64_t tile_end = min((int64_t)(blockIdx.x + 1) * tiles_per_block, ntiles);
+
+    for (int c = 0; c < ncat; c++) {
+        __syncthreads();
+        for (int idx = tid; idx < nd.nchild * MP * LD; idx += 256) {
+            const int k = idx / (MP * LD), r = idx - k * (MP * LD);
+            const int i = r / LD, j = r - i * LD;
+            sh[idx] = (i < N && j < N) ? P[((size_t)c * nnodes + ch[k].pnode) * N * N + i * N + j] : 0.0;
+        }
+        if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+        __syncthreads();
+
+        for (int64_t tile = (int64_t)blockIdx.x * tiles_per_block + warp; tile < tile_end; tile += 8) {
+            const int64_t s0 = tile * 8;
+            double out[MT][4];
+            double car[2] = {0.0, 0.0};
+            for (int k = 0; k < nd.nchild; k++) {
+                const LevelChild cd = ch[k];
+                const double* Pm = sh + (size_t)k * MP * LD;
+                double cf[MT][4];
+                double tc[2] = {0.0, 0.0};
+                if (cd.kind == 0) {
+                    const uchar2 st = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0 + tig * 2);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double* r0 = Pm + (mt * 16 + g) * LD;
+                        const double* r1 = r0 + 8 * LD;
+                        cf[mt][0] = r0[st.x]; cf[mt][1] = r0[st.y];
+                        cf[mt][2] = r1[st.x]; cf[mt][3] = r1[st.y];
+                    }
+                } else {
+                    const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (N + 1) * spad + s0;
+                    double b[KS][2];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) {
+                        const int k0 = ks * 8 + tig, k1 = k0 + 4;
+                        b[ks][0] = (k0 < N) ? src[(int64_t)k0 * spad + g] : 0.0;
+                        b[ks][1] = (k1 < N) ? src[(int64_t)k1 * spad + g] : 0.0;
+                    }
+                    const double2 q = *reinterpret_cast<const double2*>(src + (int64_t)N * spad + tig * 2);
+                    tc[0] = q.x; tc[1] = q.y;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
+                        const double* r0 = Pm + (mt * 16 + g) * LD + tig;
+                        const double* r1 = r0 + 8 * LD;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ks++)
+                            dmma_16x8x8(cf[mt], r0[ks * 8], r1[ks * 8], r0[ks * 8 + 4], r1[ks * 8 + 4], b[ks][0], b[ks][1]);
+                    }
+                }
+                if (k == 0) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) out[mt][e] = cf[mt][e];
+                    car[0] = tc[0]; car[1] = tc[1];
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) out[mt][e] = out[mt][e] * cf[mt][e];
+                    car[0] = car[0] + tc[0]; car[1] = car[1] + tc[1];
+                    shift_frag<N>(out, car, g, thr);
+                }
+            }
+            if (!nd.is_root || store_root) {
+                double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * (N + 1) * spad + s0 + tig * 2;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const int r0 = mt * 16 + g, r1 = r0 + 8;
+                    if (r0 < N) *reinterpret_cast<double2*>(dst + (int64_t)r0 * spad) = make_double2(out[mt][0], out[mt][1]);
+                    if (r1 < N) *reinterpret_cast<double2*>(dst + (int64_t)r1 * spad) = make_double2(out[mt][2], out[mt][3]);
+                }
+                if (g == 0) *reinterpret_cast<double2*>(dst + (int64_t)N * spad) = make_double2(car[0], car[1]);
+            }
+            if (nd.is_root) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double p0 = shPi[mt * 16 + g], p1 = shPi[mt * 16 + g + 8];
+                    out[mt][0] *= p0; out[mt][1] *= p0; out[mt][2] *= p1; out[mt][3] *= p1;
+                }
+                if (shift_at_root) shift_frag<N>(out, car, g, thr);
+                double sum[2] = {0.0, 0.0};
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {      // padded rows hold exact zeros
+                    sum[0] += out[mt][0] + out[mt][2];
+                    sum[1] += out[mt][1] + out[mt][3];
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+                    sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+                }
+                if (g == 0)
+                    *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                        make_double2(log(sum[0]) + car[0], log(sum[1]) + car[1]);
+            }
+        }
+    }
+}
+
+inline bool dmma_supported(int n) { return n == 20 || n == 61; }
+
+template <int N>
+int launch_level_dmma_n(const LevelNode* nodes, const LevelChild* children, int first, int count, int max_arity,
+                        const double* P, int nnodes, int ncat, const uint8_t* tips, int64_t tips_ld, double* pool,
+                        int64_t slot_stride, int64_t spad, const double* pi, double thr, int shift_at_root,
+                        double* site_cat, int store_root, int sm_count, size_t smem_optin, cudaStream_t stream)
+{
+    using S = DmmaShape<N>;
+    const size_t smem = ((size_t)max_arity * S::MP * S::LD + S::MP) * sizeof(double);
+    if (smem > smem_optin) return -2;
+    auto kern = level_dmma<N>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) return -1;
+    const int64_t ntiles = spad / 8;
+    int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count * occ / count);
+    int64_t tpb = (ntiles + want_blocks - 1) / want_blocks;
+    tpb = std::max<int64_t>(8, (tpb + 7) / 8 * 8);
+    const int64_t gx = (ntiles + tpb - 1) / tpb;
+    kern<<<dim3((unsigned)gx, count), 256, smem, stream>>>(nodes, children, first, P, nnodes, ncat, tips, tips_ld, pool,
+                                                           slot_stride, spad, pi, thr, shift_at_root, site_cat,
+                                                           store_root, (int)tpb);
+    return 0;
+}
+
+// Returns 0 on success, -2 when the node arity needs more shared memory than the SM has
+// (the caller falls back to level_dense), -1 on a launch-configuration error.
+inline int launch_level_dmma(int n, const LevelNode* nodes, const LevelChild* children, int first, int count,
+                             int max_arity, const double* P, int nnodes, int ncat, const uint8_t* tips,
+                             int64_t tips_ld, double* pool, int64_t slot_stride, int64_t spad, const double* pi,
+                             double thr, int shift_at_root, double* site_cat, int store_root, int sm_count,
+                             size_t smem_optin, cudaStream_t stream)
+{
+    if (n == 20)
+        return launch_level_dmma_n<20>(nodes, children, first, count, max_arity, P, nnodes, ncat, tips, tips_ld, pool,
+                                       slot_stride, spad, pi, thr, shift_at_root, site_cat, store_root, sm_count,
+                                       smem_optin, stream);
+    if (n == 61)
+        return launch_level_dmma_n<61>(nodes, children, first, count, max_arity, P, nnodes, ncat, tips, tips_ld, pool,
+                                       slot_stride, spad, pi, thr, shift_at_root, site_cat, store_root, sm_count,
+                                       smem_optin, stream);
     return -1;
 }
 
