@@ -1,0 +1,86 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares,
+and refuses to compute without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from phylogenetics_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "phylo_b200.h")) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = header_symbols()
+    assert len(declared) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (pb_[a-z0-9_]+)", out))
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTS) == declared       # the ctypes table covers the whole header
+
+
+def test_no_torch_or_python_dependency_in_the_abi_library():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out
+
+
+def test_sm100a_cubin_embedded():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the behaviour on a box without a GPU")
+def test_fails_loudly_without_a_gpu():
+    from phylogenetics_b200.engine import LikelihoodContext, transition_matrices_eigen
+    import numpy as np
+    with pytest.raises(_lib.PhyloB200Error) as e:
+        LikelihoodContext(4, 100, 8)
+    assert e.value.code == _lib.PB_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.PhyloB200Error):
+        transition_matrices_eigen(np.eye(4), np.zeros(4), np.eye(4), [0.1])
+
+
+def test_invalid_arguments_are_rejected_before_touching_the_device():
+    from phylogenetics_b200.engine import LikelihoodContext
+    for bad in [dict(nstates=1, nsites=10, ntaxa=3), dict(nstates=65, nsites=10, ntaxa=3),
+                dict(nstates=4, nsites=0, ntaxa=3), dict(nstates=4, nsites=10, ntaxa=0),
+                dict(nstates=4, nsites=10, ntaxa=3, ncat=0)]:
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            LikelihoodContext(**bad)
+
+
+def test_host_eigensystem_helper_reconstructs_q():
+    """pb_host_reversible_eigensystem: Q = U diag(lambda) U^-1 for GTR, WAG-sized and codon-sized Q."""
+    import numpy as np
+    from phylogenetics_b200.engine import host_reversible_eigensystem
+    from oracle import models_ref as M
+    rng = np.random.default_rng(2)
+    for n in (4, 20, 61):
+        pi = rng.dirichlet(np.full(n, 5.0))
+        ex = M.make_symetric(n, lambda i, j: rng.gamma(1.0, 1.0))
+        Q = M.gtr(pi, ex)
+        U, lam, Ui = host_reversible_eigensystem(Q, pi)
+        assert np.abs(U @ np.diag(lam) @ Ui - Q).max() < 1e-13
+        assert np.abs(U @ Ui - np.eye(n)).max() < 1e-13
+        assert abs(lam.max()) < 1e-13 and (lam <= 1e-13).all()
+    # a non-reversible matrix is refused
+    Qn = np.array([[-1., 1., 0., 0.], [0., -1., 1., 0.], [0., 0., -1., 1.], [1., 0., 0., -1.]])
+    with pytest.raises(_lib.PhyloB200Error):
+        host_reversible_eigensystem(Qn, np.full(4, 0.25))
