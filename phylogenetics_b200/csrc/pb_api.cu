@@ -78,6 +78,14 @@ struct pb_ctx {
     std::vector<int> lv_first;          // first LevelNode of every level (+ end)
     std::vector<int> slot_of_node;      // CLV slot of every internal node (level path)
     int nslots = 0, max_arity = 0;
+    // sequential (depth-first, deeper subtree first) schedule for the persistent dense kernel
+    std::vector<LevelNode> sq_nodes;
+    std::vector<LevelChild> sq_children;
+    int sq_nslots = 0;
+    DevBuf<LevelNode> d_sq_nodes;
+    DevBuf<LevelChild> d_sq_children;
+    int dmma_per_level = 0;             // option "dmma_per_level": one launch per tree level instead
+    int dmma_seq_tiles = 16;            // option "dmma_group_tiles": 8-site tiles per group (x8 sites)
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
@@ -89,6 +97,7 @@ struct pb_ctx {
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
+    int level4_minb = 4;                // option "level4_min_blocks": occupancy target of the level4 kernel
     bool force_dense = false;           // option "dense_scalar": use the DFMA level kernel instead of DMMA
 
     // inputs
@@ -152,7 +161,7 @@ int path_of(const pb_ctx* c)
     const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0 || c->have_masks;
     if (c->n == 4) {
         if (!level && c->have_tree) {
-            if (fused_smem_bytes(c) <= c->smem_optin && c->nnodes < 65536) return PATH_FUSED4;
+            if (fused_smem_bytes(c) <= c->smem_optin) return PATH_FUSED4;
         }
         return PATH_LEVEL4;
     }
@@ -267,6 +276,53 @@ int compile_tree(pb_ctx* c)
     c->lv_first.push_back((int)c->lv_nodes.size());
     c->nslots = nslots;
 
+    // ---- sequential schedule: depth-first post-order, the subtree needing more live CLVs first
+    {
+        c->sq_nodes.clear();
+        c->sq_children.clear();
+        std::vector<int> sq_slot(nn, -1), free_sq;
+        int nsq = 0;
+        std::vector<std::pair<int, int>> st;          // (node, next child rank)
+        std::vector<std::vector<int>> kids(nn);
+        for (int v = 0; v < nn; v++) {
+            for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; k++) kids[v].push_back(c->child_idx[k]);
+            std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) { return su[a] > su[b]; });
+        }
+        st.push_back({c->root, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            const int v = top.first;
+            if (top.second < (int)kids[v].size()) {
+                const int ch = kids[v][top.second++];
+                if (c->child_ptr[ch] != c->child_ptr[ch + 1]) st.push_back({ch, 0});
+                continue;
+            }
+            st.pop_back();
+            int slot;
+            if (keep) slot = c->slot_of_node[v];
+            else if (!free_sq.empty()) { slot = free_sq.back(); free_sq.pop_back(); }
+            else slot = nsq++;
+            // the output slot must differ from the children's: allocate before freeing theirs
+            sq_slot[v] = slot;
+            LevelNode nd;
+            nd.nchild = c->child_ptr[v + 1] - c->child_ptr[v];
+            nd.child_off = (int)c->sq_children.size();
+            nd.out_slot = slot;
+            nd.is_root = (v == c->root) ? 1 : 0;
+            for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; k++) {     // reference branch order
+                const int ch = c->child_idx[k];
+                LevelChild cd;
+                cd.pad = 0;
+                cd.pnode = ch;
+                if (c->child_ptr[ch] == c->child_ptr[ch + 1]) { cd.kind = 0; cd.src = c->tip_row[ch]; }
+                else { cd.kind = 1; cd.src = sq_slot[ch]; if (!keep) free_sq.push_back(sq_slot[ch]); }
+                c->sq_children.push_back(cd);
+            }
+            c->sq_nodes.push_back(nd);
+        }
+        c->sq_nslots = keep ? c->nslots : nsq;
+    }
+
     // ---- fused accumulator/stack program (4-state path)
     c->fprog.clear();
     c->tip_order.clear();
@@ -294,11 +350,9 @@ int compile_tree(pb_ctx* c)
                 } else if (ia && ib) {
                     if (su[b] > su[a]) std::swap(a, b);   // deeper first: exact, x*y and c1+c2 commute
                     seq.push_back({a, {}, false});
-                    seq.push_back({0, {pbk::FOP_APPLY, a, -1, 0, -1}, true});
-                    seq.push_back({0, {pbk::FOP_PUSH, 0, -1, 0, -1}, true});
+                    seq.push_back({0, {pbk::FOP_PUSH, 0, -1, 0, -1}, true});     // raw CLV of a; P[a] is applied at the pop
                     seq.push_back({b, {}, false});
-                    seq.push_back({0, {pbk::FOP_APPLY, b, -1, 0, -1}, true});
-                    seq.push_back({0, {pbk::FOP_POP_MUL, 0, -1, 0, -1}, true});
+                    seq.push_back({0, {pbk::FOP_ACC_POP, b, -1, a, -1}, true});
                 } else {
                     const int in = ia ? a : b, tp = ia ? b : a;
                     seq.push_back({in, {}, false});
@@ -323,8 +377,7 @@ int compile_tree(pb_ctx* c)
         // lower to FusedOp2: tips are consumed in program order, 32 per packed word
         auto mk = [](int code, int pA, int shA, int pB, int shB) {
             FusedOp2 o;
-            o.code = (uint8_t)code; o.shA = (uint8_t)shA; o.shB = (uint8_t)shB; o.pad = 0;
-            o.pA = (uint16_t)pA; o.pB = (uint16_t)pB;
+            o.code = code; o.offA = pA * 16; o.offB = pB * 16; o.sh = shA | (shB << 8);
             return o;
         };
         int consumed = 0;
@@ -351,7 +404,7 @@ int compile_tree(pb_ctx* c)
                 const int sb = next_tip(a.tipB);
                 c->fprog.push_back(mk(a.code, a.pA, 0, a.pB, sb));
             } else {
-                c->fprog.push_back(mk(a.code, a.pA, 0, 0, 0));
+                c->fprog.push_back(mk(a.code, a.pA, 0, a.pB, 0));
             }
         }
         c->fwords = (consumed + 31) / 32;
@@ -362,6 +415,10 @@ int compile_tree(pb_ctx* c)
     PB_CUDA(c, c->d_lv_nodes.ensure(c->lv_nodes.size()));
     PB_CUDA(c, c->d_lv_children.ensure(c->lv_children.size()));
     PB_CUDA(c, c->d_fprog.ensure(c->fprog.size()));
+    PB_CUDA(c, c->d_sq_nodes.ensure(c->sq_nodes.size()));
+    PB_CUDA(c, c->d_sq_children.ensure(c->sq_children.size()));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_sq_nodes.p, c->sq_nodes.data(), c->sq_nodes.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_sq_children.p, c->sq_children.data(), c->sq_children.size() * sizeof(LevelChild), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_nodes.p, c->lv_nodes.data(), c->lv_nodes.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_children.p, c->lv_children.data(), c->lv_children.size() * sizeof(LevelChild), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog.p, c->fprog.data(), c->fprog.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
@@ -479,24 +536,41 @@ int run_pruning(pb_ctx* c)
     }
     // level-scheduled paths
     c->slot_stride = (int64_t)c->ncat * (n + 1) * c->spad;
-    PB_CUDA(c, c->d_pool.ensure((size_t)c->nslots * c->slot_stride));
+    PB_CUDA(c, c->d_pool.ensure((size_t)std::max(c->nslots, c->sq_nslots) * c->slot_stride));
     const int store_root = (c->flags & PB_FLAG_KEEP_CLV) ? 1 : 0;
+    if (path == PATH_LEVEL_DMMA && !c->dmma_per_level) {
+        // one persistent launch: every block walks the whole tree for its groups of sites
+        int rc = pbk::launch_level_dmma(n, c->d_sq_nodes.p, c->d_sq_children.p, 0, (int)c->sq_nodes.size(),
+                                        c->max_arity, c->d_P.p, c->nnodes, c->ncat, c->d_tips.p, c->spad,
+                                        c->d_pool.p, c->slot_stride, c->spad, c->d_pi.p, c->threshold,
+                                        c->shift_at_root, c->d_site_cat.p, store_root, c->sm_count, c->smem_optin,
+                                        true, c->dmma_seq_tiles, c->stream);
+        if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma launch configuration failed");
+        c->launches++;
+        PB_CUDA(c, cudaGetLastError());
+        return PB_OK;
+    }
     for (size_t l = 0; l + 1 < c->lv_first.size(); l++) {
         const int first = c->lv_first[l], count = c->lv_first[l + 1] - first;
         if (path == PATH_LEVEL4) {
-            size_t smem = (size_t)c->max_arity * c->ncat * 16 * sizeof(double);
-            if (smem > 32768) smem = 0;
-            dim3 grid((unsigned)((c->spad / 2 + 255) / 256), count);
-            pbk::level4<<<grid, 256, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes,
-                                                        c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride,
-                                                        c->spad, c->d_pi.p, c->threshold, c->shift_at_root,
-                                                        c->d_site_cat.p, store_root);
+            dim3 grid((unsigned)((c->spad / 2 + 255) / 256), count, c->ncat);
+#define PB_LEVEL4_ARGS c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->d_tips.p, c->spad, \
+                       c->d_pool.p, c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,        \
+                       c->d_site_cat.p, store_root
+            switch (c->level4_minb) {
+            case 3: pbk::level4<3><<<grid, 256, 0, c->stream>>>(PB_LEVEL4_ARGS); break;
+            case 5: pbk::level4<5><<<grid, 256, 0, c->stream>>>(PB_LEVEL4_ARGS); break;
+            case 6: pbk::level4<6><<<grid, 256, 0, c->stream>>>(PB_LEVEL4_ARGS); break;
+            default: pbk::level4<4><<<grid, 256, 0, c->stream>>>(PB_LEVEL4_ARGS); break;
+            }
+#undef PB_LEVEL4_ARGS
             c->launches++;
         } else if (path == PATH_LEVEL_DMMA) {
             int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->max_arity,
                                             c->d_P.p, c->nnodes, c->ncat, c->d_tips.p, c->spad, c->d_pool.p,
                                             c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,
-                                            c->d_site_cat.p, store_root, c->sm_count, c->smem_optin, c->stream);
+                                            c->d_site_cat.p, store_root, c->sm_count, c->smem_optin, false, 0,
+                                            c->stream);
             if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma launch configuration failed");
             c->launches++;
         } else {
@@ -970,6 +1044,14 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_spt = iv;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
+    } else if (k == "level4_min_blocks") {
+        if (iv < 3 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "level4_min_blocks must be 3..6");
+        c->level4_minb = iv;
+    } else if (k == "dmma_per_level") {
+        c->dmma_per_level = iv != 0;
+    } else if (k == "dmma_group_tiles") {
+        if (iv < 8 || iv > 1024 || iv % 8) return fail(c, PB_ERR_INVALID_ARG, "dmma_group_tiles must be a multiple of 8 in 8..1024");
+        c->dmma_seq_tiles = iv;
     } else if (k == "dense_scalar") {
         c->force_dense = iv != 0;
     } else {

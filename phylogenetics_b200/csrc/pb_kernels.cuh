@@ -137,84 +137,118 @@ __device__ __forceinline__ double root4(double (&v)[4], double carry, const doub
 }
 
 // --------------------------------------------------------------------------
-// K2 (level-scheduled, 4 states): one launch per tree level, blockIdx.y = node of the
-// level, each thread owns TWO adjacent sites (16-byte vector loads/stores on every
-// plane) and loops over the rate categories.  Children are folded left to right
-// exactly as List.reduce_exn ~f:SV.mul does (lib/phylo_ctmc.ml:91-95).
-// Algorithmic traffic per site.node: 8*C*5*(k_inner + 1) + k_tip bytes.
+// K2 (level-scheduled, 4 states): one launch per tree level; blockIdx.y = node of the level,
+// blockIdx.z = rate category; each thread owns TWO adjacent sites (16-byte vector loads and
+// stores on every state plane).  Children are folded left to right exactly as
+// List.reduce_exn ~f:SV.mul does (lib/phylo_ctmc.ml:91-95).  Binary nodes (the common case)
+// issue the loads of both children before any arithmetic so that ~160 bytes per thread are
+// in flight.  Algorithmic traffic per site.node: 8*C*5*(k_inner + 1) + k_tip bytes.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+struct Term4 {           // one child's contribution for the thread's two sites
+    double a[4], b[4], ca, cb;
+};
+
+__device__ __forceinline__ void load_child4(const LevelChild cd, const double* __restrict__ Pm,
+                                            const uint8_t* __restrict__ tips, int64_t tips_ld,
+                                            const double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+                                            int c, int64_t s0, double2 (&raw)[5], uchar2& st)
+{
+    if (cd.kind == 0) {
+        st = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0);
+    } else {
+        const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * 5 * spad + s0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) raw[i] = __ldcs(reinterpret_cast<const double2*>(src + (int64_t)i * spad));
+    }
+}
+
+__device__ __forceinline__ void term_child4(const LevelChild cd, const double* __restrict__ Pm,
+                                            const double2 (&raw)[5], const uchar2 st, Term4& t)
+{
+    if (cd.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { t.a[i] = Pm[i * 4 + st.x]; t.b[i] = Pm[i * 4 + st.y]; }
+        t.ca = 0.0; t.cb = 0.0;
+    } else {
+        double xa[4], xb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { xa[i] = raw[i].x; xb[i] = raw[i].y; }
+        matvec4(Pm, xa, t.a);
+        matvec4(Pm, xb, t.b);
+        t.ca = raw[4].x; t.cb = raw[4].y;
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 level4(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children, int node_base,
-       const double* __restrict__ P, int nnodes, int ncat,
+       const double* __restrict__ P, int nnodes,
        const uint8_t* __restrict__ tips, int64_t tips_ld,
        double* __restrict__ pool, int64_t slot_stride, int64_t spad,
        const double* __restrict__ pi, double thr, int shift_at_root,
        double* __restrict__ site_cat, int store_root)
 {
-    extern __shared__ double shP[];   // [nchild][ncat][16] when it fits, else unused
+    __shared__ double shP[2 * 16];    // the two matrices of a binary node (other arities read P from L1)
     const LevelNode nd = nodes[node_base + blockIdx.y];
     const LevelChild* ch = children + nd.child_off;
-    const bool staged = (size_t)nd.nchild * ncat * 16 * sizeof(double) <= 32768;
-    if (staged) {
-        for (int idx = threadIdx.x; idx < nd.nchild * ncat * 16; idx += blockDim.x) {
-            const int k = idx / (ncat * 16), r = idx - k * ncat * 16;
-            const int c = r / 16, e = r - c * 16;
-            shP[idx] = P[((size_t)c * nnodes + ch[k].pnode) * 16 + e];
-        }
+    const int c = blockIdx.z;
+    const double* Pc = P + (size_t)c * nnodes * 16;
+    if (nd.nchild == 2) {
+        if (threadIdx.x < 32) shP[threadIdx.x] = Pc[(size_t)ch[threadIdx.x >> 4].pnode * 16 + (threadIdx.x & 15)];
         __syncthreads();
     }
     const int64_t s0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (s0 >= spad) return;
 
-    for (int c = 0; c < ncat; c++) {
-        double va[4], vb[4], ca = 0.0, cb = 0.0;
+    double va[4], vb[4], ca, cb;
+    if (nd.nchild == 2) {
+        const LevelChild c0 = ch[0], c1 = ch[1];
+        double2 r0[5], r1[5];
+        uchar2 st0 = make_uchar2(0, 0), st1 = make_uchar2(0, 0);
+        load_child4(c0, shP, tips, tips_ld, pool, slot_stride, spad, c, s0, r0, st0);
+        load_child4(c1, shP + 16, tips, tips_ld, pool, slot_stride, spad, c, s0, r1, st1);
+        Term4 t0, t1;
+        term_child4(c0, shP, r0, st0, t0);
+        term_child4(c1, shP + 16, r1, st1, t1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { va[i] = t0.a[i] * t1.a[i]; vb[i] = t0.b[i] * t1.b[i]; }
+        ca = t0.ca + t1.ca; cb = t0.cb + t1.cb;
+        shift4(va, ca, thr);
+        shift4(vb, cb, thr);
+    } else {
+        ca = 0.0; cb = 0.0;
         for (int k = 0; k < nd.nchild; k++) {
             const LevelChild cd = ch[k];
-            const double* Pm = staged ? (shP + ((size_t)k * ncat + c) * 16)
-                                      : (P + ((size_t)c * nnodes + cd.pnode) * 16);
-            double ta[4], tb[4], tca, tcb;
-            if (cd.kind == 0) {
-                const uchar2 st = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) { ta[i] = Pm[i * 4 + st.x]; tb[i] = Pm[i * 4 + st.y]; }
-                tca = 0.0; tcb = 0.0;
-            } else {
-                const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * 5 * spad + s0;
-                double xa[4], xb[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double2 q = *reinterpret_cast<const double2*>(src + (int64_t)i * spad);
-                    xa[i] = q.x; xb[i] = q.y;
-                }
-                const double2 qc = *reinterpret_cast<const double2*>(src + 4 * spad);
-                tca = qc.x; tcb = qc.y;
-                matvec4(Pm, xa, ta);
-                matvec4(Pm, xb, tb);
-            }
+            const double* Pm = Pc + (size_t)cd.pnode * 16;
+            double2 r[5];
+            uchar2 st = make_uchar2(0, 0);
+            load_child4(cd, Pm, tips, tips_ld, pool, slot_stride, spad, c, s0, r, st);
+            Term4 t;
+            term_child4(cd, Pm, r, st, t);
             if (k == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) { va[i] = ta[i]; vb[i] = tb[i]; }
-                ca = tca; cb = tcb;
+                for (int i = 0; i < 4; i++) { va[i] = t.a[i]; vb[i] = t.b[i]; }
+                ca = t.ca; cb = t.cb;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) { va[i] = va[i] * ta[i]; vb[i] = vb[i] * tb[i]; }
-                ca = ca + tca; cb = cb + tcb;
+                for (int i = 0; i < 4; i++) { va[i] = va[i] * t.a[i]; vb[i] = vb[i] * t.b[i]; }
+                ca = ca + t.ca; cb = cb + t.cb;
                 shift4(va, ca, thr);
                 shift4(vb, cb, thr);
             }
         }
-        if (!nd.is_root || store_root) {
-            double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * 5 * spad + s0;
+    }
+    if (!nd.is_root || store_root) {
+        double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * 5 * spad + s0;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                *reinterpret_cast<double2*>(dst + (int64_t)i * spad) = make_double2(va[i], vb[i]);
-            *reinterpret_cast<double2*>(dst + 4 * spad) = make_double2(ca, cb);
-        }
-        if (nd.is_root) {
-            const double la = root4(va, ca, pi, thr, shift_at_root);
-            const double lb = root4(vb, cb, pi, thr, shift_at_root);
-            *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0) = make_double2(la, lb);
-        }
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<double2*>(dst + (int64_t)i * spad) = make_double2(va[i], vb[i]);
+        *reinterpret_cast<double2*>(dst + 4 * spad) = make_double2(ca, cb);
+    }
+    if (nd.is_root) {
+        const double la = root4(va, ca, pi, thr, shift_at_root);
+        const double lb = root4(vb, cb, pi, thr, shift_at_root);
+        *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0) = make_double2(la, lb);
     }
 }
 

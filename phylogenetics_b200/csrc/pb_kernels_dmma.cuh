@@ -73,18 +73,31 @@ level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ c
            const uint8_t* __restrict__ tips, int64_t tips_ld,
            double* __restrict__ pool, int64_t slot_stride, int64_t spad,
            const double* __restrict__ pi, double thr, int shift_at_root,
-           double* __restrict__ site_cat, int store_root, int tiles_per_block)
+           double* __restrict__ site_cat, int store_root, int tiles_per_block, int seq_count)
 {
     using S = DmmaShape<N>;
     constexpr int MP = S::MP, LD = S::LD, MT = S::MT, KS = S::KS;
-    extern __shared__ double sh[];           // [nchild][MP*LD] then pi[MP]
-    const LevelNode nd = nodes[node_base + blockIdx.y];
-    const LevelChild* ch = children + nd.child_off;
-    double* shPi = sh + (size_t)nd.nchild * MP * LD;
+    extern __shared__ double shraw[];        // pi[MP] then [nchild][MP*LD]
+    double* shPi = shraw;
+    double* sh = shraw + MP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tig = lane & 3;
     const int64_t ntiles = spad / 8;
-    const int64_t tile_end = min((int64_t)(blockIdx.x + 1) * tiles_per_block, ntiles);
+    // seq_count == 0: one node per launch row (blockIdx.y), blocks split the sites once.
+    // seq_count  > 0: persistent blocks; each takes groups of tiles_per_block site tiles and walks ALL
+    //                 seq_count nodes (post-order) for a group before moving on, so the group's
+    //                 conditional likelihoods are produced and consumed while still in L2.
+    const bool seq = seq_count > 0;
+    const int nloop = seq ? seq_count : 1;
+    const int64_t ngroups = seq ? (ntiles + tiles_per_block - 1) / tiles_per_block : 1;
+    if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+
+    for (int64_t grp = seq ? blockIdx.x : 0; grp < ngroups; grp += (seq ? gridDim.x : 1)) {
+    const int64_t tile_begin = (seq ? grp : (int64_t)blockIdx.x) * tiles_per_block;
+    const int64_t tile_end = min(tile_begin + tiles_per_block, ntiles);
+    for (int ni = 0; ni < nloop; ni++) {
+    const LevelNode nd = nodes[node_base + (seq ? ni : (int)blockIdx.y)];
+    const LevelChild* ch = children + nd.child_off;
 
     for (int c = 0; c < ncat; c++) {
         __syncthreads();
@@ -93,10 +106,9 @@ level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ c
             const int i = r / LD, j = r - i * LD;
             sh[idx] = (i < N && j < N) ? P[((size_t)c * nnodes + ch[k].pnode) * N * N + i * N + j] : 0.0;
         }
-        if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
         __syncthreads();
 
-        for (int64_t tile = (int64_t)blockIdx.x * tiles_per_block + warp; tile < tile_end; tile += 8) {
+        for (int64_t tile = tile_begin + warp; tile < tile_end; tile += 8) {
             const int64_t s0 = tile * 8;
             double out[MT][4];
             double car[2] = {0.0, 0.0};
@@ -184,6 +196,8 @@ level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ c
             }
         }
     }
+    }   // nodes
+    }   // groups
 }
 
 inline bool dmma_supported(int n) { return n == 20 || n == 61; }
@@ -192,7 +206,8 @@ template <int N>
 int launch_level_dmma_n(const LevelNode* nodes, const LevelChild* children, int first, int count, int max_arity,
                         const double* P, int nnodes, int ncat, const uint8_t* tips, int64_t tips_ld, double* pool,
                         int64_t slot_stride, int64_t spad, const double* pi, double thr, int shift_at_root,
-                        double* site_cat, int store_root, int sm_count, size_t smem_optin, cudaStream_t stream)
+                        double* site_cat, int store_root, int sm_count, size_t smem_optin, bool sequential,
+                        int seq_tiles, cudaStream_t stream)
 {
     using S = DmmaShape<N>;
     const size_t smem = ((size_t)max_arity * S::MP * S::LD + S::MP) * sizeof(double);
@@ -202,32 +217,42 @@ int launch_level_dmma_n(const LevelNode* nodes, const LevelChild* children, int 
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) return -1;
     const int64_t ntiles = spad / 8;
+    if (sequential) {
+        const int64_t tpb = seq_tiles;                       // tiles per group (8 warps x tiles each)
+        const int64_t ngroups = (ntiles + tpb - 1) / tpb;
+        const int64_t gx = std::min<int64_t>(ngroups, (int64_t)sm_count * occ);
+        kern<<<dim3((unsigned)gx, 1), 256, smem, stream>>>(nodes, children, first, P, nnodes, ncat, tips, tips_ld, pool,
+                                                            slot_stride, spad, pi, thr, shift_at_root, site_cat,
+                                                            store_root, (int)tpb, count);
+        return 0;
+    }
     int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count * occ / count);
     int64_t tpb = (ntiles + want_blocks - 1) / want_blocks;
     tpb = std::max<int64_t>(8, (tpb + 7) / 8 * 8);
     const int64_t gx = (ntiles + tpb - 1) / tpb;
     kern<<<dim3((unsigned)gx, count), 256, smem, stream>>>(nodes, children, first, P, nnodes, ncat, tips, tips_ld, pool,
                                                            slot_stride, spad, pi, thr, shift_at_root, site_cat,
-                                                           store_root, (int)tpb);
+                                                           store_root, (int)tpb, 0);
     return 0;
 }
 
 // Returns 0 on success, -2 when the node arity needs more shared memory than the SM has
 // (the caller falls back to level_dense), -1 on a launch-configuration error.
+// sequential: one persistent launch walks nodes [first, first+count) in order for each site group.
 inline int launch_level_dmma(int n, const LevelNode* nodes, const LevelChild* children, int first, int count,
                              int max_arity, const double* P, int nnodes, int ncat, const uint8_t* tips,
                              int64_t tips_ld, double* pool, int64_t slot_stride, int64_t spad, const double* pi,
                              double thr, int shift_at_root, double* site_cat, int store_root, int sm_count,
-                             size_t smem_optin, cudaStream_t stream)
+                             size_t smem_optin, bool sequential, int seq_tiles, cudaStream_t stream)
 {
     if (n == 20)
         return launch_level_dmma_n<20>(nodes, children, first, count, max_arity, P, nnodes, ncat, tips, tips_ld, pool,
                                        slot_stride, spad, pi, thr, shift_at_root, site_cat, store_root, sm_count,
-                                       smem_optin, stream);
+                                       smem_optin, sequential, seq_tiles, stream);
     if (n == 61)
         return launch_level_dmma_n<61>(nodes, children, first, count, max_arity, P, nnodes, ncat, tips, tips_ld, pool,
                                        slot_stride, spad, pi, thr, shift_at_root, site_cat, store_root, sm_count,
-                                       smem_optin, stream);
+                                       smem_optin, sequential, seq_tiles, stream);
     return -1;
 }
 

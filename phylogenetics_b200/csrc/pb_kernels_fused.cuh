@@ -27,13 +27,13 @@
 
 namespace pbk {
 
-struct FusedOp2 {          // 8 bytes, read uniformly from shared memory
-    uint8_t code;          // FusedOpCode, or FOP_LOADW
-    uint8_t shA, shB;      // bit offset of tip A / B in the current packed word
-    uint8_t pad;
-    uint16_t pA, pB;       // node ids = indices of the P matrices
+struct FusedOp2 {          // 16 bytes: one uniform 128-bit shared-memory load per instruction
+    int code;              // FusedOpCode, FOP_LOADW or FOP_ACC_POP
+    int offA, offB;        // offsets (in doubles) of P[pA], P[pB] in the staged matrices: node id * 16
+    int sh;                // shA | shB << 8: bit offsets of tip A / B in the current packed word
 };
-constexpr int FOP_LOADW = 8;   // advance the packed-tip window by one 64-bit word
+constexpr int FOP_LOADW = 8;     // advance the packed-tip window by one 64-bit word
+constexpr int FOP_ACC_POP = 9;   // ACC = shiftmul(P[pA].ACC, P[pB].pop())   (both children inner)
 
 // Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
 // 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
@@ -93,12 +93,20 @@ struct Scale {             // log-scale accumulator of one (site, category)
     }
 };
 
+// max of non-negative doubles through their bit patterns (monotone for x >= 0; a negative
+// rounding residue compares below every positive value, as it should).
+__device__ __forceinline__ double max_nonneg(double a, double b)
+{
+    return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+
 template <bool EXACT_LOG>
 __device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, double thr)
 {
-    const double mn = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
-    if (!(mn > thr)) {
-        const double mx = fmax(fmax(v[0], v[1]), fmax(v[2], v[3]));
+    // min v > thr  <=>  every component > thr (a NaN fails the test, like the reference's compare)
+    const bool keep = (v[0] > thr) & (v[1] > thr) & (v[2] > thr) & (v[3] > thr);
+    if (!keep) {
+        const double mx = max_nonneg(max_nonneg(v[0], v[1]), max_nonneg(v[2], v[3]));
         const double inv = 1.0 / mx;
         v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
         sc.add(mx);
@@ -123,8 +131,8 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     {
         const double* Pg = P + (size_t)c * nnodes * 16;
         for (int idx = tid; idx < nnodes * 16; idx += BLOCK) shP[idx] = Pg[idx];
-        const uint2* src = reinterpret_cast<const uint2*>(prog);
-        uint2* dst = reinterpret_cast<uint2*>(shOps);
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
         for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
     }
     __syncthreads();
@@ -148,10 +156,56 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         }
         int sp = 0;
         for (int ip = 0; ip < nops; ip++) {
-            const FusedOp2 op = shOps[ip];
-            const double* PA = shP + (int)op.pA * 16;
-            const double* PB = shP + (int)op.pB * 16;
-            switch (op.code) {
+            const int4 opw = reinterpret_cast<const int4*>(shOps)[ip];
+            const double* PA = shP + opw.y;
+            const double* PB = shP + opw.z;
+            const int shA = opw.w & 0xff, shB = opw.w >> 8;
+            switch (opw.x) {
+            case FOP_APPLY_MUL_TIP: {
+                double pm[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sb = (int)(cur[q] >> shB) & 3;
+                    double y[4];
+                    matvec4(pm, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * PB[i * 4 + sb];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_ACC_POP: {
+                sp--;
+                const double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
+                double pm[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+                double y[SPT][4];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) matvec4(pm, v[q], y[q]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) pm[i] = PB[i];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double x[4], z[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+                    matvec4(pm, x, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[q][i] * z[i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_TIP_TIP:
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    const int sa = (int)(cur[q] >> shA) & 3, sb = (int)(cur[q] >> shB) & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa] * PB[i * 4 + sb];
+                    shift4s(v[q], sc[q], thr);
+                }
+                break;
             case FOP_LOADW:
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
@@ -160,19 +214,10 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                 }
                 word++;
                 break;
-            case FOP_TIP_TIP:
-#pragma unroll
-                for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> op.shA) & 3, sb = (int)(cur[q] >> op.shB) & 3;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa] * PB[i * 4 + sb];
-                    shift4s(v[q], sc[q], thr);
-                }
-                break;
             case FOP_TIP:
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> op.shA) & 3;
+                    const int sa = (int)(cur[q] >> shA) & 3;
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa];
                 }
@@ -192,26 +237,12 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
             case FOP_MUL_TIP:
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> op.shA) & 3;
+                    const int sa = (int)(cur[q] >> shA) & 3;
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * PA[i * 4 + sa];
                     shift4s(v[q], sc[q], thr);
                 }
                 break;
-            case FOP_APPLY_MUL_TIP: {
-                double pm[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) pm[i] = PA[i];
-#pragma unroll
-                for (int q = 0; q < SPT; q++) {
-                    const int sb = (int)(cur[q] >> op.shB) & 3;
-                    double y[4];
-                    matvec4(pm, v[q], y);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * PB[i * 4 + sb];
-                    shift4s(v[q], sc[q], thr);
-                }
-            } break;
             case FOP_PUSH: {
                 double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
 #pragma unroll

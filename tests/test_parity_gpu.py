@@ -210,3 +210,38 @@ def test_out_of_range_tip_state_is_an_error():
             ctx.set_tips(tips)
             with pytest.raises(_lib.PhyloB200InvalidArgument):
                 ctx.loglik()
+
+
+@pytest.mark.parametrize("model,ntaxa,nsites", [("wag", 40, 2100), ("mg94", 24, 900)])
+@pytest.mark.parametrize("opts", [{}, {"dmma_per_level": 1}, {"dmma_group_tiles": 8}, {"dense_scalar": 1}])
+def test_dense_kernel_modes(model, ntaxa, nsites, opts):
+    """DMMA kernel in its persistent tree-walking mode (default), per-level launches, a different
+    group size, and the scalar DFMA kernel: all against the oracle, with and without CLVs kept."""
+    case = cases.make_case("dm" + model, model, ntaxa, nsites, seed=5)
+    P = case.host_P()
+    expect = oracle_per_site(case, P)
+    for keep in (False, True):
+        with run_ctx(case, "direct", keep=keep, P=P) as ctx:
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            assert ctx.path_name == ("level_dense" if "dense_scalar" in opts else "level_dmma")
+            total, per_site = ctx.loglik(per_site=True)
+            check(per_site, total, expect)
+            if keep:
+                f = case.flat
+                clv, car = C.conditional_likelihoods(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P[0], 5,
+                                                     tips=case.tips)
+                for v in range(f.nnodes):
+                    gv, gc = ctx.get_clv(v)
+                    np.testing.assert_allclose(gv[5], clv[v], rtol=1e-11, atol=1e-300)
+                    np.testing.assert_allclose(gc[5], car[v], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("minb", [3, 4, 5, 6])
+def test_level4_occupancy_variants(minb):
+    case = cases.make_case("lv4", "gtr", 50, 5000, ncat=3, seed=6)
+    P = case.host_P()
+    with run_ctx(case, "direct", level=True, P=P) as ctx:
+        ctx.set_option("level4_min_blocks", minb)
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P))

@@ -13,13 +13,15 @@ for name, model, ntaxa, nsites in [("c3", "wag", 64, 200_000), ("c4", "mg94", 32
     case = cases.make_case(name, model, ntaxa, nsites, seed=100)
     f = case.flat
     ref = None
-    for scalar in (0, 1):
+    for opts in ({}, {"dmma_group_tiles": 8}, {"dmma_group_tiles": 32}, {"dmma_group_tiles": 64}, {"dmma_per_level": 1},
+                 {"dense_scalar": 1}):
         with LikelihoodContext(case.n, nsites, f.nleaves) as ctx:
             ctx.set_tree(f, case.bl)
             ctx.set_rate_matrix(case.Q, case.pi)
             ctx.set_root_frequencies(case.pi)
             ctx.set_tips(case.tips)
-            ctx.set_option("dense_scalar", scalar)
+            for k, v in opts.items():
+                ctx.set_option(k, v)
             ctx.set_timing(True)
             ms = []
             for _ in range(5):
@@ -30,7 +32,7 @@ for name, model, ntaxa, nsites in [("c3", "wag", 64, 200_000), ("c4", "mg94", 32
             byts = (8 * (n + 1) * (2 * T - 4) + T + 8) * nsites
             flops = (2 * n * n * (T - 2) + n * (T - 1)) * nsites
             best = min(m[1] for m in ms[1:])
-            print(json.dumps({"config": name, "path": ctx.path_name, "pmat_ms": ms[-1][0], "pruning_ms": best,
+            print(json.dumps({"config": name, "path": ctx.path_name, "opts": opts, "pmat_ms": ms[-1][0], "pruning_ms": best,
                               "root_ms": ms[-1][2], "GBps": byts / best / 1e6, "TFLOPs": flops / best / 1e9,
                               "total": tot, "rel_vs_first": abs(tot - ref) / abs(ref),
                               "launches": ctx.kernel_launches}), flush=True)
