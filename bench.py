@@ -213,6 +213,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step():
         nonlocal total_t
+        ctx.set_branch_lengths(case.bl)      # new branch lengths every evaluation: P(t) is rebuilt (kernel K1)
         ctx.enqueue()
         if world > 1:
             if total_t is None:
@@ -278,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(e2e_steps):
+        ctx.set_branch_lengths(case.bl)
         ctx.set_tips_ptr(tips_pinned.data_ptr(), nsites)
         tot = ctx.loglik()
         if world > 1:

@@ -84,7 +84,7 @@ struct pb_ctx {
     int sq_nslots = 0;
     DevBuf<LevelNode> d_sq_nodes;
     DevBuf<LevelChild> d_sq_children;
-    int dmma_per_level = 0;             // option "dmma_per_level": one launch per tree level instead
+    int dmma_per_level = 1;             // option "dmma_per_level": one launch per tree level instead
     int dmma_seq_tiles = 16;            // option "dmma_group_tiles": 8-site tiles per group (x8 sites)
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
@@ -781,8 +781,8 @@ int pb_set_branch_lengths(pb_ctx* c, const double* bl)
     c->branch_len.assign(bl, bl + c->nnodes);
     c->branch_len[c->root] = 0.0;
     PB_CUDA(c, c->d_blen.ensure(c->nnodes));
+    // pageable source: the runtime stages it before returning, so no synchronisation is needed here
     PB_CUDA(c, cudaMemcpyAsync(c->d_blen.p, c->branch_len.data(), c->nnodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_blen = true;
     c->p_dirty = true;
     return PB_OK;

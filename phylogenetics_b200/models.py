@@ -339,7 +339,7 @@ class Site_evolution_model:
         nstates = 4
 
         @classmethod
-        def transition_probability_matrix(cls, param, device=0):
+        def transition_probability_matrix(cls, param=None, device=0):
             U, lam, Uinv = cls.rate_matrix_reduction(param)
             return lambda t: engine.transition_matrices_eigen(U, lam, Uinv, [t], device=device)[0]
 
@@ -348,12 +348,12 @@ class Site_evolution_model:
         nstates = 4
 
         @classmethod
-        def transition_probability_matrix(cls, param, device=0):
+        def transition_probability_matrix(cls, param=None, device=0):
             Q = cls.rate_matrix(param)
             return lambda t: engine.transition_matrices_expm(Q, [t], device=device)[0]
 
         @classmethod
-        def stationary_distribution(cls, param):
+        def stationary_distribution(cls, param=None):
             return Rate_matrix.stationary_distribution(cls.rate_matrix(param))
 
     class JC69(_Diag):
