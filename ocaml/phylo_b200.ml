@@ -1,0 +1,130 @@
+(* OCaml side of the drop-in: evaluates the reference's closures eagerly, flattens the tree and
+   calls the C stubs (phylo_b200_stubs.c).  Source-only here: see INTEGRATION.md. *)
+open Core
+open Phylogenetics
+
+type ctx
+type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.t
+type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
+type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
+
+type flat_tree = { root : int ; child_ptr : int32_vec ; child_idx : int32_vec ; tip_row : int32_vec }
+
+external create_ : int -> int -> int -> int -> int -> int -> ctx = "pb_stub_create_bytecode" "pb_stub_create"
+external set_mode : ctx -> int -> unit = "pb_stub_set_mode"
+external set_rescaling : ctx -> float -> bool -> unit = "pb_stub_set_rescaling"
+external set_tree_ : ctx -> int -> int32_vec -> int32_vec -> int32_vec -> float_vec -> unit
+  = "pb_stub_set_tree_bytecode" "pb_stub_set_tree"
+external set_branch_lengths : ctx -> float_vec -> unit = "pb_stub_set_branch_lengths"
+external set_tips : ctx -> tip_matrix -> unit = "pb_stub_set_tips"
+external set_root_frequencies : ctx -> Linear_algebra.vec -> unit = "pb_stub_set_root_frequencies"
+external set_categories_ : ctx -> float_vec -> float_vec -> unit = "pb_stub_set_categories"
+external set_eigensystem : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
+  = "pb_stub_set_eigensystem"
+external set_rate_matrix : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> unit = "pb_stub_set_rate_matrix"
+external set_rate_matrix_general : ctx -> Linear_algebra.mat -> unit = "pb_stub_set_rate_matrix_general"
+external set_pmatrices : ctx -> float_vec -> unit = "pb_stub_set_pmatrices"
+external loglik_ : ctx -> float_vec -> float = "pb_stub_loglik"
+
+let keep_clv_flag = 1
+let mode_phylo_ctmc = 0
+
+let create ?(device = 0) ?(ncat = 1) ?(keep_clv = false) ~nstates ~nsites ~ntaxa () =
+  create_ device nstates ncat nsites ntaxa (if keep_clv then keep_clv_flag else 0)
+
+let set_tree ctx t ~branch_lengths = set_tree_ ctx t.root t.child_ptr t.child_idx t.tip_row branch_lengths
+let set_categories ctx ~rates ~weights = set_categories_ ctx rates weights
+
+let empty_vec = Bigarray.(Array1.create float64 c_layout 0)
+let loglik ctx ?(per_site = empty_vec) () = loglik_ ctx per_site
+
+(* Pre-order numbering of a Tree.t (lib/tree.ml:3-13). *)
+let flatten (t : _ Tree.t) =
+  let nodes = Queue.create () in   (* (children ids in branch order, leaf payload option, branch payload option) *)
+  let rec visit t bdata =
+    let id = Queue.length nodes in
+    Queue.enqueue nodes (ref [], None, bdata) ;
+    (match t with
+     | Tree.Leaf l -> Queue.set nodes id (ref [], Some l, bdata)
+     | Node n ->
+       let kids = List1.map n.branches ~f:(fun (Tree.Branch b) -> visit b.tip (Some b.data)) |> List1.to_list in
+       let (r, _, _) = Queue.get nodes id in
+       r := kids) ;
+    id
+  in
+  let root = visit t None in
+  let n = Queue.length nodes in
+  let child_ptr = Bigarray.(Array1.create int32 c_layout (n + 1)) in
+  let child_idx = Bigarray.(Array1.create int32 c_layout (max 1 (n - 1))) in
+  let tip_row = Bigarray.(Array1.create int32 c_layout n) in
+  let leaves = Queue.create () and branches = Array.create ~len:n None in
+  let k = ref 0 in
+  child_ptr.{0} <- 0l ;
+  Queue.iteri nodes ~f:(fun v (kids, leaf, bdata) ->
+      branches.(v) <- bdata ;
+      (match leaf with
+       | Some l -> tip_row.{v} <- Int32.of_int_exn (Queue.length leaves) ; Queue.enqueue leaves l
+       | None -> tip_row.{v} <- (-1l)) ;
+      List.iter !kids ~f:(fun c -> child_idx.{!k} <- Int32.of_int_exn c ; incr k) ;
+      child_ptr.{v + 1} <- Int32.of_int_exn !k) ;
+  { root ; child_ptr ; child_idx ; tip_row }, Queue.to_array leaves, branches
+
+let pruning_sites t ~nstates ~nsites ~transition_probabilities ~leaf_state ~root_frequencies =
+  let flat, leaves, branches = flatten t in
+  let nnodes = Bigarray.Array1.dim flat.tip_row and ntaxa = Array.length leaves in
+  let ctx = create ~nstates ~nsites ~ntaxa () in
+  let zero = Bigarray.(Array1.create float64 c_layout nnodes) in
+  Bigarray.Array1.fill zero 0. ;
+  set_tree ctx flat ~branch_lengths:zero ;
+  (* transition_probabilities is called once per branch; decompositions are multiplied out on the host
+     (Phylo_ctmc.matrix_decomposition_reduce, lib/phylo_ctmc.ml:13-24) *)
+  let p = Bigarray.(Array1.create float64 c_layout (nnodes * nstates * nstates)) in
+  Bigarray.Array1.fill p 0. ;
+  Array.iteri branches ~f:(fun v -> function
+      | None -> ()
+      | Some b ->
+        let m = Phylo_ctmc.matrix_decomposition_reduce ~dim:nstates (transition_probabilities b) in
+        for j = 0 to nstates - 1 do
+          for i = 0 to nstates - 1 do
+            p.{v * nstates * nstates + j * nstates + i} <- Linear_algebra.Matrix.get m i j   (* column-major *)
+          done
+        done) ;
+  set_pmatrices ctx p ;
+  let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
+  Array.iteri leaves ~f:(fun row l -> for s = 0 to nsites - 1 do tips.{row, s} <- leaf_state l s done) ;
+  set_tips ctx tips ;
+  set_mode ctx mode_phylo_ctmc ;
+  set_root_frequencies ctx root_frequencies ;
+  let per_site = Bigarray.(Array1.create float64 c_layout nsites) in
+  let total = loglik ctx ~per_site () in
+  total, per_site
+
+let pruning t ~nstates ~transition_probabilities ~leaf_state ~root_frequencies =
+  fst (pruning_sites t ~nstates ~nsites:1 ~transition_probabilities
+         ~leaf_state:(fun l _ -> leaf_state l) ~root_frequencies)
+
+module Felsenstein (A : Alphabet.S_int) (Align : Felsenstein.Alignment with type base := A.t)
+    (E : Site_evolution_model.S_with_reduction with type mat := A.matrix and type vec := A.vector) =
+struct
+  let evaluate ~threshold param tree align =
+    let t = Phylogenetic_tree.to_tree tree in
+    let flat, leaves, branches = flatten t in
+    let nnodes = Bigarray.Array1.dim flat.tip_row and ntaxa = Array.length leaves in
+    let nsites = Align.length align in
+    let ctx = create ~nstates:A.card ~nsites ~ntaxa () in
+    let bl = Bigarray.(Array1.create float64 c_layout nnodes) in
+    Array.iteri branches ~f:(fun v b -> bl.{v} <- Option.value b ~default:0.) ;
+    set_tree ctx flat ~branch_lengths:bl ;
+    let u, lambda, uinv = E.rate_matrix_reduction param in
+    set_eigensystem ctx (u :> Linear_algebra.mat) (lambda :> Linear_algebra.vec) (uinv :> Linear_algebra.mat) ;
+    let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
+    Array.iteri leaves ~f:(fun row (_, index) ->
+        for s = 0 to nsites - 1 do tips.{row, s} <- A.to_int (Align.get_base align ~seq:index ~pos:s) done) ;
+    set_tips ctx tips ;
+    set_rescaling ctx threshold false ;     (* shift_normal, no shift after x pi: lib/felsenstein.ml:47-48,57-64 *)
+    set_root_frequencies ctx (E.stationary_distribution param :> Linear_algebra.vec) ;
+    loglik ctx ()
+
+  let felsenstein param tree align = evaluate ~threshold:0.0000001 param tree align
+  let felsenstein_noshift param tree align = evaluate ~threshold:Float.neg_infinity param tree align
+end

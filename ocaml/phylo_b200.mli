@@ -1,0 +1,72 @@
+(** GPU (B200) evaluation of the phylogenetic likelihood behind the reference's signatures.
+
+    Source-only in this repository (no OCaml toolchain in the build image): see INTEGRATION.md.
+    [Phylo_ctmc.pruning] and [Felsenstein.Make(..).felsenstein] keep their types; the batched
+    entry points are new and are what a caller with many sites should use. *)
+
+open Phylogenetics
+
+type ctx
+(** One (tree, alignment, model) evaluator on one GPU; finalised by the GC. *)
+
+type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.t
+type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
+type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
+
+type flat_tree = {
+  root : int ;
+  child_ptr : int32_vec ;   (** node v's children: child_idx.{child_ptr.{v}} .. child_idx.{child_ptr.{v+1} - 1} *)
+  child_idx : int32_vec ;   (** in the order of [Tree.Node.branches] (the left fold of pruning follows it) *)
+  tip_row : int32_vec ;     (** row of the tip matrix for leaves, -1 for internal nodes *)
+}
+
+val flatten : ('n, 'l, 'b) Tree.t -> flat_tree * 'l array * 'b option array
+(** Pre-order numbering; also returns the leaf payloads (by tip row) and the payload of the branch
+    above every node ([None] for the root). *)
+
+val create : ?device:int -> ?ncat:int -> ?keep_clv:bool -> nstates:int -> nsites:int -> ntaxa:int -> unit -> ctx
+
+(** {2 Drop-in replacements} *)
+
+val pruning :
+  ('n, 'l, 'b) Tree.t ->
+  nstates:int ->
+  transition_probabilities:('b -> Phylo_ctmc.matrix_decomposition) ->
+  leaf_state:('l -> int) ->
+  root_frequencies:Linear_algebra.vec ->
+  float
+(** Same type and value as [Phylo_ctmc.pruning] (lib/phylo_ctmc.mli:55-61).  One site per call:
+    correct but dominated by transfer latency; prefer {!pruning_sites}. *)
+
+val pruning_sites :
+  ('n, 'l, 'b) Tree.t ->
+  nstates:int ->
+  nsites:int ->
+  transition_probabilities:('b -> Phylo_ctmc.matrix_decomposition) ->
+  leaf_state:('l -> int -> int) ->
+  root_frequencies:Linear_algebra.vec ->
+  float * float_vec
+(** All sites of an alignment at once: total and per-site log-likelihoods.  [leaf_state l i] is the
+    state of leaf [l] at site [i]; both closures are evaluated eagerly on the host (once per branch,
+    once per (leaf, site)). *)
+
+module Felsenstein (A : Alphabet.S_int) (Align : Felsenstein.Alignment with type base := A.t)
+    (E : Site_evolution_model.S_with_reduction with type mat := A.matrix and type vec := A.vector) : sig
+  val felsenstein : E.param -> Phylogenetic_tree.t -> Align.t -> float
+  (** Same type and value as [Felsenstein.Make(A)(Align)(E).felsenstein] (lib/felsenstein.mli:47);
+      P(t) of every branch is rebuilt on the device from [E.rate_matrix_reduction]. *)
+  val felsenstein_noshift : E.param -> Phylogenetic_tree.t -> Align.t -> float
+end
+
+(** {2 Low-level access (one call per C-ABI entry point)} *)
+
+val set_tree : ctx -> flat_tree -> branch_lengths:float_vec -> unit
+val set_branch_lengths : ctx -> float_vec -> unit
+val set_tips : ctx -> tip_matrix -> unit
+val set_root_frequencies : ctx -> Linear_algebra.vec -> unit
+val set_categories : ctx -> rates:float_vec -> weights:float_vec -> unit
+val set_eigensystem : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
+val set_rate_matrix : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> unit
+val set_rate_matrix_general : ctx -> Linear_algebra.mat -> unit
+val set_pmatrices : ctx -> float_vec -> unit
+val loglik : ctx -> ?per_site:float_vec -> unit -> float
