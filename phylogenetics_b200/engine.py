@@ -95,9 +95,18 @@ class LikelihoodContext:
         """states: uint8 [ntaxa][>=nsites] host array (numpy, or a pinned torch tensor's numpy view)."""
         states = np.asarray(states)
         if states.dtype != np.uint8 or states.ndim != 2 or states.shape[0] != self.ntaxa \
-                or states.strides[1] != 1:
-            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tips must be uint8 [ntaxa][nsites], site-contiguous")
-        self._ck(lib.pb_set_tips(self._ctx, states.ctypes.data, states.strides[0]))
+                or states.shape[1] < self.nsites:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tips must be uint8 [ntaxa][>=nsites]")
+        ntaxa, width = states.shape
+        if ntaxa == 1 or width == 1:
+            # numpy leaves the strides of length-1 axes arbitrary: use a dense copy and ld = width
+            states = np.ascontiguousarray(states)
+            ld = width
+        else:
+            if states.strides[1] != 1 or states.strides[0] < width:
+                states = np.ascontiguousarray(states)
+            ld = states.strides[0]          # row-padded views are passed through as they are
+        self._ck(lib.pb_set_tips(self._ctx, states.ctypes.data, ld))
 
     def set_tips_ptr(self, host_ptr, ld):
         self._ck(lib.pb_set_tips(self._ctx, ctypes.c_void_p(host_ptr), int(ld)))
