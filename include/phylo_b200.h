@@ -132,6 +132,11 @@ int pb_set_pmatrices(pb_ctx *ctx, const double *P);
  * Phylo_ctmc.pruning) and, when per_site != NULL, each site's value [nsites].
  * Blocking; results are host memory. */
 int pb_loglik(pb_ctx *ctx, double *total, double *per_site);
+/* One-call evaluation from HOST tip states: copies the alignment to the device in column chunks
+ * on a second stream while the previous chunk is being pruned (copy/compute overlap), then
+ * behaves like pb_loglik.  `states` should be pinned memory for the copies to be asynchronous.
+ * The states stay resident afterwards, as after pb_set_tips. */
+int pb_loglik_host(pb_ctx *ctx, const uint8_t *states, int64_t ld, double *total, double *per_site);
 /* Non-blocking half: enqueue P(t) + pruning + root reduction on the stream. */
 int pb_loglik_enqueue(pb_ctx *ctx);
 /* Blocking half: wait for the stream and fetch.  per_site may be NULL. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
     "pb_set_tree", "pb_set_branch_lengths", "pb_set_tips", "pb_set_tips_device", "pb_set_tip_masks",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
-    "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_enqueue",
+    "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
@@ -74,6 +74,7 @@ def _load():
         "pb_set_rate_matrix_general": (ci, [vp, vp]),
         "pb_set_pmatrices": (ci, [vp, vp]),
         "pb_loglik": (ci, [vp, vp, vp]),
+        "pb_loglik_host": (ci, [vp, vp, i64, vp, vp]),
         "pb_loglik_enqueue": (ci, [vp]),
         "pb_loglik_fetch": (ci, [vp, vp, vp]),
         "pb_result_device_ptrs": (ci, [vp, vp, vp]),

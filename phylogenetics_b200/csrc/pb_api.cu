@@ -118,6 +118,12 @@ struct pb_ctx {
     double* h_total = nullptr;   // pinned: [0] = total, [1] = bad-tip flag (as int)
     bool evaluated = false;
 
+    // pipelined host evaluation (pb_loglik_host)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    cudaEvent_t ev_start = nullptr;
+    int host_chunks = 8;                // option "host_chunks"
+
     // optional per-phase device timing (pb_set_timing)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -408,6 +414,21 @@ int compile_tree(pb_ctx* c)
             }
         }
         c->fwords = (consumed + 31) / 32;
+        // fold every PUSH into the instruction before it (skipping window loads, which commute with it)
+        std::vector<FusedOp2> folded;
+        for (const FusedOp2& o : c->fprog) {
+            if (o.code == pbk::FOP_PUSH) {
+                int j = (int)folded.size() - 1;
+                while (j >= 0 && folded[j].code == pbk::FOP_LOADW) j--;
+                if (j >= 0 && !(folded[j].code & pbk::FOP_PUSH_AFTER)) { folded[j].code |= pbk::FOP_PUSH_AFTER; continue; }
+                FusedOp2 p2 = o;
+                p2.code = pbk::FOP_PUSH | pbk::FOP_PUSH_AFTER;      // stand-alone push
+                folded.push_back(p2);
+                continue;
+            }
+            folded.push_back(o);
+        }
+        c->fprog.swap(folded);
     }
     c->pack_dirty = true;
 
@@ -468,8 +489,9 @@ int launch_level_dense(pb_ctx* c, int first, int count, int store_root)
     return PB_OK;
 }
 
+// Fused pruning of the site columns [site0, site1) (multiples of the tile size; the whole shard by default).
 template <int BLOCK, int SPT, bool EXACT>
-int launch_fused4_variant(pb_ctx* c)
+int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
 {
     auto kern = pbk::fused4<BLOCK, SPT, EXACT>;
     const size_t smem = fused_smem_bytes(c);
@@ -477,35 +499,35 @@ int launch_fused4_variant(pb_ctx* c)
     int occ = 0;
     PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
     if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4: kernel does not fit on an SM");
-    const int64_t ntiles = c->spad / (BLOCK * SPT);
+    const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
     int64_t gx = ((int64_t)c->sm_count * occ + c->ncat - 1) / c->ncat;
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
     dim3 grid((unsigned)gx, c->ncat);
     kern<<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1), c->d_P.p,
-                                           c->nnodes, c->d_packed.p, c->spad, ntiles, c->d_pi.p, c->threshold,
+                                           c->nnodes, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
                                            c->shift_at_root, c->d_site_cat.p);
     c->launches++;
     return PB_OK;
 }
 
-int launch_fused4(pb_ctx* c)
+int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
 {
     const int key = c->fused_block * 10 + c->fused_spt;
     if (c->fused_exact_log) {
         switch (key) {
-        case 1281: return launch_fused4_variant<128, 1, true>(c);
-        case 2561: return launch_fused4_variant<256, 1, true>(c);
-        case 2562: return launch_fused4_variant<256, 2, true>(c);
-        case 5121: return launch_fused4_variant<512, 1, true>(c);
-        default: return launch_fused4_variant<128, 2, true>(c);
+        case 1281: return launch_fused4_variant<128, 1, true>(c, site0, site1);
+        case 2561: return launch_fused4_variant<256, 1, true>(c, site0, site1);
+        case 2562: return launch_fused4_variant<256, 2, true>(c, site0, site1);
+        case 5121: return launch_fused4_variant<512, 1, true>(c, site0, site1);
+        default: return launch_fused4_variant<128, 2, true>(c, site0, site1);
         }
     }
     switch (key) {
-    case 1281: return launch_fused4_variant<128, 1, false>(c);
-    case 2561: return launch_fused4_variant<256, 1, false>(c);
-    case 2562: return launch_fused4_variant<256, 2, false>(c);
-    case 5121: return launch_fused4_variant<512, 1, false>(c);
-    default: return launch_fused4_variant<128, 2, false>(c);
+    case 1281: return launch_fused4_variant<128, 1, false>(c, site0, site1);
+    case 2561: return launch_fused4_variant<256, 1, false>(c, site0, site1);
+    case 2562: return launch_fused4_variant<256, 2, false>(c, site0, site1);
+    case 5121: return launch_fused4_variant<512, 1, false>(c, site0, site1);
+    default: return launch_fused4_variant<128, 2, false>(c, site0, site1);
     }
 }
 
@@ -519,12 +541,12 @@ int run_pruning(pb_ctx* c)
             PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
             pbk::pack_tips4<<<(unsigned)((c->spad + 255) / 256), 256, 0, c->stream>>>(
                 c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad,
-                c->d_bad.p);
+                0, c->spad, c->d_bad.p);
             c->launches++;
             c->pack_dirty = false;
             c->tips_checked = true;
         }
-        int rc = launch_fused4(c);
+        int rc = launch_fused4(c, 0, c->spad);
         if (rc != PB_OK) return rc;
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
@@ -599,7 +621,7 @@ int run_root_reduction(pb_ctx* c)
     PB_CUDA(c, c->d_partials.ensure((size_t)blocks));
     PB_CUDA(c, c->d_total.ensure(1));
     pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p, c->nsites,
-                                                               c->spad, c->d_per_site.p, c->d_partials.p);
+                                                               c->spad, 0, c->d_per_site.p, c->d_partials.p);
     pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, blocks, c->d_total.p);
     c->launches += 2;
     PB_CUDA(c, cudaGetLastError());
@@ -682,6 +704,9 @@ void pb_destroy(pb_ctx* c)
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     if (c->h_total) cudaFreeHost(c->h_total);
     for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
     c->d_tips.release(); c->d_masks.release(); c->d_pi.release(); c->d_rates.release(); c->d_weights.release();
     c->d_blen.release(); c->d_U.release(); c->d_lambda.release(); c->d_Uinv.release(); c->d_Q.release();
@@ -964,6 +989,78 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
     return PB_OK;
 }
 
+int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, double* per_site)
+{
+    PB_ENTER(c);
+    if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
+    if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
+    if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
+    if (path_of(c) != PATH_FUSED4 || c->host_chunks == 1 || c->spad < 8192) {
+        int rc = pb_set_tips(c, states, ld);
+        if (rc != PB_OK) return rc;
+        return pb_loglik(c, total, per_site);
+    }
+    // Pipeline: the alignment crosses PCIe in column chunks on a copy stream while the previous
+    // chunk is packed, pruned and root-reduced on the compute stream.
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    if (!c->copy_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_start) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    while ((int)c->chunk_events.size() < c->host_chunks) {
+        cudaEvent_t e;
+        PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = build_pmatrices(c)) != PB_OK) return rc;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    const int64_t nblocks = (c->nsites + 255) / 256;
+    PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
+    PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
+    PB_CUDA(c, c->d_partials.ensure((size_t)nblocks));
+    PB_CUDA(c, c->d_total.ensure(1));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
+    PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+    const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
+    int k = 0;
+    for (int64_t s0 = 0; s0 < c->spad; s0 += chunk, k++) {
+        const int64_t s1 = std::min(s0 + chunk, c->spad);
+        const int64_t w = std::min(s1, c->nsites) - s0;
+        if (w > 0)
+            PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p + s0, c->spad, states + s0, ld, w, c->ntaxa,
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+        PB_CUDA(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+        pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
+            c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad, s0, s1,
+            c->d_bad.p);
+        c->launches++;
+        if ((rc = launch_fused4(c, s0, s1)) != PB_OK) return rc;
+        const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
+        if (b1 > b0) {
+            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p,
+                                                                          c->nsites, c->spad, b0, c->d_per_site.p,
+                                                                          c->d_partials.p);
+            c->launches++;
+        }
+    }
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, nblocks, c->d_total.p);
+    c->launches++;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    c->have_tips = true;
+    c->have_masks = false;
+    c->pack_dirty = false;
+    c->tips_checked = true;
+    c->evaluated = true;
+    return pb_loglik_fetch(c, total, per_site);
+}
+
 int pb_loglik(pb_ctx* c, double* total, double* per_site)
 {
     int rc = pb_loglik_enqueue(c);
@@ -1052,6 +1149,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "dmma_group_tiles") {
         if (iv < 8 || iv > 1024 || iv % 8) return fail(c, PB_ERR_INVALID_ARG, "dmma_group_tiles must be a multiple of 8 in 8..1024");
         c->dmma_seq_tiles = iv;
+    } else if (k == "host_chunks") {
+        if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "host_chunks must be in 1..64");
+        c->host_chunks = iv;
     } else if (k == "dense_scalar") {
         c->force_dense = iv != 0;
     } else {

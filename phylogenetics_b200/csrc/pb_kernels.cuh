@@ -349,11 +349,12 @@ __device__ __forceinline__ double block_sum_256(double x, double* red)
 
 __global__ void __launch_bounds__(256)
 root_combine(const double* __restrict__ site_cat, int ncat, const double* __restrict__ weights,
-             int64_t nsites, int64_t spad, double* __restrict__ per_site,
+             int64_t nsites, int64_t spad, int64_t block0, double* __restrict__ per_site,
              double* __restrict__ partials)
 {
     __shared__ double red[8];
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t blk = block0 + blockIdx.x;        // a launch may cover a window of the site blocks
+    const int64_t s = blk * blockDim.x + threadIdx.x;
     double out = 0.0;
     if (s < nsites) {
         if (ncat == 1) {
@@ -373,7 +374,7 @@ root_combine(const double* __restrict__ site_cat, int ncat, const double* __rest
         per_site[s] = out;
     }
     const double bs = block_sum_256(out, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (threadIdx.x == 0) partials[blk] = bs;
 }
 
 __global__ void __launch_bounds__(256)

@@ -40,10 +40,11 @@ constexpr int FOP_ACC_POP = 9;   // ACC = shiftmul(P[pA].ACC, P[pB].pop())   (bo
 // Also flags any state >= 4.
 __global__ void __launch_bounds__(256)
 pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__ order, int ntips,
-           int nwords, uint64_t* __restrict__ packed, int64_t spad, int* __restrict__ bad_flag)
+           int nwords, uint64_t* __restrict__ packed, int64_t spad, int64_t site0, int64_t site1,
+           int* __restrict__ bad_flag)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= spad) return;
+    const int64_t s = site0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // columns [site0, site1)
+    if (s >= site1) return;
     int bad = 0;
     for (int w = 0; w < nwords; w++) {
         uint64_t word = 0;
@@ -113,13 +114,38 @@ __device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, do
     }
 }
 
+// Shared-memory loads by 32-bit shared address: the P matrices are indexed by an offset read from
+// the instruction stream, and plain pointer arithmetic makes the compiler go through generic
+// addressing (S2R SR_CgaCtaId + LEA per access).
+__device__ __forceinline__ double lds_f64(unsigned addr)
+{
+    double x;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ void lds_mat16(unsigned addr, double (&m)[16])
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[2 * i]), "=d"(m[2 * i + 1]) : "r"(addr + 16u * i));
+}
+// column s of the row-major 4x4 matrix at addr
+__device__ __forceinline__ void lds_col4(unsigned addr, int s, double (&c)[4])
+{
+    const unsigned a = addr + 8u * (unsigned)s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = lds_f64(a + 32u * i);
+}
+
+constexpr int FOP_PUSH_AFTER = 0x100;   // flag in the code word: push ACC after the instruction
+
 // Persistent kernel: grid = (blocks_x, ncat); each block stages the P matrices of its category
 // once and then loops over tiles of BLOCK*SPT sites.
 template <int BLOCK, int SPT, bool EXACT_LOG>
 __global__ void __launch_bounds__(BLOCK)
 fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
        const double* __restrict__ P, int nnodes,
-       const uint64_t* __restrict__ packed, int64_t spad, int64_t ntiles,
+       const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
        const double* __restrict__ pi, double thr, int shift_at_root,
        double* __restrict__ site_cat)
 {
@@ -136,56 +162,54 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
     }
     __syncthreads();
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(shP);
     double pir[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) pir[i] = pi[i];
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t s0 = tile * (BLOCK * SPT) + tid;       // site of slot q: s0 + q*BLOCK
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {     // tiles [tile0, tile0 + ntiles)
+        const int64_t s0 = (tile0 + tile) * (BLOCK * SPT) + tid;              // site of slot q: s0 + q*BLOCK
         double v[SPT][4];
         Scale<EXACT_LOG> sc[SPT];
         uint64_t cur[SPT], nxt[SPT];
-        int word = 2;
+        const uint64_t* pk = packed + s0;
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
             sc[q].init();
-            cur[q] = packed[s0 + q * BLOCK];
-            nxt[q] = packed[spad + s0 + q * BLOCK];
+            cur[q] = pk[q * BLOCK];
+            nxt[q] = pk[spad + q * BLOCK];
 #pragma unroll
             for (int i = 0; i < 4; i++) v[q][i] = 1.0;
         }
-        int sp = 0;
+        pk += 2 * spad;
+        double* st = shS + tid;                               // stack pointer (this thread's column)
+        const int4* opp = reinterpret_cast<const int4*>(shOps);
         for (int ip = 0; ip < nops; ip++) {
-            const int4 opw = reinterpret_cast<const int4*>(shOps)[ip];
-            const double* PA = shP + opw.y;
-            const double* PB = shP + opw.z;
+            const int4 opw = opp[ip];
+            const unsigned PA = pbase + 8u * (unsigned)opw.y;
+            const unsigned PB = pbase + 8u * (unsigned)opw.z;
             const int shA = opw.w & 0xff, shB = opw.w >> 8;
-            switch (opw.x) {
-            case FOP_APPLY_MUL_TIP: {
+            const int code = opw.x & 0xff;
+            if (code == FOP_APPLY_MUL_TIP) {
                 double pm[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+                lds_mat16(PA, pm);
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    const int sb = (int)(cur[q] >> shB) & 3;
-                    double y[4];
+                    double y[4], t[4];
+                    lds_col4(PB, (int)(cur[q] >> shB) & 3, t);
                     matvec4(pm, v[q], y);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * PB[i * 4 + sb];
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
                     shift4s(v[q], sc[q], thr);
                 }
-            } break;
-            case FOP_ACC_POP: {
-                sp--;
-                const double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
+            } else if (code == FOP_ACC_POP) {
+                st -= 4 * BLOCK * SPT;
                 double pm[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+                lds_mat16(PA, pm);
                 double y[SPT][4];
 #pragma unroll
                 for (int q = 0; q < SPT; q++) matvec4(pm, v[q], y[q]);
-#pragma unroll
-                for (int i = 0; i < 16; i++) pm[i] = PB[i];
+                lds_mat16(PB, pm);
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double x[4], z[4];
@@ -196,36 +220,29 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     for (int i = 0; i < 4; i++) v[q][i] = y[q][i] * z[i];
                     shift4s(v[q], sc[q], thr);
                 }
-            } break;
-            case FOP_TIP_TIP:
+            } else if (code == FOP_TIP_TIP) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> shA) & 3, sb = (int)(cur[q] >> shB) & 3;
+                    double a[4], b[4];
+                    lds_col4(PA, (int)(cur[q] >> shA) & 3, a);
+                    lds_col4(PB, (int)(cur[q] >> shB) & 3, b);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa] * PB[i * 4 + sb];
+                    for (int i = 0; i < 4; i++) v[q][i] = a[i] * b[i];
                     shift4s(v[q], sc[q], thr);
                 }
-                break;
-            case FOP_LOADW:
+            } else if (code == FOP_LOADW) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     cur[q] = nxt[q];
-                    nxt[q] = packed[(int64_t)word * spad + s0 + q * BLOCK];   // array is padded by 2 words
+                    nxt[q] = pk[q * BLOCK];                   // the array is padded by 2 words
                 }
-                word++;
-                break;
-            case FOP_TIP:
+                pk += spad;
+            } else if (code == FOP_TIP) {
 #pragma unroll
-                for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> shA) & 3;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = PA[i * 4 + sa];
-                }
-                break;
-            case FOP_APPLY: {
+                for (int q = 0; q < SPT; q++) lds_col4(PA, (int)(cur[q] >> shA) & 3, v[q]);
+            } else if (code == FOP_APPLY) {
                 double pm[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) pm[i] = PA[i];
+                lds_mat16(PA, pm);
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
@@ -233,35 +250,24 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i];
                 }
-            } break;
-            case FOP_MUL_TIP:
+            } else if (code == FOP_MUL_TIP) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    const int sa = (int)(cur[q] >> shA) & 3;
+                    double t[4];
+                    lds_col4(PA, (int)(cur[q] >> shA) & 3, t);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * PA[i * 4 + sa];
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
                     shift4s(v[q], sc[q], thr);
                 }
-                break;
-            case FOP_PUSH: {
-                double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
-#pragma unroll
-                for (int q = 0; q < SPT; q++)
-#pragma unroll
-                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
-                sp++;
-            } break;
-            case FOP_POP_MUL: {
-                sp--;
-                const double* st = shS + (size_t)sp * 4 * BLOCK * SPT + tid;
+            } else if (code == FOP_POP_MUL) {
+                st -= 4 * BLOCK * SPT;
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = st[(i * SPT + q) * BLOCK] * v[q][i];
                     shift4s(v[q], sc[q], thr);
                 }
-            } break;
-            case FOP_ROOT:
+            } else if (code == FOP_ROOT) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
 #pragma unroll
@@ -270,8 +276,13 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
                     site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
                 }
-                break;
-            default: break;
+            }
+            if (opw.x & FOP_PUSH_AFTER) {                     // also the stand-alone FOP_PUSH
+#pragma unroll
+                for (int q = 0; q < SPT; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                st += 4 * BLOCK * SPT;
             }
         }
     }

@@ -155,6 +155,23 @@ class LikelihoodContext:
         self._ck(lib.pb_loglik(self._ctx, ctypes.byref(total), None if ps is None else ps.ctypes.data))
         return (total.value, ps) if per_site else total.value
 
+    def loglik_host(self, states, per_site=False):
+        """pb_loglik_host: evaluate straight from a host tip matrix (uint8 [ntaxa][>=nsites], ideally
+        pinned), overlapping the host-to-device copy with the pruning."""
+        states = np.asarray(states)
+        if states.dtype != np.uint8 or states.ndim != 2 or states.shape[0] != self.ntaxa \
+                or states.shape[1] < self.nsites or (states.shape[1] > 1 and states.strides[1] != 1):
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tips must be uint8 [ntaxa][>=nsites], site-contiguous")
+        ld = states.strides[0] if min(states.shape) > 1 else states.shape[1]
+        return self.loglik_host_ptr(states.ctypes.data, ld, per_site)
+
+    def loglik_host_ptr(self, host_ptr, ld, per_site=False):
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_loglik_host(self._ctx, ctypes.c_void_p(host_ptr), int(ld), ctypes.byref(total),
+                                    None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
     def enqueue(self):
         self._ck(lib.pb_loglik_enqueue(self._ctx))
 

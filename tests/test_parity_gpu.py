@@ -245,3 +245,26 @@ def test_level4_occupancy_variants(minb):
         ctx.set_option("level4_min_blocks", minb)
         total, per_site = ctx.loglik(per_site=True)
     check(per_site, total, oracle_per_site(case, P))
+
+
+@pytest.mark.parametrize("nsites,chunks", [(20000, 8), (9001, 3), (50000, 1), (1000, 8)])
+def test_pipelined_host_evaluation(nsites, chunks):
+    """pb_loglik_host: chunked copy overlapped with pruning gives the same per-site values as the
+    two-step pb_set_tips + pb_loglik, on ragged sizes and when it falls back (few sites)."""
+    case = cases.make_case("host", "gtr", 40, nsites, ncat=4, seed=8)
+    P = case.host_P()
+    expect = oracle_per_site(case, P)
+    with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("host_chunks", chunks)
+        total, per_site = ctx.loglik_host(case.tips, per_site=True)
+        check(per_site, total, expect)
+        total2, per_site2 = ctx.loglik(per_site=True)            # tips stay resident afterwards
+        assert total2 == total and np.array_equal(per_site, per_site2)
+        bad = case.tips.copy()
+        bad[7, nsites - 1] = 4
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.loglik_host(bad)
+    # a level-path context falls back to copy-then-evaluate
+    with run_ctx(case, "direct", level=True, P=P) as ctx:
+        total3, per_site3 = ctx.loglik_host(case.tips, per_site=True)
+        check(per_site3, total3, expect)
