@@ -94,6 +94,7 @@ struct pb_ctx {
     DevBuf<LevelChild> d_lv_children;
     DevBuf<FusedOp2> d_fprog;
     DevBuf<int> d_tip_order;
+    DevBuf<uint8_t> d_is_leaf;
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
@@ -443,6 +444,12 @@ int compile_tree(pb_ctx* c)
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_nodes.p, c->lv_nodes.data(), c->lv_nodes.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_lv_children.p, c->lv_children.data(), c->lv_children.size() * sizeof(LevelChild), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog.p, c->fprog.data(), c->fprog.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    {
+        std::vector<uint8_t> leaf(nn);
+        for (int v = 0; v < nn; v++) leaf[v] = c->child_ptr[v] == c->child_ptr[v + 1];
+        PB_CUDA(c, c->d_is_leaf.ensure(nn));
+        PB_CUDA(c, cudaMemcpy(c->d_is_leaf.p, leaf.data(), nn, cudaMemcpyHostToDevice));
+    }
     PB_CUDA(c, c->d_tip_order.ensure(c->tip_order.size()));
     PB_CUDA(c, cudaMemcpyAsync(c->d_tip_order.p, c->tip_order.data(), c->tip_order.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -504,7 +511,7 @@ int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
     dim3 grid((unsigned)gx, c->ncat);
     kern<<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1), c->d_P.p,
-                                           c->nnodes, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
+                                           c->d_is_leaf.p, c->nnodes, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
                                            c->shift_at_root, c->d_site_cat.p);
     c->launches++;
     return PB_OK;
@@ -519,6 +526,7 @@ int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
         case 2561: return launch_fused4_variant<256, 1, true>(c, site0, site1);
         case 2562: return launch_fused4_variant<256, 2, true>(c, site0, site1);
         case 5121: return launch_fused4_variant<512, 1, true>(c, site0, site1);
+        case 1284: return launch_fused4_variant<128, 4, true>(c, site0, site1);
         default: return launch_fused4_variant<128, 2, true>(c, site0, site1);
         }
     }
@@ -527,6 +535,8 @@ int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
     case 2561: return launch_fused4_variant<256, 1, false>(c, site0, site1);
     case 2562: return launch_fused4_variant<256, 2, false>(c, site0, site1);
     case 5121: return launch_fused4_variant<512, 1, false>(c, site0, site1);
+    case 1284: return launch_fused4_variant<128, 4, false>(c, site0, site1);
+    case 2564: return launch_fused4_variant<256, 4, false>(c, site0, site1);
     default: return launch_fused4_variant<128, 2, false>(c, site0, site1);
     }
 }
@@ -1137,7 +1147,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         if (iv != 128 && iv != 256 && iv != 512) return fail(c, PB_ERR_INVALID_ARG, "fused_block must be 128, 256 or 512");
         c->fused_block = iv;
     } else if (k == "fused_spt") {
-        if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1 or 2");
+        if (iv != 1 && iv != 2 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1, 2 or 4");
         c->fused_spt = iv;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
@@ -1157,7 +1167,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else {
         return fail(c, PB_ERR_INVALID_ARG, "unknown option: " + k);
     }
-    if (c->fused_block == 512 && c->fused_spt == 2) c->fused_spt = 1;
+    if (c->fused_block == 512 && c->fused_spt > 1) c->fused_spt = 1;
+    if (c->fused_block == 256 && c->fused_spt == 4 && c->fused_exact_log) c->fused_spt = 2;
     return PB_OK;
 }
 

@@ -101,16 +101,39 @@ __device__ __forceinline__ double max_nonneg(double a, double b)
     return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
 }
 
+// min v > thr  <=>  every component > thr (a NaN fails the test, like the reference's compare)
+__device__ __forceinline__ bool keep4(const double (&v)[4], double thr)
+{
+    return (v[0] > thr) & (v[1] > thr) & (v[2] > thr) & (v[3] > thr);
+}
+
+template <bool EXACT_LOG>
+__device__ __forceinline__ void rescale4(double (&v)[4], Scale<EXACT_LOG>& sc)
+{
+    const double mx = max_nonneg(max_nonneg(v[0], v[1]), max_nonneg(v[2], v[3]));
+    const double inv = 1.0 / mx;
+    v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
+    sc.add(mx);
+}
+
 template <bool EXACT_LOG>
 __device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, double thr)
 {
-    // min v > thr  <=>  every component > thr (a NaN fails the test, like the reference's compare)
-    const bool keep = (v[0] > thr) & (v[1] > thr) & (v[2] > thr) & (v[3] > thr);
-    if (!keep) {
-        const double mx = max_nonneg(max_nonneg(v[0], v[1]), max_nonneg(v[2], v[3]));
-        const double inv = 1.0 / mx;
-        v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
-        sc.add(mx);
+    if (!keep4(v, thr)) rescale4(v, sc);
+}
+
+// SV.shift for the thread's SPT sites with ONE branch on the common path (no site rescales).
+template <int SPT, bool EXACT_LOG>
+__device__ __forceinline__ void shift_all(double (&v)[SPT][4], Scale<EXACT_LOG> (&sc)[SPT], double thr)
+{
+    bool keep[SPT];
+    bool all = true;
+#pragma unroll
+    for (int q = 0; q < SPT; q++) { keep[q] = keep4(v[q], thr); all &= keep[q]; }
+    if (!all) {
+#pragma unroll
+        for (int q = 0; q < SPT; q++)
+            if (!keep[q]) rescale4(v[q], sc[q]);
     }
 }
 
@@ -129,12 +152,13 @@ __device__ __forceinline__ void lds_mat16(unsigned addr, double (&m)[16])
     for (int i = 0; i < 8; i++)
         asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m[2 * i]), "=d"(m[2 * i + 1]) : "r"(addr + 16u * i));
 }
-// column s of the row-major 4x4 matrix at addr
+// column s of a leaf branch's matrix: leaf matrices are staged TRANSPOSED, so the column is
+// 32 contiguous bytes
 __device__ __forceinline__ void lds_col4(unsigned addr, int s, double (&c)[4])
 {
-    const unsigned a = addr + 8u * (unsigned)s;
-#pragma unroll
-    for (int i = 0; i < 4; i++) c[i] = lds_f64(a + 32u * i);
+    const unsigned a = addr + 32u * (unsigned)s;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "r"(a));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c[2]), "=d"(c[3]) : "r"(a + 16u));
 }
 
 constexpr int FOP_PUSH_AFTER = 0x100;   // flag in the code word: push ACC after the instruction
@@ -144,7 +168,7 @@ constexpr int FOP_PUSH_AFTER = 0x100;   // flag in the code word: push ACC after
 template <int BLOCK, int SPT, bool EXACT_LOG>
 __global__ void __launch_bounds__(BLOCK)
 fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
-       const double* __restrict__ P, int nnodes,
+       const double* __restrict__ P, const uint8_t* __restrict__ is_leaf, int nnodes,
        const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
        const double* __restrict__ pi, double thr, int shift_at_root,
        double* __restrict__ site_cat)
@@ -156,7 +180,10 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     const int c = blockIdx.y, tid = threadIdx.x;
     {
         const double* Pg = P + (size_t)c * nnodes * 16;
-        for (int idx = tid; idx < nnodes * 16; idx += BLOCK) shP[idx] = Pg[idx];
+        for (int idx = tid; idx < nnodes * 16; idx += BLOCK) {
+            const int node = idx >> 4, e = idx & 15;           // leaf branches: transposed (column look-ups)
+            shP[is_leaf[node] ? (node * 16 + (e & 3) * 4 + (e >> 2)) : idx] = Pg[idx];
+        }
         const int4* src = reinterpret_cast<const int4*>(prog);
         int4* dst = reinterpret_cast<int4*>(shOps);
         for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
@@ -200,8 +227,8 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     matvec4(pm, v[q], y);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
-                    shift4s(v[q], sc[q], thr);
                 }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
             } else if (code == FOP_ACC_POP) {
                 st -= 4 * BLOCK * SPT;
                 double pm[16];
@@ -218,8 +245,8 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     matvec4(pm, x, z);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[q][i] * z[i];
-                    shift4s(v[q], sc[q], thr);
                 }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
             } else if (code == FOP_TIP_TIP) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
@@ -228,8 +255,8 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     lds_col4(PB, (int)(cur[q] >> shB) & 3, b);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = a[i] * b[i];
-                    shift4s(v[q], sc[q], thr);
                 }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
             } else if (code == FOP_LOADW) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {

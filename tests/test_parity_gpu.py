@@ -185,7 +185,7 @@ def test_errors_are_reported_not_thrown():
         LikelihoodContext(1, 10, 3)
 
 
-@pytest.mark.parametrize("block,spt,exact", [(128, 1, 0), (256, 1, 1), (512, 1, 0), (128, 2, 1), (256, 2, 0)])
+@pytest.mark.parametrize("block,spt,exact", [(128, 1, 0), (256, 1, 1), (512, 1, 0), (128, 2, 1), (256, 2, 0), (128, 4, 0), (256, 4, 0), (128, 4, 1)])
 def test_fused_variants(block, spt, exact):
     """Every compiled shape of the fused kernel, with the reference-style log carry and the
     mantissa/exponent accumulator, on a tree deep enough to use the stack and >32 tips

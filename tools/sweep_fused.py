@@ -16,7 +16,7 @@ case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
 out = []
 ref = None
-for block, spt, exact in [(128, 1, 0), (256, 1, 0), (512, 1, 0), (128, 2, 0), (256, 2, 0), (256, 1, 1), (256, 2, 1), ("level", 3, 0), ("level", 4, 0), ("level", 5, 0), ("level", 6, 0)]:
+for block, spt, exact in [(128, 1, 0), (256, 1, 0), (512, 1, 0), (128, 2, 0), (256, 2, 0), (128, 4, 0), (256, 4, 0), (256, 1, 1), (256, 2, 1), ("level", 3, 0), ("level", 4, 0), ("level", 5, 0), ("level", 6, 0)]:
     level = block == "level"
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4, level_kernels=level) as ctx:
         ctx.set_tree(f, case.bl)
