@@ -166,6 +166,7 @@ size_t fused_smem_bytes(const pb_ctx* c)
 int path_of(const pb_ctx* c)
 {
     const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0 || c->have_masks;
+    if (c->have_masks) return PATH_LEVEL_DENSE;
     if (c->n == 4) {
         if (!level && c->have_tree) {
             if (fused_smem_bytes(c) <= c->smem_optin) return PATH_FUSED4;
@@ -482,18 +483,25 @@ int build_pmatrices(pb_ctx* c)
     return PB_OK;
 }
 
+template <int N, bool MASKS>
+int launch_level_dense_m(pb_ctx* c, int first, int count, int store_root)
+{
+    const size_t smem = (size_t)(N * N + N * 128) * sizeof(double);
+    auto kern = pbk::level_dense<N, MASKS>;
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(c->spad / 128), count);
+    kern<<<grid, 128, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->ncat,
+                                         c->d_tips.p, c->d_masks.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
+                                         c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root);
+    c->launches++;
+    return PB_OK;
+}
+
 template <int N>
 int launch_level_dense(pb_ctx* c, int first, int count, int store_root)
 {
-    const size_t smem = (size_t)(N * N + N * 128) * sizeof(double);
-    PB_CUDA(c, cudaFuncSetAttribute(pbk::level_dense<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(c->spad / 128), count);
-    pbk::level_dense<N><<<grid, 128, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p,
-                                                        c->nnodes, c->ncat, c->d_tips.p, c->spad, c->d_pool.p,
-                                                        c->slot_stride, c->spad, c->d_pi.p, c->threshold,
-                                                        c->shift_at_root, c->d_site_cat.p, store_root);
-    c->launches++;
-    return PB_OK;
+    return c->have_masks ? launch_level_dense_m<N, true>(c, first, count, store_root)
+                         : launch_level_dense_m<N, false>(c, first, count, store_root);
 }
 
 // Fused pruning of the site columns [site0, site1) (multiples of the tile size; the whole shard by default).
@@ -561,7 +569,7 @@ int run_pruning(pb_ctx* c)
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
     }
-    if (!c->tips_checked) {
+    if (!c->tips_checked && !c->have_masks) {
         pbk::validate_tips<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_tips.p, (int64_t)c->ntaxa * c->spad, n, c->d_bad.p);
         c->launches++;
         c->tips_checked = true;
@@ -610,6 +618,7 @@ int run_pruning(pb_ctx* c)
             switch (n) {
             case 2: rc = launch_level_dense<2>(c, first, count, store_root); break;
             case 3: rc = launch_level_dense<3>(c, first, count, store_root); break;
+            case 4: rc = launch_level_dense<4>(c, first, count, store_root); break;
             case 5: rc = launch_level_dense<5>(c, first, count, store_root); break;
             case 20: rc = launch_level_dense<20>(c, first, count, store_root); break;
             case 61: rc = launch_level_dense<61>(c, first, count, store_root); break;
@@ -865,8 +874,17 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
 int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
 {
     PB_ENTER(c);
-    (void)masks; (void)ld;
-    return fail(c, PB_ERR_STATE, "tip state-set masks (Missing_values / Ambiguous) are not built yet");
+    if (!masks || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "masks: null pointer or ld < nsites");
+    const size_t count = (size_t)c->ntaxa * c->spad;
+    const bool fresh = c->d_masks.count < count || !c->d_masks.p;
+    PB_CUDA(c, c->d_masks.ensure(count));
+    if (fresh) PB_CUDA(c, cudaMemsetAsync(c->d_masks.p, 0, count * sizeof(uint64_t), c->stream));
+    PB_CUDA(c, cudaMemcpy2DAsync(c->d_masks.p, c->spad * sizeof(uint64_t), masks, ld * sizeof(uint64_t),
+                                 c->nsites * sizeof(uint64_t), c->ntaxa, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    c->have_masks = true;
+    c->have_tips = true;
+    return PB_OK;
 }
 
 int pb_set_root_frequencies(pb_ctx* c, const double* pi)
@@ -1096,6 +1114,16 @@ int pb_get_clv(pb_ctx* c, int node, int cat, double* v, double* carry)
         return fail(c, PB_ERR_INVALID_ARG, "pb_get_clv: bad node/category/pointer");
     const int n = c->n;
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->child_ptr[node] == c->child_ptr[node + 1] && c->have_masks) {   // leaf: set indicator, carry 0 (NaN if missing)
+        std::vector<uint64_t> row(c->nsites);
+        PB_CUDA(c, cudaMemcpy(row.data(), c->d_masks.p + (size_t)c->tip_row[node] * c->spad,
+                              c->nsites * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        for (int64_t s = 0; s < c->nsites; s++) {
+            for (int i = 0; i < n; i++) v[s * n + i] = (double)((row[s] >> i) & 1u);
+            carry[s] = row[s] ? 0.0 : NAN;
+        }
+        return PB_OK;
+    }
     if (c->child_ptr[node] == c->child_ptr[node + 1]) {      // leaf: indicator, carry 0
         std::vector<uint8_t> row(c->nsites);
         PB_CUDA(c, cudaMemcpy(row.data(), c->d_tips.p + (size_t)c->tip_row[node] * c->spad, c->nsites, cudaMemcpyDeviceToHost));

@@ -256,12 +256,18 @@ level4(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ child
 // K2 (level-scheduled, N states, scalar DFMA version): one thread per site, the child's
 // CLV tile and its P matrix staged in shared memory, running product in registers.
 // Baseline and fallback for the tensor-core kernel (level_dmma, pb_kernels_dmma.cuh).
+//
+// MASKS = true is the Missing_values / Ambiguous form (lib/phylo_ctmc.ml:145-172, :280-302):
+// a tip is a SET of states (bit i of a 64-bit mask; Ambiguous.leaf_indicator :234-242) and its
+// term is P . indicator; an empty set is a missing observation (None): that child is skipped,
+// no product and no shift, and a node all of whose children are None is None itself.  "None" is
+// carried in HBM as a NaN in the carry plane, and as +inf in site_cat (-> log-likelihood 0).
 // --------------------------------------------------------------------------
-template <int N>
+template <int N, bool MASKS>
 __global__ void __launch_bounds__(128)
 level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children,
             int node_base, const double* __restrict__ P, int nnodes, int ncat,
-            const uint8_t* __restrict__ tips, int64_t tips_ld,
+            const uint8_t* __restrict__ tips, const uint64_t* __restrict__ masks, int64_t tips_ld,
             double* __restrict__ pool, int64_t slot_stride, int64_t spad,
             const double* __restrict__ pi, double thr, int shift_at_root,
             double* __restrict__ site_cat, int store_root)
@@ -277,6 +283,7 @@ level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
     for (int c = 0; c < ncat; c++) {
         double acc[N];
         double carry = 0.0;
+        bool have = false;            // MASKS: at least one child had an observation below it
         for (int k = 0; k < nd.nchild; k++) {
             const LevelChild cd = ch[k];
             __syncthreads();
@@ -284,44 +291,63 @@ level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
             for (int idx = tid; idx < N * N; idx += 128) shP[idx] = Pg[idx];
             double tc = 0.0;
             int st = 0;
+            uint64_t m = 0;
+            bool ok = true;
             if (cd.kind == 0) {
-                st = tips[(int64_t)cd.src * tips_ld + s];
+                if (MASKS) { m = masks[(int64_t)cd.src * tips_ld + s]; ok = m != 0; }
+                else st = tips[(int64_t)cd.src * tips_ld + s];
             } else {
                 const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (N + 1) * spad + s;
 #pragma unroll 4
                 for (int j = 0; j < N; j++) shX[j * 128 + tid] = src[(int64_t)j * spad];
                 tc = src[(int64_t)N * spad];
+                if (MASKS) ok = !isnan(tc);
             }
             __syncthreads();
-            if (k == 0) carry = tc; else carry = carry + tc;
+            const bool first = MASKS ? !have : (k == 0);
+            if (ok) carry = first ? tc : carry + tc;
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 double t;
                 if (cd.kind == 0) {
-                    t = shP[i * N + st];
+                    if (MASKS) {          // dgemv against the 0/1 indicator: sum of the set columns, ascending
+                        t = 0.0;
+                        for (int j = 0; j < N; j++)
+                            if ((m >> j) & 1) t += shP[i * N + j];
+                    } else {
+                        t = shP[i * N + st];
+                    }
                 } else {
                     t = shP[i * N] * shX[tid];
 #pragma unroll 4
                     for (int j = 1; j < N; j++) t = fma(shP[i * N + j], shX[j * 128 + tid], t);
                 }
-                acc[i] = (k == 0) ? t : acc[i] * t;
+                if (ok) acc[i] = first ? t : acc[i] * t;
             }
-            if (k > 0) shiftN<N>(acc, carry, thr);
+            if (ok && !first) shiftN<N>(acc, carry, thr);
+            if (ok) have = true;
         }
+        const bool none = MASKS && !have;
         if (!nd.is_root || store_root) {
             double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * (N + 1) * spad + s;
 #pragma unroll
-            for (int i = 0; i < N; i++) dst[(int64_t)i * spad] = acc[i];
-            dst[(int64_t)N * spad] = carry;
+            for (int i = 0; i < N; i++) dst[(int64_t)i * spad] = none ? 0.0 : acc[i];
+            dst[(int64_t)N * spad] = none ? NAN : carry;
         }
         if (nd.is_root) {
+            double out;
+            if (none) {
+                out = INFINITY;        // all-missing site: root_combine turns it into 0. (:172, :302)
+            } else {
 #pragma unroll
-            for (int i = 0; i < N; i++) acc[i] = acc[i] * pi[i];
-            if (shift_at_root) shiftN<N>(acc, carry, thr);
-            double sum = acc[0];
+                for (int i = 0; i < N; i++) acc[i] = acc[i] * pi[i];
+                if (shift_at_root) shiftN<N>(acc, carry, thr);
+                double sum = acc[0];
 #pragma unroll
-            for (int i = 1; i < N; i++) sum += acc[i];
-            site_cat[(int64_t)c * spad + s] = log(sum) + carry;
+                for (int i = 1; i < N; i++) sum += acc[i];
+                out = log(sum) + carry;
+            }
+            site_cat[(int64_t)c * spad + s] = out;
         }
     }
 }
@@ -357,7 +383,9 @@ root_combine(const double* __restrict__ site_cat, int ncat, const double* __rest
     const int64_t s = blk * blockDim.x + threadIdx.x;
     double out = 0.0;
     if (s < nsites) {
-        if (ncat == 1) {
+        if (site_cat[s] == INFINITY) {          // no observation at all in this column: 0. like the reference
+            out = 0.0;
+        } else if (ncat == 1) {
             out = site_cat[s];
         } else {
             double m = site_cat[s];
