@@ -1,8 +1,10 @@
 // K2, level-scheduled, dense alphabets (20 amino acids, 61 sense codons) on the FP64 tensor
 // cores: parent[i][site] = sum_j P[i][j] child[j][site] is a GEMM with M = parent states,
 // K = child states, N = sites, issued as mma.sync.aligned.m16n8k8 .f64 tiles (SASS: DMMA.16x8x8;
-// tcgen05.mma has no FP64 kind).  Measured on B200: m16n8k8 sustains 74 TFLOP/s, twice m8n8k4
-// and twice the DFMA pipe (profiles/fp64_peak_r01.json).
+// tcgen05.mma has no FP64 kind).  Measured on B200 (tools/fp64_peak2.cu,
+// profiles/r01_fp64_peak_dmma_shapes.jsonl): every mma.sync .f64 shape lowers to DMMA.8x8x4 and
+// sustains 36.8 TFLOP/s, the same as the DFMA pipe's 37 TFLOP/s peak — the tensor path saves
+// issue slots and register-file bandwidth, not pipe time.
 //
 // Restates the node step of Phylo_ctmc.pruning (lib/phylo_ctmc.ml:91-95): one mat-vec per
 // inner child (a column look-up for a leaf child), children folded left to right with SV.mul,
