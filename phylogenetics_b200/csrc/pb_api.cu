@@ -89,7 +89,7 @@ struct pb_ctx {
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
-    int fused_block = 256, fused_spt = 2, fused_exact_log = 0;
+    int fused_block = 256, fused_spt = 1, fused_exact_log = 0;
     DevBuf<LevelNode> d_lv_nodes;
     DevBuf<LevelChild> d_lv_children;
     DevBuf<FusedOp2> d_fprog;
