@@ -85,6 +85,7 @@ struct pb_ctx {
     DevBuf<LevelNode> d_sq_nodes;
     DevBuf<LevelChild> d_sq_children;
     int dmma_per_level = 1;             // option "dmma_per_level": one launch per tree level instead
+    int dmma_version = 2;               // option "dmma_version": 2 = cp.async-pipelined kernel (arity <= 2), 1 = direct loads
     int dmma_seq_tiles = 16;            // option "dmma_group_tiles": 8-site tiles per group (x8 sites)
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
@@ -604,6 +605,13 @@ int run_pruning(pb_ctx* c)
             default: pbk::level4<4><<<grid, 256, 0, c->stream>>>(PB_LEVEL4_ARGS); break;
             }
 #undef PB_LEVEL4_ARGS
+            c->launches++;
+        } else if (path == PATH_LEVEL_DMMA && c->dmma_version == 2 && c->max_arity <= 2) {
+            int rc = pbk::launch_level_dmma2(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
+                                             c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
+                                             c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root,
+                                             c->sm_count, c->smem_optin, c->stream);
+            if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma2 launch configuration failed");
             c->launches++;
         } else if (path == PATH_LEVEL_DMMA) {
             int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->max_arity,
@@ -1182,6 +1190,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "level4_min_blocks") {
         if (iv < 3 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "level4_min_blocks must be 3..6");
         c->level4_minb = iv;
+    } else if (k == "dmma_version") {
+        if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "dmma_version must be 1 or 2");
+        c->dmma_version = iv;
     } else if (k == "dmma_per_level") {
         c->dmma_per_level = iv != 0;
     } else if (k == "dmma_group_tiles") {

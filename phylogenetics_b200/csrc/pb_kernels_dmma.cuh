@@ -202,6 +202,223 @@ level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ c
     }   // groups
 }
 
+// --------------------------------------------------------------------------
+// level_dmma2: the same node step, software-pipelined.  Every warp owns a private double buffer in
+// shared memory and streams the CLV tiles of its NEXT 8 sites with cp.async (16-byte chunks, no
+// register staging) while the tensor cores work on the current tile, so the DMMAs never wait on
+// HBM.  Rows of a staged tile are 64 bytes (8 sites); 16-byte chunk c of row k is stored at chunk
+// c ^ (k & 3), which makes the 8-byte B-fragment loads bank-conflict free.  Arity <= 2.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+template <int N>
+__global__ void __launch_bounds__(256, (N <= 32 ? 2 : 1))
+level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children, int node_base,
+            const double* __restrict__ P, int nnodes, int ncat,
+            const uint8_t* __restrict__ tips, int64_t tips_ld,
+            double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+            const double* __restrict__ pi, double thr, int shift_at_root,
+            double* __restrict__ site_cat, int store_root, int tiles_per_block)
+{
+    using S = DmmaShape<N>;
+    constexpr int MP = S::MP, LD = S::LD, MT = S::MT, KS = S::KS;
+    constexpr int XROWS = N + 1;                 // state planes + the carry plane
+    constexpr int XSZ = XROWS * 8;               // doubles per staged child tile
+    extern __shared__ double shraw[];            // pi[MP] | P[2][MP*LD] | X[8 warps][2 stages][2 children][XSZ]
+    double* shPi = shraw;
+    double* sh = shraw + MP;
+    double* shX = sh + 2 * MP * LD;
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int64_t ntiles = spad / 8;
+    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_block;
+    const int64_t tile_end = min(tile_begin + tiles_per_block, ntiles);
+    double* myX = shX + (size_t)warp * 4 * XSZ;
+    if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+    const LevelChild cd0 = ch[0];
+    const LevelChild cd1 = ch[nd.nchild > 1 ? 1 : 0];
+
+    for (int c = 0; c < ncat; c++) {
+        __syncthreads();
+        for (int idx = tid; idx < nd.nchild * MP * LD; idx += 256) {
+            const int k = idx / (MP * LD), r = idx - k * (MP * LD);
+            const int i = r / LD, j = r - i * LD;
+            sh[idx] = (i < N && j < N) ? P[((size_t)c * nnodes + ch[k].pnode) * N * N + i * N + j] : 0.0;
+        }
+        __syncthreads();
+
+        // stage the CLV planes (and carry) of every inner child for one tile; tips go to registers
+        auto prefetch = [&](int64_t tile, int stage, uchar2 (&st)[2]) {
+            const int64_t s0 = tile * 8;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (k >= nd.nchild) break;
+                const LevelChild cd = k ? cd1 : cd0;
+                if (cd.kind == 0) {
+                    st[k] = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0 + tig * 2);
+                } else {
+                    const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (N + 1) * spad + s0;
+                    double* dst = myX + (size_t)(stage * 2 + k) * XSZ;
+                    for (int idx = lane; idx < XROWS * 4; idx += 32) {
+                        const int row = idx >> 2, q = idx & 3;
+                        cp_async16(dst + row * 8 + ((q ^ (row & 3)) << 1), src + (int64_t)row * spad + (q << 1));
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+
+        uchar2 st_cur[2] = {make_uchar2(0, 0), make_uchar2(0, 0)}, st_nxt[2] = {make_uchar2(0, 0), make_uchar2(0, 0)};
+        int64_t tile = tile_begin + warp;
+        if (tile < tile_end) prefetch(tile, 0, st_cur);
+        int stage = 0;
+        for (; tile < tile_end; tile += 8, stage ^= 1) {
+            const bool more = tile + 8 < tile_end;
+            if (more) { prefetch(tile + 8, stage ^ 1, st_nxt); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
+            const int64_t s0 = tile * 8;
+            double out[MT][4];
+            double car[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (k >= nd.nchild) break;
+                const LevelChild cd = k ? cd1 : cd0;
+                const double* Pm = sh + (size_t)k * MP * LD;
+                double cf[MT][4];
+                double tc[2] = {0.0, 0.0};
+                if (cd.kind == 0) {
+                    const uchar2 st = st_cur[k];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double* r0 = Pm + (mt * 16 + g) * LD;
+                        const double* r1 = r0 + 8 * LD;
+                        cf[mt][0] = r0[st.x]; cf[mt][1] = r0[st.y];
+                        cf[mt][2] = r1[st.x]; cf[mt][3] = r1[st.y];
+                    }
+                } else {
+                    const double* X = myX + (size_t)(stage * 2 + k) * XSZ;
+                    double b[KS][2];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) {
+                        const int k0 = ks * 8 + tig, k1 = k0 + 4;         // (k0 & 3) == (k1 & 3) == tig
+                        const int off = (((g >> 1) ^ tig) << 1) + (g & 1);
+                        b[ks][0] = (k0 < N) ? X[k0 * 8 + off] : 0.0;
+                        b[ks][1] = (k1 < N) ? X[k1 * 8 + off] : 0.0;
+                    }
+                    const double2 q = *reinterpret_cast<const double2*>(X + N * 8 + ((tig ^ (N & 3)) << 1));
+                    tc[0] = q.x; tc[1] = q.y;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
+                        const double* r0 = Pm + (mt * 16 + g) * LD + tig;
+                        const double* r1 = r0 + 8 * LD;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ks++)
+                            dmma_16x8x8(cf[mt], r0[ks * 8], r1[ks * 8], r0[ks * 8 + 4], r1[ks * 8 + 4], b[ks][0], b[ks][1]);
+                    }
+                }
+                if (k == 0) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) out[mt][e] = cf[mt][e];
+                    car[0] = tc[0]; car[1] = tc[1];
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) out[mt][e] = out[mt][e] * cf[mt][e];
+                    car[0] = car[0] + tc[0]; car[1] = car[1] + tc[1];
+                    shift_frag<N>(out, car, g, thr);
+                }
+            }
+            __syncwarp();                       // every lane is done reading this stage before it is refilled
+            if (!nd.is_root || store_root) {
+                double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * (N + 1) * spad + s0 + tig * 2;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const int r0 = mt * 16 + g, r1 = r0 + 8;
+                    if (r0 < N) *reinterpret_cast<double2*>(dst + (int64_t)r0 * spad) = make_double2(out[mt][0], out[mt][1]);
+                    if (r1 < N) *reinterpret_cast<double2*>(dst + (int64_t)r1 * spad) = make_double2(out[mt][2], out[mt][3]);
+                }
+                if (g == 0) *reinterpret_cast<double2*>(dst + (int64_t)N * spad) = make_double2(car[0], car[1]);
+            }
+            if (nd.is_root) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double p0 = shPi[mt * 16 + g], p1 = shPi[mt * 16 + g + 8];
+                    out[mt][0] *= p0; out[mt][1] *= p0; out[mt][2] *= p1; out[mt][3] *= p1;
+                }
+                if (shift_at_root) shift_frag<N>(out, car, g, thr);
+                double sum[2] = {0.0, 0.0};
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    sum[0] += out[mt][0] + out[mt][2];
+                    sum[1] += out[mt][1] + out[mt][3];
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+                    sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+                }
+                if (g == 0)
+                    *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                        make_double2(log(sum[0]) + car[0], log(sum[1]) + car[1]);
+            }
+            st_cur[0] = st_nxt[0]; st_cur[1] = st_nxt[1];
+        }
+    }
+}
+
+template <int N>
+int launch_level_dmma2_n(const LevelNode* nodes, const LevelChild* children, int first, int count,
+                         const double* P, int nnodes, int ncat, const uint8_t* tips, int64_t tips_ld, double* pool,
+                         int64_t slot_stride, int64_t spad, const double* pi, double thr, int shift_at_root,
+                         double* site_cat, int store_root, int sm_count, size_t smem_optin, cudaStream_t stream)
+{
+    using S = DmmaShape<N>;
+    const size_t smem = ((size_t)S::MP + 2 * S::MP * S::LD + (size_t)8 * 4 * (N + 1) * 8) * sizeof(double);
+    if (smem > smem_optin) return -2;
+    auto kern = level_dmma2<N>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) return -1;
+    const int64_t ntiles = spad / 8;
+    int64_t want_blocks = std::max<int64_t>(1, (int64_t)sm_count * occ / count);
+    int64_t tpb = (ntiles + want_blocks - 1) / want_blocks;
+    tpb = std::max<int64_t>(8, (tpb + 7) / 8 * 8);
+    const int64_t gx = (ntiles + tpb - 1) / tpb;
+    kern<<<dim3((unsigned)gx, count), 256, smem, stream>>>(nodes, children, first, P, nnodes, ncat, tips, tips_ld, pool,
+                                                           slot_stride, spad, pi, thr, shift_at_root, site_cat,
+                                                           store_root, (int)tpb);
+    return 0;
+}
+
+inline int launch_level_dmma2(int n, const LevelNode* nodes, const LevelChild* children, int first, int count,
+                              const double* P, int nnodes, int ncat, const uint8_t* tips, int64_t tips_ld,
+                              double* pool, int64_t slot_stride, int64_t spad, const double* pi, double thr,
+                              int shift_at_root, double* site_cat, int store_root, int sm_count, size_t smem_optin,
+                              cudaStream_t stream)
+{
+    if (n == 20)
+        return launch_level_dmma2_n<20>(nodes, children, first, count, P, nnodes, ncat, tips, tips_ld, pool, slot_stride,
+                                        spad, pi, thr, shift_at_root, site_cat, store_root, sm_count, smem_optin, stream);
+    if (n == 61)
+        return launch_level_dmma2_n<61>(nodes, children, first, count, P, nnodes, ncat, tips, tips_ld, pool, slot_stride,
+                                        spad, pi, thr, shift_at_root, site_cat, store_root, sm_count, smem_optin, stream);
+    return -1;
+}
+
 inline bool dmma_supported(int n) { return n == 20 || n == 61; }
 
 template <int N>

@@ -213,7 +213,7 @@ def test_out_of_range_tip_state_is_an_error():
 
 
 @pytest.mark.parametrize("model,ntaxa,nsites", [("wag", 40, 2100), ("mg94", 24, 900)])
-@pytest.mark.parametrize("opts", [{}, {"dmma_per_level": 0}, {"dmma_per_level": 0, "dmma_group_tiles": 8}, {"dense_scalar": 1}])
+@pytest.mark.parametrize("opts", [{}, {"dmma_version": 1}, {"dmma_per_level": 0}, {"dmma_per_level": 0, "dmma_group_tiles": 8}, {"dense_scalar": 1}])
 def test_dense_kernel_modes(model, ntaxa, nsites, opts):
     """DMMA kernel with per-level launches (default), in its persistent tree-walking mode, with a
     different group size, and the scalar DFMA kernel: all against the oracle, with and without CLVs kept."""
