@@ -140,13 +140,16 @@ level_dmma(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ c
                     const double2 q = *reinterpret_cast<const double2*>(src + (int64_t)N * spad + tig * 2);
                     tc[0] = q.x; tc[1] = q.y;
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
-                        const double* r0 = Pm + (mt * 16 + g) * LD + tig;
-                        const double* r1 = r0 + 8 * LD;
+                    for (int mt = 0; mt < MT; mt++) cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
+                    // k-step outermost: the MT accumulator tiles are independent DMMA chains in flight
 #pragma unroll
-                        for (int ks = 0; ks < KS; ks++)
-                            dmma_16x8x8(cf[mt], r0[ks * 8], r1[ks * 8], r0[ks * 8 + 4], r1[ks * 8 + 4], b[ks][0], b[ks][1]);
+                    for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) {
+                            const double* r0 = Pm + (mt * 16 + g) * LD + tig + ks * 8;
+                            const double* r1 = r0 + 8 * LD;
+                            dmma_16x8x8(cf[mt], r0[0], r1[0], r0[4], r1[4], b[ks][0], b[ks][1]);
+                        }
                     }
                 }
                 if (k == 0) {
@@ -231,10 +234,11 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
     constexpr int MP = S::MP, LD = S::LD, MT = S::MT, KS = S::KS;
     constexpr int XROWS = N + 1;                 // state planes + the carry plane
     constexpr int XSZ = XROWS * 8;               // doubles per staged child tile
-    extern __shared__ double shraw[];            // pi[MP] | P[2][MP*LD] | X[8 warps][2 stages][2 children][XSZ]
+    extern __shared__ double shraw[];            // pi[MP] | P[2][MP*LD] | X[8 warps][2 stages][2 children][XSZ] | tips
     double* shPi = shraw;
     double* sh = shraw + MP;
     double* shX = sh + 2 * MP * LD;
+    unsigned long long* shT = reinterpret_cast<unsigned long long*>(shX + (size_t)8 * 4 * XSZ);   // [8][2][2] x 8 tip bytes
     const LevelNode nd = nodes[node_base + blockIdx.y];
     const LevelChild* ch = children + nd.child_off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,6 +247,7 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
     const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_block;
     const int64_t tile_end = min(tile_begin + tiles_per_block, ntiles);
     double* myX = shX + (size_t)warp * 4 * XSZ;
+    unsigned long long* myT = shT + warp * 4;
     if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
     const LevelChild cd0 = ch[0];
     const LevelChild cd1 = ch[nd.nchild > 1 ? 1 : 0];
@@ -257,14 +262,17 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
         __syncthreads();
 
         // stage the CLV planes (and carry) of every inner child for one tile; tips go to registers
-        auto prefetch = [&](int64_t tile, int stage, uchar2 (&st)[2]) {
+        auto prefetch = [&](int64_t tile, int stage) {
             const int64_t s0 = tile * 8;
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 if (k >= nd.nchild) break;
                 const LevelChild cd = k ? cd1 : cd0;
-                if (cd.kind == 0) {
-                    st[k] = *reinterpret_cast<const uchar2*>(tips + (int64_t)cd.src * tips_ld + s0 + tig * 2);
+                if (cd.kind == 0) {            // the tile's 8 tip bytes, asynchronously like the CLV planes
+                    if (lane == 0) {
+                        const unsigned d = (unsigned)__cvta_generic_to_shared(myT + stage * 2 + k);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(tips + (int64_t)cd.src * tips_ld + s0) : "memory");
+                    }
                 } else {
                     const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (N + 1) * spad + s0;
                     double* dst = myX + (size_t)(stage * 2 + k) * XSZ;
@@ -277,13 +285,12 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
             cp_async_commit();
         };
 
-        uchar2 st_cur[2] = {make_uchar2(0, 0), make_uchar2(0, 0)}, st_nxt[2] = {make_uchar2(0, 0), make_uchar2(0, 0)};
         int64_t tile = tile_begin + warp;
-        if (tile < tile_end) prefetch(tile, 0, st_cur);
+        if (tile < tile_end) prefetch(tile, 0);
         int stage = 0;
         for (; tile < tile_end; tile += 8, stage ^= 1) {
             const bool more = tile + 8 < tile_end;
-            if (more) { prefetch(tile + 8, stage ^ 1, st_nxt); cp_async_wait<1>(); }
+            if (more) { prefetch(tile + 8, stage ^ 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncwarp();
             const int64_t s0 = tile * 8;
@@ -297,7 +304,8 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
                 double cf[MT][4];
                 double tc[2] = {0.0, 0.0};
                 if (cd.kind == 0) {
-                    const uchar2 st = st_cur[k];
+                    const unsigned char* tb = reinterpret_cast<const unsigned char*>(myT + stage * 2 + k) + tig * 2;
+                    const uchar2 st = make_uchar2(tb[0], tb[1]);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
                         const double* r0 = Pm + (mt * 16 + g) * LD;
@@ -318,13 +326,16 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
                     const double2 q = *reinterpret_cast<const double2*>(X + N * 8 + ((tig ^ (N & 3)) << 1));
                     tc[0] = q.x; tc[1] = q.y;
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
-                        const double* r0 = Pm + (mt * 16 + g) * LD + tig;
-                        const double* r1 = r0 + 8 * LD;
+                    for (int mt = 0; mt < MT; mt++) cf[mt][0] = cf[mt][1] = cf[mt][2] = cf[mt][3] = 0.0;
+                    // k-step outermost: the MT accumulator tiles are independent DMMA chains in flight
 #pragma unroll
-                        for (int ks = 0; ks < KS; ks++)
-                            dmma_16x8x8(cf[mt], r0[ks * 8], r1[ks * 8], r0[ks * 8 + 4], r1[ks * 8 + 4], b[ks][0], b[ks][1]);
+                    for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) {
+                            const double* r0 = Pm + (mt * 16 + g) * LD + tig + ks * 8;
+                            const double* r1 = r0 + 8 * LD;
+                            dmma_16x8x8(cf[mt], r0[0], r1[0], r0[4], r1[4], b[ks][0], b[ks][1]);
+                        }
                     }
                 }
                 if (k == 0) {
@@ -375,7 +386,6 @@ level_dmma2(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
                     *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
                         make_double2(log(sum[0]) + car[0], log(sum[1]) + car[1]);
             }
-            st_cur[0] = st_nxt[0]; st_cur[1] = st_nxt[1];
         }
     }
 }
@@ -387,7 +397,7 @@ int launch_level_dmma2_n(const LevelNode* nodes, const LevelChild* children, int
                          double* site_cat, int store_root, int sm_count, size_t smem_optin, cudaStream_t stream)
 {
     using S = DmmaShape<N>;
-    const size_t smem = ((size_t)S::MP + 2 * S::MP * S::LD + (size_t)8 * 4 * (N + 1) * 8) * sizeof(double);
+    const size_t smem = ((size_t)S::MP + 2 * S::MP * S::LD + (size_t)8 * 4 * (N + 1) * 8 + 8 * 4) * sizeof(double);
     if (smem > smem_optin) return -2;
     auto kern = level_dmma2<N>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
