@@ -94,6 +94,13 @@ int pb_set_rescaling(pb_ctx *ctx, double threshold, int shift_at_root);
 int pb_set_tree(pb_ctx *ctx, int nnodes, int root, const int32_t *child_ptr,
                 const int32_t *child_idx, const int32_t *tip_row, const double *branch_len);
 int pb_set_branch_lengths(pb_ctx *ctx, const double *branch_len /* [nnodes] */);
+/* Change ONE branch length (the branch above `node`; Phylogenetic_tree.set_branch_lengths,
+ * lib/phylogenetic_tree.ml:153-161, one coordinate at a time).  With PB_FLAG_KEEP_CLV the next
+ * evaluation recomputes only the conditional likelihoods on the path from that branch to the
+ * root: every other node's array is already resident.  pb_nodes_recomputed reports how many
+ * internal nodes the last evaluation touched. */
+int pb_update_branch_length(pb_ctx *ctx, int node, double t);
+int pb_nodes_recomputed(const pb_ctx *ctx);
 
 /* Observed states, one byte per (taxon, site): states[row*ld + site] in 0..nstates-1
  * (`leaf_state`, lib/phylo_ctmc.mli:58; evaluated eagerly by the caller).  Host memory. */

@@ -78,6 +78,11 @@ struct pb_ctx {
     std::vector<int> lv_first;          // first LevelNode of every level (+ end)
     std::vector<int> slot_of_node;      // CLV slot of every internal node (level path)
     int nslots = 0, max_arity = 0;
+    std::vector<int> lv_node_id;        // tree node of every LevelNode
+    std::vector<char> dirty;            // nodes whose CLV must be recomputed (partial re-evaluation)
+    bool all_dirty = true, partial_ok = false;
+    int last_nodes_recomputed = 0;
+    DevBuf<LevelNode> d_sel_nodes;
     // sequential (depth-first, deeper subtree first) schedule for the persistent dense kernel
     std::vector<LevelNode> sq_nodes;
     std::vector<LevelChild> sq_children;
@@ -235,6 +240,9 @@ int compile_tree(pb_ctx* c)
     for (int v : order) if (c->child_ptr[v] != c->child_ptr[v + 1]) internals.push_back(v);
     std::stable_sort(internals.begin(), internals.end(), [&](int a, int b) { return level[a] < level[b]; });
     c->lv_nodes.clear();
+    c->lv_node_id.clear();
+    c->dirty.assign(nn, 0);
+    c->all_dirty = true;
     c->lv_children.clear();
     c->lv_first.clear();
     c->slot_of_node.assign(nn, -1);
@@ -271,6 +279,7 @@ int compile_tree(pb_ctx* c)
                 c->lv_children.push_back(cd);
             }
             c->lv_nodes.push_back(nd);
+            c->lv_node_id.push_back(v);
         }
         if (!keep)
             for (size_t q = i; q < j; q++) {
@@ -485,13 +494,13 @@ int build_pmatrices(pb_ctx* c)
 }
 
 template <int N, bool MASKS>
-int launch_level_dense_m(pb_ctx* c, int first, int count, int store_root)
+int launch_level_dense_m(pb_ctx* c, const LevelNode* nodes, int first, int count, int store_root)
 {
     const size_t smem = (size_t)(N * N + N * 128) * sizeof(double);
     auto kern = pbk::level_dense<N, MASKS>;
     PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(c->spad / 128), count);
-    kern<<<grid, 128, smem, c->stream>>>(c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->ncat,
+    kern<<<grid, 128, smem, c->stream>>>(nodes, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->ncat,
                                          c->d_tips.p, c->d_masks.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
                                          c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root);
     c->launches++;
@@ -499,10 +508,10 @@ int launch_level_dense_m(pb_ctx* c, int first, int count, int store_root)
 }
 
 template <int N>
-int launch_level_dense(pb_ctx* c, int first, int count, int store_root)
+int launch_level_dense(pb_ctx* c, const LevelNode* nodes, int first, int count, int store_root)
 {
-    return c->have_masks ? launch_level_dense_m<N, true>(c, first, count, store_root)
-                         : launch_level_dense_m<N, false>(c, first, count, store_root);
+    return c->have_masks ? launch_level_dense_m<N, true>(c, nodes, first, count, store_root)
+                         : launch_level_dense_m<N, false>(c, nodes, first, count, store_root);
 }
 
 // Fused pruning of the site columns [site0, site1) (multiples of the tile size; the whole shard by default).
@@ -591,11 +600,36 @@ int run_pruning(pb_ctx* c)
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
     }
-    for (size_t l = 0; l + 1 < c->lv_first.size(); l++) {
-        const int first = c->lv_first[l], count = c->lv_first[l + 1] - first;
+    // What to (re)compute: every level, or — when only some branch lengths changed since the last
+    // evaluation and every CLV is resident (PB_FLAG_KEEP_CLV) — just the ancestors of those branches.
+    const LevelNode* lvn = c->d_lv_nodes.p;
+    std::vector<std::pair<int, int>> segments;      // (first, count) per launch, in level order
+    const bool partial = c->partial_ok && !c->all_dirty && (c->flags & PB_FLAG_KEEP_CLV) && c->evaluated;
+    if (!partial) {
+        for (size_t l = 0; l + 1 < c->lv_first.size(); l++)
+            segments.push_back({c->lv_first[l], c->lv_first[l + 1] - c->lv_first[l]});
+    } else {
+        std::vector<LevelNode> sel;
+        for (size_t l = 0; l + 1 < c->lv_first.size(); l++) {
+            const int begin = (int)sel.size();
+            for (int q = c->lv_first[l]; q < c->lv_first[l + 1]; q++)
+                if (c->dirty[c->lv_node_id[q]]) sel.push_back(c->lv_nodes[q]);
+            if ((int)sel.size() > begin) segments.push_back({begin, (int)sel.size() - begin});
+        }
+        PB_CUDA(c, c->d_sel_nodes.ensure(std::max<size_t>(sel.size(), 1)));
+        PB_CUDA(c, cudaMemcpyAsync(c->d_sel_nodes.p, sel.data(), sel.size() * sizeof(LevelNode), cudaMemcpyHostToDevice, c->stream));
+        lvn = c->d_sel_nodes.p;
+        c->last_nodes_recomputed = (int)sel.size();
+    }
+    if (!partial) c->last_nodes_recomputed = (int)c->lv_nodes.size();
+    std::fill(c->dirty.begin(), c->dirty.end(), 0);
+    c->all_dirty = false;
+    c->partial_ok = true;
+    for (const auto& seg : segments) {
+        const int first = seg.first, count = seg.second;
         if (path == PATH_LEVEL4) {
             dim3 grid((unsigned)((c->spad / 2 + 255) / 256), count, c->ncat);
-#define PB_LEVEL4_ARGS c->d_lv_nodes.p, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->d_tips.p, c->spad, \
+#define PB_LEVEL4_ARGS lvn, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->d_tips.p, c->spad, \
                        c->d_pool.p, c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,        \
                        c->d_site_cat.p, store_root
             switch (c->level4_minb) {
@@ -607,14 +641,14 @@ int run_pruning(pb_ctx* c)
 #undef PB_LEVEL4_ARGS
             c->launches++;
         } else if (path == PATH_LEVEL_DMMA && c->dmma_version == 2 && c->max_arity <= 2) {
-            int rc = pbk::launch_level_dmma2(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
+            int rc = pbk::launch_level_dmma2(n, lvn, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
                                              c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
                                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root,
                                              c->sm_count, c->smem_optin, c->stream);
             if (rc != 0) return fail(c, PB_ERR_CUDA, "level_dmma2 launch configuration failed");
             c->launches++;
         } else if (path == PATH_LEVEL_DMMA) {
-            int rc = pbk::launch_level_dmma(n, c->d_lv_nodes.p, c->d_lv_children.p, first, count, c->max_arity,
+            int rc = pbk::launch_level_dmma(n, lvn, c->d_lv_children.p, first, count, c->max_arity,
                                             c->d_P.p, c->nnodes, c->ncat, c->d_tips.p, c->spad, c->d_pool.p,
                                             c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,
                                             c->d_site_cat.p, store_root, c->sm_count, c->smem_optin, false, 0,
@@ -624,13 +658,13 @@ int run_pruning(pb_ctx* c)
         } else {
             int rc;
             switch (n) {
-            case 2: rc = launch_level_dense<2>(c, first, count, store_root); break;
-            case 3: rc = launch_level_dense<3>(c, first, count, store_root); break;
-            case 4: rc = launch_level_dense<4>(c, first, count, store_root); break;
-            case 5: rc = launch_level_dense<5>(c, first, count, store_root); break;
-            case 20: rc = launch_level_dense<20>(c, first, count, store_root); break;
-            case 61: rc = launch_level_dense<61>(c, first, count, store_root); break;
-            case 64: rc = launch_level_dense<64>(c, first, count, store_root); break;
+            case 2: rc = launch_level_dense<2>(c, lvn, first, count, store_root); break;
+            case 3: rc = launch_level_dense<3>(c, lvn, first, count, store_root); break;
+            case 4: rc = launch_level_dense<4>(c, lvn, first, count, store_root); break;
+            case 5: rc = launch_level_dense<5>(c, lvn, first, count, store_root); break;
+            case 20: rc = launch_level_dense<20>(c, lvn, first, count, store_root); break;
+            case 61: rc = launch_level_dense<61>(c, lvn, first, count, store_root); break;
+            case 64: rc = launch_level_dense<64>(c, lvn, first, count, store_root); break;
             default:
                 return fail(c, PB_ERR_INVALID_ARG, "nstates: compiled sizes are 2,3,4,5,20,61,64");
             }
@@ -766,6 +800,7 @@ int pb_set_mode(pb_ctx* c, int mode)
     if (mode == PB_MODE_PHYLO_CTMC) { c->threshold = 1e-6; c->shift_at_root = 1; }
     else if (mode == PB_MODE_FELSENSTEIN) { c->threshold = 0.0000001; c->shift_at_root = 0; }
     else return fail(c, PB_ERR_INVALID_ARG, "unknown mode");
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -774,6 +809,7 @@ int pb_set_rescaling(pb_ctx* c, double threshold, int shift_at_root)
     PB_ENTER(c);
     c->threshold = threshold;
     c->shift_at_root = shift_at_root ? 1 : 0;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -815,6 +851,7 @@ int pb_set_tree(pb_ctx* c, int nnodes, int root, const int32_t* child_ptr, const
     c->have_tree = true;
     c->have_blen = false;
     c->p_dirty = true;
+    c->all_dirty = true;
     if (c->psrc == PSRC_DIRECT) c->psrc = PSRC_NONE;   // matrices belonged to the old tree
     c->evaluated = false;
     int rc = compile_tree(c);
@@ -837,8 +874,25 @@ int pb_set_branch_lengths(pb_ctx* c, const double* bl)
     PB_CUDA(c, cudaMemcpyAsync(c->d_blen.p, c->branch_len.data(), c->nnodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->have_blen = true;
     c->p_dirty = true;
+    c->all_dirty = true;
     return PB_OK;
 }
+
+int pb_update_branch_length(pb_ctx* c, int node, double t)
+{
+    PB_ENTER(c);
+    if (!c->have_tree || !c->have_blen) return fail(c, PB_ERR_STATE, "set the tree and all branch lengths first");
+    if (node < 0 || node >= c->nnodes || node == c->root) return fail(c, PB_ERR_INVALID_ARG, "pb_update_branch_length: no such branch");
+    if (!(t >= 0.0)) return fail(c, PB_ERR_INVALID_ARG, "branch lengths must be >= 0");
+    if (c->psrc == PSRC_DIRECT) return fail(c, PB_ERR_STATE, "matrices were supplied directly: branch lengths are not in use");
+    c->branch_len[node] = t;
+    PB_CUDA(c, cudaMemcpyAsync(c->d_blen.p + node, &c->branch_len[node], sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->p_dirty = true;
+    for (int v = c->parent[node]; v >= 0; v = c->parent[v]) c->dirty[v] = 1;    // the path to the root
+    return PB_OK;
+}
+
+int pb_nodes_recomputed(const pb_ctx* c) { return c ? c->last_nodes_recomputed : 0; }
 
 static int alloc_tips(pb_ctx* c)
 {
@@ -861,6 +915,7 @@ int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
     c->have_masks = false;
     c->pack_dirty = true;
     c->tips_checked = false;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -876,6 +931,7 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     c->have_masks = false;
     c->pack_dirty = true;
     c->tips_checked = false;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -892,6 +948,7 @@ int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_masks = true;
     c->have_tips = true;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -903,6 +960,7 @@ int pb_set_root_frequencies(pb_ctx* c, const double* pi)
     PB_CUDA(c, cudaMemcpyAsync(c->d_pi.p, pi, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_pi = true;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -918,6 +976,7 @@ int pb_set_categories(pb_ctx* c, const double* rates, const double* weights)
     PB_CUDA(c, cudaMemcpyAsync(c->d_weights.p, c->h_weights.data(), c->ncat * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->p_dirty = true;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -938,6 +997,7 @@ int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const d
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->psrc = PSRC_EIGEN;
     c->p_dirty = true;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -972,6 +1032,7 @@ int pb_set_rate_matrix_general(pb_ctx* c, const double* Q)
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->psrc = PSRC_EXPM;
     c->p_dirty = true;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -989,6 +1050,7 @@ int pb_set_pmatrices(pb_ctx* c, const double* P)
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->psrc = PSRC_DIRECT;
     c->p_dirty = false;
+    c->all_dirty = true;
     return PB_OK;
 }
 
@@ -1093,6 +1155,7 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
     c->have_masks = false;
     c->pack_dirty = false;
     c->tips_checked = true;
+    c->all_dirty = true;
     c->evaluated = true;
     return pb_loglik_fetch(c, total, per_site);
 }

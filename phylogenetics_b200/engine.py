@@ -91,6 +91,14 @@ class LikelihoodContext:
             raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "branch_lengths must have nnodes entries")
         self._ck(lib.pb_set_branch_lengths(self._ctx, bl.ctypes.data))
 
+    def update_branch_length(self, node, t):
+        """Change one branch length; with keep_clv the next evaluation only redoes the path to the root."""
+        self._ck(lib.pb_update_branch_length(self._ctx, int(node), float(t)))
+
+    @property
+    def nodes_recomputed(self):
+        return int(lib.pb_nodes_recomputed(self._ctx))
+
     def set_tips(self, states):
         """states: uint8 [ntaxa][>=nsites] host array (numpy, or a pinned torch tensor's numpy view)."""
         states = np.asarray(states)

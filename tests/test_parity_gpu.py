@@ -268,3 +268,38 @@ def test_pipelined_host_evaluation(nsites, chunks):
     with run_ctx(case, "direct", level=True, P=P) as ctx:
         total3, per_site3 = ctx.loglik_host(case.tips, per_site=True)
         check(per_site3, total3, expect)
+
+
+@pytest.mark.parametrize("model,ntaxa,nsites,ncat", [("gtr", 60, 3000, 4), ("wag", 20, 700, 1)])
+def test_partial_reevaluation_after_one_branch_change(model, ntaxa, nsites, ncat):
+    """f2: with the CLVs resident, changing one branch length recomputes only the path
+    from that branch to the root; the result equals a full evaluation and the oracle."""
+    case = cases.make_case("partial" + model, model, ntaxa, nsites, ncat=ncat, seed=31)
+    f = case.flat
+    rng = np.random.default_rng(2)
+    with run_ctx(case, "eigen", keep=True) as ctx, run_ctx(case, "eigen") as full:
+        ctx.loglik()
+        assert ctx.nodes_recomputed == f.ninternal
+        bl = case.bl.copy()
+        for _ in range(4):
+            v = int(rng.integers(1, f.nnodes))
+            bl[v] = float(rng.uniform(0.01, 0.6))
+            ctx.update_branch_length(v, bl[v])
+            total, per_site = ctx.loglik(per_site=True)
+            depth = 0
+            u = v
+            parent = {int(c): p for p in range(f.nnodes) for c in f.children(p)}
+            while u in parent:
+                u = parent[u]
+                depth += 1
+            assert ctx.nodes_recomputed == depth < f.ninternal
+            full.set_branch_lengths(bl)
+            t2, ps2 = full.loglik(per_site=True)
+            np.testing.assert_allclose(per_site, ps2, rtol=1e-12)
+            P = ctx.get_pmatrices()
+            case2 = cases.Case("p", f, bl, case.Q, case.pi, case.tips, case.rates, case.weights)
+            check(per_site, total, oracle_per_site(case2, P))
+        # an unrelated change invalidates everything
+        ctx.set_categories(case.rates, case.weights)
+        ctx.loglik()
+        assert ctx.nodes_recomputed == f.ninternal
