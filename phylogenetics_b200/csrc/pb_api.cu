@@ -101,6 +101,13 @@ struct pb_ctx {
     DevBuf<FusedOp2> d_fprog;
     DevBuf<int> d_tip_order;
     DevBuf<uint8_t> d_is_leaf;
+    // fused4c: inner-branch matrices through constant memory
+    std::vector<FusedOp2> fprog_c;
+    std::vector<int> inner_nodes, leaf_nodes;
+    DevBuf<FusedOp2> d_fprog_c;
+    DevBuf<int> d_inner_nodes, d_leaf_nodes;
+    DevBuf<double> d_Pc;
+    int fused_const = 1;                // option "fused_const": use fused4c when the tree has <= 128 inner branches
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
@@ -441,6 +448,25 @@ int compile_tree(pb_ctx* c)
             folded.push_back(o);
         }
         c->fprog.swap(folded);
+        // fused4c addressing: inner matrices by compact index into constant memory, leaf matrices by
+        // compact index into shared memory
+        c->inner_nodes.clear();
+        c->leaf_nodes.clear();
+        std::vector<int> compact(nn, -1);
+        for (int v = 0; v < nn; v++) {
+            if (v == c->root) continue;
+            if (is_inner(v)) { compact[v] = (int)c->inner_nodes.size(); c->inner_nodes.push_back(v); }
+            else { compact[v] = (int)c->leaf_nodes.size(); c->leaf_nodes.push_back(v); }
+        }
+        c->fprog_c = c->fprog;
+        for (FusedOp2& o : c->fprog_c) {
+            const int code = o.code & 0xff;
+            const bool usesA = code == pbk::FOP_TIP_TIP || code == pbk::FOP_TIP || code == pbk::FOP_MUL_TIP ||
+                               code == pbk::FOP_APPLY || code == pbk::FOP_APPLY_MUL_TIP || code == pbk::FOP_ACC_POP;
+            const bool usesB = code == pbk::FOP_TIP_TIP || code == pbk::FOP_APPLY_MUL_TIP || code == pbk::FOP_ACC_POP;
+            if (usesA) o.offA = compact[o.offA / 16] * 16;
+            if (usesB) o.offB = compact[o.offB / 16] * 16;
+        }
     }
     c->pack_dirty = true;
 
@@ -461,6 +487,12 @@ int compile_tree(pb_ctx* c)
         PB_CUDA(c, c->d_is_leaf.ensure(nn));
         PB_CUDA(c, cudaMemcpy(c->d_is_leaf.p, leaf.data(), nn, cudaMemcpyHostToDevice));
     }
+    PB_CUDA(c, c->d_fprog_c.ensure(c->fprog_c.size()));
+    PB_CUDA(c, c->d_inner_nodes.ensure(std::max<size_t>(c->inner_nodes.size(), 1)));
+    PB_CUDA(c, c->d_leaf_nodes.ensure(std::max<size_t>(c->leaf_nodes.size(), 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_c.p, c->fprog_c.data(), c->fprog_c.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_inner_nodes.p, c->inner_nodes.data(), c->inner_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_leaf_nodes.p, c->leaf_nodes.data(), c->leaf_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, c->d_tip_order.ensure(c->tip_order.size()));
     PB_CUDA(c, cudaMemcpyAsync(c->d_tip_order.p, c->tip_order.data(), c->tip_order.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -535,8 +567,71 @@ int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
     return PB_OK;
 }
 
+template <int BLOCK, int SPT, int BUF>
+int launch_fused4c_variant(pb_ctx* c, int cat, int64_t site0, int64_t site1)
+{
+    auto kern = pbk::fused4c<BLOCK, SPT, false, BUF>;
+    const size_t smem = (size_t)c->leaf_nodes.size() * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * BLOCK * SPT * 8 +
+                        c->fprog_c.size() * sizeof(FusedOp2);
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+    if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4c: kernel does not fit on an SM");
+    const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * occ, ntiles));
+    kern<<<(unsigned)gx, BLOCK, smem, c->stream>>>(c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1),
+                                                   c->d_P.p, c->d_leaf_nodes.p, (int)c->leaf_nodes.size(), c->nnodes,
+                                                   cat, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
+                                                   c->shift_at_root, c->d_site_cat.p);
+    c->launches++;
+    return PB_OK;
+}
+
+bool fused_const_ok(const pb_ctx* c)
+{
+    return c->fused_const && !c->fused_exact_log && (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS &&
+           (c->fused_spt == 1 || c->fused_spt == 2) && (c->fused_block == 256 || c->fused_block == 512);
+}
+
+// One launch per category; the category's inner matrices travel device -> constant bank in stream order.
+int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
+{
+    if (regather) {
+        PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * pbk::FUSED_CONST_MATS * 16));
+        pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_inner_nodes.p, (int)c->inner_nodes.size(),
+                                                                     c->nnodes, c->d_Pc.p);
+        c->launches++;
+    }
+    const size_t bytes = (size_t)pbk::FUSED_CONST_MATS * 16 * sizeof(double);
+    for (int cat = 0; cat < c->ncat; cat++) {
+        const int buf = cat & 1;
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat * pbk::FUSED_CONST_MATS * 16, bytes,
+                                           buf * bytes, cudaMemcpyDeviceToDevice, c->stream));
+        int rc;
+        const int key = c->fused_block * 10 + c->fused_spt;
+        if (buf == 0) {
+            switch (key) {
+            case 2562: rc = launch_fused4c_variant<256, 2, 0>(c, cat, site0, site1); break;
+            case 5121: rc = launch_fused4c_variant<512, 1, 0>(c, cat, site0, site1); break;
+            case 5122: rc = launch_fused4c_variant<512, 2, 0>(c, cat, site0, site1); break;
+            default: rc = launch_fused4c_variant<256, 1, 0>(c, cat, site0, site1); break;
+            }
+        } else {
+            switch (key) {
+            case 2562: rc = launch_fused4c_variant<256, 2, 1>(c, cat, site0, site1); break;
+            case 5121: rc = launch_fused4c_variant<512, 1, 1>(c, cat, site0, site1); break;
+            case 5122: rc = launch_fused4c_variant<512, 2, 1>(c, cat, site0, site1); break;
+            default: rc = launch_fused4c_variant<256, 1, 1>(c, cat, site0, site1); break;
+            }
+        }
+        if (rc != PB_OK) return rc;
+    }
+    return PB_OK;
+}
+
 int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
 {
+    if (fused_const_ok(c)) return launch_fused4c(c, site0, site1, site0 == 0);
     const int key = c->fused_block * 10 + c->fused_spt;
     if (c->fused_exact_log) {
         switch (key) {
@@ -1248,6 +1343,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_spt") {
         if (iv != 1 && iv != 2 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1, 2 or 4");
         c->fused_spt = iv;
+    } else if (k == "fused_const") {
+        c->fused_const = iv != 0;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
     } else if (k == "level4_min_blocks") {
@@ -1269,7 +1366,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else {
         return fail(c, PB_ERR_INVALID_ARG, "unknown option: " + k);
     }
-    if (c->fused_block == 512 && c->fused_spt > 1) c->fused_spt = 1;
+    if (c->fused_block == 512 && c->fused_spt > 1 && !c->fused_const) c->fused_spt = 1;
     if (c->fused_block == 256 && c->fused_spt == 4 && c->fused_exact_log) c->fused_spt = 2;
     return PB_OK;
 }

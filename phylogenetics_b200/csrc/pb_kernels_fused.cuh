@@ -315,4 +315,186 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     }
 }
 
+// --------------------------------------------------------------------------
+// fused4c: the same traversal with the INNER-branch matrices in constant memory.
+//
+// ncu on fused4 (profiles/r01c_ncu_full_fused4_v5_variants.txt) shows the LSU data pipe at 92 % of
+// peak: broadcasting a 128-byte matrix from shared memory to the 32 lanes of a warp costs 32 lanes x
+// 128 B of register-write bandwidth, whatever the bank pattern.  The instruction stream is uniform,
+// so the matrix address is warp-uniform: from the constant bank the 16 doubles go to UNIFORM
+// registers once per warp (LDCU) and the DFMA/DMUL take them as uniform operands - no per-lane
+// traffic at all.  Leaf-branch matrices are looked up with a per-lane column index, which the
+// constant path would serialise, so they stay in shared memory (transposed).
+// One launch per rate category; the category's <= 128 inner matrices (16 KB) are copied into one of
+// two constant buffers, device to device, in stream order.
+// --------------------------------------------------------------------------
+constexpr int FUSED_CONST_MATS = 128;
+__constant__ double cPinner[2][FUSED_CONST_MATS * 16];
+
+// d_Pc[c][k][16] = P[c][inner_nodes[k]][16]
+__global__ void gather_inner_p(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
+                               int nnodes, double* __restrict__ Pc)
+{
+    const int c = blockIdx.y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ninner * 16; idx += gridDim.x * blockDim.x)
+        Pc[((size_t)c * FUSED_CONST_MATS + (idx >> 4)) * 16 + (idx & 15)] =
+            P[((size_t)c * nnodes + inner_nodes[idx >> 4]) * 16 + (idx & 15)];
+}
+
+template <int BUF>
+__device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (&y)[4])
+{
+    const double* m = cPinner[BUF] + off;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double a = m[i * 4 + 0] * x[0];
+        a = fma(m[i * 4 + 1], x[1], a);
+        a = fma(m[i * 4 + 2], x[2], a);
+        a = fma(m[i * 4 + 3], x[3], a);
+        y[i] = a;
+    }
+}
+
+// prog: offsets of inner matrices index cPinner (compact inner index * 16); offsets of leaf matrices
+// index the shared-memory array of the ntips leaf matrices (compact leaf index * 16).
+template <int BLOCK, int SPT, bool EXACT_LOG, int BUF>
+__global__ void __launch_bounds__(BLOCK)
+fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
+        const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat,
+        const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
+        const double* __restrict__ pi, double thr, int shift_at_root,
+        double* __restrict__ site_cat)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                                       // [nleaf][16], transposed, of this category
+    double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shS + (size_t)stack_depth * 4 * BLOCK * SPT);
+    const int c = cat, tid = threadIdx.x;
+    {
+        const double* Pg = P + (size_t)c * nnodes * 16;
+        for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
+            const int k = idx >> 4, e = idx & 15;
+            shP[k * 16 + (e & 3) * 4 + (e >> 2)] = Pg[(size_t)leaf_nodes[k] * 16 + e];
+        }
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
+        for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
+    }
+    __syncthreads();
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(shP);
+    double pir[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) pir[i] = pi[i];
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t s0 = (tile0 + tile) * (BLOCK * SPT) + tid;
+        double v[SPT][4];
+        Scale<EXACT_LOG> sc[SPT];
+        uint64_t cur[SPT], nxt[SPT];
+        const uint64_t* pk = packed + s0;
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            sc[q].init();
+            cur[q] = pk[q * BLOCK];
+            nxt[q] = pk[spad + q * BLOCK];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[q][i] = 1.0;
+        }
+        pk += 2 * spad;
+        double* st = shS + tid;
+        const int4* opp = reinterpret_cast<const int4*>(shOps);
+        for (int ip = 0; ip < nops; ip++) {
+            const int4 opw = opp[ip];
+            const int offA = opw.y, offB = opw.z;
+            const int shA = opw.w & 0xff, shB = opw.w >> 8;
+            const int code = opw.x & 0xff;
+            if (code == FOP_APPLY_MUL_TIP) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4], t[4];
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
+                    matvec4c<BUF>(offA, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
+                }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
+            } else if (code == FOP_ACC_POP) {
+                st -= 4 * BLOCK * SPT;
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double x[4], y[4], z[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+                    matvec4c<BUF>(offA, v[q], y);
+                    matvec4c<BUF>(offB, x, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
+                }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
+            } else if (code == FOP_TIP_TIP) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double a[4], b[4];
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, a);
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, b);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = a[i] * b[i];
+                }
+                shift_all<SPT, EXACT_LOG>(v, sc, thr);
+            } else if (code == FOP_LOADW) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    cur[q] = nxt[q];
+                    nxt[q] = pk[q * BLOCK];
+                }
+                pk += spad;
+            } else if (code == FOP_TIP) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, v[q]);
+            } else if (code == FOP_APPLY) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4];
+                    matvec4c<BUF>(offA, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i];
+                }
+            } else if (code == FOP_MUL_TIP) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double t[4];
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, t);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } else if (code == FOP_POP_MUL) {
+                st -= 4 * BLOCK * SPT;
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = st[(i * SPT + q) * BLOCK] * v[q][i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } else if (code == FOP_ROOT) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
+                    if (shift_at_root) shift4s(v[q], sc[q], thr);
+                    const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
+                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                }
+            }
+            if (opw.x & FOP_PUSH_AFTER) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                st += 4 * BLOCK * SPT;
+            }
+        }
+    }
+}
+
 }  // namespace pbk

@@ -193,6 +193,7 @@ def test_fused_variants(block, spt, exact):
     case = cases.make_case("fusedv", "gtr", 97, 3001, ncat=2, seed=3)
     P = case.host_P()
     with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("fused_const", 0)
         ctx.set_option("fused_block", block)
         ctx.set_option("fused_spt", spt)
         ctx.set_option("fused_exact_log", exact)
@@ -303,3 +304,21 @@ def test_partial_reevaluation_after_one_branch_change(model, ntaxa, nsites, ncat
         ctx.set_categories(case.rates, case.weights)
         ctx.loglik()
         assert ctx.nodes_recomputed == f.ninternal
+
+
+@pytest.mark.parametrize("block,spt", [(256, 1), (256, 2), (512, 1), (512, 2)])
+@pytest.mark.parametrize("ntaxa,ncat", [(97, 3), (129, 1), (130, 2), (12, 4)])
+def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
+    """fused4c (inner-branch matrices through the constant bank, one launch per category): trees with
+    up to 128 inner branches use it, larger ones fall back to the shared-memory kernel."""
+    case = cases.make_case("fusedc", "gtr", ntaxa, 2500, ncat=ncat, seed=4)
+    P = case.host_P()
+    with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("fused_const", 1)
+        ctx.set_option("fused_block", block)
+        ctx.set_option("fused_spt", spt)
+        assert ctx.path_name == "fused4"
+        total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, oracle_per_site(case, P))
+        total2 = ctx.loglik_host(case.tips)
+        assert total2 == total

@@ -16,7 +16,9 @@ case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
 out = []
 ref = None
-for block, spt, exact in [(128, 1, 0), (256, 1, 0), (512, 1, 0), (128, 2, 0), (256, 2, 0), (128, 4, 0), (256, 4, 0), (256, 1, 1), (256, 2, 1), ("level", 3, 0), ("level", 4, 0), ("level", 5, 0), ("level", 6, 0)]:
+VARIANTS = [(256, 1, 0, 1), (256, 2, 0, 1), (512, 1, 0, 1), (512, 2, 0, 1), (256, 1, 0, 0), (256, 2, 0, 0), (512, 1, 0, 0),
+            (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0)]
+for block, spt, exact, const in VARIANTS:
     level = block == "level"
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4, level_kernels=level) as ctx:
         ctx.set_tree(f, case.bl)
@@ -27,6 +29,7 @@ for block, spt, exact in [(128, 1, 0), (256, 1, 0), (512, 1, 0), (128, 2, 0), (2
         if level:
             ctx.set_option("level4_min_blocks", spt)
         else:
+            ctx.set_option("fused_const", const)
             ctx.set_option("fused_block", block)
             ctx.set_option("fused_spt", spt)
             ctx.set_option("fused_exact_log", exact)
@@ -37,7 +40,7 @@ for block, spt, exact in [(128, 1, 0), (256, 1, 0), (512, 1, 0), (128, 2, 0), (2
             ms.append(ctx.get_timing()[1])
         if ref is None:
             ref = tot
-        rec = {"variant": "%sx%s exact=%d" % (block, spt, exact), "path": ctx.path_name,
+        rec = {"variant": "%sx%s exact=%d const=%d" % (block, spt, exact, const), "path": ctx.path_name,
                "pruning_ms_min": min(ms[1:]), "pruning_ms_first": ms[0], "total": tot,
                "rel_vs_first": abs(tot - ref) / abs(ref)}
         print(json.dumps(rec), flush=True)
