@@ -95,7 +95,7 @@ struct pb_ctx {
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
-    int fused_block = 256, fused_spt = 1, fused_exact_log = 0;
+    int fused_block = 256, fused_spt = 2, fused_exact_log = 0;
     DevBuf<LevelNode> d_lv_nodes;
     DevBuf<LevelChild> d_lv_children;
     DevBuf<FusedOp2> d_fprog;
@@ -590,7 +590,7 @@ int launch_fused4c_variant(pb_ctx* c, int cat, int64_t site0, int64_t site1)
 bool fused_const_ok(const pb_ctx* c)
 {
     return c->fused_const && !c->fused_exact_log && (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS &&
-           (c->fused_spt == 1 || c->fused_spt == 2) && (c->fused_block == 256 || c->fused_block == 512);
+           !(c->fused_block == 512 && c->fused_spt == 4) && !(c->fused_block == 128 && c->fused_spt == 1);
 }
 
 // One launch per category; the category's inner matrices travel device -> constant bank in stream order.
@@ -612,6 +612,9 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
         if (buf == 0) {
             switch (key) {
             case 2562: rc = launch_fused4c_variant<256, 2, 0>(c, cat, site0, site1); break;
+            case 2564: rc = launch_fused4c_variant<256, 4, 0>(c, cat, site0, site1); break;
+            case 1282: rc = launch_fused4c_variant<128, 2, 0>(c, cat, site0, site1); break;
+            case 1284: rc = launch_fused4c_variant<128, 4, 0>(c, cat, site0, site1); break;
             case 5121: rc = launch_fused4c_variant<512, 1, 0>(c, cat, site0, site1); break;
             case 5122: rc = launch_fused4c_variant<512, 2, 0>(c, cat, site0, site1); break;
             default: rc = launch_fused4c_variant<256, 1, 0>(c, cat, site0, site1); break;
@@ -619,6 +622,9 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
         } else {
             switch (key) {
             case 2562: rc = launch_fused4c_variant<256, 2, 1>(c, cat, site0, site1); break;
+            case 2564: rc = launch_fused4c_variant<256, 4, 1>(c, cat, site0, site1); break;
+            case 1282: rc = launch_fused4c_variant<128, 2, 1>(c, cat, site0, site1); break;
+            case 1284: rc = launch_fused4c_variant<128, 4, 1>(c, cat, site0, site1); break;
             case 5121: rc = launch_fused4c_variant<512, 1, 1>(c, cat, site0, site1); break;
             case 5122: rc = launch_fused4c_variant<512, 2, 1>(c, cat, site0, site1); break;
             default: rc = launch_fused4c_variant<256, 1, 1>(c, cat, site0, site1); break;
@@ -1368,6 +1374,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     }
     if (c->fused_block == 512 && c->fused_spt > 1 && !c->fused_const) c->fused_spt = 1;
     if (c->fused_block == 256 && c->fused_spt == 4 && c->fused_exact_log) c->fused_spt = 2;
+    if (c->fused_block == 512 && c->fused_spt == 4) c->fused_spt = 2;
     return PB_OK;
 }
 

@@ -16,7 +16,7 @@ case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
 out = []
 ref = None
-VARIANTS = [(256, 1, 0, 1), (256, 2, 0, 1), (512, 1, 0, 1), (512, 2, 0, 1), (256, 1, 0, 0), (256, 2, 0, 0), (512, 1, 0, 0),
+VARIANTS = [(256, 1, 0, 1), (256, 2, 0, 1), (512, 1, 0, 1), (512, 2, 0, 1), (128, 2, 0, 1), (128, 4, 0, 1), (256, 4, 0, 1), (256, 1, 0, 0), (256, 2, 0, 0), (512, 1, 0, 0),
             (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0)]
 for block, spt, exact, const in VARIANTS:
     level = block == "level"
