@@ -567,10 +567,10 @@ int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
     return PB_OK;
 }
 
-template <int BLOCK, int SPT, int BUF>
-int launch_fused4c_variant(pb_ctx* c, int cat, int64_t site0, int64_t site1)
+template <int BLOCK, int SPT>
+int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_t site1)
 {
-    auto kern = pbk::fused4c<BLOCK, SPT, false, BUF>;
+    auto kern = pbk::fused4c<BLOCK, SPT, false>;
     const size_t smem = (size_t)c->leaf_nodes.size() * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * BLOCK * SPT * 8 +
                         c->fprog_c.size() * sizeof(FusedOp2);
     PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -578,57 +578,48 @@ int launch_fused4c_variant(pb_ctx* c, int cat, int64_t site0, int64_t site1)
     PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
     if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4c: kernel does not fit on an SM");
     const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
-    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * occ, ntiles));
-    kern<<<(unsigned)gx, BLOCK, smem, c->stream>>>(c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1),
-                                                   c->d_P.p, c->d_leaf_nodes.p, (int)c->leaf_nodes.size(), c->nnodes,
-                                                   cat, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
-                                                   c->shift_at_root, c->d_site_cat.p);
+    int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
+    gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
+    kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
+        c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
+        (int)c->leaf_nodes.size(), c->nnodes, cat0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
+        c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p);
     c->launches++;
     return PB_OK;
 }
 
 bool fused_const_ok(const pb_ctx* c)
 {
-    return c->fused_const && !c->fused_exact_log && (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS &&
+    return c->fused_const && !c->fused_exact_log && !c->inner_nodes.empty() &&
+           (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS &&
            !(c->fused_block == 512 && c->fused_spt == 4) && !(c->fused_block == 128 && c->fused_spt == 1);
 }
 
-// One launch per category; the category's inner matrices travel device -> constant bank in stream order.
+// The inner matrices of as many categories as the constant bank holds per launch.
 int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
 {
+    const int ninner = (int)c->inner_nodes.size();
     if (regather) {
-        PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * pbk::FUSED_CONST_MATS * 16));
-        pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_inner_nodes.p, (int)c->inner_nodes.size(),
-                                                                     c->nnodes, c->d_Pc.p);
+        PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * ninner * 16));
+        pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_inner_nodes.p, ninner, c->nnodes,
+                                                                     c->d_Pc.p);
         c->launches++;
     }
-    const size_t bytes = (size_t)pbk::FUSED_CONST_MATS * 16 * sizeof(double);
-    for (int cat = 0; cat < c->ncat; cat++) {
-        const int buf = cat & 1;
-        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat * pbk::FUSED_CONST_MATS * 16, bytes,
-                                           buf * bytes, cudaMemcpyDeviceToDevice, c->stream));
+    const int per_launch = std::max(1, std::min(c->ncat, pbk::FUSED_CONST_MATS / ninner));
+    for (int cat0 = 0; cat0 < c->ncat; cat0 += per_launch) {
+        const int k = std::min(per_launch, c->ncat - cat0);
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat0 * ninner * 16,
+                                           (size_t)k * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
+                                           c->stream));
         int rc;
-        const int key = c->fused_block * 10 + c->fused_spt;
-        if (buf == 0) {
-            switch (key) {
-            case 2562: rc = launch_fused4c_variant<256, 2, 0>(c, cat, site0, site1); break;
-            case 2564: rc = launch_fused4c_variant<256, 4, 0>(c, cat, site0, site1); break;
-            case 1282: rc = launch_fused4c_variant<128, 2, 0>(c, cat, site0, site1); break;
-            case 1284: rc = launch_fused4c_variant<128, 4, 0>(c, cat, site0, site1); break;
-            case 5121: rc = launch_fused4c_variant<512, 1, 0>(c, cat, site0, site1); break;
-            case 5122: rc = launch_fused4c_variant<512, 2, 0>(c, cat, site0, site1); break;
-            default: rc = launch_fused4c_variant<256, 1, 0>(c, cat, site0, site1); break;
-            }
-        } else {
-            switch (key) {
-            case 2562: rc = launch_fused4c_variant<256, 2, 1>(c, cat, site0, site1); break;
-            case 2564: rc = launch_fused4c_variant<256, 4, 1>(c, cat, site0, site1); break;
-            case 1282: rc = launch_fused4c_variant<128, 2, 1>(c, cat, site0, site1); break;
-            case 1284: rc = launch_fused4c_variant<128, 4, 1>(c, cat, site0, site1); break;
-            case 5121: rc = launch_fused4c_variant<512, 1, 1>(c, cat, site0, site1); break;
-            case 5122: rc = launch_fused4c_variant<512, 2, 1>(c, cat, site0, site1); break;
-            default: rc = launch_fused4c_variant<256, 1, 1>(c, cat, site0, site1); break;
-            }
+        switch (c->fused_block * 10 + c->fused_spt) {
+        case 2562: rc = launch_fused4c_variant<256, 2>(c, cat0, k, site0, site1); break;
+        case 2564: rc = launch_fused4c_variant<256, 4>(c, cat0, k, site0, site1); break;
+        case 1282: rc = launch_fused4c_variant<128, 2>(c, cat0, k, site0, site1); break;
+        case 1284: rc = launch_fused4c_variant<128, 4>(c, cat0, k, site0, site1); break;
+        case 5121: rc = launch_fused4c_variant<512, 1>(c, cat0, k, site0, site1); break;
+        case 5122: rc = launch_fused4c_variant<512, 2>(c, cat0, k, site0, site1); break;
+        default: rc = launch_fused4c_variant<256, 1>(c, cat0, k, site0, site1); break;
         }
         if (rc != PB_OK) return rc;
     }

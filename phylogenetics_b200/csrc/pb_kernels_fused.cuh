@@ -325,26 +325,27 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
 // registers once per warp (LDCU) and the DFMA/DMUL take them as uniform operands - no per-lane
 // traffic at all.  Leaf-branch matrices are looked up with a per-lane column index, which the
 // constant path would serialise, so they stay in shared memory (transposed).
-// One launch per rate category; the category's <= 128 inner matrices (16 KB) are copied into one of
-// two constant buffers, device to device, in stream order.
+// The constant bank (64 KB) holds the inner matrices of as many rate categories as fit (4 categories
+// of a 128-taxon tree: 4 x 127 x 128 B = 65 024 B); one launch covers those categories
+// (blockIdx.y), further categories take further launches.  The matrices travel device -> constant
+// bank in stream order (cudaMemcpyToSymbolAsync, device to device).
 // --------------------------------------------------------------------------
-constexpr int FUSED_CONST_MATS = 128;
-__constant__ double cPinner[2][FUSED_CONST_MATS * 16];
+constexpr int FUSED_CONST_MATS = 508;              // 65 024 bytes: all the user constant bank but 512 bytes
+__constant__ double cPinner[FUSED_CONST_MATS * 16];
 
-// d_Pc[c][k][16] = P[c][inner_nodes[k]][16]
+// d_Pc[c][k][16] = P[c][inner_nodes[k]][16]   (categories packed back to back: ninner matrices each)
 __global__ void gather_inner_p(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
                                int nnodes, double* __restrict__ Pc)
 {
     const int c = blockIdx.y;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ninner * 16; idx += gridDim.x * blockDim.x)
-        Pc[((size_t)c * FUSED_CONST_MATS + (idx >> 4)) * 16 + (idx & 15)] =
+        Pc[((size_t)c * ninner + (idx >> 4)) * 16 + (idx & 15)] =
             P[((size_t)c * nnodes + inner_nodes[idx >> 4]) * 16 + (idx & 15)];
 }
 
-template <int BUF>
 __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (&y)[4])
 {
-    const double* m = cPinner[BUF] + off;
+    const double* m = cPinner + off;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         double a = m[i * 4 + 0] * x[0];
@@ -357,10 +358,10 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
 
 // prog: offsets of inner matrices index cPinner (compact inner index * 16); offsets of leaf matrices
 // index the shared-memory array of the ntips leaf matrices (compact leaf index * 16).
-template <int BLOCK, int SPT, bool EXACT_LOG, int BUF>
+template <int BLOCK, int SPT, bool EXACT_LOG>
 __global__ void __launch_bounds__(BLOCK)
 fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
-        const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat,
+        const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int ninner,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
         double* __restrict__ site_cat)
@@ -369,7 +370,8 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     double* shP = sh;                                       // [nleaf][16], transposed, of this category
     double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
     FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shS + (size_t)stack_depth * 4 * BLOCK * SPT);
-    const int c = cat, tid = threadIdx.x;
+    const int c = cat0 + blockIdx.y, tid = threadIdx.x;     // this launch covers categories cat0 .. cat0 + gridDim.y - 1
+    const int cbase = blockIdx.y * ninner * 16;             // where this category's inner matrices sit in cPinner
     {
         const double* Pg = P + (size_t)c * nnodes * 16;
         for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
@@ -413,7 +415,7 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                 for (int q = 0; q < SPT; q++) {
                     double y[4], t[4];
                     lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
-                    matvec4c<BUF>(offA, v[q], y);
+                    matvec4c(cbase + offA, v[q], y);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
                 }
@@ -425,8 +427,8 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     double x[4], y[4], z[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
-                    matvec4c<BUF>(offA, v[q], y);
-                    matvec4c<BUF>(offB, x, z);
+                    matvec4c(cbase + offA, v[q], y);
+                    matvec4c(cbase + offB, x, z);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
                 }
@@ -455,7 +457,7 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
-                    matvec4c<BUF>(offA, v[q], y);
+                    matvec4c(cbase + offA, v[q], y);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i];
                 }

@@ -306,8 +306,8 @@ def test_partial_reevaluation_after_one_branch_change(model, ntaxa, nsites, ncat
         assert ctx.nodes_recomputed == f.ninternal
 
 
-@pytest.mark.parametrize("block,spt", [(256, 1), (256, 2), (512, 1), (512, 2)])
-@pytest.mark.parametrize("ntaxa,ncat", [(97, 3), (129, 1), (130, 2), (12, 4)])
+@pytest.mark.parametrize("block,spt", [(256, 1), (256, 2), (512, 2), (128, 4)])
+@pytest.mark.parametrize("ntaxa,ncat", [(97, 3), (128, 4), (130, 4), (300, 3), (12, 4)])
 def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
     """fused4c (inner-branch matrices through the constant bank, one launch per category): trees with
     up to 128 inner branches use it, larger ones fall back to the shared-memory kernel."""
@@ -322,3 +322,13 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
         check(per_site, total, oracle_per_site(case, P))
         total2 = ctx.loglik_host(case.tips)
         assert total2 == total
+
+
+def test_fused_large_tree_falls_back_to_shared_memory_matrices():
+    """More than 508 inner branches do not fit the constant bank: the shared-memory kernel takes over."""
+    case = cases.make_case("fusedbig", "gtr", 600, 700, ncat=1, seed=4)
+    P = case.host_P()
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name == "fused4"
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P))
