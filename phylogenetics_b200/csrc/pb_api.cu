@@ -107,6 +107,7 @@ struct pb_ctx {
     DevBuf<FusedOp2> d_fprog_c;
     DevBuf<int> d_inner_nodes, d_leaf_nodes;
     DevBuf<double> d_Pc;
+    int fused_const_cats = 1;           // option "fused_const_cats": categories per fused4c launch
     int fused_const = 1;                // option "fused_const": use fused4c when the tree has <= 128 inner branches
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
@@ -591,7 +592,8 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_
 bool fused_const_ok(const pb_ctx* c)
 {
     return c->fused_const && !c->fused_exact_log && !c->inner_nodes.empty() &&
-           (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS &&
+           (int)c->inner_nodes.size() * c->fused_const_cats <= pbk::FUSED_CONST_MATS &&
+           (int)c->inner_nodes.size() <= 128 &&
            !(c->fused_block == 512 && c->fused_spt == 4) && !(c->fused_block == 128 && c->fused_spt == 1);
 }
 
@@ -605,9 +607,12 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
                                                                      c->d_Pc.p);
         c->launches++;
     }
-    const int per_launch = std::max(1, std::min(c->ncat, pbk::FUSED_CONST_MATS / ninner));
+    // One category per launch: with several categories resident on an SM their 16 KB matrix sets evict
+    // each other from the constant cache (measured: 4 categories per launch is slower, see
+    // profiles/r01f_sweep_c2_fused4c.jsonl); per-category launches keep every block of an SM on one set.
+    const int per_launch = c->fused_const_cats;
     for (int cat0 = 0; cat0 < c->ncat; cat0 += per_launch) {
-        const int k = std::min(per_launch, c->ncat - cat0);
+        const int k = std::min(per_launch, c->ncat - cat0);          // (the last launch may hold fewer)
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat0 * ninner * 16,
                                            (size_t)k * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
                                            c->stream));
@@ -1340,6 +1345,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_spt") {
         if (iv != 1 && iv != 2 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1, 2 or 4");
         c->fused_spt = iv;
+    } else if (k == "fused_const_cats") {
+        if (iv < 1 || iv > 8) return fail(c, PB_ERR_INVALID_ARG, "fused_const_cats must be in 1..8");
+        c->fused_const_cats = iv;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
     } else if (k == "fused_exact_log") {

@@ -322,6 +322,9 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
         check(per_site, total, oracle_per_site(case, P))
         total2 = ctx.loglik_host(case.tips)
         assert total2 == total
+        ctx.set_option("fused_const_cats", 2)               # two categories per launch share the constant bank
+        total3, per_site3 = ctx.loglik(per_site=True)
+        assert total3 == total and np.array_equal(per_site3, per_site)
 
 
 def test_fused_large_tree_falls_back_to_shared_memory_matrices():
