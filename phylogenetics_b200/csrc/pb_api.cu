@@ -137,7 +137,7 @@ struct pb_ctx {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
-    int host_chunks = 8;                // option "host_chunks"
+    int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)
 
     // optional per-phase device timing (pb_set_timing)
     bool timing = false;
