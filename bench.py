@@ -28,6 +28,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout (libraries such as NCCL print banners on fd 1:
+    main() points fd 1 at stderr for the duration of the run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 METRIC = "pruning site-node updates/sec"
 UNIT = "site-node updates/s"
 
@@ -151,7 +165,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_block(cfg, seconds=12.0):
@@ -362,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline_block(cfg)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -379,6 +393,10 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "level"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # anything else written to fd 1 (NCCL banner, ...) goes to stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
