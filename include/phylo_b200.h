@@ -111,6 +111,20 @@ int pb_set_tips_device(pb_ctx *ctx, const uint8_t *d_states, int64_t ld);
  * lib/phylo_ctmc.ml:234-242); 0 = missing observation (Missing_values: leaf_state = None). */
 int pb_set_tip_masks(pb_ctx *ctx, const uint64_t *masks, int64_t ld);
 
+/* f4 — alignment text straight to tip states, encoded on the device: text[row*ld + site*w .. +w) with
+ * w = 1 (nucleotides: A,C,G,T either case, lib/nucleotide.ml:8-13; amino acids:
+ * "ACDEFGHIKLMNPQRSTVWY", lib/amino_acid.ml:4) or w = 3 (sense codons over TCAG, universal code,
+ * lib/codon.ml:51-58,73).  A character outside the alphabet or a stop codon -> PB_ERR_INVALID_ARG
+ * (the reference raises Invalid_argument in of_char_exn). */
+#define PB_ALPHABET_DNA        0
+#define PB_ALPHABET_AMINO_ACID 1
+#define PB_ALPHABET_CODON      2
+int pb_set_tips_text(pb_ctx *ctx, const char *text, int64_t ld, int alphabet);
+/* f4 — site-pattern compression: the context holds the DISTINCT columns and w[s] is how many
+ * original sites show column s; the total becomes sum_s w[s] * logL[s] (per-site values stay per
+ * pattern).  NULL removes the weights. */
+int pb_set_site_weights(pb_ctx *ctx, const double *w /* [nsites] */);
+
 int pb_set_root_frequencies(pb_ctx *ctx, const double *pi /* [nstates] */);
 /* Rate categories: branch lengths are multiplied by rates[k]; site likelihood =
  * sum_k weights[k] * L_k.  (Extension: the reference has no rate heterogeneity.) */

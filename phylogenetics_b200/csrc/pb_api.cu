@@ -112,6 +112,9 @@ struct pb_ctx {
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
+    int level4_async = 1;               // option "level4_async": cp.async-pipelined level kernel for binary trees
+    int level4_waves = 4;               // option "level4_waves": CTAs per SM slot per launch (tile granularity)
+    int min_arity = 0;
     int level4_minb = 4;                // option "level4_min_blocks": occupancy target of the level4 kernel
     bool force_dense = false;           // option "dense_scalar": use the DFMA level kernel instead of DMMA
 
@@ -128,7 +131,9 @@ struct pb_ctx {
     bool p_dirty = true;
 
     // work + outputs
-    DevBuf<double> d_pool, d_site_cat, d_per_site, d_partials, d_total;
+    DevBuf<double> d_pool, d_site_cat, d_per_site, d_partials, d_total, d_site_weights;
+    DevBuf<unsigned char> d_text, d_lut;
+    bool have_site_weights = false;
     int64_t slot_stride = 0;
     double* h_total = nullptr;   // pinned: [0] = total, [1] = bad-tip flag (as int)
     bool evaluated = false;
@@ -219,10 +224,12 @@ int compile_tree(pb_ctx* c)
 
     std::vector<int> level(nn, 0), su(nn, 0);
     c->max_arity = 0;
+    c->min_arity = 1 << 30;
     for (int v : order) {
         const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
         if (c0 == c1) continue;
         c->max_arity = std::max(c->max_arity, c1 - c0);
+        c->min_arity = std::min(c->min_arity, c1 - c0);
         int lv = 0;
         for (int k = c0; k < c1; k++) lv = std::max(lv, level[c->child_idx[k]]);
         level[v] = lv + 1;
@@ -724,7 +731,27 @@ int run_pruning(pb_ctx* c)
     c->partial_ok = true;
     for (const auto& seg : segments) {
         const int first = seg.first, count = seg.second;
-        if (path == PATH_LEVEL4) {
+        if (path == PATH_LEVEL4 && c->level4_async && c->max_arity == 2 && c->min_arity == 2) {
+            // software-pipelined form (binary trees): CTAs walk consecutive tiles with cp.async prefetch
+            const size_t smem = 32 * sizeof(double) + (size_t)2 * 2 * 5 * 256 * 16 + (size_t)2 * 2 * 256 * 4;
+            static bool attr_set = false;
+            if (!attr_set) {
+                PB_CUDA(c, cudaFuncSetAttribute(pbk::level4_async, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            const int64_t ntiles = c->spad / 512;
+            const int64_t units = (int64_t)count * c->ncat;
+            int64_t chunks = std::max<int64_t>(1, ((int64_t)c->sm_count * 2 * c->level4_waves + units - 1) / units);
+            chunks = std::min(chunks, ntiles);
+            const int64_t tpc = (ntiles + chunks - 1) / chunks;
+            chunks = (ntiles + tpc - 1) / tpc;
+            dim3 grid((unsigned)chunks, count, c->ncat);
+            pbk::level4_async<<<grid, 256, smem, c->stream>>>(lvn, c->d_lv_children.p, first, c->d_P.p, c->nnodes,
+                                                              c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
+                                                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p,
+                                                              store_root, (int)tpc);
+            c->launches++;
+        } else if (path == PATH_LEVEL4) {
             dim3 grid((unsigned)((c->spad / 2 + 255) / 256), count, c->ncat);
 #define PB_LEVEL4_ARGS lvn, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->d_tips.p, c->spad, \
                        c->d_pool.p, c->slot_stride, c->spad, c->d_pi.p, c->threshold, c->shift_at_root,        \
@@ -778,7 +805,8 @@ int run_root_reduction(pb_ctx* c)
     PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
     PB_CUDA(c, c->d_partials.ensure((size_t)blocks));
     PB_CUDA(c, c->d_total.ensure(1));
-    pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p, c->nsites,
+    pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p,
+                                                               c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
                                                                c->spad, 0, c->d_per_site.p, c->d_partials.p);
     pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, blocks, c->d_total.p);
     c->launches += 2;
@@ -1032,6 +1060,71 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     return PB_OK;
 }
 
+int pb_set_site_weights(pb_ctx* c, const double* w)
+{
+    PB_ENTER(c);
+    if (!w) { c->have_site_weights = false; return PB_OK; }
+    for (int64_t s = 0; s < c->nsites; s++)
+        if (!(w[s] >= 0.0)) return fail(c, PB_ERR_INVALID_ARG, "site weights must be >= 0");
+    PB_CUDA(c, c->d_site_weights.ensure((size_t)c->spad));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_site_weights.p, w, sizeof(double) * c->nsites, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_site_weights = true;
+    return PB_OK;
+}
+
+int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
+{
+    PB_ENTER(c);
+    const int width = alphabet == PB_ALPHABET_CODON ? 3 : 1;
+    if (!text || ld < c->nsites * width) return fail(c, PB_ERR_INVALID_ARG, "text: null pointer or ld too small");
+    const int expect = alphabet == PB_ALPHABET_DNA ? 4 : alphabet == PB_ALPHABET_AMINO_ACID ? 20 : alphabet == PB_ALPHABET_CODON ? 61 : -1;
+    if (expect < 0) return fail(c, PB_ERR_INVALID_ARG, "unknown alphabet");
+    if (expect != c->n) return fail(c, PB_ERR_INVALID_ARG, "alphabet size does not match nstates");
+    unsigned char lut[256 + 64];
+    memset(lut, 255, sizeof(lut));
+    if (alphabet == PB_ALPHABET_DNA) {                       // lib/nucleotide.ml:8-13 (either case)
+        const char* up = "ACGT"; const char* lo = "acgt";
+        for (int i = 0; i < 4; i++) { lut[(unsigned char)up[i]] = i; lut[(unsigned char)lo[i]] = i; }
+    } else if (alphabet == PB_ALPHABET_AMINO_ACID) {         // lib/amino_acid.ml:4 (upper case only)
+        const char* aa = "ACDEFGHIKLMNPQRSTVWY";
+        for (int i = 0; i < 20; i++) lut[(unsigned char)aa[i]] = i;
+    } else {                                                 // lib/codon.ml:51-58,73: TCAG order, universal code, stops removed
+        const char* nuc = "TCAG";
+        for (int i = 0; i < 4; i++) lut[(unsigned char)nuc[i]] = i;
+        const char* code = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+        int k = 0;
+        for (int t = 0; t < 64; t++) lut[256 + t] = (code[t] == '*') ? 255 : (unsigned char)k++;
+    }
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(c, c->d_lut.ensure(sizeof(lut)));
+    PB_CUDA(c, c->d_text.ensure((size_t)c->ntaxa * c->nsites * width));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpy2DAsync(c->d_text.p, c->nsites * width, text, ld, c->nsites * width, c->ntaxa,
+                                 cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    dim3 grid((unsigned)std::min<int64_t>((c->nsites + 255) / 256, 1024), c->ntaxa);
+    pbk::encode_text<<<grid, 256, 0, c->stream>>>(c->d_text.p, c->nsites * width, width, c->d_lut.p, c->d_tips.p, c->spad,
+                                                  c->nsites, c->d_bad.p);
+    c->launches++;
+    PB_CUDA(c, cudaGetLastError());
+    int bad = 0;
+    PB_CUDA(c, cudaMemcpyAsync(&bad, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (bad) {
+        PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+        c->have_tips = false;
+        return fail(c, PB_ERR_INVALID_ARG, "alignment text has a character outside the alphabet (or a stop codon)");
+    }
+    c->have_tips = true;
+    c->have_masks = false;
+    c->pack_dirty = true;
+    c->tips_checked = true;
+    c->all_dirty = true;
+    return PB_OK;
+}
+
 int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
 {
     PB_ENTER(c);
@@ -1235,9 +1328,9 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
         if ((rc = launch_fused4(c, s0, s1)) != PB_OK) return rc;
         const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
         if (b1 > b0) {
-            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p,
-                                                                          c->nsites, c->spad, b0, c->d_per_site.p,
-                                                                          c->d_partials.p);
+            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(
+                c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
+                c->spad, b0, c->d_per_site.p, c->d_partials.p);
             c->launches++;
         }
     }
@@ -1352,6 +1445,11 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const = iv != 0;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
+    } else if (k == "level4_async") {
+        c->level4_async = iv != 0;
+    } else if (k == "level4_waves") {
+        if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "level4_waves must be in 1..64");
+        c->level4_waves = iv;
     } else if (k == "level4_min_blocks") {
         if (iv < 3 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "level4_min_blocks must be 3..6");
         c->level4_minb = iv;

@@ -253,6 +253,122 @@ level4(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ child
 }
 
 // --------------------------------------------------------------------------
+// level4_async: level4 for binary nodes, software-pipelined with per-thread cp.async.
+//
+// A compute-free kernel with level4's traffic (10 planes read, 5 written, 16 B per thread per
+// plane) reaches 6.7 TB/s on this B200 (tools/stream_probe.cu) while level4 sits at 5.6 TB/s inside
+// its kernels: it holds 64 registers per thread, so too few loads are in flight while threads
+// compute and store.  Here every thread copies the 160 bytes of its NEXT tile straight into its own
+// shared-memory slots (LDGSTS: asynchronous, no registers, no barrier - a thread reads back only what
+// it copied) and meanwhile works on the current tile: two tiles of traffic stay in flight per thread.
+// grid = (chunks, nodes of the level, ncat); a CTA walks tiles_per_cta consecutive 512-site tiles.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+level4_async(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children, int node_base,
+             const double* __restrict__ P, int nnodes,
+             const uint8_t* __restrict__ tips, int64_t tips_ld,
+             double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+             const double* __restrict__ pi, double thr, int shift_at_root,
+             double* __restrict__ site_cat, int store_root, int tiles_per_cta)
+{
+    extern __shared__ double shbuf[];           // P[2][16] | stage[2][child 2][plane 5][256 threads] double2 | tips
+    double* shP = shbuf;
+    double2* shX = reinterpret_cast<double2*>(shbuf + 32);
+    unsigned* shT = reinterpret_cast<unsigned*>(shX + 2 * 2 * 5 * 256);          // [stage 2][child 2][256]
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    const int c = blockIdx.z, tid = threadIdx.x;
+    const LevelChild c0 = ch[0], c1 = ch[1];
+    if (tid < 32) shP[tid] = P[((size_t)c * nnodes + (tid < 16 ? c0.pnode : c1.pnode)) * 16 + (tid & 15)];
+    __syncthreads();
+    const int64_t ntiles = spad / 512;
+    const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    const int64_t t_end = min(t_begin + tiles_per_cta, ntiles);
+
+    auto issue = [&](int64_t tile, int stage) {
+        const int64_t s0 = tile * 512 + 2 * tid;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const LevelChild cd = k ? c1 : c0;
+            if (cd.kind == 0) {
+                // 4 aligned tip bytes holding this thread's two sites
+                cp_async_4(shT + (stage * 2 + k) * 256 + tid, tips + (int64_t)cd.src * tips_ld + (s0 & ~(int64_t)3));
+            } else {
+                const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * 5 * spad + s0;
+                double2* dst = shX + ((stage * 2 + k) * 5) * 256 + tid;
+#pragma unroll
+                for (int i = 0; i < 5; i++) cp_async_16(dst + i * 256, src + (int64_t)i * spad);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (t_begin < t_end) issue(t_begin, 0);
+    int stage = 0;
+    for (int64_t tile = t_begin; tile < t_end; tile++, stage ^= 1) {
+        if (tile + 1 < t_end) {
+            issue(tile + 1, stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const int64_t s0 = tile * 512 + 2 * tid;
+        Term4 t[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const LevelChild cd = k ? c1 : c0;
+            const double* Pm = shP + 16 * k;
+            if (cd.kind == 0) {
+                const unsigned w = shT[(stage * 2 + k) * 256 + tid];
+                const unsigned sh = (unsigned)(s0 & 3) * 8;          // 0 or 16
+                const int sa = (w >> sh) & 0xff, sb = (w >> (sh + 8)) & 0xff;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { t[k].a[i] = Pm[i * 4 + sa]; t[k].b[i] = Pm[i * 4 + sb]; }
+                t[k].ca = 0.0; t[k].cb = 0.0;
+            } else {
+                const double2* x = shX + ((stage * 2 + k) * 5) * 256 + tid;
+                double xa[4], xb[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const double2 q = x[i * 256]; xa[i] = q.x; xb[i] = q.y; }
+                const double2 qc = x[4 * 256];
+                matvec4(Pm, xa, t[k].a);
+                matvec4(Pm, xb, t[k].b);
+                t[k].ca = qc.x; t[k].cb = qc.y;
+            }
+        }
+        double va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { va[i] = t[0].a[i] * t[1].a[i]; vb[i] = t[0].b[i] * t[1].b[i]; }
+        double ca = t[0].ca + t[1].ca, cb = t[0].cb + t[1].cb;
+        shift4(va, ca, thr);
+        shift4(vb, cb, thr);
+        if (!nd.is_root || store_root) {
+            double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * 5 * spad + s0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<double2*>(dst + (int64_t)i * spad) = make_double2(va[i], vb[i]);
+            *reinterpret_cast<double2*>(dst + 4 * spad) = make_double2(ca, cb);
+        }
+        if (nd.is_root) {
+            const double la = root4(va, ca, pi, thr, shift_at_root);
+            const double lb = root4(vb, cb, pi, thr, shift_at_root);
+            *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0) = make_double2(la, lb);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
 // K2 (level-scheduled, N states, scalar DFMA version): one thread per site, the child's
 // CLV tile and its P matrix staged in shared memory, running product in registers.
 // Baseline and fallback for the tensor-core kernel (level_dmma, pb_kernels_dmma.cuh).
@@ -375,6 +491,7 @@ __device__ __forceinline__ double block_sum_256(double x, double* red)
 
 __global__ void __launch_bounds__(256)
 root_combine(const double* __restrict__ site_cat, int ncat, const double* __restrict__ weights,
+             const double* __restrict__ site_weights,   // nullable: multiplicity of every column (pattern compression)
              int64_t nsites, int64_t spad, int64_t block0, double* __restrict__ per_site,
              double* __restrict__ partials)
 {
@@ -400,6 +517,7 @@ root_combine(const double* __restrict__ site_cat, int ncat, const double* __rest
             }
         }
         per_site[s] = out;
+        if (site_weights) out = site_weights[s] * out;
     }
     const double bs = block_sum_256(out, red);
     if (threadIdx.x == 0) partials[blk] = bs;

@@ -72,6 +72,31 @@ validate_tips(const uint8_t* __restrict__ tips, int64_t total, int nstates, int*
     if (bad) atomicOr(bad_flag, 1);
 }
 
+// f4: alignment text -> tip states on the device.  text[row*ld + site*width .. + width) is the symbol
+// of taxon `row` at `site`; width 1 goes through a 256-entry table (nucleotides, amino acids),
+// width 3 (codons) through the nucleotide table and then a 64-entry sense-codon table.  255 marks
+// a character outside the alphabet (flagged, like Nucleotide.of_char_exn's invalid_arg).
+__global__ void __launch_bounds__(256)
+encode_text(const unsigned char* __restrict__ text, int64_t ld, int width, const unsigned char* __restrict__ lut,
+            uint8_t* __restrict__ tips, int64_t tips_ld, int64_t nsites, int* __restrict__ bad_flag)
+{
+    const int row = blockIdx.y;
+    int bad = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsites; s += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned char* p = text + (int64_t)row * ld + s * width;
+        unsigned st;
+        if (width == 1) {
+            st = lut[p[0]];
+        } else {
+            const unsigned a = lut[p[0]], b = lut[p[1]], c = lut[p[2]];
+            st = (a > 3u || b > 3u || c > 3u) ? 255u : lut[256 + a * 16 + b * 4 + c];
+        }
+        bad |= (st == 255u);
+        tips[(int64_t)row * tips_ld + s] = (uint8_t)st;
+    }
+    if (bad) atomicOr(bad_flag, 1);
+}
+
 template <bool EXACT_LOG>
 struct Scale {             // log-scale accumulator of one (site, category)
     double m;              // EXACT_LOG: running sum of logs; else mantissa product in [2^-400, 1]

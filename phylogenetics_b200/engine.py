@@ -122,6 +122,23 @@ class LikelihoodContext:
     def set_tips_device(self, device_ptr, ld):
         self._ck(lib.pb_set_tips_device(self._ctx, ctypes.c_void_p(device_ptr), int(ld)))
 
+    def set_tips_text(self, rows, alphabet):
+        """rows: one str/bytes per taxon (all the same length); encoded to states on the device."""
+        rows = [r.encode() if isinstance(r, str) else bytes(r) for r in rows]
+        width = 3 if alphabet == _lib.PB_ALPHABET_CODON else 1
+        if len(rows) != self.ntaxa or any(len(r) != self.nsites * width for r in rows):
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "need ntaxa rows of nsites symbols")
+        self._ck(lib.pb_set_tips_text(self._ctx, b"".join(rows), self.nsites * width, int(alphabet)))
+
+    def set_site_weights(self, w):
+        if w is None:
+            self._ck(lib.pb_set_site_weights(self._ctx, None))
+            return
+        w = _f64(w)
+        if len(w) != self.nsites:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "need one weight per site")
+        self._ck(lib.pb_set_site_weights(self._ctx, w.ctypes.data))
+
     def set_tip_masks(self, masks):
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
         self._ck(lib.pb_set_tip_masks(self._ctx, masks.ctypes.data, masks.shape[1]))
@@ -265,3 +282,11 @@ def host_reversible_eigensystem(Q, pi):
     if rc != 0:
         raise _lib.PhyloB200Error(rc, "rate matrix is not reversible with respect to pi")
     return np.ascontiguousarray(U.T), lam, np.ascontiguousarray(Ui.T)
+
+
+def compress_site_patterns(tips):
+    """f4: distinct alignment columns, their multiplicities, and the map back to the original sites
+    (tips[:, s] == patterns[:, inverse[s]])."""
+    tips = np.asarray(tips)
+    patterns, inverse, counts = np.unique(tips, axis=1, return_inverse=True, return_counts=True)
+    return np.ascontiguousarray(patterns), counts.astype(np.float64), np.asarray(inverse).reshape(-1)

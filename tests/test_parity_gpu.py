@@ -243,6 +243,7 @@ def test_level4_occupancy_variants(minb):
     case = cases.make_case("lv4", "gtr", 50, 5000, ncat=3, seed=6)
     P = case.host_P()
     with run_ctx(case, "direct", level=True, P=P) as ctx:
+        ctx.set_option("level4_async", 0)
         ctx.set_option("level4_min_blocks", minb)
         total, per_site = ctx.loglik(per_site=True)
     check(per_site, total, oracle_per_site(case, P))
@@ -335,3 +336,21 @@ def test_fused_large_tree_falls_back_to_shared_memory_matrices():
         assert ctx.path_name == "fused4"
         total, per_site = ctx.loglik(per_site=True)
     check(per_site, total, oracle_per_site(case, P))
+
+
+@pytest.mark.parametrize("waves", [1, 4, 16])
+@pytest.mark.parametrize("nsites", [777, 40000])
+def test_level4_async_pipeline(waves, nsites):
+    """The cp.async-pipelined level kernel (binary trees) against the oracle, for several tile
+    granularities, ragged sizes, Felsenstein mode and with every CLV kept."""
+    case = cases.make_case("lv4a", "gtr", 70, nsites, ncat=4, seed=9)
+    P = case.host_P()
+    for mode in (_lib.PB_MODE_PHYLO_CTMC, _lib.PB_MODE_FELSENSTEIN):
+        expect = oracle_per_site(case, P, mode)
+        for keep in (False, True):
+            with run_ctx(case, "direct", level=True, keep=keep, mode=mode, P=P) as ctx:
+                ctx.set_option("level4_async", 1)
+                ctx.set_option("level4_waves", waves)
+                assert ctx.path_name == "level4"
+                total, per_site = ctx.loglik(per_site=True)
+                check(per_site, total, expect)

@@ -17,16 +17,21 @@ f = case.flat
 out = []
 ref = None
 VARIANTS = [(256, 1, 0, 1), (256, 2, 0, 1), (512, 1, 0, 1), (512, 2, 0, 1), (128, 2, 0, 1), (128, 4, 0, 1), (256, 4, 0, 1), (256, 1, 0, 0), (256, 2, 0, 0), (512, 1, 0, 0),
-            (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0)]
+            (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0), ("level_async", 1, 0, 0), ("level_async", 2, 0, 0),
+            ("level_async", 4, 0, 0), ("level_async", 8, 0, 0), ("level_async", 16, 0, 0)]
 for block, spt, exact, const in VARIANTS:
-    level = block == "level"
+    level = str(block).startswith("level")
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4, level_kernels=level) as ctx:
         ctx.set_tree(f, case.bl)
         ctx.set_categories(case.rates, case.weights)
         ctx.set_rate_matrix(case.Q, case.pi)
         ctx.set_root_frequencies(case.pi)
         ctx.set_tips(case.tips)
-        if level:
+        if block == "level_async":
+            ctx.set_option("level4_async", 1)
+            ctx.set_option("level4_waves", spt)
+        elif level:
+            ctx.set_option("level4_async", 0)
             ctx.set_option("level4_min_blocks", spt)
         else:
             ctx.set_option("fused_const", const)
