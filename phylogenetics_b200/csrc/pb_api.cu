@@ -113,7 +113,7 @@ struct pb_ctx {
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
     int level4_async = 1;               // option "level4_async": cp.async-pipelined level kernel for binary trees
-    int level4_waves = 4;               // option "level4_waves": CTAs per SM slot per launch (tile granularity)
+    int level4_waves = 16;              // option "level4_waves": CTAs per SM slot per launch (tile granularity)
     int min_arity = 0;
     int level4_minb = 4;                // option "level4_min_blocks": occupancy target of the level4 kernel
     bool force_dense = false;           // option "dense_scalar": use the DFMA level kernel instead of DMMA
@@ -176,10 +176,27 @@ void to_row_major(int n, size_t count, const double* in, double* out)
             for (int j = 0; j < n; j++) out[m * n * n + i * n + j] = in[m * n * n + j * n + i];
 }
 
+size_t fused_smem_bytes_for(const pb_ctx* c, int block, int spt)
+{
+    return (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * block * spt * 8 +
+           c->fprog.size() * sizeof(FusedOp2);
+}
+
+// The all-shared-memory fused kernel keeps every branch matrix of the category in smem; large trees
+// shrink the tile (and with it the stack area) before giving up on the fused path.
+bool fused_shape(const pb_ctx* c, int* block, int* spt)
+{
+    const int cand[3][2] = {{c->fused_block, c->fused_spt}, {256, 1}, {128, 1}};
+    for (const auto& k : cand)
+        if (fused_smem_bytes_for(c, k[0], k[1]) <= c->smem_optin) { *block = k[0]; *spt = k[1]; return true; }
+    return false;
+}
+
 size_t fused_smem_bytes(const pb_ctx* c)
 {
-    return (size_t)c->nnodes * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * c->fused_block * c->fused_spt * 8 +
-           c->fprog.size() * sizeof(FusedOp2);
+    int b = c->fused_block, q = c->fused_spt;
+    fused_shape(c, &b, &q);
+    return fused_smem_bytes_for(c, b, q);
 }
 
 int path_of(const pb_ctx* c)
@@ -641,7 +658,9 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
 int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
 {
     if (fused_const_ok(c)) return launch_fused4c(c, site0, site1, site0 == 0);
-    const int key = c->fused_block * 10 + c->fused_spt;
+    int fb = c->fused_block, fq = c->fused_spt;
+    if (!fused_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4: the tree does not fit shared memory");
+    const int key = fb * 10 + fq;
     if (c->fused_exact_log) {
         switch (key) {
         case 1281: return launch_fused4_variant<128, 1, true>(c, site0, site1);

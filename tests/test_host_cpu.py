@@ -140,3 +140,11 @@ def test_string_alignment_encoding():
     from phylogenetics_b200 import _lib
     with pytest.raises(_lib.PhyloB200InvalidArgument):
         A.encode(A.of_string_list(["ACGN"]), ["T0"])
+
+
+def test_compress_site_patterns_host():
+    from phylogenetics_b200.engine import compress_site_patterns
+    tips = np.array([[0, 1, 0, 3, 1, 0], [2, 2, 2, 0, 2, 2]], dtype=np.uint8)
+    patterns, counts, inverse = compress_site_patterns(tips)
+    assert patterns.shape == (2, 3) and sorted(counts.tolist()) == [1.0, 2.0, 3.0]
+    assert np.array_equal(patterns[:, inverse], tips)

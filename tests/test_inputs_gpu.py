@@ -1,0 +1,71 @@
+"""f4: alignment text encoded to tip states on the device, and site-pattern
+compression with weights — the per-site output is re-expanded, the total counts original sites."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import c_oracle as C
+from phylogenetics_b200 import _lib, models
+from phylogenetics_b200.engine import LikelihoodContext, compress_site_patterns
+
+pytestmark = pytest.mark.gpu
+
+
+def ctx_for(case, P):
+    ctx = LikelihoodContext(case.n, case.nsites, case.flat.nleaves, ncat=case.ncat)
+    ctx.set_tree(case.flat, case.bl)
+    ctx.set_categories(case.rates, case.weights)
+    ctx.set_pmatrices(P)
+    ctx.set_root_frequencies(case.pi)
+    return ctx
+
+
+@pytest.mark.parametrize("model,alphabet,symbols", [
+    ("gtr", _lib.PB_ALPHABET_DNA, list("ACGT")),
+    ("wag", _lib.PB_ALPHABET_AMINO_ACID, list(models.AMINO_ACIDS)),
+    ("mg94", _lib.PB_ALPHABET_CODON, models.Codon.ns_triplets),
+])
+def test_text_alignment_encoded_on_device(model, alphabet, symbols):
+    case = cases.make_case("txt" + model, model, 9, 700, seed=4)
+    P = case.host_P()
+    rows = ["".join(symbols[s] for s in row) for row in case.tips]
+    if alphabet == _lib.PB_ALPHABET_DNA:
+        rows[2] = rows[2].lower()                        # Nucleotide.of_char_exn accepts either case
+    with ctx_for(case, P) as a, ctx_for(case, P) as b:
+        a.set_tips(case.tips)
+        b.set_tips_text(rows, alphabet)
+        ta, pa = a.loglik(per_site=True)
+        tb, pb_ = b.loglik(per_site=True)
+        assert ta == tb and np.array_equal(pa, pb_)
+        bad = list(rows)
+        bad[4] = ("N" if alphabet != _lib.PB_ALPHABET_CODON else "TAA") + bad[4][(1 if alphabet != _lib.PB_ALPHABET_CODON else 3):]
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            b.set_tips_text(bad, alphabet)
+    with pytest.raises(_lib.PhyloB200InvalidArgument):
+        with ctx_for(case, P) as cwrong:
+            cwrong.set_tips_text(rows, (alphabet + 1) % 3)    # alphabet does not match nstates
+
+
+def test_site_pattern_compression():
+    case = cases.make_case("pat", "k80", 6, 5000, seed=2)      # few taxa: many repeated columns
+    P = case.host_P()
+    f = case.flat
+    patterns, counts, inverse = compress_site_patterns(case.tips)
+    assert patterns.shape[1] < case.nsites / 3 and counts.sum() == case.nsites
+    assert np.array_equal(patterns[:, inverse], case.tips)
+    expect = C.pruning(4, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi, tips=case.tips)
+    with LikelihoodContext(4, patterns.shape[1], f.nleaves) as ctx:
+        ctx.set_tree(f, case.bl)
+        ctx.set_pmatrices(P)
+        ctx.set_root_frequencies(case.pi)
+        ctx.set_tips(patterns)
+        ctx.set_site_weights(counts)
+        total, per_pattern = ctx.loglik(per_site=True)
+        per_site = per_pattern[inverse]                                   # re-expanded to original sites
+        assert (np.abs(per_site - expect) / np.abs(expect)).max() <= 1e-9
+        assert abs(total - C.sum_exact(expect)) <= 1e-10 * abs(total)
+        ctx.set_site_weights(None)
+        unweighted = ctx.loglik()
+        assert abs(unweighted - per_pattern.sum()) <= 1e-10 * abs(unweighted)
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.set_site_weights(-counts)

@@ -17,8 +17,8 @@ f = case.flat
 out = []
 ref = None
 VARIANTS = [(256, 1, 0, 1), (256, 2, 0, 1), (512, 1, 0, 1), (512, 2, 0, 1), (128, 2, 0, 1), (128, 4, 0, 1), (256, 4, 0, 1), (256, 1, 0, 0), (256, 2, 0, 0), (512, 1, 0, 0),
-            (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0), ("level_async", 1, 0, 0), ("level_async", 2, 0, 0),
-            ("level_async", 4, 0, 0), ("level_async", 8, 0, 0), ("level_async", 16, 0, 0)]
+            (128, 2, 0, 0), (256, 1, 1, 0), ("level", 4, 0, 0), ("level_async", 24, 0, 0), ("level_async", 32, 0, 0),
+            ("level_async", 8, 0, 0), ("level_async", 16, 0, 0), ("level_async", 64, 0, 0)]
 for block, spt, exact, const in VARIANTS:
     level = str(block).startswith("level")
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4, level_kernels=level) as ctx:
