@@ -112,6 +112,7 @@ struct pb_ctx {
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
+    bool level4_async_ready = false;
     int level4_async = 1;               // option "level4_async": cp.async-pipelined level kernel for binary trees
     int level4_waves = 16;              // option "level4_waves": CTAs per SM slot per launch (tile granularity)
     int min_arity = 0;
@@ -753,10 +754,9 @@ int run_pruning(pb_ctx* c)
         if (path == PATH_LEVEL4 && c->level4_async && c->max_arity == 2 && c->min_arity == 2) {
             // software-pipelined form (binary trees): CTAs walk consecutive tiles with cp.async prefetch
             const size_t smem = 32 * sizeof(double) + (size_t)2 * 2 * 5 * 256 * 16 + (size_t)2 * 2 * 256 * 4;
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (!c->level4_async_ready) {       // per context: the attribute is per device
                 PB_CUDA(c, cudaFuncSetAttribute(pbk::level4_async, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+                c->level4_async_ready = true;
             }
             const int64_t ntiles = c->spad / 512;
             const int64_t units = (int64_t)count * c->ncat;

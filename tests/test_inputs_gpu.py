@@ -38,7 +38,8 @@ def test_text_alignment_encoded_on_device(model, alphabet, symbols):
         tb, pb_ = b.loglik(per_site=True)
         assert ta == tb and np.array_equal(pa, pb_)
         bad = list(rows)
-        bad[4] = ("N" if alphabet != _lib.PB_ALPHABET_CODON else "TAA") + bad[4][(1 if alphabet != _lib.PB_ALPHABET_CODON else 3):]
+        junk = {_lib.PB_ALPHABET_DNA: "N", _lib.PB_ALPHABET_AMINO_ACID: "B", _lib.PB_ALPHABET_CODON: "TAA"}[alphabet]
+        bad[4] = junk + bad[4][len(junk):]                   # outside the alphabet / a stop codon
         with pytest.raises(_lib.PhyloB200InvalidArgument):
             b.set_tips_text(bad, alphabet)
     with pytest.raises(_lib.PhyloB200InvalidArgument):
