@@ -91,6 +91,7 @@ struct pb_ctx {
     DevBuf<LevelChild> d_sq_children;
     int dmma_per_level = 1;             // option "dmma_per_level": one launch per tree level instead
     int dmma_version = 2;               // option "dmma_version": 2 = cp.async-pipelined kernel (arity <= 2), 1 = direct loads
+    int dmma_tip_levels_v1 = 1;         // option: levels made of tip-only nodes use the unstaged kernel (2 CTAs/SM)
     int dmma_seq_tiles = 16;            // option "dmma_group_tiles": 8-site tiles per group (x8 sites)
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
@@ -593,6 +594,17 @@ int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
     return PB_OK;
 }
 
+// true when every node of the launch has only leaf children (the cherries of level 1)
+bool segment_all_tips(const pb_ctx* c, int first, int count)
+{
+    for (int q = first; q < first + count; q++) {
+        const LevelNode& nd = c->lv_nodes[q];
+        for (int k = 0; k < nd.nchild; k++)
+            if (c->lv_children[nd.child_off + k].kind != 0) return false;
+    }
+    return true;
+}
+
 template <int BLOCK, int SPT>
 int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_t site1)
 {
@@ -783,7 +795,8 @@ int run_pruning(pb_ctx* c)
             }
 #undef PB_LEVEL4_ARGS
             c->launches++;
-        } else if (path == PATH_LEVEL_DMMA && c->dmma_version == 2 && c->max_arity <= 2) {
+        } else if (path == PATH_LEVEL_DMMA && c->dmma_version == 2 && c->max_arity <= 2 &&
+                   !(c->dmma_tip_levels_v1 && !partial && segment_all_tips(c, first, count))) {
             int rc = pbk::launch_level_dmma2(n, lvn, c->d_lv_children.p, first, count, c->d_P.p, c->nnodes,
                                              c->ncat, c->d_tips.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
                                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root,
@@ -1475,6 +1488,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "dmma_version") {
         if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "dmma_version must be 1 or 2");
         c->dmma_version = iv;
+    } else if (k == "dmma_tip_levels_v1") {
+        c->dmma_tip_levels_v1 = iv != 0;
     } else if (k == "dmma_per_level") {
         c->dmma_per_level = iv != 0;
     } else if (k == "dmma_group_tiles") {

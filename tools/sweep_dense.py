@@ -13,7 +13,7 @@ for name, model, ntaxa, nsites in [("c3", "wag", 64, 200_000), ("c4", "mg94", 32
     case = cases.make_case(name, model, ntaxa, nsites, seed=100)
     f = case.flat
     ref = None
-    for opts in ({}, {"dmma_version": 1}, {"dmma_per_level": 0, "dmma_group_tiles": 64},
+    for opts in ({}, {"dmma_tip_levels_v1": 0}, {"dmma_version": 1},
                  {"dense_scalar": 1}):
         with LikelihoodContext(case.n, nsites, f.nleaves) as ctx:
             ctx.set_tree(f, case.bl)
