@@ -311,13 +311,25 @@ def run_ours(args, rank, world, local_rank):
         value = units / t_max
         pm = np.array(prune_ms)                                    # [steps][3] ms
         prune_avg_ms = float(pm[:, 1].mean())
-        nlaunch_prune = max(1, launches // args.steps - 3) if ctx.path_name != "fused4" else 1
+        fused_const = ctx.path_name == "fused4" and n == 4 and ninternal - 1 <= 128
+        kernel_name = "fused4c" if fused_const else ctx.path_name
+        nlaunch_prune = (ncat if fused_const else 1) if ctx.path_name == "fused4" else max(1, launches // args.steps - 3)
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh)
+            if cfg == "c2" and not args.sites and tj.get(kernel_name, {}).get("dram_bytes_per_launch"):
+                traffic, traffic_src = tj[kernel_name]["dram_bytes_per_launch"], tj[kernel_name]["source"]
+        except (OSError, ValueError):
+            pass
         bytes_eval = algorithmic_bytes_per_site(n, ncat, ntaxa) * nsites
         flops_eval = algorithmic_flops_per_site(n, ncat, ntaxa) * nsites
         achieved = bytes_eval / (prune_avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "true_bound": "fp64 pipe" if ctx.path_name == "fused4" else "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": "of " + peak_kind,
-                "kernel": ctx.path_name, "launches_per_step": nlaunch_prune,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_kind": "of " + peak_kind,
+                "kernel": kernel_name, "launches_per_step": nlaunch_prune,
+                "algorithmic_bytes_per_launch": bytes_eval / nlaunch_prune,
                 "kernel_ms_per_step": prune_avg_ms,
                 "algorithmic_bytes_per_step": bytes_eval,
                 "fp64_tflops_achieved": flops_eval / (prune_avg_ms * 1e-3) / 1e12,
