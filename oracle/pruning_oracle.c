@@ -5,9 +5,11 @@
  * call into this file.  Allowed users: tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py.
  *
- * Parity status: unpinned by reference outputs (the OCaml reference cannot be
- * built here); pinned by closed forms, the reference tests' RNG-free
- * properties and an mpmath restatement (see oracle/__init__.py).
+ * Parity status: pinned against the reference's golden vector -117.326089
+ * (tests/expect/phylo_ctmc_substitution_mappings.expected:5) through a replay of
+ * its GSL random stream (tests/test_oracle_reference_golden.py), and certified
+ * to ~1e-13 by closed forms, the reference tests' RNG-free properties and a
+ * 60-digit mpmath restatement (see oracle/__init__.py).
  *
  * Algorithm followed, operation for operation:
  *   Phylo_ctmc.pruning            lib/phylo_ctmc.ml:83-98
