@@ -29,6 +29,8 @@
  *     the rest to Failure (the reference's conventions).
  *   - One context = one caller thread.  Device work is enqueued on the context's
  *     CUDA stream; the blocking entry points synchronise that stream only.
+ *     Several contexts may share a device (the library serialises its own use of the
+ *     device's constant bank between them).
  *   - There is no CPU fallback: every compute entry point fails with
  *     PB_ERR_CUDA when no sm_100 device is usable.
  */

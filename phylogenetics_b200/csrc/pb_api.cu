@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,12 @@ using pbk::LevelNode;
 namespace {
 
 thread_local std::string g_create_error;
+
+// The fused 4-state kernel stages matrices in the device's constant bank, which every context on
+// that device shares: users are serialised by a host mutex around the enqueue and, on the device,
+// by an event recorded after the last kernel that read the bank.
+std::mutex g_const_mutex;
+cudaEvent_t g_const_event[64] = {};
 
 enum PSource { PSRC_NONE = 0, PSRC_EIGEN = 1, PSRC_DIRECT = 2, PSRC_EXPM = 3 };
 enum Path { PATH_FUSED4 = 0, PATH_LEVEL4 = 1, PATH_LEVEL_DENSE = 2, PATH_LEVEL_DMMA = 3 };
@@ -91,7 +98,7 @@ struct pb_ctx {
     DevBuf<LevelChild> d_sq_children;
     int dmma_per_level = 1;             // option "dmma_per_level": one launch per tree level instead
     int dmma_version = 2;               // option "dmma_version": 2 = cp.async-pipelined kernel (arity <= 2), 1 = direct loads
-    int dmma_tip_levels_v1 = 1;         // option: levels made of tip-only nodes use the unstaged kernel (2 CTAs/SM)
+    int dmma_tip_levels_v1 = 0;         // option: levels made of tip-only nodes use the unstaged kernel (2 CTAs/SM)
     int dmma_seq_tiles = 16;            // option "dmma_group_tiles": 8-site tiles per group (x8 sites)
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
@@ -637,6 +644,10 @@ bool fused_const_ok(const pb_ctx* c)
 // The inner matrices of as many categories as the constant bank holds per launch.
 int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
 {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    cudaEvent_t& bank_free = g_const_event[c->device & 63];
+    if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
+    else PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));     // another stream may still be reading the bank
     const int ninner = (int)c->inner_nodes.size();
     if (regather) {
         PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * ninner * 16));
@@ -665,6 +676,7 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
         }
         if (rc != PB_OK) return rc;
     }
+    PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
     return PB_OK;
 }
 
@@ -919,6 +931,8 @@ void pb_destroy(pb_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);   // work may still use our buffers
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     if (c->h_total) cudaFreeHost(c->h_total);
     for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -940,6 +954,7 @@ void pb_destroy(pb_ctx* c)
 int pb_set_stream(pb_ctx* c, void* s)
 {
     PB_ENTER(c);
+    if ((cudaStream_t)s != c->stream) PB_CUDA(c, cudaStreamSynchronize(c->stream));   // finish what the old stream holds
     c->stream = (cudaStream_t)s;      // 0 is a valid handle: the CUDA default stream
     return PB_OK;
 }
@@ -947,6 +962,7 @@ int pb_set_stream(pb_ctx* c, void* s)
 int pb_use_private_stream(pb_ctx* c)
 {
     PB_ENTER(c);
+    if (c->stream != c->own_stream) PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = c->own_stream;
     return PB_OK;
 }

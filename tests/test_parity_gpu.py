@@ -354,3 +354,20 @@ def test_level4_async_pipeline(waves, nsites):
                 assert ctx.path_name == "level4"
                 total, per_site = ctx.loglik(per_site=True)
                 check(per_site, total, expect)
+
+
+def test_two_contexts_share_the_device_constant_bank():
+    """Two contexts with different trees and models interleave evaluations on one GPU: the fused
+    kernel's constant-bank staging must not leak from one to the other."""
+    a = cases.make_case("ctxa", "gtr", 60, 4000, ncat=4, seed=41)
+    b = cases.make_case("ctxb", "k80", 33, 6000, ncat=2, seed=42)
+    Pa, Pb = a.host_P(), b.host_P()
+    ea, eb = oracle_per_site(a, Pa), oracle_per_site(b, Pb)
+    with run_ctx(a, "direct", P=Pa) as ca, run_ctx(b, "direct", P=Pb) as cb:
+        for _ in range(3):
+            ca.enqueue()
+            cb.enqueue()
+            ta, pa = ca.fetch(per_site=True)
+            tb, pb_ = cb.fetch(per_site=True)
+            check(pa, ta, ea)
+            check(pb_, tb, eb)
