@@ -13,6 +13,7 @@
 #include "pb_kernels.cuh"
 #include "pb_kernels_fused.cuh"
 #include "pb_kernels_dmma.cuh"
+#include "pb_kernels_fdmma.cuh"
 #include "pb_kernels_expm.cuh"
 #include "pb_host_linalg.h"
 
@@ -31,7 +32,7 @@ std::mutex g_const_mutex;
 cudaEvent_t g_const_event[64] = {};
 
 enum PSource { PSRC_NONE = 0, PSRC_EIGEN = 1, PSRC_DIRECT = 2, PSRC_EXPM = 3 };
-enum Path { PATH_FUSED4 = 0, PATH_LEVEL4 = 1, PATH_LEVEL_DENSE = 2, PATH_LEVEL_DMMA = 3 };
+enum Path { PATH_FUSED4 = 0, PATH_LEVEL4 = 1, PATH_LEVEL_DENSE = 2, PATH_LEVEL_DMMA = 3, PATH_FUSED_DMMA = 4 };
 
 template <typename T>
 struct DevBuf {
@@ -117,6 +118,14 @@ struct pb_ctx {
     DevBuf<double> d_Pc;
     int fused_const_cats = 1;           // option "fused_const_cats": categories per fused4c launch
     int fused_const = 1;                // option "fused_const": use fused4c when the tree has <= 128 inner branches
+    // fused_dmma: the same program for 20 / 61 states (compact matrix indices, tip rows, matrix order)
+    std::vector<FusedOp2> fprog_d;
+    std::vector<int> mlist;
+    int dstack = 0;
+    int fused_dmma = 1;                 // option "fused_dmma": site-resident tensor-core kernel for 20 / 61 states
+    DevBuf<FusedOp2> d_fprog_d;
+    DevBuf<int> d_mlist;
+    DevBuf<double> d_Ppad, d_PTleaf, d_gstack;
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
     bool pack_dirty = true, tips_checked = false;
@@ -219,6 +228,12 @@ int path_of(const pb_ctx* c)
         return PATH_LEVEL4;
     }
     if (!c->have_masks && pbk::dmma_supported(c->n) && !c->force_dense) {
+        if (!level && c->have_tree && c->fused_dmma) {
+            int ssm = 0;
+            size_t smem = 0;
+            if (pbk::fused_dmma_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem))
+                return PATH_FUSED_DMMA;
+        }
         const int mp = (c->n + 15) / 16 * 16, ld = (c->n + 7) / 8 * 8 + 4;
         if (((size_t)std::max(c->max_arity, 1) * mp * ld + mp) * sizeof(double) <= c->smem_optin) return PATH_LEVEL_DMMA;
     }
@@ -501,10 +516,40 @@ int compile_tree(pb_ctx* c)
             if (usesA) o.offA = compact[o.offA / 16] * 16;
             if (usesB) o.offB = compact[o.offB / 16] * 16;
         }
+        // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
+        c->fprog_d.clear();
+        c->mlist.clear();
+        c->dstack = 0;
+        int sp = 0;
+        for (const AOp& a : aops) {
+            if (a.code == pbk::FOP_PUSH) {
+                c->dstack = std::max(c->dstack, ++sp);
+                if (!c->fprog_d.empty() && !(c->fprog_d.back().code & pbk::FOP_PUSH_AFTER)) { c->fprog_d.back().code |= pbk::FOP_PUSH_AFTER; continue; }
+                c->fprog_d.push_back({pbk::FOP_PUSH | pbk::FOP_PUSH_AFTER, 0, 0, 0});
+                continue;
+            }
+            FusedOp2 o{a.code, 0, 0, 0};
+            const int rowA = a.tipA >= 0 ? c->tip_row[a.tipA] : 0, rowB = a.tipB >= 0 ? c->tip_row[a.tipB] : 0;
+            o.sh = rowA | (rowB << 16);
+            switch (a.code) {
+            case pbk::FOP_TIP_TIP: o.offA = compact[a.pA]; o.offB = compact[a.pB]; break;
+            case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: o.offA = compact[a.pA]; break;
+            case pbk::FOP_APPLY: o.offA = compact[a.pA]; c->mlist.push_back(o.offA); break;
+            case pbk::FOP_APPLY_MUL_TIP: o.offA = compact[a.pA]; o.offB = compact[a.pB]; c->mlist.push_back(o.offA); break;
+            case pbk::FOP_ACC_POP: o.offA = compact[a.pA]; o.offB = compact[a.pB]; c->mlist.push_back(o.offA); c->mlist.push_back(o.offB); sp--; break;
+            case pbk::FOP_POP_MUL: sp--; break;
+            default: break;
+            }
+            c->fprog_d.push_back(o);
+        }
     }
     c->pack_dirty = true;
 
     // upload
+    PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
+    PB_CUDA(c, c->d_mlist.ensure(std::max<size_t>(c->mlist.size(), 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_d.p, c->fprog_d.data(), c->fprog_d.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_mlist.p, c->mlist.data(), c->mlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, c->d_lv_nodes.ensure(c->lv_nodes.size()));
     PB_CUDA(c, c->d_lv_children.ensure(c->lv_children.size()));
     PB_CUDA(c, c->d_fprog.ensure(c->fprog.size()));
@@ -707,6 +752,33 @@ int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
     }
 }
 
+// Site-resident tensor-core path (20 / 61 states): pad the branch matrices, then one persistent launch.
+int launch_fused_dmma_path(pb_ctx* c)
+{
+    const int n = c->n;
+    const int ninner = (int)c->inner_nodes.size(), nleaf = (int)c->leaf_nodes.size();
+    int ssm = 0;
+    size_t smem = 0;
+    if (!pbk::fused_dmma_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem))
+        return fail(c, PB_ERR_CUDA, "fused_dmma: the tree does not fit shared memory");
+    PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma_matsz(n), 1)));
+    PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma_leafsz(n), 1)));
+    pbk::launch_fdmma_prepare(n, c->d_P.p, c->d_inner_nodes.p, ninner, c->d_leaf_nodes.p, nleaf, c->nnodes, c->ncat,
+                              c->d_Ppad.p, c->d_PTleaf.p, c->stream);
+    c->launches++;
+    const int64_t work = c->spad / 64 * c->ncat;
+    const int grid = pbk::fused_dmma_grid(n, c->sm_count, smem, work);
+    if (grid < 1) return fail(c, PB_ERR_CUDA, "fused_dmma launch configuration failed");
+    const int gdepth = c->dstack - ssm;
+    PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * 256 * pbk::fused_dmma_frag(n), 1)));
+    pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,
+                         c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
+                         c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
+    pbk::launch_fused_dmma(n, a, grid, smem, c->stream);
+    c->launches++;
+    return PB_OK;
+}
+
 int run_pruning(pb_ctx* c)
 {
     const int n = c->n;
@@ -723,6 +795,17 @@ int run_pruning(pb_ctx* c)
             c->tips_checked = true;
         }
         int rc = launch_fused4(c, 0, c->spad);
+        if (rc != PB_OK) return rc;
+        PB_CUDA(c, cudaGetLastError());
+        return PB_OK;
+    }
+    if (path == PATH_FUSED_DMMA) {
+        if (!c->tips_checked) {
+            pbk::validate_tips<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_tips.p, (int64_t)c->ntaxa * c->spad, n, c->d_bad.p);
+            c->launches++;
+            c->tips_checked = true;
+        }
+        int rc = launch_fused_dmma_path(c);
         if (rc != PB_OK) return rc;
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
@@ -1501,6 +1584,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "level4_min_blocks") {
         if (iv < 3 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "level4_min_blocks must be 3..6");
         c->level4_minb = iv;
+    } else if (k == "fused_dmma") {
+        c->fused_dmma = value != 0.0;
     } else if (k == "dmma_version") {
         if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "dmma_version must be 1 or 2");
         c->dmma_version = iv;
@@ -1556,6 +1641,7 @@ const char* pb_path_name(const pb_ctx* c)
     case PATH_FUSED4: return "fused4";
     case PATH_LEVEL4: return "level4";
     case PATH_LEVEL_DMMA: return "level_dmma";
+    case PATH_FUSED_DMMA: return "fused_dmma";
     default: return "level_dense";
     }
 }

@@ -1,0 +1,382 @@
+// K2, fused site-resident form for dense alphabets (20 amino acids, 61 sense codons) on the FP64
+// tensor cores: a CTA of 8 warps walks the WHOLE tree for 64 sites (8 per warp); conditional
+// likelihoods never leave the SM.
+//
+// Restates Phylo_ctmc.pruning (lib/phylo_ctmc.ml:83-98) with SV.mul / SV.shift (:33-40, :76-78), on
+// the same host-compiled accumulator/stack program as the 4-state fused kernel (pb_api.cu).
+//   * ACC (the running SV of the subtree being folded) lives in registers in the DMMA C-fragment
+//     layout: rows = states, columns = the warp's 8 sites.
+//   * A mat-vec P.ACC is a GEMM [states x states] x [states x 8 sites]: ACC is written to a per-warp
+//     shared-memory tile (XOR-swizzled 64-byte rows), read back as B fragments, and multiplied by
+//     the branch's P, zero-padded to MP x (KP+4) and staged in shared memory for the whole CTA.
+//     The matrices arrive by cp.async, double buffered: matrix m+1 streams in from L2 while the
+//     tensor cores work on matrix m (one CTA barrier per matrix).
+//   * A leaf child is a column look-up in the leaf branch's matrix, read from a transposed,
+//     padded copy in global memory (a column is contiguous; the 1-2 MB of leaf matrices live in L2).
+//   * The stack holds C fragments lane-privately in shared memory: no layout change on push/pop.
+//   * Rescaling decisions and rescaled vectors are the reference's; the log-scale factors of a site
+//     are accumulated as (mantissa, binary exponent) and logged once at the root, as in fused4.
+// HBM traffic per site: ntaxa bytes in, 8 bytes out.  Bound: the FP64 tensor pipe.
+#pragma once
+#include "pb_kernels_dmma.cuh"
+#include "pb_kernels_fused.cuh"
+
+namespace pbk {
+
+template <int N>
+struct FdmmaShape {
+    using S = DmmaShape<N>;
+    static constexpr int MATSZ = S::MP * S::LD;          // doubles per staged (padded) inner matrix
+    static constexpr int XSZ = S::KP * 8;                // doubles per warp conversion tile
+    static constexpr int FRAG = S::MT * 4;               // doubles per lane per stack entry
+    static constexpr int NBUF = (N <= 32) ? 4 : 2;       // ring of staged inner matrices
+    static constexpr int CTAS = (N <= 32) ? 2 : 1;       // resident CTAs per SM the shared-memory budget is cut for
+    static constexpr size_t fixed_bytes(int ntaxa, int nops, int nmat)
+    {
+        return ((size_t)S::MP + (size_t)NBUF * MATSZ + 8 * XSZ) * sizeof(double) + (size_t)ntaxa * 64 +
+               (size_t)nops * sizeof(FusedOp2) + (size_t)nmat * sizeof(int) + 16;
+    }
+    static constexpr size_t level_bytes = (size_t)256 * FRAG * sizeof(double);
+};
+
+// Ppad[c][k] = P[c][inner_nodes[k]] zero-padded to MP x LD (row-major);
+// PTleaf[c][k] = transpose of P[c][leaf_nodes[k]] zero-padded to N columns x MP rows.
+template <int N>
+__global__ void fdmma_prepare(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
+                              const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
+                              double* __restrict__ Ppad, double* __restrict__ PTleaf)
+{
+    using S = DmmaShape<N>;
+    const int c = blockIdx.y, k = blockIdx.x;
+    if (k < ninner) {
+        const double* src = P + ((size_t)c * nnodes + inner_nodes[k]) * N * N;
+        double* dst = Ppad + ((size_t)c * ninner + k) * S::MP * S::LD;
+        for (int idx = threadIdx.x; idx < S::MP * S::LD; idx += blockDim.x) {
+            const int i = idx / S::LD, j = idx - i * S::LD;
+            dst[idx] = (i < N && j < N) ? src[i * N + j] : 0.0;
+        }
+    } else {
+        const int l = k - ninner;
+        const double* src = P + ((size_t)c * nnodes + leaf_nodes[l]) * N * N;
+        double* dst = PTleaf + ((size_t)c * nleaf + l) * N * S::MP;
+        for (int idx = threadIdx.x; idx < N * S::MP; idx += blockDim.x) {
+            const int s = idx / S::MP, i = idx - s * S::MP;
+            dst[idx] = (i < N) ? src[i * N + s] : 0.0;
+        }
+    }
+}
+
+// SV.shift on a C-fragment tile with the (mantissa, exponent) scale accumulators of the lane's two sites.
+template <int N>
+__device__ __forceinline__ void shift_frag_scaled(double (&v)[DmmaShape<N>::MT][4], Scale<false> (&sc)[2], int g, double thr)
+{
+    constexpr int MT = DmmaShape<N>::MT;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            if (mt * 16 + g < N) { mn = fmin(mn, v[mt][j]); mx = fmax(mx, v[mt][j]); }
+            if (mt * 16 + g + 8 < N) { mn = fmin(mn, v[mt][2 + j]); mx = fmax(mx, v[mt][2 + j]); }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (!(mn > thr)) {
+            const double inv = 1.0 / mx;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) { v[mt][j] = inv * v[mt][j]; v[mt][2 + j] = inv * v[mt][2 + j]; }
+            sc[j].add(mx);
+        }
+    }
+}
+
+// prog: FusedOp2 with offA / offB = compact inner (APPLY, APPLY_MUL_TIP.A, ACC_POP) or leaf index,
+// sh = tip row A | tip row B << 16.  mlist: compact inner indices in the order the program consumes them.
+// The first stack_smem stack levels live in shared memory, deeper ones in gstack (per CTA, L2-resident).
+template <int N>
+__global__ void __launch_bounds__(256, FdmmaShape<N>::CTAS)
+fused_dmma(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int stack_smem,
+           double* __restrict__ gstack, int gdepth,
+           const double* __restrict__ Ppad, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
+           const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
+           const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat)
+{
+    using S = DmmaShape<N>;
+    using F = FdmmaShape<N>;
+    constexpr int MP = S::MP, LD = S::LD, MT = S::MT, KS = S::KS, NBUF = F::NBUF;
+    extern __shared__ double shraw[];
+    double* shPi = shraw;                                   // [MP]
+    double* shM = shPi + MP;                                // [NBUF][MATSZ] ring of staged inner matrices
+    double* shX = shM + NBUF * F::MATSZ;                    // [8 warps][XSZ] C -> B conversion tiles
+    double* shS = shX + 8 * F::XSZ;                         // [stack_smem][FRAG][256 threads]
+    uint8_t* shT = reinterpret_cast<uint8_t*>(shS + (size_t)stack_smem * 256 * F::FRAG);   // [ntaxa][64]
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (size_t)ntaxa * 64);
+    int* shMl = reinterpret_cast<int*>(shOps + nops);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+    {
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
+        for (int idx = tid; idx < nops; idx += 256) dst[idx] = src[idx];
+        for (int idx = tid; idx < nmat; idx += 256) shMl[idx] = mlist[idx];
+    }
+    double* myX = shX + warp * F::XSZ;
+    gstack += (size_t)blockIdx.x * gdepth * 256 * F::FRAG;
+    auto slot = [&](int level) -> double* {                 // element k of the entry is slot[k * 256]
+        return (level < stack_smem ? shS + (size_t)level * 256 * F::FRAG
+                                   : gstack + (size_t)(level - stack_smem) * 256 * F::FRAG) + tid;
+    };
+    __syncthreads();
+    const int64_t ntiles = spad / 64;
+    const int64_t work = ntiles * ncat;
+
+    for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const int c = (int)(w / ntiles);
+        const int64_t tile0 = (w - (int64_t)c * ntiles) * 64;             // the CTA's 64 sites
+        const int64_t s0 = tile0 + warp * 8;                             // this warp's 8 sites
+        const double* Pc = Ppad + (size_t)c * ninner * F::MATSZ;
+        const double* PTc = PTleaf + (size_t)c * nleaf * N * MP;
+        __syncthreads();                                     // the previous tile is done with shT and shM
+        // tips of the CTA's 64 sites, every taxon: 4 x 16-byte chunks per row
+        for (int idx = tid; idx < ntaxa * 4; idx += 256) {
+            const int row = idx >> 2, q = idx & 3;
+            cp_async16(shT + row * 64 + q * 16, tips + (int64_t)row * tips_ld + tile0 + q * 16);
+        }
+        cp_async_commit();
+        auto load_matrix = [&](int m) {                      // inner matrix #m of the program -> ring slot m % NBUF
+            if (m < nmat) {
+                const double* src = Pc + (size_t)shMl[m] * F::MATSZ;
+                double* dst = shM + (m % NBUF) * F::MATSZ;
+                for (int idx = tid; idx < F::MATSZ / 2; idx += 256) cp_async16(dst + idx * 2, src + idx * 2);
+            }
+            cp_async_commit();                               // (an empty group keeps the group count uniform)
+        };
+#pragma unroll
+        for (int m = 0; m < NBUF - 1; m++) load_matrix(m);
+        int m_next = 0;                                      // next matrix the program will consume
+        auto acquire = [&]() -> const double* {             // matrix m_next has landed; refill the slot of m_next - 1
+            cp_async_wait<NBUF - 2>();
+            __syncthreads();
+            load_matrix(m_next + NBUF - 1);
+            const double* Pm = shM + (m_next % NBUF) * F::MATSZ;
+            m_next++;
+            return Pm;
+        };
+        cp_async_wait<NBUF - 1>();
+        __syncthreads();                                     // tips landed
+
+        double acc[MT][4];
+        Scale<false> sc[2];
+        sc[0].init(); sc[1].init();
+        int sp = 0;
+
+        // y = P . x   (x in C-fragment registers -> swizzled smem tile -> B fragments -> DMMA)
+        auto apply = [&](const double* Pm, const double (&x)[MT][4], double (&y)[MT][4]) {
+            __syncwarp();
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const int r0 = mt * 16 + g, r1 = r0 + 8;     // rows >= N hold zeros (P is zero padded)
+                if (r0 < S::KP) *reinterpret_cast<double2*>(myX + r0 * 8 + ((tig ^ (r0 & 3)) << 1)) = make_double2(x[mt][0], x[mt][1]);
+                if (r1 < S::KP) *reinterpret_cast<double2*>(myX + r1 * 8 + ((tig ^ (r1 & 3)) << 1)) = make_double2(x[mt][2], x[mt][3]);
+            }
+            __syncwarp();
+            double b[KS][2];
+            const int off = (((g >> 1) ^ tig) << 1) + (g & 1);
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                b[ks][0] = myX[(ks * 8 + tig) * 8 + off];
+                b[ks][1] = myX[(ks * 8 + tig + 4) * 8 + off];
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) y[mt][0] = y[mt][1] = y[mt][2] = y[mt][3] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double* r0 = Pm + (mt * 16 + g) * LD + tig + ks * 8;
+                    const double* r1 = r0 + 8 * LD;
+                    dmma_16x8x8(y[mt], r0[0], r1[0], r0[4], r1[4], b[ks][0], b[ks][1]);
+                }
+            }
+        };
+        // column look-up of a leaf branch: the lane's rows for its two sites
+        auto leaf_cols = [&](int leaf, int tiprow, double (&t)[MT][4]) {
+            const uint8_t* tb = shT + tiprow * 64 + warp * 8 + tig * 2;
+            const double* ca = PTc + ((size_t)leaf * N + min((int)tb[0], N - 1)) * MP;
+            const double* cb = PTc + ((size_t)leaf * N + min((int)tb[1], N - 1)) * MP;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                t[mt][0] = ca[mt * 16 + g]; t[mt][1] = cb[mt * 16 + g];
+                t[mt][2] = ca[mt * 16 + g + 8]; t[mt][3] = cb[mt * 16 + g + 8];
+            }
+        };
+
+        for (int ip = 0; ip < nops; ip++) {
+            const int4 opw = reinterpret_cast<const int4*>(shOps)[ip];
+            const int code = opw.x & 0xff, rowA = opw.w & 0xffff, rowB = (opw.w >> 16) & 0xffff;
+            if (code == FOP_APPLY_MUL_TIP) {
+                double y[MT][4], t[MT][4];
+                leaf_cols(opw.z, rowB, t);
+                apply(acquire(), acc, y);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = y[mt][e] * t[mt][e];
+                shift_frag_scaled<N>(acc, sc, g, thr);
+            } else if (code == FOP_ACC_POP) {
+                const double* top = slot(--sp);
+                double y[MT][4], x[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) x[mt][e] = top[(mt * 4 + e) * 256];
+                apply(acquire(), acc, y);
+                apply(acquire(), x, acc);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = y[mt][e] * acc[mt][e];
+                shift_frag_scaled<N>(acc, sc, g, thr);
+            } else if (code == FOP_TIP_TIP) {
+                double t[MT][4];
+                leaf_cols(opw.y, rowA, acc);
+                leaf_cols(opw.z, rowB, t);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = acc[mt][e] * t[mt][e];
+                shift_frag_scaled<N>(acc, sc, g, thr);
+            } else if (code == FOP_TIP) {
+                leaf_cols(opw.y, rowA, acc);
+            } else if (code == FOP_APPLY) {
+                double y[MT][4];
+                apply(acquire(), acc, y);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = y[mt][e];
+            } else if (code == FOP_MUL_TIP) {
+                double t[MT][4];
+                leaf_cols(opw.y, rowA, t);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = acc[mt][e] * t[mt][e];
+                shift_frag_scaled<N>(acc, sc, g, thr);
+            } else if (code == FOP_POP_MUL) {
+                const double* top = slot(--sp);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[mt][e] = top[(mt * 4 + e) * 256] * acc[mt][e];
+                shift_frag_scaled<N>(acc, sc, g, thr);
+            } else if (code == FOP_ROOT) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double p0 = shPi[mt * 16 + g], p1 = shPi[mt * 16 + g + 8];
+                    acc[mt][0] *= p0; acc[mt][1] *= p0; acc[mt][2] *= p1; acc[mt][3] *= p1;
+                }
+                if (shift_at_root) shift_frag_scaled<N>(acc, sc, g, thr);
+                double sum[2] = {0.0, 0.0};
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {            // padded rows hold exact zeros
+                    sum[0] += acc[mt][0] + acc[mt][2];
+                    sum[1] += acc[mt][1] + acc[mt][3];
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+                    sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+                }
+                if (g == 0)
+                    *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                        make_double2(log(sum[0]) + sc[0].value(), log(sum[1]) + sc[1].value());
+            }
+            if (opw.x & FOP_PUSH_AFTER) {
+                double* top = slot(sp++);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) top[(mt * 4 + e) * 256] = acc[mt][e];
+            }
+        }
+        cp_async_wait<0>();                                  // drain the trailing (empty) groups
+    }
+}
+
+// Shared-memory plan: how many stack levels stay on chip (the rest spill to an L2-resident scratch).
+// Returns false when even the fixed part (matrix ring, conversion tiles, the tile's tips, the program)
+// does not fit — the caller then takes the level-scheduled path.
+template <int N>
+bool fused_dmma_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+{
+    using F = FdmmaShape<N>;
+    const size_t budget = F::CTAS == 1 ? smem_optin : (smem_optin + 1024) / F::CTAS - 1024;
+    const size_t fixed = F::fixed_bytes(ntaxa, nops, nmat);
+    if (fixed > budget) return false;
+    const int fit = (int)std::min<size_t>((budget - fixed) / F::level_bytes, (size_t)stack_depth);
+    *stack_smem = fit;
+    *smem = fixed + (size_t)fit * F::level_bytes;
+    return true;
+}
+
+inline bool fused_dmma_plan(int n, size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+{
+    if (n == 20) return fused_dmma_plan_n<20>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
+    if (n == 61) return fused_dmma_plan_n<61>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
+    return false;
+}
+
+inline size_t fused_dmma_matsz(int n) { return n == 20 ? FdmmaShape<20>::MATSZ : FdmmaShape<61>::MATSZ; }
+inline size_t fused_dmma_leafsz(int n) { return n == 20 ? 20 * DmmaShape<20>::MP : 61 * DmmaShape<61>::MP; }
+inline size_t fused_dmma_frag(int n) { return n == 20 ? FdmmaShape<20>::FRAG : FdmmaShape<61>::FRAG; }
+
+template <int N>
+int fused_dmma_grid_n(int sm_count, size_t smem, int64_t work)
+{
+    auto kern = fused_dmma<N>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) return -1;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)sm_count * occ));
+}
+
+inline int fused_dmma_grid(int n, int sm_count, size_t smem, int64_t work)
+{
+    return n == 20 ? fused_dmma_grid_n<20>(sm_count, smem, work) : fused_dmma_grid_n<61>(sm_count, smem, work);
+}
+
+struct FusedDmmaArgs {
+    const FusedOp2* prog; int nops; const int* mlist; int nmat; int stack_smem; double* gstack; int gdepth;
+    const double* Ppad; const double* PTleaf; int ninner, nleaf, ncat;
+    const uint8_t* tips; int64_t tips_ld; int ntaxa; int64_t spad;
+    const double* pi; double thr; int shift_at_root; double* site_cat;
+};
+
+template <int N>
+void launch_fused_dmma_n(const FusedDmmaArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+    fused_dmma<N><<<grid, 256, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
+                                               a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
+                                               a.pi, a.thr, a.shift_at_root, a.site_cat);
+}
+
+inline void launch_fused_dmma(int n, const FusedDmmaArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+    if (n == 20) launch_fused_dmma_n<20>(a, grid, smem, stream);
+    else launch_fused_dmma_n<61>(a, grid, smem, stream);
+}
+
+inline void launch_fdmma_prepare(int n, const double* P, const int* inner_nodes, int ninner, const int* leaf_nodes, int nleaf,
+                                 int nnodes, int ncat, double* Ppad, double* PTleaf, cudaStream_t stream)
+{
+    dim3 grid(ninner + nleaf, ncat);
+    if (n == 20) fdmma_prepare<20><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Ppad, PTleaf);
+    else fdmma_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Ppad, PTleaf);
+}
+
+}  // namespace pbk

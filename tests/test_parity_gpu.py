@@ -222,7 +222,7 @@ def test_dense_kernel_modes(model, ntaxa, nsites, opts):
     P = case.host_P()
     expect = oracle_per_site(case, P)
     for keep in (False, True):
-        with run_ctx(case, "direct", keep=keep, P=P) as ctx:
+        with run_ctx(case, "direct", level=True, keep=keep, P=P) as ctx:
             for k, v in opts.items():
                 ctx.set_option(k, v)
             assert ctx.path_name == ("level_dense" if "dense_scalar" in opts else "level_dmma")
@@ -236,6 +236,83 @@ def test_dense_kernel_modes(model, ntaxa, nsites, opts):
                     gv, gc = ctx.get_clv(v)
                     np.testing.assert_allclose(gv[5], clv[v], rtol=1e-11, atol=1e-300)
                     np.testing.assert_allclose(gc[5], car[v], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("model,ntaxa,nsites,ncat,tree_kind", [
+    ("wag", 64, 1500, 1, "bd"), ("wag", 40, 2100, 3, "random"), ("wag", 150, 333, 2, "bd"), ("wag", 3, 65, 1, "bd"),
+    ("mg94", 32, 700, 1, "bd"), ("mg94", 24, 900, 2, "random"), ("mutsel", 70, 129, 1, "bd"), ("mg94", 2, 64, 1, "bd"),
+])
+def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind):
+    """The site-resident tensor-core kernel (default path for 20 / 61 states): birth-death and random
+    trees, several categories, ragged site counts, trees deep enough that the stack spills out of
+    shared memory (61 states keeps at most 3 levels on chip), Felsenstein mode, and the fall-back switch."""
+    case = cases.make_case("fd" + model, model, ntaxa, nsites, ncat=ncat, seed=7, tree_kind=tree_kind)
+    P = case.host_P()
+    expect = oracle_per_site(case, P)
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name == "fused_dmma"
+        total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, expect)
+        total2, per_site2 = ctx.loglik(per_site=True)            # bit-reproducible
+        assert total2 == total and np.array_equal(per_site, per_site2)
+        ctx.set_option("fused_dmma", 0)
+        assert ctx.path_name == "level_dmma"
+        total3, per_site3 = ctx.loglik(per_site=True)
+        check(per_site3, total3, expect)
+    with run_ctx(case, "direct", mode=_lib.PB_MODE_FELSENSTEIN, P=P) as ctx:
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P, _lib.PB_MODE_FELSENSTEIN))
+
+
+def test_fused_dmma_balanced_tree_spills_the_stack():
+    """A perfectly balanced 64-taxon tree needs 5 stack levels: more than shared memory holds for 61 states."""
+    from phylogenetics_b200 import tree as T, synthetic, models
+    rng = np.random.default_rng(21)
+    nodes = [T.leaf(i) for i in range(64)]
+    while len(nodes) > 1:
+        nodes = [T.binary_node(None, T.branch(float(rng.uniform(0.02, 0.4)), nodes[i]),
+                               T.branch(float(rng.uniform(0.02, 0.4)), nodes[i + 1])) for i in range(0, len(nodes), 2)]
+    flat = T.flatten(nodes[0])
+    bl = flat.branch_lengths(float)
+    np_ = models.Nucleotide_process.random_gtr(rng, 10.0)
+    p = dict(nucleotide_rates=models.Nucleotide_process.rate_matrix(np_),
+             nucleotide_stat_dist=models.Nucleotide_process.stationary_distribution(np_), omega=0.4)
+    Q, pi = models.MG94.rate_matrix(p), models.MG94.stationary_distribution(p)
+    P = synthetic.host_transition_matrices(Q, pi, bl)
+    tips = synthetic.simulate_alignment(rng, flat, P, pi, 200)
+    case = cases.Case("balanced", flat, bl, Q, pi, tips)
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name == "fused_dmma"
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P))
+
+
+def test_fused_dmma_kary_tree():
+    """Multifurcating and unary nodes through the tensor-core program (TIP / MUL_TIP / APPLY / POP_MUL ops)."""
+    from phylogenetics_b200 import tree as T, synthetic
+    rng = np.random.default_rng(5)
+    t = T.node(None, [
+        T.branch(0.11, T.leaf(0)),
+        T.branch(0.2, T.node(None, [T.branch(0.05, T.leaf(1)), T.branch(0.3, T.leaf(2)), T.branch(0.1, T.leaf(3)),
+                                    T.branch(0.4, T.node(None, [T.branch(0.2, T.leaf(4)), T.branch(0.15, T.leaf(5))]))])),
+        T.branch(0.07, T.node(None, [T.branch(0.3, T.node(None, [T.branch(0.1, T.leaf(6)), T.branch(0.2, T.leaf(7))]))])),
+        T.branch(0.25, T.node(None, [T.branch(0.2, T.node(None, [T.branch(0.3, T.leaf(8)), T.branch(0.1, T.leaf(9))])),
+                                     T.branch(0.1, T.node(None, [T.branch(0.2, T.leaf(10)), T.branch(0.6, T.leaf(11))])),
+                                     T.branch(0.3, T.leaf(12))])),
+    ])
+    flat = T.flatten(t)
+    bl = flat.branch_lengths(float)
+    w = cases.wag()
+    pi = w.freqs / w.freqs.sum()
+    from phylogenetics_b200 import models
+    Q = models.Rate_matrix.scaled_rate_matrix(pi, models.Rate_matrix.make(20, lambda i, j: w.rate_matrix[i, j] * pi[j]))
+    P = synthetic.host_transition_matrices(Q, pi, bl)
+    tips = synthetic.simulate_alignment(rng, flat, P, pi, 333)
+    case = cases.Case("kary20", flat, bl, Q, pi, tips)
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name == "fused_dmma"
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, oracle_per_site(case, P))
 
 
 @pytest.mark.parametrize("minb", [3, 4, 5, 6])

@@ -37,7 +37,7 @@ def problem():
 
 
 @pytest.mark.parametrize("source", ["expm_kernel", "host_matrices", "eigensystem"])
-@pytest.mark.parametrize("opts", [{}, {"dmma_version": 1}, {"dense_scalar": 1}])
+@pytest.mark.parametrize("opts", [{}, {"fused_dmma": 0}, {"fused_dmma": 0, "dmma_version": 1}, {"dense_scalar": 1}])
 def test_gpu_prints_the_reference_value(problem, source, opts):
     fx, f, bl, q, freqs, tips = problem
     with LikelihoodContext(20, 1, len(fx["tip_states"])) as ctx:
