@@ -308,6 +308,348 @@ fused_dmma(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ 
     }
 }
 
+// --------------------------------------------------------------------------
+// fused_dmma2: the same program with the warps DECOUPLED.  In fused_dmma the CTA barrier per branch
+// matrix keeps all warps in the same phase, so the tensor pipe idles whenever they rescale, convert
+// layouts or gather tip columns together (ncu: 52 % DMMA pipe at 61 states, 34 % at 20).  Here
+//   * a producer warp streams the inner branch matrices, cut into k-panels, through a ring in
+//     shared memory with 1-D bulk copies (cp.async.bulk, one elected lane) completing on "full"
+//     mbarriers; every compute warp releases a panel with one arrive on its "empty" mbarrier;
+//   * compute warps never meet at a CTA barrier: each runs the program for its own 8 sites at its
+//     own pace (up to a ring's worth apart), so one warp's rescaling overlaps another's DMMAs;
+//   * a panel holds, per parent-state row, the 8 k-columns of one k-step reordered as
+//     (k, k+4) pairs: one 16-byte load per row gives both A-fragment halves, conflict free;
+//   * stack entries are stored in the B-fragment tile layout, so the popped operand of a
+//     two-inner-children node feeds the tensor cores without passing through registers.
+// Sites are split over CTAs in 8-site units (balanced to one unit), every CTA walks all categories.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// Release of a ring slot whose contents were read with ld.shared: the arrive must not be issued before
+// the loads have RETURNED — an mbarrier arrive does not queue behind earlier shared-memory loads, and
+// with 15 warps bursting 16-byte fragment loads the load queue can be deeper than the refill latency
+// of the slot (seen on B200 as rare stale A fragments).  `witness` is the AND of the high words of the
+// loaded values: the arrive is predicated on it not being all ones (never true for transition
+// probabilities), which makes the instruction wait on the loads' scoreboards.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* b, uint32_t witness)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0xffffffff;\n @p mbarrier.arrive.shared::cta.b64 _, [%0];\n}"
+                 ::"r"(smem_u32(b)), "r"(witness) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+template <int N>
+struct Fd2Shape {
+    using S = DmmaShape<N>;
+    static constexpr int NW = 15;                               // compute warps per CTA (+1 producer warp = 512 threads, 128 registers each)
+    static constexpr int KPP = (N <= 32) ? S::KS : 1;           // k-steps per ring panel
+    static constexpr int NPAN = S::KS / KPP;                    // panels per matrix
+    static constexpr int PSZ = S::MP * 8 * KPP;                 // doubles per panel
+    static constexpr int MATSZ = S::MP * 8 * S::KS;             // doubles per panelled matrix
+    static constexpr int XSZ = S::KP * 8;                       // doubles per 8-site tile [KP states][8 sites]
+    static constexpr int NSLOT = (N <= 32) ? 6 : 14;            // ring slots
+    static constexpr size_t BAR_BYTES = 256;
+    static constexpr size_t fixed_bytes(int ntaxa, int nops, int nmat)
+    {
+        return BAR_BYTES + ((size_t)NSLOT * PSZ + S::MP + (size_t)NW * XSZ) * sizeof(double) + (size_t)NW * ntaxa * 8 +
+               (size_t)nops * sizeof(FusedOp2) + (size_t)nmat * sizeof(int) + 16;
+    }
+    static constexpr size_t level_bytes = (size_t)NW * XSZ * sizeof(double);
+};
+
+// Apanel[c][k][ks][row][tig][h] = P[c][inner_nodes[k]][row][ks*8 + tig + 4h], zero padded.
+template <int N>
+__global__ void fdmma2_prepare(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
+                               const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
+                               double* __restrict__ Apanel, double* __restrict__ PTleaf)
+{
+    using S = DmmaShape<N>;
+    using F = Fd2Shape<N>;
+    const int c = blockIdx.y, k = blockIdx.x;
+    if (k < ninner) {
+        const double* src = P + ((size_t)c * nnodes + inner_nodes[k]) * N * N;
+        double* dst = Apanel + ((size_t)c * ninner + k) * F::MATSZ;
+        for (int idx = threadIdx.x; idx < F::MATSZ; idx += blockDim.x) {
+            const int h = idx & 1, tig = (idx >> 1) & 3, row = (idx >> 3) % S::MP, ks = idx / (8 * S::MP);
+            const int col = ks * 8 + tig + 4 * h;
+            dst[idx] = (row < N && col < N) ? src[row * N + col] : 0.0;
+        }
+    } else {
+        const int l = k - ninner;
+        const double* src = P + ((size_t)c * nnodes + leaf_nodes[l]) * N * N;
+        double* dst = PTleaf + ((size_t)c * nleaf + l) * N * S::MP;
+        for (int idx = threadIdx.x; idx < N * S::MP; idx += blockDim.x) {
+            const int s = idx / S::MP, i = idx - s * S::MP;
+            dst[idx] = (i < N) ? src[i * N + s] : 0.0;
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__((Fd2Shape<N>::NW + 1) * 32, 1)
+fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int stack_smem,
+            double* __restrict__ gstack, int gdepth,
+            const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
+            const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
+            const double* __restrict__ pi, double thr, int shift_at_root, int stagger, double* __restrict__ site_cat)
+{
+    using S = DmmaShape<N>;
+    using F = Fd2Shape<N>;
+    constexpr int MP = S::MP, MT = S::MT, NW = F::NW, NSLOT = F::NSLOT, KPP = F::KPP, NPAN = F::NPAN;
+    extern __shared__ __align__(128) unsigned char shbytes[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(shbytes);              // [NSLOT]
+    uint64_t* empty = full + NSLOT;                                       // [NSLOT]
+    double* ring = reinterpret_cast<double*>(shbytes + F::BAR_BYTES);   // [NSLOT][PSZ]
+    double* shPi = ring + NSLOT * F::PSZ;                                 // [MP]
+    double* shX = shPi + MP;                                              // [NW][XSZ]
+    double* shS = shX + NW * F::XSZ;                                      // [stack_smem][NW][XSZ]
+    uint8_t* shT = reinterpret_cast<uint8_t*>(shS + (size_t)stack_smem * NW * F::XSZ);   // [NW][ntaxa][8]
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (size_t)NW * ntaxa * 8);
+    int* shMl = reinterpret_cast<int*>(shOps + nops);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; i++) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+    {
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
+        for (int idx = tid; idx < nops; idx += blockDim.x) dst[idx] = src[idx];
+        for (int idx = tid; idx < nmat; idx += blockDim.x) shMl[idx] = mlist[idx];
+    }
+    __syncthreads();                                         // the only CTA-wide barrier
+
+    // this CTA's 8-site units [lo, hi), NW per round
+    const int64_t units = spad / 8;
+    const int64_t lo = units * blockIdx.x / gridDim.x, hi = units * (blockIdx.x + 1) / gridDim.x;
+    const int rounds = (int)((hi - lo + NW - 1) / NW);
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() { if (++slot == NSLOT) { slot = 0; phase ^= 1; } };
+
+    if (warp == NW) {                                        // ---- producer: one lane feeds the ring
+        if (lane == 0) {
+            for (int c = 0; c < ncat; c++)
+                for (int r = 0; r < rounds; r++)
+                    for (int m = 0; m < nmat; m++) {
+                        const double* src = Apanel + ((size_t)c * ninner + shMl[m]) * F::MATSZ;
+                        for (int p = 0; p < NPAN; p++) {
+                            mbar_wait(empty + slot, phase ^ 1);
+                            mbar_expect_tx(full + slot, F::PSZ * sizeof(double));
+                            bulk_g2s(ring + slot * F::PSZ, src + p * F::PSZ, F::PSZ * sizeof(double), full + slot);
+                            advance();
+                        }
+                    }
+        }
+        return;
+    }
+
+    // ---- compute warps
+    double* myX = shX + warp * F::XSZ;
+    uint8_t* myT = shT + (size_t)warp * ntaxa * 8;
+    gstack += ((size_t)blockIdx.x * gdepth * NW + warp) * F::XSZ;
+    auto level_tile = [&](int level) -> double* {
+        return level < stack_smem ? shS + ((size_t)level * NW + warp) * F::XSZ
+                                  : gstack + (size_t)(level - stack_smem) * NW * F::XSZ;
+    };
+    const int boff = (((g >> 1) ^ tig) << 1) + (g & 1);     // B-fragment column of this lane in a swizzled row
+
+    // registers (C-fragment layout) -> 8-site tile [state][site], 16-byte chunk q of row r at q ^ (r & 3)
+    auto to_tile = [&](double* T, const double (&x)[MT][4]) {
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;         // rows >= N hold zeros
+            if (r0 < S::KP) *reinterpret_cast<double2*>(T + r0 * 8 + ((tig ^ (r0 & 3)) << 1)) = make_double2(x[mt][0], x[mt][1]);
+            if (r1 < S::KP) *reinterpret_cast<double2*>(T + r1 * 8 + ((tig ^ (r1 & 3)) << 1)) = make_double2(x[mt][2], x[mt][3]);
+        }
+        __syncwarp();
+    };
+    // y = P . x, x read as B fragments from a tile, P from the next NPAN panels of the ring
+    auto apply = [&](const double* T, double (&y)[MT][4]) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) y[mt][0] = y[mt][1] = y[mt][2] = y[mt][3] = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < NPAN; p++) {
+            double b[KPP][2];
+#pragma unroll
+            for (int kk = 0; kk < KPP; kk++) {
+                const int ks = p * KPP + kk;
+                b[kk][0] = T[(ks * 8 + tig) * 8 + boff];
+                b[kk][1] = T[(ks * 8 + tig + 4) * 8 + boff];
+            }
+            mbar_wait(full + slot, phase);
+            const double* A = ring + slot * F::PSZ + g * 8 + tig * 2;
+            uint32_t witness = 0xffffffffu;
+#pragma unroll
+            for (int kk = 0; kk < KPP; kk++) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double2 lo2 = *reinterpret_cast<const double2*>(A + (kk * MP + mt * 16) * 8);
+                    const double2 hi2 = *reinterpret_cast<const double2*>(A + (kk * MP + mt * 16 + 8) * 8);
+                    witness &= (uint32_t)__double2hiint(lo2.x) & (uint32_t)__double2hiint(hi2.x);
+                    dmma_16x8x8(y[mt], lo2.x, hi2.x, lo2.y, hi2.y, b[kk][0], b[kk][1]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after(empty + slot, witness);
+            advance();
+        }
+    };
+    auto leaf_ptrs = [&](const double* PTc, int leaf, int tiprow, const double*& ca, const double*& cb) {
+        const uint8_t* tb = myT + tiprow * 8 + tig * 2;
+        ca = PTc + ((size_t)leaf * N + min((int)tb[0], N - 1)) * MP + g;
+        cb = PTc + ((size_t)leaf * N + min((int)tb[1], N - 1)) * MP + g;
+    };
+
+    if (stagger > 0 && (warp & 4)) __nanosleep(stagger);     // start half of the warps out of phase
+
+    for (int c = 0; c < ncat; c++) {
+        const double* PTc = PTleaf + (size_t)c * nleaf * N * MP;
+        for (int r = 0; r < rounds; r++) {
+            const int64_t unit = lo + (int64_t)r * NW + warp;
+            if (unit >= hi) {                                // no sites left for this warp: keep the ring moving
+                for (int p = 0; p < nmat * NPAN; p++) {
+                    mbar_wait(full + slot, phase);
+                    if (lane == 0) mbar_arrive(empty + slot);
+                    advance();
+                }
+                continue;
+            }
+            const int64_t s0 = unit * 8;
+            __syncwarp();
+            for (int row = lane; row < ntaxa; row += 32)
+                *reinterpret_cast<uint2*>(myT + row * 8) = *reinterpret_cast<const uint2*>(tips + (int64_t)row * tips_ld + s0);
+            __syncwarp();
+
+            double acc[MT][4];
+            Scale<false> sc[2];
+            sc[0].init(); sc[1].init();
+            int sp = 0;
+#pragma unroll 1
+            for (int ip = 0; ip < nops; ip++) {
+                const int4 opw = reinterpret_cast<const int4*>(shOps)[ip];
+                const int code = opw.x & 0xff, rowA = opw.w & 0xffff, rowB = (opw.w >> 16) & 0xffff;
+                if (code == FOP_APPLY_MUL_TIP) {
+                    double y[MT][4];
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.z, rowB, ca, cb);
+                    to_tile(myX, acc);
+                    apply(myX, y);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        acc[mt][0] = y[mt][0] * ca[mt * 16]; acc[mt][1] = y[mt][1] * cb[mt * 16];
+                        acc[mt][2] = y[mt][2] * ca[mt * 16 + 8]; acc[mt][3] = y[mt][3] * cb[mt * 16 + 8];
+                    }
+                    shift_frag_scaled<N>(acc, sc, g, thr);
+                } else if (code == FOP_ACC_POP) {
+                    double y[MT][4];
+                    to_tile(myX, acc);
+                    apply(myX, y);
+                    apply(level_tile(--sp), acc);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc[mt][e] = y[mt][e] * acc[mt][e];
+                    shift_frag_scaled<N>(acc, sc, g, thr);
+                } else if (code == FOP_TIP_TIP) {
+                    const double *ca, *cb, *da, *db;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+                    leaf_ptrs(PTc, opw.z, rowB, da, db);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        acc[mt][0] = ca[mt * 16] * da[mt * 16]; acc[mt][1] = cb[mt * 16] * db[mt * 16];
+                        acc[mt][2] = ca[mt * 16 + 8] * da[mt * 16 + 8]; acc[mt][3] = cb[mt * 16 + 8] * db[mt * 16 + 8];
+                    }
+                    shift_frag_scaled<N>(acc, sc, g, thr);
+                } else if (code == FOP_TIP) {
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        acc[mt][0] = ca[mt * 16]; acc[mt][1] = cb[mt * 16];
+                        acc[mt][2] = ca[mt * 16 + 8]; acc[mt][3] = cb[mt * 16 + 8];
+                    }
+                } else if (code == FOP_APPLY) {
+                    to_tile(myX, acc);
+                    apply(myX, acc);
+                } else if (code == FOP_MUL_TIP) {
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        acc[mt][0] *= ca[mt * 16]; acc[mt][1] *= cb[mt * 16];
+                        acc[mt][2] *= ca[mt * 16 + 8]; acc[mt][3] *= cb[mt * 16 + 8];
+                    }
+                    shift_frag_scaled<N>(acc, sc, g, thr);
+                } else if (code == FOP_POP_MUL) {
+                    const double* T = level_tile(--sp);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const int r0 = mt * 16 + g, r1 = r0 + 8;
+                        if (r0 < S::KP) {
+                            const double2 v = *reinterpret_cast<const double2*>(T + r0 * 8 + ((tig ^ (r0 & 3)) << 1));
+                            acc[mt][0] *= v.x; acc[mt][1] *= v.y;
+                        }
+                        if (r1 < S::KP) {
+                            const double2 v = *reinterpret_cast<const double2*>(T + r1 * 8 + ((tig ^ (r1 & 3)) << 1));
+                            acc[mt][2] *= v.x; acc[mt][3] *= v.y;
+                        }
+                    }
+                    shift_frag_scaled<N>(acc, sc, g, thr);
+                } else if (code == FOP_ROOT) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double p0 = shPi[mt * 16 + g], p1 = shPi[mt * 16 + g + 8];
+                        acc[mt][0] *= p0; acc[mt][1] *= p0; acc[mt][2] *= p1; acc[mt][3] *= p1;
+                    }
+                    if (shift_at_root) shift_frag_scaled<N>(acc, sc, g, thr);
+                    double sum[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {        // padded rows hold exact zeros
+                        sum[0] += acc[mt][0] + acc[mt][2];
+                        sum[1] += acc[mt][1] + acc[mt][3];
+                    }
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+                        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+                    }
+                    if (g == 0)
+                        *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                            make_double2(log(sum[0]) + sc[0].value(), log(sum[1]) + sc[1].value());
+                }
+                if (opw.x & FOP_PUSH_AFTER) to_tile(level_tile(sp++), acc);
+            }
+        }
+    }
+}
+
 // Shared-memory plan: how many stack levels stay on chip (the rest spill to an L2-resident scratch).
 // Returns false when even the fixed part (matrix ring, conversion tiles, the tile's tips, the program)
 // does not fit — the caller then takes the level-scheduled path.
@@ -377,6 +719,63 @@ inline void launch_fdmma_prepare(int n, const double* P, const int* inner_nodes,
     dim3 grid(ninner + nleaf, ncat);
     if (n == 20) fdmma_prepare<20><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Ppad, PTleaf);
     else fdmma_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Ppad, PTleaf);
+}
+
+// ---- fused_dmma2 host side
+template <int N>
+bool fused_dmma2_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+{
+    using F = Fd2Shape<N>;
+    const size_t fixed = F::fixed_bytes(ntaxa, nops, nmat);
+    if (fixed > smem_optin) return false;
+    const int fit = (int)std::min<size_t>((smem_optin - fixed) / F::level_bytes, (size_t)stack_depth);
+    *stack_smem = fit;
+    *smem = fixed + (size_t)fit * F::level_bytes;
+    return true;
+}
+
+inline bool fused_dmma2_plan(int n, size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+{
+    if (n == 20) return fused_dmma2_plan_n<20>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
+    if (n == 61) return fused_dmma2_plan_n<61>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
+    return false;
+}
+
+inline size_t fused_dmma2_matsz(int n) { return n == 20 ? Fd2Shape<20>::MATSZ : Fd2Shape<61>::MATSZ; }
+inline size_t fused_dmma2_tilesz(int n) { return n == 20 ? Fd2Shape<20>::XSZ * Fd2Shape<20>::NW : Fd2Shape<61>::XSZ * Fd2Shape<61>::NW; }
+
+template <int N>
+int launch_fused_dmma2_n(const FusedDmmaArgs& a, int stagger, int sm_count, size_t smem, cudaStream_t stream)
+{
+    using F = Fd2Shape<N>;
+    auto kern = fused_dmma2<N>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    const int64_t units = a.spad / 8;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + F::NW - 1) / F::NW, sm_count));
+    kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
+                                                   a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
+                                                   a.pi, a.thr, a.shift_at_root, stagger, a.site_cat);
+    return grid;
+}
+
+inline int launch_fused_dmma2(int n, const FusedDmmaArgs& a, int stagger, int sm_count, size_t smem, cudaStream_t stream)
+{
+    return n == 20 ? launch_fused_dmma2_n<20>(a, stagger, sm_count, smem, stream)
+                   : launch_fused_dmma2_n<61>(a, stagger, sm_count, smem, stream);
+}
+
+inline int fused_dmma2_grid(int n, int sm_count, int64_t spad)
+{
+    const int nw = n == 20 ? Fd2Shape<20>::NW : Fd2Shape<61>::NW;
+    return (int)std::max<int64_t>(1, std::min<int64_t>((spad / 8 + nw - 1) / nw, sm_count));
+}
+
+inline void launch_fdmma2_prepare(int n, const double* P, const int* inner_nodes, int ninner, const int* leaf_nodes, int nleaf,
+                                  int nnodes, int ncat, double* Apanel, double* PTleaf, cudaStream_t stream)
+{
+    dim3 grid(ninner + nleaf, ncat);
+    if (n == 20) fdmma2_prepare<20><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
+    else fdmma2_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
 }
 
 }  // namespace pbk

@@ -242,7 +242,8 @@ def test_dense_kernel_modes(model, ntaxa, nsites, opts):
     ("wag", 64, 1500, 1, "bd"), ("wag", 40, 2100, 3, "random"), ("wag", 150, 333, 2, "bd"), ("wag", 3, 65, 1, "bd"),
     ("mg94", 32, 700, 1, "bd"), ("mg94", 24, 900, 2, "random"), ("mutsel", 70, 129, 1, "bd"), ("mg94", 2, 64, 1, "bd"),
 ])
-def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind):
+@pytest.mark.parametrize("version", [2, 1])
+def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
     """The site-resident tensor-core kernel (default path for 20 / 61 states): birth-death and random
     trees, several categories, ragged site counts, trees deep enough that the stack spills out of
     shared memory (61 states keeps at most 3 levels on chip), Felsenstein mode, and the fall-back switch."""
@@ -250,6 +251,7 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind):
     P = case.host_P()
     expect = oracle_per_site(case, P)
     with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("fused_dmma_version", version)
         assert ctx.path_name == "fused_dmma"
         total, per_site = ctx.loglik(per_site=True)
         check(per_site, total, expect)
@@ -260,6 +262,7 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind):
         total3, per_site3 = ctx.loglik(per_site=True)
         check(per_site3, total3, expect)
     with run_ctx(case, "direct", mode=_lib.PB_MODE_FELSENSTEIN, P=P) as ctx:
+        ctx.set_option("fused_dmma_version", version)
         total, per_site = ctx.loglik(per_site=True)
     check(per_site, total, oracle_per_site(case, P, _lib.PB_MODE_FELSENSTEIN))
 
@@ -281,10 +284,14 @@ def test_fused_dmma_balanced_tree_spills_the_stack():
     P = synthetic.host_transition_matrices(Q, pi, bl)
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 200)
     case = cases.Case("balanced", flat, bl, Q, pi, tips)
-    with run_ctx(case, "direct", P=P) as ctx:
-        assert ctx.path_name == "fused_dmma"
-        total, per_site = ctx.loglik(per_site=True)
-    check(per_site, total, oracle_per_site(case, P))
+    expect = oracle_per_site(case, P)
+    for version, stagger in ((2, 0), (2, 2000), (1, 0)):
+        with run_ctx(case, "direct", P=P) as ctx:
+            ctx.set_option("fused_dmma_version", version)
+            ctx.set_option("fused_dmma_stagger", stagger)
+            assert ctx.path_name == "fused_dmma"
+            total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, expect)
 
 
 def test_fused_dmma_kary_tree():
@@ -309,10 +316,12 @@ def test_fused_dmma_kary_tree():
     P = synthetic.host_transition_matrices(Q, pi, bl)
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 333)
     case = cases.Case("kary20", flat, bl, Q, pi, tips)
-    with run_ctx(case, "direct", P=P) as ctx:
-        assert ctx.path_name == "fused_dmma"
-        total, per_site = ctx.loglik(per_site=True)
-    check(per_site, total, oracle_per_site(case, P))
+    for version in (2, 1):
+        with run_ctx(case, "direct", P=P) as ctx:
+            ctx.set_option("fused_dmma_version", version)
+            assert ctx.path_name == "fused_dmma"
+            total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, oracle_per_site(case, P))
 
 
 @pytest.mark.parametrize("minb", [3, 4, 5, 6])

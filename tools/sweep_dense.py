@@ -13,8 +13,12 @@ for name, model, ntaxa, nsites in [("c3", "wag", 64, 200_000), ("c4", "mg94", 32
     case = cases.make_case(name, model, ntaxa, nsites, seed=100)
     f = case.flat
     ref = None
-    for opts in ({}, {"dmma_tip_levels_v1": 0}, {"dmma_version": 1},
-                 {"dense_scalar": 1}):
+    variants = [{"fused_dmma_version": 2}, {"fused_dmma_version": 2, "fused_dmma_stagger": 1000},
+                {"fused_dmma_version": 2, "fused_dmma_stagger": 3000}, {"fused_dmma_version": 2, "fused_dmma_stagger": 10000},
+                {"fused_dmma_version": 1}, {"fused_dmma": 0}, {"fused_dmma": 0, "dmma_version": 1}, {"fused_dmma": 0, "dense_scalar": 1}]
+    if len(sys.argv) > 1:
+        variants = [json.loads(a) for a in sys.argv[1:]]
+    for opts in variants:
         with LikelihoodContext(case.n, nsites, f.nleaves) as ctx:
             ctx.set_tree(f, case.bl)
             ctx.set_rate_matrix(case.Q, case.pi)
