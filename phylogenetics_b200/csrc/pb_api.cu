@@ -127,6 +127,7 @@ struct pb_ctx {
     int fused_dmma = 1;                 // option "fused_dmma": site-resident tensor-core kernel for 20 / 61 states
     int fused_dmma_version = 2;         // option "fused_dmma_version": 2 = decoupled warps + bulk-copy ring, 1 = CTA-synchronous
     int fused_dmma_stagger = 0;         // option "fused_dmma_stagger": start delay (ns) of every other warp quad
+    int fused_dmma_spill = 0;           // option "fused_dmma_spill": test hook, all stack levels in the L2 scratch
     DevBuf<FusedOp2> d_fprog_d;
     DevBuf<int> d_mlist;
     DevBuf<double> d_Ppad, d_PTleaf, d_gstack;
@@ -233,9 +234,11 @@ int path_of(const pb_ctx* c)
     }
     if (!c->have_masks && pbk::dmma_supported(c->n) && !c->force_dense) {
         if (!level && c->have_tree && c->fused_dmma) {
-            int ssm = 0;
+            int ssm = 0, nslot = 0;
             size_t smem = 0;
-            if (pbk::fused_dmma_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem))
+            if ((c->fused_dmma_version == 2 &&
+                 pbk::fused_dmma2_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) ||
+                pbk::fused_dmma_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem))
                 return PATH_FUSED_DMMA;
         }
         const int mp = (c->n + 15) / 16 * 16, ld = (c->n + 7) / 8 * 8 + 4;
@@ -761,14 +764,13 @@ int launch_fused_dmma_path(pb_ctx* c)
 {
     const int n = c->n;
     const int ninner = (int)c->inner_nodes.size(), nleaf = (int)c->leaf_nodes.size();
-    int ssm = 0;
+    int ssm = 0, nslot = 0;
     size_t smem = 0;
     if (c->fused_dmma_version == 2 &&
-        pbk::fused_dmma2_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem)) {
-        if (const char* dbg = getenv("PB_DEBUG_FD2")) {
-            const int f = atoi(dbg);
-            if (f & 1) { smem -= (size_t)ssm * pbk::fused_dmma2_tilesz(n) * sizeof(double); ssm = 0; }
-            fprintf(stderr, "[fd2] dstack=%d ssm=%d smem=%zu nops=%zu nmat=%zu\n", c->dstack, ssm, smem, c->fprog_d.size(), c->mlist.size());
+        pbk::fused_dmma2_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) {
+        if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
+            smem -= (size_t)ssm * pbk::fused_dmma2_tilesz(n) * sizeof(double);
+            ssm = 0;
         }
         PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma2_matsz(n), 1)));
         PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma_leafsz(n), 1)));
@@ -776,12 +778,12 @@ int launch_fused_dmma_path(pb_ctx* c)
                                    c->d_Ppad.p, c->d_PTleaf.p, c->stream);
         c->launches++;
         const int grid = pbk::fused_dmma2_grid(n, c->sm_count, c->spad);
-        const int gdepth = c->dstack - ssm;
+        const int gdepth = c->dstack + 1 - ssm;
         PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * pbk::fused_dmma2_tilesz(n), 1)));
         pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,
                              c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
-        if (pbk::launch_fused_dmma2(n, a, c->fused_dmma_stagger, c->sm_count, smem, c->stream) < 1)
+        if (pbk::launch_fused_dmma2(n, a, nslot, c->fused_dmma_stagger, c->sm_count, smem, c->stream) < 1)
             return fail(c, PB_ERR_CUDA, "fused_dmma2 launch configuration failed");
         c->launches++;
         return PB_OK;
@@ -1616,6 +1618,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_dmma_version") {
         if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1 or 2");
         c->fused_dmma_version = iv;
+    } else if (k == "fused_dmma_spill") {
+        c->fused_dmma_spill = iv != 0;
     } else if (k == "fused_dmma_stagger") {
         if (iv < 0) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_stagger must be 0..1000000 ns");
         c->fused_dmma_stagger = iv;

@@ -93,6 +93,45 @@ __device__ __forceinline__ void shift_frag_scaled(double (&v)[DmmaShape<N>::MT][
     }
 }
 
+// The same SV.shift with fewer cross-lane steps: the `min v > thr` test is a per-lane predicate combined
+// by one ballot per site, and the maxima are reduced only when some site of the warp rescales, with the
+// two sites of a lane folded into one butterfly (even row groups carry site 0, odd ones site 1).
+template <int N>
+__device__ __forceinline__ void shift_frag_ballot(double (&v)[DmmaShape<N>::MT][4], Scale<false> (&sc)[2], int lane, double thr)
+{
+    constexpr int MT = DmmaShape<N>::MT;
+    const int g = lane >> 2, tig = lane & 3;
+    bool ok[2] = {true, true};
+    double mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            if (mt * 16 + g < N) { ok[j] = ok[j] && (v[mt][j] > thr); mx[j] = fmax(mx[j], v[mt][j]); }
+            if (mt * 16 + g + 8 < N) { ok[j] = ok[j] && (v[mt][2 + j] > thr); mx[j] = fmax(mx[j], v[mt][2 + j]); }
+        }
+    const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
+    if ((b0 & b1) == 0xffffffffu) return;                   // warp-uniform: nothing to rescale
+    const bool odd = g & 1;
+    double keep = odd ? mx[1] : mx[0];
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, odd ? mx[0] : mx[1], 4));
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, keep, 8));
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, keep, 16));
+    const double other = __shfl_xor_sync(0xffffffffu, keep, 4);
+    const double m[2] = {odd ? other : keep, odd ? keep : other};
+    const unsigned grp = 0x11111111u << tig;                // the 8 row groups holding this lane's two sites
+    const unsigned bits[2] = {b0, b1};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        if ((bits[j] & grp) != grp) {
+            const double inv = 1.0 / m[j];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) { v[mt][j] = inv * v[mt][j]; v[mt][2 + j] = inv * v[mt][2 + j]; }
+            sc[j].add(m[j]);
+        }
+    }
+}
+
 // prog: FusedOp2 with offA / offB = compact inner (APPLY, APPLY_MUL_TIP.A, ACC_POP) or leaf index,
 // sh = tip row A | tip row B << 16.  mlist: compact inner indices in the order the program consumes them.
 // The first stack_smem stack levels live in shared memory, deeper ones in gstack (per CTA, L2-resident).
@@ -370,14 +409,15 @@ struct Fd2Shape {
     static constexpr int PSZ = S::MP * 8 * KPP;                 // doubles per panel
     static constexpr int MATSZ = S::MP * 8 * S::KS;             // doubles per panelled matrix
     static constexpr int XSZ = S::KP * 8;                       // doubles per 8-site tile [KP states][8 sites]
-    static constexpr int NSLOT = (N <= 32) ? 6 : 14;            // ring slots
+    static constexpr int NSLOT_MAX = (N <= 32) ? 8 : 14;        // ring slots: as many as fit once the stack is on chip,
+    static constexpr int NSLOT_MIN = (N <= 32) ? 3 : 6;         // between these bounds (16 mbarrier pairs are reserved)
     static constexpr size_t BAR_BYTES = 256;
-    static constexpr size_t fixed_bytes(int ntaxa, int nops, int nmat)
+    static constexpr size_t fixed_bytes(int nslot, int ntaxa, int nops, int nmat)
     {
-        return BAR_BYTES + ((size_t)NSLOT * PSZ + S::MP + (size_t)NW * XSZ) * sizeof(double) + (size_t)NW * ntaxa * 8 +
+        return BAR_BYTES + ((size_t)nslot * PSZ + S::MP) * sizeof(double) + (((size_t)NW * ntaxa * 8 + 15) & ~(size_t)15) +
                (size_t)nops * sizeof(FusedOp2) + (size_t)nmat * sizeof(int) + 16;
     }
-    static constexpr size_t level_bytes = (size_t)NW * XSZ * sizeof(double);
+    static constexpr size_t level_bytes = (size_t)NW * XSZ * sizeof(double);   // one stack level (or the scratch tile) of all warps
 };
 
 // Apanel[c][k][ks][row][tig][h] = P[c][inner_nodes[k]][row][ks*8 + tig + 4h], zero padded.
@@ -410,7 +450,7 @@ __global__ void fdmma2_prepare(const double* __restrict__ P, const int* __restri
 
 template <int N>
 __global__ void __launch_bounds__((Fd2Shape<N>::NW + 1) * 32, 1)
-fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int stack_smem,
+fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int nslot, int stack_smem,
             double* __restrict__ gstack, int gdepth,
             const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
             const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
@@ -418,21 +458,20 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
 {
     using S = DmmaShape<N>;
     using F = Fd2Shape<N>;
-    constexpr int MP = S::MP, MT = S::MT, NW = F::NW, NSLOT = F::NSLOT, KPP = F::KPP, NPAN = F::NPAN;
+    constexpr int MP = S::MP, MT = S::MT, NW = F::NW, KPP = F::KPP, NPAN = F::NPAN;
     extern __shared__ __align__(128) unsigned char shbytes[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(shbytes);              // [NSLOT]
-    uint64_t* empty = full + NSLOT;                                       // [NSLOT]
-    double* ring = reinterpret_cast<double*>(shbytes + F::BAR_BYTES);   // [NSLOT][PSZ]
-    double* shPi = ring + NSLOT * F::PSZ;                                 // [MP]
-    double* shX = shPi + MP;                                              // [NW][XSZ]
-    double* shS = shX + NW * F::XSZ;                                      // [stack_smem][NW][XSZ]
+    uint64_t* full = reinterpret_cast<uint64_t*>(shbytes);              // [nslot] (16 reserved)
+    uint64_t* empty = full + 16;                                          // [nslot]
+    double* ring = reinterpret_cast<double*>(shbytes + F::BAR_BYTES);   // [nslot][PSZ]
+    double* shPi = ring + nslot * F::PSZ;                                 // [MP]
+    double* shS = shPi + MP;                                              // [stack_smem][NW][XSZ]: stack levels; the level above the top is scratch
     uint8_t* shT = reinterpret_cast<uint8_t*>(shS + (size_t)stack_smem * NW * F::XSZ);   // [NW][ntaxa][8]
-    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (size_t)NW * ntaxa * 8);
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (((size_t)NW * ntaxa * 8 + 15) & ~(size_t)15));
     int* shMl = reinterpret_cast<int*>(shOps + nops);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tig = lane & 3;
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; i++) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
+        for (int i = 0; i < nslot; i++) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < MP) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
@@ -450,7 +489,7 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
     const int rounds = (int)((hi - lo + NW - 1) / NW);
     int slot = 0;
     uint32_t phase = 0;
-    auto advance = [&]() { if (++slot == NSLOT) { slot = 0; phase ^= 1; } };
+    auto advance = [&]() { if (++slot == nslot) { slot = 0; phase ^= 1; } };
 
     if (warp == NW) {                                        // ---- producer: one lane feeds the ring
         if (lane == 0) {
@@ -470,7 +509,6 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
     }
 
     // ---- compute warps
-    double* myX = shX + warp * F::XSZ;
     uint8_t* myT = shT + (size_t)warp * ntaxa * 8;
     gstack += ((size_t)blockIdx.x * gdepth * NW + warp) * F::XSZ;
     auto level_tile = [&](int level) -> double* {
@@ -559,24 +597,26 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                     double y[MT][4];
                     const double *ca, *cb;
                     leaf_ptrs(PTc, opw.z, rowB, ca, cb);
-                    to_tile(myX, acc);
-                    apply(myX, y);
+                    double* X = level_tile(sp);              // scratch: the free level above the stack top
+                    to_tile(X, acc);
+                    apply(X, y);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
                         acc[mt][0] = y[mt][0] * ca[mt * 16]; acc[mt][1] = y[mt][1] * cb[mt * 16];
                         acc[mt][2] = y[mt][2] * ca[mt * 16 + 8]; acc[mt][3] = y[mt][3] * cb[mt * 16 + 8];
                     }
-                    shift_frag_scaled<N>(acc, sc, g, thr);
+                    shift_frag_ballot<N>(acc, sc, lane, thr);
                 } else if (code == FOP_ACC_POP) {
                     double y[MT][4];
-                    to_tile(myX, acc);
-                    apply(myX, y);
+                    double* X = level_tile(sp);
+                    to_tile(X, acc);
+                    apply(X, y);
                     apply(level_tile(--sp), acc);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                         for (int e = 0; e < 4; e++) acc[mt][e] = y[mt][e] * acc[mt][e];
-                    shift_frag_scaled<N>(acc, sc, g, thr);
+                    shift_frag_ballot<N>(acc, sc, lane, thr);
                 } else if (code == FOP_TIP_TIP) {
                     const double *ca, *cb, *da, *db;
                     leaf_ptrs(PTc, opw.y, rowA, ca, cb);
@@ -586,7 +626,7 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                         acc[mt][0] = ca[mt * 16] * da[mt * 16]; acc[mt][1] = cb[mt * 16] * db[mt * 16];
                         acc[mt][2] = ca[mt * 16 + 8] * da[mt * 16 + 8]; acc[mt][3] = cb[mt * 16 + 8] * db[mt * 16 + 8];
                     }
-                    shift_frag_scaled<N>(acc, sc, g, thr);
+                    shift_frag_ballot<N>(acc, sc, lane, thr);
                 } else if (code == FOP_TIP) {
                     const double *ca, *cb;
                     leaf_ptrs(PTc, opw.y, rowA, ca, cb);
@@ -596,8 +636,9 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                         acc[mt][2] = ca[mt * 16 + 8]; acc[mt][3] = cb[mt * 16 + 8];
                     }
                 } else if (code == FOP_APPLY) {
-                    to_tile(myX, acc);
-                    apply(myX, acc);
+                    double* X = level_tile(sp);
+                    to_tile(X, acc);
+                    apply(X, acc);
                 } else if (code == FOP_MUL_TIP) {
                     const double *ca, *cb;
                     leaf_ptrs(PTc, opw.y, rowA, ca, cb);
@@ -606,7 +647,7 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                         acc[mt][0] *= ca[mt * 16]; acc[mt][1] *= cb[mt * 16];
                         acc[mt][2] *= ca[mt * 16 + 8]; acc[mt][3] *= cb[mt * 16 + 8];
                     }
-                    shift_frag_scaled<N>(acc, sc, g, thr);
+                    shift_frag_ballot<N>(acc, sc, lane, thr);
                 } else if (code == FOP_POP_MUL) {
                     const double* T = level_tile(--sp);
 #pragma unroll
@@ -621,14 +662,14 @@ fused_dmma2(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                             acc[mt][2] *= v.x; acc[mt][3] *= v.y;
                         }
                     }
-                    shift_frag_scaled<N>(acc, sc, g, thr);
+                    shift_frag_ballot<N>(acc, sc, lane, thr);
                 } else if (code == FOP_ROOT) {
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
                         const double p0 = shPi[mt * 16 + g], p1 = shPi[mt * 16 + g + 8];
                         acc[mt][0] *= p0; acc[mt][1] *= p0; acc[mt][2] *= p1; acc[mt][3] *= p1;
                     }
-                    if (shift_at_root) shift_frag_scaled<N>(acc, sc, g, thr);
+                    if (shift_at_root) shift_frag_ballot<N>(acc, sc, lane, thr);
                     double sum[2] = {0.0, 0.0};
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {        // padded rows hold exact zeros
@@ -722,22 +763,29 @@ inline void launch_fdmma_prepare(int n, const double* P, const int* inner_nodes,
 }
 
 // ---- fused_dmma2 host side
+// Shared-memory plan: stack_depth + 1 tiles per warp are needed (the level above the top is the layout-
+// conversion scratch).  The ring gives up slots (down to NSLOT_MIN) before a level leaves the chip;
+// levels that still do not fit live in an L2-resident scratch (correct, slower).
 template <int N>
-bool fused_dmma2_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+bool fused_dmma2_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* nslot, int* stack_smem, size_t* smem)
 {
     using F = Fd2Shape<N>;
-    const size_t fixed = F::fixed_bytes(ntaxa, nops, nmat);
-    if (fixed > smem_optin) return false;
-    const int fit = (int)std::min<size_t>((smem_optin - fixed) / F::level_bytes, (size_t)stack_depth);
+    const int levels = stack_depth + 1;
+    if (F::fixed_bytes(F::NSLOT_MIN, ntaxa, nops, nmat) > smem_optin) return false;
+    int ns = F::NSLOT_MAX;
+    while (ns > F::NSLOT_MIN && F::fixed_bytes(ns, ntaxa, nops, nmat) + (size_t)levels * F::level_bytes > smem_optin) ns--;
+    const size_t fixed = F::fixed_bytes(ns, ntaxa, nops, nmat);
+    const int fit = (int)std::min<size_t>((smem_optin - fixed) / F::level_bytes, (size_t)levels);
+    *nslot = ns;
     *stack_smem = fit;
     *smem = fixed + (size_t)fit * F::level_bytes;
     return true;
 }
 
-inline bool fused_dmma2_plan(int n, size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* stack_smem, size_t* smem)
+inline bool fused_dmma2_plan(int n, size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* nslot, int* stack_smem, size_t* smem)
 {
-    if (n == 20) return fused_dmma2_plan_n<20>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
-    if (n == 61) return fused_dmma2_plan_n<61>(smem_optin, stack_depth, ntaxa, nops, nmat, stack_smem, smem);
+    if (n == 20) return fused_dmma2_plan_n<20>(smem_optin, stack_depth, ntaxa, nops, nmat, nslot, stack_smem, smem);
+    if (n == 61) return fused_dmma2_plan_n<61>(smem_optin, stack_depth, ntaxa, nops, nmat, nslot, stack_smem, smem);
     return false;
 }
 
@@ -745,23 +793,23 @@ inline size_t fused_dmma2_matsz(int n) { return n == 20 ? Fd2Shape<20>::MATSZ : 
 inline size_t fused_dmma2_tilesz(int n) { return n == 20 ? Fd2Shape<20>::XSZ * Fd2Shape<20>::NW : Fd2Shape<61>::XSZ * Fd2Shape<61>::NW; }
 
 template <int N>
-int launch_fused_dmma2_n(const FusedDmmaArgs& a, int stagger, int sm_count, size_t smem, cudaStream_t stream)
+int launch_fused_dmma2_n(const FusedDmmaArgs& a, int nslot, int stagger, int sm_count, size_t smem, cudaStream_t stream)
 {
     using F = Fd2Shape<N>;
     auto kern = fused_dmma2<N>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     const int64_t units = a.spad / 8;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + F::NW - 1) / F::NW, sm_count));
-    kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
+    kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
                                                    a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
                                                    a.pi, a.thr, a.shift_at_root, stagger, a.site_cat);
     return grid;
 }
 
-inline int launch_fused_dmma2(int n, const FusedDmmaArgs& a, int stagger, int sm_count, size_t smem, cudaStream_t stream)
+inline int launch_fused_dmma2(int n, const FusedDmmaArgs& a, int nslot, int stagger, int sm_count, size_t smem, cudaStream_t stream)
 {
-    return n == 20 ? launch_fused_dmma2_n<20>(a, stagger, sm_count, smem, stream)
-                   : launch_fused_dmma2_n<61>(a, stagger, sm_count, smem, stream);
+    return n == 20 ? launch_fused_dmma2_n<20>(a, nslot, stagger, sm_count, smem, stream)
+                   : launch_fused_dmma2_n<61>(a, nslot, stagger, sm_count, smem, stream);
 }
 
 inline int fused_dmma2_grid(int n, int sm_count, int64_t spad)

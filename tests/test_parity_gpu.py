@@ -285,13 +285,32 @@ def test_fused_dmma_balanced_tree_spills_the_stack():
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 200)
     case = cases.Case("balanced", flat, bl, Q, pi, tips)
     expect = oracle_per_site(case, P)
-    for version, stagger in ((2, 0), (2, 2000), (1, 0)):
+    for version, stagger, spill in ((2, 0, 0), (2, 2000, 0), (2, 0, 1), (1, 0, 0)):
         with run_ctx(case, "direct", P=P) as ctx:
             ctx.set_option("fused_dmma_version", version)
             ctx.set_option("fused_dmma_stagger", stagger)
+            ctx.set_option("fused_dmma_spill", spill)
             assert ctx.path_name == "fused_dmma"
             total, per_site = ctx.loglik(per_site=True)
         check(per_site, total, expect)
+
+
+@pytest.mark.parametrize("model,ntaxa,nsites,ncat", [("wag", 150, 5000, 2), ("mg94", 32, 20000, 1)])
+def test_fused_dmma_many_passes_are_reproducible(model, ntaxa, nsites, ncat):
+    """Several rounds and categories per CTA: the ring hand-over between decoupled warps (a slot must not be
+    refilled before every warp's fragment loads have returned) is exercised under load; repeated
+    evaluations must agree bit for bit with each other and with the CTA-synchronous kernel."""
+    case = cases.make_case("fd" + model, model, ntaxa, nsites, ncat=ncat, seed=7)
+    P = case.host_P()
+    with run_ctx(case, "direct", P=P) as ctx:
+        ctx.set_option("fused_dmma_version", 1)
+        ref = ctx.loglik(per_site=True)[1]
+    check(ref, math.fsum(ref), oracle_per_site(case, P))
+    for spill in (0, 1):
+        with run_ctx(case, "direct", P=P) as ctx:
+            ctx.set_option("fused_dmma_spill", spill)
+            for _ in range(6):
+                assert np.array_equal(ctx.loglik(per_site=True)[1], ref)
 
 
 def test_fused_dmma_kary_tree():
