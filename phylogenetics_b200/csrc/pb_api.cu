@@ -127,6 +127,7 @@ struct pb_ctx {
     int fused_dmma = 1;                 // option "fused_dmma": site-resident tensor-core kernel for 20 / 61 states
     int fused_dmma_version = 2;         // option "fused_dmma_version": 2 = decoupled warps + bulk-copy ring, 1 = CTA-synchronous
     int fused_dmma_stagger = 0;         // option "fused_dmma_stagger": start delay (ns) of every other warp quad
+    int fused_dmma_slots = 0;           // option "fused_dmma_slots": cap on the ring slots (0 = as many as fit)
     int fused_dmma_spill = 0;           // option "fused_dmma_spill": test hook, all stack levels in the L2 scratch
     DevBuf<FusedOp2> d_fprog_d;
     DevBuf<int> d_mlist;
@@ -771,6 +772,10 @@ int launch_fused_dmma_path(pb_ctx* c)
         if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
             smem -= (size_t)ssm * pbk::fused_dmma2_tilesz(n) * sizeof(double);
             ssm = 0;
+        }
+        if (c->fused_dmma_slots > 0 && c->fused_dmma_slots < nslot) {     // tuning hook: a shorter ring
+            smem -= (size_t)(nslot - c->fused_dmma_slots) * pbk::fused_dmma2_panelsz(n) * sizeof(double);
+            nslot = c->fused_dmma_slots;
         }
         PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma2_matsz(n), 1)));
         PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma_leafsz(n), 1)));
@@ -1618,6 +1623,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_dmma_version") {
         if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1 or 2");
         c->fused_dmma_version = iv;
+    } else if (k == "fused_dmma_slots") {
+        if (iv != 0 && (iv < 2 || iv > 14)) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_slots must be 0 or 2..14");
+        c->fused_dmma_slots = iv;
     } else if (k == "fused_dmma_spill") {
         c->fused_dmma_spill = iv != 0;
     } else if (k == "fused_dmma_stagger") {

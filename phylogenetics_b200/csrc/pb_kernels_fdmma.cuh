@@ -403,7 +403,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 template <int N>
 struct Fd2Shape {
     using S = DmmaShape<N>;
-    static constexpr int NW = 15;                               // compute warps per CTA (+1 producer warp = 512 threads, 128 registers each)
+    static constexpr int NW = 15;                               // compute warps per CTA (+1 producer warp = 512 threads, 128 registers each; 23 warps x 80 registers measured slower)
     static constexpr int KPP = (N <= 32) ? S::KS : 1;           // k-steps per ring panel
     static constexpr int NPAN = S::KS / KPP;                    // panels per matrix
     static constexpr int PSZ = S::MP * 8 * KPP;                 // doubles per panel
@@ -789,6 +789,7 @@ inline bool fused_dmma2_plan(int n, size_t smem_optin, int stack_depth, int ntax
     return false;
 }
 
+inline size_t fused_dmma2_panelsz(int n) { return n == 20 ? Fd2Shape<20>::PSZ : Fd2Shape<61>::PSZ; }
 inline size_t fused_dmma2_matsz(int n) { return n == 20 ? Fd2Shape<20>::MATSZ : Fd2Shape<61>::MATSZ; }
 inline size_t fused_dmma2_tilesz(int n) { return n == 20 ? Fd2Shape<20>::XSZ * Fd2Shape<20>::NW : Fd2Shape<61>::XSZ * Fd2Shape<61>::NW; }
 
