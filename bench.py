@@ -64,6 +64,9 @@ def algorithmic_flops_per_site(n, ncat, ntaxa):
     return ncat * (2 * n * n * (ntaxa - 2) + n * (ntaxa - 1))
 
 
+FP64_DMMA_PEAK_TFLOPS = 36.8      # profiles/r01_fp64_peak_dmma_shapes.jsonl
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -265,14 +268,18 @@ def run_ours(args, rank, world, local_rank):
     prune_ms = []
     barrier()
     t_wall0 = time.time()
+    # The K steps are queued without host synchronisation (a host sync per step would put launch latency
+    # and, for N > 1, the Python-side collective overhead inside every event pair); each step keeps its own
+    # event pair, the L2 flush sits between the pairs, and the per-phase events of every step are read back
+    # from the library's timing ring afterwards.
     for a, b in ev:
         flush.zero_()                    # L2 flush, outside the event pair
         a.record(stream)
         step()
         b.record(stream)
-        b.synchronize()
-        prune_ms.append(ctx.get_timing())
     barrier()
+    ring = 64
+    prune_ms = [ctx.get_timing(back) for back in range(min(args.steps, ring) - 1, -1, -1)]
     t_wall1 = time.time()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     launches = ctx.kernel_launches - launches0
@@ -337,6 +344,19 @@ def run_ours(args, rank, world, local_rank):
                          "so against the level-scheduled algorithmic bytes the fraction can exceed 1; its own "
                          "bound is the FP64 pipe" if ctx.path_name in ("fused4", "fused_dmma") else
                          "level-scheduled: every inner CLV written once and read once")}
+        if ctx.path_name == "fused_dmma":
+            # dense alphabets on the FP64 tensor cores: the roofline is the DMMA pipe.  Peak = this pool's
+            # measured mma.sync f64 throughput (tools/fp64_peak2.cu, profiles/r01_fp64_peak_dmma_shapes.jsonl);
+            # MEASURED_PEAKS.json carries no FP64 figure.
+            tf = flops_eval / (prune_avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": tf / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                    "peak_kind": "measured FP64 DMMA (own micro-benchmark; not in MEASURED_PEAKS.json)",
+                    "kernel": "fused_dmma2", "launches_per_step": 1, "kernel_ms_per_step": prune_avg_ms,
+                    "algorithmic_flops_per_launch": flops_eval,
+                    "hbm_gbs_vs_level_scheduled_bytes": achieved,
+                    "note": "algorithmic flops (SURVEY 8d: tip children are look-ups, padding not counted) / pruning-phase time; "
+                            "ncu DMMA-pipe activity in profiles/r01i_ncu_full_fused_dmma2_c3_c4.txt"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,

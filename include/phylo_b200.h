@@ -186,6 +186,10 @@ int pb_set_option(pb_ctx *ctx, const char *name, double value);
  * reduction of the LAST evaluation (pb_get_timing waits for it). */
 int pb_set_timing(pb_ctx *ctx, int on);
 int pb_get_timing(pb_ctx *ctx, double *ms /* [3] */);
+/* The same for the evaluation enqueued `back` evaluations before the last one (0 = last); the
+ * events of the 64 most recent timed evaluations are kept, so a caller can queue many
+ * evaluations without synchronising and read their phase times afterwards. */
+int pb_get_timing_at(pb_ctx *ctx, int back, double *ms /* [3] */);
 
 /* How many kernels of this library the context has launched so far. */
 int64_t pb_kernel_launches(const pb_ctx *ctx);

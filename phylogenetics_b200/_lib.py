@@ -31,7 +31,7 @@ EXPORTS = [
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_get_pmatrices",
-    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
+    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
 ]
 
@@ -88,6 +88,7 @@ def _load():
         "pb_set_option": (ci, [vp, ctypes.c_char_p, dbl]),
         "pb_set_timing": (ci, [vp, ci]),
         "pb_get_timing": (ci, [vp, vp]),
+        "pb_get_timing_at": (ci, [vp, ci, vp]),
         "pb_kernel_launches": (i64, [vp]),
         "pb_path_name": (ctypes.c_char_p, [vp]),
         "pb_transition_matrices_eigen": (ci, [ci, ci, ci, vp, vp, vp, vp, vp]),

@@ -170,7 +170,10 @@ struct pb_ctx {
 
     // optional per-phase device timing (pb_set_timing)
     bool timing = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int TIMING_RING = 64;        // evaluations whose phase events are kept (pb_get_timing_at)
+    cudaEvent_t ev_ring[TIMING_RING][4] = {};
+    cudaEvent_t* ev = ev_ring[0];                 // event set of the evaluation being enqueued
+    int64_t timed_evals = 0;
 };
 
 namespace {
@@ -1052,7 +1055,8 @@ void pb_destroy(pb_ctx* c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     if (c->h_total) cudaFreeHost(c->h_total);
-    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (auto& set : c->ev_ring)
+        for (int i = 0; i < 4; i++) if (set[i]) cudaEventDestroy(set[i]);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1415,7 +1419,7 @@ int pb_loglik_enqueue(pb_ctx* c)
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
     if (!c->have_tips) return fail(c, PB_ERR_STATE, "tip states not set");
     if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
-    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     int rc = build_pmatrices(c);
     if (rc != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -1464,7 +1468,7 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
         PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->chunk_events.push_back(e);
     }
-    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     if ((rc = build_pmatrices(c)) != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     const int64_t nblocks = (c->nsites + 255) / 256;
@@ -1658,24 +1662,30 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
 int pb_set_timing(pb_ctx* c, int on)
 {
     PB_ENTER(c);
-    if (on && !c->ev[0])
-        for (int i = 0; i < 4; i++) PB_CUDA(c, cudaEventCreate(&c->ev[i]));
+    if (on && !c->ev_ring[0][0])
+        for (auto& set : c->ev_ring)
+            for (int i = 0; i < 4; i++) PB_CUDA(c, cudaEventCreate(&set[i]));
     c->timing = on != 0;
     return PB_OK;
 }
 
-int pb_get_timing(pb_ctx* c, double* ms)
+int pb_get_timing_at(pb_ctx* c, int back, double* ms)
 {
     PB_ENTER(c);
-    if (!c->timing || !c->evaluated || !ms) return fail(c, PB_ERR_STATE, "timing is off or nothing was evaluated");
-    PB_CUDA(c, cudaEventSynchronize(c->ev[3]));
+    if (!c->timing || c->timed_evals == 0 || !ms) return fail(c, PB_ERR_STATE, "timing is off or nothing was evaluated");
+    if (back < 0 || back >= pb_ctx::TIMING_RING || back >= c->timed_evals)
+        return fail(c, PB_ERR_INVALID_ARG, "pb_get_timing_at: that evaluation is not (or no longer) recorded");
+    cudaEvent_t* set = c->ev_ring[(c->timed_evals - 1 - back) % pb_ctx::TIMING_RING];
+    PB_CUDA(c, cudaEventSynchronize(set[3]));
     for (int i = 0; i < 3; i++) {
         float t = 0.f;
-        PB_CUDA(c, cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]));
+        PB_CUDA(c, cudaEventElapsedTime(&t, set[i], set[i + 1]));
         ms[i] = t;
     }
     return PB_OK;
 }
+
+int pb_get_timing(pb_ctx* c, double* ms) { return pb_get_timing_at(c, 0, ms); }
 
 int64_t pb_kernel_launches(const pb_ctx* c) { return c ? c->launches : 0; }
 

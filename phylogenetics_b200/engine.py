@@ -228,10 +228,11 @@ class LikelihoodContext:
     def set_timing(self, on=True):
         self._ck(lib.pb_set_timing(self._ctx, int(bool(on))))
 
-    def get_timing(self):
-        """(pmat_ms, pruning_ms, root_ms) of the last evaluation, from CUDA events on the stream."""
+    def get_timing(self, back=0):
+        """(pmat_ms, pruning_ms, root_ms) of the last evaluation (or the one `back` evaluations before
+        it, up to 63), from CUDA events on the stream."""
         ms = np.empty(3)
-        self._ck(lib.pb_get_timing(self._ctx, ms.ctypes.data))
+        self._ck(lib.pb_get_timing_at(self._ctx, int(back), ms.ctypes.data))
         return tuple(float(x) for x in ms)
 
     def total_as_cuda_array(self):

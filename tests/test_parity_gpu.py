@@ -476,3 +476,22 @@ def test_two_contexts_share_the_device_constant_bank():
             tb, pb_ = cb.fetch(per_site=True)
             check(pa, ta, ea)
             check(pb_, tb, eb)
+
+
+def test_timing_ring_keeps_queued_evaluations():
+    """pb_get_timing_at: phase times of evaluations queued without synchronising, oldest to newest."""
+    case = cases.make_case("timing", "gtr", 30, 20000, ncat=2, seed=4)
+    with run_ctx(case, "eigen") as ctx:
+        ctx.set_timing(True)
+        with pytest.raises(_lib.PhyloB200Error):
+            ctx.get_timing()
+        for _ in range(5):
+            ctx.enqueue()
+        total, _ = ctx.fetch(per_site=True)
+        times = [ctx.get_timing(back) for back in range(5)]
+        assert all(len(t) == 3 and all(x >= 0.0 for x in t) and t[1] > 0.0 for t in times)
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.get_timing(5)
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.get_timing(64)
+        assert ctx.get_timing() == times[0]
