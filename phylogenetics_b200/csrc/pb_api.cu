@@ -125,7 +125,8 @@ struct pb_ctx {
     std::vector<int> mlist;
     int dstack = 0;
     int fused_dmma = 1;                 // option "fused_dmma": site-resident tensor-core kernel for 20 / 61 states
-    int fused_dmma_version = 2;         // option "fused_dmma_version": 2 = decoupled warps + bulk-copy ring, 1 = CTA-synchronous
+    int fused_dmma_version = 3;         // option "fused_dmma_version": 3 = decoupled warps + bulk-copy ring on m8n8k4 tiles,
+                                        // 2 = the same on m16n8k8 tiles, 1 = CTA-synchronous
     int fused_dmma_stagger = 0;         // option "fused_dmma_stagger": start delay (ns) of every other warp quad
     int fused_dmma_slots = 0;           // option "fused_dmma_slots": cap on the ring slots (0 = as many as fit)
     int fused_dmma_spill = 0;           // option "fused_dmma_spill": test hook, all stack levels in the L2 scratch
@@ -240,7 +241,9 @@ int path_of(const pb_ctx* c)
         if (!level && c->have_tree && c->fused_dmma) {
             int ssm = 0, nslot = 0;
             size_t smem = 0;
-            if ((c->fused_dmma_version == 2 &&
+            if ((c->fused_dmma_version == 3 &&
+                 pbk::fused_dmma3_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) ||
+                (c->fused_dmma_version == 2 &&
                  pbk::fused_dmma2_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) ||
                 pbk::fused_dmma_plan(c->n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &ssm, &smem))
                 return PATH_FUSED_DMMA;
@@ -770,6 +773,32 @@ int launch_fused_dmma_path(pb_ctx* c)
     const int ninner = (int)c->inner_nodes.size(), nleaf = (int)c->leaf_nodes.size();
     int ssm = 0, nslot = 0;
     size_t smem = 0;
+    if (c->fused_dmma_version == 3 &&
+        pbk::fused_dmma3_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) {
+        if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
+            smem -= (size_t)ssm * pbk::fused_dmma3_tilesz(n) * sizeof(double);
+            ssm = 0;
+        }
+        if (c->fused_dmma_slots > 0 && c->fused_dmma_slots < nslot) {     // tuning hook: a shorter ring
+            smem -= (size_t)(nslot - c->fused_dmma_slots) * pbk::fused_dmma3_panelsz(n) * sizeof(double);
+            nslot = c->fused_dmma_slots;
+        }
+        PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma3_matsz(n), 1)));
+        PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma3_leafsz(n), 1)));
+        pbk::launch_fdmma3_prepare(n, c->d_P.p, c->d_inner_nodes.p, ninner, c->d_leaf_nodes.p, nleaf, c->nnodes, c->ncat,
+                                   c->d_Ppad.p, c->d_PTleaf.p, c->stream);
+        c->launches++;
+        const int grid = pbk::fused_dmma2_grid(n, c->sm_count, c->spad);
+        const int gdepth = c->dstack + 1 - ssm;
+        PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * pbk::fused_dmma3_tilesz(n), 1)));
+        pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,
+                             c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
+                             c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
+        if (pbk::launch_fused_dmma3(n, a, nslot, c->sm_count, smem, c->stream) < 1)
+            return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
+        c->launches++;
+        return PB_OK;
+    }
     if (c->fused_dmma_version == 2 &&
         pbk::fused_dmma2_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) {
         if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
@@ -1625,7 +1654,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_dmma") {
         c->fused_dmma = value != 0.0;
     } else if (k == "fused_dmma_version") {
-        if (iv != 1 && iv != 2) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1 or 2");
+        if (iv < 1 || iv > 3) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1, 2 or 3");
         c->fused_dmma_version = iv;
     } else if (k == "fused_dmma_slots") {
         if (iv != 0 && (iv < 2 || iv > 14)) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_slots must be 0 or 2..14");

@@ -762,6 +762,325 @@ inline void launch_fdmma_prepare(int n, const double* P, const int* inner_nodes,
     else fdmma_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Ppad, PTleaf);
 }
 
+// --------------------------------------------------------------------------
+// fused_dmma3: fused_dmma2 re-tiled on the native DMMA shape, mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; the
+// m16n8k8 form is four of these).  Parent states are padded to a multiple of 8 and child states to a
+// multiple of 4 instead of 16 and 8: a 20-state mat-vec takes 3 x 5 = 15 DMMAs instead of 24 (the FP64
+// tensor and vector instructions share one pipe on B200 — profiles/r01i_fp64_dfma_dmma_share_pipe.json —
+// so padding is paid in full), fragments are 2 doubles per 8-row tile, and every per-row loop (leaf
+// columns, rescaling, layout conversion) shrinks with the padding.  61 states: 8 x 16 = 128, as before.
+// Ring panels hold, per 8-row tile and PAIR of k-steps, one 16-byte (k, k+4) entry per lane:
+// panel[kk][mt][lane] = { P[mt*8+g][(2kk)*4+tig], P[mt*8+g][(2kk+1)*4+tig] }.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int N>
+struct Fd3Shape {
+    static constexpr int NW = 15;                               // compute warps per CTA (+1 producer warp)
+    static constexpr int M8 = (N + 7) / 8;                      // 8-row tiles of parent states (20: 3, 61: 8)
+    static constexpr int K4 = (N + 3) / 4;                      // k-steps of 4 child states (20: 5, 61: 16)
+    static constexpr int KP2 = (K4 + 1) / 2;                    // pairs of k-steps (20: 3, 61: 8)
+    static constexpr int KR = K4 * 4;                           // rows of an 8-site tile (20, 64)
+    static constexpr int MP8 = M8 * 8;                          // padded parent states (24, 64)
+    static constexpr int KPP = (N <= 32) ? KP2 : 1;             // k-step pairs per ring panel
+    static constexpr int NPAN = KP2 / KPP;                      // panels per matrix
+    static constexpr int PSZ = KPP * M8 * 64;                   // doubles per panel (20: 576, 61: 512)
+    static constexpr int MATSZ = KP2 * M8 * 64;
+    static constexpr int XSZ = KR * 8;                          // doubles per 8-site tile
+    static constexpr int NSLOT_MAX = (N <= 32) ? 8 : 14;
+    static constexpr int NSLOT_MIN = (N <= 32) ? 3 : 6;
+    static constexpr size_t BAR_BYTES = 256;
+    static constexpr size_t fixed_bytes(int nslot, int ntaxa, int nops, int nmat)
+    {
+        return BAR_BYTES + ((size_t)nslot * PSZ + MP8) * sizeof(double) + (((size_t)NW * ntaxa * 8 + 15) & ~(size_t)15) +
+               (size_t)nops * sizeof(FusedOp2) + (size_t)nmat * sizeof(int) + 16;
+    }
+    static constexpr size_t level_bytes = (size_t)NW * XSZ * sizeof(double);
+};
+
+template <int N>
+__global__ void fdmma3_prepare(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
+                               const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
+                               double* __restrict__ Apanel, double* __restrict__ PTleaf)
+{
+    using F = Fd3Shape<N>;
+    const int c = blockIdx.y, k = blockIdx.x;
+    if (k < ninner) {
+        const double* src = P + ((size_t)c * nnodes + inner_nodes[k]) * N * N;
+        double* dst = Apanel + ((size_t)c * ninner + k) * F::MATSZ;
+        for (int idx = threadIdx.x; idx < F::MATSZ; idx += blockDim.x) {
+            const int h = idx & 1, lane = (idx >> 1) & 31, mt = (idx >> 6) % F::M8, pr = idx / (64 * F::M8);
+            const int row = mt * 8 + (lane >> 2), col = (2 * pr + h) * 4 + (lane & 3);
+            dst[idx] = (row < N && col < N) ? src[row * N + col] : 0.0;
+        }
+    } else {
+        const int l = k - ninner;
+        const double* src = P + ((size_t)c * nnodes + leaf_nodes[l]) * N * N;
+        double* dst = PTleaf + ((size_t)c * nleaf + l) * N * F::MP8;
+        for (int idx = threadIdx.x; idx < N * F::MP8; idx += blockDim.x) {
+            const int s = idx / F::MP8, i = idx - s * F::MP8;
+            dst[idx] = (i < N) ? src[i * N + s] : 0.0;
+        }
+    }
+}
+
+// SV.shift on 8-row C tiles: v[mt][j] = state mt*8+g of the lane's site j (same scheme as shift_frag_ballot).
+template <int N>
+__device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Scale<false> (&sc)[2], int lane, double thr)
+{
+    constexpr int M8 = Fd3Shape<N>::M8;
+    const int g = lane >> 2, tig = lane & 3;
+    bool ok[2] = {true, true};
+    double mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int mt = 0; mt < M8; mt++)
+            if (mt * 8 + 7 < N || mt * 8 + g < N) { ok[j] = ok[j] && (v[mt][j] > thr); mx[j] = fmax(mx[j], v[mt][j]); }
+    const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
+    if ((b0 & b1) == 0xffffffffu) return;
+    const bool odd = g & 1;
+    double keep = odd ? mx[1] : mx[0];
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, odd ? mx[0] : mx[1], 4));
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, keep, 8));
+    keep = fmax(keep, __shfl_xor_sync(0xffffffffu, keep, 16));
+    const double other = __shfl_xor_sync(0xffffffffu, keep, 4);
+    const double m[2] = {odd ? other : keep, odd ? keep : other};
+    const unsigned grp = 0x11111111u << tig;
+    const unsigned bits[2] = {b0, b1};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        if ((bits[j] & grp) != grp) {
+            const double inv = 1.0 / m[j];
+#pragma unroll
+            for (int mt = 0; mt < M8; mt++) v[mt][j] = inv * v[mt][j];
+            sc[j].add(m[j]);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__((Fd3Shape<N>::NW + 1) * 32, 1)
+fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int nslot, int stack_smem,
+            double* __restrict__ gstack, int gdepth,
+            const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
+            const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
+            const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat)
+{
+    using F = Fd3Shape<N>;
+    constexpr int M8 = F::M8, K4 = F::K4, MP8 = F::MP8, NW = F::NW, KPP = F::KPP, NPAN = F::NPAN;
+    extern __shared__ __align__(128) unsigned char shbytes[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(shbytes);              // [nslot] (16 reserved)
+    uint64_t* empty = full + 16;
+    double* ring = reinterpret_cast<double*>(shbytes + F::BAR_BYTES);   // [nslot][PSZ]
+    double* shPi = ring + nslot * F::PSZ;                                 // [MP8]
+    double* shS = shPi + MP8;                                             // [stack_smem][NW][XSZ]
+    uint8_t* shT = reinterpret_cast<uint8_t*>(shS + (size_t)stack_smem * NW * F::XSZ);   // [NW][ntaxa][8]
+    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (((size_t)NW * ntaxa * 8 + 15) & ~(size_t)15));
+    int* shMl = reinterpret_cast<int*>(shOps + nops);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    if (tid == 0) {
+        for (int i = 0; i < nslot; i++) { mbar_init(full + i, 1); mbar_init(empty + i, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < MP8) shPi[tid] = (tid < N) ? pi[tid] : 0.0;
+    {
+        const int4* src = reinterpret_cast<const int4*>(prog);
+        int4* dst = reinterpret_cast<int4*>(shOps);
+        for (int idx = tid; idx < nops; idx += blockDim.x) dst[idx] = src[idx];
+        for (int idx = tid; idx < nmat; idx += blockDim.x) shMl[idx] = mlist[idx];
+    }
+    __syncthreads();                                         // the only CTA-wide barrier
+
+    const int64_t units = spad / 8;
+    const int64_t lo = units * blockIdx.x / gridDim.x, hi = units * (blockIdx.x + 1) / gridDim.x;
+    const int rounds = (int)((hi - lo + NW - 1) / NW);
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() { if (++slot == nslot) { slot = 0; phase ^= 1; } };
+
+    if (warp == NW) {                                        // ---- producer: one lane feeds the ring
+        if (lane == 0) {
+            for (int c = 0; c < ncat; c++)
+                for (int r = 0; r < rounds; r++)
+                    for (int m = 0; m < nmat; m++) {
+                        const double* src = Apanel + ((size_t)c * ninner + shMl[m]) * F::MATSZ;
+                        for (int p = 0; p < NPAN; p++) {
+                            mbar_wait(empty + slot, phase ^ 1);
+                            mbar_expect_tx(full + slot, F::PSZ * sizeof(double));
+                            bulk_g2s(ring + slot * F::PSZ, src + p * F::PSZ, F::PSZ * sizeof(double), full + slot);
+                            advance();
+                        }
+                    }
+        }
+        return;
+    }
+
+    // ---- compute warps
+    uint8_t* myT = shT + (size_t)warp * ntaxa * 8;
+    gstack += ((size_t)blockIdx.x * gdepth * NW + warp) * F::XSZ;
+    auto level_tile = [&](int level) -> double* {
+        return level < stack_smem ? shS + ((size_t)level * NW + warp) * F::XSZ
+                                  : gstack + (size_t)(level - stack_smem) * NW * F::XSZ;
+    };
+    const int boff = (((g >> 1) ^ tig) << 1) + (g & 1);     // B-fragment column of this lane in a swizzled row
+
+    // registers (C tiles) -> 8-site tile [state][site], 16-byte chunk q of row r at q ^ (r & 3)
+    auto to_tile = [&](double* T, const double (&x)[M8][2]) {
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < M8; mt++) {
+            const int r = mt * 8 + g;                        // rows >= N hold zeros
+            if (mt * 8 + 7 < F::KR || r < F::KR)
+                *reinterpret_cast<double2*>(T + r * 8 + ((tig ^ (r & 3)) << 1)) = make_double2(x[mt][0], x[mt][1]);
+        }
+        __syncwarp();
+    };
+    // y = P . x, x read as B fragments from a tile, P from the next NPAN panels of the ring
+    auto apply = [&](const double* T, double (&y)[M8][2]) {
+#pragma unroll
+        for (int mt = 0; mt < M8; mt++) y[mt][0] = y[mt][1] = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < NPAN; p++) {
+            double b[KPP][2];
+#pragma unroll
+            for (int kk = 0; kk < KPP; kk++) {
+                const int ks = 2 * (p * KPP + kk);
+                b[kk][0] = T[(ks * 4 + tig) * 8 + boff];
+                b[kk][1] = (ks + 1 < K4) ? T[((ks + 1) * 4 + tig) * 8 + boff] : 0.0;
+            }
+            mbar_wait(full + slot, phase);
+            const double* A = ring + slot * F::PSZ + lane * 2;
+            uint32_t witness = 0xffffffffu;
+#pragma unroll
+            for (int kk = 0; kk < KPP; kk++) {
+#pragma unroll
+                for (int mt = 0; mt < M8; mt++) {
+                    const double2 a = *reinterpret_cast<const double2*>(A + (kk * M8 + mt) * 64);
+                    witness &= (uint32_t)__double2hiint(a.x);
+                    dmma_8x8x4(y[mt], a.x, b[kk][0]);
+                    if (2 * (p * KPP + kk) + 1 < K4) dmma_8x8x4(y[mt], a.y, b[kk][1]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after(empty + slot, witness);
+            advance();
+        }
+    };
+    auto leaf_ptrs = [&](const double* PTc, int leaf, int tiprow, const double*& ca, const double*& cb) {
+        const uint8_t* tb = myT + tiprow * 8 + tig * 2;
+        ca = PTc + ((size_t)leaf * N + min((int)tb[0], N - 1)) * MP8 + g;
+        cb = PTc + ((size_t)leaf * N + min((int)tb[1], N - 1)) * MP8 + g;
+    };
+
+    for (int c = 0; c < ncat; c++) {
+        const double* PTc = PTleaf + (size_t)c * nleaf * N * MP8;
+        for (int r = 0; r < rounds; r++) {
+            const int64_t unit = lo + (int64_t)r * NW + warp;
+            if (unit >= hi) {                                // no sites left for this warp: keep the ring moving
+                for (int p = 0; p < nmat * NPAN; p++) {
+                    mbar_wait(full + slot, phase);
+                    if (lane == 0) mbar_arrive(empty + slot);
+                    advance();
+                }
+                continue;
+            }
+            const int64_t s0 = unit * 8;
+            __syncwarp();
+            for (int row = lane; row < ntaxa; row += 32)
+                *reinterpret_cast<uint2*>(myT + row * 8) = *reinterpret_cast<const uint2*>(tips + (int64_t)row * tips_ld + s0);
+            __syncwarp();
+
+            double acc[M8][2];
+            Scale<false> sc[2];
+            sc[0].init(); sc[1].init();
+            int sp = 0;
+#pragma unroll 1
+            for (int ip = 0; ip < nops; ip++) {
+                const int4 opw = reinterpret_cast<const int4*>(shOps)[ip];
+                const int code = opw.x & 0xff, rowA = opw.w & 0xffff, rowB = (opw.w >> 16) & 0xffff;
+                if (code == FOP_APPLY_MUL_TIP) {
+                    double y[M8][2];
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.z, rowB, ca, cb);
+                    double* X = level_tile(sp);              // scratch: the free level above the stack top
+                    to_tile(X, acc);
+                    apply(X, y);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = y[mt][0] * ca[mt * 8]; acc[mt][1] = y[mt][1] * cb[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (code == FOP_ACC_POP) {
+                    double y[M8][2];
+                    double* X = level_tile(sp);
+                    to_tile(X, acc);
+                    apply(X, y);
+                    apply(level_tile(--sp), acc);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] *= y[mt][0]; acc[mt][1] *= y[mt][1]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (code == FOP_TIP_TIP) {
+                    const double *ca, *cb, *da, *db;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+                    leaf_ptrs(PTc, opw.z, rowB, da, db);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = ca[mt * 8] * da[mt * 8]; acc[mt][1] = cb[mt * 8] * db[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (code == FOP_TIP) {
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = ca[mt * 8]; acc[mt][1] = cb[mt * 8]; }
+                } else if (code == FOP_APPLY) {
+                    double* X = level_tile(sp);
+                    to_tile(X, acc);
+                    apply(X, acc);
+                } else if (code == FOP_MUL_TIP) {
+                    const double *ca, *cb;
+                    leaf_ptrs(PTc, opw.y, rowA, ca, cb);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] *= ca[mt * 8]; acc[mt][1] *= cb[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (code == FOP_POP_MUL) {
+                    const double* T = level_tile(--sp);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) {
+                        const int r = mt * 8 + g;
+                        if (mt * 8 + 7 < F::KR || r < F::KR) {
+                            const double2 v = *reinterpret_cast<const double2*>(T + r * 8 + ((tig ^ (r & 3)) << 1));
+                            acc[mt][0] *= v.x; acc[mt][1] *= v.y;
+                        }
+                    }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (code == FOP_ROOT) {
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) {
+                        const double p0 = shPi[mt * 8 + g];
+                        acc[mt][0] *= p0; acc[mt][1] *= p0;
+                    }
+                    if (shift_at_root) shift_tiles8<N>(acc, sc, lane, thr);
+                    double sum[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { sum[0] += acc[mt][0]; sum[1] += acc[mt][1]; }   // padded rows are exact zeros
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+                        sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+                    }
+                    if (g == 0)
+                        *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                            make_double2(log(sum[0]) + sc[0].value(), log(sum[1]) + sc[1].value());
+                }
+                if (opw.x & FOP_PUSH_AFTER) to_tile(level_tile(sp++), acc);
+            }
+        }
+    }
+}
+
 // ---- fused_dmma2 host side
 // Shared-memory plan: stack_depth + 1 tiles per warp are needed (the level above the top is the layout-
 // conversion scratch).  The ring gives up slots (down to NSLOT_MIN) before a level leaves the chip;
@@ -825,6 +1144,62 @@ inline void launch_fdmma2_prepare(int n, const double* P, const int* inner_nodes
     dim3 grid(ninner + nleaf, ncat);
     if (n == 20) fdmma2_prepare<20><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
     else fdmma2_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
+}
+
+// ---- fused_dmma3 host side (same plan rules as fused_dmma2)
+template <int N>
+bool fused_dmma3_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* nslot, int* stack_smem, size_t* smem)
+{
+    using F = Fd3Shape<N>;
+    const int levels = stack_depth + 1;
+    if (F::fixed_bytes(F::NSLOT_MIN, ntaxa, nops, nmat) > smem_optin) return false;
+    int ns = F::NSLOT_MAX;
+    while (ns > F::NSLOT_MIN && F::fixed_bytes(ns, ntaxa, nops, nmat) + (size_t)levels * F::level_bytes > smem_optin) ns--;
+    const size_t fixed = F::fixed_bytes(ns, ntaxa, nops, nmat);
+    const int fit = (int)std::min<size_t>((smem_optin - fixed) / F::level_bytes, (size_t)levels);
+    *nslot = ns;
+    *stack_smem = fit;
+    *smem = fixed + (size_t)fit * F::level_bytes;
+    return true;
+}
+
+inline bool fused_dmma3_plan(int n, size_t smem_optin, int stack_depth, int ntaxa, int nops, int nmat, int* nslot, int* stack_smem, size_t* smem)
+{
+    if (n == 20) return fused_dmma3_plan_n<20>(smem_optin, stack_depth, ntaxa, nops, nmat, nslot, stack_smem, smem);
+    if (n == 61) return fused_dmma3_plan_n<61>(smem_optin, stack_depth, ntaxa, nops, nmat, nslot, stack_smem, smem);
+    return false;
+}
+
+inline size_t fused_dmma3_panelsz(int n) { return n == 20 ? Fd3Shape<20>::PSZ : Fd3Shape<61>::PSZ; }
+inline size_t fused_dmma3_matsz(int n) { return n == 20 ? Fd3Shape<20>::MATSZ : Fd3Shape<61>::MATSZ; }
+inline size_t fused_dmma3_leafsz(int n) { return n == 20 ? 20 * Fd3Shape<20>::MP8 : 61 * Fd3Shape<61>::MP8; }
+inline size_t fused_dmma3_tilesz(int n) { return n == 20 ? Fd3Shape<20>::XSZ * Fd3Shape<20>::NW : Fd3Shape<61>::XSZ * Fd3Shape<61>::NW; }
+
+template <int N>
+int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
+{
+    using F = Fd3Shape<N>;
+    auto kern = fused_dmma3<N>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    const int64_t units = a.spad / 8;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + F::NW - 1) / F::NW, sm_count));
+    kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
+                                                   a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
+                                                   a.pi, a.thr, a.shift_at_root, a.site_cat);
+    return grid;
+}
+
+inline int launch_fused_dmma3(int n, const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
+{
+    return n == 20 ? launch_fused_dmma3_n<20>(a, nslot, sm_count, smem, stream) : launch_fused_dmma3_n<61>(a, nslot, sm_count, smem, stream);
+}
+
+inline void launch_fdmma3_prepare(int n, const double* P, const int* inner_nodes, int ninner, const int* leaf_nodes, int nleaf,
+                                  int nnodes, int ncat, double* Apanel, double* PTleaf, cudaStream_t stream)
+{
+    dim3 grid(ninner + nleaf, ncat);
+    if (n == 20) fdmma3_prepare<20><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
+    else fdmma3_prepare<61><<<grid, 256, 0, stream>>>(P, inner_nodes, ninner, leaf_nodes, nleaf, nnodes, Apanel, PTleaf);
 }
 
 }  // namespace pbk

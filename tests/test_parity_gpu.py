@@ -242,7 +242,7 @@ def test_dense_kernel_modes(model, ntaxa, nsites, opts):
     ("wag", 64, 1500, 1, "bd"), ("wag", 40, 2100, 3, "random"), ("wag", 150, 333, 2, "bd"), ("wag", 3, 65, 1, "bd"),
     ("mg94", 32, 700, 1, "bd"), ("mg94", 24, 900, 2, "random"), ("mutsel", 70, 129, 1, "bd"), ("mg94", 2, 64, 1, "bd"),
 ])
-@pytest.mark.parametrize("version", [2, 1])
+@pytest.mark.parametrize("version", [3, 2, 1])
 def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
     """The site-resident tensor-core kernel (default path for 20 / 61 states): birth-death and random
     trees, several categories, ragged site counts, trees deep enough that the stack spills out of
@@ -285,7 +285,7 @@ def test_fused_dmma_balanced_tree_spills_the_stack():
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 200)
     case = cases.Case("balanced", flat, bl, Q, pi, tips)
     expect = oracle_per_site(case, P)
-    for version, stagger, spill in ((2, 0, 0), (2, 2000, 0), (2, 0, 1), (1, 0, 0)):
+    for version, stagger, spill in ((3, 0, 0), (3, 0, 1), (2, 0, 0), (2, 2000, 0), (2, 0, 1), (1, 0, 0)):
         with run_ctx(case, "direct", P=P) as ctx:
             ctx.set_option("fused_dmma_version", version)
             ctx.set_option("fused_dmma_stagger", stagger)
@@ -306,11 +306,20 @@ def test_fused_dmma_many_passes_are_reproducible(model, ntaxa, nsites, ncat):
         ctx.set_option("fused_dmma_version", 1)
         ref = ctx.loglik(per_site=True)[1]
     check(ref, math.fsum(ref), oracle_per_site(case, P))
-    for spill in (0, 1):
-        with run_ctx(case, "direct", P=P) as ctx:
-            ctx.set_option("fused_dmma_spill", spill)
-            for _ in range(6):
-                assert np.array_equal(ctx.loglik(per_site=True)[1], ref)
+    for version in (3, 2):
+        first = None
+        for spill in (0, 1):
+            with run_ctx(case, "direct", P=P) as ctx:
+                ctx.set_option("fused_dmma_version", version)
+                ctx.set_option("fused_dmma_spill", spill)
+                for _ in range(6):
+                    got = ctx.loglik(per_site=True)[1]
+                    if version == 2:
+                        assert np.array_equal(got, ref)       # same tile shape, same summation order as version 1
+                    else:
+                        first = got if first is None else first
+                        assert np.array_equal(got, first)
+                        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
 
 
 def test_fused_dmma_kary_tree():
@@ -335,7 +344,7 @@ def test_fused_dmma_kary_tree():
     P = synthetic.host_transition_matrices(Q, pi, bl)
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 333)
     case = cases.Case("kary20", flat, bl, Q, pi, tips)
-    for version in (2, 1):
+    for version in (3, 2, 1):
         with run_ctx(case, "direct", P=P) as ctx:
             ctx.set_option("fused_dmma_version", version)
             assert ctx.path_name == "fused_dmma"

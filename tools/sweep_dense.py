@@ -13,9 +13,7 @@ for name, model, ntaxa, nsites in [("c3", "wag", 64, 200_000), ("c4", "mg94", 32
     case = cases.make_case(name, model, ntaxa, nsites, seed=100)
     f = case.flat
     ref = None
-    variants = [{"fused_dmma_version": 2}, {"fused_dmma_version": 2, "fused_dmma_stagger": 1000},
-                {"fused_dmma_version": 2, "fused_dmma_stagger": 3000}, {"fused_dmma_version": 2, "fused_dmma_stagger": 10000},
-                {"fused_dmma_version": 1}, {"fused_dmma": 0}, {"fused_dmma": 0, "dmma_version": 1}, {"fused_dmma": 0, "dense_scalar": 1}]
+    variants = [{"fused_dmma_version": 3}, {"fused_dmma_version": 2}, {"fused_dmma_version": 1}, {"fused_dmma": 0}, {"fused_dmma": 0, "dmma_version": 1}, {"fused_dmma": 0, "dense_scalar": 1}]
     if len(sys.argv) > 1:
         variants = [json.loads(a) for a in sys.argv[1:]]
     for opts in variants:
