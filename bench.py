@@ -352,11 +352,11 @@ def run_ours(args, rank, world, local_rank):
             roof = {"bound": "tensor", "achieved": tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": tf / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
                     "peak_kind": "measured FP64 DMMA (own micro-benchmark; not in MEASURED_PEAKS.json)",
-                    "kernel": "fused_dmma2", "launches_per_step": 1, "kernel_ms_per_step": prune_avg_ms,
+                    "kernel": "fused_dmma3", "launches_per_step": 1, "kernel_ms_per_step": prune_avg_ms,
                     "algorithmic_flops_per_launch": flops_eval,
                     "hbm_gbs_vs_level_scheduled_bytes": achieved,
                     "note": "algorithmic flops (SURVEY 8d: tip children are look-ups, padding not counted) / pruning-phase time; "
-                            "ncu DMMA-pipe activity in profiles/r01i_ncu_full_fused_dmma2_c3_c4.txt"}
+                            "ncu DMMA-pipe activity in profiles/r01j_ncu_full_fused_dmma3_c3_c4.txt"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,

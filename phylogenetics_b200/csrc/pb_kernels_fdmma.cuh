@@ -780,7 +780,7 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
 
 template <int N>
 struct Fd3Shape {
-    static constexpr int NW = 15;                               // compute warps per CTA (+1 producer warp)
+    static constexpr int NW = (N <= 32) ? 23 : 15;              // compute warps per CTA (+1 producer warp): 768 threads x 80 registers at 20 states (measured: 15 warps 1.02 ms, 23 0.915, 31 0.908 at c3), 512 x 128 at 61
     static constexpr int M8 = (N + 7) / 8;                      // 8-row tiles of parent states (20: 3, 61: 8)
     static constexpr int K4 = (N + 3) / 4;                      // k-steps of 4 child states (20: 5, 61: 16)
     static constexpr int KP2 = (K4 + 1) / 2;                    // pairs of k-steps (20: 3, 61: 8)
