@@ -322,6 +322,19 @@ def test_fused_dmma_many_passes_are_reproducible(model, ntaxa, nsites, ncat):
                         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("model,ntaxa,nsites", [("wag", 700, 40), ("mg94", 300, 24), ("wag", 2500, 9)])
+def test_dense_alphabet_big_trees(model, ntaxa, nsites):
+    """Trees whose per-warp tip tiles, program or stack outgrow shared memory: the planner must step down
+    (fewer ring slots, spilled stack levels, the CTA-synchronous kernel, finally the level kernels) and stay exact."""
+    case = cases.make_case("big" + model, model, ntaxa, nsites, seed=9)
+    P = case.host_P()
+    expect = oracle_per_site(case, P)
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name in ("fused_dmma", "level_dmma")
+        total, per_site = ctx.loglik(per_site=True)
+    check(per_site, total, expect)
+
+
 def test_fused_dmma_kary_tree():
     """Multifurcating and unary nodes through the tensor-core program (TIP / MUL_TIP / APPLY / POP_MUL ops)."""
     from phylogenetics_b200 import tree as T, synthetic
