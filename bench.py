@@ -75,10 +75,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def build_case(cfg, nsites, seed):
+def build_case(cfg, nsites, seed, site_seed=None):
     import cases
     model, ntaxa, _, ncat, _ = CONFIGS[cfg]
-    return cases.make_case(cfg, model, ntaxa, nsites, ncat=ncat, seed=seed)
+    return cases.make_case(cfg, model, ntaxa, nsites, ncat=ncat, seed=seed, site_seed=site_seed)
 
 
 class ClockSampler:
@@ -208,7 +208,8 @@ def run_ours(args, rank, world, local_rank):
     cfg = args.config
     model, ntaxa, full_sites, ncat, desc = CONFIGS[cfg]
     nsites = args.sites or full_sites
-    case = build_case(cfg, nsites, seed=100 + rank)          # every rank simulates its own site shard
+    # one problem, sharded by site columns: every rank has the SAME tree and model and simulates its own columns
+    case = build_case(cfg, nsites, seed=100, site_seed=rank)
     f = case.flat
     n = case.n
     ninternal = f.ninternal
@@ -228,10 +229,12 @@ def run_ours(args, rank, world, local_rank):
 
     total_t = None
 
-    def step():
+    def step(mid=None):
         nonlocal total_t
         ctx.set_branch_lengths(case.bl)      # new branch lengths every evaluation: P(t) is rebuilt (kernel K1)
         ctx.enqueue()
+        if mid is not None:
+            mid.record(stream)               # local work of the step ends here; what follows is the collective
         if world > 1:
             if total_t is None:
                 total_t = torch.as_tensor(ctx.total_as_cuda_array(), device="cuda")
@@ -272,12 +275,21 @@ def run_ours(args, rank, world, local_rank):
     # and, for N > 1, the Python-side collective overhead inside every event pair); each step keeps its own
     # event pair, the L2 flush sits between the pairs, and the per-phase events of every step are read back
     # from the library's timing ring afterwards.
-    for a, b in ev:
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for (a, b), m in zip(ev, mids):
         flush.zero_()                    # L2 flush, outside the event pair
         a.record(stream)
-        step()
+        step(m)
         b.record(stream)
     barrier()
+    collective_ms = [m.elapsed_time(b) for (a, b), m in zip(ev, mids)]
+    local_ms = [a.elapsed_time(m) for (a, b), m in zip(ev, mids)]
+    per_rank = None
+    if world > 1:                          # where the step time goes on every rank: local work vs waiting in the collective
+        mine = torch.tensor([sum(local_ms) / len(local_ms), sum(collective_ms) / len(collective_ms)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"local_ms": [float(x[0]) for x in allr], "collective_ms": [float(x[1]) for x in allr]}
     ring = 64
     prune_ms = [ctx.get_timing(back) for back in range(min(args.steps, ring) - 1, -1, -1)]
     t_wall1 = time.time()
@@ -371,6 +383,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(case.tips.nbytes),
                     "d2h_bytes_per_step": 8, "steps": e2e_steps,
                     "note": "pb_set_branch_lengths + pb_loglik_host per step: tips copied from pinned host memory in column chunks overlapped with the pruning, total read back to the host"},
+            "collective_ms_per_step": (sum(collective_ms) / len(collective_ms)) if world > 1 else 0.0,
+            "per_rank_ms": per_rank,
             "gpu_launches": int(launches),
             "phase_ms": {"pmat": float(pm[:, 0].mean()), "pruning": prune_avg_ms, "root": float(pm[:, 2].mean())},
             "clocks": clocks,

@@ -38,7 +38,9 @@ class Case:
         return P
 
 
-def make_case(name, n_kind, ntaxa, nsites, ncat=1, alpha=0.5, seed=0, tree_kind="bd"):
+def make_case(name, n_kind, ntaxa, nsites, ncat=1, alpha=0.5, seed=0, tree_kind="bd", site_seed=None):
+    """`seed` fixes the tree and the model; `site_seed` (optional) draws the alignment columns from a separate
+    stream, so that several shards of ONE problem (same tree and model, different columns) can be generated."""
     rng = np.random.default_rng(synthetic.BASE_SEED + seed)
     if tree_kind == "bd":
         t = synthetic.birth_death_tree(rng, ntaxa)
@@ -70,5 +72,6 @@ def make_case(name, n_kind, ntaxa, nsites, ncat=1, alpha=0.5, seed=0, tree_kind=
         raise ValueError(n_kind)
     rates, weights = models.gamma_category_rates(alpha, ncat)
     P = synthetic.host_transition_matrices(Q, pi, bl, rates)
-    tips = synthetic.simulate_alignment(rng, flat, P, pi, nsites, weights)
+    site_rng = rng if site_seed is None else np.random.default_rng([synthetic.BASE_SEED + seed, int(site_seed)])
+    tips = synthetic.simulate_alignment(site_rng, flat, P, pi, nsites, weights)
     return Case(name, flat, bl, Q, pi, tips, rates, weights)
