@@ -173,6 +173,14 @@ int pb_result_device_ptrs(pb_ctx *ctx, const double **d_total, const double **d_
  * shifted_vector SV (v, carry) of lib/phylo_ctmc.ml:26 per site.  For a leaf the
  * indicator vector with carry 0. */
 int pb_get_clv(pb_ctx *ctx, int node, int cat, double *v, double *carry);
+/* Phylo_ctmc.conditional_simulation (lib/phylo_ctmc.mli:80-90, .ml:122-143; Missing_values
+ * :199-229; Ambiguous :331-360), batched over sites on the device: one joint draw of every
+ * node's state given the leaves, from the conditional likelihoods of the last evaluation (needs
+ * PB_FLAG_KEEP_CLV, one rate category).  states[node*ld + site]; an observed leaf keeps its state,
+ * a missing / ambiguous leaf (pb_set_tip_masks) is drawn from the prior (restricted to its set).
+ * The variates come from a counter-based generator keyed by (seed, site, node): the same seed
+ * gives the same draw; the stream is not GSL's. */
+int pb_conditional_simulation(pb_ctx *ctx, uint64_t seed, uint8_t *states /* host [nnodes][ld] */, int64_t ld);
 /* Copy out the matrices in use: P[(k*nnodes + v)*n*n ...] column-major. */
 int pb_get_pmatrices(pb_ctx *ctx, double *P);
 

@@ -379,3 +379,72 @@ def pruning_mixture(t, nstates, tp_for_category, leaf_state, root_frequencies, w
     if m == -math.inf:
         return m
     return m + math.log(sum(w * math.exp(l - m) for w, l in zip(weights, ls)))
+
+
+# ------------------------------------------------------------------ conditional simulation
+def conditional_simulation(rng, root, child_ptr, child_idx, P, clv, carry, root_frequencies, leaf_sets):
+    """Phylo_ctmc.conditional_simulation (lib/phylo_ctmc.ml:122-143) with the Missing_values (:199-229)
+    and Ambiguous (:331-360) leaf rules, on a flattened tree, for one site: top down, a node's state is
+    drawn with weights prior_i * cl_i (prior = root frequencies, then the parent's row of P); a node whose
+    carry is NaN (nothing observed below it) and a missing leaf are drawn from the prior, an ambiguous leaf
+    from the prior restricted to its set.  `rng` is a numpy Generator (the reference uses
+    Gsl.Randist.discrete: same distribution, another stream).  leaf_sets[v] = allowed states of leaf v
+    (None = missing).  Returns the state of every node."""
+    n = len(root_frequencies)
+    states = np.full(len(child_ptr) - 1, -1, dtype=np.int64)
+
+    def draw(w):
+        w = np.asarray(w, float)
+        return int(rng.choice(len(w), p=w / w.sum()))
+
+    stack = [(root, np.asarray(root_frequencies, float))]
+    while stack:
+        v, prior = stack.pop()
+        kids = child_idx[child_ptr[v]:child_ptr[v + 1]]
+        if len(kids) == 0:
+            allowed = leaf_sets[v]
+            if allowed is None:
+                states[v] = draw(prior)
+            elif len(allowed) == 1:
+                states[v] = allowed[0]
+            else:
+                w = np.zeros(n)
+                w[list(allowed)] = prior[list(allowed)]
+                states[v] = draw(w)
+            continue
+        states[v] = draw(prior if np.isnan(carry[v]) else prior * clv[v])
+        for ch in kids:
+            stack.append((ch, P[ch][states[v]]))
+    return states
+
+
+def conditional_simulation_exact(root, child_ptr, child_idx, P, root_frequencies, leaf_sets):
+    """The distribution conditional_simulation draws from, by enumeration (small trees): the joint
+    probability of every assignment of the unobserved nodes given the leaves,
+    proportional to pi[root] * prod over branches of P[child][state(parent), state(child)].
+    Returns (free_nodes, table) with table[assignment tuple] = probability."""
+    import itertools
+    n = len(root_frequencies)
+    nn = len(child_ptr) - 1
+    parent = np.full(nn, -1)
+    for v in range(nn):
+        for ch in child_idx[child_ptr[v]:child_ptr[v + 1]]:
+            parent[ch] = v
+    choices = []
+    for v in range(nn):
+        if child_ptr[v] == child_ptr[v + 1]:
+            s = leaf_sets[v]
+            choices.append(list(range(n)) if s is None else list(s))
+        else:
+            choices.append(list(range(n)))
+    free = [v for v in range(nn) if len(choices[v]) > 1]
+    table = {}
+    for assign in itertools.product(*choices):
+        p = root_frequencies[assign[root]]
+        for v in range(nn):
+            if v != root:
+                p *= P[v][assign[parent[v]], assign[v]]
+        key = tuple(assign[v] for v in free)
+        table[key] = table.get(key, 0.0) + p
+    z = sum(table.values())
+    return free, {k: p / z for k, p in table.items()}

@@ -30,7 +30,7 @@ EXPORTS = [
     "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
-    "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_get_pmatrices",
+    "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
 ]
@@ -84,6 +84,7 @@ def _load():
         "pb_loglik_fetch": (ci, [vp, vp, vp]),
         "pb_result_device_ptrs": (ci, [vp, vp, vp]),
         "pb_get_clv": (ci, [vp, ci, ci, vp, vp]),
+        "pb_conditional_simulation": (ci, [vp, ctypes.c_uint64, vp, ctypes.c_int64]),
         "pb_get_pmatrices": (ci, [vp, vp]),
         "pb_set_option": (ci, [vp, ctypes.c_char_p, dbl]),
         "pb_set_timing": (ci, [vp, ci]),

@@ -93,6 +93,8 @@ struct pb_ctx {
     bool all_dirty = true, partial_ok = false;
     int last_nodes_recomputed = 0;
     DevBuf<LevelNode> d_sel_nodes;
+    DevBuf<pbk::SimNode> d_sim_nodes;   // pb_conditional_simulation: nodes in pre-order
+    DevBuf<uint8_t> d_states;           //   and the sampled states [nnodes][spad]
     // sequential (depth-first, deeper subtree first) schedule for the persistent dense kernel
     std::vector<LevelNode> sq_nodes;
     std::vector<LevelChild> sq_children;
@@ -1601,6 +1603,38 @@ int pb_get_clv(pb_ctx* c, int node, int cat, double* v, double* carry)
         for (int i = 0; i < n; i++) v[s * n + i] = planes[(size_t)i * c->nsites + s];
         carry[s] = planes[(size_t)n * c->nsites + s];
     }
+    return PB_OK;
+}
+
+int pb_conditional_simulation(pb_ctx* c, uint64_t seed, uint8_t* states, int64_t ld)
+{
+    PB_ENTER(c);
+    if (!(c->flags & PB_FLAG_KEEP_CLV)) return fail(c, PB_ERR_STATE, "pb_conditional_simulation needs PB_FLAG_KEEP_CLV");
+    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (c->ncat != 1) return fail(c, PB_ERR_STATE, "pb_conditional_simulation: one rate category only (as the reference)");
+    if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "pb_conditional_simulation: bad output buffer");
+    // parents before children
+    std::vector<pbk::SimNode> pre;
+    pre.reserve(c->nnodes);
+    std::vector<int> stack{c->root};
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        const bool leaf = c->child_ptr[v] == c->child_ptr[v + 1];
+        pre.push_back({v, c->parent[v], leaf ? -1 : c->slot_of_node[v], leaf ? c->tip_row[v] : -1});
+        for (int k = c->child_ptr[v + 1] - 1; k >= c->child_ptr[v]; k--) stack.push_back(c->child_idx[k]);
+    }
+    PB_CUDA(c, c->d_sim_nodes.ensure(pre.size()));
+    PB_CUDA(c, c->d_states.ensure((size_t)c->nnodes * c->spad));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_sim_nodes.p, pre.data(), pre.size() * sizeof(pbk::SimNode), cudaMemcpyHostToDevice, c->stream));
+    pbk::conditional_simulation<<<(unsigned)((c->nsites + 255) / 256), 256, 0, c->stream>>>(
+        c->d_sim_nodes.p, (int)pre.size(), c->nnodes, c->n, c->d_P.p, c->d_pi.p, c->d_pool.p, c->slot_stride, c->spad,
+        c->d_tips.p, c->have_masks ? c->d_masks.p : nullptr, c->nsites, seed, c->d_states.p);
+    c->launches++;
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaMemcpy2DAsync(states, (size_t)ld, c->d_states.p, (size_t)c->spad, (size_t)c->nsites, c->nnodes,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));            // `pre` is read by the asynchronous upload
     return PB_OK;
 }
 

@@ -533,4 +533,82 @@ final_sum(const double* __restrict__ partials, int64_t count, double* __restrict
     if (threadIdx.x == 0) *total = bs;
 }
 
+// --------------------------------------------------------------------------
+// f3: ancestral states drawn from their joint conditional distribution given the leaves, from the
+// conditional likelihoods the level kernels left in HBM.  Restates Phylo_ctmc.conditional_simulation
+// (lib/phylo_ctmc.ml:122-143) and its Missing_values / Ambiguous variants (:199-229, :331-360): top
+// down, a node's state is drawn with weights prior_i * cl_i, where prior = root frequencies at the root
+// and the parent's row of the branch matrix below it; a node without information under it (NaN
+// carry) and a missing leaf are drawn from the prior alone, an ambiguous leaf from the prior
+// restricted to its state set, an observed leaf keeps its state.
+// One thread per site walks the nodes in pre-order (parents first); every plane read is coalesced
+// across sites.  The uniform variates come from a counter-based generator keyed by (seed, site, node)
+// — the distribution is the reference's, the random stream is not GSL's.
+// --------------------------------------------------------------------------
+struct SimNode {
+    int node;      // tree node
+    int parent;    // its parent (-1 for the root)
+    int slot;      // CLV slot of an inner node, -1 for a leaf
+    int tip_row;   // row of the tip matrix for a leaf
+};
+
+__device__ __forceinline__ double uniform01(uint64_t seed, uint64_t site, uint64_t node, uint64_t nnodes)
+{
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (site * nnodes + node + 1);      // splitmix64 of a unique counter
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;                                  // second round: seeds differing in few bits
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * 0x1p-53;
+}
+
+__global__ void __launch_bounds__(256)
+conditional_simulation(const SimNode* __restrict__ nodes, int count, int nnodes, int n,
+                       const double* __restrict__ P, const double* __restrict__ pi,
+                       const double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+                       const uint8_t* __restrict__ tips, const uint64_t* __restrict__ masks, int64_t nsites,
+                       uint64_t seed, uint8_t* __restrict__ states)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const uint64_t all = n >= 64 ? ~0ull : ((1ull << n) - 1);
+    for (int k = 0; k < count; k++) {
+        const SimNode nd = nodes[k];
+        const double* prior = nd.parent < 0 ? pi : P + ((size_t)nd.node * n + states[(int64_t)nd.parent * spad + s]) * n;
+        const double* cl = nullptr;            // weights = prior_i * cl_i (cl == nullptr: prior alone)
+        uint64_t allowed = all;
+        int st = -1;
+        if (nd.slot < 0) {
+            if (!masks) {
+                st = tips[(int64_t)nd.tip_row * spad + s];
+            } else {
+                const uint64_t m = masks[(int64_t)nd.tip_row * spad + s] & all;
+                if (m && !(m & (m - 1))) st = __ffsll((long long)m) - 1;      // a single observed state
+                else if (m) allowed = m;                                       // ambiguous: the prior restricted to the set
+            }
+        } else {
+            const double* base = pool + (size_t)nd.slot * slot_stride + s;
+            if (!isnan(base[(int64_t)n * spad])) cl = base;                    // NaN carry: nothing observed below this node
+        }
+        if (st < 0) {
+            double total = 0.0;
+            for (int i = 0; i < n; i++)
+                if ((allowed >> i) & 1) total += prior[i] * (cl ? cl[(int64_t)i * spad] : 1.0);
+            const double u = uniform01(seed, (uint64_t)s, (uint64_t)nd.node, (uint64_t)nnodes) * total;
+            double cum = 0.0;
+            for (int i = 0; i < n; i++) {
+                if (!((allowed >> i) & 1)) continue;
+                const double w = prior[i] * (cl ? cl[(int64_t)i * spad] : 1.0);
+                if (w > 0.0) st = i;                                           // the last state with weight: guard against u*total == cum
+                cum += w;
+                if (cum > u) break;
+            }
+            if (st < 0) st = 0;
+        }
+        states[(int64_t)nd.node * spad + s] = (uint8_t)st;
+    }
+}
+
 }  // namespace pbk

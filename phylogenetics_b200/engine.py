@@ -217,6 +217,13 @@ class LikelihoodContext:
         self._ck(lib.pb_get_clv(self._ctx, int(node), int(cat), v.ctypes.data, c.ctypes.data))
         return v, c
 
+    def conditional_simulation(self, seed):
+        """One joint draw of every node's state per site given the leaves (pb_conditional_simulation):
+        uint8 [nnodes][nsites].  Needs keep_clv=True and a prior evaluation."""
+        out = np.empty((self.nnodes, self.nsites), dtype=np.uint8)
+        self._ck(lib.pb_conditional_simulation(self._ctx, int(seed) & 0xFFFFFFFFFFFFFFFF, out.ctypes.data, self.nsites))
+        return out
+
     def get_pmatrices(self):
         Pc = np.empty((self.ncat, self.nnodes, self.nstates, self.nstates))
         self._ck(lib.pb_get_pmatrices(self._ctx, Pc.ctypes.data))

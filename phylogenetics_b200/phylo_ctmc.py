@@ -122,3 +122,17 @@ def conditional_likelihoods(t, nstates, leaf_state, transition_probabilities, de
                        node=lambda v, _d: (clv[v, 0].copy(), float(carry[v, 0])),
                        leaf=lambda row, _d: row_state[row],
                        branch=lambda v, d: (d, P[v]))
+
+
+def conditional_simulation_sites(seed, t, nstates, leaf_state, transition_probabilities, nsites, root_frequencies, device=0):
+    """Phylo_ctmc.conditional_simulation (lib/phylo_ctmc.mli:80-90, .ml:122-143) for every site at once, on
+    the device: conditional likelihoods (kept in HBM) followed by one top-down joint draw of all node states.
+    Returns (flat, states uint8 [nnodes][nsites]); observed leaves keep their states.  `seed` keys a
+    counter-based generator (the reference threads a Gsl.Rng.t: same distribution, another stream)."""
+    flat, P, ctx = _prepare(t, nstates, transition_probabilities, device, True, nsites)
+    with ctx:
+        ctx.set_mode(_lib.PB_MODE_PHYLO_CTMC)
+        ctx.set_tips(_leaf_matrix(flat, leaf_state, nsites, nstates))
+        ctx.set_root_frequencies(np.asarray(root_frequencies, dtype=np.float64))
+        ctx.loglik()
+        return flat, ctx.conditional_simulation(seed)

@@ -222,3 +222,35 @@ def test_wag_parses():
     assert np.allclose(rm.sum(axis=1), 0.0, atol=1e-12)
     # A<->R exchangeability 0.551571 sits at (A, R) in ACDEF.. order
     assert rm["ACDEFGHIKLMNPQRSTVWY".index("A"), "ACDEFGHIKLMNPQRSTVWY".index("R")] == 0.551571
+
+
+def test_conditional_simulation_sampler_matches_its_exact_distribution():
+    """oracle: the restated sampler (lib/phylo_ctmc.ml:122-143) draws from pi[root] * prod P[parent, child]
+    restricted to the leaves — the property the reference's expect test checks against rejection sampling
+    (tests/expect/phylo_ctmc_conditional_simulation.ml:66-81)."""
+    import collections
+    from oracle import phylo_ctmc_ref as R, linalg_ref as la
+    rng = np.random.default_rng(4)
+    # ((0:0.8,1:1.2):0.4,(2:0.6,3:0.3):0.1), nodes: 0 root, 1 left inner, 2,3 leaves, 4 right inner, 5,6 leaves
+    child_ptr = np.array([0, 2, 4, 4, 4, 6, 6, 6])
+    child_idx = np.array([1, 4, 2, 3, 5, 6])
+    bl = [0.0, 0.4, 0.8, 1.2, 0.1, 0.6, 0.3]
+    pi = rng.dirichlet(np.ones(4))
+    Q = np.array([[(a + b + 14) / 20.0 * pi[b] if a != b else 0.0 for b in range(4)] for a in range(4)])
+    Q -= np.diag(Q.sum(1))
+    P = np.array([la.expm(t * Q) for t in bl])
+    leaf_sets = {2: [2], 3: None, 5: [0, 3], 6: [1]}
+    # conditional likelihoods by hand (leaf vectors are indicators of the sets; a missing leaf contributes nothing)
+    ind = lambda s: np.array([1.0 if (s is None or i in s) else 0.0 for i in range(4)])
+    cl = {v: ind(s) for v, s in leaf_sets.items()}
+    cl[1] = P[2] @ cl[2]                               # leaf 3 is missing: skipped
+    cl[4] = (P[5] @ cl[5]) * (P[6] @ cl[6])
+    cl[0] = (P[1] @ cl[1]) * (P[4] @ cl[4])
+    clv = np.array([cl[v] for v in range(7)])
+    carry = np.zeros(7)
+    free, table = R.conditional_simulation_exact(0, child_ptr, child_idx, P, pi, leaf_sets)
+    n = 20000
+    draws = np.array([R.conditional_simulation(rng, 0, child_ptr, child_idx, P, clv, carry, pi, leaf_sets) for _ in range(n)])
+    counts = collections.Counter(map(tuple, draws[:, free].tolist()))
+    for key, p in table.items():
+        assert abs(counts.get(key, 0) / n - p) <= 5 * np.sqrt(p * (1 - p) / n) + 1e-4
