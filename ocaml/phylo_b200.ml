@@ -25,6 +25,7 @@ external set_rate_matrix : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> un
 external set_rate_matrix_general : ctx -> Linear_algebra.mat -> unit = "pb_stub_set_rate_matrix_general"
 external set_pmatrices : ctx -> float_vec -> unit = "pb_stub_set_pmatrices"
 external loglik_ : ctx -> float_vec -> float = "pb_stub_loglik"
+external conditional_simulation_ : ctx -> int64 -> tip_matrix -> unit = "pb_stub_conditional_simulation"
 
 let keep_clv_flag = 1
 let mode_phylo_ctmc = 0
@@ -34,6 +35,14 @@ let create ?(device = 0) ?(ncat = 1) ?(keep_clv = false) ~nstates ~nsites ~ntaxa
 
 let set_tree ctx t ~branch_lengths = set_tree_ ctx t.root t.child_ptr t.child_idx t.tip_row branch_lengths
 let set_categories ctx ~rates ~weights = set_categories_ ctx rates weights
+
+(* Phylo_ctmc.conditional_simulation for every site: states.{node, site}; needs ~keep_clv:true and a
+   prior [loglik].  The seed is drawn from the caller's Gsl.Rng.t so that runs stay reproducible. *)
+let conditional_simulation ctx rng ~nnodes ~nsites =
+  let states = Bigarray.(Array2.create int8_unsigned c_layout nnodes nsites) in
+  let seed = Int64.of_int (Gsl.Rng.uniform_int rng (1 lsl 30)) in
+  conditional_simulation_ ctx seed states ;
+  states
 
 let empty_vec = Bigarray.(Array1.create float64 c_layout 0)
 let loglik ctx ?(per_site = empty_vec) () = loglik_ ctx per_site

@@ -70,3 +70,7 @@ val set_rate_matrix : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> unit
 val set_rate_matrix_general : ctx -> Linear_algebra.mat -> unit
 val set_pmatrices : ctx -> float_vec -> unit
 val loglik : ctx -> ?per_site:float_vec -> unit -> float
+
+(** [Phylo_ctmc.conditional_simulation] for every site at once ([pb_conditional_simulation]):
+    [states.{node, site}] after a [loglik] on a context created with [~keep_clv:true]. *)
+val conditional_simulation : ctx -> Gsl.Rng.t -> nnodes:int -> nsites:int -> tip_matrix

@@ -168,6 +168,15 @@ CAMLprim value pb_stub_get_clv(value ctx, value node, value cat, value v, value 
     return Val_unit;
 }
 
+/* states: int8_unsigned Array2 [nnodes][nsites] (c_layout); seed: Int64 drawn by the caller from its Gsl.Rng.t */
+CAMLprim value pb_stub_conditional_simulation(value ctx, value seed, value states)
+{
+    check(Ctx_val(ctx), pb_conditional_simulation(Ctx_val(ctx), (uint64_t)Int64_val(seed),
+                                                  (uint8_t *)Caml_ba_data_val(states),
+                                                  (int64_t)Caml_ba_array_val(states)->dim[1]));
+    return Val_unit;
+}
+
 /* Stand-alone P(t): u, uinv Lacaml mats; lambda, ts vecs; out: float64 Array1 of count*n*n (column-major each) */
 CAMLprim value pb_stub_transition_matrices_eigen(value device, value u, value lambda, value uinv, value ts, value out)
 {
