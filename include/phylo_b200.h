@@ -184,9 +184,18 @@ int pb_conditional_simulation(pb_ctx *ctx, uint64_t seed, uint8_t *states /* hos
 /* Copy out the matrices in use: P[(k*nnodes + v)*n*n ...] column-major. */
 int pb_get_pmatrices(pb_ctx *ctx, double *P);
 
-/* Tunables (all optional): "fused_block" (128|256|512 threads), "fused_spt" (1|2 sites per
- * thread), "fused_exact_log" (1: the fused kernel adds log(max v) at every rescaling like the
- * reference's carry; 0 (default): it accumulates the product of the maxima and takes one log). */
+/* Tunables (all optional; defaults are the measured best).
+ * 4 states, site-resident kernel: "fused_block" (128|256|512 threads), "fused_spt" (1|2|4 sites per
+ *   thread), "fused_exact_log" (1: add log(max v) at every rescaling like the reference's carry;
+ *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
+ *   matrices through the constant bank), "fused_const_cats" (categories per launch).
+ * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
+ *   "level4_min_blocks".
+ * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
+ *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_slots" (cap on the matrix ring),
+ *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
+ *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
+ * "host_chunks": column chunks of pb_loglik_host.  Unknown names are PB_ERR_INVALID_ARG. */
 int pb_set_option(pb_ctx *ctx, const char *name, double value);
 
 /* Device timing of the phases of an evaluation, measured with CUDA events on the
