@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -108,7 +109,10 @@ struct pb_ctx {
     std::vector<FusedOp2> fprog;
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
-    int fused_block = 256, fused_spt = 2, fused_exact_log = 0;
+    int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
+    uint64_t fprog_version = 0;         // identifies the compiled program in the constant bank (launch_fused4c)
+    int fused_pow2 = 1;                 // option "fused_pow2": power-of-two scale factors in the site-resident 4-state kernels
+                                        // (exact and branch-free; 0 = the reference's factor 1/max)
     DevBuf<LevelNode> d_lv_nodes;
     DevBuf<LevelChild> d_lv_children;
     DevBuf<FusedOp2> d_fprog;
@@ -216,7 +220,7 @@ size_t fused_smem_bytes_for(const pb_ctx* c, int block, int spt)
 // shrink the tile (and with it the stack area) before giving up on the fused path.
 bool fused_shape(const pb_ctx* c, int* block, int* spt)
 {
-    const int cand[3][2] = {{c->fused_block, c->fused_spt}, {256, 1}, {128, 1}};
+    const int cand[4][2] = {{c->fused_block, c->fused_spt}, {256, 2}, {256, 1}, {128, 1}};
     for (const auto& k : cand)
         if (fused_smem_bytes_for(c, k[0], k[1]) <= c->smem_optin) { *block = k[0]; *spt = k[1]; return true; }
     return false;
@@ -560,6 +564,10 @@ int compile_tree(pb_ctx* c)
         }
     }
     c->pack_dirty = true;
+    {
+        static std::atomic<uint64_t> next_version{1};
+        c->fprog_version = next_version++;
+    }
 
     // upload
     PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
@@ -642,7 +650,7 @@ int launch_level_dense(pb_ctx* c, const LevelNode* nodes, int first, int count, 
 }
 
 // Fused pruning of the site columns [site0, site1) (multiples of the tile size; the whole shard by default).
-template <int BLOCK, int SPT, bool EXACT>
+template <int BLOCK, int SPT, int EXACT>
 int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
 {
     auto kern = pbk::fused4<BLOCK, SPT, EXACT>;
@@ -673,12 +681,28 @@ bool segment_all_tips(const pb_ctx* c, int first, int count)
     return true;
 }
 
-template <int BLOCK, int SPT>
+size_t fused4c_smem_for(const pb_ctx* c, int block, int spt)
+{
+    return (size_t)c->leaf_nodes.size() * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * block * spt * 8;
+}
+
+// The requested shape if its stack fits shared memory, else the next smaller compiled one.
+bool fused4c_shape(const pb_ctx* c, int* block, int* spt)
+{
+    const int cand[5][2] = {{c->fused_block, c->fused_spt}, {256, 2}, {128, 2}, {256, 1}, {0, 0}};
+    for (const auto& k : cand) {
+        const int key = k[0] * 10 + k[1];
+        const bool compiled = key == 2561 || key == 2562 || key == 2564 || key == 1282 || key == 1284 || key == 5121 || key == 5122;
+        if (compiled && fused4c_smem_for(c, k[0], k[1]) <= c->smem_optin) { *block = k[0]; *spt = k[1]; return true; }
+    }
+    return false;
+}
+
+template <int BLOCK, int SPT, int SCALING>
 int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_t site1)
 {
-    auto kern = pbk::fused4c<BLOCK, SPT, false>;
-    const size_t smem = (size_t)c->leaf_nodes.size() * 16 * 8 + (size_t)std::max(c->fstack, 1) * 4 * BLOCK * SPT * 8 +
-                        c->fprog_c.size() * sizeof(FusedOp2);
+    auto kern = pbk::fused4c<BLOCK, SPT, SCALING>;
+    const size_t smem = fused4c_smem_for(c, BLOCK, SPT);
     PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
@@ -694,12 +718,26 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_
     return PB_OK;
 }
 
+template <int SCALING>
+int launch_fused4c_shape(pb_ctx* c, int block, int spt, int cat0, int k, int64_t site0, int64_t site1)
+{
+    switch (block * 10 + spt) {
+    case 2562: return launch_fused4c_variant<256, 2, SCALING>(c, cat0, k, site0, site1);
+    case 2564: return launch_fused4c_variant<256, 4, SCALING>(c, cat0, k, site0, site1);
+    case 1282: return launch_fused4c_variant<128, 2, SCALING>(c, cat0, k, site0, site1);
+    case 1284: return launch_fused4c_variant<128, 4, SCALING>(c, cat0, k, site0, site1);
+    case 5121: return launch_fused4c_variant<512, 1, SCALING>(c, cat0, k, site0, site1);
+    case 5122: return launch_fused4c_variant<512, 2, SCALING>(c, cat0, k, site0, site1);
+    default: return launch_fused4c_variant<256, 1, SCALING>(c, cat0, k, site0, site1);
+    }
+}
+
 bool fused_const_ok(const pb_ctx* c)
 {
+    int b = 0, q = 0;
     return c->fused_const && !c->fused_exact_log && !c->inner_nodes.empty() &&
-           (int)c->inner_nodes.size() * c->fused_const_cats <= pbk::FUSED_CONST_MATS &&
-           (int)c->inner_nodes.size() <= 128 &&
-           !(c->fused_block == 512 && c->fused_spt == 4) && !(c->fused_block == 128 && c->fused_spt == 1);
+           (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS && (int)c->inner_nodes.size() <= 128 &&
+           (int)c->fprog_c.size() <= pbk::FUSED_CONST_OPS && fused4c_shape(c, &b, &q);
 }
 
 // The inner matrices of as many categories as the constant bank holds per launch.
@@ -710,6 +748,8 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
     if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
     else PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));     // another stream may still be reading the bank
     const int ninner = (int)c->inner_nodes.size();
+    int fb = 0, fq = 0;
+    if (!fused4c_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4c: the tree does not fit shared memory");
     if (regather) {
         PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * ninner * 16));
         pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_inner_nodes.p, ninner, c->nnodes,
@@ -719,26 +759,41 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
     // One category per launch: with several categories resident on an SM their 16 KB matrix sets evict
     // each other from the constant cache (measured: 4 categories per launch is slower, see
     // profiles/r01f_sweep_c2_fused4c.jsonl); per-category launches keep every block of an SM on one set.
-    const int per_launch = c->fused_const_cats;
+    const int per_launch = std::max(1, std::min(c->fused_const_cats, pbk::FUSED_CONST_MATS / std::max(ninner, 1)));
+    // the program shares the bank: upload it unless this context's current program is already there
+    static const pb_ctx* prog_owner[64] = {};
+    static uint64_t prog_version[64] = {};
+    if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != c->fprog_version) {
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, c->d_fprog_c.p, c->fprog_c.size() * sizeof(FusedOp2), 0,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+        prog_owner[c->device & 63] = c;
+        prog_version[c->device & 63] = c->fprog_version;
+    }
     for (int cat0 = 0; cat0 < c->ncat; cat0 += per_launch) {
         const int k = std::min(per_launch, c->ncat - cat0);          // (the last launch may hold fewer)
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat0 * ninner * 16,
                                            (size_t)k * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
                                            c->stream));
-        int rc;
-        switch (c->fused_block * 10 + c->fused_spt) {
-        case 2562: rc = launch_fused4c_variant<256, 2>(c, cat0, k, site0, site1); break;
-        case 2564: rc = launch_fused4c_variant<256, 4>(c, cat0, k, site0, site1); break;
-        case 1282: rc = launch_fused4c_variant<128, 2>(c, cat0, k, site0, site1); break;
-        case 1284: rc = launch_fused4c_variant<128, 4>(c, cat0, k, site0, site1); break;
-        case 5121: rc = launch_fused4c_variant<512, 1>(c, cat0, k, site0, site1); break;
-        case 5122: rc = launch_fused4c_variant<512, 2>(c, cat0, k, site0, site1); break;
-        default: rc = launch_fused4c_variant<256, 1>(c, cat0, k, site0, site1); break;
-        }
+        const int rc = c->fused_pow2 ? launch_fused4c_shape<pbk::SCALE_POW2>(c, fb, fq, cat0, k, site0, site1)
+                                     : launch_fused4c_shape<pbk::SCALE_PRODUCT>(c, fb, fq, cat0, k, site0, site1);
         if (rc != PB_OK) return rc;
     }
     PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
     return PB_OK;
+}
+
+template <int SCALING>
+int launch_fused4_shape(pb_ctx* c, int block, int spt, int64_t site0, int64_t site1)
+{
+    switch (block * 10 + spt) {
+    case 1281: return launch_fused4_variant<128, 1, SCALING>(c, site0, site1);
+    case 2561: return launch_fused4_variant<256, 1, SCALING>(c, site0, site1);
+    case 2562: return launch_fused4_variant<256, 2, SCALING>(c, site0, site1);
+    case 5121: return launch_fused4_variant<512, 1, SCALING>(c, site0, site1);
+    case 1284: return launch_fused4_variant<128, 4, SCALING>(c, site0, site1);
+    case 2564: return launch_fused4_variant<256, 4, SCALING>(c, site0, site1);
+    default: return launch_fused4_variant<128, 2, SCALING>(c, site0, site1);
+    }
 }
 
 int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
@@ -746,26 +801,9 @@ int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
     if (fused_const_ok(c)) return launch_fused4c(c, site0, site1, site0 == 0);
     int fb = c->fused_block, fq = c->fused_spt;
     if (!fused_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4: the tree does not fit shared memory");
-    const int key = fb * 10 + fq;
-    if (c->fused_exact_log) {
-        switch (key) {
-        case 1281: return launch_fused4_variant<128, 1, true>(c, site0, site1);
-        case 2561: return launch_fused4_variant<256, 1, true>(c, site0, site1);
-        case 2562: return launch_fused4_variant<256, 2, true>(c, site0, site1);
-        case 5121: return launch_fused4_variant<512, 1, true>(c, site0, site1);
-        case 1284: return launch_fused4_variant<128, 4, true>(c, site0, site1);
-        default: return launch_fused4_variant<128, 2, true>(c, site0, site1);
-        }
-    }
-    switch (key) {
-    case 1281: return launch_fused4_variant<128, 1, false>(c, site0, site1);
-    case 2561: return launch_fused4_variant<256, 1, false>(c, site0, site1);
-    case 2562: return launch_fused4_variant<256, 2, false>(c, site0, site1);
-    case 5121: return launch_fused4_variant<512, 1, false>(c, site0, site1);
-    case 1284: return launch_fused4_variant<128, 4, false>(c, site0, site1);
-    case 2564: return launch_fused4_variant<256, 4, false>(c, site0, site1);
-    default: return launch_fused4_variant<128, 2, false>(c, site0, site1);
-    }
+    if (c->fused_exact_log) return launch_fused4_shape<pbk::SCALE_EXACT_LOG>(c, fb, fq, site0, site1);
+    if (c->fused_pow2) return launch_fused4_shape<pbk::SCALE_POW2>(c, fb, fq, site0, site1);
+    return launch_fused4_shape<pbk::SCALE_PRODUCT>(c, fb, fq, site0, site1);
 }
 
 // Site-resident tensor-core path (20 / 61 states): pad the branch matrices, then one persistent launch.
@@ -1675,6 +1713,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const_cats = iv;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
+    } else if (k == "fused_pow2") {
+        c->fused_pow2 = iv != 0;
     } else if (k == "fused_exact_log") {
         c->fused_exact_log = iv != 0;
     } else if (k == "level4_async") {

@@ -97,14 +97,24 @@ encode_text(const unsigned char* __restrict__ text, int64_t ld, int width, const
     if (bad) atomicOr(bad_flag, 1);
 }
 
-template <bool EXACT_LOG>
+// Scaling modes of the site-resident kernels (template parameter EXACT_LOG, historically a bool):
+//   0  reference rule, v := (1/max v) v; the maxima are multiplied into (mantissa m, exponent e), one log at the root
+//   1  reference rule, carry += log(max v) at every event, literally lib/phylo_ctmc.ml:33-40
+//   2  same test (min v > thr keeps the vector), but the scale factor is the power of two 2^-k with
+//      k = exponent(max v): exact (no rounding at all), branch-free, no division; the carry is k ln 2
+constexpr int SCALE_PRODUCT = 0, SCALE_EXACT_LOG = 1, SCALE_POW2 = 2;
+#ifndef POW2_BRANCH_FREE
+#define POW2_BRANCH_FREE 1
+#endif
+
+template <int EXACT_LOG>
 struct Scale {             // log-scale accumulator of one (site, category)
-    double m;              // EXACT_LOG: running sum of logs; else mantissa product in [2^-400, 1]
+    double m;              // mode 1: running sum of logs; mode 0: mantissa product in [2^-400, 1]; mode 2: unused
     int e;
-    __device__ __forceinline__ void init() { m = EXACT_LOG ? 0.0 : 1.0; e = 0; }
+    __device__ __forceinline__ void init() { m = EXACT_LOG == 1 ? 0.0 : 1.0; e = 0; }
     __device__ __forceinline__ void add(double mx)
     {
-        if (EXACT_LOG) {
+        if (EXACT_LOG == 1) {
             m += log(mx);
         } else {
             m *= mx;
@@ -115,7 +125,8 @@ struct Scale {             // log-scale accumulator of one (site, category)
     }
     __device__ __forceinline__ double value() const
     {
-        return EXACT_LOG ? m : (log(m) + (double)e * 0.693147180559945309417232121458);
+        if (EXACT_LOG == 2) return (double)e * 0.693147180559945309417232121458;
+        return EXACT_LOG == 1 ? m : (log(m) + (double)e * 0.693147180559945309417232121458);
     }
 };
 
@@ -132,25 +143,57 @@ __device__ __forceinline__ bool keep4(const double (&v)[4], double thr)
     return (v[0] > thr) & (v[1] > thr) & (v[2] > thr) & (v[3] > thr);
 }
 
-template <bool EXACT_LOG>
+template <int EXACT_LOG>
 __device__ __forceinline__ void rescale4(double (&v)[4], Scale<EXACT_LOG>& sc)
 {
+    if (EXACT_LOG == 2) {
+        const int h = max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
+        const int k = (h >> 20) - 1023;
+        const double f = __hiloint2double((1023 - k) << 20, 0);
+        v[0] *= f; v[1] *= f; v[2] *= f; v[3] *= f;
+        sc.e += k;
+        return;
+    }
     const double mx = max_nonneg(max_nonneg(v[0], v[1]), max_nonneg(v[2], v[3]));
     const double inv = 1.0 / mx;
     v[0] = inv * v[0]; v[1] = inv * v[1]; v[2] = inv * v[2]; v[3] = inv * v[3];
     sc.add(mx);
 }
 
-template <bool EXACT_LOG>
+template <int EXACT_LOG>
 __device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, double thr)
 {
+    if (EXACT_LOG == 2 && POW2_BRANCH_FREE) {                     // branch-free, as in shift_all
+        const bool keep = keep4(v, thr);
+        const int h = max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
+        const int k = keep ? 0 : (h >> 20) - 1023;
+        const double f = __hiloint2double((1023 - k) << 20, 0);
+        v[0] *= f; v[1] *= f; v[2] *= f; v[3] *= f;
+        sc.e += k;
+        return;
+    }
     if (!keep4(v, thr)) rescale4(v, sc);
 }
 
 // SV.shift for the thread's SPT sites with ONE branch on the common path (no site rescales).
-template <int SPT, bool EXACT_LOG>
+template <int SPT, int EXACT_LOG>
 __device__ __forceinline__ void shift_all(double (&v)[SPT][4], Scale<EXACT_LOG> (&sc)[SPT], double thr)
 {
+    if (EXACT_LOG == 2 && POW2_BRANCH_FREE) {
+        // power-of-two scaling, no branch: the biased exponent of the largest component comes from the high
+        // words (non-negative doubles order like their bit patterns; a negative rounding residue loses)
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            const bool keep = keep4(v[q], thr);
+            const int h = max(max(__double2hiint(v[q][0]), __double2hiint(v[q][1])),
+                              max(__double2hiint(v[q][2]), __double2hiint(v[q][3])));
+            const int k = keep ? 0 : (h >> 20) - 1023;
+            const double f = __hiloint2double((1023 - k) << 20, 0);
+            v[q][0] *= f; v[q][1] *= f; v[q][2] *= f; v[q][3] *= f;
+            sc[q].e += k;
+        }
+        return;
+    }
     bool keep[SPT];
     bool all = true;
 #pragma unroll
@@ -190,7 +233,7 @@ constexpr int FOP_PUSH_AFTER = 0x100;   // flag in the code word: push ACC after
 
 // Persistent kernel: grid = (blocks_x, ncat); each block stages the P matrices of its category
 // once and then loops over tiles of BLOCK*SPT sites.
-template <int BLOCK, int SPT, bool EXACT_LOG>
+template <int BLOCK, int SPT, int EXACT_LOG>
 __global__ void __launch_bounds__(BLOCK)
 fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
        const double* __restrict__ P, const uint8_t* __restrict__ is_leaf, int nnodes,
@@ -355,8 +398,14 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
 // (blockIdx.y), further categories take further launches.  The matrices travel device -> constant
 // bank in stream order (cudaMemcpyToSymbolAsync, device to device).
 // --------------------------------------------------------------------------
-constexpr int FUSED_CONST_MATS = 508;              // 65 024 bytes: all the user constant bank but 512 bytes
+// The instruction stream sits in the constant bank as well: the interpreter's fetch is then a uniform load
+// (LDCU) and the matrix offsets are uniform BY CONSTRUCTION.  (With the program in shared memory the
+// compiler has to prove the offsets warp-uniform to use uniform loads for the matrices; ptxas did for one
+// form of the rescaling code and did not for another, a 20 % difference.)
+constexpr int FUSED_CONST_MATS = 380;              // 48 640 bytes of inner matrices
+constexpr int FUSED_CONST_OPS = 960;               // 15 360 bytes of program; together 64 000 of the 65 536 bytes
 __constant__ double cPinner[FUSED_CONST_MATS * 16];
+__constant__ int4 cProg[FUSED_CONST_OPS];
 
 // d_Pc[c][k][16] = P[c][inner_nodes[k]][16]   (categories packed back to back: ninner matrices each)
 __global__ void gather_inner_p(const double* __restrict__ P, const int* __restrict__ inner_nodes, int ninner,
@@ -383,8 +432,8 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
 
 // prog: offsets of inner matrices index cPinner (compact inner index * 16); offsets of leaf matrices
 // index the shared-memory array of the ntips leaf matrices (compact leaf index * 16).
-template <int BLOCK, int SPT, bool EXACT_LOG>
-__global__ void __launch_bounds__(BLOCK)
+template <int BLOCK, int SPT, int EXACT_LOG>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 && SPT <= 2) ? 3 : 1)
 fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int ninner,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
@@ -394,7 +443,6 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     extern __shared__ double sh[];
     double* shP = sh;                                       // [nleaf][16], transposed, of this category
     double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
-    FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shS + (size_t)stack_depth * 4 * BLOCK * SPT);
     const int c = cat0 + blockIdx.y, tid = threadIdx.x;     // this launch covers categories cat0 .. cat0 + gridDim.y - 1
     const int cbase = blockIdx.y * ninner * 16;             // where this category's inner matrices sit in cPinner
     {
@@ -403,9 +451,6 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
             const int k = idx >> 4, e = idx & 15;
             shP[k * 16 + (e & 3) * 4 + (e >> 2)] = Pg[(size_t)leaf_nodes[k] * 16 + e];
         }
-        const int4* src = reinterpret_cast<const int4*>(prog);
-        int4* dst = reinterpret_cast<int4*>(shOps);
-        for (int idx = tid; idx < nops; idx += BLOCK) dst[idx] = src[idx];
     }
     __syncthreads();
     const unsigned pbase = (unsigned)__cvta_generic_to_shared(shP);
@@ -429,9 +474,8 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         }
         pk += 2 * spad;
         double* st = shS + tid;
-        const int4* opp = reinterpret_cast<const int4*>(shOps);
         for (int ip = 0; ip < nops; ip++) {
-            const int4 opw = opp[ip];
+            const int4 opw = cProg[ip];                      // uniform fetch
             const int offA = opw.y, offB = opw.z;
             const int shA = opw.w & 0xff, shB = opw.w >> 8;
             const int code = opw.x & 0xff;

@@ -185,17 +185,19 @@ def test_errors_are_reported_not_thrown():
         LikelihoodContext(1, 10, 3)
 
 
+@pytest.mark.parametrize("pow2", [1, 0])
 @pytest.mark.parametrize("block,spt,exact", [(128, 1, 0), (256, 1, 1), (512, 1, 0), (128, 2, 1), (256, 2, 0), (128, 4, 0), (256, 4, 0), (128, 4, 1)])
-def test_fused_variants(block, spt, exact):
-    """Every compiled shape of the fused kernel, with the reference-style log carry and the
-    mantissa/exponent accumulator, on a tree deep enough to use the stack and >32 tips
-    (several packed words)."""
+def test_fused_variants(block, spt, exact, pow2):
+    """Every compiled shape of the fused kernel in its three scaling modes — power-of-two factors (default),
+    the reference's factor 1/max with the mantissa/exponent accumulator, and the reference's literal log
+    carry — on a tree deep enough to use the stack and >32 tips (several packed words)."""
     case = cases.make_case("fusedv", "gtr", 97, 3001, ncat=2, seed=3)
     P = case.host_P()
     with run_ctx(case, "direct", P=P) as ctx:
         ctx.set_option("fused_const", 0)
         ctx.set_option("fused_block", block)
         ctx.set_option("fused_spt", spt)
+        ctx.set_option("fused_pow2", pow2)
         ctx.set_option("fused_exact_log", exact)
         assert ctx.path_name == "fused4"
         total, per_site = ctx.loglik(per_site=True)
@@ -434,17 +436,20 @@ def test_partial_reevaluation_after_one_branch_change(model, ntaxa, nsites, ncat
         assert ctx.nodes_recomputed == f.ninternal
 
 
-@pytest.mark.parametrize("block,spt", [(256, 1), (256, 2), (512, 2), (128, 4)])
+@pytest.mark.parametrize("pow2", [1, 0])
+@pytest.mark.parametrize("block,spt", [(256, 1), (256, 2), (256, 4), (512, 2), (128, 4)])
 @pytest.mark.parametrize("ntaxa,ncat", [(97, 3), (128, 4), (130, 4), (300, 3), (12, 4)])
-def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
-    """fused4c (inner-branch matrices through the constant bank, one launch per category): trees with
-    up to 128 inner branches use it, larger ones fall back to the shared-memory kernel."""
+def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
+    """fused4c (program and inner-branch matrices through the constant bank, one launch per category): trees
+    with up to 128 inner branches use it, larger ones fall back to the shared-memory kernel; both scale-factor
+    rules (power of two / the reference's 1/max)."""
     case = cases.make_case("fusedc", "gtr", ntaxa, 2500, ncat=ncat, seed=4)
     P = case.host_P()
     with run_ctx(case, "direct", P=P) as ctx:
         ctx.set_option("fused_const", 1)
         ctx.set_option("fused_block", block)
         ctx.set_option("fused_spt", spt)
+        ctx.set_option("fused_pow2", pow2)
         assert ctx.path_name == "fused4"
         total, per_site = ctx.loglik(per_site=True)
         check(per_site, total, oracle_per_site(case, P))
@@ -456,7 +461,7 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat):
 
 
 def test_fused_large_tree_falls_back_to_shared_memory_matrices():
-    """More than 508 inner branches do not fit the constant bank: the shared-memory kernel takes over."""
+    """More than 128 inner branches: the shared-memory kernel takes over."""
     case = cases.make_case("fusedbig", "gtr", 600, 700, ncat=1, seed=4)
     P = case.host_P()
     with run_ctx(case, "direct", P=P) as ctx:
