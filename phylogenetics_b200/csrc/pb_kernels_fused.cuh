@@ -163,13 +163,13 @@ __device__ __forceinline__ void rescale4(double (&v)[4], Scale<EXACT_LOG>& sc)
 template <int EXACT_LOG>
 __device__ __forceinline__ void shift4s(double (&v)[4], Scale<EXACT_LOG>& sc, double thr)
 {
-    if (EXACT_LOG == 2 && POW2_BRANCH_FREE) {                     // branch-free, as in shift_all
-        const bool keep = keep4(v, thr);
-        const int h = max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
-        const int k = keep ? 0 : (h >> 20) - 1023;
-        const double f = __hiloint2double((1023 - k) << 20, 0);
+    if (EXACT_LOG == 2 && POW2_BRANCH_FREE) {                     // the same rule as in shift_all
+        const int h0 = __double2hiint(v[0]), h1 = __double2hiint(v[1]), h2 = __double2hiint(v[2]), h3 = __double2hiint(v[3]);
+        const int hmin = min(min(h0, h1), min(h2, h3)), hmax = max(max(h0, h1), max(h2, h3));
+        const int d = (hmin > __double2hiint(thr)) ? 1023 : (hmax >> 20);
+        const double f = __hiloint2double((2046 - d) << 20, 0);
         v[0] *= f; v[1] *= f; v[2] *= f; v[3] *= f;
-        sc.e += k;
+        sc.e += d - 1023;
         return;
     }
     if (!keep4(v, thr)) rescale4(v, sc);
@@ -180,17 +180,20 @@ template <int SPT, int EXACT_LOG>
 __device__ __forceinline__ void shift_all(double (&v)[SPT][4], Scale<EXACT_LOG> (&sc)[SPT], double thr)
 {
     if (EXACT_LOG == 2 && POW2_BRANCH_FREE) {
-        // power-of-two scaling, no branch: the biased exponent of the largest component comes from the high
-        // words (non-negative doubles order like their bit patterns; a negative rounding residue loses)
+        // Power-of-two scaling without a branch and without FP64 instructions in the test: non-negative doubles
+        // order like their bit patterns, so the smallest / largest component are found on the high words (a
+        // negative rounding residue counts as small).  keep <=> min v > thr, compared on the upper 32 bits
+        // (v whose high word equals the threshold's is rescaled too: a sliver of 2^-20 relative width).
+        const int thr_hi = __double2hiint(thr);
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
-            const bool keep = keep4(v[q], thr);
-            const int h = max(max(__double2hiint(v[q][0]), __double2hiint(v[q][1])),
-                              max(__double2hiint(v[q][2]), __double2hiint(v[q][3])));
-            const int k = keep ? 0 : (h >> 20) - 1023;
-            const double f = __hiloint2double((1023 - k) << 20, 0);
+            const int h0 = __double2hiint(v[q][0]), h1 = __double2hiint(v[q][1]);
+            const int h2 = __double2hiint(v[q][2]), h3 = __double2hiint(v[q][3]);
+            const int hmin = min(min(h0, h1), min(h2, h3)), hmax = max(max(h0, h1), max(h2, h3));
+            const int d = (hmin > thr_hi) ? 1023 : (hmax >> 20);        // biased exponent to take out (1023: none)
+            const double f = __hiloint2double((2046 - d) << 20, 0);     // 2^(1023 - d)
             v[q][0] *= f; v[q][1] *= f; v[q][2] *= f; v[q][3] *= f;
-            sc[q].e += k;
+            sc[q].e += d - 1023;
         }
         return;
     }
