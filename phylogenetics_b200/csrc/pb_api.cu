@@ -834,7 +834,7 @@ int launch_fused_dmma_path(pb_ctx* c)
         pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,
                              c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
-        if (pbk::launch_fused_dmma3(n, a, nslot, c->sm_count, smem, c->stream) < 1)
+        if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
             return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
         c->launches++;
         return PB_OK;

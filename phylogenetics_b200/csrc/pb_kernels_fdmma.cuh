@@ -863,7 +863,47 @@ __device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Sc
     }
 }
 
+// Power-of-two form (scaling mode 2 of pb_kernels_fused.cuh): the test and the exponent of the largest
+// component are taken on the high words, so the cross-lane steps are one ballot per site and 32-bit
+// shuffles, and there is no division; v is multiplied by an exact power of two.
 template <int N>
+__device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Scale<2> (&sc)[2], int lane, double thr)
+{
+    constexpr int M8 = Fd3Shape<N>::M8;
+    const int g = lane >> 2, tig = lane & 3;
+    const int thr_hi = __double2hiint(thr);
+    int hmin[2] = {0x7fffffff, 0x7fffffff}, hmax[2] = {(int)0x80000000, (int)0x80000000};
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int mt = 0; mt < M8; mt++)
+            if (mt * 8 + 7 < N || mt * 8 + g < N) {
+                const int h = __double2hiint(v[mt][j]);
+                hmin[j] = min(hmin[j], h);
+                hmax[j] = max(hmax[j], h);
+            }
+    const unsigned b0 = __ballot_sync(0xffffffffu, hmin[0] > thr_hi), b1 = __ballot_sync(0xffffffffu, hmin[1] > thr_hi);
+    if ((b0 & b1) == 0xffffffffu) return;                   // warp-uniform: nothing to rescale
+    const bool odd = g & 1;
+    int keep = odd ? hmax[1] : hmax[0];
+    keep = max(keep, __shfl_xor_sync(0xffffffffu, odd ? hmax[0] : hmax[1], 4));
+    keep = max(keep, __shfl_xor_sync(0xffffffffu, keep, 8));
+    keep = max(keep, __shfl_xor_sync(0xffffffffu, keep, 16));
+    const int other = __shfl_xor_sync(0xffffffffu, keep, 4);
+    const int m[2] = {odd ? other : keep, odd ? keep : other};
+    const unsigned grp = 0x11111111u << tig;
+    const unsigned bits[2] = {b0, b1};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int d = ((bits[j] & grp) == grp) ? 1023 : (m[j] >> 20);      // biased exponent to take out (1023: none)
+        const double f = __hiloint2double((2046 - d) << 20, 0);
+#pragma unroll
+        for (int mt = 0; mt < M8; mt++) v[mt][j] *= f;
+        sc[j].e += d - 1023;
+    }
+}
+
+template <int N, int SCALING>
 __global__ void __launch_bounds__((Fd3Shape<N>::NW + 1) * 32, 1)
 fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int nslot, int stack_smem,
             double* __restrict__ gstack, int gdepth,
@@ -997,7 +1037,7 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
             __syncwarp();
 
             double acc[M8][2];
-            Scale<false> sc[2];
+            Scale<SCALING> sc[2];
             sc[0].init(); sc[1].init();
             int sp = 0;
 #pragma unroll 1
@@ -1175,11 +1215,11 @@ inline size_t fused_dmma3_matsz(int n) { return n == 20 ? Fd3Shape<20>::MATSZ : 
 inline size_t fused_dmma3_leafsz(int n) { return n == 20 ? 20 * Fd3Shape<20>::MP8 : 61 * Fd3Shape<61>::MP8; }
 inline size_t fused_dmma3_tilesz(int n) { return n == 20 ? Fd3Shape<20>::XSZ * Fd3Shape<20>::NW : Fd3Shape<61>::XSZ * Fd3Shape<61>::NW; }
 
-template <int N>
+template <int N, int SCALING>
 int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
 {
     using F = Fd3Shape<N>;
-    auto kern = fused_dmma3<N>;
+    auto kern = fused_dmma3<N, SCALING>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     const int64_t units = a.spad / 8;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + F::NW - 1) / F::NW, sm_count));
@@ -1189,9 +1229,11 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
     return grid;
 }
 
-inline int launch_fused_dmma3(int n, const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
+inline int launch_fused_dmma3(int n, bool pow2, const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
 {
-    return n == 20 ? launch_fused_dmma3_n<20>(a, nslot, sm_count, smem, stream) : launch_fused_dmma3_n<61>(a, nslot, sm_count, smem, stream);
+    if (pow2)
+        return n == 20 ? launch_fused_dmma3_n<20, 2>(a, nslot, sm_count, smem, stream) : launch_fused_dmma3_n<61, 2>(a, nslot, sm_count, smem, stream);
+    return n == 20 ? launch_fused_dmma3_n<20, 0>(a, nslot, sm_count, smem, stream) : launch_fused_dmma3_n<61, 0>(a, nslot, sm_count, smem, stream);
 }
 
 inline void launch_fdmma3_prepare(int n, const double* P, const int* inner_nodes, int ninner, const int* leaf_nodes, int nleaf,

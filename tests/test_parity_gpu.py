@@ -259,6 +259,9 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
         check(per_site, total, expect)
         total2, per_site2 = ctx.loglik(per_site=True)            # bit-reproducible
         assert total2 == total and np.array_equal(per_site, per_site2)
+        ctx.set_option("fused_pow2", 0)                         # the reference's scale factor 1/max instead of 2^-k
+        total4, per_site4 = ctx.loglik(per_site=True)
+        check(per_site4, total4, expect)
         ctx.set_option("fused_dmma", 0)
         assert ctx.path_name == "level_dmma"
         total3, per_site3 = ctx.loglik(per_site=True)
