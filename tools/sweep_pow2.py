@@ -16,6 +16,7 @@ nsites = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
 res = {}
+CATS = int(os.environ.get("CATS", "0"))
 for block, spt, pow2 in [(256, 2, 0), (256, 2, 1), (256, 1, 1), (128, 2, 1), (256, 4, 1)]:
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
         ctx.set_tree(f, case.bl)
@@ -26,6 +27,8 @@ for block, spt, pow2 in [(256, 2, 0), (256, 2, 1), (256, 1, 1), (128, 2, 1), (25
         ctx.set_option("fused_block", block)
         ctx.set_option("fused_spt", spt)
         ctx.set_option("fused_pow2", pow2)
+        if CATS:
+            ctx.set_option("fused_const_cats", CATS)
         ctx.set_timing(True)
         ms = []
         for _ in range(6):
