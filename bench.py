@@ -375,7 +375,8 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc + (" per GPU" if world > 1 else ""), "sites_per_gpu": nsites,
                        "ntaxa": ntaxa, "nstates": n, "ncat": ncat, "internal_nodes": ninternal,
-                       "path": ctx.path_name, "l2": "flushed between steps (256 MiB memset outside the event pairs)",
+                       "path": ctx.path_name,
+                       "rescaling": "reference trigger (min v <= threshold), exact power-of-two factor; see reference_scale_factor", "l2": "flushed between steps (256 MiB memset outside the event pairs)",
                        "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
                        "parity_gate": {"per_site_max_rel_err": rel, "sites_checked": chk,
                                        "total_vs_sum_of_sites_rel": tot_rel}},
@@ -389,6 +390,28 @@ def run_ours(args, rank, world, local_rank):
             "phase_ms": {"pmat": float(pm[:, 0].mean()), "pruning": prune_avg_ms, "root": float(pm[:, 2].mean())},
             "clocks": clocks,
         }
+        if world == 1 and ctx.path_name in ("fused4", "fused_dmma"):
+            # the same site-resident kernel with the reference's own scale factor (v := v / max v) instead of
+            # the default exact power of two ("Rescaling"): time and agreement
+            ctx.set_option("fused_pow2", 0)
+            if n == 4:
+                ctx.set_option("fused_spt", 2)          # that mode's fastest shape (profiles/r01f_sweep_c2_fused4c.jsonl)
+            ms = []
+            for it in range(8):
+                flush.zero_()
+                ctx.set_branch_lengths(case.bl)
+                tot_ref, ps_ref = ctx.loglik(per_site=True)
+                if it >= 3:
+                    ms.append(sum(ctx.get_timing()))
+            ref_ms = float(np.mean(ms))
+            line["reference_scale_factor"] = {
+                "ms_per_step_device_phases": ref_ms, "value": nsites * ninternal / (ref_ms * 1e-3), "unit": UNIT,
+                "per_site_max_rel_diff_vs_default": float(np.max(np.abs(ps_ref - per_site0) / np.abs(per_site0))),
+                "note": "option fused_pow2=0: rescaling multiplies by 1/max v exactly as SV.shift does; the default "
+                        "multiplies by 2^-exponent(max v), which is exact in floating point"}
+            ctx.set_option("fused_pow2", 1)
+            if n == 4:
+                ctx.set_option("fused_spt", 4)
         if world == 1 and n == 4 and ctx.path_name == "fused4":
             # the level-scheduled kernel the north star describes (CLVs materialised in HBM), same inputs
             ctx.close()
