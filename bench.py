@@ -65,6 +65,7 @@ def algorithmic_flops_per_site(n, ncat, ntaxa):
 
 
 FP64_DMMA_PEAK_TFLOPS = 36.8      # profiles/r01_fp64_peak_dmma_shapes.jsonl
+FP64_DFMA_PEAK_TFLOPS = 34.8      # profiles/r01_fp64_peak.json (measured DFMA rate; algorithmic flops exclude rescaling)
 
 
 def measured_peaks():
@@ -352,6 +353,8 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms_per_step": prune_avg_ms,
                 "algorithmic_bytes_per_step": bytes_eval,
                 "fp64_tflops_achieved": flops_eval / (prune_avg_ms * 1e-3) / 1e12,
+                "fp64_peak_tflops": FP64_DFMA_PEAK_TFLOPS,
+                "fp64_frac": flops_eval / (prune_avg_ms * 1e-3) / 1e12 / FP64_DFMA_PEAK_TFLOPS,
                 "note": ("fused4 keeps conditional likelihoods on chip: it moves ntaxa+8C bytes/site of HBM, "
                          "so against the level-scheduled algorithmic bytes the fraction can exceed 1; its own "
                          "bound is the FP64 pipe" if ctx.path_name in ("fused4", "fused_dmma") else
