@@ -58,12 +58,20 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def test_two_ranks_optimise_like_one_context():
     world = 2
+    port = _free_port()
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        procs = [ctx.Process(target=_worker, args=(r, world, 29631, out)) for r in range(world)]
+        procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
         for p in procs:
             p.start()
         for p in procs:
