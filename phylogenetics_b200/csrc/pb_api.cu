@@ -828,7 +828,7 @@ int launch_fused_dmma_path(pb_ctx* c)
         pbk::launch_fdmma3_prepare(n, c->d_P.p, c->d_inner_nodes.p, ninner, c->d_leaf_nodes.p, nleaf, c->nnodes, c->ncat,
                                    c->d_Ppad.p, c->d_PTleaf.p, c->stream);
         c->launches++;
-        const int grid = pbk::fused_dmma2_grid(n, c->sm_count, c->spad);
+        const int grid = pbk::fused_dmma3_grid(n, c->sm_count, c->spad);
         const int gdepth = c->dstack + 1 - ssm;
         PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * pbk::fused_dmma3_tilesz(n), 1)));
         pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,

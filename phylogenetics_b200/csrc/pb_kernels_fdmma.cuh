@@ -1214,6 +1214,11 @@ inline size_t fused_dmma3_panelsz(int n) { return n == 20 ? Fd3Shape<20>::PSZ : 
 inline size_t fused_dmma3_matsz(int n) { return n == 20 ? Fd3Shape<20>::MATSZ : Fd3Shape<61>::MATSZ; }
 inline size_t fused_dmma3_leafsz(int n) { return n == 20 ? 20 * Fd3Shape<20>::MP8 : 61 * Fd3Shape<61>::MP8; }
 inline size_t fused_dmma3_tilesz(int n) { return n == 20 ? Fd3Shape<20>::XSZ * Fd3Shape<20>::NW : Fd3Shape<61>::XSZ * Fd3Shape<61>::NW; }
+inline int fused_dmma3_grid(int n, int sm_count, int64_t spad)
+{
+    const int nw = n == 20 ? Fd3Shape<20>::NW : Fd3Shape<61>::NW;
+    return (int)std::max<int64_t>(1, std::min<int64_t>((spad / 8 + nw - 1) / nw, sm_count));
+}
 
 template <int N, int SCALING>
 int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
@@ -1221,8 +1226,7 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
     using F = Fd3Shape<N>;
     auto kern = fused_dmma3<N, SCALING>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    const int64_t units = a.spad / 8;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + F::NW - 1) / F::NW, sm_count));
+    const int grid = fused_dmma3_grid(N, sm_count, a.spad);
     kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
                                                    a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
                                                    a.pi, a.thr, a.shift_at_root, a.site_cat);
