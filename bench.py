@@ -304,26 +304,40 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # end-to-end through the public API with HOST buffers: H2D of the step's tips from pinned
-    # memory + evaluation + D2H of the total, every step.
+    # memory + evaluation + D2H of the total, every step.  Nucleotide alignments cross PCIe 2-bit packed
+    # (pb_loglik_host_packed2, the layout the binding fills from `leaf_state` for 4-state alphabets,
+    # INTEGRATION.md); the byte-per-site call (pb_loglik_host) is timed beside it.
     e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(2):
-        ctx.loglik_host_ptr(tips_pinned.data_ptr(), nsites)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        ctx.set_branch_lengths(case.bl)
-        tot = ctx.loglik_host_ptr(tips_pinned.data_ptr(), nsites)
+
+    def e2e_loop(call):
+        for _ in range(2):
+            call()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            ctx.set_branch_lengths(case.bl)
+            tot = call()
+            if world > 1:
+                tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt)
+                tot = float(tt.item())
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
-            tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt)
-            tot = float(tt.item())
-    e1.record(stream)
-    barrier()
-    e2e_t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = world * nsites * ninternal * e2e_steps / float(e2e_t.item())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * nsites * ninternal * e2e_steps / float(t.item()), tot
+
+    e2e_bytes_val, tot_bytes = e2e_loop(lambda: ctx.loglik_host_ptr(tips_pinned.data_ptr(), nsites))
+    e2e_val, e2e_h2d, e2e_call = e2e_bytes_val, int(case.tips.nbytes), "pb_loglik_host (one byte per site)"
+    if n == 4:
+        from phylogenetics_b200.engine import pack_tips2
+        packed_pinned = torch.from_numpy(pack_tips2(case.tips)).pin_memory()
+        e2e_val, tot_packed = e2e_loop(lambda: ctx.loglik_host_packed2_ptr(packed_pinned.data_ptr(), packed_pinned.shape[1]))
+        if not abs(tot_packed - tot_bytes) <= 1e-12 * abs(tot_bytes):
+            raise SystemExit("packed and byte-per-site evaluations disagree: %r %r" % (tot_packed, tot_bytes))
+        e2e_h2d, e2e_call = int(packed_pinned.numel()), "pb_loglik_host_packed2 (2-bit packed nucleotides, 4 sites per byte)"
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -384,9 +398,10 @@ def run_ours(args, rank, world, local_rank):
                        "parity_gate": {"per_site_max_rel_err": rel, "sites_checked": chk,
                                        "total_vs_sum_of_sites_rel": tot_rel}},
             "roofline": roof,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(case.tips.nbytes),
-                    "d2h_bytes_per_step": 8, "steps": e2e_steps,
-                    "note": "pb_set_branch_lengths + pb_loglik_host per step: tips copied from pinned host memory in column chunks overlapped with the pruning, total read back to the host"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": 8, "steps": e2e_steps, "call": e2e_call,
+                    "byte_per_site": {"value": e2e_bytes_val, "h2d_bytes_per_step": int(case.tips.nbytes), "call": "pb_loglik_host"},
+                    "note": "pb_set_branch_lengths + one host-alignment evaluation call per step: tips copied from pinned host memory in column chunks overlapped with the pruning, total read back to the host"},
             "collective_ms_per_step": (sum(collective_ms) / len(collective_ms)) if world > 1 else 0.0,
             "per_rank_ms": per_rank,
             "gpu_launches": int(launches),

@@ -151,6 +151,7 @@ struct pb_ctx {
 
     // inputs
     DevBuf<uint8_t> d_tips;
+    DevBuf<uint8_t> d_tips2;            // 2-bit packed upload buffer [ntaxa][spad/4] (pb_*_packed2)
     DevBuf<uint64_t> d_masks;
     bool have_tips = false, have_masks = false;
     DevBuf<double> d_pi, d_rates, d_weights, d_blen;
@@ -741,8 +742,9 @@ bool fused_const_ok(const pb_ctx* c)
 }
 
 // The inner matrices of as many categories as the constant bank holds per launch.
-int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
+int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
 {
+    if (cat_hi < 0) cat_hi = c->ncat;
     std::lock_guard<std::mutex> lock(g_const_mutex);
     cudaEvent_t& bank_free = g_const_event[c->device & 63];
     if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
@@ -769,8 +771,8 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather)
         prog_owner[c->device & 63] = c;
         prog_version[c->device & 63] = c->fprog_version;
     }
-    for (int cat0 = 0; cat0 < c->ncat; cat0 += per_launch) {
-        const int k = std::min(per_launch, c->ncat - cat0);          // (the last launch may hold fewer)
+    for (int cat0 = cat_lo; cat0 < cat_hi; cat0 += per_launch) {
+        const int k = std::min(per_launch, cat_hi - cat0);           // (the last launch may hold fewer)
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat0 * ninner * 16,
                                            (size_t)k * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
                                            c->stream));
@@ -1298,6 +1300,29 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     return PB_OK;
 }
 
+int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
+{
+    PB_ENTER(c);
+    const int64_t nbytes = (c->nsites + 3) / 4;
+    if (c->n != 4) return fail(c, PB_ERR_STATE, "2-bit packed tips are for 4-state alphabets");
+    if (!packed || ld < nbytes) return fail(c, PB_ERR_INVALID_ARG, "packed tips: null pointer or ld < ceil(nsites / 4)");
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(c, c->d_tips2.ensure((size_t)c->ntaxa * (c->spad / 4)));
+    PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips2.p, c->spad / 4, packed, ld, nbytes, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
+    pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
+        c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, 0, nbytes);
+    c->launches++;
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    c->have_tips = true;
+    c->have_masks = false;
+    c->pack_dirty = true;
+    c->tips_checked = false;
+    c->all_dirty = true;
+    return PB_OK;
+}
+
 int pb_set_site_weights(pb_ctx* c, const double* w)
 {
     PB_ENTER(c);
@@ -1515,14 +1540,16 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
     return PB_OK;
 }
 
-int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, double* per_site)
+static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool packed2, double* total, double* per_site)
 {
     PB_ENTER(c);
-    if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
+    if (packed2 && c->n != 4) return fail(c, PB_ERR_STATE, "2-bit packed tips are for 4-state alphabets");
+    if (!states || ld < (packed2 ? (c->nsites + 3) / 4 : c->nsites))
+        return fail(c, PB_ERR_INVALID_ARG, packed2 ? "packed tips: null pointer or ld < ceil(nsites / 4)" : "tips: null pointer or ld < nsites");
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
     if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
     if (path_of(c) != PATH_FUSED4 || c->host_chunks == 1 || c->spad < 8192) {
-        int rc = pb_set_tips(c, states, ld);
+        int rc = packed2 ? pb_set_tips_packed2(c, states, ld) : pb_set_tips(c, states, ld);
         if (rc != PB_OK) return rc;
         return pb_loglik(c, total, per_site);
     }
@@ -1530,6 +1557,7 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
     // chunk is packed, pruned and root-reduced on the compute stream.
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
+    if (packed2) PB_CUDA(c, c->d_tips2.ensure((size_t)c->ntaxa * (c->spad / 4)));
     if (!c->copy_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->ev_start) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     while ((int)c->chunk_events.size() < c->host_chunks) {
@@ -1550,19 +1578,35 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
     PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
     PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
     const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
+    // A 2-bit packed alignment crosses PCIe faster than one category is pruned: only the first category is
+    // pruned chunk by chunk behind the copy, the others run once over all the sites at full efficiency.
+    const bool first_cat_only = packed2 && c->ncat > 1 && fused_const_ok(c);
     int k = 0;
     for (int64_t s0 = 0; s0 < c->spad; s0 += chunk, k++) {
         const int64_t s1 = std::min(s0 + chunk, c->spad);
         const int64_t w = std::min(s1, c->nsites) - s0;
-        if (w > 0)
+        if (w > 0 && !packed2)
             PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p + s0, c->spad, states + s0, ld, w, c->ntaxa,
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+        if (w > 0 && packed2)                                // chunk bounds are multiples of 1024 sites = 256 bytes
+            PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips2.p + s0 / 4, c->spad / 4, states + s0 / 4, ld, (w + 3) / 4, c->ntaxa,
                                          cudaMemcpyHostToDevice, c->copy_stream));
         PB_CUDA(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
         PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+        if (w > 0 && packed2) {
+            const int64_t nb = (w + 3) / 4;
+            pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nb + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
+                c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, s0 / 4, s0 / 4 + nb);
+            c->launches++;
+        }
         pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
             c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad, s0, s1,
             c->d_bad.p);
         c->launches++;
+        if (first_cat_only) {                                // the other categories follow once, over all the sites
+            if ((rc = launch_fused4c(c, s0, s1, s0 == 0, 0, 1)) != PB_OK) return rc;
+            continue;
+        }
         if ((rc = launch_fused4(c, s0, s1)) != PB_OK) return rc;
         const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
         if (b1 > b0) {
@@ -1571,6 +1615,13 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
                 c->spad, b0, c->d_per_site.p, c->d_partials.p);
             c->launches++;
         }
+    }
+    if (first_cat_only) {
+        if (c->ncat > 1 && (rc = launch_fused4c(c, 0, c->spad, false, 1, c->ncat)) != PB_OK) return rc;
+        pbk::root_combine<<<(unsigned)nblocks, 256, 0, c->stream>>>(
+            c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
+            c->spad, 0, c->d_per_site.p, c->d_partials.p);
+        c->launches++;
     }
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, nblocks, c->d_total.p);
@@ -1586,6 +1637,16 @@ int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, 
     c->all_dirty = true;
     c->evaluated = true;
     return pb_loglik_fetch(c, total, per_site);
+}
+
+int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, double* per_site)
+{
+    return loglik_host_impl(c, states, ld, false, total, per_site);
+}
+
+int pb_loglik_host_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld, double* total, double* per_site)
+{
+    return loglik_host_impl(c, packed, ld, true, total, per_site);
 }
 
 int pb_loglik(pb_ctx* c, double* total, double* per_site)

@@ -62,6 +62,21 @@ pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__
     if (bad) atomicOr(bad_flag, 1);
 }
 
+// Nucleotide alignments that cross PCIe 2-bit packed (pb_set_tips_packed2 / pb_loglik_host_packed2): byte b of a
+// row holds sites 4b..4b+3, site 4b+j in bits 2j..2j+1.  One thread per packed byte writes its four states
+// as one 32-bit store into the uint8 tip matrix every kernel reads; columns [byte0, byte1) of every row.
+__global__ void __launch_bounds__(256)
+expand_tips2(const uint8_t* __restrict__ in, int64_t ld_in, uint8_t* __restrict__ tips, int64_t ld_out,
+             int64_t byte0, int64_t byte1)
+{
+    const int row = blockIdx.y;
+    for (int64_t b = byte0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < byte1; b += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned v = in[(int64_t)row * ld_in + b];
+        const unsigned out = (v & 3u) | ((v & 12u) << 6) | ((v & 48u) << 12) | ((v & 192u) << 18);
+        *reinterpret_cast<unsigned*>(tips + (int64_t)row * ld_out + 4 * b) = out;
+    }
+}
+
 // Flags tip states >= nstates (the level kernels index P with them).
 __global__ void __launch_bounds__(256)
 validate_tips(const uint8_t* __restrict__ tips, int64_t total, int nstates, int* __restrict__ bad_flag)

@@ -197,6 +197,28 @@ class LikelihoodContext:
                                     None if ps is None else ps.ctypes.data))
         return (total.value, ps) if per_site else total.value
 
+    def loglik_host_packed2_ptr(self, host_ptr, ld, per_site=False):
+        """pb_loglik_host_packed2: the same from a 2-bit packed host alignment (uint8 [ntaxa][>= ceil(nsites/4)],
+        see pack_tips2)."""
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_loglik_host_packed2(self._ctx, ctypes.c_void_p(host_ptr), int(ld), ctypes.byref(total),
+                                            None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
+    def loglik_host_packed2(self, packed, per_site=False):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if packed.ndim != 2 or packed.shape[0] != self.ntaxa or packed.shape[1] < (self.nsites + 3) // 4:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "packed tips must be uint8 [ntaxa][>= ceil(nsites/4)]")
+        return self.loglik_host_packed2_ptr(packed.ctypes.data, packed.shape[1], per_site)
+
+    def set_tips_packed2(self, packed):
+        """pb_set_tips_packed2: upload a 2-bit packed nucleotide alignment (4 sites per byte)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if packed.ndim != 2 or packed.shape[0] != self.ntaxa or packed.shape[1] < (self.nsites + 3) // 4:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "packed tips must be uint8 [ntaxa][>= ceil(nsites/4)]")
+        self._ck(lib.pb_set_tips_packed2(self._ctx, packed.ctypes.data, packed.shape[1]))
+
     def enqueue(self):
         self._ck(lib.pb_loglik_enqueue(self._ctx))
 
@@ -290,6 +312,19 @@ def host_reversible_eigensystem(Q, pi):
     if rc != 0:
         raise _lib.PhyloB200Error(rc, "rate matrix is not reversible with respect to pi")
     return np.ascontiguousarray(U.T), lam, np.ascontiguousarray(Ui.T)
+
+
+def pack_tips2(tips):
+    """uint8 states 0..3 [ntaxa][nsites] -> 2-bit packed [ntaxa][ceil(nsites/4)]: site 4b+j in bits 2j..2j+1 of byte b
+    (the host layout of pb_set_tips_packed2 / pb_loglik_host_packed2)."""
+    tips = np.asarray(tips, dtype=np.uint8)
+    if tips.ndim != 2 or (tips.size and tips.max() > 3):
+        raise ValueError("pack_tips2: states must be 0..3, shape [ntaxa][nsites]")
+    n = tips.shape[1]
+    pad = (-n) % 4
+    t = np.pad(tips, ((0, 0), (0, pad))) if pad else tips
+    t = t.reshape(t.shape[0], -1, 4)
+    return (t[:, :, 0] | (t[:, :, 1] << 2) | (t[:, :, 2] << 4) | (t[:, :, 3] << 6)).astype(np.uint8)
 
 
 def compress_site_patterns(tips):

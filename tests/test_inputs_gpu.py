@@ -70,3 +70,35 @@ def test_site_pattern_compression():
         assert abs(unweighted - per_pattern.sum()) <= 1e-10 * abs(unweighted)
         with pytest.raises(_lib.PhyloB200InvalidArgument):
             ctx.set_site_weights(-counts)
+
+
+@pytest.mark.parametrize("nsites,chunks", [(20001, 4), (50000, 3), (1003, 8), (7, 1)])
+def test_two_bit_packed_host_alignment(nsites, chunks):
+    """pb_set_tips_packed2 / pb_loglik_host_packed2: a nucleotide alignment that crosses PCIe at 4 sites per byte
+    gives bit-identical results to the byte-per-site calls, on ragged site counts, through the chunked
+    pipeline and its small-input fall-back, and for the level kernels (which read the expanded matrix)."""
+    import cases
+    from phylogenetics_b200.engine import pack_tips2
+    case = cases.make_case("pk2", "gtr", 37, nsites, ncat=2, seed=6)
+    packed = pack_tips2(case.tips)
+    assert packed.shape == (37, (nsites + 3) // 4)
+    for level in (False, True):
+        with LikelihoodContext(4, nsites, 37, ncat=2, level_kernels=level) as ctx:
+            ctx.set_tree(case.flat, case.bl)
+            ctx.set_categories(case.rates, case.weights)
+            ctx.set_rate_matrix(case.Q, case.pi)
+            ctx.set_root_frequencies(case.pi)
+            ctx.set_option("host_chunks", chunks)
+            ctx.set_tips(case.tips)
+            total, per_site = ctx.loglik(per_site=True)
+            ctx.set_tips_packed2(packed)
+            total2, per_site2 = ctx.loglik(per_site=True)
+            assert total2 == total and np.array_equal(per_site2, per_site)
+            total3, per_site3 = ctx.loglik_host_packed2(packed, per_site=True)
+            assert np.array_equal(per_site3, per_site)
+            assert abs(total3 - total) <= 1e-12 * abs(total)
+            total4 = ctx.loglik()                        # the expanded matrix stays resident
+            assert abs(total4 - total) <= 1e-12 * abs(total)
+    with LikelihoodContext(20, 10, 5) as ctx:            # 4 states only
+        with pytest.raises(_lib.PhyloB200Error):
+            ctx.set_tips_packed2(np.zeros((5, 3), np.uint8))

@@ -1,0 +1,26 @@
+"""End-to-end time of one evaluation from a pinned host alignment (c2 shape), byte-per-site vs 2-bit packed,
+as a function of the number of column chunks of the copy/compute pipeline."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import cases
+from phylogenetics_b200.engine import LikelihoodContext, pack_tips2
+nsites = 1_000_000
+case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
+f = case.flat
+tips = torch.from_numpy(case.tips).pin_memory()
+packed = torch.from_numpy(pack_tips2(case.tips)).pin_memory()
+with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
+    ctx.set_tree(f, case.bl); ctx.set_categories(case.rates, case.weights)
+    ctx.set_rate_matrix(case.Q, case.pi); ctx.set_root_frequencies(case.pi)
+    for chunks in (1, 2, 3, 4, 6, 8):
+        ctx.set_option("host_chunks", chunks)
+        for name, call in (("packed2", lambda: ctx.loglik_host_packed2_ptr(packed.data_ptr(), packed.shape[1])),
+                           ("bytes", lambda: ctx.loglik_host_ptr(tips.data_ptr(), nsites))):
+            call(); call()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(10):
+                ctx.set_branch_lengths(case.bl); call()
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
+            print(json.dumps({"host_chunks": chunks, "input": name, "ms_per_evaluation": dt * 1e3}), flush=True)
