@@ -17,6 +17,7 @@ external set_tree_ : ctx -> int -> int32_vec -> int32_vec -> int32_vec -> float_
   = "pb_stub_set_tree_bytecode" "pb_stub_set_tree"
 external set_branch_lengths : ctx -> float_vec -> unit = "pb_stub_set_branch_lengths"
 external set_tips : ctx -> tip_matrix -> unit = "pb_stub_set_tips"
+external set_tips_packed2 : ctx -> tip_matrix -> unit = "pb_stub_set_tips_packed2"
 external set_root_frequencies : ctx -> Linear_algebra.vec -> unit = "pb_stub_set_root_frequencies"
 external set_categories_ : ctx -> float_vec -> float_vec -> unit = "pb_stub_set_categories"
 external set_eigensystem : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
@@ -99,9 +100,23 @@ let pruning_sites t ~nstates ~nsites ~transition_probabilities ~leaf_state ~root
           done
         done) ;
   set_pmatrices ctx p ;
-  let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
-  Array.iteri leaves ~f:(fun row l -> for s = 0 to nsites - 1 do tips.{row, s} <- leaf_state l s done) ;
-  set_tips ctx tips ;
+  (* leaf_state is evaluated once per (leaf, site) either way; nucleotides are written 2-bit packed, 4 sites per
+     byte, which is what crosses PCIe (pb_set_tips_packed2) *)
+  if nstates = 4 then begin
+    let nbytes = (nsites + 3) / 4 in
+    let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nbytes) in
+    Bigarray.Array2.fill tips 0 ;
+    Array.iteri leaves ~f:(fun row l ->
+        for s = 0 to nsites - 1 do
+          tips.{row, s / 4} <- tips.{row, s / 4} lor (leaf_state l s lsl (2 * (s land 3)))
+        done) ;
+    set_tips_packed2 ctx tips
+  end
+  else begin
+    let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
+    Array.iteri leaves ~f:(fun row l -> for s = 0 to nsites - 1 do tips.{row, s} <- leaf_state l s done) ;
+    set_tips ctx tips
+  end ;
   set_mode ctx mode_phylo_ctmc ;
   set_root_frequencies ctx root_frequencies ;
   let per_site = Bigarray.(Array1.create float64 c_layout nsites) in

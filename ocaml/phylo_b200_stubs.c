@@ -103,6 +103,21 @@ CAMLprim value pb_stub_set_tips(value ctx, value tips)
     CAMLreturn(Val_unit);
 }
 
+/* tips: int8_unsigned Array2 [ntaxa][ceil(nsites/4)], nucleotides 2-bit packed (site 4b+j in bits 2j..2j+1 of byte b) */
+CAMLprim value pb_stub_set_tips_packed2(value ctx, value tips)
+{
+    CAMLparam2(ctx, tips);
+    pb_ctx *c = Ctx_val(ctx);
+    const uint8_t *p = (const uint8_t *)Caml_ba_data_val(tips);
+    int64_t ld = Caml_ba_array_val(tips)->dim[1];
+    int rc;
+    caml_release_runtime_system();
+    rc = pb_set_tips_packed2(c, p, ld);
+    caml_acquire_runtime_system();
+    check(c, rc);
+    CAMLreturn(Val_unit);
+}
+
 CAMLprim value pb_stub_set_root_frequencies(value ctx, value pi)
 {
     check(Ctx_val(ctx), pb_set_root_frequencies(Ctx_val(ctx), (const double *)Caml_ba_data_val(pi)));
