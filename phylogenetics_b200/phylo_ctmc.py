@@ -79,7 +79,12 @@ def pruning_sites(t, nstates, transition_probabilities, leaf_state, nsites, root
     flat, _, ctx = _prepare(t, nstates, transition_probabilities, device, False, nsites, level_kernels)
     with ctx:
         ctx.set_mode(_lib.PB_MODE_PHYLO_CTMC)
-        ctx.set_tips(_leaf_matrix(flat, leaf_state, nsites, nstates))
+        tips = _leaf_matrix(flat, leaf_state, nsites, nstates)
+        if nstates == 4:
+            from .engine import pack_tips2
+            ctx.set_tips_packed2(pack_tips2(tips))        # nucleotides cross PCIe at 4 sites per byte
+        else:
+            ctx.set_tips(tips)
         ctx.set_root_frequencies(root_frequencies)
         _, per_site = ctx.loglik(per_site=True)
     return per_site
