@@ -14,6 +14,7 @@ packed = torch.from_numpy(pack_tips2(case.tips)).pin_memory()
 with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
     ctx.set_tree(f, case.bl); ctx.set_categories(case.rates, case.weights)
     ctx.set_rate_matrix(case.Q, case.pi); ctx.set_root_frequencies(case.pi)
+    ctx.set_timing(True)
     for chunks in (1, 2, 3, 4, 6, 8):
         ctx.set_option("host_chunks", chunks)
         for name, call in (("packed2", lambda: ctx.loglik_host_packed2_ptr(packed.data_ptr(), packed.shape[1])),
@@ -23,4 +24,5 @@ with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
             for _ in range(10):
                 ctx.set_branch_lengths(case.bl); call()
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 10
-            print(json.dumps({"host_chunks": chunks, "input": name, "ms_per_evaluation": dt * 1e3}), flush=True)
+            print(json.dumps({"host_chunks": chunks, "input": name, "ms_per_evaluation": dt * 1e3,
+                              "device_phases_ms_last": ctx.get_timing()}), flush=True)
