@@ -148,3 +148,17 @@ def test_compress_site_patterns_host():
     patterns, counts, inverse = compress_site_patterns(tips)
     assert patterns.shape == (2, 3) and sorted(counts.tolist()) == [1.0, 2.0, 3.0]
     assert np.array_equal(patterns[:, inverse], tips)
+
+
+def test_pack_tips2_layout():
+    """Host layout of pb_set_tips_packed2: site 4b+j of a row in bits 2j..2j+1 of byte b, ragged tail zero padded."""
+    from phylogenetics_b200.engine import pack_tips2
+    rng = np.random.default_rng(3)
+    for nsites in (1, 4, 7, 1003):
+        tips = rng.integers(0, 4, size=(5, nsites), dtype=np.uint8)
+        packed = pack_tips2(tips)
+        assert packed.shape == (5, (nsites + 3) // 4) and packed.dtype == np.uint8
+        back = np.stack([(packed >> (2 * j)) & 3 for j in range(4)], axis=2).reshape(5, -1)[:, :nsites]
+        assert np.array_equal(back, tips)
+    with pytest.raises(ValueError):
+        pack_tips2(np.array([[0, 4]], dtype=np.uint8))
