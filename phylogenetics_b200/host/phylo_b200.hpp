@@ -146,6 +146,16 @@ public:
         nnodes_ = f.nnodes();
     }
     void set_tips(const std::vector<uint8_t>& tips, int64_t ld) { check(c_, pb_set_tips(c_, tips.data(), ld)); }
+    // nucleotides 2-bit packed, 4 sites per byte (pb_set_tips_packed2)
+    void set_tips_packed2(const std::vector<uint8_t>& packed, int64_t ld) { check(c_, pb_set_tips_packed2(c_, packed.data(), ld)); }
+    void set_option(const char* name, double value) { check(c_, pb_set_option(c_, name, value)); }
+    // Phylo_ctmc.conditional_simulation for every site: states[node * nsites + site] (needs PB_FLAG_KEEP_CLV)
+    std::vector<uint8_t> conditional_simulation(uint64_t seed)
+    {
+        std::vector<uint8_t> states((size_t)nnodes_ * (size_t)nsites_);
+        check(c_, pb_conditional_simulation(c_, seed, states.data(), nsites_));
+        return states;
+    }
     void set_root_frequencies(const Vec& pi) { check(c_, pb_set_root_frequencies(c_, pi.data())); }
     void set_eigensystem(const Mat& u, const Vec& lambda, const Mat& uinv)
     {

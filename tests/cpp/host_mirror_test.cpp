@@ -79,6 +79,45 @@ int main()
         std::printf("%-58s %s\n", "evaluation before inputs -> Failure", threw ? "ok" : "FAIL");
         failures += !threw;
     }
+    // 5. 2-bit packed nucleotide upload == byte-per-site upload; both scale-factor rules; conditional simulation
+    {
+        using T = Tree<int, int, double>;
+        auto t = T::binary_node(0, T::branch(0.4, T::binary_node(0, T::branch(0.8, T::leaf(0)), T::branch(1.2, T::leaf(1)))),
+                                T::branch(0.1, T::binary_node(0, T::branch(0.6, T::leaf(2)), T::branch(0.3, T::leaf(3)))));
+        std::vector<const int*> leaf_payloads;
+        std::vector<const double*> branch_payloads;
+        const FlatTree f = flatten(*t, leaf_payloads, branch_payloads);
+        const int64_t nsites = 9;
+        std::vector<uint8_t> tips(4 * nsites), packed(4 * 3, 0);
+        for (int r = 0; r < 4; r++)
+            for (int64_t s = 0; s < nsites; s++) {
+                tips[r * nsites + s] = (uint8_t)((r * 7 + s * 3) & 3);
+                packed[r * 3 + s / 4] |= (uint8_t)(tips[r * nsites + s] << (2 * (s & 3)));
+            }
+        const auto red = SEM::K80::rate_matrix_reduction(2.0);
+        Vec bl((size_t)f.nnodes(), 0.0);
+        for (int v = 0; v < f.nnodes(); v++) bl[v] = branch_payloads[v] ? *branch_payloads[v] : 0.0;
+        double totals[3];
+        std::vector<uint8_t> states;
+        for (int k = 0; k < 3; k++) {
+            Context c(4, nsites, 4, 1, 0, k == 2 ? PB_FLAG_KEEP_CLV : 0);
+            c.set_tree(f, &bl);
+            c.set_eigensystem(red.p, red.diag, red.p_inv);
+            c.set_root_frequencies(Vec(4, 0.25));
+            if (k == 1) { c.set_option("fused_pow2", 0); c.set_tips_packed2(packed, 3); }
+            else c.set_tips(tips, nsites);
+            totals[k] = c.loglik();
+            if (k == 2) states = c.conditional_simulation(42);
+        }
+        expect_close("packed upload + 1/max factor == bytes + 2^-k factor", totals[1], totals[0], 1e-14);
+        expect_close("level kernels (kept CLVs) == site-resident kernel", totals[2], totals[0], 1e-14);
+        bool leaves_kept = true;
+        for (int v = 0; v < f.nnodes(); v++)
+            if (f.child_ptr[v] == f.child_ptr[v + 1])
+                for (int64_t s = 0; s < nsites; s++) leaves_kept &= states[v * nsites + s] == tips[f.tip_row[v] * nsites + s];
+        std::printf("%-58s %s\n", "conditional_simulation keeps the observed leaves", leaves_kept ? "ok" : "FAIL");
+        failures += !leaves_kept;
+    }
     std::printf(failures ? "%d FAILED\n" : "all ok\n", failures);
     return failures ? 1 : 0;
 }
