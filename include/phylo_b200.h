@@ -194,7 +194,9 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  * 4 states, site-resident kernel: "fused_block" (128|256|512 threads), "fused_spt" (1|2|4 sites per
  *   thread), "fused_exact_log" (1: add log(max v) at every rescaling like the reference's carry;
  *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
- *   matrices through the constant bank), "fused_const_cats" (categories per launch).
+ *   matrices through the constant bank), "fused_const_cats" (categories per launch), "fused_pow2" (1 (default):
+ *   exact power-of-two scale factors; 0: the reference's factor 1/max v), "fused_cherry" (tabulate the nodes
+ *   with two leaf children).
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,

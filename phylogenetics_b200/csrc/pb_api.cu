@@ -110,6 +110,12 @@ struct pb_ctx {
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
+    std::vector<FusedOp2> fprog_cherry;    // fprog_c with the leaf-leaf nodes turned into table look-ups (FOP_CHERRY)
+    std::vector<int> cherry_nodes;         // [ncherry][2]: tree nodes of the two leaves
+    DevBuf<FusedOp2> d_fprog_cherry;
+    DevBuf<int> d_cherry_nodes, d_cherry_k;
+    DevBuf<double> d_cherry_v;
+    int fused_cherry = 1;                  // option "fused_cherry": tabulate leaf-leaf nodes (power-of-two mode of fused4c)
     uint64_t fprog_version = 0;         // identifies the compiled program in the constant bank (launch_fused4c)
     int fused_pow2 = 1;                 // option "fused_pow2": power-of-two scale factors in the site-resident 4-state kernels
                                         // (exact and branch-free; 0 = the reference's factor 1/max)
@@ -537,6 +543,17 @@ int compile_tree(pb_ctx* c)
             if (usesA) o.offA = compact[o.offA / 16] * 16;
             if (usesB) o.offB = compact[o.offB / 16] * 16;
         }
+        // cherries: every TIP_TIP instruction becomes a look-up in a per-evaluation table of its 16 possible results
+        c->fprog_cherry = c->fprog_c;
+        c->cherry_nodes.clear();
+        for (FusedOp2& o : c->fprog_cherry) {
+            if ((o.code & 0xff) != pbk::FOP_TIP_TIP) continue;
+            c->cherry_nodes.push_back(c->leaf_nodes[o.offA / 16]);
+            c->cherry_nodes.push_back(c->leaf_nodes[o.offB / 16]);
+            o.code = (o.code & ~0xff) | pbk::FOP_CHERRY;
+            o.offA = (int)c->cherry_nodes.size() / 2 - 1;
+            o.offB = 0;
+        }
         // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
         c->fprog_d.clear();
         c->mlist.clear();
@@ -571,6 +588,10 @@ int compile_tree(pb_ctx* c)
     }
 
     // upload
+    PB_CUDA(c, c->d_fprog_cherry.ensure(std::max<size_t>(c->fprog_cherry.size(), 1)));
+    PB_CUDA(c, c->d_cherry_nodes.ensure(std::max<size_t>(c->cherry_nodes.size(), 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_cherry.p, c->fprog_cherry.data(), c->fprog_cherry.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_cherry_nodes.p, c->cherry_nodes.data(), c->cherry_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
     PB_CUDA(c, c->d_mlist.ensure(std::max<size_t>(c->mlist.size(), 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_d.p, c->fprog_d.data(), c->fprog_d.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
@@ -714,7 +735,8 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
         (int)c->leaf_nodes.size(), c->nnodes, cat0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
-        c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p);
+        c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, (int)c->cherry_nodes.size() / 2,
+        c->d_site_cat.p);
     c->launches++;
     return PB_OK;
 }
@@ -765,11 +787,21 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     // the program shares the bank: upload it unless this context's current program is already there
     static const pb_ctx* prog_owner[64] = {};
     static uint64_t prog_version[64] = {};
-    if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != c->fprog_version) {
-        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, c->d_fprog_c.p, c->fprog_c.size() * sizeof(FusedOp2), 0,
-                                           cudaMemcpyDeviceToDevice, c->stream));
+    const int ncherry = (int)c->cherry_nodes.size() / 2;
+    const bool cherry = c->fused_cherry && c->fused_pow2 && ncherry > 0;
+    const uint64_t want_version = c->fprog_version * 2 + (cherry ? 1 : 0);
+    if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != want_version) {
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, cherry ? c->d_fprog_cherry.p : c->d_fprog_c.p,
+                                           c->fprog_c.size() * sizeof(FusedOp2), 0, cudaMemcpyDeviceToDevice, c->stream));
         prog_owner[c->device & 63] = c;
-        prog_version[c->device & 63] = c->fprog_version;
+        prog_version[c->device & 63] = want_version;
+    }
+    if (cherry && regather) {
+        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * ncherry * 64));
+        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * ncherry * 16));
+        pbk::build_cherry_tables<<<dim3(ncherry, c->ncat), 32, 0, c->stream>>>(c->d_P.p, c->d_cherry_nodes.p, ncherry, c->nnodes,
+                                                                               c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
+        c->launches++;
     }
     for (int cat0 = cat_lo; cat0 < cat_hi; cat0 += per_launch) {
         const int k = std::min(per_launch, cat_hi - cat0);           // (the last launch may hold fewer)
@@ -1774,6 +1806,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const_cats = iv;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
+    } else if (k == "fused_cherry") {
+        c->fused_cherry = iv != 0;
     } else if (k == "fused_pow2") {
         c->fused_pow2 = iv != 0;
     } else if (k == "fused_exact_log") {

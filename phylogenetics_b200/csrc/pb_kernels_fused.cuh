@@ -34,6 +34,7 @@ struct FusedOp2 {          // 16 bytes: one uniform 128-bit shared-memory load p
 };
 constexpr int FOP_LOADW = 8;     // advance the packed-tip window by one 64-bit word
 constexpr int FOP_ACC_POP = 9;   // ACC = shiftmul(P[pA].ACC, P[pB].pop())   (both children inner)
+constexpr int FOP_CHERRY = 10;   // ACC = table[cherry offA][tip A, tip B]: the 16 possible rescaled products of a node with two leaf children
 
 // Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
 // 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
@@ -448,14 +449,40 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
     }
 }
 
+// A node whose two children are leaves (a "cherry", about a third of the internal nodes of a birth-death tree)
+// can only take 16 values per rate category: col(P_A, a) o col(P_B, b), rescaled.  They are tabulated once per
+// evaluation — same arithmetic, same power-of-two rescaling as the kernel's TIP_TIP instruction — so the
+// kernel replaces two column look-ups, four multiplications and a rescaling by one 32-byte look-up and an
+// integer add.  tabV[(c * ncherry + j) * 16 + a * 4 + b][4], tabK[...] = binary exponent taken out.
+__global__ void build_cherry_tables(const double* __restrict__ P, const int* __restrict__ cherry_nodes, int ncherry, int nnodes,
+                                    double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+{
+    const int c = blockIdx.y, j = blockIdx.x, idx = threadIdx.x;
+    if (idx >= 16) return;
+    const double* PA = P + ((size_t)c * nnodes + cherry_nodes[2 * j]) * 16;
+    const double* PB = P + ((size_t)c * nnodes + cherry_nodes[2 * j + 1]) * 16;
+    const int a = idx >> 2, b = idx & 3;
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = PA[i * 4 + a] * PB[i * 4 + b];
+    Scale<SCALE_POW2> sc;
+    sc.init();
+    shift4s(v, sc, thr);
+    const size_t e = ((size_t)c * ncherry + j) * 16 + idx;
+#pragma unroll
+    for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
+    tabK[e] = sc.e;
+}
+
 // prog: offsets of inner matrices index cPinner (compact inner index * 16); offsets of leaf matrices
 // index the shared-memory array of the ntips leaf matrices (compact leaf index * 16).
 template <int BLOCK, int SPT, int EXACT_LOG>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 && SPT <= 2) ? 3 : 1)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1))
 fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int ninner,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
+        const double* __restrict__ tabV, const int* __restrict__ tabK, int ncherry,
         double* __restrict__ site_cat)
 {
     extern __shared__ double sh[];
@@ -520,6 +547,18 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
                 }
                 shift_all<SPT, EXACT_LOG>(v, sc, thr);
+            } else if (code == FOP_CHERRY) {
+                if (EXACT_LOG == 2) {                        // (only the power-of-two mode tabulates its cherries)
+                    const double2* tv = reinterpret_cast<const double2*>(tabV) + ((size_t)c * ncherry + offA) * 32;
+                    const int* tk = tabK + ((size_t)c * ncherry + offA) * 16;
+#pragma unroll
+                    for (int q = 0; q < SPT; q++) {
+                        const int idx = (((int)(cur[q] >> shA) & 3) << 2) | ((int)(cur[q] >> shB) & 3);
+                        const double2 lo = __ldg(tv + idx * 2), hi = __ldg(tv + idx * 2 + 1);
+                        v[q][0] = lo.x; v[q][1] = lo.y; v[q][2] = hi.x; v[q][3] = hi.y;
+                        sc[q].e += __ldg(tk + idx);
+                    }
+                }
             } else if (code == FOP_TIP_TIP) {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {

@@ -17,6 +17,7 @@ case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
 res = {}
 CATS = int(os.environ.get("CATS", "0"))
+CHERRY = int(os.environ.get("CHERRY", "1"))
 for block, spt, pow2 in [(256, 2, 0), (256, 2, 1), (256, 1, 1), (128, 2, 1), (256, 4, 1)]:
     with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
         ctx.set_tree(f, case.bl)
@@ -27,6 +28,7 @@ for block, spt, pow2 in [(256, 2, 0), (256, 2, 1), (256, 1, 1), (128, 2, 1), (25
         ctx.set_option("fused_block", block)
         ctx.set_option("fused_spt", spt)
         ctx.set_option("fused_pow2", pow2)
+        ctx.set_option("fused_cherry", CHERRY)
         if CATS:
             ctx.set_option("fused_const_cats", CATS)
         ctx.set_timing(True)
