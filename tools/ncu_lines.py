@@ -12,7 +12,12 @@ min_s = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[1]; ix = {k: i for i, k in enumerate(h)}
-sass = [(r[ix["Source"]].strip(), int(r[ix["# Samples"]] or 0)) for r in rows[2:] if len(r) > ix["# Samples"]]
+body = rows[2:]
+for i, r in enumerate(body):                     # a report with several launches: the first one only
+    if r and r[0] == "Kernel Name":
+        body = body[:i]
+        break
+sass = [(r[ix["Source"]].strip(), int(r[ix["# Samples"]] or 0)) for r in body if len(r) > ix["# Samples"] and r[ix["# Samples"]].isdigit()]
 # listing: instructions of the kernel in order with current line
 lines = open(listing).read().splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l)
