@@ -7,6 +7,7 @@ type ctx
 type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.t
 type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
 type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
+type float_mat = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array2.t
 
 type flat_tree = { root : int ; child_ptr : int32_vec ; child_idx : int32_vec ; tip_row : int32_vec }
 
@@ -27,6 +28,12 @@ external set_rate_matrix_general : ctx -> Linear_algebra.mat -> unit = "pb_stub_
 external set_pmatrices : ctx -> float_vec -> unit = "pb_stub_set_pmatrices"
 external loglik_ : ctx -> float_vec -> float = "pb_stub_loglik"
 external conditional_simulation_ : ctx -> int64 -> tip_matrix -> unit = "pb_stub_conditional_simulation"
+external get_clv_ : ctx -> int -> int -> float_mat -> float_vec -> unit = "pb_stub_get_clv"
+external transition_matrices_eigen_ :
+  int -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> float_vec -> float_vec -> unit
+  = "pb_stub_transition_matrices_eigen_bytecode" "pb_stub_transition_matrices_eigen"
+external transition_matrices_expm_ : int -> Linear_algebra.mat -> float_vec -> float_vec -> unit
+  = "pb_stub_transition_matrices_expm"
 
 let keep_clv_flag = 1
 let mode_phylo_ctmc = 0
@@ -44,6 +51,37 @@ let conditional_simulation ctx rng ~nnodes ~nsites =
   let seed = Int64.of_int (Gsl.Rng.uniform_int rng (1 lsl 30)) in
   conditional_simulation_ ctx seed states ;
   states
+
+(* The shifted vectors (v, carry) of one node for every site (lib/phylo_ctmc.ml:26): v.{site, state}, carry.{site};
+   needs ~keep_clv:true and a prior [loglik]. *)
+let conditional_likelihood ctx ?(cat = 0) ~node ~nsites ~nstates () =
+  let v = Bigarray.(Array2.create float64 c_layout nsites nstates) in
+  let carry = Bigarray.(Array1.create float64 c_layout nsites) in
+  get_clv_ ctx node cat v carry ;
+  v, carry
+
+(* P(t) for many t in one launch; the k-th matrix is returned as a Lacaml matrix (column-major as it comes back). *)
+let unpack_matrices ~n ~count (out : float_vec) =
+  Array.init count ~f:(fun k ->
+      let m = Lacaml.D.Mat.create n n in
+      for j = 1 to n do for i = 1 to n do m.{i, j} <- out.{k * n * n + (j - 1) * n + (i - 1)} done done ;
+      m)
+
+let float_vec_of_array a = Bigarray.(Array1.of_array float64 c_layout a)
+
+(* Site_evolution_model.Make_diag(..).transition_probability_matrix (lib/site_evolution_model.ml:43-47) for every t *)
+let transition_matrices_eigen ?(device = 0) ~u ~lambda ~uinv ts =
+  let n = Lacaml.D.Vec.dim lambda and count = Array.length ts in
+  let out = Bigarray.(Array1.create float64 c_layout (count * n * n)) in
+  transition_matrices_eigen_ device u lambda uinv (float_vec_of_array ts) out ;
+  unpack_matrices ~n ~count out
+
+(* Matrix.expm (t * q) for every t (lib/linear_algebra.ml:308-404; lib/rate_matrix.ml:132-138) *)
+let transition_matrices_expm ?(device = 0) q ts =
+  let n = Lacaml.D.Mat.dim1 q and count = Array.length ts in
+  let out = Bigarray.(Array1.create float64 c_layout (count * n * n)) in
+  transition_matrices_expm_ device q (float_vec_of_array ts) out ;
+  unpack_matrices ~n ~count out
 
 let empty_vec = Bigarray.(Array1.create float64 c_layout 0)
 let loglik ctx ?(per_site = empty_vec) () = loglik_ ctx per_site

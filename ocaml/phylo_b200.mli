@@ -12,6 +12,7 @@ type ctx
 type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.t
 type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
 type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
+type float_mat = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array2.t
 
 type flat_tree = {
   root : int ;
@@ -63,6 +64,10 @@ end
 val set_tree : ctx -> flat_tree -> branch_lengths:float_vec -> unit
 val set_branch_lengths : ctx -> float_vec -> unit
 val set_tips : ctx -> tip_matrix -> unit
+val set_tips_packed2 : ctx -> tip_matrix -> unit
+(** Nucleotides 2-bit packed, [ntaxa] x [ceil(nsites/4)]: site [4b+j] in bits [2j..2j+1] of byte [b]. *)
+val set_mode : ctx -> int -> unit
+val set_rescaling : ctx -> float -> bool -> unit
 val set_root_frequencies : ctx -> Linear_algebra.vec -> unit
 val set_categories : ctx -> rates:float_vec -> weights:float_vec -> unit
 val set_eigensystem : ctx -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
@@ -74,3 +79,18 @@ val loglik : ctx -> ?per_site:float_vec -> unit -> float
 (** [Phylo_ctmc.conditional_simulation] for every site at once ([pb_conditional_simulation]):
     [states.{node, site}] after a [loglik] on a context created with [~keep_clv:true]. *)
 val conditional_simulation : ctx -> Gsl.Rng.t -> nnodes:int -> nsites:int -> tip_matrix
+
+(** The shifted vectors of [Phylo_ctmc.conditional_likelihoods] (lib/phylo_ctmc.mli:68-73) at one node, for every
+    site: [(v, carry)] with [v.{site, state}]; context created with [~keep_clv:true], after a [loglik]. *)
+val conditional_likelihood :
+  ctx -> ?cat:int -> node:int -> nsites:int -> nstates:int -> unit -> float_mat * float_vec
+
+(** {2 Stand-alone P(t) producers} *)
+
+val transition_matrices_eigen :
+  ?device:int -> u:Linear_algebra.mat -> lambda:Linear_algebra.vec -> uinv:Linear_algebra.mat -> float array ->
+  Linear_algebra.mat array
+(** [Site_evolution_model.Make_diag(..).transition_probability_matrix] for many branch lengths in one launch. *)
+
+val transition_matrices_expm : ?device:int -> Linear_algebra.mat -> float array -> Linear_algebra.mat array
+(** [Matrix.expm (Matrix.scal_mul t q)] for many [t] in one launch ([Rate_matrix.transition_probability_matrix]). *)

@@ -2,8 +2,11 @@
  * OCaml C stubs over include/phylo_b200.h — the reference-side binding a maintainer of
  * biocaml/phylogenetics would add (lib/dune: foreign_stubs + c_library_flags -lphylo_b200).
  *
- * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no OCaml toolchain (no caml/*.h).
- * The C ABI underneath is exercised from Python ctypes instead (tests/).  See INTEGRATION.md.
+ * The build image has no OCaml toolchain (no caml headers), so this file is never built against the real
+ * OCaml runtime here.  It IS compiled (-Wall -Wextra -Werror) against a mock of the runtime's C interface
+ * (tests/ocaml_mock/caml/) and executed on the GPU by tests/ocaml_mock/stubs_driver.c, which replays the call
+ * sequences of ocaml/phylo_b200.ml with Bigarray descriptors built in C (tests/test_ocaml_stubs.py).  See
+ * INTEGRATION.md.
  *
  * Buffers: Linear_algebra.mat / vec are Lacaml.D.mat / vec = float64 Bigarrays in Fortran layout
  * (lib/linear_algebra.ml:151-152); Caml_ba_data_val gives the column-major double* the ABI takes

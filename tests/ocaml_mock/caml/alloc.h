@@ -1,0 +1,7 @@
+/* MOCK of <caml/alloc.h> (see mlvalues.h). */
+#ifndef MOCK_CAML_ALLOC_H
+#define MOCK_CAML_ALLOC_H
+#include "mlvalues.h"
+CAMLextern value caml_copy_double(double d);
+CAMLextern value caml_copy_int64(int64_t i);
+#endif

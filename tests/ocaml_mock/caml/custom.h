@@ -1,0 +1,31 @@
+/* MOCK of <caml/custom.h> (see mlvalues.h): struct custom_operations with the eight fields of OCaml >= 4.08. */
+#ifndef MOCK_CAML_CUSTOM_H
+#define MOCK_CAML_CUSTOM_H
+#include <stddef.h>
+#include "mlvalues.h"
+
+struct custom_fixed_length;
+struct custom_operations {
+    const char *identifier;
+    void (*finalize)(value v);
+    int (*compare)(value v1, value v2);
+    intnat (*hash)(value v);
+    void (*serialize)(value v, uintnat *bsize_32, uintnat *bsize_64);
+    uintnat (*deserialize)(void *dst);
+    int (*compare_ext)(value v1, value v2);
+    const struct custom_fixed_length *fixed_length;
+};
+#define custom_finalize_default NULL
+#define custom_compare_default NULL
+#define custom_hash_default NULL
+#define custom_serialize_default NULL
+#define custom_deserialize_default NULL
+#define custom_compare_ext_default NULL
+#define custom_fixed_length_default NULL
+
+/* a custom block here: { ops, payload... } */
+struct caml_mock_custom { struct custom_operations *ops; char data[]; };
+#define Custom_ops_val(v) (((struct caml_mock_custom *)(v))->ops)
+#define Data_custom_val(v) ((void *)((struct caml_mock_custom *)(v))->data)
+CAMLextern value caml_alloc_custom(struct custom_operations *ops, uintnat size, uintnat mem, uintnat max);
+#endif
