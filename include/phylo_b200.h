@@ -164,7 +164,8 @@ int pb_loglik(pb_ctx *ctx, double *total, double *per_site);
  * behaves like pb_loglik.  `states` should be pinned memory for the copies to be asynchronous.
  * The states stay resident afterwards, as after pb_set_tips. */
 int pb_loglik_host(pb_ctx *ctx, const uint8_t *states, int64_t ld, double *total, double *per_site);
-/* The same from a 2-bit packed host alignment (see pb_set_tips_packed2). */
+/* The same from a 2-bit packed host alignment (see pb_set_tips_packed2).  The alignment stays resident 2-bit
+ * packed; the byte-per-site matrix other entry points read is expanded on the device when one of them needs it. */
 int pb_loglik_host_packed2(pb_ctx *ctx, const uint8_t *packed, int64_t ld, double *total, double *per_site);
 /* Non-blocking half: enqueue P(t) + pruning + root reduction on the stream. */
 int pb_loglik_enqueue(pb_ctx *ctx);
@@ -203,7 +204,9 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_slots" (cap on the matrix ring),
  *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
  *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
- * "host_chunks": column chunks of pb_loglik_host.  Unknown names are PB_ERR_INVALID_ARG. */
+ * "host_chunks": column chunks of pb_loglik_host; "host_lead_cats": rate categories pruned chunk by chunk
+ *   behind a 2-bit packed copy (the others run once over all the sites); "fused_const_group" (1 (default): the
+ *   constant bank is loaded for as many categories as it holds).  Unknown names are PB_ERR_INVALID_ARG. */
 int pb_set_option(pb_ctx *ctx, const char *name, double value);
 
 /* Device timing of the phases of an evaluation, measured with CUDA events on the

@@ -1,5 +1,5 @@
 (* OCaml side of the drop-in: evaluates the reference's closures eagerly, flattens the tree and
-   calls the C stubs (phylo_b200_stubs.c).  Source-only here: see INTEGRATION.md. *)
+   calls the C stubs (phylo_b200_stubs.c).  Not compiled here (no OCaml toolchain); the stubs are tested against a mock runtime: see INTEGRATION.md. *)
 open Core
 open Phylogenetics
 

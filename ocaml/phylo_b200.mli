@@ -1,6 +1,7 @@
 (** GPU (B200) evaluation of the phylogenetic likelihood behind the reference's signatures.
 
-    Source-only in this repository (no OCaml toolchain in the build image): see INTEGRATION.md.
+    Not compiled in this repository (no OCaml toolchain in the build image); the C stubs underneath are
+    tested against a mock of the runtime: see INTEGRATION.md.
     [Phylo_ctmc.pruning] and [Felsenstein.Make(..).felsenstein] keep their types; the batched
     entry points are new and are what a caller with many sites should use. *)
 

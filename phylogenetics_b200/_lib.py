@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphylo_b200.so")
+# PHYLO_B200_LIB names another build of the same library (A/B measurements of a kernel variant, tools/ab_lib.py).
+LIB_PATH = os.environ.get("PHYLO_B200_LIB") or os.path.join(_HERE, "libphylo_b200.so")
 
 PB_OK = 0
 PB_ERR_INVALID_ARG = -1

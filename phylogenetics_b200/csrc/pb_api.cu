@@ -178,8 +178,11 @@ struct pb_ctx {
 
     // pipelined host evaluation (pb_loglik_host)
     cudaStream_t copy_stream = nullptr;
+    bool tip_bytes_stale = false;       // the alignment is resident 2-bit packed (d_tips2); d_tips is expanded on demand
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
+    int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
+    int host_lead_cats = 1;             // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
     int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)
 
     // optional per-phase device timing (pb_set_timing)
@@ -721,7 +724,7 @@ bool fused4c_shape(const pb_ctx* c, int* block, int* spt)
 }
 
 template <int BLOCK, int SPT, int SCALING>
-int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_t site1)
+int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
 {
     auto kern = pbk::fused4c<BLOCK, SPT, SCALING>;
     const size_t smem = fused4c_smem_for(c, BLOCK, SPT);
@@ -734,7 +737,7 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
-        (int)c->leaf_nodes.size(), c->nnodes, cat0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
+        (int)c->leaf_nodes.size(), c->nnodes, cat0, slot0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
         c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, (int)c->cherry_nodes.size() / 2,
         c->d_site_cat.p);
     c->launches++;
@@ -742,16 +745,16 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int64_t site0, int64_
 }
 
 template <int SCALING>
-int launch_fused4c_shape(pb_ctx* c, int block, int spt, int cat0, int k, int64_t site0, int64_t site1)
+int launch_fused4c_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slot0, int64_t site0, int64_t site1)
 {
     switch (block * 10 + spt) {
-    case 2562: return launch_fused4c_variant<256, 2, SCALING>(c, cat0, k, site0, site1);
-    case 2564: return launch_fused4c_variant<256, 4, SCALING>(c, cat0, k, site0, site1);
-    case 1282: return launch_fused4c_variant<128, 2, SCALING>(c, cat0, k, site0, site1);
-    case 1284: return launch_fused4c_variant<128, 4, SCALING>(c, cat0, k, site0, site1);
-    case 5121: return launch_fused4c_variant<512, 1, SCALING>(c, cat0, k, site0, site1);
-    case 5122: return launch_fused4c_variant<512, 2, SCALING>(c, cat0, k, site0, site1);
-    default: return launch_fused4c_variant<256, 1, SCALING>(c, cat0, k, site0, site1);
+    case 2562: return launch_fused4c_variant<256, 2, SCALING>(c, cat0, k, slot0, site0, site1);
+    case 2564: return launch_fused4c_variant<256, 4, SCALING>(c, cat0, k, slot0, site0, site1);
+    case 1282: return launch_fused4c_variant<128, 2, SCALING>(c, cat0, k, slot0, site0, site1);
+    case 1284: return launch_fused4c_variant<128, 4, SCALING>(c, cat0, k, slot0, site0, site1);
+    case 5121: return launch_fused4c_variant<512, 1, SCALING>(c, cat0, k, slot0, site0, site1);
+    case 5122: return launch_fused4c_variant<512, 2, SCALING>(c, cat0, k, slot0, site0, site1);
+    default: return launch_fused4c_variant<256, 1, SCALING>(c, cat0, k, slot0, site0, site1);
     }
 }
 
@@ -803,14 +806,20 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
                                                                                c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
         c->launches++;
     }
-    for (int cat0 = cat_lo; cat0 < cat_hi; cat0 += per_launch) {
-        const int k = std::min(per_launch, cat_hi - cat0);           // (the last launch may hold fewer)
-        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)cat0 * ninner * 16,
-                                           (size_t)k * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
+    // The bank is loaded for as many categories as it holds (3 x 126 matrices at 128 taxa) and the launches of
+    // those categories follow each other without a copy in between.
+    const int per_load = c->fused_const_group ? std::max(per_launch, pbk::FUSED_CONST_MATS / std::max(ninner, 1)) : per_launch;
+    for (int g0 = cat_lo; g0 < cat_hi; g0 += per_load) {
+        const int gk = std::min(per_load, cat_hi - g0);
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)g0 * ninner * 16,
+                                           (size_t)gk * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
                                            c->stream));
-        const int rc = c->fused_pow2 ? launch_fused4c_shape<pbk::SCALE_POW2>(c, fb, fq, cat0, k, site0, site1)
-                                     : launch_fused4c_shape<pbk::SCALE_PRODUCT>(c, fb, fq, cat0, k, site0, site1);
-        if (rc != PB_OK) return rc;
+        for (int cat0 = g0; cat0 < g0 + gk; cat0 += per_launch) {
+            const int k = std::min(per_launch, g0 + gk - cat0);       // (the last launch may hold fewer)
+            const int rc = c->fused_pow2 ? launch_fused4c_shape<pbk::SCALE_POW2>(c, fb, fq, cat0, k, cat0 - g0, site0, site1)
+                                         : launch_fused4c_shape<pbk::SCALE_PRODUCT>(c, fb, fq, cat0, k, cat0 - g0, site0, site1);
+            if (rc != PB_OK) return rc;
+        }
     }
     PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
     return PB_OK;
@@ -919,11 +928,29 @@ int launch_fused_dmma_path(pb_ctx* c)
     return PB_OK;
 }
 
+// After pb_loglik_host_packed2 the alignment is resident 2-bit packed only; whoever reads the byte-per-site
+// matrix expands it first (once).
+int ensure_tip_bytes(pb_ctx* c)
+{
+    if (!c->tip_bytes_stale) return PB_OK;
+    const int64_t nbytes = (c->nsites + 3) / 4;
+    pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
+        c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, 0, nbytes);
+    c->launches++;
+    PB_CUDA(c, cudaGetLastError());
+    c->tip_bytes_stale = false;
+    return PB_OK;
+}
+
 int run_pruning(pb_ctx* c)
 {
     const int n = c->n;
     const int path = path_of(c);
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    if (path != PATH_FUSED4 || c->pack_dirty) {
+        const int rc = ensure_tip_bytes(c);
+        if (rc != PB_OK) return rc;
+    }
     if (path == PATH_FUSED4) {
         if (c->pack_dirty) {
             PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
@@ -1300,6 +1327,15 @@ static int alloc_tips(pb_ctx* c)
     return PB_OK;
 }
 
+static int alloc_tips2(pb_ctx* c)          // 2-bit upload buffer; padding columns read as state 0
+{
+    const size_t bytes = (size_t)c->ntaxa * (c->spad / 4);
+    const bool fresh = c->d_tips2.count < bytes || !c->d_tips2.p;
+    PB_CUDA(c, c->d_tips2.ensure(bytes));
+    if (fresh) PB_CUDA(c, cudaMemsetAsync(c->d_tips2.p, 0, bytes, c->stream));
+    return PB_OK;
+}
+
 int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
 {
     PB_ENTER(c);
@@ -1310,6 +1346,7 @@ int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_tips = true;
     c->have_masks = false;
+    c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
@@ -1326,6 +1363,7 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_tips = true;
     c->have_masks = false;
+    c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
@@ -1340,7 +1378,7 @@ int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
     if (!packed || ld < nbytes) return fail(c, PB_ERR_INVALID_ARG, "packed tips: null pointer or ld < ceil(nsites / 4)");
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
-    PB_CUDA(c, c->d_tips2.ensure((size_t)c->ntaxa * (c->spad / 4)));
+    if ((rc = alloc_tips2(c)) != PB_OK) return rc;
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips2.p, c->spad / 4, packed, ld, nbytes, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
     pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
         c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, 0, nbytes);
@@ -1349,6 +1387,7 @@ int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     c->have_tips = true;
     c->have_masks = false;
+    c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
@@ -1414,6 +1453,7 @@ int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
     }
     c->have_tips = true;
     c->have_masks = false;
+    c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = true;
     c->all_dirty = true;
@@ -1589,7 +1629,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     // chunk is packed, pruned and root-reduced on the compute stream.
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
-    if (packed2) PB_CUDA(c, c->d_tips2.ensure((size_t)c->ntaxa * (c->spad / 4)));
+    if (packed2 && (rc = alloc_tips2(c)) != PB_OK) return rc;
     if (!c->copy_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->ev_start) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     while ((int)c->chunk_events.size() < c->host_chunks) {
@@ -1610,9 +1650,12 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
     PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
     const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
-    // A 2-bit packed alignment crosses PCIe faster than one category is pruned: only the first category is
-    // pruned chunk by chunk behind the copy, the others run once over all the sites at full efficiency.
+    // 2-bit packed: only the first `host_lead_cats` categories (default 1) are pruned chunk by chunk behind the
+    // copy, the others run once over all the sites.  A launch costs one round of the persistent blocks (~0.09 ms)
+    // however few tiles it has, so more chunked launches lose more than the overlap wins
+    // (profiles/r01m_sweep_e2e_chunks_x_lead_cats.jsonl).
     const bool first_cat_only = packed2 && c->ncat > 1 && fused_const_ok(c);
+    const int lead_cats = std::max(1, std::min(c->host_lead_cats, c->ncat));
     int k = 0;
     for (int64_t s0 = 0; s0 < c->spad; s0 += chunk, k++) {
         const int64_t s1 = std::min(s0 + chunk, c->spad);
@@ -1625,18 +1668,22 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
                                          cudaMemcpyHostToDevice, c->copy_stream));
         PB_CUDA(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
         PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
-        if (w > 0 && packed2) {
-            const int64_t nb = (w + 3) / 4;
-            pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nb + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
-                c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, s0 / 4, s0 / 4 + nb);
+        if (packed2) {
+            // The program-order words come straight from the 2-bit upload.  The byte-per-site matrix that other
+            // consumers read (level kernels, pb_get_clv, a re-pack after pb_set_tree) is expanded when one of them
+            // asks for it (ensure_tip_bytes): an evaluation loop over host alignments never pays for it.
+            pbk::pack_tips4_from2<<<(unsigned)(((s1 - s0) / 4 + 255) / 256), 256, 0, c->stream>>>(
+                c->d_tips2.p, c->spad / 4, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad,
+                s0 / 4, s1 / 4);
+            c->launches++;
+        } else {
+            pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
+                c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad, s0, s1,
+                c->d_bad.p);
             c->launches++;
         }
-        pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
-            c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad, s0, s1,
-            c->d_bad.p);
-        c->launches++;
         if (first_cat_only) {                                // the other categories follow once, over all the sites
-            if ((rc = launch_fused4c(c, s0, s1, s0 == 0, 0, 1)) != PB_OK) return rc;
+            if ((rc = launch_fused4c(c, s0, s1, s0 == 0, 0, lead_cats)) != PB_OK) return rc;
             continue;
         }
         if ((rc = launch_fused4(c, s0, s1)) != PB_OK) return rc;
@@ -1649,7 +1696,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         }
     }
     if (first_cat_only) {
-        if (c->ncat > 1 && (rc = launch_fused4c(c, 0, c->spad, false, 1, c->ncat)) != PB_OK) return rc;
+        if (c->ncat > lead_cats && (rc = launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
         pbk::root_combine<<<(unsigned)nblocks, 256, 0, c->stream>>>(
             c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
             c->spad, 0, c->d_per_site.p, c->d_partials.p);
@@ -1668,6 +1715,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     c->tips_checked = true;
     c->all_dirty = true;
     c->evaluated = true;
+    c->tip_bytes_stale = packed2;
     return pb_loglik_fetch(c, total, per_site);
 }
 
@@ -1705,6 +1753,10 @@ int pb_get_clv(pb_ctx* c, int node, int cat, double* v, double* carry)
     if (node < 0 || node >= c->nnodes || cat < 0 || cat >= c->ncat || !v || !carry)
         return fail(c, PB_ERR_INVALID_ARG, "pb_get_clv: bad node/category/pointer");
     const int n = c->n;
+    if (c->child_ptr[node] == c->child_ptr[node + 1] && !c->have_masks) {      // a leaf's row of the byte-per-site matrix
+        const int rc = ensure_tip_bytes(c);
+        if (rc != PB_OK) return rc;
+    }
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->child_ptr[node] == c->child_ptr[node + 1] && c->have_masks) {   // leaf: set indicator, carry 0 (NaN if missing)
         std::vector<uint64_t> row(c->nsites);
@@ -1754,6 +1806,10 @@ int pb_conditional_simulation(pb_ctx* c, uint64_t seed, uint8_t* states, int64_t
         const bool leaf = c->child_ptr[v] == c->child_ptr[v + 1];
         pre.push_back({v, c->parent[v], leaf ? -1 : c->slot_of_node[v], leaf ? c->tip_row[v] : -1});
         for (int k = c->child_ptr[v + 1] - 1; k >= c->child_ptr[v]; k--) stack.push_back(c->child_idx[k]);
+    }
+    if (!c->have_masks) {
+        const int rc = ensure_tip_bytes(c);
+        if (rc != PB_OK) return rc;
     }
     PB_CUDA(c, c->d_sim_nodes.ensure(pre.size()));
     PB_CUDA(c, c->d_states.ensure((size_t)c->nnodes * c->spad));
@@ -1843,6 +1899,11 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "dmma_group_tiles") {
         if (iv < 8 || iv > 1024 || iv % 8) return fail(c, PB_ERR_INVALID_ARG, "dmma_group_tiles must be a multiple of 8 in 8..1024");
         c->dmma_seq_tiles = iv;
+    } else if (k == "fused_const_group") {
+        c->fused_const_group = iv != 0;
+    } else if (k == "host_lead_cats") {
+        if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "host_lead_cats must be in 1..64");
+        c->host_lead_cats = iv;
     } else if (k == "host_chunks") {
         if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "host_chunks must be in 1..64");
         c->host_chunks = iv;

@@ -78,6 +78,36 @@ expand_tips2(const uint8_t* __restrict__ in, int64_t ld_in, uint8_t* __restrict_
     }
 }
 
+// The two steps above in one, for the pipelined host evaluation (pb_loglik_host_packed2): 2-bit codes in the
+// HOST layout (in[row][byte], 4 sites per byte) -> 2-bit codes in PROGRAM order (packed[word][site], 32 tips per
+// word).  One thread per byte column = 4 sites: per 32 tips it gathers one byte per tip (32 consecutive bytes per
+// warp and row) and writes its sites' four words as two 16-byte stores.  Moves ntaxa/4 bytes in and
+// ntaxa/4 (rounded up to whole words) bytes out per site, against 1.25 + 1.4 bytes per tip for expand + pack.
+__global__ void __launch_bounds__(256)
+pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __restrict__ order, int ntips, int nwords,
+                 uint64_t* __restrict__ packed, int64_t spad, int64_t byte0, int64_t byte1)
+{
+    const int64_t b = byte0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // byte columns [byte0, byte1)
+    if (b >= byte1) return;
+    for (int w = 0; w < nwords; w++) {
+        uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 16
+        for (int j = 0; j < 32; j++) {
+            const int k = w * 32 + j;
+            if (k < ntips) {
+                const uint64_t v = in[(int64_t)order[k] * ld_in + b];
+                w0 |= (v & 3u) << (2 * j);
+                w1 |= ((v >> 2) & 3u) << (2 * j);
+                w2 |= ((v >> 4) & 3u) << (2 * j);
+                w3 |= (v >> 6) << (2 * j);
+            }
+        }
+        ulonglong2* out = reinterpret_cast<ulonglong2*>(packed + (int64_t)w * spad + 4 * b);   // 32-byte aligned
+        out[0] = make_ulonglong2(w0, w1);
+        out[1] = make_ulonglong2(w2, w3);
+    }
+}
+
 // Flags tip states >= nstates (the level kernels index P with them).
 __global__ void __launch_bounds__(256)
 validate_tips(const uint8_t* __restrict__ tips, int64_t total, int nstates, int* __restrict__ bad_flag)
@@ -479,7 +509,7 @@ __global__ void build_cherry_tables(const double* __restrict__ P, const int* __r
 template <int BLOCK, int SPT, int EXACT_LOG>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1))
 fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
-        const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int ninner,
+        const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int slot0, int ninner,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
         const double* __restrict__ tabV, const int* __restrict__ tabK, int ncherry,
@@ -489,7 +519,7 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
     double* shP = sh;                                       // [nleaf][16], transposed, of this category
     double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
     const int c = cat0 + blockIdx.y, tid = threadIdx.x;     // this launch covers categories cat0 .. cat0 + gridDim.y - 1
-    const int cbase = blockIdx.y * ninner * 16;             // where this category's inner matrices sit in cPinner
+    const int cbase = (slot0 + blockIdx.y) * ninner * 16;   // where this category's inner matrices sit in cPinner
     {
         const double* Pg = P + (size_t)c * nnodes * 16;
         for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
@@ -503,6 +533,8 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
 #pragma unroll
     for (int i = 0; i < 4; i++) pir[i] = pi[i];
 
+    // (Dealing WARP tiles of 32 * SPT sites round-robin over blocks and warps, so that a short last round spreads
+    // over every SM, was measured slower: 1.34 against 1.22 ms at c2, profiles/r01m_ab_fused4c_variants.jsonl.)
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t s0 = (tile0 + tile) * (BLOCK * SPT) + tid;
         double v[SPT][4];
@@ -520,7 +552,8 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         pk += 2 * spad;
         double* st = shS + tid;
         for (int ip = 0; ip < nops; ip++) {
-            const int4 opw = cProg[ip];                      // uniform fetch
+            const int4 opw = cProg[ip];                      // uniform fetch (fetching one instruction ahead was
+                                                             // measured slower: 1.46 against 1.23 ms at c2)
             const int offA = opw.y, offB = opw.z;
             const int shA = opw.w & 0xff, shB = opw.w >> 8;
             const int code = opw.x & 0xff;

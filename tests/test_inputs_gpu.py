@@ -99,6 +99,9 @@ def test_two_bit_packed_host_alignment(nsites, chunks):
             assert abs(total3 - total) <= 1e-12 * abs(total)
             total4 = ctx.loglik()                        # the expanded matrix stays resident
             assert abs(total4 - total) <= 1e-12 * abs(total)
+            ctx.set_tree(case.flat, case.bl)             # ... also the byte-per-site copy expanded on the side stream:
+            total5, per_site5 = ctx.loglik(per_site=True)    # a new tree re-packs the tips from it
+            assert total5 == total and np.array_equal(per_site5, per_site)
     with LikelihoodContext(20, 10, 5) as ctx:            # 4 states only
         with pytest.raises(_lib.PhyloB200Error):
             ctx.set_tips_packed2(np.zeros((5, 3), np.uint8))
