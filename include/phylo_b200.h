@@ -197,7 +197,7 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
  *   matrices through the constant bank), "fused_const_cats" (categories per launch), "fused_pow2" (1 (default):
  *   exact power-of-two scale factors; 0: the reference's factor 1/max v), "fused_cherry" (tabulate the nodes
- *   with two leaf children).
+ *   with two leaf children), "fused_triple" (and the parents of such a node and a leaf).
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,

@@ -112,8 +112,12 @@ struct pb_ctx {
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
     std::vector<FusedOp2> fprog_cherry;    // fprog_c with the leaf-leaf nodes turned into table look-ups (FOP_CHERRY)
     std::vector<int> cherry_nodes;         // [ncherry][2]: tree nodes of the two leaves
-    DevBuf<FusedOp2> d_fprog_cherry;
-    DevBuf<int> d_cherry_nodes, d_cherry_k;
+    std::vector<FusedOp2> fprog_triple;    // fprog_cherry with (cherry ; APPLY_MUL_TIP) pairs merged into one look-up
+    std::vector<int> triple_nodes;         // [ntriple][4]: leaf A, leaf B, the cherry's node, leaf C
+    int fprog_bank_nops = 0;               // length of the program variant launch_fused4c put in the constant bank
+    int fused_triple = 1;                  // option "fused_triple": tabulate the parents of a cherry and a leaf as well
+    DevBuf<FusedOp2> d_fprog_cherry, d_fprog_triple;
+    DevBuf<int> d_cherry_nodes, d_triple_nodes, d_cherry_k;
     DevBuf<double> d_cherry_v;
     int fused_cherry = 1;                  // option "fused_cherry": tabulate leaf-leaf nodes (power-of-two mode of fused4c)
     uint64_t fprog_version = 0;         // identifies the compiled program in the constant bank (launch_fused4c)
@@ -551,11 +555,42 @@ int compile_tree(pb_ctx* c)
         c->cherry_nodes.clear();
         for (FusedOp2& o : c->fprog_cherry) {
             if ((o.code & 0xff) != pbk::FOP_TIP_TIP) continue;
+            if ((o.sh >> 8) != (o.sh & 0xff) + 2) continue;         // (never: the two tips are consumed back to back)
             c->cherry_nodes.push_back(c->leaf_nodes[o.offA / 16]);
             c->cherry_nodes.push_back(c->leaf_nodes[o.offB / 16]);
             o.code = (o.code & ~0xff) | pbk::FOP_CHERRY;
-            o.offA = (int)c->cherry_nodes.size() / 2 - 1;
-            o.offB = 0;
+            o.offA = ((int)c->cherry_nodes.size() / 2 - 1) * 16;    // first table entry; index = (window >> shA) & 15
+            o.offB = 15;
+            o.sh &= 0xff;                                           // (tip B sits right above tip A in the window)
+        }
+        // clades of three leaves: a cherry's look-up directly followed by APPLY_MUL_TIP on the same window becomes
+        // one look-up among 64 values (the third tip sits right above the cherry's two)
+        c->fprog_triple.clear();
+        c->triple_nodes.clear();
+        {
+            const int ncherry = (int)c->cherry_nodes.size() / 2;
+            const std::vector<FusedOp2>& src = c->fprog_cherry;
+            for (size_t i = 0; i < src.size(); i++) {
+                const FusedOp2& o = src[i];
+                if (o.code == pbk::FOP_CHERRY && i + 1 < src.size() && (src[i + 1].code & 0xff) == pbk::FOP_APPLY_MUL_TIP &&
+                    (src[i + 1].sh >> 8) == o.sh + 4) {
+                    const FusedOp2& ap = src[i + 1];
+                    const int j = o.offA / 16;
+                    c->triple_nodes.push_back(c->cherry_nodes[2 * j]);
+                    c->triple_nodes.push_back(c->cherry_nodes[2 * j + 1]);
+                    c->triple_nodes.push_back(c->inner_nodes[ap.offA / 16]);
+                    c->triple_nodes.push_back(c->leaf_nodes[ap.offB / 16]);
+                    FusedOp2 t;
+                    t.code = (ap.code & ~0xff) | pbk::FOP_CHERRY;
+                    t.offA = ncherry * 16 + ((int)c->triple_nodes.size() / 4 - 1) * 64;
+                    t.offB = 63;
+                    t.sh = o.sh;
+                    c->fprog_triple.push_back(t);
+                    i++;
+                    continue;
+                }
+                c->fprog_triple.push_back(o);
+            }
         }
         // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
         c->fprog_d.clear();
@@ -595,6 +630,10 @@ int compile_tree(pb_ctx* c)
     PB_CUDA(c, c->d_cherry_nodes.ensure(std::max<size_t>(c->cherry_nodes.size(), 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_cherry.p, c->fprog_cherry.data(), c->fprog_cherry.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_cherry_nodes.p, c->cherry_nodes.data(), c->cherry_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, c->d_fprog_triple.ensure(std::max<size_t>(c->fprog_triple.size(), 1)));
+    PB_CUDA(c, c->d_triple_nodes.ensure(std::max<size_t>(c->triple_nodes.size(), 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_triple.p, c->fprog_triple.data(), c->fprog_triple.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_triple_nodes.p, c->triple_nodes.data(), c->triple_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
     PB_CUDA(c, c->d_mlist.ensure(std::max<size_t>(c->mlist.size(), 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_d.p, c->fprog_d.data(), c->fprog_d.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
@@ -736,9 +775,10 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
-        c->d_fprog_c.p, (int)c->fprog_c.size(), std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
+        c->d_fprog_c.p, c->fprog_bank_nops, std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
         (int)c->leaf_nodes.size(), c->nnodes, cat0, slot0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
-        c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, (int)c->cherry_nodes.size() / 2,
+        c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p,
+        (int)c->cherry_nodes.size() / 2 * 16 + (int)c->triple_nodes.size() / 4 * 64,
         c->d_site_cat.p);
     c->launches++;
     return PB_OK;
@@ -790,21 +830,30 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     // the program shares the bank: upload it unless this context's current program is already there
     static const pb_ctx* prog_owner[64] = {};
     static uint64_t prog_version[64] = {};
-    const int ncherry = (int)c->cherry_nodes.size() / 2;
+    const int ncherry = (int)c->cherry_nodes.size() / 2, ntriple = (int)c->triple_nodes.size() / 4;
     const bool cherry = c->fused_cherry && c->fused_pow2 && ncherry > 0;
-    const uint64_t want_version = c->fprog_version * 2 + (cherry ? 1 : 0);
+    const bool triple = cherry && c->fused_triple && ntriple > 0;
+    const int ntab = ncherry * 16 + ntriple * 64;                    // table entries per category
+    const uint64_t want_version = c->fprog_version * 4 + (cherry ? 1 : 0) + (triple ? 2 : 0);
+    const FusedOp2* prog = triple ? c->d_fprog_triple.p : cherry ? c->d_fprog_cherry.p : c->d_fprog_c.p;
+    c->fprog_bank_nops = (int)(triple ? c->fprog_triple.size() : c->fprog_c.size());
     if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != want_version) {
-        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, cherry ? c->d_fprog_cherry.p : c->d_fprog_c.p,
-                                           c->fprog_c.size() * sizeof(FusedOp2), 0, cudaMemcpyDeviceToDevice, c->stream));
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, prog, c->fprog_bank_nops * sizeof(FusedOp2), 0,
+                                           cudaMemcpyDeviceToDevice, c->stream));
         prog_owner[c->device & 63] = c;
         prog_version[c->device & 63] = want_version;
     }
     if (cherry && regather) {
-        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * ncherry * 64));
-        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * ncherry * 16));
+        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * ntab * 4));
+        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * ntab));
         pbk::build_cherry_tables<<<dim3(ncherry, c->ncat), 32, 0, c->stream>>>(c->d_P.p, c->d_cherry_nodes.p, ncherry, c->nnodes,
-                                                                               c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
+                                                                               ntab, c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
         c->launches++;
+        if (ntriple > 0) {                                           // (built even when the option is off: it may be switched on)
+            pbk::build_triple_tables<<<dim3(ntriple, c->ncat), 64, 0, c->stream>>>(
+                c->d_P.p, c->d_triple_nodes.p, ntriple, ncherry, c->nnodes, ntab, c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
+            c->launches++;
+        }
     }
     // The bank is loaded for as many categories as it holds (3 x 126 matrices at 128 taxa) and the launches of
     // those categories follow each other without a copy in between.
@@ -1862,6 +1911,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const_cats = iv;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
+    } else if (k == "fused_triple") {
+        c->fused_triple = iv != 0;
     } else if (k == "fused_cherry") {
         c->fused_cherry = iv != 0;
     } else if (k == "fused_pow2") {

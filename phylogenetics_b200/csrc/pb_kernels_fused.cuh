@@ -34,7 +34,8 @@ struct FusedOp2 {          // 16 bytes: one uniform 128-bit shared-memory load p
 };
 constexpr int FOP_LOADW = 8;     // advance the packed-tip window by one 64-bit word
 constexpr int FOP_ACC_POP = 9;   // ACC = shiftmul(P[pA].ACC, P[pB].pop())   (both children inner)
-constexpr int FOP_CHERRY = 10;   // ACC = table[cherry offA][tip A, tip B]: the 16 possible rescaled products of a node with two leaf children
+constexpr int FOP_CHERRY = 10;   // ACC = table[offA + ((window >> shA) & offB)]: the 16 possible values of a node with two leaf
+                                 // children, or the 64 of the parent of such a node and a leaf (see build_cherry_tables)
 
 // Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
 // 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
@@ -483,22 +484,59 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
 // can only take 16 values per rate category: col(P_A, a) o col(P_B, b), rescaled.  They are tabulated once per
 // evaluation — same arithmetic, same power-of-two rescaling as the kernel's TIP_TIP instruction — so the
 // kernel replaces two column look-ups, four multiplications and a rescaling by one 32-byte look-up and an
-// integer add.  tabV[(c * ncherry + j) * 16 + a * 4 + b][4], tabK[...] = binary exponent taken out.
+// integer add.  The parent of a cherry and a leaf (a clade of three leaves, a sixth of the internal nodes) can
+// only take 64 values: the same treatment replaces the cherry's look-up AND a whole APPLY_MUL_TIP instruction
+// (matrix-vector product, column look-up, product, rescaling).
+// One table per category, `ntab` entries of (4 doubles, 1 exponent): cherry j at entries [16 j, 16 j + 16),
+// index a + 4 b; triple t at [16 ncherry + 64 t, +64), index a + 4 b + 16 c — the order the three tips occupy in
+// the packed word, so the kernel's index is ONE shift and mask.
 __global__ void build_cherry_tables(const double* __restrict__ P, const int* __restrict__ cherry_nodes, int ncherry, int nnodes,
-                                    double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+                                    int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
 {
     const int c = blockIdx.y, j = blockIdx.x, idx = threadIdx.x;
     if (idx >= 16) return;
     const double* PA = P + ((size_t)c * nnodes + cherry_nodes[2 * j]) * 16;
     const double* PB = P + ((size_t)c * nnodes + cherry_nodes[2 * j + 1]) * 16;
-    const int a = idx >> 2, b = idx & 3;
+    const int a = idx & 3, b = idx >> 2;
     double v[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) v[i] = PA[i * 4 + a] * PB[i * 4 + b];
     Scale<SCALE_POW2> sc;
     sc.init();
     shift4s(v, sc, thr);
-    const size_t e = ((size_t)c * ncherry + j) * 16 + idx;
+    const size_t e = (size_t)c * ntab + j * 16 + idx;
+#pragma unroll
+    for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
+    tabK[e] = sc.e;
+}
+
+// triple_nodes[t] = {leaf A, leaf B, the cherry's node (its branch matrix is applied), leaf C}
+__global__ void build_triple_tables(const double* __restrict__ P, const int* __restrict__ triple_nodes, int ntriple, int ncherry,
+                                    int nnodes, int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+{
+    const int c = blockIdx.y, t = blockIdx.x, idx = threadIdx.x;
+    if (idx >= 64) return;
+    const double* PA = P + ((size_t)c * nnodes + triple_nodes[4 * t]) * 16;
+    const double* PB = P + ((size_t)c * nnodes + triple_nodes[4 * t + 1]) * 16;
+    const double* m = P + ((size_t)c * nnodes + triple_nodes[4 * t + 2]) * 16;
+    const double* PC = P + ((size_t)c * nnodes + triple_nodes[4 * t + 3]) * 16;
+    const int a = idx & 3, b = (idx >> 2) & 3, cc = idx >> 4;
+    double x[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[i] = PA[i * 4 + a] * PB[i * 4 + b];        // the cherry (FOP_TIP_TIP)
+    Scale<SCALE_POW2> sc;
+    sc.init();
+    shift4s(x, sc, thr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                             // FOP_APPLY_MUL_TIP, as matvec4c does it
+        double y = m[i * 4 + 0] * x[0];
+        y = fma(m[i * 4 + 1], x[1], y);
+        y = fma(m[i * 4 + 2], x[2], y);
+        y = fma(m[i * 4 + 3], x[3], y);
+        v[i] = y * PC[i * 4 + cc];
+    }
+    shift4s(v, sc, thr);
+    const size_t e = (size_t)c * ntab + ncherry * 16 + t * 64 + idx;
 #pragma unroll
     for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
     tabK[e] = sc.e;
@@ -512,7 +550,7 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes, int cat0, int slot0, int ninner,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
-        const double* __restrict__ tabV, const int* __restrict__ tabK, int ncherry,
+        const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab,
         double* __restrict__ site_cat)
 {
     extern __shared__ double sh[];
@@ -581,12 +619,12 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                 }
                 shift_all<SPT, EXACT_LOG>(v, sc, thr);
             } else if (code == FOP_CHERRY) {
-                if (EXACT_LOG == 2) {                        // (only the power-of-two mode tabulates its cherries)
-                    const double2* tv = reinterpret_cast<const double2*>(tabV) + ((size_t)c * ncherry + offA) * 32;
-                    const int* tk = tabK + ((size_t)c * ncherry + offA) * 16;
+                if (EXACT_LOG == 2) {                        // (only the power-of-two mode tabulates): offA = first entry, offB = index mask
+                    const double2* tv = reinterpret_cast<const double2*>(tabV) + ((size_t)c * ntab + offA) * 2;
+                    const int* tk = tabK + ((size_t)c * ntab + offA);
 #pragma unroll
                     for (int q = 0; q < SPT; q++) {
-                        const int idx = (((int)(cur[q] >> shA) & 3) << 2) | ((int)(cur[q] >> shB) & 3);
+                        const int idx = (int)(cur[q] >> shA) & offB;
                         const double2 lo = __ldg(tv + idx * 2), hi = __ldg(tv + idx * 2 + 1);
                         v[q][0] = lo.x; v[q][1] = lo.y; v[q][2] = hi.x; v[q][3] = hi.y;
                         sc[q].e += __ldg(tk + idx);

@@ -461,6 +461,9 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
         ctx.set_option("fused_const_cats", 2)               # two categories per launch share the constant bank
         total3, per_site3 = ctx.loglik(per_site=True)
         assert total3 == total and np.array_equal(per_site3, per_site)
+        ctx.set_option("fused_triple", 0)                   # clades of three leaves: cherry look-up + APPLY_MUL_TIP instead of one look-up
+        total5, per_site5 = ctx.loglik(per_site=True)
+        assert total5 == total and np.array_equal(per_site5, per_site)
         ctx.set_option("fused_cherry", 0)                   # leaf-leaf nodes computed in the kernel instead of tabulated
         total4, per_site4 = ctx.loglik(per_site=True)
         assert total4 == total and np.array_equal(per_site4, per_site)
