@@ -197,7 +197,9 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
  *   matrices through the constant bank), "fused_const_cats" (categories per launch), "fused_pow2" (1 (default):
  *   exact power-of-two scale factors; 0: the reference's factor 1/max v), "fused_cherry" (tabulate the nodes
- *   with two leaf children), "fused_triple" (and the parents of such a node and a leaf).
+ *   with two leaf children), "fused_clade_leaves" (2..6, default 5: the largest clade whose 4^k
+ *   possible values are tabulated the same way; fewer when the alignment has fewer than 8 * 4^k sites unless
+ *   "fused_clade_force"), "fused_triple" (0: cherries only).
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,

@@ -110,14 +110,18 @@ struct pb_ctx {
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
-    std::vector<FusedOp2> fprog_cherry;    // fprog_c with the leaf-leaf nodes turned into table look-ups (FOP_CHERRY)
-    std::vector<int> cherry_nodes;         // [ncherry][2]: tree nodes of the two leaves
-    std::vector<FusedOp2> fprog_triple;    // fprog_cherry with (cherry ; APPLY_MUL_TIP) pairs merged into one look-up
-    std::vector<int> triple_nodes;         // [ntriple][4]: leaf A, leaf B, the cherry's node, leaf C
+    std::vector<FusedOp2> fprog_tab;       // fprog_c with the small clades turned into table look-ups (FOP_CHERRY)
+    std::vector<pbk::CladeTab> clades;     // the tabulated clades of fprog_tab
+    bool tables_stale = true;              // the tables must be rebuilt before the next launch (new program variant)
+    int tab_leaves = -1;                   // the clade size limit fprog_tab was built for (-1: not built)
+    int ntab = 0;                          // table entries per category
     int fprog_bank_nops = 0;               // length of the program variant launch_fused4c put in the constant bank
-    int fused_triple = 1;                  // option "fused_triple": tabulate the parents of a cherry and a leaf as well
-    DevBuf<FusedOp2> d_fprog_cherry, d_fprog_triple;
-    DevBuf<int> d_cherry_nodes, d_triple_nodes, d_cherry_k;
+    int fused_triple = 1;                  // option "fused_triple": 0 = tabulate cherries only
+    int fused_clade_force = 0;             // option "fused_clade_force" (test hook): tabulate up to the limit however few the sites
+    int fused_clade_leaves = 5;            // option "fused_clade_leaves": largest tabulated clade (2..6 leaves)
+    DevBuf<FusedOp2> d_fprog_tab;
+    DevBuf<pbk::CladeTab> d_clades;
+    DevBuf<int> d_cherry_k;
     DevBuf<double> d_cherry_v;
     int fused_cherry = 1;                  // option "fused_cherry": tabulate leaf-leaf nodes (power-of-two mode of fused4c)
     uint64_t fprog_version = 0;         // identifies the compiled program in the constant bank (launch_fused4c)
@@ -550,48 +554,7 @@ int compile_tree(pb_ctx* c)
             if (usesA) o.offA = compact[o.offA / 16] * 16;
             if (usesB) o.offB = compact[o.offB / 16] * 16;
         }
-        // cherries: every TIP_TIP instruction becomes a look-up in a per-evaluation table of its 16 possible results
-        c->fprog_cherry = c->fprog_c;
-        c->cherry_nodes.clear();
-        for (FusedOp2& o : c->fprog_cherry) {
-            if ((o.code & 0xff) != pbk::FOP_TIP_TIP) continue;
-            if ((o.sh >> 8) != (o.sh & 0xff) + 2) continue;         // (never: the two tips are consumed back to back)
-            c->cherry_nodes.push_back(c->leaf_nodes[o.offA / 16]);
-            c->cherry_nodes.push_back(c->leaf_nodes[o.offB / 16]);
-            o.code = (o.code & ~0xff) | pbk::FOP_CHERRY;
-            o.offA = ((int)c->cherry_nodes.size() / 2 - 1) * 16;    // first table entry; index = (window >> shA) & 15
-            o.offB = 15;
-            o.sh &= 0xff;                                           // (tip B sits right above tip A in the window)
-        }
-        // clades of three leaves: a cherry's look-up directly followed by APPLY_MUL_TIP on the same window becomes
-        // one look-up among 64 values (the third tip sits right above the cherry's two)
-        c->fprog_triple.clear();
-        c->triple_nodes.clear();
-        {
-            const int ncherry = (int)c->cherry_nodes.size() / 2;
-            const std::vector<FusedOp2>& src = c->fprog_cherry;
-            for (size_t i = 0; i < src.size(); i++) {
-                const FusedOp2& o = src[i];
-                if (o.code == pbk::FOP_CHERRY && i + 1 < src.size() && (src[i + 1].code & 0xff) == pbk::FOP_APPLY_MUL_TIP &&
-                    (src[i + 1].sh >> 8) == o.sh + 4) {
-                    const FusedOp2& ap = src[i + 1];
-                    const int j = o.offA / 16;
-                    c->triple_nodes.push_back(c->cherry_nodes[2 * j]);
-                    c->triple_nodes.push_back(c->cherry_nodes[2 * j + 1]);
-                    c->triple_nodes.push_back(c->inner_nodes[ap.offA / 16]);
-                    c->triple_nodes.push_back(c->leaf_nodes[ap.offB / 16]);
-                    FusedOp2 t;
-                    t.code = (ap.code & ~0xff) | pbk::FOP_CHERRY;
-                    t.offA = ncherry * 16 + ((int)c->triple_nodes.size() / 4 - 1) * 64;
-                    t.offB = 63;
-                    t.sh = o.sh;
-                    c->fprog_triple.push_back(t);
-                    i++;
-                    continue;
-                }
-                c->fprog_triple.push_back(o);
-            }
-        }
+        c->tab_leaves = -1;                     // the tabulated variant is built on demand (build_table_program)
         // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
         c->fprog_d.clear();
         c->mlist.clear();
@@ -626,14 +589,6 @@ int compile_tree(pb_ctx* c)
     }
 
     // upload
-    PB_CUDA(c, c->d_fprog_cherry.ensure(std::max<size_t>(c->fprog_cherry.size(), 1)));
-    PB_CUDA(c, c->d_cherry_nodes.ensure(std::max<size_t>(c->cherry_nodes.size(), 1)));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_cherry.p, c->fprog_cherry.data(), c->fprog_cherry.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_cherry_nodes.p, c->cherry_nodes.data(), c->cherry_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, c->d_fprog_triple.ensure(std::max<size_t>(c->fprog_triple.size(), 1)));
-    PB_CUDA(c, c->d_triple_nodes.ensure(std::max<size_t>(c->triple_nodes.size(), 1)));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_triple.p, c->fprog_triple.data(), c->fprog_triple.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_triple_nodes.p, c->triple_nodes.data(), c->triple_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
     PB_CUDA(c, c->d_mlist.ensure(std::max<size_t>(c->mlist.size(), 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_d.p, c->fprog_d.data(), c->fprog_d.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
@@ -777,8 +732,7 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         c->d_fprog_c.p, c->fprog_bank_nops, std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
         (int)c->leaf_nodes.size(), c->nnodes, cat0, slot0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
-        c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p,
-        (int)c->cherry_nodes.size() / 2 * 16 + (int)c->triple_nodes.size() / 4 * 64,
+        c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->ntab,
         c->d_site_cat.p);
     c->launches++;
     return PB_OK;
@@ -806,6 +760,95 @@ bool fused_const_ok(const pb_ctx* c)
            (int)c->fprog_c.size() <= pbk::FUSED_CONST_OPS && fused4c_shape(c, &b, &q);
 }
 
+// Finds the clades of at most `max_leaves` leaves whose instructions can be replaced by one table look-up and
+// writes the program variant that does so (pbk::build_clade_tables explains the tables).  A clade qualifies when
+// its leaves are consumed back to back from ONE packed-tip word: the walk below keeps, for the accumulator and
+// every stack entry, the instruction range that produced it, how many tips it consumed and where the first one
+// sits in the window; a window load (FOP_LOADW) closes everything live for further merging.
+int build_table_program(pb_ctx* c, int max_leaves)
+{
+    struct Sym { int start, k, sh0; bool open; };
+    struct Cand { int start, end, k, sh0; };
+    const std::vector<FusedOp2>& prog = c->fprog_c;
+    std::vector<Cand> cands;
+    if (max_leaves >= 2) {
+        Sym acc{0, 0, 0, false};
+        std::vector<Sym> stack;
+        for (int i = 0; i < (int)prog.size(); i++) {
+            const FusedOp2& o = prog[i];
+            const int code = o.code & 0xff, shA = o.sh & 0xff, shB = o.sh >> 8;
+            bool produces = true;
+            if (code == pbk::FOP_LOADW) {
+                acc.open = false;
+                for (Sym& e : stack) e.open = false;
+                produces = false;
+            } else if (code == pbk::FOP_TIP_TIP) {
+                acc = {i, 2, shA, shB == shA + 2};
+            } else if (code == pbk::FOP_TIP) {
+                acc = {i, 1, shA, true};
+            } else if (code == pbk::FOP_MUL_TIP) {
+                acc.open = acc.open && shA == acc.sh0 + 2 * acc.k;
+                acc.k++;
+            } else if (code == pbk::FOP_APPLY_MUL_TIP) {
+                acc.open = acc.open && shB == acc.sh0 + 2 * acc.k;
+                acc.k++;
+            } else if (code == pbk::FOP_ACC_POP || code == pbk::FOP_POP_MUL) {
+                if (stack.empty()) return fail(c, PB_ERR_STATE, "fused program: stack underflow");
+                const Sym x = stack.back();
+                stack.pop_back();
+                acc = {x.start, x.k + acc.k, x.sh0, x.open && acc.open && acc.sh0 == x.sh0 + 2 * x.k};
+            } else if (code == pbk::FOP_APPLY) {
+                // the branch matrix of a finished subtree: same tips
+            } else {                                     // FOP_PUSH (stand-alone), FOP_ROOT
+                if (code == pbk::FOP_ROOT) acc.open = false;
+                produces = false;
+            }
+            if (produces && acc.open && acc.k >= 2 && acc.k <= max_leaves) cands.push_back({acc.start, i, acc.k, acc.sh0});
+            if (o.code & pbk::FOP_PUSH_AFTER) stack.push_back(acc);
+        }
+    }
+    // maximal candidates (ranges are nested or disjoint: keep those not inside a kept one), largest first
+    std::vector<Cand> kept;
+    for (int j = (int)cands.size() - 1; j >= 0; j--) {
+        bool inside = false;
+        for (const Cand& kq : kept) inside = inside || (cands[j].start >= kq.start && cands[j].end <= kq.end);
+        if (!inside) kept.push_back(cands[j]);
+    }
+    std::sort(kept.begin(), kept.end(), [](const Cand& a, const Cand& b) { return a.start < b.start; });
+    c->clades.clear();
+    c->fprog_tab.clear();
+    c->ntab = 0;
+    size_t next = 0;
+    for (int i = 0; i < (int)prog.size(); i++) {
+        if (next < kept.size() && kept[next].start == i) {
+            const Cand& kq = kept[next++];
+            pbk::CladeTab t{};
+            t.op0 = kq.start; t.op1 = kq.end; t.sh0 = kq.sh0; t.k = kq.k; t.ent0 = c->ntab;
+            c->clades.push_back(t);
+            FusedOp2 o;
+            o.code = pbk::FOP_CHERRY | (prog[kq.end].code & pbk::FOP_PUSH_AFTER);
+            o.offA = c->ntab;                            // first table entry; index = (window >> sh) & offB
+            o.offB = (1 << (2 * kq.k)) - 1;
+            o.sh = kq.sh0;
+            c->fprog_tab.push_back(o);
+            c->ntab += 1 << (2 * kq.k);
+            i = kq.end;
+            continue;
+        }
+        c->fprog_tab.push_back(prog[i]);
+    }
+    c->tab_leaves = max_leaves;
+    c->tables_stale = true;
+    if (!c->clades.empty()) {
+        PB_CUDA(c, c->d_fprog_tab.ensure(c->fprog_tab.size()));
+        PB_CUDA(c, c->d_clades.ensure(c->clades.size()));
+        // (pageable host vectors: the copies complete before the calls return)
+        PB_CUDA(c, cudaMemcpyAsync(c->d_fprog_tab.p, c->fprog_tab.data(), c->fprog_tab.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+        PB_CUDA(c, cudaMemcpyAsync(c->d_clades.p, c->clades.data(), c->clades.size() * sizeof(pbk::CladeTab), cudaMemcpyHostToDevice, c->stream));
+    }
+    return PB_OK;
+}
+
 // The inner matrices of as many categories as the constant bank holds per launch.
 int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
 {
@@ -830,30 +873,35 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     // the program shares the bank: upload it unless this context's current program is already there
     static const pb_ctx* prog_owner[64] = {};
     static uint64_t prog_version[64] = {};
-    const int ncherry = (int)c->cherry_nodes.size() / 2, ntriple = (int)c->triple_nodes.size() / 4;
-    const bool cherry = c->fused_cherry && c->fused_pow2 && ncherry > 0;
-    const bool triple = cherry && c->fused_triple && ntriple > 0;
-    const int ntab = ncherry * 16 + ntriple * 64;                    // table entries per category
-    const uint64_t want_version = c->fprog_version * 4 + (cherry ? 1 : 0) + (triple ? 2 : 0);
-    const FusedOp2* prog = triple ? c->d_fprog_triple.p : cherry ? c->d_fprog_cherry.p : c->d_fprog_c.p;
-    c->fprog_bank_nops = (int)(triple ? c->fprog_triple.size() : c->fprog_c.size());
+    // small clades as table look-ups (power-of-two mode): the program variant for the current size limit
+    // (a table of 4^k entries is only worth building when the alignment has many more sites than that)
+    int want_leaves = (c->fused_cherry && c->fused_pow2) ? (c->fused_triple ? c->fused_clade_leaves : 2) : 0;
+    while (!c->fused_clade_force && want_leaves > 2 && (int64_t)8 << (2 * want_leaves) > c->nsites) want_leaves--;
+    if (c->tab_leaves != want_leaves) {
+        const int rc = build_table_program(c, want_leaves);
+        if (rc != PB_OK) return rc;
+    }
+    const bool tabulated = !c->clades.empty();
+    const uint64_t want_version = c->fprog_version * 8 + (uint64_t)want_leaves;
+    const FusedOp2* prog = tabulated ? c->d_fprog_tab.p : c->d_fprog_c.p;
+    c->fprog_bank_nops = (int)(tabulated ? c->fprog_tab.size() : c->fprog_c.size());
     if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != want_version) {
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, prog, c->fprog_bank_nops * sizeof(FusedOp2), 0,
                                            cudaMemcpyDeviceToDevice, c->stream));
         prog_owner[c->device & 63] = c;
         prog_version[c->device & 63] = want_version;
     }
-    if (cherry && regather) {
-        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * ntab * 4));
-        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * ntab));
-        pbk::build_cherry_tables<<<dim3(ncherry, c->ncat), 32, 0, c->stream>>>(c->d_P.p, c->d_cherry_nodes.p, ncherry, c->nnodes,
-                                                                               ntab, c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
+    if (tabulated && (regather || c->tables_stale)) {
+        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * c->ntab * 4));
+        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->ntab));
+        int kmax = 2;
+        for (const pbk::CladeTab& t : c->clades) kmax = std::max(kmax, t.k);
+        const unsigned gz = (unsigned)std::max(1, (1 << (2 * kmax)) / 256);
+        pbk::build_clade_tables<<<dim3((unsigned)c->clades.size(), c->ncat, gz), 256, 0, c->stream>>>(
+            c->d_fprog_c.p, c->d_clades.p, c->d_P.p, c->d_inner_nodes.p, c->d_leaf_nodes.p, c->nnodes, c->ntab, c->threshold,
+            c->d_cherry_v.p, c->d_cherry_k.p);
         c->launches++;
-        if (ntriple > 0) {                                           // (built even when the option is off: it may be switched on)
-            pbk::build_triple_tables<<<dim3(ntriple, c->ncat), 64, 0, c->stream>>>(
-                c->d_P.p, c->d_triple_nodes.p, ntriple, ncherry, c->nnodes, ntab, c->threshold, c->d_cherry_v.p, c->d_cherry_k.p);
-            c->launches++;
-        }
+        c->tables_stale = false;
     }
     // The bank is loaded for as many categories as it holds (3 x 126 matrices at 128 taxa) and the launches of
     // those categories follow each other without a copy in between.
@@ -1913,6 +1961,11 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const = iv != 0;
     } else if (k == "fused_triple") {
         c->fused_triple = iv != 0;
+    } else if (k == "fused_clade_force") {
+        c->fused_clade_force = iv != 0;
+    } else if (k == "fused_clade_leaves") {
+        if (iv < 2 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "fused_clade_leaves must be in 2..6");
+        c->fused_clade_leaves = iv;
     } else if (k == "fused_cherry") {
         c->fused_cherry = iv != 0;
     } else if (k == "fused_pow2") {

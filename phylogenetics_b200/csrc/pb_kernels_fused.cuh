@@ -34,8 +34,8 @@ struct FusedOp2 {          // 16 bytes: one uniform 128-bit shared-memory load p
 };
 constexpr int FOP_LOADW = 8;     // advance the packed-tip window by one 64-bit word
 constexpr int FOP_ACC_POP = 9;   // ACC = shiftmul(P[pA].ACC, P[pB].pop())   (both children inner)
-constexpr int FOP_CHERRY = 10;   // ACC = table[offA + ((window >> shA) & offB)]: the 16 possible values of a node with two leaf
-                                 // children, or the 64 of the parent of such a node and a leaf (see build_cherry_tables)
+constexpr int FOP_CHERRY = 10;   // ACC = table[offA + ((window >> shA) & offB)]: the 4^k possible values of a clade of k leaves
+                                 // (16 for a node with two leaf children, ...; see build_clade_tables)
 
 // Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
 // 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
@@ -480,66 +480,95 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
     }
 }
 
-// A node whose two children are leaves (a "cherry", about a third of the internal nodes of a birth-death tree)
-// can only take 16 values per rate category: col(P_A, a) o col(P_B, b), rescaled.  They are tabulated once per
-// evaluation — same arithmetic, same power-of-two rescaling as the kernel's TIP_TIP instruction — so the
-// kernel replaces two column look-ups, four multiplications and a rescaling by one 32-byte look-up and an
-// integer add.  The parent of a cherry and a leaf (a clade of three leaves, a sixth of the internal nodes) can
-// only take 64 values: the same treatment replaces the cherry's look-up AND a whole APPLY_MUL_TIP instruction
-// (matrix-vector product, column look-up, product, rescaling).
-// One table per category, `ntab` entries of (4 doubles, 1 exponent): cherry j at entries [16 j, 16 j + 16),
-// index a + 4 b; triple t at [16 ncherry + 64 t, +64), index a + 4 b + 16 c — the order the three tips occupy in
-// the packed word, so the kernel's index is ONE shift and mask.
-__global__ void build_cherry_tables(const double* __restrict__ P, const int* __restrict__ cherry_nodes, int ncherry, int nnodes,
-                                    int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
-{
-    const int c = blockIdx.y, j = blockIdx.x, idx = threadIdx.x;
-    if (idx >= 16) return;
-    const double* PA = P + ((size_t)c * nnodes + cherry_nodes[2 * j]) * 16;
-    const double* PB = P + ((size_t)c * nnodes + cherry_nodes[2 * j + 1]) * 16;
-    const int a = idx & 3, b = idx >> 2;
-    double v[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = PA[i * 4 + a] * PB[i * 4 + b];
-    Scale<SCALE_POW2> sc;
-    sc.init();
-    shift4s(v, sc, thr);
-    const size_t e = (size_t)c * ntab + j * 16 + idx;
-#pragma unroll
-    for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
-    tabK[e] = sc.e;
-}
+// Small clades are tabulated.  A subtree with k leaves can only take 4^k values per rate category, whatever the
+// site: a node with two leaf children (a "cherry", a third of the internal nodes of a birth-death tree) 16, the
+// parent of a cherry and a leaf 64, a clade of four leaves 256, ...  Once per evaluation every such clade (up to
+// `fused_clade_leaves` leaves, all of them in one packed-tip word) gets a table of its possible conditional
+// likelihood vectors and scale exponents, computed by INTERPRETING THE CLADE'S OWN INSTRUCTIONS of the program with
+// the kernel's arithmetic — same operation order, same FMAs, same power-of-two rescaling, so the kernel's results
+// do not change by a bit — and the kernel replaces the whole clade (column look-ups, matrix-vector products,
+// rescalings, stack traffic) by ONE 32-byte look-up and an integer add (FOP_CHERRY).  The leaves of a clade are
+// consumed back to back, so the table index is one shift and mask of the packed-tip window.
+// One table per category, `ntab` entries of (4 doubles, 1 exponent); clade t owns entries [ent0, ent0 + 4^k).
+struct CladeTab {
+    int op0, op1;      // the clade's instructions in the untabulated program (inclusive)
+    int sh0, k;        // bit offset of its first tip in the window, number of leaves
+    int ent0, pad[3];
+};
 
-// triple_nodes[t] = {leaf A, leaf B, the cherry's node (its branch matrix is applied), leaf C}
-__global__ void build_triple_tables(const double* __restrict__ P, const int* __restrict__ triple_nodes, int ntriple, int ncherry,
-                                    int nnodes, int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+__global__ void __launch_bounds__(256)
+build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict__ tabs, const double* __restrict__ P,
+                   const int* __restrict__ inner_nodes, const int* __restrict__ leaf_nodes, int nnodes, int ntab, double thr,
+                   double* __restrict__ tabV, int* __restrict__ tabK)
 {
-    const int c = blockIdx.y, t = blockIdx.x, idx = threadIdx.x;
-    if (idx >= 64) return;
-    const double* PA = P + ((size_t)c * nnodes + triple_nodes[4 * t]) * 16;
-    const double* PB = P + ((size_t)c * nnodes + triple_nodes[4 * t + 1]) * 16;
-    const double* m = P + ((size_t)c * nnodes + triple_nodes[4 * t + 2]) * 16;
-    const double* PC = P + ((size_t)c * nnodes + triple_nodes[4 * t + 3]) * 16;
-    const int a = idx & 3, b = (idx >> 2) & 3, cc = idx >> 4;
-    double x[4], v[4];
+    const CladeTab tb = tabs[blockIdx.x];
+    const int c = blockIdx.y;
+    const double* Pc = P + (size_t)c * nnodes * 16;
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < (1 << (2 * tb.k)); idx += gridDim.z * blockDim.x) {
+        const uint64_t cur = (uint64_t)idx << tb.sh0;          // the window as the kernel would see it
+        double v[4] = {1.0, 1.0, 1.0, 1.0}, stk[8][4];
+        int sp = 0;
+        Scale<SCALE_POW2> sc;
+        sc.init();
+        for (int ip = tb.op0; ip <= tb.op1; ip++) {
+            const FusedOp2 o = prog[ip];
+            const int code = o.code & 0xff, shA = o.sh & 0xff, shB = o.sh >> 8;
+            // inner matrices are row-major (matvec4, the expression of matvec4c); a leaf's column s is P[i*4 + s]
+            auto inner = [&](int off) { return Pc + (size_t)inner_nodes[off / 16] * 16; };
+            auto leaf = [&](int off) { return Pc + (size_t)leaf_nodes[off / 16] * 16; };
+            const int tA = (int)(cur >> shA) & 3, tB = (int)(cur >> shB) & 3;
+            if (code == FOP_APPLY_MUL_TIP) {
+                const double* lf = leaf(o.offB);
+                double y[4];
+                matvec4(inner(o.offA), v, y);
 #pragma unroll
-    for (int i = 0; i < 4; i++) x[i] = PA[i * 4 + a] * PB[i * 4 + b];        // the cherry (FOP_TIP_TIP)
-    Scale<SCALE_POW2> sc;
-    sc.init();
-    shift4s(x, sc, thr);
+                for (int i = 0; i < 4; i++) v[i] = y[i] * lf[i * 4 + tB];
+                shift4s(v, sc, thr);
+            } else if (code == FOP_ACC_POP) {
+                double y[4], z[4];
+                sp--;
+                matvec4(inner(o.offA), v, y);
+                matvec4(inner(o.offB), stk[sp], z);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {                                             // FOP_APPLY_MUL_TIP, as matvec4c does it
-        double y = m[i * 4 + 0] * x[0];
-        y = fma(m[i * 4 + 1], x[1], y);
-        y = fma(m[i * 4 + 2], x[2], y);
-        y = fma(m[i * 4 + 3], x[3], y);
-        v[i] = y * PC[i * 4 + cc];
+                for (int i = 0; i < 4; i++) v[i] = y[i] * z[i];
+                shift4s(v, sc, thr);
+            } else if (code == FOP_TIP_TIP) {
+                const double* la = leaf(o.offA);
+                const double* lb = leaf(o.offB);
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = la[i * 4 + tA] * lb[i * 4 + tB];
+                shift4s(v, sc, thr);
+            } else if (code == FOP_TIP) {
+                const double* la = leaf(o.offA);
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = la[i * 4 + tA];
+            } else if (code == FOP_APPLY) {
+                double y[4];
+                matvec4(inner(o.offA), v, y);
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = y[i];
+            } else if (code == FOP_MUL_TIP) {
+                const double* la = leaf(o.offA);
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = v[i] * la[i * 4 + tA];
+                shift4s(v, sc, thr);
+            } else if (code == FOP_POP_MUL) {
+                sp--;
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = stk[sp][i] * v[i];
+                shift4s(v, sc, thr);
+            }
+            if ((o.code & FOP_PUSH_AFTER) && ip < tb.op1) {     // (the last instruction's push stays in the program)
+#pragma unroll
+                for (int i = 0; i < 4; i++) stk[sp][i] = v[i];
+                sp++;
+            }
+        }
+        const size_t e = (size_t)c * ntab + tb.ent0 + idx;
+#pragma unroll
+        for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
+        tabK[e] = sc.e;
     }
-    shift4s(v, sc, thr);
-    const size_t e = (size_t)c * ntab + ncherry * 16 + t * 64 + idx;
-#pragma unroll
-    for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
-    tabK[e] = sc.e;
 }
 
 // prog: offsets of inner matrices index cPinner (compact inner index * 16); offsets of leaf matrices

@@ -461,7 +461,12 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
         ctx.set_option("fused_const_cats", 2)               # two categories per launch share the constant bank
         total3, per_site3 = ctx.loglik(per_site=True)
         assert total3 == total and np.array_equal(per_site3, per_site)
-        ctx.set_option("fused_triple", 0)                   # clades of three leaves: cherry look-up + APPLY_MUL_TIP instead of one look-up
+        ctx.set_option("fused_clade_force", 1)              # (with 2 500 sites the library would stop at 4 leaves)
+        for leaves in (6, 5, 3, 2):                         # largest tabulated clade (default 5): bit-identical whatever it is
+            ctx.set_option("fused_clade_leaves", leaves)
+            total5, per_site5 = ctx.loglik(per_site=True)
+            assert total5 == total and np.array_equal(per_site5, per_site), leaves
+        ctx.set_option("fused_triple", 0)                   # cherries only
         total5, per_site5 = ctx.loglik(per_site=True)
         assert total5 == total and np.array_equal(per_site5, per_site)
         ctx.set_option("fused_cherry", 0)                   # leaf-leaf nodes computed in the kernel instead of tabulated
