@@ -40,28 +40,41 @@ constexpr int FOP_CHERRY = 10;   // ACC = table[offA + ((window >> shA) & offB)]
 // Tip states uint8 [ntaxa][ld] -> 2-bit codes in program order: packed[w][site], bits
 // 2j..2j+1 of word w = state of the (32 w + j)-th tip the program consumes.
 // Also flags any state >= 4.
+// (The 32 loads of a word are issued before any of them is used, from row indices staged in shared memory: a
+// first form that loaded order[k] and then the byte inside a guarded loop ran its 2 x ntaxa loads per thread back
+// to back, 70 us per 250k sites.)
+constexpr int PACK_ORDER_SMEM = 8192;     // tips whose row indices are staged in shared memory (else read from global)
+
 __global__ void __launch_bounds__(256)
 pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__ order, int ntips,
            int nwords, uint64_t* __restrict__ packed, int64_t spad, int64_t site0, int64_t site1,
            int* __restrict__ bad_flag)
 {
+    __shared__ int s_order[PACK_ORDER_SMEM];
+    const bool staged = ntips <= PACK_ORDER_SMEM;
+    if (staged) {
+        for (int i = threadIdx.x; i < ntips; i += blockDim.x) s_order[i] = order[i];
+        __syncthreads();
+    }
+    const int* ord = staged ? s_order : order;
     const int64_t s = site0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // columns [site0, site1)
     if (s >= site1) return;
-    int bad = 0;
+    unsigned bad = 0;
     for (int w = 0; w < nwords; w++) {
+        unsigned st[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) st[j] = tips[(int64_t)ord[min(w * 32 + j, ntips - 1)] * ld + s];
         uint64_t word = 0;
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; j++) {
-            const int k = w * 32 + j;
-            if (k < ntips) {
-                const unsigned st = tips[(int64_t)order[k] * ld + s];
-                bad |= (st > 3u);
-                word |= (uint64_t)(st & 3u) << (2 * j);
+            if (w * 32 + j < ntips) {
+                bad |= st[j];
+                word |= (uint64_t)(st[j] & 3u) << (2 * j);
             }
         }
         packed[(int64_t)w * spad + s] = word;
     }
-    if (bad) atomicOr(bad_flag, 1);
+    if (bad > 3u) atomicOr(bad_flag, 1);
 }
 
 // Nucleotide alignments that cross PCIe 2-bit packed (pb_set_tips_packed2 / pb_loglik_host_packed2): byte b of a
@@ -88,19 +101,28 @@ __global__ void __launch_bounds__(256)
 pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __restrict__ order, int ntips, int nwords,
                  uint64_t* __restrict__ packed, int64_t spad, int64_t byte0, int64_t byte1)
 {
+    __shared__ int s_order[PACK_ORDER_SMEM];
+    const bool staged = ntips <= PACK_ORDER_SMEM;
+    if (staged) {
+        for (int i = threadIdx.x; i < ntips; i += blockDim.x) s_order[i] = order[i];
+        __syncthreads();
+    }
+    const int* ord = staged ? s_order : order;
     const int64_t b = byte0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // byte columns [byte0, byte1)
     if (b >= byte1) return;
     for (int w = 0; w < nwords; w++) {
+        unsigned v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = in[(int64_t)ord[min(w * 32 + j, ntips - 1)] * ld_in + b];
         uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll 16
+#pragma unroll
         for (int j = 0; j < 32; j++) {
-            const int k = w * 32 + j;
-            if (k < ntips) {
-                const uint64_t v = in[(int64_t)order[k] * ld_in + b];
-                w0 |= (v & 3u) << (2 * j);
-                w1 |= ((v >> 2) & 3u) << (2 * j);
-                w2 |= ((v >> 4) & 3u) << (2 * j);
-                w3 |= (v >> 6) << (2 * j);
+            if (w * 32 + j < ntips) {
+                const uint64_t x = v[j];
+                w0 |= (x & 3u) << (2 * j);
+                w1 |= ((x >> 2) & 3u) << (2 * j);
+                w2 |= ((x >> 4) & 3u) << (2 * j);
+                w3 |= (x >> 6) << (2 * j);
             }
         }
         ulonglong2* out = reinterpret_cast<ulonglong2*>(packed + (int64_t)w * spad + 4 * b);   // 32-byte aligned

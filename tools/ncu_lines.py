@@ -1,6 +1,6 @@
 """Attribute ncu stall samples of one kernel to CUDA source lines.
 
-  python tools/ncu_lines.py <report.ncu-rep> <cubin.txt from `nvdisasm -g -c`> <mangled-kernel-substring> [min_samples]
+  python tools/ncu_lines.py <report.ncu-rep> <cubin.txt from `nvdisasm -g -c`> <mangled-kernel-substring> [min_samples] [demangled-name-substring]
 
 The SASS page of the report and the nvdisasm listing are walked in lock-step (same instruction order);
 the `//## File ..., line N` markers of the listing give every instruction its source line.
@@ -11,12 +11,13 @@ rep, listing, kern = sys.argv[1:4]
 min_s = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-h = rows[1]; ix = {k: i for i, k in enumerate(h)}
-body = rows[2:]
-for i, r in enumerate(body):                     # a report with several launches: the first one only
-    if r and r[0] == "Kernel Name":
-        body = body[:i]
-        break
+# a report with several launches: the first launch of the kernel whose demangled name contains argv[5] (default: the first)
+want = sys.argv[5] if len(sys.argv) > 5 else ""
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+first = next(i for i in heads if want in rows[i][1])
+end = next((i for i in heads if i > first), len(rows))
+h = rows[first + 1]; ix = {k: i for i, k in enumerate(h)}
+body = rows[first + 2:end]
 sass = [(r[ix["Source"]].strip(), int(r[ix["# Samples"]] or 0)) for r in body if len(r) > ix["# Samples"] and r[ix["# Samples"]].isdigit()]
 # listing: instructions of the kernel in order with current line
 lines = open(listing).read().splitlines()
