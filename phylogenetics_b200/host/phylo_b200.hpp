@@ -4,6 +4,7 @@
 // behaviour as lib/phylo_ctmc.mli, lib/felsenstein.mli, lib/site_evolution_model.mli.
 // Header-only; link against libphylo_b200.so.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <functional>
 #include <memory>
@@ -359,5 +360,102 @@ struct Felsenstein {
     double felsenstein(typename Model::param p, const Phylogenetic_tree& t, const Align& a) const { return evaluate(p, t, a, 0.0000001); }
     double felsenstein_noshift(typename Model::param p, const Phylogenetic_tree& t, const Align& a) const { return evaluate(p, t, a, -INFINITY); }
 };
+
+// Nelder_mead.minimize (lib/nelder_mead.ml:53-132): the derivative-free simplex search that turns one likelihood
+// evaluation into a workload (BASELINE config 5).  alpha = 1, gamma = 2, rho = sigma = 0.5; the search stops when the
+// sample standard deviation of the simplex values (Gsl.Stats.sd) falls below `tol` or after `maxit` iterations.
+// `f` is opaque: with the GPU evaluator it uploads O(branches) scalars and reads one double back per call.
+namespace Nelder_mead {
+
+using Point = std::vector<double>;
+
+inline Point centroid(const std::vector<Point>& xs)                       // :40-47
+{
+    if (xs.empty()) throw std::invalid_argument("Nelder_mead.centroid: empty array");
+    Point c(xs[0].size());
+    for (size_t i = 0; i < c.size(); i++) {
+        double acc = 0.0;
+        for (const Point& x : xs) acc = acc + x[i];
+        c[i] = acc / (double)xs.size();
+    }
+    return c;
+}
+
+inline Point update(const Point& from, double alpha, const Point& towards)  // :49-51
+{
+    Point y(from.size());
+    for (size_t i = 0; i < y.size(); i++) y[i] = from[i] + alpha * (towards[i] - from[i]);
+    return y;
+}
+
+inline double sd(const std::vector<double>& v)         // Gsl.Stats.sd: running mean and variance, n - 1 denominator
+{
+    double mean = 0.0, var = 0.0;
+    for (size_t i = 0; i < v.size(); i++) mean += (v[i] - mean) / (double)(i + 1);
+    for (size_t i = 0; i < v.size(); i++) { const double d = v[i] - mean; var += (d * d - var) / (double)(i + 1); }
+    return std::sqrt(var * ((double)v.size() / ((double)v.size() - 1.0)));
+}
+
+inline std::vector<int> array_order(const std::vector<double>& v)         // Utils.array_order: ranks, ties by index
+{
+    std::vector<int> r(v.size());
+    for (size_t i = 0; i < r.size(); i++) r[i] = (int)i;
+    std::stable_sort(r.begin(), r.end(), [&](int a, int b) { return v[a] < v[b]; });
+    return r;
+}
+
+struct Result { double value; Point point; int iterations; };
+
+template <class F, class S>
+Result minimize(F&& f, S&& sample, double tol = 1e-8, int maxit = 100000)
+{
+    const double alpha = 1.0, gamma = 2.0, rho = 0.5, sigma = 0.5;
+    const Point first = sample();          // like the reference, the first draw only fixes the dimension
+    const size_t n = first.size();
+    if (n == 0) throw std::invalid_argument("Nelder_mead.minimize: sample returns empty vectors");
+    std::vector<Point> pts(n + 1);
+    std::vector<double> obj(n + 1);
+    for (Point& p : pts) {
+        p = sample();
+        if (p.size() != n) throw std::invalid_argument("Nelder_mead.minimize: sample returns vectors of varying lengths");
+    }
+    for (size_t k = 0; k <= n; k++) obj[k] = f(pts[k]);
+    for (int it = 0;; it++) {
+        const std::vector<int> rk = array_order(obj);
+        const int best = rk[0], worst = rk[n];
+        const double f_second_worst = obj[rk[n - 1]];
+        std::vector<Point> keep;
+        for (size_t k = 0; k < n; k++) keep.push_back(pts[rk[k]]);
+        const Point c = centroid(keep);
+        const Point x_r = update(c, -alpha, pts[worst]);
+        const double f_r = f(x_r);
+        if (f_r < obj[best]) {                                             // expansion
+            const Point x_e = update(c, gamma, x_r);
+            const double f_e = f(x_e);
+            pts[worst] = f_e < f_r ? x_e : x_r;
+            obj[worst] = std::fmin(f_r, f_e);
+        } else if (f_r < f_second_worst) {                                 // reflection
+            pts[worst] = x_r;
+            obj[worst] = f_r;
+        } else {
+            const bool outside = f_r < obj[worst];
+            const Point x_c = update(c, rho, outside ? x_r : pts[worst]);
+            const double f_c = f(x_c);
+            if (outside ? f_c <= f_r : f_c < obj[worst]) {                 // contraction
+                pts[worst] = x_c;
+                obj[worst] = f_c;
+            } else {                                                       // shrink towards the best point
+                for (size_t k = 0; k <= n; k++) {
+                    if ((int)k == best) continue;
+                    pts[k] = update(pts[best], sigma, pts[k]);
+                    obj[k] = f(pts[k]);
+                }
+            }
+        }
+        if (sd(obj) < tol || it >= maxit) return Result{obj[best], pts[best], it};
+    }
+}
+
+}  // namespace Nelder_mead
 
 }  // namespace phylo_b200

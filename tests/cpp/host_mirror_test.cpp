@@ -118,6 +118,31 @@ int main()
         std::printf("%-58s %s\n", "conditional_simulation keeps the observed leaves", leaves_kept ? "ok" : "FAIL");
         failures += !leaves_kept;
     }
+    // 6. Nelder_mead.minimize driving the GPU evaluator (the shape of BASELINE config 5 in miniature): the length of
+    //    the branch above T2 of the mCMC fixture's tree, on a log scale, maximising Felsenstein(K80 kappa = 2)
+    {
+        using PT = Phylogenetic_tree;
+        using Align = std::map<std::string, std::string>;
+        Align align{{"T0", "AACGTTAC"}, {"T1", "AACGTTAC"}, {"T2", "AGCGTCAC"}, {"T3", "TACGATAC"}};
+        Felsenstein<SEM::K80, Align> F;
+        F.get_base = [](const Align& a, const std::string& seq, int64_t pos) { return (int)std::string("ACGT").find(a.at(seq)[pos]); };
+        F.length = [](const Align& a) { return (int64_t)a.begin()->second.size(); };
+        int evaluations = 0;
+        auto objective = [&](const Nelder_mead::Point& x) {
+            evaluations++;
+            auto tree = PT::node(0.1, PT::node(0.1, PT::leaf("T0"), 0.1, PT::leaf("T1")), 0.1,
+                                 PT::node(std::exp(x[0]), PT::leaf("T2"), 0.1, PT::leaf("T3")));
+            return -F.felsenstein(2.0, *tree, align);
+        };
+        double start = -3.0;
+        const auto r = Nelder_mead::minimize(objective, [&] { start += 1.0; return Nelder_mead::Point{start}; }, 1e-10, 200);
+        const double f0 = objective(r.point);
+        const bool stationary = objective({r.point[0] + 0.05}) >= f0 && objective({r.point[0] - 0.05}) >= f0;
+        const bool improved = f0 <= objective({-2.0}) && f0 <= objective({-1.0});
+        std::printf("%-58s t = %.6f, -logL = %.9f, %d evaluations %s\n", "Nelder_mead over one branch length on the GPU",
+                    std::exp(r.point[0]), f0, evaluations, (stationary && improved) ? "ok" : "FAIL");
+        failures += !(stationary && improved);
+    }
     std::printf(failures ? "%d FAILED\n" : "all ok\n", failures);
     return failures ? 1 : 0;
 }

@@ -41,3 +41,46 @@ def test_argument_errors_and_helpers():
     assert NM._array_order([3.0, 1.0, 2.0, 1.0]) == [1, 3, 2, 0]
     _, _, its = NM.minimize(lambda x: x[0] ** 2, lambda: [5.0], maxit=3, tol=0.0)
     assert its == 3
+
+
+def test_cpp_mirror_matches_the_python_mirror_run_by_run():
+    """phylogenetics_b200/host/phylo_b200.hpp, namespace Nelder_mead: the reference's three inline tests from
+    starting points drawn from one 32-bit LCG — the C++ program and this test replay the same stream, so the two
+    mirrors must agree on the value reached and on the number of iterations, not only on `< 1e-3`."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "_build", "nelder_mead_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-ffp-contract=off",
+                    "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "phylogenetics_b200", "host"),
+                    os.path.join(root, "tests", "cpp", "nelder_mead_test.cpp"), "-o", exe,
+                    "-L" + os.path.join(root, "phylogenetics_b200"), "-lphylo_b200",
+                    "-Wl,-rpath,$ORIGIN/../../../phylogenetics_b200"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "all ok" in out.stdout and "FAIL" not in out.stdout, out.stdout + out.stderr
+    got = {l.split()[1]: (float(l.split()[2]), int(l.split()[3])) for l in out.stdout.splitlines() if l.startswith("RESULT")}
+
+    state = [12345]
+
+    def nxt():
+        state[0] = (state[0] * 1664525 + 1013904223) & 0xFFFFFFFF
+        return state[0] / 4294967296.0 * 200.0 - 100.0
+
+    def draw(n):
+        return lambda: [nxt() for _ in range(n)]
+
+    def rosen(x):
+        a, b = x[1] - x[0] * x[0], 1.0 - x[0]
+        return 100.0 * (a * a) + b * b
+
+    def powell(x):
+        a, b, c, d = x[0] + 10.0 * x[1], x[2] - x[3], x[1] - 2.0 * x[2], x[0] - x[3]
+        return a * a + 5.0 * (b * b) + (c * c) * (c * c) + 10.0 * ((d * d) * (d * d))
+
+    want = {"parabola": NM.minimize(lambda x: x[0] * x[0], draw(1), tol=1e-3),
+            "rosenbrock": NM.minimize(rosen, draw(2)),
+            "powell": NM.minimize(powell, draw(4))}
+    for name, (obj, _, its) in want.items():
+        assert got[name][1] == its, (name, got[name], obj, its)
+        assert got[name][0] == obj, (name, got[name], obj)
