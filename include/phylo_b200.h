@@ -37,6 +37,7 @@
 #ifndef PHYLO_B200_H
 #define PHYLO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -167,6 +168,11 @@ int pb_loglik_host(pb_ctx *ctx, const uint8_t *states, int64_t ld, double *total
 /* The same from a 2-bit packed host alignment (see pb_set_tips_packed2).  The alignment stays resident 2-bit
  * packed; the byte-per-site matrix other entry points read is expanded on the device when one of them needs it. */
 int pb_loglik_host_packed2(pb_ctx *ctx, const uint8_t *packed, int64_t ld, double *total, double *per_site);
+/* Page-lock / release a caller-owned host buffer (e.g. the payload of an OCaml Bigarray, which lives outside the
+ * OCaml heap and does not move) so that the chunked copies above are asynchronous.  No context: the message of a
+ * failure is pb_last_error(NULL). */
+int pb_pin_host_memory(void *p, size_t bytes);
+int pb_unpin_host_memory(void *p);
 /* Non-blocking half: enqueue P(t) + pruning + root reduction on the stream. */
 int pb_loglik_enqueue(pb_ctx *ctx);
 /* Blocking half: wait for the stream and fetch.  per_site may be NULL. */

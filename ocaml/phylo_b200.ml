@@ -8,6 +8,7 @@ type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.
 type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
 type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
 type float_mat = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array2.t
+type mask_matrix = (int64, Bigarray.int64_elt, Bigarray.c_layout) Bigarray.Array2.t
 
 type flat_tree = { root : int ; child_ptr : int32_vec ; child_idx : int32_vec ; tip_row : int32_vec }
 
@@ -34,6 +35,19 @@ external transition_matrices_eigen_ :
   = "pb_stub_transition_matrices_eigen_bytecode" "pb_stub_transition_matrices_eigen"
 external transition_matrices_expm_ : int -> Linear_algebra.mat -> float_vec -> float_vec -> unit
   = "pb_stub_transition_matrices_expm"
+external set_tip_masks : ctx -> mask_matrix -> unit = "pb_stub_set_tip_masks"
+external set_tips_text_ : ctx -> tip_matrix -> int -> unit = "pb_stub_set_tips_text"
+external set_site_weights_ : ctx -> float_vec -> unit = "pb_stub_set_site_weights"
+external update_branch_length : ctx -> int -> float -> unit = "pb_stub_update_branch_length"
+external nodes_recomputed : ctx -> int = "pb_stub_nodes_recomputed"
+external set_option : ctx -> string -> float -> unit = "pb_stub_set_option"
+external get_pmatrices_ : ctx -> float_vec -> unit = "pb_stub_get_pmatrices"
+external path_name : ctx -> string = "pb_stub_path_name"
+external kernel_launches : ctx -> int = "pb_stub_kernel_launches"
+external loglik_host_ : ctx -> tip_matrix -> float_vec -> float = "pb_stub_loglik_host"
+external loglik_host_packed2_ : ctx -> tip_matrix -> float_vec -> float = "pb_stub_loglik_host_packed2"
+external pin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit = "pb_stub_pin"
+external unpin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit = "pb_stub_unpin"
 
 let keep_clv_flag = 1
 let mode_phylo_ctmc = 0
@@ -85,6 +99,23 @@ let transition_matrices_expm ?(device = 0) q ts =
 
 let empty_vec = Bigarray.(Array1.create float64 c_layout 0)
 let loglik ctx ?(per_site = empty_vec) () = loglik_ ctx per_site
+
+(* One call per evaluation from a host alignment: the copy runs in column chunks while the previous chunk is pruned.
+   [pin] the tip matrix once if it is evaluated repeatedly. *)
+let loglik_host ctx ?(per_site = empty_vec) tips = loglik_host_ ctx tips per_site
+let loglik_host_packed2 ctx ?(per_site = empty_vec) tips = loglik_host_packed2_ ctx tips per_site
+
+let set_site_weights ctx = function
+  | Some w -> set_site_weights_ ctx w
+  | None -> set_site_weights_ ctx empty_vec
+
+let alphabet_dna = 0 and alphabet_amino_acid = 1 and alphabet_codon = 2
+let set_tips_text ctx ~alphabet text = set_tips_text_ ctx text alphabet
+
+let get_pmatrices ctx ~ncat ~nnodes ~nstates =
+  let p = Bigarray.(Array1.create float64 c_layout (ncat * nnodes * nstates * nstates)) in
+  get_pmatrices_ ctx p ;
+  p
 
 (* Pre-order numbering of a Tree.t (lib/tree.ml:3-13). *)
 let flatten (t : _ Tree.t) =
@@ -138,9 +169,13 @@ let pruning_sites t ~nstates ~nsites ~transition_probabilities ~leaf_state ~root
           done
         done) ;
   set_pmatrices ctx p ;
+  set_mode ctx mode_phylo_ctmc ;
+  set_root_frequencies ctx root_frequencies ;
+  let per_site = Bigarray.(Array1.create float64 c_layout nsites) in
   (* leaf_state is evaluated once per (leaf, site) either way; nucleotides are written 2-bit packed, 4 sites per
-     byte, which is what crosses PCIe (pb_set_tips_packed2) *)
-  if nstates = 4 then begin
+     byte, which is what crosses PCIe; the evaluation is ONE call that overlaps the copy with the pruning
+     (pb_loglik_host_packed2 / pb_loglik_host) *)
+  let tips = if nstates = 4 then begin
     let nbytes = (nsites + 3) / 4 in
     let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nbytes) in
     Bigarray.Array2.fill tips 0 ;
@@ -148,13 +183,45 @@ let pruning_sites t ~nstates ~nsites ~transition_probabilities ~leaf_state ~root
         for s = 0 to nsites - 1 do
           tips.{row, s / 4} <- tips.{row, s / 4} lor (leaf_state l s lsl (2 * (s land 3)))
         done) ;
-    set_tips_packed2 ctx tips
+    `Packed tips
   end
   else begin
     let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
     Array.iteri leaves ~f:(fun row l -> for s = 0 to nsites - 1 do tips.{row, s} <- leaf_state l s done) ;
-    set_tips ctx tips
-  end ;
+    `Bytes tips
+  end in
+  let total = match tips with
+    | `Packed t -> loglik_host_packed2 ctx ~per_site t
+    | `Bytes t -> loglik_host ctx ~per_site t
+  in
+  total, per_site
+
+(* Phylo_ctmc.Missing_values.pruning / Ambiguous.pruning (lib/phylo_ctmc.ml:145-172, 280-302) for every site:
+   [leaf_states l i] is the set of states compatible with the observation at leaf [l], site [i], as a bit mask
+   (bit k = state k; 0 = missing).  [Missing_values]: [Some s -> 1 lsl s | None -> 0]; [Ambiguous]: the mask of
+   the states for which the reference's [leaf_state l s] is true. *)
+let pruning_sites_masks t ~nstates ~nsites ~transition_probabilities ~leaf_states ~root_frequencies =
+  let flat, leaves, branches = flatten t in
+  let nnodes = Bigarray.Array1.dim flat.tip_row and ntaxa = Array.length leaves in
+  let ctx = create ~nstates ~nsites ~ntaxa () in
+  let zero = Bigarray.(Array1.create float64 c_layout nnodes) in
+  Bigarray.Array1.fill zero 0. ;
+  set_tree ctx flat ~branch_lengths:zero ;
+  let p = Bigarray.(Array1.create float64 c_layout (nnodes * nstates * nstates)) in
+  Bigarray.Array1.fill p 0. ;
+  Array.iteri branches ~f:(fun v -> function
+      | None -> ()
+      | Some b ->
+        let m = Phylo_ctmc.matrix_decomposition_reduce ~dim:nstates (transition_probabilities b) in
+        for j = 0 to nstates - 1 do
+          for i = 0 to nstates - 1 do
+            p.{v * nstates * nstates + j * nstates + i} <- Linear_algebra.Matrix.get m i j
+          done
+        done) ;
+  set_pmatrices ctx p ;
+  let masks = Bigarray.(Array2.create int64 c_layout ntaxa nsites) in
+  Array.iteri leaves ~f:(fun row l -> for s = 0 to nsites - 1 do masks.{row, s} <- leaf_states l s done) ;
+  set_tip_masks ctx masks ;
   set_mode ctx mode_phylo_ctmc ;
   set_root_frequencies ctx root_frequencies ;
   let per_site = Bigarray.(Array1.create float64 c_layout nsites) in

@@ -14,6 +14,7 @@ type int32_vec = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array1.
 type float_vec = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array1.t
 type tip_matrix = (int, Bigarray.int8_unsigned_elt, Bigarray.c_layout) Bigarray.Array2.t
 type float_mat = (float, Bigarray.float64_elt, Bigarray.c_layout) Bigarray.Array2.t
+type mask_matrix = (int64, Bigarray.int64_elt, Bigarray.c_layout) Bigarray.Array2.t
 
 type flat_tree = {
   root : int ;
@@ -51,6 +52,17 @@ val pruning_sites :
 (** All sites of an alignment at once: total and per-site log-likelihoods.  [leaf_state l i] is the
     state of leaf [l] at site [i]; both closures are evaluated eagerly on the host (once per branch,
     once per (leaf, site)). *)
+
+val pruning_sites_masks :
+  ('n, 'l, 'b) Tree.t ->
+  nstates:int ->
+  nsites:int ->
+  transition_probabilities:('b -> Phylo_ctmc.matrix_decomposition) ->
+  leaf_states:('l -> int -> int64) ->
+  root_frequencies:Linear_algebra.vec ->
+  float * float_vec
+(** [Phylo_ctmc.Missing_values.pruning] / [Phylo_ctmc.Ambiguous.pruning] (lib/phylo_ctmc.ml:145-172, 280-302) for all
+    sites: [leaf_states l i] is the bit mask of the states compatible with leaf [l] at site [i] ([0L] = missing). *)
 
 module Felsenstein (A : Alphabet.S_int) (Align : Felsenstein.Alignment with type base := A.t)
     (E : Site_evolution_model.S_with_reduction with type mat := A.matrix and type vec := A.vector) : sig
@@ -95,3 +107,28 @@ val transition_matrices_eigen :
 
 val transition_matrices_expm : ?device:int -> Linear_algebra.mat -> float array -> Linear_algebra.mat array
 (** [Matrix.expm (Matrix.scal_mul t q)] for many [t] in one launch ([Rate_matrix.transition_probability_matrix]). *)
+
+(** {2 The rest of the C ABI} *)
+
+val set_tip_masks : ctx -> mask_matrix -> unit
+val set_tips_text : ctx -> alphabet:int -> tip_matrix -> unit
+val alphabet_dna : int
+val alphabet_amino_acid : int
+val alphabet_codon : int
+val set_site_weights : ctx -> float_vec option -> unit
+val update_branch_length : ctx -> int -> float -> unit
+(** One branch (by the node below it); with [~keep_clv:true] the next [loglik] recomputes only the path to the root. *)
+val nodes_recomputed : ctx -> int
+val set_option : ctx -> string -> float -> unit
+val get_pmatrices : ctx -> ncat:int -> nnodes:int -> nstates:int -> float_vec
+val path_name : ctx -> string
+val kernel_launches : ctx -> int
+
+val loglik_host : ctx -> ?per_site:float_vec -> tip_matrix -> float
+val loglik_host_packed2 : ctx -> ?per_site:float_vec -> tip_matrix -> float
+(** One call per evaluation from a host alignment ([pb_loglik_host], [pb_loglik_host_packed2]): the copy to the
+    device runs in column chunks while the previous chunk is pruned. *)
+
+val pin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit
+val unpin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit
+(** Page-lock / release a Bigarray's payload so that those copies are asynchronous. *)

@@ -219,3 +219,89 @@ CAMLprim value pb_stub_transition_matrices_expm(value device, value q, value ts,
                                             (const double *)Caml_ba_data_val(ts), (double *)Caml_ba_data_val(out)));
     return Val_unit;
 }
+
+/* ---- the rest of include/phylo_b200.h ---------------------------------------------------------------- */
+
+/* masks: (int64, int64_elt, c_layout) Array2 [ntaxa][nsites]; bit i set = state i compatible, 0 = missing
+ * (Phylo_ctmc.Missing_values / Ambiguous, lib/phylo_ctmc.ml:145-172, 232-302) */
+CAMLprim value pb_stub_set_tip_masks(value ctx, value masks)
+{
+    check(Ctx_val(ctx), pb_set_tip_masks(Ctx_val(ctx), (const uint64_t *)Caml_ba_data_val(masks),
+                                         (int64_t)Caml_ba_array_val(masks)->dim[1]));
+    return Val_unit;
+}
+
+/* text: (char, int8_unsigned_elt, c_layout) Array2 [ntaxa][nsites * width]; alphabet: PB_ALPHABET_* */
+CAMLprim value pb_stub_set_tips_text(value ctx, value text, value alphabet)
+{
+    check(Ctx_val(ctx), pb_set_tips_text(Ctx_val(ctx), (const char *)Caml_ba_data_val(text),
+                                         (int64_t)Caml_ba_array_val(text)->dim[1], Int_val(alphabet)));
+    return Val_unit;
+}
+
+/* w: float64 Array1 [nsites], or an empty one to remove the weights */
+CAMLprim value pb_stub_set_site_weights(value ctx, value w)
+{
+    const double *p = Caml_ba_array_val(w)->dim[0] > 0 ? (const double *)Caml_ba_data_val(w) : NULL;
+    check(Ctx_val(ctx), pb_set_site_weights(Ctx_val(ctx), p));
+    return Val_unit;
+}
+
+CAMLprim value pb_stub_update_branch_length(value ctx, value node, value t)
+{
+    check(Ctx_val(ctx), pb_update_branch_length(Ctx_val(ctx), Int_val(node), Double_val(t)));
+    return Val_unit;
+}
+
+CAMLprim value pb_stub_nodes_recomputed(value ctx) { return Val_int(pb_nodes_recomputed(Ctx_val(ctx))); }
+
+CAMLprim value pb_stub_set_option(value ctx, value name, value v)
+{
+    check(Ctx_val(ctx), pb_set_option(Ctx_val(ctx), String_val(name), Double_val(v)));
+    return Val_unit;
+}
+
+/* p: float64 Array1 of ncat * nnodes * n * n */
+CAMLprim value pb_stub_get_pmatrices(value ctx, value p)
+{
+    check(Ctx_val(ctx), pb_get_pmatrices(Ctx_val(ctx), (double *)Caml_ba_data_val(p)));
+    return Val_unit;
+}
+
+CAMLprim value pb_stub_path_name(value ctx) { return caml_copy_string(pb_path_name(Ctx_val(ctx))); }
+CAMLprim value pb_stub_kernel_launches(value ctx) { return Val_long((long)pb_kernel_launches(Ctx_val(ctx))); }
+
+/* One-call evaluation from a host alignment, copy and pruning overlapped (pb_loglik_host / _packed2): the calls the
+ * end-to-end throughput is quoted on.  tips as in pb_stub_set_tips / pb_stub_set_tips_packed2; pin the Bigarray once
+ * with pb_stub_pin for the copies to be asynchronous. */
+static value loglik_host(value ctx, value tips, value per_site, int packed2)
+{
+    CAMLparam3(ctx, tips, per_site);
+    pb_ctx *c = Ctx_val(ctx);
+    const uint8_t *p = (const uint8_t *)Caml_ba_data_val(tips);
+    int64_t ld = Caml_ba_array_val(tips)->dim[1];
+    double *ps = Caml_ba_array_val(per_site)->dim[0] > 0 ? (double *)Caml_ba_data_val(per_site) : NULL;
+    double total = 0.0;
+    int rc;
+    caml_release_runtime_system();
+    rc = packed2 ? pb_loglik_host_packed2(c, p, ld, &total, ps) : pb_loglik_host(c, p, ld, &total, ps);
+    caml_acquire_runtime_system();
+    check(c, rc);
+    CAMLreturn(caml_copy_double(total));
+}
+CAMLprim value pb_stub_loglik_host(value ctx, value tips, value per_site) { return loglik_host(ctx, tips, per_site, 0); }
+CAMLprim value pb_stub_loglik_host_packed2(value ctx, value tips, value per_site) { return loglik_host(ctx, tips, per_site, 1); }
+
+/* Page-lock / release the payload of a Bigarray (it lives outside the OCaml heap and does not move). */
+CAMLprim value pb_stub_pin(value ba)
+{
+    struct caml_ba_array *b = Caml_ba_array_val(ba);
+    size_t bytes = caml_ba_byte_size(b);
+    check(NULL, pb_pin_host_memory(b->data, bytes));
+    return Val_unit;
+}
+CAMLprim value pb_stub_unpin(value ba)
+{
+    check(NULL, pb_unpin_host_memory(Caml_ba_data_val(ba)));
+    return Val_unit;
+}

@@ -28,7 +28,7 @@ PB_ALPHABET_DNA, PB_ALPHABET_AMINO_ACID, PB_ALPHABET_CODON = 0, 1, 2
 # Every symbol include/phylo_b200.h declares (tests check the .so exports them all).
 EXPORTS = [
     "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
-    "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tips_packed2", "pb_loglik_host_packed2", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
+    "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tips_packed2", "pb_loglik_host_packed2", "pb_pin_host_memory", "pb_unpin_host_memory", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
@@ -83,6 +83,8 @@ def _load():
         "pb_loglik": (ci, [vp, vp, vp]),
         "pb_loglik_host": (ci, [vp, vp, i64, vp, vp]),
         "pb_loglik_host_packed2": (ci, [vp, vp, i64, vp, vp]),
+        "pb_pin_host_memory": (ci, [vp, ctypes.c_size_t]),
+        "pb_unpin_host_memory": (ci, [vp]),
         "pb_loglik_enqueue": (ci, [vp]),
         "pb_loglik_fetch": (ci, [vp, vp, vp]),
         "pb_result_device_ptrs": (ci, [vp, vp, vp]),

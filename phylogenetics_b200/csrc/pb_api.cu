@@ -1623,6 +1623,24 @@ int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const d
     return PB_OK;
 }
 
+// Page-lock a caller-owned host buffer (an OCaml Bigarray payload lives outside the OCaml heap and does not move)
+// so that the chunked copies of pb_loglik_host / pb_loglik_host_packed2 overlap with the pruning.
+int pb_pin_host_memory(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return fail(nullptr, PB_ERR_INVALID_ARG, "pb_pin_host_memory: null pointer or empty range");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(nullptr, e, "cudaHostRegister"); }
+    return PB_OK;
+}
+
+int pb_unpin_host_memory(void* p)
+{
+    if (!p) return fail(nullptr, PB_ERR_INVALID_ARG, "pb_unpin_host_memory: null pointer");
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(nullptr, e, "cudaHostUnregister"); }
+    return PB_OK;
+}
+
 int pb_host_reversible_eigensystem(int n, const double* Q, const double* pi, double* U, double* lambda, double* Uinv)
 {
     if (n < 1 || n > 64 || !Q || !pi || !U || !lambda || !Uinv) return PB_ERR_INVALID_ARG;

@@ -4,4 +4,5 @@
 #include "mlvalues.h"
 CAMLextern value caml_copy_double(double d);
 CAMLextern value caml_copy_int64(int64_t i);
+CAMLextern value caml_copy_string(const char *s);
 #endif

@@ -14,6 +14,8 @@ struct caml_ba_array {
     void *proxy;
     intnat dim[4];
 };
+CAMLextern uintnat caml_ba_byte_size(struct caml_ba_array *b);     /* payload size in bytes */
+#define CAML_BA_KIND_MASK 0xff
 #define Caml_ba_array_val(v) ((struct caml_ba_array *)(v))
 #define Caml_ba_data_val(v) (Caml_ba_array_val(v)->data)
 #endif

@@ -36,5 +36,7 @@ typedef uintptr_t uintnat;
 /* boxed float / int64: here a pointer to a malloc'd scalar */
 #define Double_val(v) (*(const double *)(v))
 #define Int64_val(v) (*(const int64_t *)(v))
+/* OCaml string: here a NUL-terminated C string */
+#define String_val(v) ((const char *)(v))
 
 #endif

@@ -61,6 +61,19 @@ value caml_copy_int64(int64_t i)
     *p = i;
     return (value)p;
 }
+value caml_copy_string(const char *str)
+{
+    char *p = malloc(strlen(str) + 1);
+    strcpy(p, str);
+    return (value)p;
+}
+uintnat caml_ba_byte_size(struct caml_ba_array *b)
+{
+    static const int elt[] = {4, 8, 1, 1, 2, 2, 4, 8};          /* enum caml_ba_kind order */
+    uintnat n = elt[b->flags & CAML_BA_KIND_MASK];
+    for (intnat i = 0; i < b->num_dims; i++) n *= (uintnat)b->dim[i];
+    return n;
+}
 value caml_alloc_custom(struct custom_operations *ops, uintnat size, uintnat mem, uintnat max)
 {
     (void)mem; (void)max;
@@ -106,6 +119,19 @@ value pb_stub_conditional_simulation(value, value, value);
 value pb_stub_transition_matrices_eigen(value, value, value, value, value, value);
 value pb_stub_transition_matrices_eigen_bytecode(value *, int);
 value pb_stub_transition_matrices_expm(value, value, value, value);
+value pb_stub_set_tip_masks(value, value);
+value pb_stub_set_tips_text(value, value, value);
+value pb_stub_set_site_weights(value, value);
+value pb_stub_update_branch_length(value, value, value);
+value pb_stub_nodes_recomputed(value);
+value pb_stub_set_option(value, value, value);
+value pb_stub_get_pmatrices(value, value);
+value pb_stub_path_name(value);
+value pb_stub_kernel_launches(value);
+value pb_stub_loglik_host(value, value, value);
+value pb_stub_loglik_host_packed2(value, value, value);
+value pb_stub_pin(value);
+value pb_stub_unpin(value);
 
 /* ---- checks ----------------------------------------------------------------------------------------- */
 
@@ -314,8 +340,85 @@ int main(void)
         finalise(ctx);
     }
 
+    /* 6. the rest of the header: state-set masks (Missing_values / Ambiguous), alignment text, site weights, options,
+     *    introspection, the one-call pipelined host evaluation on a pinned Bigarray, partial re-evaluation */
+    {
+        enum { S = 12000 };                                  /* enough columns for the chunked copy/compute pipeline */
+        double bl[7] = {0.0, 0.4, 0.8, 1.2, 0.1, 0.6, 0.3};
+        double q[16];
+        for (int k = 0; k < 16; k++) q[k] = (k % 5 == 0) ? -1.0 : 1.0 / 3.0;
+        static uint8_t bytes[4][S], packed[4][S / 4], text[4][S];
+        static int64_t masks[4][S];
+        static double per_site[3][S], w[S];
+        memset(packed, 0, sizeof packed);
+        for (int r = 0; r < 4; r++)
+            for (int s = 0; s < S; s++) {
+                const int st = s == 0 ? r : (r * 5 + s * 7 + (s >> 3)) & 3;     /* column 0 is A,C,G,T */
+                bytes[r][s] = (uint8_t)st;
+                packed[r][s / 4] |= (uint8_t)(st << (2 * (s & 3)));
+                text[r][s] = (uint8_t)"ACGT"[st];
+                masks[r][s] = (int64_t)1 << st;
+                w[s] = 1.0 + (s % 3);
+            }
+        for (int r = 0; r < 4; r++) { masks[r][1] = 0; masks[r][2] = 15; }         /* all missing; all fully ambiguous */
+        value ctx = make_ctx(4, 1, S, 4, 0);
+        set_tree4(ctx, bl);
+        pb_stub_set_rate_matrix(ctx, ba2(q, 4, 4, CAML_BA_FLOAT64, CAML_BA_FORTRAN_LAYOUT), ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_set_mode(ctx, Val_int(PB_MODE_PHYLO_CTMC));
+        pb_stub_set_root_frequencies(ctx, ba1(quarter, 4, CAML_BA_FLOAT64));
+        value vpacked = ba2(packed, 4, S / 4, CAML_BA_UINT8, CAML_BA_C_LAYOUT);
+        pb_stub_pin(vpacked);
+        const double t_host = Double_val(pb_stub_loglik_host_packed2(ctx, vpacked, ba1(per_site[0], S, CAML_BA_FLOAT64)));
+        pb_stub_unpin(vpacked);
+        expect_close("loglik_host_packed2 on a pinned Bigarray: site 0", per_site[0][0], -6.157406549426741, 1e-13);
+        expect_true("  path_name / kernel_launches", !strcmp(String_val(pb_stub_path_name(ctx)), "fused4") &&
+                                                     Long_val(pb_stub_kernel_launches(ctx)) > 0);
+        const double t_bytes = Double_val(pb_stub_loglik_host(ctx, ba2(bytes, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT),
+                                                              ba1(per_site[1], S, CAML_BA_FLOAT64)));
+        expect_true("  loglik_host (one byte per site) agrees per site, bit for bit", !memcmp(per_site[0], per_site[1], sizeof per_site[0]));
+        expect_close("  and in total", t_bytes, t_host, 1e-13);
+        pb_stub_set_tips_text(ctx, ba2(text, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT), Val_int(PB_ALPHABET_DNA));
+        pb_stub_set_option(ctx, caml_copy_string("fused_clade_leaves"), caml_copy_double(2.0));
+        const double t_text = Double_val(pb_stub_loglik(ctx, ba1(per_site[2], S, CAML_BA_FLOAT64)));
+        expect_true("set_tips_text + set_option: the same per-site values", fabs(t_text - t_bytes) <= 1e-13 * fabs(t_bytes) && !memcmp(per_site[1], per_site[2], sizeof per_site[1]));
+        EXPECT_RAISES("set_option with an unknown name -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_option(ctx, caml_copy_string("no_such_option"), caml_copy_double(1.0)));
+        pb_stub_set_site_weights(ctx, ba1(w, S, CAML_BA_FLOAT64));
+        double weighted = 0.0;
+        for (int s = 0; s < S; s++) weighted += w[s] * per_site[1][s];
+        expect_close("set_site_weights: total = sum w[s] logL[s]", Double_val(pb_stub_loglik(ctx, ba1(&empty, 0, CAML_BA_FLOAT64))), weighted, 1e-12);
+        pb_stub_set_site_weights(ctx, ba1(&empty, 0, CAML_BA_FLOAT64));
+        pb_stub_set_tip_masks(ctx, ba2(masks, 4, S, CAML_BA_INT64, CAML_BA_C_LAYOUT));
+        pb_stub_loglik(ctx, ba1(per_site[2], S, CAML_BA_FLOAT64));
+        expect_close("set_tip_masks: singleton sets = observed states", per_site[2][0], -6.157406549426741, 1e-13);
+        expect_true("  an all-missing column and a fully ambiguous one give log-likelihood 0", per_site[2][1] == 0.0 && fabs(per_site[2][2]) < 1e-13);
+        expect_close("  every other column as with observed states", per_site[2][S - 1], per_site[1][S - 1], 1e-13);
+        finalise(ctx);
+
+        /* partial re-evaluation: one branch changes, only its path to the root is recomputed */
+        value keep = make_ctx(4, 1, S, 4, PB_FLAG_KEEP_CLV);
+        set_tree4(keep, bl);
+        pb_stub_set_rate_matrix(keep, ba2(q, 4, 4, CAML_BA_FLOAT64, CAML_BA_FORTRAN_LAYOUT), ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_set_mode(keep, Val_int(PB_MODE_PHYLO_CTMC));
+        pb_stub_set_root_frequencies(keep, ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_set_tips(keep, ba2(bytes, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT));
+        pb_stub_loglik(keep, ba1(&empty, 0, CAML_BA_FLOAT64));
+        pb_stub_update_branch_length(keep, Val_int(5), caml_copy_double(0.9));
+        const double t_part = Double_val(pb_stub_loglik(keep, ba1(&empty, 0, CAML_BA_FLOAT64)));
+        const int recomputed = Int_val(pb_stub_nodes_recomputed(keep));
+        bl[5] = 0.9;
+        pb_stub_set_branch_lengths(keep, ba1(bl, 7, CAML_BA_FLOAT64));
+        const double t_full = Double_val(pb_stub_loglik(keep, ba1(&empty, 0, CAML_BA_FLOAT64)));
+        expect_close("update_branch_length: partial re-evaluation = full evaluation", t_part, t_full, 1e-14);
+        expect_true("  only the path to the root was recomputed (2 of 3 internal nodes)", recomputed == 2);
+        static double pm[7 * 16];
+        pb_stub_get_pmatrices(keep, ba1(pm, 7 * 16, CAML_BA_FLOAT64));
+        expect_close("get_pmatrices: P(0.9)(A,A) of the changed branch", pm[5 * 16], 0.25 + 0.75 * exp(-4.0 * 0.9 / 3.0), 1e-13);
+        finalise(keep);
+    }
+
     expect_true("runtime lock: every release paired with an acquire, none across a raise", lock_errors == 0 && !lock_released);
-    expect_true("every context finalised", finalised == 6);
+    expect_true("every context finalised", finalised == 8);
     printf(failures ? "%d FAILED\n" : "all ok\n", failures);
     return failures ? 1 : 0;
 }
