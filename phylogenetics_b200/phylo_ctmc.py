@@ -141,3 +141,69 @@ def conditional_simulation_sites(seed, t, nstates, leaf_state, transition_probab
         ctx.set_root_frequencies(np.asarray(root_frequencies, dtype=np.float64))
         ctx.loglik()
         return flat, ctx.conditional_simulation(seed)
+
+
+def _mask_matrix(flat, nsites, mask_of):
+    """uint64 [nleaves][nsites]: bit k set = state k compatible with the observation; 0 = missing."""
+    masks = np.zeros((flat.nleaves, nsites), dtype=np.uint64)
+    for row, data in enumerate(flat.leaf_data):
+        for s in range(nsites):
+            masks[row, s] = mask_of(data, s)
+    return masks
+
+
+def _pruning_sites_masks(t, nstates, transition_probabilities, mask_of, nsites, root_frequencies, device):
+    flat, _, ctx = _prepare(t, nstates, transition_probabilities, device, False, nsites)
+    with ctx:
+        ctx.set_mode(_lib.PB_MODE_PHYLO_CTMC)
+        ctx.set_tip_masks(_mask_matrix(flat, nsites, mask_of))
+        ctx.set_root_frequencies(root_frequencies)
+        _, per_site = ctx.loglik(per_site=True)
+    return per_site
+
+
+class Missing_values:
+    """Phylo_ctmc.Missing_values (lib/phylo_ctmc.mli:91-128, .ml:145-172): leaves may be unobserved.
+    `leaf_state` returns a state or None; a missing child contributes nothing (no product, no shift) and a site
+    without any observation has log-likelihood 0."""
+
+    @staticmethod
+    def pruning_sites(t, nstates, transition_probabilities, leaf_state, nsites, root_frequencies, device=0):
+        """All sites at once: leaf_state(leaf payload, site) -> int | None."""
+        def mask_of(data, s):
+            st = leaf_state(data, s)
+            if st is None:
+                return 0
+            if not 0 <= st < nstates:
+                raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "leaf state out of range")
+            return 1 << st
+        return _pruning_sites_masks(t, nstates, transition_probabilities, mask_of, nsites, root_frequencies, device)
+
+    @staticmethod
+    def pruning(t, nstates, transition_probabilities, leaf_state, root_frequencies, device=0):
+        """One site, the reference's signature: leaf_state(leaf payload) -> int | None."""
+        return float(Missing_values.pruning_sites(t, nstates, transition_probabilities, lambda l, _s: leaf_state(l), 1,
+                                                  root_frequencies, device=device)[0])
+
+
+class Ambiguous:
+    """Phylo_ctmc.Ambiguous (lib/phylo_ctmc.mli:130-160, .ml:232-302): `leaf_state l i` tells whether state i is
+    compatible with the observation at leaf l; the tip vector is the 0/1 indicator of that set, an empty set is a
+    missing observation."""
+
+    @staticmethod
+    def pruning_sites(t, nstates, transition_probabilities, leaf_state, nsites, root_frequencies, device=0):
+        """All sites at once: leaf_state(leaf payload, site, state) -> bool."""
+        def mask_of(data, s):
+            m = 0
+            for i in range(nstates):
+                if leaf_state(data, s, i):
+                    m |= 1 << i
+            return m
+        return _pruning_sites_masks(t, nstates, transition_probabilities, mask_of, nsites, root_frequencies, device)
+
+    @staticmethod
+    def pruning(t, nstates, transition_probabilities, leaf_state, root_frequencies, device=0):
+        """One site, the reference's signature: leaf_state(leaf payload, state) -> bool."""
+        return float(Ambiguous.pruning_sites(t, nstates, transition_probabilities, lambda l, _s, i: leaf_state(l, i), 1,
+                                             root_frequencies, device=device)[0])

@@ -144,3 +144,60 @@ def test_matrix_decomposition_closure_and_errors():
         phylo_ctmc.pruning(t, 4, lambda l: np.eye(3), lambda leaf: 0, pi)
     with pytest.raises(_lib.PhyloB200InvalidArgument):
         phylo_ctmc.pruning(t, 4, dec, lambda leaf: 5, pi)
+
+
+def test_missing_values_and_ambiguous_mirrors():
+    """Phylo_ctmc.Missing_values.pruning and Phylo_ctmc.Ambiguous.pruning through the host mirror (names and
+    closures as in lib/phylo_ctmc.mli:91-160), against the oracle's restatement of lib/phylo_ctmc.ml:145-172, 280-302,
+    on the 4-leaf tree of tests/expect/phylo_ctmc_conditional_simulation.ml:7-17 and a random 40-leaf tree."""
+    from oracle import linalg_ref as la
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    Q = M.gtr(pi, M.make_symetric(4, lambda a, b: float(a + 7 + b + 7) / 20.0))
+    tp = lambda bl: [("Mat", la.expm(bl * Q))]
+    rng = random.Random(5)
+
+    def both(build):
+        return build(T.leaf, T.branch, T.binary_node), build(R.Leaf, R.Branch, R.binary_node)
+
+    def four(leaf, branch, node):
+        return node(None, branch(0.4, node(None, branch(0.8, leaf("A1")), branch(1.2, leaf("A2")))),
+                    branch(0.1, node(None, branch(0.6, leaf("B")), branch(0.3, leaf("C")))))
+
+    def random_shape(n):
+        shape = list(range(n))
+        while len(shape) > 1:
+            i, j = sorted(rng.sample(range(len(shape)), 2))
+            b = shape.pop(j)
+            a = shape.pop(i)
+            shape.append((a, rng.uniform(0.01, 0.8), b, rng.uniform(0.01, 0.8)))
+        return shape[0]
+
+    shape = random_shape(40)
+
+    def big(leaf, branch, node):
+        def rec(s):
+            if not isinstance(s, tuple):
+                return leaf(s)
+            return node(None, branch(s[1], rec(s[0])), branch(s[3], rec(s[2])))
+        return rec(shape)
+
+    for build, names in ((four, ["A1", "A2", "B", "C"]), (big, list(range(40)))):
+        t, ot = both(build)
+        for trial in range(6):
+            obs = {l: (None if rng.random() < 0.3 else rng.randrange(4)) for l in names}
+            if trial == 0:
+                obs = {l: None for l in names}                    # nothing observed: log-likelihood 0
+            got = phylo_ctmc.Missing_values.pruning(t, 4, tp, lambda l: obs[l], pi)
+            exp = R.missing_values_pruning(ot, 4, tp, lambda l: obs[l], pi)
+            assert (got == 0.0 and exp == 0.0) if trial == 0 else abs(got - exp) <= 1e-10 * abs(exp)
+            sets = {l: {i for i in range(4) if rng.random() < 0.4} for l in names}
+            got = phylo_ctmc.Ambiguous.pruning(t, 4, tp, lambda l, i: i in sets[l], pi)
+            exp = R.ambiguous_pruning(ot, 4, tp, lambda l: (lambda i: i in sets[l]), pi)
+            assert abs(got - exp) <= 1e-10 * max(abs(exp), 1e-300)
+    # the batched forms: one call for all sites
+    t, ot = both(big)
+    nsites = 33
+    obs = [{l: (None if rng.random() < 0.25 else rng.randrange(4)) for l in range(40)} for _ in range(nsites)]
+    got = phylo_ctmc.Missing_values.pruning_sites(t, 4, tp, lambda l, s: obs[s][l], nsites, pi)
+    exp = np.array([R.missing_values_pruning(ot, 4, tp, lambda l: obs[s][l], pi) for s in range(nsites)])
+    np.testing.assert_allclose(got, exp, rtol=1e-10)
