@@ -250,6 +250,18 @@ int pb_transition_matrices_expm(int device, int n, int count, const double *Q,
 int pb_host_reversible_eigensystem(int n, const double *Q, const double *pi,
                                    double *U, double *lambda, double *Uinv);
 
+/* Host-only introspection of the 4-state instruction programs the library compiles for a tree — the plain program
+ * and the one in which clades of up to `max_leaves` leaves are table look-ups — for tests of the host compiler
+ * (tests/test_fused_program_cpu.py interprets them on the CPU against the oracle).  No device is touched.
+ * counts[8] = {instructions, instructions of the tabulated program, tips, packed words per site, stack depth,
+ * inner branches, leaf branches, tabulated clades}; an instruction is 4 ints {code, offA, offB, sh}
+ * (pb_kernels_fused.cuh); tip_order[k] = tip-matrix row consumed k-th; inner_nodes / leaf_nodes map the compact
+ * matrix indices (off / 16) to node ids; a clade is 5 ints {op0, op1, sh0, leaves, first table entry}. */
+int pb_debug_fused_program(int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
+                           const int32_t *tip_row, int ntaxa, int max_leaves, int32_t *counts,
+                           int32_t *ops, int32_t *ops_tab, int cap_ops, int32_t *tip_order,
+                           int32_t *inner_nodes, int32_t *leaf_nodes, int32_t *clades, int cap_clades);
+
 const char *pb_version(void);
 
 #ifdef __cplusplus

@@ -33,7 +33,7 @@ EXPORTS = [
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
-    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_version",
+    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_version",
 ]
 
 
@@ -100,6 +100,7 @@ def _load():
         "pb_transition_matrices_eigen": (ci, [ci, ci, ci, vp, vp, vp, vp, vp]),
         "pb_transition_matrices_expm": (ci, [ci, ci, ci, vp, vp, vp]),
         "pb_host_reversible_eigensystem": (ci, [ci, vp, vp, vp, vp, vp]),
+        "pb_debug_fused_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, vp, vp, ci]),
         "pb_version": (ctypes.c_char_p, []),
     }
     for name, (res, args) in sig.items():

@@ -3,6 +3,8 @@
 #include "../../include/phylo_b200.h"
 
 #include <algorithm>
+#include <cstring>
+#include <memory>
 #include <cmath>
 #include <atomic>
 #include <cstdio>
@@ -112,6 +114,7 @@ struct pb_ctx {
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
     std::vector<FusedOp2> fprog_tab;       // fprog_c with the small clades turned into table look-ups (FOP_CHERRY)
     std::vector<pbk::CladeTab> clades;     // the tabulated clades of fprog_tab
+    bool plan_only = false;                // a context without a device, used by pb_debug_fused_program only
     bool tables_stale = true;              // the tables must be rebuilt before the next launch (new program variant)
     int tab_leaves = -1;                   // the clade size limit fprog_tab was built for (-1: not built)
     int ntab = 0;                          // table entries per category
@@ -588,6 +591,8 @@ int compile_tree(pb_ctx* c)
         c->fprog_version = next_version++;
     }
 
+    if (c->plan_only) return PB_OK;          // pb_debug_fused_program: host-side compilation only, no device
+
     // upload
     PB_CUDA(c, c->d_fprog_d.ensure(std::max<size_t>(c->fprog_d.size(), 1)));
     PB_CUDA(c, c->d_mlist.ensure(std::max<size_t>(c->mlist.size(), 1)));
@@ -839,7 +844,7 @@ int build_table_program(pb_ctx* c, int max_leaves)
     }
     c->tab_leaves = max_leaves;
     c->tables_stale = true;
-    if (!c->clades.empty()) {
+    if (!c->clades.empty() && !c->plan_only) {
         PB_CUDA(c, c->d_fprog_tab.ensure(c->fprog_tab.size()));
         PB_CUDA(c, c->d_clades.ensure(c->clades.size()));
         // (pageable host vectors: the copies complete before the calls return)
@@ -1620,6 +1625,58 @@ int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const d
     c->psrc = PSRC_EIGEN;
     c->p_dirty = true;
     c->all_dirty = true;
+    return PB_OK;
+}
+
+// Host-only introspection of what compile_tree / build_table_program produce for a tree (4 states): no device is
+// touched, nothing is evaluated.  The tests interpret the programs on the CPU against the oracle.
+int pb_debug_fused_program(int nnodes, int root, const int32_t* child_ptr, const int32_t* child_idx, const int32_t* tip_row,
+                           int ntaxa, int max_leaves, int32_t* counts, int32_t* ops, int32_t* ops_tab, int cap_ops,
+                           int32_t* tip_order, int32_t* inner_nodes, int32_t* leaf_nodes, int32_t* clades, int cap_clades)
+{
+    if (!child_ptr || !child_idx || !tip_row || !counts || !ops || !ops_tab || !tip_order || !inner_nodes || !leaf_nodes ||
+        !clades || nnodes < 2 || root < 0 || root >= nnodes || ntaxa < 1 || child_ptr[0] != 0 || child_ptr[nnodes] != nnodes - 1)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_fused_program: bad arguments");
+    std::unique_ptr<pb_ctx> c(new pb_ctx());
+    c->plan_only = true;
+    c->n = 4;
+    c->ncat = 1;
+    c->ntaxa = ntaxa;
+    c->nsites = 1;
+    c->spad = 1024;
+    c->nnodes = nnodes;
+    c->root = root;
+    c->child_ptr.assign(child_ptr, child_ptr + nnodes + 1);
+    c->child_idx.assign(child_idx, child_idx + nnodes - 1);
+    c->tip_row.assign(tip_row, tip_row + nnodes);
+    c->parent.assign(nnodes, -1);
+    for (int v = 0; v < nnodes; v++)
+        for (int k = child_ptr[v]; k < child_ptr[v + 1]; k++) {
+            const int ch = child_idx[k];
+            if (ch < 0 || ch >= nnodes || ch == root || c->parent[ch] != -1)
+                return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_fused_program: bad child index");
+            c->parent[ch] = v;
+        }
+    int rc = compile_tree(c.get());
+    if (rc == PB_OK) rc = build_table_program(c.get(), max_leaves);
+    if (rc != PB_OK) return fail(nullptr, rc, c->err);
+    if ((int)c->fprog_c.size() > cap_ops || (int)c->clades.size() > cap_clades)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_fused_program: output buffers too small");
+    static_assert(sizeof(FusedOp2) == 4 * sizeof(int32_t), "one instruction is four 32-bit words");
+    std::memcpy(ops, c->fprog_c.data(), c->fprog_c.size() * sizeof(FusedOp2));
+    std::memcpy(ops_tab, c->fprog_tab.data(), c->fprog_tab.size() * sizeof(FusedOp2));
+    std::copy(c->tip_order.begin(), c->tip_order.end(), tip_order);
+    std::copy(c->inner_nodes.begin(), c->inner_nodes.end(), inner_nodes);
+    std::copy(c->leaf_nodes.begin(), c->leaf_nodes.end(), leaf_nodes);
+    for (size_t i = 0; i < c->clades.size(); i++) {
+        const pbk::CladeTab& t = c->clades[i];
+        const int32_t row[5] = {t.op0, t.op1, t.sh0, t.k, t.ent0};
+        std::copy(row, row + 5, clades + 5 * i);
+    }
+    const int32_t cnt[8] = {(int32_t)c->fprog_c.size(), (int32_t)c->fprog_tab.size(), (int32_t)c->tip_order.size(), c->fwords,
+                            std::max(c->fstack, 1), (int32_t)c->inner_nodes.size(), (int32_t)c->leaf_nodes.size(),
+                            (int32_t)c->clades.size()};
+    std::copy(cnt, cnt + 8, counts);
     return PB_OK;
 }
 
