@@ -175,3 +175,23 @@ def test_bad_arguments_are_reported():
     p = z.ctypes.data_as(ctypes.c_void_p)
     assert _lib.lib.pb_debug_fused_program(1, 0, p, p, p, 1, 2, p, p, p, 8, p, p, p, p, 8) == _lib.PB_ERR_INVALID_ARG
     assert b"bad arguments" in _lib.lib.pb_last_error(None)
+
+
+def test_random_shapes_property():
+    """hypothesis: random arities, sizes, clade limits; the interpreted programs equal the oracle every time."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), st.integers(3, 140), st.integers(0, 6), st.booleans())
+    def prop(seed, nleaves, max_leaves, kary):
+        rng = np.random.default_rng(seed)
+        if kary:
+            t = random_kary_tree(rng, nleaves)
+        else:
+            t = synthetic.random_binary_tree(rng, nleaves)
+        flat = T.flatten(t)
+        Q, pi = synthetic.random_gtr(rng, 10.0)
+        P = synthetic.host_transition_matrices(Q, pi, flat.branch_lengths(float), np.ones(1))
+        tips = synthetic.simulate_alignment(rng, flat, P, pi, 64, np.ones(1))
+        check(flat, P[0], pi, tips, max_leaves)
+    prop()
