@@ -256,7 +256,10 @@ int pb_host_reversible_eigensystem(int n, const double *Q, const double *pi,
  * counts[8] = {instructions, instructions of the tabulated program, tips, packed words per site, stack depth,
  * inner branches, leaf branches, tabulated clades}; an instruction is 4 ints {code, offA, offB, sh}
  * (pb_kernels_fused.cuh); tip_order[k] = tip-matrix row consumed k-th; inner_nodes / leaf_nodes map the compact
- * matrix indices (off / 16) to node ids; a clade is 5 ints {op0, op1, sh0, leaves, first table entry}. */
+ * matrix indices (off / 16) to node ids; a clade is 6 ints {op0, op1, sh0, leaves, first table entry, pre}.
+ * max_leaves | 0x100 plans the variant in which a table holds P . v for its consumer (pre = that inner matrix's
+ * offset, else -1; the consumer carries the flag 0x200 / 0x400 for operand A / B): a kernel build option that is
+ * off by default (FUSED_PREAPPLY, pb_kernels_fused.cuh). */
 int pb_debug_fused_program(int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
                            const int32_t *tip_row, int ntaxa, int max_leaves, int32_t *counts,
                            int32_t *ops, int32_t *ops_tab, int cap_ops, int32_t *tip_order,

@@ -114,6 +114,8 @@ struct pb_ctx {
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
     std::vector<FusedOp2> fprog_tab;       // fprog_c with the small clades turned into table look-ups (FOP_CHERRY)
     std::vector<pbk::CladeTab> clades;     // the tabulated clades of fprog_tab
+    int fused_preapply = 0;                // option "fused_preapply" (only in a build with -DFUSED_PREAPPLY=1)
+    bool tab_preapply = false;             // what fprog_tab was built with
     bool plan_only = false;                // a context without a device, used by pb_debug_fused_program only
     bool tables_stale = true;              // the tables must be rebuilt before the next launch (new program variant)
     int tab_leaves = -1;                   // the clade size limit fprog_tab was built for (-1: not built)
@@ -770,7 +772,7 @@ bool fused_const_ok(const pb_ctx* c)
 // its leaves are consumed back to back from ONE packed-tip word: the walk below keeps, for the accumulator and
 // every stack entry, the instruction range that produced it, how many tips it consumed and where the first one
 // sits in the window; a window load (FOP_LOADW) closes everything live for further merging.
-int build_table_program(pb_ctx* c, int max_leaves)
+int build_table_program(pb_ctx* c, int max_leaves, bool preapply = false)
 {
     struct Sym { int start, k, sh0; bool open; };
     struct Cand { int start, end, k, sh0; };
@@ -828,7 +830,7 @@ int build_table_program(pb_ctx* c, int max_leaves)
         if (next < kept.size() && kept[next].start == i) {
             const Cand& kq = kept[next++];
             pbk::CladeTab t{};
-            t.op0 = kq.start; t.op1 = kq.end; t.sh0 = kq.sh0; t.k = kq.k; t.ent0 = c->ntab;
+            t.op0 = kq.start; t.op1 = kq.end; t.sh0 = kq.sh0; t.k = kq.k; t.ent0 = c->ntab; t.pre = -1;
             c->clades.push_back(t);
             FusedOp2 o;
             o.code = pbk::FOP_CHERRY | (prog[kq.end].code & pbk::FOP_PUSH_AFTER);
@@ -841,6 +843,35 @@ int build_table_program(pb_ctx* c, int max_leaves)
             continue;
         }
         c->fprog_tab.push_back(prog[i]);
+    }
+    if (preapply) {
+        // Which instruction consumes each table value, and does it apply a branch matrix to it first?  Walk the
+        // program with, for the accumulator and every stack entry, the index of the clade whose raw table value it
+        // still is (-1 otherwise).  FOP_ACC_POP / FOP_APPLY_MUL_TIP apply a matrix to such an operand: the table gets
+        // that matrix (CladeTab::pre) and the instruction a flag to skip the product.
+        int acc = -1, next_clade = 0;
+        std::vector<int> stack;
+        for (FusedOp2& o : c->fprog_tab) {
+            const int code = o.code & 0xff;
+            if (code == pbk::FOP_CHERRY) {
+                acc = next_clade++;
+            } else if (code == pbk::FOP_ACC_POP) {
+                const int b = stack.back();
+                stack.pop_back();
+                if (acc >= 0) { c->clades[acc].pre = o.offA; o.code |= pbk::FOP_PRE_A; }
+                if (b >= 0) { c->clades[b].pre = o.offB; o.code |= pbk::FOP_PRE_B; }
+                acc = -1;
+            } else if (code == pbk::FOP_APPLY_MUL_TIP) {
+                if (acc >= 0) { c->clades[acc].pre = o.offA; o.code |= pbk::FOP_PRE_A; }
+                acc = -1;
+            } else if (code == pbk::FOP_POP_MUL) {
+                stack.pop_back();
+                acc = -1;
+            } else if (code != pbk::FOP_LOADW && code != pbk::FOP_PUSH) {
+                acc = -1;                              // FOP_TIP_TIP, FOP_TIP, FOP_MUL_TIP, FOP_APPLY, FOP_ROOT: no table value survives
+            }
+            if (o.code & pbk::FOP_PUSH_AFTER) stack.push_back(acc);
+        }
     }
     c->tab_leaves = max_leaves;
     c->tables_stale = true;
@@ -882,12 +913,14 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     // (a table of 4^k entries is only worth building when the alignment has many more sites than that)
     int want_leaves = (c->fused_cherry && c->fused_pow2) ? (c->fused_triple ? c->fused_clade_leaves : 2) : 0;
     while (!c->fused_clade_force && want_leaves > 2 && (int64_t)8 << (2 * want_leaves) > c->nsites) want_leaves--;
-    if (c->tab_leaves != want_leaves) {
-        const int rc = build_table_program(c, want_leaves);
+    const bool want_pre = FUSED_PREAPPLY && c->fused_preapply;      // (a kernel build option, off by default)
+    if (c->tab_leaves != want_leaves || c->tab_preapply != want_pre) {
+        const int rc = build_table_program(c, want_leaves, want_pre);
         if (rc != PB_OK) return rc;
+        c->tab_preapply = want_pre;
     }
     const bool tabulated = !c->clades.empty();
-    const uint64_t want_version = c->fprog_version * 8 + (uint64_t)want_leaves;
+    const uint64_t want_version = c->fprog_version * 16 + (uint64_t)want_leaves * 2 + (want_pre ? 1 : 0);
     const FusedOp2* prog = tabulated ? c->d_fprog_tab.p : c->d_fprog_c.p;
     c->fprog_bank_nops = (int)(tabulated ? c->fprog_tab.size() : c->fprog_c.size());
     if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != want_version) {
@@ -1658,7 +1691,7 @@ int pb_debug_fused_program(int nnodes, int root, const int32_t* child_ptr, const
             c->parent[ch] = v;
         }
     int rc = compile_tree(c.get());
-    if (rc == PB_OK) rc = build_table_program(c.get(), max_leaves);
+    if (rc == PB_OK) rc = build_table_program(c.get(), max_leaves & 0xff, (max_leaves & 0x100) != 0);
     if (rc != PB_OK) return fail(nullptr, rc, c->err);
     if ((int)c->fprog_c.size() > cap_ops || (int)c->clades.size() > cap_clades)
         return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_fused_program: output buffers too small");
@@ -1670,8 +1703,8 @@ int pb_debug_fused_program(int nnodes, int root, const int32_t* child_ptr, const
     std::copy(c->leaf_nodes.begin(), c->leaf_nodes.end(), leaf_nodes);
     for (size_t i = 0; i < c->clades.size(); i++) {
         const pbk::CladeTab& t = c->clades[i];
-        const int32_t row[5] = {t.op0, t.op1, t.sh0, t.k, t.ent0};
-        std::copy(row, row + 5, clades + 5 * i);
+        const int32_t row[6] = {t.op0, t.op1, t.sh0, t.k, t.ent0, t.pre};
+        std::copy(row, row + 6, clades + 6 * i);
     }
     const int32_t cnt[8] = {(int32_t)c->fprog_c.size(), (int32_t)c->fprog_tab.size(), (int32_t)c->tip_order.size(), c->fwords,
                             std::max(c->fstack, 1), (int32_t)c->inner_nodes.size(), (int32_t)c->leaf_nodes.size(),
@@ -2036,6 +2069,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const = iv != 0;
     } else if (k == "fused_triple") {
         c->fused_triple = iv != 0;
+    } else if (k == "fused_preapply") {
+        if (iv != 0 && !FUSED_PREAPPLY) return fail(c, PB_ERR_INVALID_ARG, "fused_preapply: this build has no FUSED_PREAPPLY kernels");
+        c->fused_preapply = iv != 0;
     } else if (k == "fused_clade_force") {
         c->fused_clade_force = iv != 0;
     } else if (k == "fused_clade_leaves") {

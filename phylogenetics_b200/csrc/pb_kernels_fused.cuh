@@ -302,6 +302,15 @@ __device__ __forceinline__ void lds_col4(unsigned addr, int s, double (&c)[4])
 }
 
 constexpr int FOP_PUSH_AFTER = 0x100;   // flag in the code word: push ACC after the instruction
+// FUSED_PREAPPLY (off by default; host side checked on the CPU, kernel side not measured yet): a tabulated clade is
+// consumed by exactly one parent instruction, which first applies the clade's branch matrix to it; the table can
+// hold P . v instead of v and the parent skips that product.  The flags say which operand of FOP_ACC_POP /
+// FOP_APPLY_MUL_TIP already carries its matrix.
+constexpr int FOP_PRE_A = 0x200;        // operand A (the accumulator) is a pre-applied table value
+constexpr int FOP_PRE_B = 0x400;        // operand B (the popped value) is a pre-applied table value
+#ifndef FUSED_PREAPPLY
+#define FUSED_PREAPPLY 0
+#endif
 
 // Persistent kernel: grid = (blocks_x, ncat); each block stages the P matrices of its category
 // once and then loops over tiles of BLOCK*SPT sites.
@@ -515,7 +524,9 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
 struct CladeTab {
     int op0, op1;      // the clade's instructions in the untabulated program (inclusive)
     int sh0, k;        // bit offset of its first tip in the window, number of leaves
-    int ent0, pad[3];
+    int ent0;
+    int pre;           // >= 0: the table stores P[inner pre / 16] . v instead of v (FUSED_PREAPPLY), else -1
+    int pad[2];
 };
 
 __global__ void __launch_bounds__(256)
@@ -586,6 +597,12 @@ build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict
                 sp++;
             }
         }
+        if (tb.pre >= 0) {                                      // the consumer's branch matrix, applied here once
+            double y[4];
+            matvec4(Pc + (size_t)inner_nodes[tb.pre / 16] * 16, v, y);
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = y[i];
+        }
         const size_t e = (size_t)c * ntab + tb.ent0 + idx;
 #pragma unroll
         for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
@@ -651,6 +668,12 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                 for (int q = 0; q < SPT; q++) {
                     double y[4], t[4];
                     lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
+#if FUSED_PREAPPLY
+                    if (opw.x & FOP_PRE_A) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) y[i] = v[q][i];
+                    } else
+#endif
                     matvec4c(cbase + offA, v[q], y);
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
@@ -663,8 +686,23 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     double x[4], y[4], z[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+#if FUSED_PREAPPLY
+                    if (opw.x & FOP_PRE_A) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) y[i] = v[q][i];
+                    } else {
+                        matvec4c(cbase + offA, v[q], y);
+                    }
+                    if (opw.x & FOP_PRE_B) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) z[i] = x[i];
+                    } else {
+                        matvec4c(cbase + offB, x, z);
+                    }
+#else
                     matvec4c(cbase + offA, v[q], y);
                     matvec4c(cbase + offB, x, z);
+#endif
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
                 }

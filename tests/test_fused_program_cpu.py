@@ -18,10 +18,10 @@ from oracle import c_oracle as C
 from phylogenetics_b200 import _lib, synthetic, tree as T
 
 TIP_TIP, TIP, APPLY, MUL_TIP, PUSH, POP_MUL, APPLY_MUL_TIP, ROOT, LOADW, ACC_POP, CHERRY = range(11)
-PUSH_AFTER = 0x100
+PUSH_AFTER, PRE_A, PRE_B = 0x100, 0x200, 0x400
 
 
-def compile_program(flat, ntaxa, max_leaves):
+def compile_program(flat, ntaxa, max_leaves, preapply=False):
     nn = flat.nnodes
     cap = 8 * nn + 64
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -29,9 +29,10 @@ def compile_program(flat, ntaxa, max_leaves):
     counts = np.zeros(8, np.int32)
     ops, ops_tab = np.zeros((cap, 4), np.int32), np.zeros((cap, 4), np.int32)
     order, inner, leaf = (np.zeros(nn, np.int32) for _ in range(3))
-    clades = np.zeros((nn, 5), np.int32)
+    clades = np.zeros((nn, 6), np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = _lib.lib.pb_debug_fused_program(nn, int(flat.root), p(child_ptr), p(child_idx), p(tip_row), ntaxa, max_leaves,
+    rc = _lib.lib.pb_debug_fused_program(nn, int(flat.root), p(child_ptr), p(child_idx), p(tip_row), ntaxa,
+                                         max_leaves | (0x100 if preapply else 0),
                                          p(counts), p(ops), p(ops_tab), cap, p(order), p(inner), p(leaf), p(clades), nn)
     assert rc == 0, _lib.lib.pb_last_error(None)
     nops, nops_tab, ntips, nwords, stack, ninner, nleaf, nclades = (int(x) for x in counts)
@@ -72,9 +73,10 @@ def run(ops, prog, P, pi, windows, table=None, max_stack=None):
         elif code == POP_MUL:
             acc = stack.pop() * acc
         elif code == APPLY_MUL_TIP:
-            acc = (acc @ inner(offA).T) * col(offB, shB)
+            acc = (acc if code_w & PRE_A else acc @ inner(offA).T) * col(offB, shB)
         elif code == ACC_POP:
-            acc = (acc @ inner(offA).T) * (stack.pop() @ inner(offB).T)
+            x = stack.pop()
+            acc = (acc if code_w & PRE_A else acc @ inner(offA).T) * (x if code_w & PRE_B else x @ inner(offB).T)
         elif code == CHERRY:
             acc = table(offA, ((cur >> np.uint64(shA)) & np.uint64(offB)).astype(int))
         elif code == ROOT:
@@ -93,12 +95,13 @@ def run(ops, prog, P, pi, windows, table=None, max_stack=None):
 def clade_table(prog, P, pi):
     """entry -> vector, by interpreting each clade's instruction range on the synthetic window idx << sh0."""
     tabs = {}
-    for op0, op1, sh0, k, ent0 in prog["clades"]:
+    for op0, op1, sh0, k, ent0, pre in prog["clades"]:
         idx = np.arange(4 ** k, dtype=np.uint64)
         rng_ops = prog["ops"][op0:op1 + 1].copy()
         rng_ops[-1, 0] &= ~PUSH_AFTER                        # the last instruction's push stays in the program
         assert not (rng_ops[:, 0] & 0xff == LOADW).any()     # a clade lives in one window word
-        tabs[int(ent0)] = run(rng_ops, prog, P, pi, (idx << np.uint64(sh0))[None, :])
+        v = run(rng_ops, prog, P, pi, (idx << np.uint64(sh0))[None, :])
+        tabs[int(ent0)] = v if pre < 0 else v @ P[prog["inner"][pre // 16]].T      # the consumer's branch matrix
     return lambda ent0, i: tabs[int(ent0)][i]
 
 
@@ -116,8 +119,8 @@ def random_kary_tree(rng, nleaves):
     return items[0]
 
 
-def check(flat, P, pi, tips, max_leaves):
-    prog = compile_program(flat, tips.shape[0], max_leaves)
+def check(flat, P, pi, tips, max_leaves, preapply=False):
+    prog = compile_program(flat, tips.shape[0], max_leaves, preapply)
     assert sorted(prog["order"]) == list(range(tips.shape[0]))          # every tip consumed exactly once
     assert prog["nwords"] == (tips.shape[0] + 31) // 32
     win = windows_of(prog, tips)
@@ -129,8 +132,11 @@ def check(flat, P, pi, tips, max_leaves):
     ks = [int(k) for k in prog["clades"][:, 3]]
     assert all(2 <= k <= max(max_leaves, 2) for k in ks) if max_leaves >= 2 else not ks
     # look-ups replace instructions: the tabulated program is shorter by the clades' instructions minus one each
-    saved = sum(int(op1 - op0) for op0, op1, _, _, _ in prog["clades"])
+    saved = sum(int(op1 - op0) for op0, op1, _, _, _, _ in prog["clades"])
     assert len(prog["ops_tab"]) == len(prog["ops"]) - saved
+    # pre-applied matrices: one flag in the program per table that carries its consumer's matrix, none otherwise
+    flags = sum(int(bool(w & PRE_A)) + int(bool(w & PRE_B)) for w in prog["ops_tab"][:, 0])
+    assert flags == int((prog["clades"][:, 5] >= 0).sum()) and (preapply or flags == 0)
     return prog
 
 
@@ -139,6 +145,7 @@ def test_binary_trees(ntaxa, max_leaves):
     case = cases.make_case("prog", "gtr", ntaxa, 300, ncat=1, seed=ntaxa)
     P = case.host_P()[0]
     prog = check(case.flat, P, case.pi, case.tips, max_leaves)
+    check(case.flat, P, case.pi, case.tips, max_leaves, preapply=True)
     if max_leaves >= 2 and ntaxa >= 33:
         assert len(prog["clades"]) >= ntaxa // 8          # a birth-death tree has about n/3 cherries
 
@@ -152,7 +159,9 @@ def test_kary_and_unary_trees(seed):
     bl = flat.branch_lengths(float)
     P = synthetic.host_transition_matrices(Q, pi, bl, np.ones(1))
     tips = synthetic.simulate_alignment(rng, flat, P, pi, 200, np.ones(1))
-    check(flat, P[0], pi, tips, int(rng.integers(2, 7)))
+    k = int(rng.integers(2, 7))
+    check(flat, P[0], pi, tips, k)
+    check(flat, P[0], pi, tips, k, preapply=True)
 
 
 def test_caterpillar_crosses_word_boundaries():
@@ -182,8 +191,8 @@ def test_random_shapes_property():
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=40, deadline=None, derandomize=True)
-    @given(st.integers(0, 10 ** 6), st.integers(3, 140), st.integers(0, 6), st.booleans())
-    def prop(seed, nleaves, max_leaves, kary):
+    @given(st.integers(0, 10 ** 6), st.integers(3, 140), st.integers(0, 6), st.booleans(), st.booleans())
+    def prop(seed, nleaves, max_leaves, kary, preapply):
         rng = np.random.default_rng(seed)
         if kary:
             t = random_kary_tree(rng, nleaves)
@@ -193,5 +202,16 @@ def test_random_shapes_property():
         Q, pi = synthetic.random_gtr(rng, 10.0)
         P = synthetic.host_transition_matrices(Q, pi, flat.branch_lengths(float), np.ones(1))
         tips = synthetic.simulate_alignment(rng, flat, P, pi, 64, np.ones(1))
-        check(flat, P[0], pi, tips, max_leaves)
+        check(flat, P[0], pi, tips, max_leaves, preapply)
     prop()
+
+
+def test_preapplied_matrices_at_the_bench_shape():
+    """The c2 bench tree with clades of up to 5 leaves: 32 look-ups, and with their consumers' matrices folded into
+    the tables 32 of the 76 remaining matrix-vector products disappear."""
+    case = cases.make_case("c2", "gtr", 128, 64, ncat=4, seed=100)
+    prog = check(case.flat, case.host_P()[0], case.pi, case.tips, 5, preapply=True)
+    codes = prog["ops_tab"][:, 0]
+    matvecs = sum(2 - bool(w & PRE_A) - bool(w & PRE_B) for w in codes if w & 0xff == ACC_POP) + \
+        sum(1 - bool(w & PRE_A) for w in codes if w & 0xff == APPLY_MUL_TIP)
+    assert (codes & 0xff == CHERRY).sum() == 32 and matvecs == 76 - 32
