@@ -466,6 +466,15 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
             ctx.set_option("fused_clade_leaves", leaves)
             total5, per_site5 = ctx.loglik(per_site=True)
             assert total5 == total and np.array_equal(per_site5, per_site), leaves
+        try:                                                # tables carrying their consumer's matrix: only in a build
+            ctx.set_option("fused_preapply", 1)             # with -DFUSED_PREAPPLY=1
+        except _lib.PhyloB200InvalidArgument:
+            pass
+        else:
+            ctx.set_option("fused_clade_leaves", 5)
+            total6, per_site6 = ctx.loglik(per_site=True)
+            assert total6 == total and np.array_equal(per_site6, per_site)
+            ctx.set_option("fused_preapply", 0)
         ctx.set_option("fused_triple", 0)                   # cherries only
         total5, per_site5 = ctx.loglik(per_site=True)
         assert total5 == total and np.array_equal(per_site5, per_site)
