@@ -359,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
         bytes_eval = algorithmic_bytes_per_site(n, ncat, ntaxa) * nsites
         flops_eval = algorithmic_flops_per_site(n, ncat, ntaxa) * nsites
         achieved = bytes_eval / (prune_avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "true_bound": {"fused4": "fp64 pipe", "fused_dmma": "fp64 tensor pipe"}.get(ctx.path_name, "hbm"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        roof = {"bound": "hbm", "true_bound": {"fused4": "fp64 pipe + L1 table gathers", "fused_dmma": "fp64 tensor pipe"}.get(ctx.path_name, "hbm"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": "of " + peak_kind,
                 "kernel": kernel_name, "launches_per_step": nlaunch_prune,
@@ -371,7 +371,8 @@ def run_ours(args, rank, world, local_rank):
                 "fp64_frac": flops_eval / (prune_avg_ms * 1e-3) / 1e12 / FP64_DFMA_PEAK_TFLOPS,
                 "note": ("fused4 keeps conditional likelihoods on chip: it moves ntaxa+8C bytes/site of HBM, "
                          "so against the level-scheduled algorithmic bytes the fraction can exceed 1; its own "
-                         "bound is the FP64 pipe" if ctx.path_name in ("fused4", "fused_dmma") else
+                         "bounds are the FP64 pipe and, since small clades are table look-ups, the L1 gather path "
+                         "(profiles/r01n_ncu_full_fused4c_256x4_pow2_clades5.txt)" if ctx.path_name in ("fused4", "fused_dmma") else
                          "level-scheduled: every inner CLV written once and read once")}
         if ctx.path_name == "fused_dmma":
             # dense alphabets on the FP64 tensor cores: the roofline is the DMMA pipe.  Peak = this pool's
