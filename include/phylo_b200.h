@@ -168,6 +168,11 @@ int pb_loglik_host(pb_ctx *ctx, const uint8_t *states, int64_t ld, double *total
 /* The same from a 2-bit packed host alignment (see pb_set_tips_packed2).  The alignment stays resident 2-bit
  * packed; the byte-per-site matrix other entry points read is expanded on the device when one of them needs it. */
 int pb_loglik_host_packed2(pb_ctx *ctx, const uint8_t *packed, int64_t ld, double *total, double *per_site);
+/* Non-blocking form of the two calls above (packed2 != 0: the 2-bit layout): copies, pruning and reduction are
+ * enqueued and the call returns; the caller may queue more work behind it on the context's stream (e.g. the
+ * all-reduce of the device-resident total, pb_result_device_ptrs) before it waits in pb_loglik_fetch.  `states`
+ * must stay valid and unchanged until pb_loglik_fetch (or a synchronisation of the stream) returns. */
+int pb_loglik_host_enqueue(pb_ctx *ctx, const uint8_t *states, int64_t ld, int packed2);
 /* Page-lock / release a caller-owned host buffer (e.g. the payload of an OCaml Bigarray, which lives outside the
  * OCaml heap and does not move) so that the chunked copies above are asynchronous.  No context: the message of a
  * failure is pb_last_error(NULL). */
@@ -203,9 +208,10 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
  *   matrices through the constant bank), "fused_const_cats" (categories per launch), "fused_pow2" (1 (default):
  *   exact power-of-two scale factors; 0: the reference's factor 1/max v), "fused_cherry" (tabulate the nodes
- *   with two leaf children), "fused_clade_leaves" (2..6, default 5: the largest clade whose 4^k
+ *   with two leaf children), "fused_clade_leaves" (2..8, default 5: the largest clade whose 4^k
  *   possible values are tabulated the same way; fewer when the alignment has fewer than 8 * 4^k sites unless
- *   "fused_clade_force"), "fused_triple" (0: cherries only).
+ *   "fused_clade_force"), "fused_triple" (0: cherries only), "fused_reduced" (1 (default): the program over the reduced tree, kernel fused4t;
+ *   0: look-ups inside the full program, kernel fused4c).
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
@@ -264,6 +270,23 @@ int pb_debug_fused_program(int nnodes, int root, const int32_t *child_ptr, const
                            const int32_t *tip_row, int ntaxa, int max_leaves, int32_t *counts,
                            int32_t *ops, int32_t *ops_tab, int cap_ops, int32_t *tip_order,
                            int32_t *inner_nodes, int32_t *leaf_nodes, int32_t *clades, int cap_clades);
+
+/* The same for the program over the REDUCED tree, the default 4-state program (kernel fused4t): leaves of the reduced
+ * tree are the tabulated clades (every maximal clade of at most `max_leaves` leaves) and the loose tips; a table value
+ * is an operand of its parent's instruction.  counts[8] = {instructions, instructions of all clade ranges, packed-tip
+ * slots, packed words per site, stack depth, inner matrices applied, loose-tip matrices, clades}; slot_rows[s] = the
+ * tip-matrix row whose 2-bit state sits in slot s (32 slots per 64-bit word; -1 = padding), XORed with the state of
+ * row slot_xor_rows[s] when that is >= 0 (the tips of a clade but the first are stored as differences from the first,
+ * so that a table's most frequent entries are neighbours); ops address matrices by
+ * compact index * 16 into mat_nodes / leaf_nodes and tables by first entry (sh = shA | shB << 8 | bitsA << 16 |
+ * bitsB << 24); clade_ops address matrices by node id * 16 and tips by 2 * (ordinal within the clade); a clade is
+ * 6 ints {op0, op1 (range in clade_ops), 1 if its index is difference-coded, leaves, first table entry, pre = node id * 16 of the branch matrix the
+ * table carries, or -1 at the root}. */
+int pb_debug_reduced_program(int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
+                             const int32_t *tip_row, int ntaxa, int max_leaves, int32_t *counts,
+                             int32_t *ops, int cap_ops, int32_t *clade_ops, int cap_clade_ops,
+                             int32_t *slot_rows, int32_t *slot_xor_rows, int cap_slots, int32_t *mat_nodes, int32_t *leaf_nodes,
+                             int32_t *clades, int cap_clades);
 
 const char *pb_version(void);
 

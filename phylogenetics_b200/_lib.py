@@ -28,12 +28,12 @@ PB_ALPHABET_DNA, PB_ALPHABET_AMINO_ACID, PB_ALPHABET_CODON = 0, 1, 2
 # Every symbol include/phylo_b200.h declares (tests check the .so exports them all).
 EXPORTS = [
     "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
-    "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tips_packed2", "pb_loglik_host_packed2", "pb_pin_host_memory", "pb_unpin_host_memory", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
+    "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tips_packed2", "pb_loglik_host_packed2", "pb_loglik_host_enqueue", "pb_pin_host_memory", "pb_unpin_host_memory", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
-    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_version",
+    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_version",
 ]
 
 
@@ -83,6 +83,7 @@ def _load():
         "pb_loglik": (ci, [vp, vp, vp]),
         "pb_loglik_host": (ci, [vp, vp, i64, vp, vp]),
         "pb_loglik_host_packed2": (ci, [vp, vp, i64, vp, vp]),
+        "pb_loglik_host_enqueue": (ci, [vp, vp, i64, ci]),
         "pb_pin_host_memory": (ci, [vp, ctypes.c_size_t]),
         "pb_unpin_host_memory": (ci, [vp]),
         "pb_loglik_enqueue": (ci, [vp]),
@@ -101,6 +102,7 @@ def _load():
         "pb_transition_matrices_expm": (ci, [ci, ci, ci, vp, vp, vp]),
         "pb_host_reversible_eigensystem": (ci, [ci, vp, vp, vp, vp, vp]),
         "pb_debug_fused_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, vp, vp, ci]),
+        "pb_debug_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, ci]),
         "pb_version": (ctypes.c_char_p, []),
     }
     for name, (res, args) in sig.items():

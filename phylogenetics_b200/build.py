@@ -27,18 +27,23 @@ def _newest_source_mtime():
     return m
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
-        return OUT
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out` build a VARIANT of the library beside the shipped one (A/B measurements: load it with
+    PHYLO_B200_LIB=<out>, tools/ab_lib.py)."""
+    out = out or OUT
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_source_mtime():
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(OUT)
+    argv = sys.argv[1:]
+    defs = [argv[i + 1] for i, a in enumerate(argv) if a == "--define"]
+    outp = next((argv[i + 1] for i, a in enumerate(argv) if a == "--out"), None)
+    print(build(force="--force" in argv, verbose="--verbose" in argv, defines=defs, out=outp))

@@ -118,12 +118,28 @@ struct pb_ctx {
     bool tab_preapply = false;             // what fprog_tab was built with
     bool plan_only = false;                // a context without a device, used by pb_debug_fused_program only
     bool tables_stale = true;              // the tables must be rebuilt before the next launch (new program variant)
+    int tab_variant = 0;                   // whose tables d_cherry_* hold: 1 = fused4c (look-ups in the full program), 2 = fused4t
     int tab_leaves = -1;                   // the clade size limit fprog_tab was built for (-1: not built)
     int ntab = 0;                          // table entries per category
     int fprog_bank_nops = 0;               // length of the program variant launch_fused4c put in the constant bank
     int fused_triple = 1;                  // option "fused_triple": 0 = tabulate cherries only
     int fused_clade_force = 0;             // option "fused_clade_force" (test hook): tabulate up to the limit however few the sites
     int fused_clade_leaves = 5;            // option "fused_clade_leaves": largest tabulated clade (2..6 leaves)
+    // fused4t: the program over the reduced tree (build_reduced_program)
+    int fused_reduced = 1;                 // option "fused_reduced": 1 (default) = fused4t, 0 = fused4c with look-ups in the full program
+    std::vector<FusedOp2> rprog, cprog;    // reduced program; the clades' own (untabulated, node-addressed) instruction ranges
+    std::vector<int> rorder;               // packed-tip slot -> tip row (-1: padding), 32 slots per word, in reduced-program order
+    std::vector<int> rxorder;              // ... and the row whose state is XORed into the slot (-1: none): difference coding
+    int fused_xor = 1;                     // option "fused_xor": difference-code the tips of a tabulated clade
+    int fused_occ = 0;                     // option "fused_occ": 4 = fused4t<256, 2> compiled for 4 blocks per SM (64 registers)
+    std::vector<int> rmat_nodes, rleaf_nodes;   // branches whose matrices the reduced program applies / looks columns up in
+    std::vector<pbk::CladeTab> rclades;
+    int rwords = 0, rstack = 0, rntab = 0, r_leaves = -1;
+    bool packed_for_reduced = false;       // which slot order d_packed currently holds
+    bool reduced_fits = false;             // the last plan fits the constant bank and shared memory (want_reduced)
+    DevBuf<FusedOp2> d_rprog, d_cprog;
+    DevBuf<int> d_rorder, d_rxorder, d_rmat_nodes, d_rleaf_nodes;
+    DevBuf<pbk::CladeTab> d_rclades;
     DevBuf<FusedOp2> d_fprog_tab;
     DevBuf<pbk::CladeTab> d_clades;
     DevBuf<int> d_cherry_k;
@@ -187,7 +203,9 @@ struct pb_ctx {
     bool have_site_weights = false;
     int64_t slot_stride = 0;
     double* h_total = nullptr;   // pinned: [0] = total, [1] = bad-tip flag (as int)
-    bool evaluated = false;
+    bool evaluated = false;      // an evaluation has run since pb_set_tree (partial re-evaluation needs resident CLVs)
+    bool fresh = false;          // ... and no input has changed since: what pb_get_clv / pb_conditional_simulation /
+                                 // pb_result_device_ptrs hand out belongs to the current inputs
 
     // pipelined host evaluation (pb_loglik_host)
     cudaStream_t copy_stream = nullptr;
@@ -262,7 +280,9 @@ int path_of(const pb_ctx* c)
     if (c->have_masks) return PATH_LEVEL_DENSE;
     if (c->n == 4) {
         if (!level && c->have_tree) {
-            if (fused_smem_bytes(c) <= c->smem_optin) return PATH_FUSED4;
+            // the reduced program (fused4t) keeps only the loose tips' matrices in shared memory; the all-shared-memory
+            // kernel (fused4) needs every branch's
+            if (c->reduced_fits || fused_smem_bytes(c) <= c->smem_optin) return PATH_FUSED4;
         }
         return PATH_LEVEL4;
     }
@@ -560,6 +580,7 @@ int compile_tree(pb_ctx* c)
             if (usesB) o.offB = compact[o.offB / 16] * 16;
         }
         c->tab_leaves = -1;                     // the tabulated variant is built on demand (build_table_program)
+        c->r_leaves = -1;                       // ... and so is the program over the reduced tree (build_reduced_program)
         // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
         c->fprog_d.clear();
         c->mlist.clear();
@@ -668,6 +689,32 @@ int launch_level_dense_m(pb_ctx* c, const LevelNode* nodes, int first, int count
     return PB_OK;
 }
 
+// Any other state count (2..64): the runtime-n form with register capacity NP.
+template <int NP, bool MASKS>
+int launch_level_dense_rt_m(pb_ctx* c, const LevelNode* nodes, int first, int count, int store_root)
+{
+    const size_t smem = (size_t)(NP * NP + NP * 128) * sizeof(double);
+    auto kern = pbk::level_dense_rt<NP, MASKS>;
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(c->spad / 128), count);
+    kern<<<grid, 128, smem, c->stream>>>(c->n, nodes, c->d_lv_children.p, first, c->d_P.p, c->nnodes, c->ncat,
+                                         c->d_tips.p, c->d_masks.p, c->spad, c->d_pool.p, c->slot_stride, c->spad,
+                                         c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p, store_root);
+    c->launches++;
+    return PB_OK;
+}
+
+int launch_level_dense_rt(pb_ctx* c, const LevelNode* nodes, int first, int count, int store_root)
+{
+#define PB_RT(NP) (c->have_masks ? launch_level_dense_rt_m<NP, true>(c, nodes, first, count, store_root) \
+                                 : launch_level_dense_rt_m<NP, false>(c, nodes, first, count, store_root))
+    if (c->n <= 8) return PB_RT(8);
+    if (c->n <= 16) return PB_RT(16);
+    if (c->n <= 32) return PB_RT(32);
+    return PB_RT(64);
+#undef PB_RT
+}
+
 template <int N>
 int launch_level_dense(pb_ctx* c, const LevelNode* nodes, int first, int count, int store_root)
 {
@@ -765,6 +812,15 @@ bool fused_const_ok(const pb_ctx* c)
     return c->fused_const && !c->fused_exact_log && !c->inner_nodes.empty() &&
            (int)c->inner_nodes.size() <= pbk::FUSED_CONST_MATS && (int)c->inner_nodes.size() <= 128 &&
            (int)c->fprog_c.size() <= pbk::FUSED_CONST_OPS && fused4c_shape(c, &b, &q);
+}
+
+// The largest clade that is tabulated (power-of-two mode only): a table of 4^k entries is only worth building when
+// the alignment has many more sites than that.
+int clade_limit(const pb_ctx* c)
+{
+    int want = (c->fused_cherry && c->fused_pow2) ? (c->fused_triple ? c->fused_clade_leaves : 2) : 0;
+    while (!c->fused_clade_force && want > 2 && (int64_t)8 << (2 * want) > c->nsites) want--;
+    return want;
 }
 
 // Finds the clades of at most `max_leaves` leaves whose instructions can be replaced by one table look-up and
@@ -885,6 +941,411 @@ int build_table_program(pb_ctx* c, int max_leaves, bool preapply = false)
     return PB_OK;
 }
 
+// ---- the program over the reduced tree (kernel fused4t) --------------------------------------------------
+// Leaves of the reduced tree: every maximal clade of at most `max_leaves` leaves (one table each) and the tips
+// outside such clades.  The emitter below follows the same rules as compile_tree (binary nodes: the child that
+// needs more stack first; other arities: the reference's left fold), with a table value or a tip as a direct
+// operand of its parent's instruction.  The same emitter, called on a clade's own subtree without tables, gives
+// the instruction range build_clade_tables interprets to fill that clade's table: the order of every
+// floating-point operation is the untabulated program's.
+struct RAbs { int code, a, b; };           // abstract instruction: operand nodes (branch = node at its lower end)
+
+void emit_reduced(const pb_ctx* c, int top, const std::vector<char>& kind, const std::vector<int>& su,
+                  std::vector<RAbs>& out)
+{
+    enum { K_INNER = 0, K_TIP = 1, K_TAB = 2 };
+    struct Item { int node; RAbs emit; bool is_emit; };
+    std::vector<Item> st;
+    st.push_back({top, {}, false});
+    while (!st.empty()) {
+        Item it = st.back();
+        st.pop_back();
+        if (it.is_emit) { out.push_back(it.emit); continue; }
+        const int v = it.node;
+        const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
+        std::vector<Item> seq;
+        if (c1 - c0 == 2) {
+            int a = c->child_idx[c0], b = c->child_idx[c0 + 1];
+            const int ka = kind[a], kb = kind[b];
+            if (ka == K_INNER && kb == K_INNER) {
+                if (su[b] > su[a]) std::swap(a, b);
+                seq.push_back({a, {}, false});
+                seq.push_back({0, {pbk::FOP_PUSH, 0, 0}, true});
+                seq.push_back({b, {}, false});
+                seq.push_back({0, {pbk::FOP_ACC_POP, b, a}, true});
+            } else if (ka == K_INNER || kb == K_INNER) {
+                const int in = ka == K_INNER ? a : b, lf = ka == K_INNER ? b : a;
+                seq.push_back({in, {}, false});
+                seq.push_back({0, {kind[lf] == K_TIP ? (int)pbk::FOP_APPLY_MUL_TIP : pbk::FOP_APPLY_MUL_TAB, in, lf}, true});
+            } else if (ka == K_TIP && kb == K_TIP) {
+                seq.push_back({0, {pbk::FOP_TIP_TIP, a, b}, true});
+            } else if (ka == K_TAB && kb == K_TAB) {
+                seq.push_back({0, {pbk::FOP_TAB_TAB, a, b}, true});
+            } else {
+                seq.push_back({0, {pbk::FOP_TAB_TIP, ka == K_TAB ? a : b, ka == K_TAB ? b : a}, true});
+            }
+        } else {
+            for (int k = c0; k < c1; k++) {                  // reference order (left fold)
+                const int ch = c->child_idx[k];
+                if (kind[ch] == K_TIP) {
+                    seq.push_back({0, {k == c0 ? (int)pbk::FOP_TIP : (int)pbk::FOP_MUL_TIP, ch, 0}, true});
+                } else if (kind[ch] == K_TAB) {
+                    seq.push_back({0, {k == c0 ? pbk::FOP_TAB : pbk::FOP_MUL_TAB, ch, 0}, true});
+                } else {
+                    if (k > c0) seq.push_back({0, {pbk::FOP_PUSH, 0, 0}, true});
+                    seq.push_back({ch, {}, false});
+                    seq.push_back({0, {pbk::FOP_APPLY, ch, 0}, true});
+                    if (k > c0) seq.push_back({0, {pbk::FOP_POP_MUL, 0, 0}, true});
+                }
+            }
+        }
+        for (auto r = seq.rbegin(); r != seq.rend(); ++r) st.push_back(*r);
+    }
+}
+
+// stack need of every node of a tree whose leaves are the nodes with kind != 0 (Sethi-Ullman, as in compile_tree)
+void stack_need(const pb_ctx* c, const std::vector<int>& postorder, const std::vector<char>& kind, std::vector<int>& su)
+{
+    su.assign(c->nnodes, 0);
+    for (int v : postorder) {
+        if (kind[v] != 0) continue;
+        const int c0 = c->child_ptr[v], c1 = c->child_ptr[v + 1];
+        if (c1 - c0 == 2) {
+            const int a = c->child_idx[c0], b = c->child_idx[c0 + 1];
+            const bool ia = kind[a] == 0, ib = kind[b] == 0;
+            if (ia && ib) su[v] = std::max(std::max(su[a], su[b]), std::min(su[a], su[b]) + 1);
+            else su[v] = ia ? su[a] : (ib ? su[b] : 0);
+        } else {
+            int need = 0;
+            for (int k = c0; k < c1; k++) {
+                const int ch = c->child_idx[k];
+                if (kind[ch] == 0) need = std::max(need, su[ch] + (k > c0 ? 1 : 0));
+            }
+            su[v] = need;
+        }
+    }
+}
+
+// folds every stand-alone PUSH into the instruction before it (window loads commute with it)
+void fold_pushes(std::vector<FusedOp2>& prog)
+{
+    std::vector<FusedOp2> folded;
+    for (const FusedOp2& o : prog) {
+        if (o.code == pbk::FOP_PUSH) {
+            int j = (int)folded.size() - 1;
+            while (j >= 0 && folded[j].code == pbk::FOP_LOADW) j--;
+            if (j >= 0 && !(folded[j].code & pbk::FOP_PUSH_AFTER)) { folded[j].code |= pbk::FOP_PUSH_AFTER; continue; }
+            FusedOp2 p2 = o;
+            p2.code = pbk::FOP_PUSH | pbk::FOP_PUSH_AFTER;
+            folded.push_back(p2);
+            continue;
+        }
+        folded.push_back(o);
+    }
+    prog.swap(folded);
+}
+
+int build_reduced_program(pb_ctx* c, int max_leaves)
+{
+    const int nn = c->nnodes;
+    auto is_leaf = [&](int v) { return c->child_ptr[v] == c->child_ptr[v + 1]; };
+    // post-order and leaves below every node
+    std::vector<int> order;
+    order.reserve(nn);
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({c->root, c->child_ptr[c->root]});
+        while (!st.empty()) {
+            auto& top = st.back();
+            if (top.second < c->child_ptr[top.first + 1]) {
+                const int ch = c->child_idx[top.second++];
+                st.push_back({ch, c->child_ptr[ch]});
+            } else {
+                order.push_back(top.first);
+                st.pop_back();
+            }
+        }
+    }
+    std::vector<int> nleaves(nn, 0);
+    for (int v : order) {
+        if (is_leaf(v)) { nleaves[v] = 1; continue; }
+        for (int k = c->child_ptr[v]; k < c->child_ptr[v + 1]; k++) nleaves[v] += nleaves[c->child_idx[k]];
+    }
+    // kinds in the reduced tree: 0 inner, 1 loose tip, 2 tabulated clade (its root), 3 inside a clade
+    std::vector<char> kind(nn, 0);
+    for (int i = nn - 1; i >= 0; i--) {                       // reverse post-order: parents before children
+        const int v = order[i];
+        const int par = c->parent[v];
+        if (par >= 0 && kind[par] >= 2) { kind[v] = 3; continue; }
+        if (is_leaf(v)) kind[v] = 1;
+        else kind[v] = (max_leaves >= 2 && nleaves[v] <= max_leaves) ? 2 : 0;
+    }
+    std::vector<int> su;
+    stack_need(c, order, kind, su);
+    c->rstack = kind[c->root] == 0 ? su[c->root] : 0;
+
+    std::vector<RAbs> aops;
+    if (kind[c->root] == 2) aops.push_back({pbk::FOP_TAB, c->root, 0});
+    else emit_reduced(c, c->root, kind, su, aops);
+    aops.push_back({pbk::FOP_ROOT, 0, 0});
+
+    // ---- the clades: tables and their own instruction ranges
+    c->rclades.clear();
+    c->cprog.clear();
+    c->rntab = 0;
+    std::vector<int> clade_of(nn, -1);
+    std::vector<std::vector<int>> clade_tips;                 // tip NODES of every clade in the order its range consumes them
+    {
+        std::vector<char> plain(nn);
+        for (int v = 0; v < nn; v++) plain[v] = is_leaf(v) ? 1 : 0;
+        std::vector<int> su_plain;
+        stack_need(c, order, plain, su_plain);
+        for (int v : order) {
+            if (kind[v] != 2) continue;
+            std::vector<RAbs> sub;
+            emit_reduced(c, v, plain, su_plain, sub);
+            pbk::CladeTab t{};
+            t.op0 = (int)c->cprog.size();
+            t.sh0 = 0;
+            t.k = nleaves[v];
+            t.ent0 = c->rntab;
+            t.pre = v == c->root ? -1 : v * 16;               // the table holds P[v] . clv(v): the consumer's product
+            t.xor_coded = c->fused_xor ? 1 : 0;
+            std::vector<int> tips;
+            auto field = [&](int leaf) { tips.push_back(leaf); return 2 * ((int)tips.size() - 1); };
+            std::vector<FusedOp2> ops;
+            for (const RAbs& a : sub) {
+                FusedOp2 o{a.code, a.a * 16, a.b * 16, 0};
+                switch (a.code) {
+                case pbk::FOP_TIP_TIP: { const int sa = field(a.a), sb = field(a.b); o.sh = sa | (sb << 8); break; }
+                case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: o.sh = field(a.a); break;
+                case pbk::FOP_APPLY_MUL_TIP: o.sh = field(a.b) << 8; break;
+                default: break;
+                }
+                ops.push_back(o);
+            }
+            fold_pushes(ops);
+            c->cprog.insert(c->cprog.end(), ops.begin(), ops.end());
+            t.op1 = (int)c->cprog.size() - 1;
+            clade_of[v] = (int)c->rclades.size();
+            c->rclades.push_back(t);
+            clade_tips.push_back(tips);
+            c->rntab += 1 << (2 * t.k);
+        }
+    }
+
+    // ---- lower: compact matrix indices, packed-tip fields (no field straddles a 64-bit word, an instruction's
+    // fields sit in one word), window loads
+    c->rmat_nodes.clear();
+    c->rleaf_nodes.clear();
+    std::vector<int> mat_idx(nn, -1), leaf_idx(nn, -1);
+    auto mat = [&](int v) { if (mat_idx[v] < 0) { mat_idx[v] = (int)c->rmat_nodes.size(); c->rmat_nodes.push_back(v); } return mat_idx[v] * 16; };
+    auto leafm = [&](int v) { if (leaf_idx[v] < 0) { leaf_idx[v] = (int)c->rleaf_nodes.size(); c->rleaf_nodes.push_back(v); } return leaf_idx[v] * 16; };
+    c->rprog.clear();
+    c->rorder.clear();
+    c->rxorder.clear();
+    int bitpos = 0;
+    auto reserve_bits = [&](int bits) {
+        if (bitpos + bits > 64) {
+            c->rorder.resize((c->rorder.size() + 31) / 32 * 32, -1);
+            c->rxorder.resize(c->rorder.size(), -1);
+            c->rprog.push_back({pbk::FOP_LOADW, 0, 0, 0});
+            bitpos = 0;
+        }
+    };
+    auto tip_field = [&](int leaf) {
+        const int sh = bitpos;
+        c->rorder.push_back(c->tip_row[leaf]);
+        c->rxorder.push_back(-1);
+        bitpos += 2;
+        return sh;
+    };
+    auto tab_field = [&](int v) {       // the clade's tips in the order its own range consumes them; all but the first
+        const int sh = bitpos;          // as differences from the first (a table's hot entries become neighbours)
+        const std::vector<int>& tips = clade_tips[clade_of[v]];
+        for (size_t j = 0; j < tips.size(); j++) {
+            c->rorder.push_back(c->tip_row[tips[j]]);
+            c->rxorder.push_back(j > 0 && c->fused_xor ? c->tip_row[tips[0]] : -1);
+        }
+        bitpos += 2 * nleaves[v];
+        return sh;
+    };
+    auto ent = [&](int v) { return c->rclades[clade_of[v]].ent0; };
+    for (const RAbs& a : aops) {
+        FusedOp2 o{a.code, 0, 0, 0};
+        switch (a.code) {
+        case pbk::FOP_TIP_TIP: { reserve_bits(4); const int sa = tip_field(a.a), sb = tip_field(a.b);
+                                 o.offA = leafm(a.a); o.offB = leafm(a.b); o.sh = sa | (sb << 8); break; }
+        case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: { reserve_bits(2); o.offA = leafm(a.a); o.sh = tip_field(a.a); break; }
+        case pbk::FOP_APPLY: o.offA = mat(a.a); break;
+        case pbk::FOP_APPLY_MUL_TIP: { reserve_bits(2); o.offA = mat(a.a); o.offB = leafm(a.b); o.sh = tip_field(a.b) << 8; break; }
+        case pbk::FOP_ACC_POP: o.offA = mat(a.a); o.offB = mat(a.b); break;
+        case pbk::FOP_TAB: case pbk::FOP_MUL_TAB: { reserve_bits(2 * nleaves[a.a]); o.offA = ent(a.a);
+                                                    o.sh = tab_field(a.a) | ((2 * nleaves[a.a]) << 16); break; }
+        case pbk::FOP_TAB_TAB: { reserve_bits(2 * (nleaves[a.a] + nleaves[a.b])); o.offA = ent(a.a); o.offB = ent(a.b);
+                                 const int sa = tab_field(a.a), sb = tab_field(a.b);
+                                 o.sh = sa | (sb << 8) | ((2 * nleaves[a.a]) << 16) | ((2 * nleaves[a.b]) << 24); break; }
+        case pbk::FOP_TAB_TIP: { reserve_bits(2 * nleaves[a.a] + 2); o.offA = ent(a.a); o.offB = leafm(a.b);
+                                 const int sa = tab_field(a.a), sb = tip_field(a.b);
+                                 o.sh = sa | (sb << 8) | ((2 * nleaves[a.a]) << 16); break; }
+        case pbk::FOP_APPLY_MUL_TAB: { reserve_bits(2 * nleaves[a.b]); o.offA = mat(a.a); o.offB = ent(a.b);
+                                       o.sh = (tab_field(a.b) << 8) | ((2 * nleaves[a.b]) << 24); break; }
+        default: break;                                       // FOP_PUSH, FOP_POP_MUL, FOP_ROOT
+        }
+        c->rprog.push_back(o);
+    }
+    fold_pushes(c->rprog);
+    c->rorder.resize(std::max<size_t>((c->rorder.size() + 31) / 32 * 32, 32), -1);
+    c->rxorder.resize(c->rorder.size(), -1);
+    c->rwords = (int)c->rorder.size() / 32;
+    c->r_leaves = max_leaves;
+    c->tables_stale = true;
+    c->pack_dirty = true;                 // the slot order follows the plan: tips packed for another limit are stale
+    if (c->plan_only) return PB_OK;
+    PB_CUDA(c, c->d_rprog.ensure(c->rprog.size()));
+    PB_CUDA(c, c->d_cprog.ensure(std::max<size_t>(c->cprog.size(), 1)));
+    PB_CUDA(c, c->d_rorder.ensure(c->rorder.size()));
+    PB_CUDA(c, c->d_rxorder.ensure(c->rxorder.size()));
+    PB_CUDA(c, c->d_rmat_nodes.ensure(std::max<size_t>(c->rmat_nodes.size(), 1)));
+    PB_CUDA(c, c->d_rleaf_nodes.ensure(std::max<size_t>(c->rleaf_nodes.size(), 1)));
+    PB_CUDA(c, c->d_rclades.ensure(std::max<size_t>(c->rclades.size(), 1)));
+    // (pageable host vectors: the copies have read them when the calls return)
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rprog.p, c->rprog.data(), c->rprog.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_cprog.p, c->cprog.data(), c->cprog.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rorder.p, c->rorder.data(), c->rorder.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rxorder.p, c->rxorder.data(), c->rxorder.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rmat_nodes.p, c->rmat_nodes.data(), c->rmat_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rleaf_nodes.p, c->rleaf_nodes.data(), c->rleaf_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_rclades.p, c->rclades.data(), c->rclades.size() * sizeof(pbk::CladeTab), cudaMemcpyHostToDevice, c->stream));
+    return PB_OK;
+}
+
+size_t fused4t_smem_for(const pb_ctx* c, int block, int spt)
+{
+    return (size_t)c->rleaf_nodes.size() * 16 * 8 + (size_t)std::max(c->rstack, 1) * 4 * block * spt * 8;
+}
+
+bool fused4t_shape(const pb_ctx* c, int* block, int* spt)
+{
+    const int cand[5][2] = {{c->fused_block, c->fused_spt}, {256, 2}, {128, 2}, {256, 1}, {0, 0}};
+    for (const auto& k : cand) {
+        const int key = k[0] * 10 + k[1];
+        const bool compiled = key == 2561 || key == 2562 || key == 2564 || key == 1282 || key == 1284;
+        if (compiled && fused4t_smem_for(c, k[0], k[1]) <= c->smem_optin) { *block = k[0]; *spt = k[1]; return true; }
+    }
+    return false;
+}
+
+// Does the next evaluation run the reduced program (fused4t)?  Plans it for the current clade limit when needed.
+int want_reduced(pb_ctx* c, bool* yes)
+{
+    *yes = false;
+    c->reduced_fits = false;
+    if (!c->fused_reduced || !c->fused_const || !c->fused_pow2 || c->fused_exact_log || c->n != 4 || !c->have_tree ||
+        (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) || c->have_masks) return PB_OK;
+    const int want_leaves = clade_limit(c);
+    if (c->r_leaves != want_leaves) {
+        const int rc = build_reduced_program(c, want_leaves);
+        if (rc != PB_OK) return rc;
+    }
+    int b = 0, q = 0;
+    *yes = (int)c->rmat_nodes.size() <= pbk::FUSED_CONST_MATS && (int)c->rprog.size() <= pbk::FUSED_CONST_OPS &&
+           fused4t_shape(c, &b, &q);
+    c->reduced_fits = *yes;
+    return PB_OK;
+}
+
+template <int BLOCK, int SPT, int MINB = 0>
+int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
+{
+    auto kern = pbk::fused4t<BLOCK, SPT, MINB>;
+    const size_t smem = fused4t_smem_for(c, BLOCK, SPT);
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+    if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4t: kernel does not fit on an SM");
+    const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
+    int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
+    gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
+    kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
+        (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
+        cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
+        c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p);
+    c->launches++;
+    return PB_OK;
+}
+
+int launch_fused4t_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slot0, int64_t site0, int64_t site1)
+{
+    switch (block * 10 + spt) {
+    case 2562: return c->fused_occ == 4 ? launch_fused4t_variant<256, 2, 4>(c, cat0, k, slot0, site0, site1)   // 64 registers
+                                        : launch_fused4t_variant<256, 2>(c, cat0, k, slot0, site0, site1);     // 72 registers
+    case 2564: return launch_fused4t_variant<256, 4>(c, cat0, k, slot0, site0, site1);
+    case 1282: return launch_fused4t_variant<128, 2>(c, cat0, k, slot0, site0, site1);
+    case 1284: return launch_fused4t_variant<128, 4>(c, cat0, k, slot0, site0, site1);
+    default: return launch_fused4t_variant<256, 1>(c, cat0, k, slot0, site0, site1);
+    }
+}
+
+// Program and matrices of the constant bank belong to whoever loaded them last (every context of the device
+// shares the bank): owner and program version per device.
+const pb_ctx* g_prog_owner[64] = {};
+uint64_t g_prog_version[64] = {};
+
+// The reduced program over the site columns [site0, site1), rate categories [cat_lo, cat_hi).  `regather`: the
+// matrices changed since the last call (new P(t)): compact them for the constant bank and refill the tables.
+int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
+{
+    if (cat_hi < 0) cat_hi = c->ncat;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    cudaEvent_t& bank_free = g_const_event[c->device & 63];
+    if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
+    else PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
+    const int nmat = (int)c->rmat_nodes.size();
+    int fb = 0, fq = 0;
+    if (!fused4t_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4t: the tree does not fit shared memory");
+    if (regather && nmat > 0) {
+        PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * nmat * 16));
+        pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_rmat_nodes.p, nmat, c->nnodes, c->d_Pc.p);
+        c->launches++;
+    }
+    const uint64_t want_version = c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2;
+    if (g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
+        PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, c->d_rprog.p, c->rprog.size() * sizeof(FusedOp2), 0,
+                                           cudaMemcpyDeviceToDevice, c->stream));
+        g_prog_owner[c->device & 63] = c;
+        g_prog_version[c->device & 63] = want_version;
+    }
+    if (!c->rclades.empty() && (regather || c->tables_stale || c->tab_variant != 2)) {
+        c->tab_variant = 2;
+        PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * c->rntab * 4));
+        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->rntab));
+        int kmax = 1;
+        for (const pbk::CladeTab& t : c->rclades) kmax = std::max(kmax, t.k);
+        const unsigned gz = (unsigned)std::max(1, (1 << (2 * kmax)) / 256);
+        pbk::build_clade_tables<true><<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
+            c->d_cprog.p, c->d_rclades.p, c->d_P.p, nullptr, nullptr, c->nnodes, c->rntab, c->threshold,
+            c->d_cherry_v.p, c->d_cherry_k.p);
+        c->launches++;
+        c->tables_stale = false;
+    }
+    const int per_launch = std::max(1, std::min(c->fused_const_cats, pbk::FUSED_CONST_MATS / std::max(nmat, 1)));
+    const int per_load = c->fused_const_group ? std::max(per_launch, pbk::FUSED_CONST_MATS / std::max(nmat, 1)) : per_launch;
+    for (int g0 = cat_lo; g0 < cat_hi; g0 += per_load) {
+        const int gk = std::min(per_load, cat_hi - g0);
+        if (nmat > 0)
+            PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)g0 * nmat * 16,
+                                               (size_t)gk * nmat * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice, c->stream));
+        for (int cat0 = g0; cat0 < g0 + gk; cat0 += per_launch) {
+            const int k = std::min(per_launch, g0 + gk - cat0);
+            const int rc = launch_fused4t_shape(c, fb, fq, cat0, k, cat0 - g0, site0, site1);
+            if (rc != PB_OK) return rc;
+        }
+    }
+    PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
+    return PB_OK;
+}
+
 // The inner matrices of as many categories as the constant bank holds per launch.
 int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
 {
@@ -907,12 +1368,9 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     // profiles/r01f_sweep_c2_fused4c.jsonl); per-category launches keep every block of an SM on one set.
     const int per_launch = std::max(1, std::min(c->fused_const_cats, pbk::FUSED_CONST_MATS / std::max(ninner, 1)));
     // the program shares the bank: upload it unless this context's current program is already there
-    static const pb_ctx* prog_owner[64] = {};
-    static uint64_t prog_version[64] = {};
     // small clades as table look-ups (power-of-two mode): the program variant for the current size limit
     // (a table of 4^k entries is only worth building when the alignment has many more sites than that)
-    int want_leaves = (c->fused_cherry && c->fused_pow2) ? (c->fused_triple ? c->fused_clade_leaves : 2) : 0;
-    while (!c->fused_clade_force && want_leaves > 2 && (int64_t)8 << (2 * want_leaves) > c->nsites) want_leaves--;
+    const int want_leaves = clade_limit(c);
     const bool want_pre = FUSED_PREAPPLY && c->fused_preapply;      // (a kernel build option, off by default)
     if (c->tab_leaves != want_leaves || c->tab_preapply != want_pre) {
         const int rc = build_table_program(c, want_leaves, want_pre);
@@ -920,22 +1378,23 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         c->tab_preapply = want_pre;
     }
     const bool tabulated = !c->clades.empty();
-    const uint64_t want_version = c->fprog_version * 16 + (uint64_t)want_leaves * 2 + (want_pre ? 1 : 0);
+    const uint64_t want_version = c->fprog_version * 64 + (uint64_t)want_leaves * 4 + (want_pre ? 1 : 0);
     const FusedOp2* prog = tabulated ? c->d_fprog_tab.p : c->d_fprog_c.p;
     c->fprog_bank_nops = (int)(tabulated ? c->fprog_tab.size() : c->fprog_c.size());
-    if (prog_owner[c->device & 63] != c || prog_version[c->device & 63] != want_version) {
+    if (g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, prog, c->fprog_bank_nops * sizeof(FusedOp2), 0,
                                            cudaMemcpyDeviceToDevice, c->stream));
-        prog_owner[c->device & 63] = c;
-        prog_version[c->device & 63] = want_version;
+        g_prog_owner[c->device & 63] = c;
+        g_prog_version[c->device & 63] = want_version;
     }
-    if (tabulated && (regather || c->tables_stale)) {
+    if (tabulated && (regather || c->tables_stale || c->tab_variant != 1)) {
+        c->tab_variant = 1;
         PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * c->ntab * 4));
         PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->ntab));
         int kmax = 2;
         for (const pbk::CladeTab& t : c->clades) kmax = std::max(kmax, t.k);
         const unsigned gz = (unsigned)std::max(1, (1 << (2 * kmax)) / 256);
-        pbk::build_clade_tables<<<dim3((unsigned)c->clades.size(), c->ncat, gz), 256, 0, c->stream>>>(
+        pbk::build_clade_tables<false><<<dim3((unsigned)c->clades.size(), c->ncat, gz), 256, 0, c->stream>>>(
             c->d_fprog_c.p, c->d_clades.p, c->d_P.p, c->d_inner_nodes.p, c->d_leaf_nodes.p, c->nnodes, c->ntab, c->threshold,
             c->d_cherry_v.p, c->d_cherry_k.p);
         c->launches++;
@@ -974,8 +1433,9 @@ int launch_fused4_shape(pb_ctx* c, int block, int spt, int64_t site0, int64_t si
     }
 }
 
-int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1)
+int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1, bool reduced)
 {
+    if (reduced) return launch_fused4t(c, site0, site1, site0 == 0);
     if (fused_const_ok(c)) return launch_fused4c(c, site0, site1, site0 == 0);
     int fb = c->fused_block, fq = c->fused_spt;
     if (!fused_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4: the tree does not fit shared memory");
@@ -1069,7 +1529,7 @@ int ensure_tip_bytes(pb_ctx* c)
 {
     if (!c->tip_bytes_stale) return PB_OK;
     const int64_t nbytes = (c->nsites + 3) / 4;
-    pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
+    pbk::expand_tips2<<<dim3(c->ntaxa, (unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048)), 256, 0, c->stream>>>(
         c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, 0, nbytes);
     c->launches++;
     PB_CUDA(c, cudaGetLastError());
@@ -1080,6 +1540,11 @@ int ensure_tip_bytes(pb_ctx* c)
 int run_pruning(pb_ctx* c)
 {
     const int n = c->n;
+    bool reduced = false;
+    {
+        const int rc = want_reduced(c, &reduced);
+        if (rc != PB_OK) return rc;
+    }
     const int path = path_of(c);
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
     if (path != PATH_FUSED4 || c->pack_dirty) {
@@ -1087,16 +1552,21 @@ int run_pruning(pb_ctx* c)
         if (rc != PB_OK) return rc;
     }
     if (path == PATH_FUSED4) {
-        if (c->pack_dirty) {
-            PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
+        int rc = PB_OK;
+        if (c->pack_dirty || c->packed_for_reduced != reduced) {
+            if (c->tip_bytes_stale && (rc = ensure_tip_bytes(c)) != PB_OK) return rc;
+            const int nwords = reduced ? c->rwords : c->fwords;
+            PB_CUDA(c, c->d_packed.ensure((size_t)(nwords + 2) * c->spad));
             pbk::pack_tips4<<<(unsigned)((c->spad + 255) / 256), 256, 0, c->stream>>>(
-                c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad,
+                c->d_tips.p, c->spad, reduced ? c->d_rorder.p : c->d_tip_order.p, reduced ? c->d_rxorder.p : nullptr,
+                reduced ? (int)c->rorder.size() : (int)c->tip_order.size(), nwords, c->d_packed.p, c->spad,
                 0, c->spad, c->d_bad.p);
             c->launches++;
             c->pack_dirty = false;
+            c->packed_for_reduced = reduced;
             c->tips_checked = true;
         }
-        int rc = launch_fused4(c, 0, c->spad);
+        rc = launch_fused4(c, 0, c->spad, reduced);
         if (rc != PB_OK) return rc;
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
@@ -1158,6 +1628,13 @@ int run_pruning(pb_ctx* c)
     std::fill(c->dirty.begin(), c->dirty.end(), 0);
     c->all_dirty = false;
     c->partial_ok = true;
+    {   // a level of a very large tree may hold more nodes than gridDim.y allows: several launches
+        std::vector<std::pair<int, int>> split;
+        for (const auto& seg : segments)
+            for (int off = 0; off < seg.second; off += 65535)
+                split.push_back({seg.first + off, std::min(65535, seg.second - off)});
+        segments.swap(split);
+    }
     for (const auto& seg : segments) {
         const int first = seg.first, count = seg.second;
         if (path == PATH_LEVEL4 && c->level4_async && c->max_arity == 2 && c->min_arity == 2) {
@@ -1218,8 +1695,7 @@ int run_pruning(pb_ctx* c)
             case 20: rc = launch_level_dense<20>(c, lvn, first, count, store_root); break;
             case 61: rc = launch_level_dense<61>(c, lvn, first, count, store_root); break;
             case 64: rc = launch_level_dense<64>(c, lvn, first, count, store_root); break;
-            default:
-                return fail(c, PB_ERR_INVALID_ARG, "nstates: compiled sizes are 2,3,4,5,20,61,64");
+            default: rc = launch_level_dense_rt(c, lvn, first, count, store_root); break;
             }
             if (rc != PB_OK) return rc;
         }
@@ -1360,6 +1836,7 @@ int pb_set_mode(pb_ctx* c, int mode)
     else if (mode == PB_MODE_FELSENSTEIN) { c->threshold = 0.0000001; c->shift_at_root = 0; }
     else return fail(c, PB_ERR_INVALID_ARG, "unknown mode");
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1369,6 +1846,7 @@ int pb_set_rescaling(pb_ctx* c, double threshold, int shift_at_root)
     c->threshold = threshold;
     c->shift_at_root = shift_at_root ? 1 : 0;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1411,10 +1889,13 @@ int pb_set_tree(pb_ctx* c, int nnodes, int root, const int32_t* child_ptr, const
     c->have_blen = false;
     c->p_dirty = true;
     c->all_dirty = true;
+    c->fresh = false;
     if (c->psrc == PSRC_DIRECT) c->psrc = PSRC_NONE;   // matrices belonged to the old tree
     c->evaluated = false;
     int rc = compile_tree(c);
     if (rc != PB_OK) { c->have_tree = false; return rc; }
+    bool reduced = false;
+    if ((rc = want_reduced(c, &reduced)) != PB_OK) { c->have_tree = false; return rc; }   // plans the 4-state program (pb_path_name)
     if (branch_len) return pb_set_branch_lengths(c, branch_len);
     return PB_OK;
 }
@@ -1434,6 +1915,7 @@ int pb_set_branch_lengths(pb_ctx* c, const double* bl)
     c->have_blen = true;
     c->p_dirty = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1447,6 +1929,7 @@ int pb_update_branch_length(pb_ctx* c, int node, double t)
     c->branch_len[node] = t;
     PB_CUDA(c, cudaMemcpyAsync(c->d_blen.p + node, &c->branch_len[node], sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->p_dirty = true;
+    c->fresh = false;
     for (int v = c->parent[node]; v >= 0; v = c->parent[v]) c->dirty[v] = 1;    // the path to the root
     return PB_OK;
 }
@@ -1479,12 +1962,16 @@ int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
     if (rc != PB_OK) return rc;
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p, c->spad, states, ld, c->nsites, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    // The caller's buffer may be page-locked (pb_pin_host_memory), in which case the copy above is truly
+    // asynchronous: wait until it has been read, so that the caller may change or free it once we return.
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_tips = true;
     c->have_masks = false;
     c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1502,6 +1989,7 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1515,23 +2003,26 @@ int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
     if (rc != PB_OK) return rc;
     if ((rc = alloc_tips2(c)) != PB_OK) return rc;
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips2.p, c->spad / 4, packed, ld, nbytes, c->ntaxa, cudaMemcpyHostToDevice, c->stream));
-    pbk::expand_tips2<<<dim3((unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048), c->ntaxa), 256, 0, c->stream>>>(
+    pbk::expand_tips2<<<dim3(c->ntaxa, (unsigned)std::min<int64_t>((nbytes + 255) / 256, 2048)), 256, 0, c->stream>>>(
         c->d_tips2.p, c->spad / 4, c->d_tips.p, c->spad, 0, nbytes);
     c->launches++;
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));     // the caller's (possibly pinned) buffer has been read
     c->have_tips = true;
     c->have_masks = false;
     c->tip_bytes_stale = false;
     c->pack_dirty = true;
     c->tips_checked = false;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
 int pb_set_site_weights(pb_ctx* c, const double* w)
 {
     PB_ENTER(c);
+    c->fresh = false;
     if (!w) { c->have_site_weights = false; return PB_OK; }
     for (int64_t s = 0; s < c->nsites; s++)
         if (!(w[s] >= 0.0)) return fail(c, PB_ERR_INVALID_ARG, "site weights must be >= 0");
@@ -1573,7 +2064,7 @@ int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_text.p, c->nsites * width, text, ld, c->nsites * width, c->ntaxa,
                                  cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
-    dim3 grid((unsigned)std::min<int64_t>((c->nsites + 255) / 256, 1024), c->ntaxa);
+    dim3 grid(c->ntaxa, (unsigned)std::min<int64_t>((c->nsites + 255) / 256, 1024));
     pbk::encode_text<<<grid, 256, 0, c->stream>>>(c->d_text.p, c->nsites * width, width, c->d_lut.p, c->d_tips.p, c->spad,
                                                   c->nsites, c->d_bad.p);
     c->launches++;
@@ -1592,6 +2083,7 @@ int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
     c->pack_dirty = true;
     c->tips_checked = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1606,9 +2098,12 @@ int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_masks.p, c->spad * sizeof(uint64_t), masks, ld * sizeof(uint64_t),
                                  c->nsites * sizeof(uint64_t), c->ntaxa, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));     // the caller's (possibly pinned) buffer has been read
+    c->fresh = false;
     c->have_masks = true;
     c->have_tips = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1621,6 +2116,7 @@ int pb_set_root_frequencies(pb_ctx* c, const double* pi)
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_pi = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1637,6 +2133,7 @@ int pb_set_categories(pb_ctx* c, const double* rates, const double* weights)
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->p_dirty = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1658,6 +2155,7 @@ int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const d
     c->psrc = PSRC_EIGEN;
     c->p_dirty = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1713,6 +2211,60 @@ int pb_debug_fused_program(int nnodes, int root, const int32_t* child_ptr, const
     return PB_OK;
 }
 
+// The same for the program over the REDUCED tree (kernel fused4t; build_reduced_program): its instructions, the
+// clades' own instruction ranges (what fills their tables), the packed-tip slot order and the matrix lists.
+int pb_debug_reduced_program(int nnodes, int root, const int32_t* child_ptr, const int32_t* child_idx, const int32_t* tip_row,
+                             int ntaxa, int max_leaves, int32_t* counts, int32_t* ops, int cap_ops, int32_t* clade_ops,
+                             int cap_clade_ops, int32_t* slot_rows, int32_t* slot_xor_rows, int cap_slots, int32_t* mat_nodes,
+                             int32_t* leaf_nodes, int32_t* clades, int cap_clades)
+{
+    if (!slot_xor_rows) return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_reduced_program: bad arguments");
+    if (!child_ptr || !child_idx || !tip_row || !counts || !ops || !clade_ops || !slot_rows || !mat_nodes || !leaf_nodes ||
+        !clades || nnodes < 2 || root < 0 || root >= nnodes || ntaxa < 1 || child_ptr[0] != 0 || child_ptr[nnodes] != nnodes - 1)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_reduced_program: bad arguments");
+    std::unique_ptr<pb_ctx> c(new pb_ctx());
+    c->plan_only = true;
+    c->n = 4;
+    c->ncat = 1;
+    c->ntaxa = ntaxa;
+    c->nsites = 1;
+    c->spad = 1024;
+    c->nnodes = nnodes;
+    c->root = root;
+    c->child_ptr.assign(child_ptr, child_ptr + nnodes + 1);
+    c->child_idx.assign(child_idx, child_idx + nnodes - 1);
+    c->tip_row.assign(tip_row, tip_row + nnodes);
+    c->parent.assign(nnodes, -1);
+    for (int v = 0; v < nnodes; v++)
+        for (int k = child_ptr[v]; k < child_ptr[v + 1]; k++) {
+            const int ch = child_idx[k];
+            if (ch < 0 || ch >= nnodes || ch == root || c->parent[ch] != -1)
+                return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_reduced_program: bad child index");
+            c->parent[ch] = v;
+        }
+    const int rc = build_reduced_program(c.get(), max_leaves);
+    if (rc != PB_OK) return fail(nullptr, rc, c->err);
+    if ((int)c->rprog.size() > cap_ops || (int)c->cprog.size() > cap_clade_ops || (int)c->rorder.size() > cap_slots ||
+        (int)c->rclades.size() > cap_clades)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_reduced_program: output buffers too small");
+    std::memcpy(ops, c->rprog.data(), c->rprog.size() * sizeof(FusedOp2));
+    std::memcpy(clade_ops, c->cprog.data(), c->cprog.size() * sizeof(FusedOp2));
+    std::copy(c->rorder.begin(), c->rorder.end(), slot_rows);
+    std::copy(c->rxorder.begin(), c->rxorder.end(), slot_xor_rows);
+    std::copy(c->rmat_nodes.begin(), c->rmat_nodes.end(), mat_nodes);
+    std::copy(c->rleaf_nodes.begin(), c->rleaf_nodes.end(), leaf_nodes);
+    for (size_t i = 0; i < c->rclades.size(); i++) {
+        const pbk::CladeTab& t = c->rclades[i];
+        const int32_t row[6] = {t.op0, t.op1, t.xor_coded, t.k, t.ent0, t.pre};
+        std::copy(row, row + 6, clades + 6 * i);
+    }
+    const int32_t cnt[8] = {(int32_t)c->rprog.size(), (int32_t)c->cprog.size(), (int32_t)c->rorder.size(), c->rwords,
+                            std::max(c->rstack, 1), (int32_t)c->rmat_nodes.size(), (int32_t)c->rleaf_nodes.size(),
+                            (int32_t)c->rclades.size()};
+    std::copy(cnt, cnt + 8, counts);
+    return PB_OK;
+}
+
 // Page-lock a caller-owned host buffer (an OCaml Bigarray payload lives outside the OCaml heap and does not move)
 // so that the chunked copies of pb_loglik_host / pb_loglik_host_packed2 overlap with the pruning.
 int pb_pin_host_memory(void* p, size_t bytes)
@@ -1763,6 +2315,7 @@ int pb_set_rate_matrix_general(pb_ctx* c, const double* Q)
     c->psrc = PSRC_EXPM;
     c->p_dirty = true;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1781,6 +2334,7 @@ int pb_set_pmatrices(pb_ctx* c, const double* P)
     c->psrc = PSRC_DIRECT;
     c->p_dirty = false;
     c->all_dirty = true;
+    c->fresh = false;
     return PB_OK;
 }
 
@@ -1801,6 +2355,7 @@ int pb_loglik_enqueue(pb_ctx* c)
     PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->evaluated = true;
+    c->fresh = true;
     return PB_OK;
 }
 
@@ -1817,7 +2372,8 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
     return PB_OK;
 }
 
-static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool packed2, double* total, double* per_site)
+static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool packed2, double* total, double* per_site,
+                            bool fetch = true)
 {
     PB_ENTER(c);
     if (packed2 && c->n != 4) return fail(c, PB_ERR_STATE, "2-bit packed tips are for 4-state alphabets");
@@ -1825,10 +2381,19 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         return fail(c, PB_ERR_INVALID_ARG, packed2 ? "packed tips: null pointer or ld < ceil(nsites / 4)" : "tips: null pointer or ld < nsites");
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
     if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
+    bool reduced = false;                                         // which 4-state program runs (and orders the packed tips)
+    {
+        const bool had_masks = c->have_masks;
+        c->have_masks = false;                                    // this call replaces whatever the context held
+        const int rc0 = want_reduced(c, &reduced);
+        c->have_masks = had_masks;
+        if (rc0 != PB_OK) return rc0;
+    }
     if (path_of(c) != PATH_FUSED4 || c->host_chunks == 1 || c->spad < 8192) {
         int rc = packed2 ? pb_set_tips_packed2(c, states, ld) : pb_set_tips(c, states, ld);
         if (rc != PB_OK) return rc;
-        return pb_loglik(c, total, per_site);
+        if ((rc = pb_loglik_enqueue(c)) != PB_OK) return rc;
+        return fetch ? pb_loglik_fetch(c, total, per_site) : PB_OK;
     }
     // Pipeline: the alignment crosses PCIe in column chunks on a copy stream while the previous
     // chunk is packed, pruned and root-reduced on the compute stream.
@@ -1846,8 +2411,12 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     if ((rc = build_pmatrices(c)) != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     const int64_t nblocks = (c->nsites + 255) / 256;
+    const int nwords = reduced ? c->rwords : c->fwords;
+    const int* d_order = reduced ? c->d_rorder.p : c->d_tip_order.p;
+    const int* d_xorder = reduced ? c->d_rxorder.p : nullptr;
+    const int nslots = reduced ? (int)c->rorder.size() : (int)c->tip_order.size();
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
-    PB_CUDA(c, c->d_packed.ensure((size_t)(c->fwords + 2) * c->spad));
+    PB_CUDA(c, c->d_packed.ensure((size_t)(nwords + 2) * c->spad));
     PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
     PB_CUDA(c, c->d_partials.ensure((size_t)nblocks));
     PB_CUDA(c, c->d_total.ensure(1));
@@ -1859,7 +2428,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     // copy, the others run once over all the sites.  A launch costs one round of the persistent blocks (~0.09 ms)
     // however few tiles it has, so more chunked launches lose more than the overlap wins
     // (profiles/r01m_sweep_e2e_chunks_x_lead_cats.jsonl).
-    const bool first_cat_only = packed2 && c->ncat > 1 && fused_const_ok(c);
+    const bool first_cat_only = packed2 && c->ncat > 1 && (reduced || fused_const_ok(c));
     const int lead_cats = std::max(1, std::min(c->host_lead_cats, c->ncat));
     int k = 0;
     for (int64_t s0 = 0; s0 < c->spad; s0 += chunk, k++) {
@@ -1878,20 +2447,19 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
             // consumers read (level kernels, pb_get_clv, a re-pack after pb_set_tree) is expanded when one of them
             // asks for it (ensure_tip_bytes): an evaluation loop over host alignments never pays for it.
             pbk::pack_tips4_from2<<<(unsigned)(((s1 - s0) / 4 + 255) / 256), 256, 0, c->stream>>>(
-                c->d_tips2.p, c->spad / 4, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad,
-                s0 / 4, s1 / 4);
+                c->d_tips2.p, c->spad / 4, d_order, d_xorder, nslots, nwords, c->d_packed.p, c->spad, s0 / 4, s1 / 4);
             c->launches++;
         } else {
             pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
-                c->d_tips.p, c->spad, c->d_tip_order.p, (int)c->tip_order.size(), c->fwords, c->d_packed.p, c->spad, s0, s1,
-                c->d_bad.p);
+                c->d_tips.p, c->spad, d_order, d_xorder, nslots, nwords, c->d_packed.p, c->spad, s0, s1, c->d_bad.p);
             c->launches++;
         }
         if (first_cat_only) {                                // the other categories follow once, over all the sites
-            if ((rc = launch_fused4c(c, s0, s1, s0 == 0, 0, lead_cats)) != PB_OK) return rc;
+            if ((rc = reduced ? launch_fused4t(c, s0, s1, s0 == 0, 0, lead_cats)
+                              : launch_fused4c(c, s0, s1, s0 == 0, 0, lead_cats)) != PB_OK) return rc;
             continue;
         }
-        if ((rc = launch_fused4(c, s0, s1)) != PB_OK) return rc;
+        if ((rc = launch_fused4(c, s0, s1, reduced)) != PB_OK) return rc;
         const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
         if (b1 > b0) {
             pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(
@@ -1901,7 +2469,8 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         }
     }
     if (first_cat_only) {
-        if (c->ncat > lead_cats && (rc = launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
+        if (c->ncat > lead_cats && (rc = reduced ? launch_fused4t(c, 0, c->spad, false, lead_cats, c->ncat)
+                                                 : launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
         pbk::root_combine<<<(unsigned)nblocks, 256, 0, c->stream>>>(
             c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
             c->spad, 0, c->d_per_site.p, c->d_partials.p);
@@ -1917,11 +2486,18 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     c->have_tips = true;
     c->have_masks = false;
     c->pack_dirty = false;
+    c->packed_for_reduced = reduced;
     c->tips_checked = true;
     c->all_dirty = true;
     c->evaluated = true;
+    c->fresh = true;
     c->tip_bytes_stale = packed2;
-    return pb_loglik_fetch(c, total, per_site);
+    return fetch ? pb_loglik_fetch(c, total, per_site) : PB_OK;
+}
+
+int pb_loglik_host_enqueue(pb_ctx* c, const uint8_t* states, int64_t ld, int packed2)
+{
+    return loglik_host_impl(c, states, ld, packed2 != 0, nullptr, nullptr, false);
 }
 
 int pb_loglik_host(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, double* per_site)
@@ -1944,7 +2520,7 @@ int pb_loglik(pb_ctx* c, double* total, double* per_site)
 int pb_result_device_ptrs(pb_ctx* c, const double** d_total, const double** d_per_site)
 {
     PB_ENTER(c);
-    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (!c->evaluated || !c->fresh) return fail(c, PB_ERR_STATE, "nothing evaluated since the inputs last changed");
     if (d_total) *d_total = c->d_total.p;
     if (d_per_site) *d_per_site = c->d_per_site.p;
     return PB_OK;
@@ -1954,7 +2530,7 @@ int pb_get_clv(pb_ctx* c, int node, int cat, double* v, double* carry)
 {
     PB_ENTER(c);
     if (!(c->flags & PB_FLAG_KEEP_CLV)) return fail(c, PB_ERR_STATE, "pb_get_clv needs PB_FLAG_KEEP_CLV");
-    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (!c->evaluated || !c->fresh) return fail(c, PB_ERR_STATE, "nothing evaluated since the inputs last changed");
     if (node < 0 || node >= c->nnodes || cat < 0 || cat >= c->ncat || !v || !carry)
         return fail(c, PB_ERR_INVALID_ARG, "pb_get_clv: bad node/category/pointer");
     const int n = c->n;
@@ -1998,7 +2574,7 @@ int pb_conditional_simulation(pb_ctx* c, uint64_t seed, uint8_t* states, int64_t
 {
     PB_ENTER(c);
     if (!(c->flags & PB_FLAG_KEEP_CLV)) return fail(c, PB_ERR_STATE, "pb_conditional_simulation needs PB_FLAG_KEEP_CLV");
-    if (!c->evaluated) return fail(c, PB_ERR_STATE, "nothing evaluated yet");
+    if (!c->evaluated || !c->fresh) return fail(c, PB_ERR_STATE, "nothing evaluated since the inputs last changed");
     if (c->ncat != 1) return fail(c, PB_ERR_STATE, "pb_conditional_simulation: one rate category only (as the reference)");
     if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "pb_conditional_simulation: bad output buffer");
     // parents before children
@@ -2067,6 +2643,14 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const_cats = iv;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
+    } else if (k == "fused_reduced") {
+        c->fused_reduced = iv != 0;
+    } else if (k == "fused_occ") {
+        if (iv != 0 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_occ must be 0 or 4");
+        c->fused_occ = iv;
+    } else if (k == "fused_xor") {
+        c->fused_xor = iv != 0;
+        c->r_leaves = -1;                  // replan (and repack) with the other coding
     } else if (k == "fused_triple") {
         c->fused_triple = iv != 0;
     } else if (k == "fused_preapply") {
@@ -2075,7 +2659,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_clade_force") {
         c->fused_clade_force = iv != 0;
     } else if (k == "fused_clade_leaves") {
-        if (iv < 2 || iv > 6) return fail(c, PB_ERR_INVALID_ARG, "fused_clade_leaves must be in 2..6");
+        if (iv < 2 || iv > 8) return fail(c, PB_ERR_INVALID_ARG, "fused_clade_leaves must be in 2..8");
         c->fused_clade_leaves = iv;
     } else if (k == "fused_cherry") {
         c->fused_cherry = iv != 0;
@@ -2130,7 +2714,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     if (c->fused_block == 512 && c->fused_spt > 1 && !c->fused_const) c->fused_spt = 1;
     if (c->fused_block == 256 && c->fused_spt == 4 && c->fused_exact_log) c->fused_spt = 2;
     if (c->fused_block == 512 && c->fused_spt == 4) c->fused_spt = 2;
-    return PB_OK;
+    bool reduced = false;
+    return want_reduced(c, &reduced);          // the options decide which 4-state program runs (pb_path_name)
 }
 
 int pb_set_timing(pb_ctx* c, int on)
@@ -2166,6 +2751,8 @@ int64_t pb_kernel_launches(const pb_ctx* c) { return c ? c->launches : 0; }
 const char* pb_path_name(const pb_ctx* c)
 {
     if (!c) return "";
+    bool reduced = false;
+    want_reduced(const_cast<pb_ctx*>(c), &reduced);       // (re)plans the 4-state program for the current options and inputs
     switch (path_of(c)) {
     case PATH_FUSED4: return "fused4";
     case PATH_LEVEL4: return "level4";

@@ -468,6 +468,110 @@ level_dense(const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ 
     }
 }
 
+// The same kernel for ANY state count n <= NP (Phylo_ctmc.pruning ~nstates is generic, lib/phylo_ctmc.mli:55-61):
+// NP in {8, 16, 32, 64} is the register capacity, loops are unrolled over NP and predicated on i < n, P is staged
+// with row stride n exactly as above.  Used for the alphabets that have no specialised instantiation (e.g. 16 or 21
+// states, a 60-codon code); the specialised sizes (4, 20, 61, ...) never come here.
+template <int NP, bool MASKS>
+__global__ void __launch_bounds__(128)
+level_dense_rt(int n, const LevelNode* __restrict__ nodes, const LevelChild* __restrict__ children,
+               int node_base, const double* __restrict__ P, int nnodes, int ncat,
+               const uint8_t* __restrict__ tips, const uint64_t* __restrict__ masks, int64_t tips_ld,
+               double* __restrict__ pool, int64_t slot_stride, int64_t spad,
+               const double* __restrict__ pi, double thr, int shift_at_root,
+               double* __restrict__ site_cat, int store_root)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                 // [n*n]
+    double* shX = sh + NP * NP;       // [n][128]
+    const LevelNode nd = nodes[node_base + blockIdx.y];
+    const LevelChild* ch = children + nd.child_off;
+    const int tid = threadIdx.x;
+    const int64_t s = (int64_t)blockIdx.x * 128 + tid;
+
+    auto shift = [&](double (&v)[NP], double& carry) {       // SV.shift over the n live components
+        double mn = v[0], mx = v[0];
+#pragma unroll
+        for (int i = 1; i < NP; i++) if (i < n) { mn = fmin(mn, v[i]); mx = fmax(mx, v[i]); }
+        if (!(mn > thr)) {
+            const double inv = 1.0 / mx;
+#pragma unroll
+            for (int i = 0; i < NP; i++) if (i < n) v[i] = inv * v[i];
+            carry += log(mx);
+        }
+    };
+
+    for (int c = 0; c < ncat; c++) {
+        double acc[NP];
+        double carry = 0.0;
+        bool have = false;
+        for (int k = 0; k < nd.nchild; k++) {
+            const LevelChild cd = ch[k];
+            __syncthreads();
+            const double* Pg = P + ((size_t)c * nnodes + cd.pnode) * n * n;
+            for (int idx = tid; idx < n * n; idx += 128) shP[idx] = Pg[idx];
+            double tc = 0.0;
+            int st = 0;
+            uint64_t m = 0;
+            bool ok = true;
+            if (cd.kind == 0) {
+                if (MASKS) { m = masks[(int64_t)cd.src * tips_ld + s]; ok = m != 0; }
+                else st = tips[(int64_t)cd.src * tips_ld + s];
+            } else {
+                const double* src = pool + (int64_t)cd.src * slot_stride + (int64_t)c * (n + 1) * spad + s;
+                for (int j = 0; j < n; j++) shX[j * 128 + tid] = src[(int64_t)j * spad];
+                tc = src[(int64_t)n * spad];
+                if (MASKS) ok = !isnan(tc);
+            }
+            __syncthreads();
+            const bool first = MASKS ? !have : (k == 0);
+            if (ok) carry = first ? tc : carry + tc;
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                if (i >= n) continue;
+                double t;
+                if (cd.kind == 0) {
+                    if (MASKS) {
+                        t = 0.0;
+                        for (int j = 0; j < n; j++)
+                            if ((m >> j) & 1) t += shP[i * n + j];
+                    } else {
+                        t = shP[i * n + st];
+                    }
+                } else {
+                    t = shP[i * n] * shX[tid];
+                    for (int j = 1; j < n; j++) t = fma(shP[i * n + j], shX[j * 128 + tid], t);
+                }
+                if (ok) acc[i] = first ? t : acc[i] * t;
+            }
+            if (ok && !first) shift(acc, carry);
+            if (ok) have = true;
+        }
+        const bool none = MASKS && !have;
+        if (!nd.is_root || store_root) {
+            double* dst = pool + (int64_t)nd.out_slot * slot_stride + (int64_t)c * (n + 1) * spad + s;
+#pragma unroll
+            for (int i = 0; i < NP; i++) if (i < n) dst[(int64_t)i * spad] = none ? 0.0 : acc[i];
+            dst[(int64_t)n * spad] = none ? NAN : carry;
+        }
+        if (nd.is_root) {
+            double out;
+            if (none) {
+                out = INFINITY;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NP; i++) if (i < n) acc[i] = acc[i] * pi[i];
+                if (shift_at_root) shift(acc, carry);
+                double sum = acc[0];
+#pragma unroll
+                for (int i = 1; i < NP; i++) if (i < n) sum += acc[i];
+                out = log(sum) + carry;
+            }
+            site_cat[(int64_t)c * spad + s] = out;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------
 // K3: per-site log-likelihood from the per-category values (log-sum-exp with the category
 // weights; identity for one category) and a deterministic two-stage sum of all sites.
@@ -503,7 +607,9 @@ root_combine(const double* __restrict__ site_cat, int ncat, const double* __rest
         if (site_cat[s] == INFINITY) {          // no observation at all in this column: 0. like the reference
             out = 0.0;
         } else if (ncat == 1) {
-            out = site_cat[s];
+            // one category: log(w_0 L) (a single weight other than 1 is the same model as a 2-category mixture
+            // whose other weight is 0; log(1.0) is exactly 0, so the reference's ncat = 1 case is untouched)
+            out = site_cat[s] + log(weights[0]);
         } else {
             double m = site_cat[s];
             for (int c = 1; c < ncat; c++) m = fmax(m, site_cat[(int64_t)c * spad + s]);

@@ -45,8 +45,11 @@ constexpr int FOP_CHERRY = 10;   // ACC = table[offA + ((window >> shA) & offB)]
 // to back, 70 us per 250k sites.)
 constexpr int PACK_ORDER_SMEM = 8192;     // tips whose row indices are staged in shared memory (else read from global)
 
+// `xorder` (nullable): slot k holds state(order[k]) XOR state(xorder[k]) when xorder[k] >= 0 — the reduced program
+// stores every tip of a tabulated clade but the first as its DIFFERENCE from the first, so that the clade's most
+// frequent patterns (all tips equal) index four ADJACENT table entries, one 128-byte line (see fused4t).
 __global__ void __launch_bounds__(256)
-pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__ order, int ntips,
+pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__ order, const int* __restrict__ xorder, int ntips,
            int nwords, uint64_t* __restrict__ packed, int64_t spad, int64_t site0, int64_t site1,
            int* __restrict__ bad_flag)
 {
@@ -62,13 +65,24 @@ pack_tips4(const uint8_t* __restrict__ tips, int64_t ld, const int* __restrict__
     unsigned bad = 0;
     for (int w = 0; w < nwords; w++) {
         unsigned st[32];
+        int row[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) st[j] = tips[(int64_t)ord[min(w * 32 + j, ntips - 1)] * ld + s];
+        for (int j = 0; j < 32; j++) row[j] = ord[min(w * 32 + j, ntips - 1)];      // a negative row is a padding slot
+#pragma unroll
+        for (int j = 0; j < 32; j++) st[j] = tips[(int64_t)max(row[j], 0) * ld + s];
+        if (xorder) {                                  // (every partner row is also a slot of its own: range-checked there)
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int xr = xorder[min(w * 32 + j, ntips - 1)];
+                bad |= (row[j] >= 0 && w * 32 + j < ntips) ? st[j] : 0u;
+                if (xr >= 0) st[j] ^= tips[(int64_t)xr * ld + s];
+            }
+        }
         uint64_t word = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-            if (w * 32 + j < ntips) {
-                bad |= st[j];
+            if (w * 32 + j < ntips && row[j] >= 0) {
+                if (!xorder) bad |= st[j];
                 word |= (uint64_t)(st[j] & 3u) << (2 * j);
             }
         }
@@ -84,8 +98,8 @@ __global__ void __launch_bounds__(256)
 expand_tips2(const uint8_t* __restrict__ in, int64_t ld_in, uint8_t* __restrict__ tips, int64_t ld_out,
              int64_t byte0, int64_t byte1)
 {
-    const int row = blockIdx.y;
-    for (int64_t b = byte0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < byte1; b += (int64_t)gridDim.x * blockDim.x) {
+    const int row = blockIdx.x;          // rows in gridDim.x (no 65535 limit on the taxa), column blocks in gridDim.y
+    for (int64_t b = byte0 + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; b < byte1; b += (int64_t)gridDim.y * blockDim.x) {
         const unsigned v = in[(int64_t)row * ld_in + b];
         const unsigned out = (v & 3u) | ((v & 12u) << 6) | ((v & 48u) << 12) | ((v & 192u) << 18);
         *reinterpret_cast<unsigned*>(tips + (int64_t)row * ld_out + 4 * b) = out;
@@ -98,8 +112,8 @@ expand_tips2(const uint8_t* __restrict__ in, int64_t ld_in, uint8_t* __restrict_
 // warp and row) and writes its sites' four words as two 16-byte stores.  Moves ntaxa/4 bytes in and
 // ntaxa/4 (rounded up to whole words) bytes out per site, against 1.25 + 1.4 bytes per tip for expand + pack.
 __global__ void __launch_bounds__(256)
-pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __restrict__ order, int ntips, int nwords,
-                 uint64_t* __restrict__ packed, int64_t spad, int64_t byte0, int64_t byte1)
+pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __restrict__ order, const int* __restrict__ xorder,
+                 int ntips, int nwords, uint64_t* __restrict__ packed, int64_t spad, int64_t byte0, int64_t byte1)
 {
     __shared__ int s_order[PACK_ORDER_SMEM];
     const bool staged = ntips <= PACK_ORDER_SMEM;
@@ -112,12 +126,22 @@ pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __res
     if (b >= byte1) return;
     for (int w = 0; w < nwords; w++) {
         unsigned v[32];
+        int row[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = in[(int64_t)ord[min(w * 32 + j, ntips - 1)] * ld_in + b];
+        for (int j = 0; j < 32; j++) row[j] = ord[min(w * 32 + j, ntips - 1)];      // a negative row is a padding slot
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = in[(int64_t)max(row[j], 0) * ld_in + b];
+        if (xorder) {                                  // 2-bit fields XOR independently: whole bytes at once
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int xr = xorder[min(w * 32 + j, ntips - 1)];
+                if (xr >= 0) v[j] ^= in[(int64_t)xr * ld_in + b];
+            }
+        }
         uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-            if (w * 32 + j < ntips) {
+            if (w * 32 + j < ntips && row[j] >= 0) {
                 const uint64_t x = v[j];
                 w0 |= (x & 3u) << (2 * j);
                 w1 |= ((x >> 2) & 3u) << (2 * j);
@@ -149,9 +173,9 @@ __global__ void __launch_bounds__(256)
 encode_text(const unsigned char* __restrict__ text, int64_t ld, int width, const unsigned char* __restrict__ lut,
             uint8_t* __restrict__ tips, int64_t tips_ld, int64_t nsites, int* __restrict__ bad_flag)
 {
-    const int row = blockIdx.y;
+    const int row = blockIdx.x;          // rows in gridDim.x, column blocks in gridDim.y
     int bad = 0;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsites; s += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t s = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; s < nsites; s += (int64_t)gridDim.y * blockDim.x) {
         const unsigned char* p = text + (int64_t)row * ld + s * width;
         unsigned st;
         if (width == 1) {
@@ -526,9 +550,11 @@ struct CladeTab {
     int sh0, k;        // bit offset of its first tip in the window, number of leaves
     int ent0;
     int pre;           // >= 0: the table stores P[inner pre / 16] . v instead of v (FUSED_PREAPPLY), else -1
-    int pad[2];
+    int xor_coded;     // the index holds tip 0 and the other tips XOR tip 0 (reduced program, pack_tips4)
+    int pad;
 };
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(256)
 build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict__ tabs, const double* __restrict__ P,
                    const int* __restrict__ inner_nodes, const int* __restrict__ leaf_nodes, int nnodes, int ntab, double thr,
@@ -538,7 +564,11 @@ build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict
     const int c = blockIdx.y;
     const double* Pc = P + (size_t)c * nnodes * 16;
     for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < (1 << (2 * tb.k)); idx += gridDim.z * blockDim.x) {
-        const uint64_t cur = (uint64_t)idx << tb.sh0;          // the window as the kernel would see it
+        uint64_t cur = (uint64_t)idx << tb.sh0;                // the window as the kernel would see it
+        if (tb.xor_coded) {   // the reduced program's fields hold tip 0 and the other tips XOR tip 0 (pack_tips4): undo
+            const uint64_t rep = (uint64_t)(idx & 3) * 0x5555555555555555ull;
+            cur ^= rep & ~3ull & ((1ull << (2 * tb.k)) - 1ull);
+        }
         double v[4] = {1.0, 1.0, 1.0, 1.0}, stk[8][4];
         int sp = 0;
         Scale<SCALE_POW2> sc;
@@ -547,8 +577,9 @@ build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict
             const FusedOp2 o = prog[ip];
             const int code = o.code & 0xff, shA = o.sh & 0xff, shB = o.sh >> 8;
             // inner matrices are row-major (matvec4, the expression of matvec4c); a leaf's column s is P[i*4 + s]
-            auto inner = [&](int off) { return Pc + (size_t)inner_nodes[off / 16] * 16; };
-            auto leaf = [&](int off) { return Pc + (size_t)leaf_nodes[off / 16] * 16; };
+            // (DIRECT: the clade mini-programs of the reduced program address matrices by node id)
+            auto inner = [&](int off) { return Pc + (DIRECT ? (size_t)off : (size_t)inner_nodes[off / 16] * 16); };
+            auto leaf = [&](int off) { return Pc + (DIRECT ? (size_t)off : (size_t)leaf_nodes[off / 16] * 16); };
             const int tA = (int)(cur >> shA) & 3, tB = (int)(cur >> shB) & 3;
             if (code == FOP_APPLY_MUL_TIP) {
                 const double* lf = leaf(o.offB);
@@ -599,7 +630,7 @@ build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict
         }
         if (tb.pre >= 0) {                                      // the consumer's branch matrix, applied here once
             double y[4];
-            matvec4(Pc + (size_t)inner_nodes[tb.pre / 16] * 16, v, y);
+            matvec4(Pc + (DIRECT ? (size_t)tb.pre : (size_t)inner_nodes[tb.pre / 16] * 16), v, y);
 #pragma unroll
             for (int i = 0; i < 4; i++) v[i] = y[i];
         }
@@ -773,6 +804,256 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
                     site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
                 }
+            }
+            if (opw.x & FOP_PUSH_AFTER) {
+#pragma unroll
+                for (int q = 0; q < SPT; q++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                st += 4 * BLOCK * SPT;
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// fused4t: the program over the REDUCED tree.
+//
+// fused4c replaces a tabulated clade's instructions by a look-up but keeps the push / pop structure of the full
+// tree, and an ncu capture (profiles/r02a_*) shows what that costs: the L1 data pipe is the limiter (71 % of its
+// wavefront slots), 40 % of it stack traffic in shared memory (a push and a pop of 128 bytes per site for every
+// node with two inner children, 32 at the bench shape although most of those children are table values) and
+// 60 % table gathers (two 16-byte and one 4-byte gather per look-up).  Here the host plans the program over the
+// tree whose leaves are the tabulated clades and the loose tips (pb_api.cu: build_reduced_program):
+//   * a table value is an OPERAND of its parent's instruction (FOP_TAB_TAB, FOP_APPLY_MUL_TAB, FOP_TAB_TIP,
+//     FOP_MUL_TAB), gathered where it is used: only nodes with two computed children push (7 instead of 32);
+//   * the order of evaluation and the stack depth follow the reduced tree (smaller stack area);
+//   * a table holds P . v, P the matrix of the branch above its clade (the consumer's product, done once per
+//     table entry instead of once per site), and its vector is ONE 32-byte gather (LDG.E.256);
+//   * only the matrices of the reduced tree's inner branches go to the constant bank and only the loose tips'
+//     matrices to shared memory: trees of up to ~1 000 taxa fit the bank.
+// The arithmetic of every node is what fused4c does in the power-of-two mode, in the same order: per-site results
+// are bit-identical (tests/test_parity_gpu.py::test_fused_reduced_program_*).
+// --------------------------------------------------------------------------
+constexpr int FOP_TAB = 11;            // ACC = T[offA][field A]                       (carry += its exponent; no shift)
+constexpr int FOP_TAB_TAB = 12;        // ACC = shiftmul(T[offA][field A], T[offB][field B])
+constexpr int FOP_TAB_TIP = 13;        // ACC = shiftmul(T[offA][field A], col(leaf offB, tip B))
+constexpr int FOP_APPLY_MUL_TAB = 14;  // ACC = shiftmul(P[offA] . ACC, T[offB][field B])
+constexpr int FOP_MUL_TAB = 15;        // ACC = shiftmul(ACC, T[offA][field A])          (arity >= 3)
+// sh word of these instructions: shA | shB << 8 | bitsA << 16 | bitsB << 24  (a field is `bits` wide at bit `sh`
+// of the current window word; a tip is a 2-bit field)
+
+__device__ __forceinline__ void tab_gather(const double* __restrict__ tv, const int* __restrict__ tk, int ent0,
+                                           uint64_t cur, int sh, unsigned mask, double (&v)[4], int& e)
+{
+    const unsigned idx = (unsigned)(cur >> sh) & mask;
+    const double* p = tv + (size_t)(ent0 + idx) * 4;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    e = __ldg(tk + ent0 + idx);
+}
+
+template <int BLOCK, int SPT, int MINB = 0>
+__global__ void __launch_bounds__(BLOCK, MINB ? MINB : (BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1)))
+fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
+        int cat0, int slot0, int nmat, const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
+        const double* __restrict__ pi, double thr, int shift_at_root,
+        const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat)
+{
+    extern __shared__ double sh[];
+    double* shP = sh;                                       // [nleaf][16] loose tips' matrices, transposed
+    double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
+    const int c = cat0 + blockIdx.y, tid = threadIdx.x;
+    const int cbase = (slot0 + blockIdx.y) * nmat * 16;     // this category's matrices in cPinner
+    {
+        const double* Pg = P + (size_t)c * nnodes * 16;
+        for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
+            const int k = idx >> 4, e = idx & 15;
+            shP[k * 16 + (e & 3) * 4 + (e >> 2)] = Pg[(size_t)leaf_nodes[k] * 16 + e];
+        }
+    }
+    __syncthreads();
+    const unsigned pbase = (unsigned)__cvta_generic_to_shared(shP);
+    const double* tv = tabV + (size_t)c * ntab * 4;
+    const int* tk = tabK + (size_t)c * ntab;
+    double pir[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) pir[i] = pi[i];
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t s0 = (tile0 + tile) * (BLOCK * SPT) + tid;
+        double v[SPT][4];
+        Scale<SCALE_POW2> sc[SPT];
+        uint64_t cur[SPT], nxt[SPT];
+        const uint64_t* pk = packed + s0;
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            sc[q].init();
+            cur[q] = pk[q * BLOCK];
+            nxt[q] = pk[spad + q * BLOCK];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[q][i] = 1.0;
+        }
+        pk += 2 * spad;
+        double* st = shS + tid;
+        for (int ip = 0; ip < nops; ip++) {
+            const int4 opw = cProg[ip];
+            const int offA = opw.y, offB = opw.z;
+            const int shA = opw.w & 0xff, shB = (opw.w >> 8) & 0xff;
+            const unsigned mA = (1u << ((opw.w >> 16) & 0xff)) - 1u, mB = (1u << ((unsigned)opw.w >> 24)) - 1u;
+            const int code = opw.x & 0xff;
+            switch (code) {            // (a dense switch: one indexed uniform branch instead of a chain of compares)
+            case FOP_APPLY_MUL_TAB: {
+                double b[SPT][4];
+                int eb[SPT];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) tab_gather(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4];
+                    matvec4c(cbase + offA, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * b[q][i];
+                    sc[q].e += eb[q];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_APPLY_MUL_TIP: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4], t[4];
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
+                    matvec4c(cbase + offA, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_TAB_TAB: {
+                double b[SPT][4];
+                int ea[SPT], eb[SPT];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);
+                    tab_gather(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * b[q][i];
+                    sc[q].e += ea[q] + eb[q];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_ACC_POP: {
+                st -= 4 * BLOCK * SPT;
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double x[4], y[4], z[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+                    matvec4c(cbase + offA, v[q], y);
+                    matvec4c(cbase + offB, x, z);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_TAB_TIP: {
+                int ea[SPT];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double t[4];
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
+                    sc[q].e += ea[q];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_LOADW: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    cur[q] = nxt[q];
+                    nxt[q] = pk[q * BLOCK];
+                }
+                pk += spad;
+            } break;
+            case FOP_TAB: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    int ea;
+                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea);
+                    sc[q].e += ea;
+                }
+            } break;
+            case FOP_MUL_TAB: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double a[4];
+                    int ea;
+                    tab_gather(tv, tk, offA, cur[q], shA, mA, a, ea);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * a[i];
+                    sc[q].e += ea;
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_TIP_TIP: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double a[4], b[4];
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, a);
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, b);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = a[i] * b[i];
+                }
+                shift_all<SPT, SCALE_POW2>(v, sc, thr);
+            } break;
+            case FOP_TIP: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, v[q]);
+            } break;
+            case FOP_APPLY: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double y[4];
+                    matvec4c(cbase + offA, v[q], y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = y[i];
+                }
+            } break;
+            case FOP_MUL_TIP: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    double t[4];
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, t);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_POP_MUL: {
+                st -= 4 * BLOCK * SPT;
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = st[(i * SPT + q) * BLOCK] * v[q][i];
+                    shift4s(v[q], sc[q], thr);
+                }
+            } break;
+            case FOP_ROOT: {
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
+                    if (shift_at_root) shift4s(v[q], sc[q], thr);
+                    const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
+                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                }
+            } break;
+            default: break;
             }
             if (opw.x & FOP_PUSH_AFTER) {
 #pragma unroll

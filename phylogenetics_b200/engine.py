@@ -77,7 +77,7 @@ class LikelihoodContext:
         ci = np.ascontiguousarray(flat.child_idx, dtype=np.int32)
         tr = np.ascontiguousarray(flat.tip_row, dtype=np.int32)
         bl = None if branch_lengths is None else _f64(branch_lengths)
-        if len(cp) != flat.nnodes + 1 or len(tr) != flat.nnodes:
+        if len(cp) != flat.nnodes + 1 or len(tr) != flat.nnodes or len(ci) != flat.nnodes - 1:
             raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tree arrays have the wrong length")
         if bl is not None and len(bl) != flat.nnodes:
             raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "branch_lengths must have nnodes entries")
@@ -141,6 +141,8 @@ class LikelihoodContext:
 
     def set_tip_masks(self, masks):
         masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        if masks.ndim != 2 or masks.shape[0] != self.ntaxa or masks.shape[1] < self.nsites:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "masks must be uint64 [ntaxa][>=nsites]")
         self._ck(lib.pb_set_tip_masks(self._ctx, masks.ctypes.data, masks.shape[1]))
 
     def set_root_frequencies(self, pi):
@@ -221,6 +223,11 @@ class LikelihoodContext:
 
     def enqueue(self):
         self._ck(lib.pb_loglik_enqueue(self._ctx))
+
+    def host_enqueue_ptr(self, host_ptr, ld, packed2=False):
+        """pb_loglik_host_enqueue: the non-blocking half of loglik_host[_packed2]_ptr; finish with fetch().  The
+        host buffer must stay valid and unchanged until then."""
+        self._ck(lib.pb_loglik_host_enqueue(self._ctx, ctypes.c_void_p(host_ptr), int(ld), int(bool(packed2))))
 
     def fetch(self, per_site=False):
         total = ctypes.c_double()

@@ -21,7 +21,19 @@ import math
 
 import numpy as np
 
-from . import engine
+
+
+class _LazyEngine:
+    """The Q / pi builders of this module are pure host code; only the P(t) producers need the native library.
+    Importing it on first use keeps `models` importable by processes that must not load the product library
+    (the CPU reference arm of bench.py generates its inputs with these builders)."""
+
+    def __getattr__(self, name):
+        from . import engine as _engine
+        return getattr(_engine, name)
+
+
+engine = _LazyEngine()
 
 NUCLEOTIDES = "ACGT"
 AMINO_ACIDS = "ACDEFGHIKLMNPQRSTVWY"

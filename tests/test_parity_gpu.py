@@ -458,6 +458,13 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
         check(per_site, total, oracle_per_site(case, P))
         total2 = ctx.loglik_host(case.tips)
         assert total2 == total
+        if pow2:                                            # the default runs the program over the REDUCED tree (fused4t);
+            ctx.set_option("fused_reduced", 0)              # look-ups inside the full program (fused4c): bit-identical
+            total0, per_site0 = ctx.loglik(per_site=True)
+            assert total0 == total and np.array_equal(per_site0, per_site)
+            ctx.set_option("fused_reduced", 1)
+            total0, per_site0 = ctx.loglik(per_site=True)
+            assert total0 == total and np.array_equal(per_site0, per_site)
         ctx.set_option("fused_const_cats", 2)               # two categories per launch share the constant bank
         total3, per_site3 = ctx.loglik(per_site=True)
         assert total3 == total and np.array_equal(per_site3, per_site)
@@ -481,6 +488,57 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
         ctx.set_option("fused_cherry", 0)                   # leaf-leaf nodes computed in the kernel instead of tabulated
         total4, per_site4 = ctx.loglik(per_site=True)
         assert total4 == total and np.array_equal(per_site4, per_site)
+
+
+@pytest.mark.parametrize("ntaxa,nsites,ncat,tree_kind", [(256, 3000, 2, "bd"), (512, 2100, 1, "bd"), (1024, 1500, 1, "bd"),
+                                                        (1500, 1100, 1, "bd"), (200, 5000, 4, "random"), (2, 1300, 4, "bd"),
+                                                        (3, 1300, 1, "bd"), (7, 70000, 2, "bd")])
+def test_fused_reduced_program_tree_sizes(ntaxa, nsites, ncat, tree_kind):
+    """fused4t on trees from 2 to 1 500 taxa (the constant bank holds the reduced tree's matrices up to about 1 000
+    taxa; beyond that the shared-memory kernel takes over), every clade limit, against the oracle and against the
+    untabulated kernels bit for bit."""
+    case = cases.make_case("fusedt", "gtr", ntaxa, nsites, ncat=ncat, seed=11, tree_kind=tree_kind)
+    P = case.host_P()
+    expect = oracle_per_site(case, P)
+    with run_ctx(case, "direct", P=P) as ctx:
+        assert ctx.path_name == "fused4"
+        total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, expect)
+        ctx.set_option("fused_clade_force", 1)
+        for leaves in (6, 4, 2):
+            ctx.set_option("fused_clade_leaves", leaves)
+            t2, p2 = ctx.loglik(per_site=True)
+            assert t2 == total and np.array_equal(p2, per_site), leaves
+        ctx.set_option("fused_cherry", 0)                   # nothing tabulated: the reduced tree is the tree
+        t2, p2 = ctx.loglik(per_site=True)
+        assert t2 == total and np.array_equal(p2, per_site)
+        ctx.set_option("fused_reduced", 0)
+        ctx.set_option("fused_const", 0)                    # the shared-memory kernel, no tables at all
+        t2, p2 = ctx.loglik(per_site=True)
+        assert t2 == total and np.array_equal(p2, per_site)
+
+
+def test_fused_reduced_program_kary_tree_and_felsenstein_mode():
+    """Arities 1..4 (left folds, unary chains, clades of mixed arity) and the Felsenstein conventions."""
+    from phylogenetics_b200 import tree as T, synthetic
+    from test_fused_program_cpu import random_kary_tree
+    for seed in range(4):
+        rng = np.random.default_rng(300 + seed)
+        flat = T.flatten(random_kary_tree(rng, 40 + 17 * seed))
+        bl = flat.branch_lengths(float)
+        Q, pi = synthetic.random_gtr(rng, 10.0)
+        tips = synthetic.simulate_alignment(rng, flat, synthetic.host_transition_matrices(Q, pi, bl), pi, 2300)
+        case = cases.Case("kary%d" % seed, flat, bl, Q, pi, tips)
+        P = case.host_P()
+        for mode in (_lib.PB_MODE_PHYLO_CTMC, _lib.PB_MODE_FELSENSTEIN):
+            with run_ctx(case, "direct", P=P, mode=mode) as ctx:
+                assert ctx.path_name == "fused4"
+                ctx.set_option("fused_clade_force", 1)
+                total, per_site = ctx.loglik(per_site=True)
+                check(per_site, total, oracle_per_site(case, P, mode))
+                ctx.set_option("fused_reduced", 0)
+                t2, p2 = ctx.loglik(per_site=True)
+                assert t2 == total and np.array_equal(p2, per_site)
 
 
 def test_fused_large_tree_falls_back_to_shared_memory_matrices():

@@ -13,6 +13,9 @@ with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
     ctx.set_tree(f, case.bl); ctx.set_categories(case.rates, case.weights); ctx.set_rate_matrix(case.Q, case.pi)
     ctx.set_root_frequencies(case.pi); ctx.set_tips(case.tips)
     ctx.set_option("fused_block", block); ctx.set_option("fused_spt", spt)
+    for kv in filter(None, os.environ.get("OPTS", "").split(",")):       # e.g. OPTS=fused_preapply=1
+        name, val = kv.split("=")
+        ctx.set_option(name, float(val))
     ctx.set_timing(True)
     for _ in range(4):
         tot = ctx.loglik()
