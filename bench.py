@@ -217,7 +217,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sites_per_step": sample, "ntaxa": ntaxa, "nstates": case.n, "ncat": ncat,
+        "config": {"workload": desc, "sites_per_gpu": sample, "sites_per_step": sample, "ntaxa": ntaxa, "nstates": case.n, "ncat": ncat,
                    "internal_nodes": f.ninternal, "sample": sample_desc, "total_loglik": total,
                    "note": "CPU restatement of the reference algorithm (oracle/pruning_oracle.c, OpenMP over "
                            "sites, P(t) precomputed per branch - the CPU-favourable choice), not the OCaml/lacaml "
@@ -406,6 +406,42 @@ def taxa_sweep_block(device, stream, flush, nsites=250_000):
     return out
 
 
+def single_process_block(case, world, tips_pinned, total_local, steps):
+    """the same N-GPU evaluation driven by ONE host thread through pb_create_sharded — one context
+    per device, ncclAllReduce of the scalar inside the library.  Run by rank 0 while the other ranks wait; every shard
+    holds rank 0's columns (the timing does not depend on which columns a device holds), so the total must be
+    N x rank 0's local total."""
+    from phylogenetics_b200.engine import ShardedContext
+    f, nsites = case.flat, case.nsites
+    s = ShardedContext(list(range(world)), case.n, nsites * world, f.nleaves, ncat=case.ncat)
+    s.set_tree(f, case.bl)
+    s.set_categories(case.rates, case.weights)
+    s.set_rate_matrix(case.Q, case.pi)
+    s.set_root_frequencies(case.pi)
+    for d in range(world):
+        assert s.shard_bounds(d) == (d * nsites, (d + 1) * nsites)
+        s.shard_set_tips_ptr(d, tips_pinned.data_ptr(), nsites)
+    for _ in range(3):
+        s.set_branch_lengths(case.bl)
+        total = s.loglik()
+    if not abs(total - world * total_local) <= 1e-12 * abs(total):
+        raise SystemExit("single-process sharded total %r != %d x %r" % (total, world, total_local))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.set_branch_lengths(case.bl)
+        total = s.loglik()                 # blocking: P(t) + pruning + reduction on every device, all-reduce, read-back
+    dt = (time.perf_counter() - t0) / steps
+    s.set_reduce(1)
+    total_ordered = s.loglik()
+    s.close()
+    return {"call": "pb_create_sharded + pb_sharded_set_branch_lengths + pb_sharded_loglik (one host thread, %d devices, "
+                    "ncclAllReduce(ncclDouble, 1) inside the library)" % world,
+            "ms_per_step_wall": dt * 1e3, "value": world * nsites * f.ninternal / dt, "unit": UNIT, "steps": steps,
+            "total": total, "total_ordered_reduce": total_ordered,
+            "note": "wall clock around blocking calls (host launch latency of N devices from one thread and the final "
+                    "synchronisation included), L2 not flushed; every shard holds rank 0's columns"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -526,6 +562,18 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not abs(tot_bytes - total0) <= 1e-12 * abs(total0):
         raise SystemExit("host-buffer and resident evaluations disagree: %r %r" % (tot_bytes, total0))
 
+    single = None
+    if world > 1:
+        # one host thread driving all N devices through the C ABI (pb_create_sharded), while the other ranks idle
+        barrier()
+        if rank == 0:
+            try:
+                single = single_process_block(case, world, tips_pinned, total0, max(5, min(args.steps, 20)))
+            except SystemExit:
+                raise
+            except Exception as e:
+                single = {"error": repr(e)}
+        barrier()
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -598,6 +646,7 @@ def run_ours(args, rank, world, local_rank):
                         "2-bit packing of the host alignment is done once outside the loop"},
         "collective_ms_per_step": (sum(collective_ms) / len(collective_ms)) if world > 1 else 0.0,
         "per_rank_ms": per_rank,
+        "single_process_sharded": single,
         "gpu_launches": int(launches),
         "phase_ms": {"pmat": float(phases[:, 0].mean()), "pruning": prune_avg_ms, "root": float(phases[:, 2].mean())},
         "clocks": clocks,

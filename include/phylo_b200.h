@@ -208,7 +208,7 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   0 (default): accumulate the product of the maxima and take one log), "fused_const" (inner
  *   matrices through the constant bank), "fused_const_cats" (categories per launch), "fused_pow2" (1 (default):
  *   exact power-of-two scale factors; 0: the reference's factor 1/max v), "fused_cherry" (tabulate the nodes
- *   with two leaf children), "fused_clade_leaves" (2..8, default 5: the largest clade whose 4^k
+ *   with two leaf children), "fused_clade_leaves" (2..8, default 7: the largest clade whose 4^k
  *   possible values are tabulated the same way; fewer when the alignment has fewer than 8 * 4^k sites unless
  *   "fused_clade_force"), "fused_triple" (0: cherries only), "fused_reduced" (1 (default): the program over the reduced tree, kernel fused4t;
  *   0: look-ups inside the full program, kernel fused4c).
@@ -237,6 +237,58 @@ int pb_get_timing_at(pb_ctx *ctx, int back, double *ms /* [3] */);
 int64_t pb_kernel_launches(const pb_ctx *ctx);
 /* Which pruning path the next pb_loglik takes: "fused4", "level4", "level_dense", ... */
 const char *pb_path_name(const pb_ctx *ctx);
+
+/* ---- multi-GPU: one host thread, the GPUs of one box ------------------- */
+
+/* Sites are independent given the tree and the model (the reference sums per-site values,
+ * lib/felsenstein.ml:73-75): the alignment's site columns are cut into ndev contiguous shards
+ * (bounds multiples of 4 sites), shard d lives in its own pb_ctx on devices[d], tree / branch lengths / model
+ * / categories are replicated (P(t) is rebuilt on every device), and the ONLY exchange is the all-reduce of
+ * one double per evaluation: ncclAllReduce(ncclDouble, count 1, sum) in place on every device's total, one
+ * communicator per device from ncclCommInitAll, all driven by the calling thread (no MPI, no second process).
+ * NCCL is bound at run time (libnccl.so.2); every NCCL failure — library not found, communicator
+ * initialisation, the collective, a device listed twice — is reported as PB_ERR_NCCL.  ndev = 1 needs no NCCL.
+ * Returns NULL on failure (message: pb_sharded_last_error(NULL)). */
+typedef struct pb_sharded pb_sharded;
+pb_sharded *pb_create_sharded(int ndev, const int *devices, int nstates, int ncat, int64_t nsites_total,
+                              int ntaxa, unsigned flags);
+void pb_sharded_destroy(pb_sharded *s);
+const char *pb_sharded_last_error(const pb_sharded *s);
+int pb_sharded_ndev(const pb_sharded *s);
+/* Shard d's own context (per-device options, timing, pb_get_clv ...) and its columns [lo, hi). */
+pb_ctx *pb_sharded_ctx(pb_sharded *s, int d);
+int pb_sharded_shard_bounds(const pb_sharded *s, int d, int64_t *lo, int64_t *hi);
+/* How the per-device totals are combined: PB_REDUCE_NCCL (default) or PB_REDUCE_ORDERED — the local totals
+ * are read back and added in shard order on the host: bit-reproducible whatever the collective's algorithm. */
+#define PB_REDUCE_NCCL    0
+#define PB_REDUCE_ORDERED 1
+int pb_sharded_set_reduce(pb_sharded *s, int how);
+/* Replicated inputs: the same call on every shard's context (see the pb_set_* of the same name). */
+int pb_sharded_set_mode(pb_sharded *s, int mode);
+int pb_sharded_set_option(pb_sharded *s, const char *name, double value);
+int pb_sharded_set_tree(pb_sharded *s, int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
+                        const int32_t *tip_row, const double *branch_len);
+int pb_sharded_set_branch_lengths(pb_sharded *s, const double *branch_len);
+int pb_sharded_update_branch_length(pb_sharded *s, int node, double t);
+int pb_sharded_set_root_frequencies(pb_sharded *s, const double *pi);
+int pb_sharded_set_categories(pb_sharded *s, const double *rates, const double *weights);
+int pb_sharded_set_eigensystem(pb_sharded *s, const double *U, const double *lambda, const double *Uinv);
+int pb_sharded_set_rate_matrix(pb_sharded *s, const double *Q, const double *pi);
+int pb_sharded_set_rate_matrix_general(pb_sharded *s, const double *Q);
+int pb_sharded_set_pmatrices(pb_sharded *s, const double *P);
+/* Sharded inputs: the caller passes the FULL alignment ([ntaxa][ld], ld >= nsites_total); every shard copies its
+ * own columns (one strided copy per device). */
+int pb_sharded_set_tips(pb_sharded *s, const uint8_t *states, int64_t ld);
+int pb_sharded_set_tips_packed2(pb_sharded *s, const uint8_t *packed, int64_t ld);
+int pb_sharded_set_tip_masks(pb_sharded *s, const uint64_t *masks, int64_t ld);
+/* One evaluation: P(t) + pruning + root reduction enqueued on every device, the all-reduce behind them, then the
+ * total (identical on every device) and, when per_site != NULL, every site's value [nsites_total] in the order of
+ * the alignment.  Blocking. */
+int pb_sharded_loglik(pb_sharded *s, double *total, double *per_site);
+/* The same straight from a HOST alignment (pb_loglik_host / pb_loglik_host_packed2 per shard, copies overlapped
+ * with the pruning on every device; packed2 != 0: the 2-bit layout). */
+int pb_sharded_loglik_host(pb_sharded *s, const uint8_t *states, int64_t ld, int packed2, double *total,
+                           double *per_site);
 
 /* ---- stand-alone P(t) producers (no context) -------------------------- */
 

@@ -21,6 +21,7 @@ PB_ERR_NUMERIC = -6
 
 PB_FLAG_KEEP_CLV = 0x1
 PB_FLAG_LEVEL_KERNELS = 0x2
+PB_REDUCE_NCCL, PB_REDUCE_ORDERED = 0, 1
 PB_MODE_PHYLO_CTMC = 0
 PB_MODE_FELSENSTEIN = 1
 PB_ALPHABET_DNA, PB_ALPHABET_AMINO_ACID, PB_ALPHABET_CODON = 0, 1, 2
@@ -34,6 +35,12 @@ EXPORTS = [
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_version",
+    "pb_create_sharded", "pb_sharded_destroy", "pb_sharded_last_error", "pb_sharded_ndev", "pb_sharded_ctx",
+    "pb_sharded_shard_bounds", "pb_sharded_set_reduce", "pb_sharded_set_mode", "pb_sharded_set_option", "pb_sharded_set_tree",
+    "pb_sharded_set_branch_lengths", "pb_sharded_update_branch_length", "pb_sharded_set_root_frequencies",
+    "pb_sharded_set_categories", "pb_sharded_set_eigensystem", "pb_sharded_set_rate_matrix",
+    "pb_sharded_set_rate_matrix_general", "pb_sharded_set_pmatrices", "pb_sharded_set_tips", "pb_sharded_set_tips_packed2",
+    "pb_sharded_set_tip_masks", "pb_sharded_loglik", "pb_sharded_loglik_host",
 ]
 
 
@@ -102,6 +109,29 @@ def _load():
         "pb_transition_matrices_expm": (ci, [ci, ci, ci, vp, vp, vp]),
         "pb_host_reversible_eigensystem": (ci, [ci, vp, vp, vp, vp, vp]),
         "pb_debug_fused_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, vp, ci, vp, vp, vp, vp, ci]),
+        "pb_create_sharded": (vp, [ci, vp, ci, ci, i64, ci, ctypes.c_uint]),
+        "pb_sharded_destroy": (None, [vp]),
+        "pb_sharded_last_error": (ctypes.c_char_p, [vp]),
+        "pb_sharded_ndev": (ci, [vp]),
+        "pb_sharded_ctx": (vp, [vp, ci]),
+        "pb_sharded_shard_bounds": (ci, [vp, ci, vp, vp]),
+        "pb_sharded_set_reduce": (ci, [vp, ci]),
+        "pb_sharded_set_mode": (ci, [vp, ci]),
+        "pb_sharded_set_option": (ci, [vp, ctypes.c_char_p, dbl]),
+        "pb_sharded_set_tree": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+        "pb_sharded_set_branch_lengths": (ci, [vp, vp]),
+        "pb_sharded_update_branch_length": (ci, [vp, ci, dbl]),
+        "pb_sharded_set_root_frequencies": (ci, [vp, vp]),
+        "pb_sharded_set_categories": (ci, [vp, vp, vp]),
+        "pb_sharded_set_eigensystem": (ci, [vp, vp, vp, vp]),
+        "pb_sharded_set_rate_matrix": (ci, [vp, vp, vp]),
+        "pb_sharded_set_rate_matrix_general": (ci, [vp, vp]),
+        "pb_sharded_set_pmatrices": (ci, [vp, vp]),
+        "pb_sharded_set_tips": (ci, [vp, vp, i64]),
+        "pb_sharded_set_tips_packed2": (ci, [vp, vp, i64]),
+        "pb_sharded_set_tip_masks": (ci, [vp, vp, i64]),
+        "pb_sharded_loglik": (ci, [vp, vp, vp]),
+        "pb_sharded_loglik_host": (ci, [vp, vp, i64, ci, vp, vp]),
         "pb_debug_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, ci]),
         "pb_version": (ctypes.c_char_p, []),
     }

@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libphylo_b200.so")
-SOURCES = ["pb_api.cu", "pb_host_linalg.cpp"]
+SOURCES = ["pb_api.cu", "pb_host_linalg.cpp", "pb_sharded.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
@@ -35,7 +35,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         return out
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
-          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -112,6 +112,8 @@ struct pb_ctx {
     std::vector<int> tip_order;         // tip rows in the order the fused program consumes them
     int fstack = 0, fwords = 0;
     int fused_block = 256, fused_spt = 4, fused_exact_log = 0;
+    bool fused_spt_set = false;            // "fused_spt" given explicitly; else fused4t runs 2 sites per thread (72 registers,
+                                           // 3 blocks per SM: measured faster than 4 sites per thread, profiles/r02c_*)
     std::vector<FusedOp2> fprog_tab;       // fprog_c with the small clades turned into table look-ups (FOP_CHERRY)
     std::vector<pbk::CladeTab> clades;     // the tabulated clades of fprog_tab
     int fused_preapply = 0;                // option "fused_preapply" (only in a build with -DFUSED_PREAPPLY=1)
@@ -124,17 +126,30 @@ struct pb_ctx {
     int fprog_bank_nops = 0;               // length of the program variant launch_fused4c put in the constant bank
     int fused_triple = 1;                  // option "fused_triple": 0 = tabulate cherries only
     int fused_clade_force = 0;             // option "fused_clade_force" (test hook): tabulate up to the limit however few the sites
-    int fused_clade_leaves = 5;            // option "fused_clade_leaves": largest tabulated clade (2..6 leaves)
+    int fused_clade_leaves = 7;            // option "fused_clade_leaves": largest tabulated clade (2..8 leaves; 7: profiles/r02c_*)
     // fused4t: the program over the reduced tree (build_reduced_program)
     int fused_reduced = 1;                 // option "fused_reduced": 1 (default) = fused4t, 0 = fused4c with look-ups in the full program
     std::vector<FusedOp2> rprog, cprog;    // reduced program; the clades' own (untabulated, node-addressed) instruction ranges
     std::vector<int> rorder;               // packed-tip slot -> tip row (-1: padding), 32 slots per word, in reduced-program order
     std::vector<int> rxorder;              // ... and the row whose state is XORed into the slot (-1: none): difference coding
     int fused_xor = 1;                     // option "fused_xor": difference-code the tips of a tabulated clade
+    int fused_masks = 1;                   // option "fused_masks": tip state sets run the reduced program (0: the level kernel)
     int fused_occ = 0;                     // option "fused_occ": 4 = fused4t<256, 2> compiled for 4 blocks per SM (64 registers)
     std::vector<int> rmat_nodes, rleaf_nodes;   // branches whose matrices the reduced program applies / looks columns up in
     std::vector<pbk::CladeTab> rclades;
     int rwords = 0, rstack = 0, rntab = 0, r_leaves = -1;
+    // tip state sets in the reduced program (4 states): the alignment's distinct sets are its alphabet (pb_set_tip_masks)
+    int mask_radix = 0;                    // how many distinct state sets occur (0: not scanned)
+    unsigned char mask_code[16] = {}, mask_set[16] = {};    // set -> code, code -> set
+    DevBuf<unsigned char> d_mask_code, d_mask_set;
+    DevBuf<unsigned> d_mask_present;
+    std::vector<pbk::PackField> rfields;   // the packed fields of the masked plan and the tip rows they encode
+    std::vector<int> rfield_rows;
+    DevBuf<pbk::PackField> d_rfields;
+    DevBuf<int> d_rfield_rows;
+    int r_radix = 0;                       // alphabet the plan was made for (4 = plain states)
+    bool r_masked = false;
+    int r_tipbits = 2;
     bool packed_for_reduced = false;       // which slot order d_packed currently holds
     bool reduced_fits = false;             // the last plan fits the constant bank and shared memory (want_reduced)
     DevBuf<FusedOp2> d_rprog, d_cprog;
@@ -276,8 +291,9 @@ size_t fused_smem_bytes(const pb_ctx* c)
 
 int path_of(const pb_ctx* c)
 {
-    const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0 || c->have_masks;
-    if (c->have_masks) return PATH_LEVEL_DENSE;
+    const bool level = (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) != 0;
+    // tip state sets: the reduced 4-state program when it fits, else the scalar level kernel
+    if (c->have_masks) return (c->n == 4 && !level && c->have_tree && c->reduced_fits) ? PATH_FUSED4 : PATH_LEVEL_DENSE;
     if (c->n == 4) {
         if (!level && c->have_tree) {
             // the reduced program (fused4t) keeps only the loose tips' matrices in shared memory; the all-shared-memory
@@ -1048,6 +1064,18 @@ void fold_pushes(std::vector<FusedOp2>& prog)
 int build_reduced_program(pb_ctx* c, int max_leaves)
 {
     const int nn = c->nnodes;
+    // plain states: radix 4, a tip is a 2-bit field; state sets (pb_set_tip_masks): the alignment's distinct sets are
+    // the alphabet, a clade of k tips has radix^k entries indexed in mixed radix, capped at the 4^max_leaves of the plain form
+    const bool masked = c->have_masks;
+    const int radix = masked ? std::max(c->mask_radix, 1) : 4;
+    auto bits_for = [](int64_t entries) { int b = 0; while (((int64_t)1 << b) < entries) b++; return b; };
+    std::vector<int64_t> pw(10, 1);
+    for (int k = 1; k < 10; k++) pw[k] = pw[k - 1] * radix;
+    int kmax = 0;
+    if (max_leaves >= 2)
+        for (int k = 1; k <= 8; k++)
+            if (pw[k] <= ((int64_t)1 << (2 * max_leaves))) kmax = k;
+    const int tipbits = masked ? bits_for(radix) : 2;
     auto is_leaf = [&](int v) { return c->child_ptr[v] == c->child_ptr[v + 1]; };
     // post-order and leaves below every node
     std::vector<int> order;
@@ -1078,7 +1106,7 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
         const int par = c->parent[v];
         if (par >= 0 && kind[par] >= 2) { kind[v] = 3; continue; }
         if (is_leaf(v)) kind[v] = 1;
-        else kind[v] = (max_leaves >= 2 && nleaves[v] <= max_leaves) ? 2 : 0;
+        else kind[v] = (kmax >= 2 && nleaves[v] <= kmax) ? 2 : 0;
     }
     std::vector<int> su;
     stack_need(c, order, kind, su);
@@ -1110,7 +1138,8 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
             t.k = nleaves[v];
             t.ent0 = c->rntab;
             t.pre = v == c->root ? -1 : v * 16;               // the table holds P[v] . clv(v): the consumer's product
-            t.xor_coded = c->fused_xor ? 1 : 0;
+            t.xor_coded = (c->fused_xor && !masked) ? 1 : 0;
+            t.radix = radix;
             std::vector<int> tips;
             auto field = [&](int leaf) { tips.push_back(leaf); return 2 * ((int)tips.size() - 1); };
             std::vector<FusedOp2> ops;
@@ -1130,7 +1159,7 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
             clade_of[v] = (int)c->rclades.size();
             c->rclades.push_back(t);
             clade_tips.push_back(tips);
-            c->rntab += 1 << (2 * t.k);
+            c->rntab += (int)pw[t.k];
         }
     }
 
@@ -1140,56 +1169,72 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
     c->rleaf_nodes.clear();
     std::vector<int> mat_idx(nn, -1), leaf_idx(nn, -1);
     auto mat = [&](int v) { if (mat_idx[v] < 0) { mat_idx[v] = (int)c->rmat_nodes.size(); c->rmat_nodes.push_back(v); } return mat_idx[v] * 16; };
-    auto leafm = [&](int v) { if (leaf_idx[v] < 0) { leaf_idx[v] = (int)c->rleaf_nodes.size(); c->rleaf_nodes.push_back(v); } return leaf_idx[v] * 16; };
+    // (a loose tip's columns in shared memory: 16 doubles, or 4 per state set of the alphabet)
+    auto leafm = [&](int v) { if (leaf_idx[v] < 0) { leaf_idx[v] = (int)c->rleaf_nodes.size(); c->rleaf_nodes.push_back(v); }
+                              return leaf_idx[v] * (masked ? 4 * radix : 16); };
     c->rprog.clear();
     c->rorder.clear();
     c->rxorder.clear();
-    int bitpos = 0;
+    c->rfields.clear();
+    c->rfield_rows.clear();
+    int bitpos = 0, wordno = 0;
+    auto tab_bits = [&](int v) { return masked ? bits_for(pw[nleaves[v]]) : 2 * nleaves[v]; };
     auto reserve_bits = [&](int bits) {
         if (bitpos + bits > 64) {
             c->rorder.resize((c->rorder.size() + 31) / 32 * 32, -1);
             c->rxorder.resize(c->rorder.size(), -1);
             c->rprog.push_back({pbk::FOP_LOADW, 0, 0, 0});
             bitpos = 0;
+            wordno++;
         }
     };
     auto tip_field = [&](int leaf) {
         const int sh = bitpos;
-        c->rorder.push_back(c->tip_row[leaf]);
-        c->rxorder.push_back(-1);
-        bitpos += 2;
+        if (masked) {
+            c->rfields.push_back({wordno, sh, (int)c->rfield_rows.size(), 1});
+            c->rfield_rows.push_back(c->tip_row[leaf]);
+        } else {
+            c->rorder.push_back(c->tip_row[leaf]);
+            c->rxorder.push_back(-1);
+        }
+        bitpos += tipbits;
         return sh;
     };
-    auto tab_field = [&](int v) {       // the clade's tips in the order its own range consumes them; all but the first
-        const int sh = bitpos;          // as differences from the first (a table's hot entries become neighbours)
+    auto tab_field = [&](int v) {       // the clade's tips in the order its own range consumes them; plain states: all
+        const int sh = bitpos;          // but the first as differences from the first (a table's hot entries become neighbours)
         const std::vector<int>& tips = clade_tips[clade_of[v]];
-        for (size_t j = 0; j < tips.size(); j++) {
-            c->rorder.push_back(c->tip_row[tips[j]]);
-            c->rxorder.push_back(j > 0 && c->fused_xor ? c->tip_row[tips[0]] : -1);
+        if (masked) {
+            c->rfields.push_back({wordno, sh, (int)c->rfield_rows.size(), (int)tips.size()});
+            for (int leaf : tips) c->rfield_rows.push_back(c->tip_row[leaf]);
+        } else {
+            for (size_t j = 0; j < tips.size(); j++) {
+                c->rorder.push_back(c->tip_row[tips[j]]);
+                c->rxorder.push_back(j > 0 && c->fused_xor ? c->tip_row[tips[0]] : -1);
+            }
         }
-        bitpos += 2 * nleaves[v];
+        bitpos += tab_bits(v);
         return sh;
     };
     auto ent = [&](int v) { return c->rclades[clade_of[v]].ent0; };
     for (const RAbs& a : aops) {
         FusedOp2 o{a.code, 0, 0, 0};
         switch (a.code) {
-        case pbk::FOP_TIP_TIP: { reserve_bits(4); const int sa = tip_field(a.a), sb = tip_field(a.b);
+        case pbk::FOP_TIP_TIP: { reserve_bits(2 * tipbits); const int sa = tip_field(a.a), sb = tip_field(a.b);
                                  o.offA = leafm(a.a); o.offB = leafm(a.b); o.sh = sa | (sb << 8); break; }
-        case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: { reserve_bits(2); o.offA = leafm(a.a); o.sh = tip_field(a.a); break; }
+        case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: { reserve_bits(tipbits); o.offA = leafm(a.a); o.sh = tip_field(a.a); break; }
         case pbk::FOP_APPLY: o.offA = mat(a.a); break;
-        case pbk::FOP_APPLY_MUL_TIP: { reserve_bits(2); o.offA = mat(a.a); o.offB = leafm(a.b); o.sh = tip_field(a.b) << 8; break; }
+        case pbk::FOP_APPLY_MUL_TIP: { reserve_bits(tipbits); o.offA = mat(a.a); o.offB = leafm(a.b); o.sh = tip_field(a.b) << 8; break; }
         case pbk::FOP_ACC_POP: o.offA = mat(a.a); o.offB = mat(a.b); break;
-        case pbk::FOP_TAB: case pbk::FOP_MUL_TAB: { reserve_bits(2 * nleaves[a.a]); o.offA = ent(a.a);
-                                                    o.sh = tab_field(a.a) | ((2 * nleaves[a.a]) << 16); break; }
-        case pbk::FOP_TAB_TAB: { reserve_bits(2 * (nleaves[a.a] + nleaves[a.b])); o.offA = ent(a.a); o.offB = ent(a.b);
+        case pbk::FOP_TAB: case pbk::FOP_MUL_TAB: { reserve_bits(tab_bits(a.a)); o.offA = ent(a.a);
+                                                    o.sh = tab_field(a.a) | (tab_bits(a.a) << 16); break; }
+        case pbk::FOP_TAB_TAB: { reserve_bits(tab_bits(a.a) + tab_bits(a.b)); o.offA = ent(a.a); o.offB = ent(a.b);
                                  const int sa = tab_field(a.a), sb = tab_field(a.b);
-                                 o.sh = sa | (sb << 8) | ((2 * nleaves[a.a]) << 16) | ((2 * nleaves[a.b]) << 24); break; }
-        case pbk::FOP_TAB_TIP: { reserve_bits(2 * nleaves[a.a] + 2); o.offA = ent(a.a); o.offB = leafm(a.b);
+                                 o.sh = sa | (sb << 8) | (tab_bits(a.a) << 16) | (tab_bits(a.b) << 24); break; }
+        case pbk::FOP_TAB_TIP: { reserve_bits(tab_bits(a.a) + tipbits); o.offA = ent(a.a); o.offB = leafm(a.b);
                                  const int sa = tab_field(a.a), sb = tip_field(a.b);
-                                 o.sh = sa | (sb << 8) | ((2 * nleaves[a.a]) << 16); break; }
-        case pbk::FOP_APPLY_MUL_TAB: { reserve_bits(2 * nleaves[a.b]); o.offA = mat(a.a); o.offB = ent(a.b);
-                                       o.sh = (tab_field(a.b) << 8) | ((2 * nleaves[a.b]) << 24); break; }
+                                 o.sh = sa | (sb << 8) | (tab_bits(a.a) << 16); break; }
+        case pbk::FOP_APPLY_MUL_TAB: { reserve_bits(tab_bits(a.b)); o.offA = mat(a.a); o.offB = ent(a.b);
+                                       o.sh = (tab_field(a.b) << 8) | (tab_bits(a.b) << 24); break; }
         default: break;                                       // FOP_PUSH, FOP_POP_MUL, FOP_ROOT
         }
         c->rprog.push_back(o);
@@ -1197,8 +1242,11 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
     fold_pushes(c->rprog);
     c->rorder.resize(std::max<size_t>((c->rorder.size() + 31) / 32 * 32, 32), -1);
     c->rxorder.resize(c->rorder.size(), -1);
-    c->rwords = (int)c->rorder.size() / 32;
+    c->rwords = masked ? wordno + 1 : (int)c->rorder.size() / 32;
     c->r_leaves = max_leaves;
+    c->r_radix = radix;
+    c->r_masked = masked;
+    c->r_tipbits = tipbits;
     c->tables_stale = true;
     c->pack_dirty = true;                 // the slot order follows the plan: tips packed for another limit are stale
     if (c->plan_only) return PB_OK;
@@ -1217,20 +1265,28 @@ int build_reduced_program(pb_ctx* c, int max_leaves)
     PB_CUDA(c, cudaMemcpyAsync(c->d_rmat_nodes.p, c->rmat_nodes.data(), c->rmat_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_rleaf_nodes.p, c->rleaf_nodes.data(), c->rleaf_nodes.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_rclades.p, c->rclades.data(), c->rclades.size() * sizeof(pbk::CladeTab), cudaMemcpyHostToDevice, c->stream));
+    if (masked) {
+        PB_CUDA(c, c->d_rfields.ensure(std::max<size_t>(c->rfields.size(), 1)));
+        PB_CUDA(c, c->d_rfield_rows.ensure(std::max<size_t>(c->rfield_rows.size(), 1)));
+        PB_CUDA(c, cudaMemcpyAsync(c->d_rfields.p, c->rfields.data(), c->rfields.size() * sizeof(pbk::PackField), cudaMemcpyHostToDevice, c->stream));
+        PB_CUDA(c, cudaMemcpyAsync(c->d_rfield_rows.p, c->rfield_rows.data(), c->rfield_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     return PB_OK;
 }
 
 size_t fused4t_smem_for(const pb_ctx* c, int block, int spt)
 {
-    return (size_t)c->rleaf_nodes.size() * 16 * 8 + (size_t)std::max(c->rstack, 1) * 4 * block * spt * 8;
+    return (size_t)c->rleaf_nodes.size() * (c->r_masked ? 4 * c->r_radix : 16) * 8 +
+           (size_t)std::max(c->rstack, 1) * 4 * block * spt * 8;
 }
 
 bool fused4t_shape(const pb_ctx* c, int* block, int* spt)
 {
-    const int cand[5][2] = {{c->fused_block, c->fused_spt}, {256, 2}, {128, 2}, {256, 1}, {0, 0}};
+    const int cand[5][2] = {{c->fused_block, c->fused_spt_set ? c->fused_spt : 2}, {256, 2}, {128, 2}, {256, 1}, {0, 0}};
     for (const auto& k : cand) {
         const int key = k[0] * 10 + k[1];
-        const bool compiled = key == 2561 || key == 2562 || key == 2564 || key == 1282 || key == 1284;
+        const bool compiled = c->r_masked ? (key == 2561 || key == 2562)       // (the state-set form: two shapes)
+                                          : (key == 2561 || key == 2562 || key == 2564 || key == 1282 || key == 1284);
         if (compiled && fused4t_smem_for(c, k[0], k[1]) <= c->smem_optin) { *block = k[0]; *spt = k[1]; return true; }
     }
     return false;
@@ -1242,9 +1298,10 @@ int want_reduced(pb_ctx* c, bool* yes)
     *yes = false;
     c->reduced_fits = false;
     if (!c->fused_reduced || !c->fused_const || !c->fused_pow2 || c->fused_exact_log || c->n != 4 || !c->have_tree ||
-        (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) || c->have_masks) return PB_OK;
+        (c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS)) || (c->have_masks && (!c->fused_masks || c->mask_radix < 1)))
+        return PB_OK;
     const int want_leaves = clade_limit(c);
-    if (c->r_leaves != want_leaves) {
+    if (c->r_leaves != want_leaves || c->r_masked != c->have_masks || (c->have_masks && c->r_radix != c->mask_radix)) {
         const int rc = build_reduced_program(c, want_leaves);
         if (rc != PB_OK) return rc;
     }
@@ -1255,10 +1312,10 @@ int want_reduced(pb_ctx* c, bool* yes)
     return PB_OK;
 }
 
-template <int BLOCK, int SPT, int MINB = 0>
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
 int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
 {
-    auto kern = pbk::fused4t<BLOCK, SPT, MINB>;
+    auto kern = pbk::fused4t<BLOCK, SPT, MINB, MASKS>;
     const size_t smem = fused4t_smem_for(c, BLOCK, SPT);
     PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -1270,13 +1327,17 @@ int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
         cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
-        c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p);
+        c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p,
+        c->r_radix, (1u << c->r_tipbits) - 1u, c->d_mask_set.p);
     c->launches++;
     return PB_OK;
 }
 
 int launch_fused4t_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slot0, int64_t site0, int64_t site1)
 {
+    if (c->r_masked)
+        return spt == 2 ? launch_fused4t_variant<256, 2, 0, true>(c, cat0, k, slot0, site0, site1)
+                        : launch_fused4t_variant<256, 1, 0, true>(c, cat0, k, slot0, site0, site1);
     switch (block * 10 + spt) {
     case 2562: return c->fused_occ == 4 ? launch_fused4t_variant<256, 2, 4>(c, cat0, k, slot0, site0, site1)   // 64 registers
                                         : launch_fused4t_variant<256, 2>(c, cat0, k, slot0, site0, site1);     // 72 registers
@@ -1309,7 +1370,7 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_rmat_nodes.p, nmat, c->nnodes, c->d_Pc.p);
         c->launches++;
     }
-    const uint64_t want_version = c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2;
+    const uint64_t want_version = (c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2) * 32 + (c->r_masked ? c->r_radix : 0);
     if (g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, c->d_rprog.p, c->rprog.size() * sizeof(FusedOp2), 0,
                                            cudaMemcpyDeviceToDevice, c->stream));
@@ -1320,12 +1381,21 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         c->tab_variant = 2;
         PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * c->rntab * 4));
         PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->rntab));
-        int kmax = 1;
-        for (const pbk::CladeTab& t : c->rclades) kmax = std::max(kmax, t.k);
-        const unsigned gz = (unsigned)std::max(1, (1 << (2 * kmax)) / 256);
-        pbk::build_clade_tables<true><<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
-            c->d_cprog.p, c->d_rclades.p, c->d_P.p, nullptr, nullptr, c->nnodes, c->rntab, c->threshold,
-            c->d_cherry_v.p, c->d_cherry_k.p);
+        int64_t emax = 1;
+        for (const pbk::CladeTab& t : c->rclades) {
+            int64_t e = 1;
+            for (int j = 0; j < t.k; j++) e *= t.radix;
+            emax = std::max(emax, e);
+        }
+        const unsigned gz = (unsigned)std::max<int64_t>(1, emax / 256);
+        if (c->r_masked)
+            pbk::build_clade_tables_masks<<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
+                c->d_cprog.p, c->d_rclades.p, c->d_P.p, c->nnodes, c->rntab, c->threshold, c->r_radix, c->d_mask_set.p,
+                c->d_cherry_v.p, c->d_cherry_k.p);
+        else
+            pbk::build_clade_tables<true><<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
+                c->d_cprog.p, c->d_rclades.p, c->d_P.p, nullptr, nullptr, c->nnodes, c->rntab, c->threshold,
+                c->d_cherry_v.p, c->d_cherry_k.p);
         c->launches++;
         c->tables_stale = false;
     }
@@ -1547,13 +1617,21 @@ int run_pruning(pb_ctx* c)
     }
     const int path = path_of(c);
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
-    if (path != PATH_FUSED4 || c->pack_dirty) {
+    if ((path != PATH_FUSED4 || c->pack_dirty) && !c->have_masks) {
         const int rc = ensure_tip_bytes(c);
         if (rc != PB_OK) return rc;
     }
     if (path == PATH_FUSED4) {
         int rc = PB_OK;
-        if (c->pack_dirty || c->packed_for_reduced != reduced) {
+        if (c->have_masks && (c->pack_dirty || !c->packed_for_reduced)) {
+            PB_CUDA(c, c->d_packed.ensure((size_t)(c->rwords + 2) * c->spad));
+            pbk::pack_fields_masks<<<(unsigned)((c->spad + 255) / 256), 256, 0, c->stream>>>(
+                c->d_masks.p, c->spad, c->d_rfields.p, (int)c->rfields.size(), c->d_rfield_rows.p, c->d_mask_code.p, c->r_radix,
+                c->rwords, c->d_packed.p, c->spad, 0, c->spad);
+            c->launches++;
+            c->pack_dirty = false;
+            c->packed_for_reduced = true;
+        } else if (c->pack_dirty || c->packed_for_reduced != reduced) {
             if (c->tip_bytes_stale && (rc = ensure_tip_bytes(c)) != PB_OK) return rc;
             const int nwords = reduced ? c->rwords : c->fwords;
             PB_CUDA(c, c->d_packed.ensure((size_t)(nwords + 2) * c->spad));
@@ -2098,8 +2176,29 @@ int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
     PB_CUDA(c, cudaMemcpy2DAsync(c->d_masks.p, c->spad * sizeof(uint64_t), masks, ld * sizeof(uint64_t),
                                  c->nsites * sizeof(uint64_t), c->ntaxa, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    c->mask_radix = 0;
+    if (c->n == 4) {
+        // which of the 16 possible state sets occur: they are the alphabet of the site-resident form (fused4t)
+        PB_CUDA(c, c->d_mask_present.ensure(1));
+        PB_CUDA(c, c->d_mask_code.ensure(16));
+        PB_CUDA(c, c->d_mask_set.ensure(16));
+        PB_CUDA(c, cudaMemsetAsync(c->d_mask_present.p, 0, sizeof(unsigned), c->stream));
+        pbk::mask_alphabet<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_masks.p, c->spad, c->nsites, c->ntaxa, c->d_mask_present.p);
+        c->launches++;
+        unsigned present = 0;
+        PB_CUDA(c, cudaMemcpyAsync(&present, c->d_mask_present.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        PB_CUDA(c, cudaStreamSynchronize(c->stream));
+        present |= 1u;                                      // padding columns hold the empty set: always code 0
+        for (int m = 0; m < 16; m++) {
+            c->mask_code[m] = 0;
+            if ((present >> m) & 1u) { c->mask_code[m] = (unsigned char)c->mask_radix; c->mask_set[c->mask_radix++] = (unsigned char)m; }
+        }
+        PB_CUDA(c, cudaMemcpyAsync(c->d_mask_code.p, c->mask_code, 16, cudaMemcpyHostToDevice, c->stream));
+        PB_CUDA(c, cudaMemcpyAsync(c->d_mask_set.p, c->mask_set, 16, cudaMemcpyHostToDevice, c->stream));
+    }
     PB_CUDA(c, cudaStreamSynchronize(c->stream));     // the caller's (possibly pinned) buffer has been read
     c->fresh = false;
+    c->pack_dirty = true;
     c->have_masks = true;
     c->have_tips = true;
     c->all_dirty = true;
@@ -2638,6 +2737,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_spt") {
         if (iv != 1 && iv != 2 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_spt must be 1, 2 or 4");
         c->fused_spt = iv;
+        c->fused_spt_set = true;
     } else if (k == "fused_const_cats") {
         if (iv < 1 || iv > 8) return fail(c, PB_ERR_INVALID_ARG, "fused_const_cats must be in 1..8");
         c->fused_const_cats = iv;
@@ -2645,6 +2745,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_const = iv != 0;
     } else if (k == "fused_reduced") {
         c->fused_reduced = iv != 0;
+    } else if (k == "fused_masks") {
+        c->fused_masks = iv != 0;
     } else if (k == "fused_occ") {
         if (iv != 0 && iv != 4) return fail(c, PB_ERR_INVALID_ARG, "fused_occ must be 0 or 4");
         c->fused_occ = iv;

@@ -551,7 +551,7 @@ struct CladeTab {
     int ent0;
     int pre;           // >= 0: the table stores P[inner pre / 16] . v instead of v (FUSED_PREAPPLY), else -1
     int xor_coded;     // the index holds tip 0 and the other tips XOR tip 0 (reduced program, pack_tips4)
-    int pad;
+    int radix;         // entries = radix^k: 4 states, or the alignment's distinct state sets (build_clade_tables_masks)
 };
 
 template <bool DIRECT>
@@ -852,29 +852,220 @@ __device__ __forceinline__ void tab_gather(const double* __restrict__ tv, const 
     e = __ldg(tk + ent0 + idx);
 }
 
-template <int BLOCK, int SPT, int MINB = 0>
+// ---- tip state SETS in the site-resident kernel (Missing_values / Ambiguous, lib/phylo_ctmc.ml:145-172, :232-302) ----
+// MASKS = true: a tip is one of the `radix` distinct state sets the alignment contains (code 0..radix-1; pb_set_tip_masks
+// scans them), a tabulated clade of k tips has radix^k entries indexed in mixed radix, and a loose tip's column is the sum
+// of the set's columns of P (dgemv against the 0/1 indicator, ascending j).  The empty set is a missing observation:
+// "None".  None is carried in memory (table entries, leaf columns, the stack) as v[0] == -1 and in registers as one flag
+// per site; the reference's rule (Missing_values.maybe_sv_mul :146-150, Ambiguous.pruning :289-296) is
+//     None x None = None,  None x v = v (NO shift),  v x w = SV.mul v w (shift),
+// and the branch matrix of a None subtree is never applied; a site with no observation at all has log-likelihood 0.
+constexpr double NONE_MARK = -1.0;
+
+template <bool MASKS>
+__device__ __forceinline__ bool is_none(const double (&x)[4]) { return MASKS && x[0] == NONE_MARK; }
+
+// v = a (x) b under the rule above; returns whether the product was formed (only then SV.mul shifts)
+template <bool MASKS>
+__device__ __forceinline__ bool combine4(double (&v)[4], bool& nv, const double (&a)[4], bool na, const double (&b)[4], bool nb)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double r = a[i] * b[i];
+        if (MASKS) { r = nb ? a[i] : r; r = na ? b[i] : r; }
+        v[i] = r;
+    }
+    nv = MASKS && na && nb;
+    return !MASKS || !(na || nb);
+}
+
+// SV.shift with exact power-of-two factors (shift_all's rule), suppressed when `on` is false
+__device__ __forceinline__ void shift_pow2(double (&v)[4], Scale<SCALE_POW2>& sc, int thr_hi, bool on)
+{
+    const int h0 = __double2hiint(v[0]), h1 = __double2hiint(v[1]), h2 = __double2hiint(v[2]), h3 = __double2hiint(v[3]);
+    const int hmin = min(min(h0, h1), min(h2, h3)), hmax = max(max(h0, h1), max(h2, h3));
+    const int d = (!on || hmin > thr_hi) ? 1023 : (hmax >> 20);
+    const double f = __hiloint2double((2046 - d) << 20, 0);
+    v[0] *= f; v[1] *= f; v[2] *= f; v[3] *= f;
+    sc.e += d - 1023;
+}
+
+// Packed fields of the masked form: field f of a site = sum_j code(mask of tip row rows[first + j]) * radix^j, `bits`
+// wide at bit `shift` of word `word` (pb_api.cu: build_reduced_program).  One thread per site.
+struct PackField { int word, shift, first, k; };
+
+__global__ void __launch_bounds__(256)
+pack_fields_masks(const uint64_t* __restrict__ masks, int64_t ld, const PackField* __restrict__ fields, int nfields,
+                  const int* __restrict__ rows, const unsigned char* __restrict__ code_of_mask /* [16] */, int radix, int nwords,
+                  uint64_t* __restrict__ packed, int64_t spad, int64_t site0, int64_t site1)
+{
+    __shared__ unsigned char lut[16];
+    if (threadIdx.x < 16) lut[threadIdx.x] = code_of_mask[threadIdx.x];
+    __syncthreads();
+    const int64_t s = site0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= site1) return;
+    uint64_t word = 0;
+    int cur_word = 0;
+    for (int f = 0; f < nfields; f++) {
+        const PackField fd = fields[f];
+        if (fd.word != cur_word) {                      // fields are sorted by word
+            packed[(int64_t)cur_word * spad + s] = word;
+            for (int w = cur_word + 1; w < fd.word; w++) packed[(int64_t)w * spad + s] = 0;
+            cur_word = fd.word;
+            word = 0;
+        }
+        unsigned idx = 0;
+        for (int j = fd.k - 1; j >= 0; j--)             // Horner: tip 0 is the lowest digit
+            idx = idx * radix + lut[masks[(int64_t)rows[fd.first + j] * ld + s] & 15u];
+        word |= (uint64_t)idx << fd.shift;
+    }
+    packed[(int64_t)cur_word * spad + s] = word;
+    for (int w = cur_word + 1; w < nwords; w++) packed[(int64_t)w * spad + s] = 0;
+}
+
+// Which of the 16 possible state sets of a 4-state alphabet occur in the alignment: bit m of *present.
+__global__ void __launch_bounds__(256)
+mask_alphabet(const uint64_t* __restrict__ masks, int64_t ld, int64_t nsites, int ntaxa, unsigned* __restrict__ present)
+{
+    unsigned seen = 0;
+    const int64_t total = (int64_t)ntaxa * nsites;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        seen |= 1u << (unsigned)(masks[(i / nsites) * ld + (i % nsites)] & 15u);
+    seen = __reduce_or_sync(0xffffffffu, seen);
+    if ((threadIdx.x & 31) == 0 && seen) atomicOr(present, seen);
+}
+
+// The tables of the masked form: entry idx of a clade decodes (mixed radix) to one state set per tip; the clade's own
+// instruction range is interpreted with the None rule above and set-column sums.  mask_of_code[c] = the state set of code c.
+__global__ void __launch_bounds__(256)
+build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __restrict__ tabs, const double* __restrict__ P,
+                         int nnodes, int ntab, double thr, int radix, const unsigned char* __restrict__ mask_of_code,
+                         double* __restrict__ tabV, int* __restrict__ tabK)
+{
+    const CladeTab tb = tabs[blockIdx.x];
+    const int c = blockIdx.y;
+    const double* Pc = P + (size_t)c * nnodes * 16;
+    int nent = 1;
+    for (int j = 0; j < tb.k; j++) nent *= radix;
+    const int thr_hi = __double2hiint(thr);
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < nent; idx += gridDim.z * blockDim.x) {
+        unsigned sets[8];                                        // state set of every tip of the clade
+        {
+            int r = idx;
+            for (int j = 0; j < tb.k; j++) { sets[j] = mask_of_code[r % radix]; r /= radix; }
+        }
+        auto column = [&](int off, int tip, double (&t)[4]) {   // P[leaf] . indicator(set): set columns added, ascending
+            const double* lf = Pc + off;
+            const unsigned m = sets[tip];
+            if (m == 0) { t[0] = NONE_MARK; t[1] = t[2] = t[3] = 0.0; return; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((m >> j) & 1u) a += lf[i * 4 + j];
+                t[i] = a;
+            }
+        };
+        double v[4] = {1.0, 1.0, 1.0, 1.0}, stk[8][4];
+        bool nv = true;                                          // nothing seen yet
+        int sp = 0;
+        Scale<SCALE_POW2> sc;
+        sc.init();
+        for (int ip = tb.op0; ip <= tb.op1; ip++) {
+            const FusedOp2 o = prog[ip];
+            const int code = o.code & 0xff, tA = (o.sh & 0xff) >> 1, tB = ((o.sh >> 8) & 0xff) >> 1;   // tip ordinals
+            if (code == FOP_APPLY_MUL_TIP) {
+                double y[4], t[4];
+                matvec4(Pc + o.offA, v, y);
+                column(o.offB, tB, t);
+                if (combine4<true>(v, nv, y, nv, t, is_none<true>(t))) shift_pow2(v, sc, thr_hi, true);
+            } else if (code == FOP_ACC_POP) {
+                double y[4], z[4];
+                sp--;
+                const bool nb = is_none<true>(stk[sp]);
+                matvec4(Pc + o.offA, v, y);
+                matvec4(Pc + o.offB, stk[sp], z);
+                if (combine4<true>(v, nv, y, nv, z, nb)) shift_pow2(v, sc, thr_hi, true);
+            } else if (code == FOP_TIP_TIP) {
+                double a[4], b[4];
+                column(o.offA, tA, a);
+                column(o.offB, tB, b);
+                if (combine4<true>(v, nv, a, is_none<true>(a), b, is_none<true>(b))) shift_pow2(v, sc, thr_hi, true);
+            } else if (code == FOP_TIP) {
+                column(o.offA, tA, v);
+                nv = is_none<true>(v);
+            } else if (code == FOP_APPLY) {
+                double y[4];
+                matvec4(Pc + o.offA, v, y);
+                if (!nv) { v[0] = y[0]; v[1] = y[1]; v[2] = y[2]; v[3] = y[3]; }
+            } else if (code == FOP_MUL_TIP) {
+                double t[4], a[4] = {v[0], v[1], v[2], v[3]};
+                column(o.offA, tA, t);
+                if (combine4<true>(v, nv, a, nv, t, is_none<true>(t))) shift_pow2(v, sc, thr_hi, true);
+            } else if (code == FOP_POP_MUL) {
+                sp--;
+                double a[4] = {v[0], v[1], v[2], v[3]};
+                if (combine4<true>(v, nv, stk[sp], is_none<true>(stk[sp]), a, nv)) shift_pow2(v, sc, thr_hi, true);
+            }
+            if ((o.code & FOP_PUSH_AFTER) && ip < tb.op1) {
+                stk[sp][0] = nv ? NONE_MARK : v[0];
+                stk[sp][1] = v[1]; stk[sp][2] = v[2]; stk[sp][3] = v[3];
+                sp++;
+            }
+        }
+        if (tb.pre >= 0 && !nv) {                                // the consumer's branch matrix, applied here once
+            double y[4];
+            matvec4(Pc + tb.pre, v, y);
+            v[0] = y[0]; v[1] = y[1]; v[2] = y[2]; v[3] = y[3];
+        }
+        const size_t e = (size_t)c * ntab + tb.ent0 + idx;
+        tabV[e * 4 + 0] = nv ? NONE_MARK : v[0];
+        tabV[e * 4 + 1] = v[1]; tabV[e * 4 + 2] = v[2]; tabV[e * 4 + 3] = v[3];
+        tabK[e] = nv ? 0 : sc.e;
+    }
+}
+
+// tip_stride: doubles per loose tip in shared memory (16, or 4 * radix with MASKS); tip_mask: (1 << bits of a tip field) - 1
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
 __global__ void __launch_bounds__(BLOCK, MINB ? MINB : (BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1)))
 fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
         int cat0, int slot0, int nmat, const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
-        const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat)
+        const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat,
+        int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code)
 {
     extern __shared__ double sh[];
-    double* shP = sh;                                       // [nleaf][16] loose tips' matrices, transposed
-    double* shS = sh + (size_t)nleaf * 16;                  // [stack_depth][4][BLOCK*SPT]
+    double* shP = sh;                                       // loose tips' columns: [nleaf][16] transposed, or [nleaf][radix][4]
+    const int tip_stride = MASKS ? 4 * radix : 16;
+    double* shS = sh + (size_t)nleaf * tip_stride;          // [stack_depth][4][BLOCK*SPT]
     const int c = cat0 + blockIdx.y, tid = threadIdx.x;
     const int cbase = (slot0 + blockIdx.y) * nmat * 16;     // this category's matrices in cPinner
     {
         const double* Pg = P + (size_t)c * nnodes * 16;
-        for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
-            const int k = idx >> 4, e = idx & 15;
-            shP[k * 16 + (e & 3) * 4 + (e >> 2)] = Pg[(size_t)leaf_nodes[k] * 16 + e];
+        if (!MASKS) {
+            for (int idx = tid; idx < nleaf * 16; idx += BLOCK) {
+                const int k = idx >> 4, e = idx & 15;
+                shP[k * 16 + (e & 3) * 4 + (e >> 2)] = Pg[(size_t)leaf_nodes[k] * 16 + e];
+            }
+        } else {
+            for (int idx = tid; idx < nleaf * radix * 4; idx += BLOCK) {     // column of state-set code cc, row i
+                const int k = idx / (radix * 4), cc = (idx >> 2) % radix, i = idx & 3;
+                const unsigned m = mask_of_code[cc];
+                const double* lf = Pg + (size_t)leaf_nodes[k] * 16 + i * 4;
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((m >> j) & 1u) a += lf[j];
+                shP[idx] = m ? a : (i == 0 ? NONE_MARK : 0.0);
+            }
         }
     }
     __syncthreads();
     const unsigned pbase = (unsigned)__cvta_generic_to_shared(shP);
     const double* tv = tabV + (size_t)c * ntab * 4;
     const int* tk = tabK + (size_t)c * ntab;
+    const int thr_hi = __double2hiint(thr);
     double pir[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) pir[i] = pi[i];
@@ -882,12 +1073,14 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t s0 = (tile0 + tile) * (BLOCK * SPT) + tid;
         double v[SPT][4];
+        bool nv[SPT];                                       // the accumulator is None (MASKS only)
         Scale<SCALE_POW2> sc[SPT];
         uint64_t cur[SPT], nxt[SPT];
         const uint64_t* pk = packed + s0;
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
             sc[q].init();
+            nv[q] = false;
             cur[q] = pk[q * BLOCK];
             nxt[q] = pk[spad + q * BLOCK];
 #pragma unroll
@@ -911,38 +1104,35 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
                     matvec4c(cbase + offA, v[q], y);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * b[q][i];
+                    const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], b[q], is_none<MASKS>(b[q]));
                     sc[q].e += eb[q];
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_APPLY_MUL_TIP: {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double y[4], t[4];
-                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)((unsigned)(cur[q] >> shB) & tip_mask), t);
                     matvec4c(cbase + offA, v[q], y);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * t[i];
+                    const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], t, is_none<MASKS>(t));
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_TAB_TAB: {
                 double b[SPT][4];
                 int ea[SPT], eb[SPT];
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);
+                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);      // (operand A straight into the accumulator)
                     tab_gather(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * b[q][i];
+                    const bool on = combine4<MASKS>(v[q], nv[q], v[q], is_none<MASKS>(v[q]), b[q], is_none<MASKS>(b[q]));
                     sc[q].e += ea[q] + eb[q];
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_ACC_POP: {
                 st -= 4 * BLOCK * SPT;
@@ -951,12 +1141,12 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                     double x[4], y[4], z[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+                    const bool nb = is_none<MASKS>(x);
                     matvec4c(cbase + offA, v[q], y);
                     matvec4c(cbase + offB, x, z);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i] * z[i];
+                    const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], z, nb);
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_TAB_TIP: {
                 int ea[SPT];
@@ -965,12 +1155,11 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double t[4];
-                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, t);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)((unsigned)(cur[q] >> shB) & tip_mask), t);
+                    const bool on = combine4<MASKS>(v[q], nv[q], v[q], is_none<MASKS>(v[q]), t, is_none<MASKS>(t));
                     sc[q].e += ea[q];
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_LOADW: {
 #pragma unroll
@@ -985,62 +1174,67 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 for (int q = 0; q < SPT; q++) {
                     int ea;
                     tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea);
+                    nv[q] = is_none<MASKS>(v[q]);
                     sc[q].e += ea;
                 }
             } break;
             case FOP_MUL_TAB: {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    double a[4];
+                    double a[4], w[4] = {v[q][0], v[q][1], v[q][2], v[q][3]};
                     int ea;
                     tab_gather(tv, tk, offA, cur[q], shA, mA, a, ea);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * a[i];
+                    const bool on = combine4<MASKS>(v[q], nv[q], w, nv[q], a, is_none<MASKS>(a));
                     sc[q].e += ea;
-                    shift4s(v[q], sc[q], thr);
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
             } break;
             case FOP_TIP_TIP: {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double a[4], b[4];
-                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, a);
-                    lds_col4(pbase + 8u * (unsigned)offB, (int)(cur[q] >> shB) & 3, b);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = a[i] * b[i];
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)((unsigned)(cur[q] >> shA) & tip_mask), a);
+                    lds_col4(pbase + 8u * (unsigned)offB, (int)((unsigned)(cur[q] >> shB) & tip_mask), b);
+                    const bool on = combine4<MASKS>(v[q], nv[q], a, is_none<MASKS>(a), b, is_none<MASKS>(b));
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
-                shift_all<SPT, SCALE_POW2>(v, sc, thr);
             } break;
             case FOP_TIP: {
 #pragma unroll
-                for (int q = 0; q < SPT; q++) lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, v[q]);
+                for (int q = 0; q < SPT; q++) {
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)((unsigned)(cur[q] >> shA) & tip_mask), v[q]);
+                    nv[q] = is_none<MASKS>(v[q]);
+                }
             } break;
             case FOP_APPLY: {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
                     matvec4c(cbase + offA, v[q], y);
+                    if (!(MASKS && nv[q])) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = y[i];
+                        for (int i = 0; i < 4; i++) v[q][i] = y[i];
+                    }
                 }
             } break;
             case FOP_MUL_TIP: {
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    double t[4];
-                    lds_col4(pbase + 8u * (unsigned)offA, (int)(cur[q] >> shA) & 3, t);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * t[i];
-                    shift4s(v[q], sc[q], thr);
+                    double t[4], w[4] = {v[q][0], v[q][1], v[q][2], v[q][3]};
+                    lds_col4(pbase + 8u * (unsigned)offA, (int)((unsigned)(cur[q] >> shA) & tip_mask), t);
+                    const bool on = combine4<MASKS>(v[q], nv[q], w, nv[q], t, is_none<MASKS>(t));
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
             } break;
             case FOP_POP_MUL: {
                 st -= 4 * BLOCK * SPT;
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
+                    double x[4], w[4] = {v[q][0], v[q][1], v[q][2], v[q][3]};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[q][i] = st[(i * SPT + q) * BLOCK] * v[q][i];
-                    shift4s(v[q], sc[q], thr);
+                    for (int i = 0; i < 4; i++) x[i] = st[(i * SPT + q) * BLOCK];
+                    const bool on = combine4<MASKS>(v[q], nv[q], x, is_none<MASKS>(x), w, nv[q]);
+                    shift_pow2(v[q], sc[q], thr_hi, on);
                 }
             } break;
             case FOP_ROOT: {
@@ -1048,18 +1242,21 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 for (int q = 0; q < SPT; q++) {
 #pragma unroll
                     for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
-                    if (shift_at_root) shift4s(v[q], sc[q], thr);
+                    shift_pow2(v[q], sc[q], thr_hi, shift_at_root != 0);
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
-                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                    // a column without any observation: +inf here, 0 after root_combine (lib/phylo_ctmc.ml:172, :302)
+                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = (MASKS && nv[q]) ? INFINITY : log(sum) + sc[q].value();
                 }
             } break;
             default: break;
             }
             if (opw.x & FOP_PUSH_AFTER) {
 #pragma unroll
-                for (int q = 0; q < SPT; q++)
+                for (int q = 0; q < SPT; q++) {
+                    st[(0 * SPT + q) * BLOCK] = (MASKS && nv[q]) ? NONE_MARK : v[q][0];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                    for (int i = 1; i < 4; i++) st[(i * SPT + q) * BLOCK] = v[q][i];
+                }
                 st += 4 * BLOCK * SPT;
             }
         }

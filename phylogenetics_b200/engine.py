@@ -289,6 +289,149 @@ class LikelihoodContext:
         return lib.pb_path_name(self._ctx).decode()
 
 
+class ShardedContext:
+    """pb_sharded: ONE host thread drives several GPUs of one box; the alignment's columns are sharded over
+    them, tree and model replicated, the total combined by an NCCL all-reduce inside the library
+    (include/phylo_b200.h, "multi-GPU").  The torchrun / one-process-per-GPU form is phylogenetics_b200.sharding."""
+
+    def __init__(self, devices, nstates, nsites, ntaxa, ncat=1, keep_clv=False, level_kernels=False):
+        flags = (_lib.PB_FLAG_KEEP_CLV if keep_clv else 0) | (_lib.PB_FLAG_LEVEL_KERNELS if level_kernels else 0)
+        self.devices = [int(d) for d in devices]
+        self.nstates, self.nsites, self.ntaxa, self.ncat = int(nstates), int(nsites), int(ntaxa), int(ncat)
+        dev = np.ascontiguousarray(self.devices, dtype=np.int32)
+        self._s = lib.pb_create_sharded(len(self.devices), dev.ctypes.data, self.nstates, self.ncat, self.nsites,
+                                        self.ntaxa, flags)
+        if not self._s:
+            msg = lib.pb_sharded_last_error(None).decode()
+            code = _lib.PB_ERR_NCCL if ("NCCL" in msg or "nccl" in msg) else \
+                (_lib.PB_ERR_INVALID_ARG if "pb_create_sharded" in msg or "must be" in msg else _lib.PB_ERR_CUDA)
+            cls = _lib.PhyloB200InvalidArgument if code == _lib.PB_ERR_INVALID_ARG else _lib.PhyloB200Error
+            raise cls(code, msg)
+        self.nnodes = 0
+
+    def close(self):
+        if getattr(self, "_s", None):
+            lib.pb_sharded_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != _lib.PB_OK:
+            msg = lib.pb_sharded_last_error(self._s).decode()
+            cls = _lib.PhyloB200InvalidArgument if rc == _lib.PB_ERR_INVALID_ARG else _lib.PhyloB200Error
+            raise cls(rc, msg)
+
+    @property
+    def ndev(self):
+        return int(lib.pb_sharded_ndev(self._s))
+
+    def shard_bounds(self, d):
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        self._ck(lib.pb_sharded_shard_bounds(self._s, int(d), ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def shard_option(self, d, name, value):
+        check(lib.pb_set_option(ctypes.c_void_p(lib.pb_sharded_ctx(self._s, int(d))), name.encode(), float(value)))
+
+    def shard_set_tips_ptr(self, d, host_ptr, ld):
+        """pb_set_tips on shard d's own context (its columns only: [ntaxa][>= hi - lo])."""
+        check(lib.pb_set_tips(ctypes.c_void_p(lib.pb_sharded_ctx(self._s, int(d))), ctypes.c_void_p(host_ptr), int(ld)))
+
+    def shard_path_name(self, d):
+        return lib.pb_path_name(ctypes.c_void_p(lib.pb_sharded_ctx(self._s, int(d)))).decode()
+
+    def set_reduce(self, how):
+        self._ck(lib.pb_sharded_set_reduce(self._s, int(how)))
+
+    def set_mode(self, mode):
+        self._ck(lib.pb_sharded_set_mode(self._s, int(mode)))
+
+    def set_option(self, name, value):
+        self._ck(lib.pb_sharded_set_option(self._s, name.encode(), float(value)))
+
+    def set_tree(self, flat, branch_lengths=None):
+        cp = np.ascontiguousarray(flat.child_ptr, dtype=np.int32)
+        ci = np.ascontiguousarray(flat.child_idx, dtype=np.int32)
+        tr = np.ascontiguousarray(flat.tip_row, dtype=np.int32)
+        bl = None if branch_lengths is None else _f64(branch_lengths)
+        if len(cp) != flat.nnodes + 1 or len(tr) != flat.nnodes or len(ci) != flat.nnodes - 1:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tree arrays have the wrong length")
+        self._ck(lib.pb_sharded_set_tree(self._s, int(flat.nnodes), int(flat.root), cp.ctypes.data, ci.ctypes.data,
+                                         tr.ctypes.data, None if bl is None else bl.ctypes.data))
+        self.nnodes = int(flat.nnodes)
+
+    def set_branch_lengths(self, branch_lengths):
+        bl = _f64(branch_lengths)
+        if len(bl) != self.nnodes:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "branch_lengths must have nnodes entries")
+        self._ck(lib.pb_sharded_set_branch_lengths(self._s, bl.ctypes.data))
+
+    def set_root_frequencies(self, pi):
+        pi = _f64(pi)
+        if len(pi) != self.nstates:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "pi must have nstates entries")
+        self._ck(lib.pb_sharded_set_root_frequencies(self._s, pi.ctypes.data))
+
+    def set_categories(self, rates, weights):
+        r, w = _f64(rates), _f64(weights)
+        if len(r) != self.ncat or len(w) != self.ncat:
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "need ncat rates and weights")
+        self._ck(lib.pb_sharded_set_categories(self._s, r.ctypes.data, w.ctypes.data))
+
+    def set_rate_matrix(self, Q, pi):
+        q, p = _colmajor(Q), _f64(pi)
+        self._ck(lib.pb_sharded_set_rate_matrix(self._s, q.ctypes.data, p.ctypes.data))
+
+    def set_rate_matrix_general(self, Q):
+        q = _colmajor(Q)
+        self._ck(lib.pb_sharded_set_rate_matrix_general(self._s, q.ctypes.data))
+
+    def set_pmatrices(self, P):
+        P = np.asarray(P, dtype=np.float64).reshape(self.ncat, self.nnodes, self.nstates, self.nstates)
+        Pc = np.ascontiguousarray(np.swapaxes(P, 2, 3))
+        self._ck(lib.pb_sharded_set_pmatrices(self._s, Pc.ctypes.data))
+
+    def set_tips(self, states):
+        """states: uint8 [ntaxa][nsites], the FULL alignment; every device keeps its own columns."""
+        states = np.ascontiguousarray(states, dtype=np.uint8)
+        if states.ndim != 2 or states.shape != (self.ntaxa, self.nsites):
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "tips must be uint8 [ntaxa][nsites]")
+        self._ck(lib.pb_sharded_set_tips(self._s, states.ctypes.data, states.shape[1]))
+
+    def set_tips_ptr(self, host_ptr, ld):
+        self._ck(lib.pb_sharded_set_tips(self._s, ctypes.c_void_p(host_ptr), int(ld)))
+
+    def set_tip_masks(self, masks):
+        masks = np.ascontiguousarray(masks, dtype=np.uint64)
+        if masks.ndim != 2 or masks.shape != (self.ntaxa, self.nsites):
+            raise _lib.PhyloB200InvalidArgument(_lib.PB_ERR_INVALID_ARG, "masks must be uint64 [ntaxa][nsites]")
+        self._ck(lib.pb_sharded_set_tip_masks(self._s, masks.ctypes.data, masks.shape[1]))
+
+    def loglik(self, per_site=False):
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_sharded_loglik(self._s, ctypes.byref(total), None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
+    def loglik_host_ptr(self, host_ptr, ld, packed2=False, per_site=False):
+        total = ctypes.c_double()
+        ps = np.empty(self.nsites) if per_site else None
+        self._ck(lib.pb_sharded_loglik_host(self._s, ctypes.c_void_p(host_ptr), int(ld), int(bool(packed2)),
+                                            ctypes.byref(total), None if ps is None else ps.ctypes.data))
+        return (total.value, ps) if per_site else total.value
+
+
 def transition_matrices_eigen(U, lam, Uinv, ts, device=0):
     """P(t) = U diag(exp(t lam)) Uinv for every t, one kernel launch (K1)."""
     u, ui, l, t = _colmajor(U), _colmajor(Uinv), _f64(lam), _f64(np.atleast_1d(ts))

@@ -55,6 +55,16 @@ def test_fails_loudly_without_a_gpu():
     assert e.value.code == _lib.PB_ERR_CUDA and "no CPU fallback" in str(e.value)
     with pytest.raises(_lib.PhyloB200Error):
         transition_matrices_eigen(np.eye(4), np.zeros(4), np.eye(4), [0.1])
+    # the multi-GPU entry point as well: no device, no silent fallback; its argument errors need no device at all
+    from phylogenetics_b200.engine import ShardedContext
+    with pytest.raises(_lib.PhyloB200Error) as e:
+        ShardedContext([0, 1], 4, 1000, 8)
+    assert e.value.code == _lib.PB_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.PhyloB200Error) as e:
+        ShardedContext([0, 0], 4, 1000, 8)
+    assert e.value.code == _lib.PB_ERR_NCCL
+    with pytest.raises(_lib.PhyloB200InvalidArgument):
+        ShardedContext([0, 1, 2], 4, 2, 8)                  # more devices than sites
 
 
 def test_invalid_arguments_are_rejected_before_touching_the_device():
