@@ -562,6 +562,25 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not abs(tot_bytes - total0) <= 1e-12 * abs(total0):
         raise SystemExit("host-buffer and resident evaluations disagree: %r %r" % (tot_bytes, total0))
 
+    c5 = None
+    if world > 1 and not args.no_extras and cfg == "c2" and not args.sites:
+        # BASELINE configs[4]: the Nelder-Mead loop on 10M sites over 8 GPUs = 1.25M sites per GPU (the same per-GPU
+        # shard at other N), 263 parameters, fixed evaluation budget, one captured evaluation replayed (CUDA graph)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from optimise_c5 import c5_loop
+        c5_sites = 1_250_000
+        c5_case = build_case("c2", c5_sites, site_seed=1000 + rank)
+        c5_ctx = new_context(c5_case, c5_sites, local_rank, stream)
+        c5_ctx.set_timing(False)
+        c5_ctx.set_tips(c5_case.tips)
+        barrier()
+        try:
+            c5 = c5_loop(c5_case, c5_ctx, world, dist, 400)
+        except Exception as e:
+            c5 = {"error": repr(e)}
+        c5_ctx.close()
+        del c5_case
+        barrier()
     single = None
     if world > 1:
         # one host thread driving all N devices through the C ABI (pb_create_sharded), while the other ranks idle
@@ -647,6 +666,7 @@ def run_ours(args, rank, world, local_rank):
         "collective_ms_per_step": (sum(collective_ms) / len(collective_ms)) if world > 1 else 0.0,
         "per_rank_ms": per_rank,
         "single_process_sharded": single,
+        "c5_nelder_mead": c5,
         "gpu_launches": int(launches),
         "phase_ms": {"pmat": float(phases[:, 0].mean()), "pruning": prune_avg_ms, "root": float(phases[:, 2].mean())},
         "clocks": clocks,

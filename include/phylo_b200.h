@@ -77,6 +77,11 @@ pb_ctx *pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, 
 void pb_destroy(pb_ctx *ctx);
 /* ctx may be NULL: last error of a failed pb_create on this thread. */
 const char *pb_last_error(const pb_ctx *ctx);
+/* The pb_status that message belongs to (a binding maps a failed pb_create to the right exception with it). */
+int pb_last_status(const pb_ctx *ctx);
+/* dims[6] = {nstates, ncat, nsites, ntaxa, nnodes of the current tree (0: none), flags}: what a binding needs to
+ * check the sizes of the buffers it is handed before it passes their pointers on (the ABI carries no sizes). */
+int pb_get_dims(const pb_ctx *ctx, int64_t *dims);
 /* Enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the
  * context's own non-blocking stream.  The handle 0 means the CUDA default stream. */
 int pb_set_stream(pb_ctx *ctx, void *cuda_stream);
@@ -215,10 +220,12 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
- *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_slots" (cap on the matrix ring),
+ *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_cherry" (1 (default): nodes with two leaf children are
+ *   tables of N^2 entries carrying their branch matrix, version 3 with power-of-two rescaling), "fused_dmma_slots" (cap on the matrix ring),
  *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
  *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
- * "host_chunks": column chunks of pb_loglik_host; "host_lead_cats": rate categories pruned chunk by chunk
+ * "graph": see pb_graph_replays.  "host_chunks": column chunks of pb_loglik_host (cut where a round of the persistent
+ *   blocks ends unless "host_chunk_align" is 0); "host_lead_cats": rate categories pruned chunk by chunk
  *   behind a 2-bit packed copy (the others run once over all the sites); "fused_const_group" (1 (default): the
  *   constant bank is loaded for as many categories as it holds).  Unknown names are PB_ERR_INVALID_ARG. */
 int pb_set_option(pb_ctx *ctx, const char *name, double value);
@@ -235,6 +242,12 @@ int pb_get_timing_at(pb_ctx *ctx, int back, double *ms /* [3] */);
 
 /* How many kernels of this library the context has launched so far. */
 int64_t pb_kernel_launches(const pb_ctx *ctx);
+/* Option "graph" (pb_set_option(ctx, "graph", 1)): an optimisation loop re-evaluates one configuration with new
+ * parameter VALUES (branch lengths, eigensystem, categories, root frequencies); the library then captures one
+ * evaluation of the 4-state site-resident program — P(t), table build, constant-bank loads, the category launches,
+ * the root reduction, the read-back — as a CUDA graph after the first plain evaluation and replays it until a call
+ * changes what would be launched (tree, tips, options, rescaling, stream ...).  How many evaluations were replays: */
+int64_t pb_graph_replays(const pb_ctx *ctx);
 /* Which pruning path the next pb_loglik takes: "fused4", "level4", "level_dense", ... */
 const char *pb_path_name(const pb_ctx *ctx);
 
@@ -339,6 +352,18 @@ int pb_debug_reduced_program(int nnodes, int root, const int32_t *child_ptr, con
                              int32_t *ops, int cap_ops, int32_t *clade_ops, int cap_clade_ops,
                              int32_t *slot_rows, int32_t *slot_xor_rows, int cap_slots, int32_t *mat_nodes, int32_t *leaf_nodes,
                              int32_t *clades, int cap_clades);
+
+/* The dense-alphabet (20 / 61 states) program over the tree whose cherries — nodes with two leaf children — are
+ * tables (kernel fused_dmma3).  counts[8] = {instructions, matrices applied (in the order the kernel's matrix ring
+ * delivers them), tables, stack depth, inner branches, leaf branches, stack depth and matrices of the untabulated
+ * program}; an instruction is 4 ints {code, A, B, rowA | rowB << 16}: A / B are compact indices into inner_nodes
+ * (matrices), leaf_nodes (tip columns) or table numbers, by operand kind; tabs[t] = {first entry, tip row A, tip row
+ * B, 0} (entry = state A * nstates + state B); tab_nodes[t] = {leaf A node, leaf B node, cherry node or -1 at the
+ * root, 0}: the table holds P[cherry] . (column of P[leaf A] * column of P[leaf B]), rescaled. */
+int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
+                                   const int32_t *tip_row, int ntaxa, int nstates, int32_t *counts, int32_t *ops,
+                                   int cap_ops, int32_t *mlist, int cap_mlist, int32_t *tabs, int32_t *tab_nodes,
+                                   int cap_tabs, int32_t *inner_nodes, int32_t *leaf_nodes);
 
 const char *pb_version(void);
 

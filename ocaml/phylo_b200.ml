@@ -48,6 +48,27 @@ external loglik_host_ : ctx -> tip_matrix -> float_vec -> float = "pb_stub_logli
 external loglik_host_packed2_ : ctx -> tip_matrix -> float_vec -> float = "pb_stub_loglik_host_packed2"
 external pin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit = "pb_stub_pin"
 external unpin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit = "pb_stub_unpin"
+external get_dims : ctx -> int * int * int * int * int * int = "pb_stub_get_dims"
+
+(* multi-GPU: one host thread, the alignment's columns sharded over the devices, NCCL all-reduce of the scalar *)
+type sharded
+external create_sharded_ : int32_vec -> int -> int -> int -> int -> int -> sharded
+  = "pb_stub_create_sharded_bytecode" "pb_stub_create_sharded"
+external sharded_ndev : sharded -> int = "pb_stub_sharded_ndev"
+external sharded_set_reduce : sharded -> int -> unit = "pb_stub_sharded_set_reduce"
+external sharded_set_rescaling : sharded -> float -> bool -> unit = "pb_stub_sharded_set_rescaling"
+external sharded_set_tree_ : sharded -> int -> int32_vec -> int32_vec -> int32_vec -> float_vec -> unit
+  = "pb_stub_sharded_set_tree_bytecode" "pb_stub_sharded_set_tree"
+external sharded_set_branch_lengths : sharded -> float_vec -> unit = "pb_stub_sharded_set_branch_lengths"
+external sharded_set_root_frequencies : sharded -> Linear_algebra.vec -> unit = "pb_stub_sharded_set_root_frequencies"
+external sharded_set_categories_ : sharded -> float_vec -> float_vec -> unit = "pb_stub_sharded_set_categories"
+external sharded_set_eigensystem : sharded -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
+  = "pb_stub_sharded_set_eigensystem"
+external sharded_set_rate_matrix : sharded -> Linear_algebra.mat -> Linear_algebra.vec -> unit = "pb_stub_sharded_set_rate_matrix"
+external sharded_set_pmatrices : sharded -> float_vec -> unit = "pb_stub_sharded_set_pmatrices"
+external sharded_set_tips : sharded -> tip_matrix -> unit = "pb_stub_sharded_set_tips"
+external sharded_loglik_ : sharded -> float_vec -> float = "pb_stub_sharded_loglik"
+external sharded_loglik_host_ : sharded -> tip_matrix -> bool -> float_vec -> float = "pb_stub_sharded_loglik_host"
 
 let keep_clv_flag = 1
 let mode_phylo_ctmc = 0
@@ -232,7 +253,92 @@ let pruning t ~nstates ~transition_probabilities ~leaf_state ~root_frequencies =
   fst (pruning_sites t ~nstates ~nsites:1 ~transition_probabilities
          ~leaf_state:(fun l _ -> leaf_state l) ~root_frequencies)
 
-module Felsenstein (A : Alphabet.S_int) (Align : Felsenstein.Alignment with type base := A.t)
+module Sharded = struct
+  type t = sharded
+  let reduce_nccl = 0 and reduce_ordered = 1
+  let create ~devices ?(ncat = 1) ~nstates ~nsites ~ntaxa () =
+    let d = Bigarray.(Array1.of_array int32 c_layout (Array.map devices ~f:Int32.of_int_exn)) in
+    create_sharded_ d nstates ncat nsites ntaxa 0
+  let ndev = sharded_ndev
+  let set_reduce = sharded_set_reduce
+  let set_rescaling = sharded_set_rescaling
+  let set_tree s t ~branch_lengths = sharded_set_tree_ s t.root t.child_ptr t.child_idx t.tip_row branch_lengths
+  let set_branch_lengths = sharded_set_branch_lengths
+  let set_root_frequencies = sharded_set_root_frequencies
+  let set_categories s ~rates ~weights = sharded_set_categories_ s rates weights
+  let set_eigensystem = sharded_set_eigensystem
+  let set_rate_matrix = sharded_set_rate_matrix
+  let set_pmatrices = sharded_set_pmatrices
+  let set_tips = sharded_set_tips
+  let loglik s ?(per_site = empty_vec) () = sharded_loglik_ s per_site
+  let loglik_host s ?(per_site = empty_vec) ?(packed2 = false) tips = sharded_loglik_host_ s tips packed2 per_site
+end
+
+(* Felsenstein.Make (lib/felsenstein.mli:11-48) with the reference's own functor arguments: E is a plain
+   Site_evolution_model.S, so P(t) of every branch is E.transition_probability_matrix param t, called ONCE PER BRANCH on
+   the host (the reference calls it once per branch per site) and uploaded ([`Mat]-style, pb_set_pmatrices); the
+   pruning, the rescaling and the sum over sites run on the device. *)
+module Felsenstein = struct
+module type Alignment = Phylogenetics.Felsenstein.Alignment
+
+module Make (A : Alphabet.S) (Align : Alignment with type base := A.t)
+    (E : Site_evolution_model.S with type mat := A.matrix and type vec := A.vector) =
+struct
+  let symbols = Array.of_list A.all          (* A.to_int is the state index (lib/alphabet.ml) *)
+
+  (* sites [first, first + nsites) of the alignment; threshold = -infinity: no rescaling at all *)
+  let evaluate ~threshold ~first ~nsites param tree align =
+    let spec_eMt = E.transition_probability_matrix param in       (* as lib/felsenstein.ml:24: specialised once *)
+    let t = Phylogenetic_tree.to_tree tree in
+    let flat, leaves, branches = flatten t in
+    let nnodes = Bigarray.Array1.dim flat.tip_row and ntaxa = Array.length leaves in
+    let n = A.card in
+    let ctx = create ~nstates:n ~nsites ~ntaxa () in
+    let zero = Bigarray.(Array1.create float64 c_layout nnodes) in
+    Bigarray.Array1.fill zero 0. ;
+    set_tree ctx flat ~branch_lengths:zero ;
+    let p = Bigarray.(Array1.create float64 c_layout (nnodes * n * n)) in
+    Bigarray.Array1.fill p 0. ;
+    Array.iteri branches ~f:(fun v -> function
+        | None -> ()
+        | Some l ->
+          let m = spec_eMt l in
+          Array.iter symbols ~f:(fun x ->
+              Array.iter symbols ~f:(fun y ->
+                  p.{v * n * n + A.to_int y * n + A.to_int x} <- A.Matrix.get m x y))) ;     (* column-major *)
+    set_pmatrices ctx p ;
+    let tips = Bigarray.(Array2.create int8_unsigned c_layout ntaxa nsites) in
+    Array.iteri leaves ~f:(fun row (_, index) ->
+        for s = 0 to nsites - 1 do tips.{row, s} <- A.to_int (Align.get_base align ~seq:index ~pos:(first + s)) done) ;
+    set_tips ctx tips ;
+    set_rescaling ctx threshold false ;     (* shift_normal, no shift after x pi: lib/felsenstein.ml:47-48,57-64 *)
+    let pi = Lacaml.D.Vec.create n in
+    let stat = E.stationary_distribution param in
+    Array.iter symbols ~f:(fun x -> pi.{A.to_int x + 1} <- A.Vector.get stat x) ;
+    set_root_frequencies ctx pi ;
+    loglik ctx ()
+
+  (* lib/felsenstein.mli:19-26.  [?shift] is an arbitrary OCaml closure applied at every node: it cannot cross the C
+     ABI, so a caller-supplied one is refused; without it the reference does not rescale at all, and neither do we. *)
+  let felsenstein_single ?shift param ~site tree align =
+    (match shift with
+     | Some _ -> invalid_arg "Phylo_b200.Felsenstein.Make.felsenstein_single: a custom ~shift closure cannot run on the device; use felsenstein_single_shift ?threshold"
+     | None -> ()) ;
+    evaluate ~threshold:Float.neg_infinity ~first:site ~nsites:1 param tree align
+
+  (* lib/felsenstein.mli:28-35 *)
+  let felsenstein_single_shift ?(threshold = 0.0000001) param ~site tree align =
+    evaluate ~threshold ~first:site ~nsites:1 param tree align
+
+  let felsenstein_noshift param tree align =
+    evaluate ~threshold:Float.neg_infinity ~first:0 ~nsites:(Align.length align) param tree align
+  let felsenstein param tree align =
+    evaluate ~threshold:0.0000001 ~first:0 ~nsites:(Align.length align) param tree align
+end
+
+(* The same for models that stage a diagonalisation (Site_evolution_model.S_with_reduction: JC69, K80, Make_diag):
+   P(t) of every branch is rebuilt ON THE DEVICE from the eigensystem (kernel pmat_eigen). *)
+module Make_with_reduction (A : Alphabet.S_int) (Align : Alignment with type base := A.t)
     (E : Site_evolution_model.S_with_reduction with type mat := A.matrix and type vec := A.vector) =
 struct
   let evaluate ~threshold param tree align =
@@ -256,4 +362,5 @@ struct
 
   let felsenstein param tree align = evaluate ~threshold:0.0000001 param tree align
   let felsenstein_noshift param tree align = evaluate ~threshold:Float.neg_infinity param tree align
+end
 end

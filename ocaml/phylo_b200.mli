@@ -64,12 +64,34 @@ val pruning_sites_masks :
 (** [Phylo_ctmc.Missing_values.pruning] / [Phylo_ctmc.Ambiguous.pruning] (lib/phylo_ctmc.ml:145-172, 280-302) for all
     sites: [leaf_states l i] is the bit mask of the states compatible with leaf [l] at site [i] ([0L] = missing). *)
 
-module Felsenstein (A : Alphabet.S_int) (Align : Felsenstein.Alignment with type base := A.t)
+(** [Phylo_b200.Felsenstein.Make] = [Felsenstein.Make] with the reference's own functor arguments and all four of its functions
+    (lib/felsenstein.mli:11-48).  [E] is a plain [Site_evolution_model.S]: [E.transition_probability_matrix param t]
+    is called once per branch on the host (Padé models included) and the matrices are uploaded; pruning, rescaling
+    and the sum over sites run on the device. *)
+module Felsenstein : sig
+module type Alignment = Phylogenetics.Felsenstein.Alignment
+
+module Make (A : Alphabet.S) (Align : Alignment with type base := A.t)
+    (E : Site_evolution_model.S with type mat := A.matrix and type vec := A.vector) : sig
+  val felsenstein_single :
+    ?shift:(float -> float -> A.vector -> A.vector * float) ->
+    E.param -> site:int -> Phylogenetic_tree.t -> Align.t -> float
+  (** No underflow prevention (the reference's default [shift]).  A caller-supplied [~shift] closure cannot cross the
+      C ABI: [Invalid_argument]. *)
+  val felsenstein_single_shift :
+    ?threshold:float -> E.param -> site:int -> Phylogenetic_tree.t -> Align.t -> float
+  val felsenstein_noshift : E.param -> Phylogenetic_tree.t -> Align.t -> float
+  val felsenstein : E.param -> Phylogenetic_tree.t -> Align.t -> float
+end
+
+(** The same for models that stage a diagonalisation ([S_with_reduction]): P(t) is rebuilt on the device. *)
+module Make_with_reduction (A : Alphabet.S_int) (Align : Alignment with type base := A.t)
     (E : Site_evolution_model.S_with_reduction with type mat := A.matrix and type vec := A.vector) : sig
   val felsenstein : E.param -> Phylogenetic_tree.t -> Align.t -> float
   (** Same type and value as [Felsenstein.Make(A)(Align)(E).felsenstein] (lib/felsenstein.mli:47);
       P(t) of every branch is rebuilt on the device from [E.rate_matrix_reduction]. *)
   val felsenstein_noshift : E.param -> Phylogenetic_tree.t -> Align.t -> float
+end
 end
 
 (** {2 Low-level access (one call per C-ABI entry point)} *)
@@ -128,6 +150,33 @@ val loglik_host : ctx -> ?per_site:float_vec -> tip_matrix -> float
 val loglik_host_packed2 : ctx -> ?per_site:float_vec -> tip_matrix -> float
 (** One call per evaluation from a host alignment ([pb_loglik_host], [pb_loglik_host_packed2]): the copy to the
     device runs in column chunks while the previous chunk is pruned. *)
+
+val get_dims : ctx -> int * int * int * int * int * int
+(** [(nstates, ncat, nsites, ntaxa, nnodes, flags)]: what the stubs check every Bigarray against. *)
+
+(** {2 Multi-GPU}  One host thread drives the GPUs of one box ([pb_create_sharded]): the alignment's columns are
+    sharded over [devices], tree and model replicated, the total combined by an NCCL all-reduce inside the library
+    ([Failure] on any NCCL error). *)
+module Sharded : sig
+  type t
+  val reduce_nccl : int
+  val reduce_ordered : int
+  val create : devices:int array -> ?ncat:int -> nstates:int -> nsites:int -> ntaxa:int -> unit -> t
+  val ndev : t -> int
+  val set_reduce : t -> int -> unit
+  val set_rescaling : t -> float -> bool -> unit
+  val set_tree : t -> flat_tree -> branch_lengths:float_vec -> unit
+  val set_branch_lengths : t -> float_vec -> unit
+  val set_root_frequencies : t -> Linear_algebra.vec -> unit
+  val set_categories : t -> rates:float_vec -> weights:float_vec -> unit
+  val set_eigensystem : t -> Linear_algebra.mat -> Linear_algebra.vec -> Linear_algebra.mat -> unit
+  val set_rate_matrix : t -> Linear_algebra.mat -> Linear_algebra.vec -> unit
+  val set_pmatrices : t -> float_vec -> unit
+  val set_tips : t -> tip_matrix -> unit
+  (** The FULL alignment; every device copies its own columns. *)
+  val loglik : t -> ?per_site:float_vec -> unit -> float
+  val loglik_host : t -> ?per_site:float_vec -> ?packed2:bool -> tip_matrix -> float
+end
 
 val pin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit
 val unpin : ('a, 'b, Bigarray.c_layout) Bigarray.Array2.t -> unit

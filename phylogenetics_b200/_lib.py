@@ -28,13 +28,13 @@ PB_ALPHABET_DNA, PB_ALPHABET_AMINO_ACID, PB_ALPHABET_CODON = 0, 1, 2
 
 # Every symbol include/phylo_b200.h declares (tests check the .so exports them all).
 EXPORTS = [
-    "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
+    "pb_create", "pb_destroy", "pb_last_error", "pb_last_status", "pb_get_dims", "pb_set_stream", "pb_use_private_stream", "pb_set_mode", "pb_set_rescaling",
     "pb_set_tree", "pb_set_branch_lengths", "pb_update_branch_length", "pb_nodes_recomputed", "pb_set_tips", "pb_set_tips_device", "pb_set_tips_packed2", "pb_loglik_host_packed2", "pb_loglik_host_enqueue", "pb_pin_host_memory", "pb_unpin_host_memory", "pb_set_tip_masks", "pb_set_tips_text", "pb_set_site_weights",
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
-    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_path_name", "pb_transition_matrices_eigen",
-    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_version",
+    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_graph_replays", "pb_path_name", "pb_transition_matrices_eigen",
+    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_debug_dense_reduced_program", "pb_version",
     "pb_create_sharded", "pb_sharded_destroy", "pb_sharded_last_error", "pb_sharded_ndev", "pb_sharded_ctx",
     "pb_sharded_shard_bounds", "pb_sharded_set_reduce", "pb_sharded_set_mode", "pb_sharded_set_option", "pb_sharded_set_tree",
     "pb_sharded_set_branch_lengths", "pb_sharded_update_branch_length", "pb_sharded_set_root_frequencies",
@@ -67,6 +67,8 @@ def _load():
         "pb_create": (vp, [ci, ci, ci, i64, ci, ctypes.c_uint]),
         "pb_destroy": (None, [vp]),
         "pb_last_error": (ctypes.c_char_p, [vp]),
+        "pb_last_status": (ci, [vp]),
+        "pb_get_dims": (ci, [vp, vp]),
         "pb_set_stream": (ci, [vp, vp]),
         "pb_use_private_stream": (ci, [vp]),
         "pb_set_mode": (ci, [vp, ci]),
@@ -104,6 +106,7 @@ def _load():
         "pb_get_timing": (ci, [vp, vp]),
         "pb_get_timing_at": (ci, [vp, ci, vp]),
         "pb_kernel_launches": (i64, [vp]),
+        "pb_graph_replays": (i64, [vp]),
         "pb_path_name": (ctypes.c_char_p, [vp]),
         "pb_transition_matrices_eigen": (ci, [ci, ci, ci, vp, vp, vp, vp, vp]),
         "pb_transition_matrices_expm": (ci, [ci, ci, ci, vp, vp, vp]),
@@ -133,6 +136,7 @@ def _load():
         "pb_sharded_loglik": (ci, [vp, vp, vp]),
         "pb_sharded_loglik_host": (ci, [vp, vp, i64, ci, vp, vp]),
         "pb_debug_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, ci]),
+        "pb_debug_dense_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp]),
         "pb_version": (ctypes.c_char_p, []),
     }
     for name, (res, args) in sig.items():

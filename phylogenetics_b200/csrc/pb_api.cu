@@ -29,6 +29,7 @@ using pbk::LevelNode;
 namespace {
 
 thread_local std::string g_create_error;
+thread_local int g_create_status = 0;
 
 // The fused 4-state kernel stages matrices in the device's constant bank, which every context on
 // that device shares: users are serialised by a host mutex around the enqueue and, on the device,
@@ -75,6 +76,7 @@ struct pb_ctx {
     double threshold = 1e-6;
     int shift_at_root = 1;
     mutable std::string err;
+    mutable int err_status = 0;
     int64_t launches = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -188,6 +190,18 @@ struct pb_ctx {
     int fused_dmma_spill = 0;           // option "fused_dmma_spill": test hook, all stack levels in the L2 scratch
     DevBuf<FusedOp2> d_fprog_d;
     DevBuf<int> d_mlist;
+    // fused_dmma3 over the reduced tree: nodes with two leaf children are tables (build_dense_reduced_program)
+    int fused_dmma_cherry = 1;          // option "fused_dmma_cherry"
+    std::vector<FusedOp2> dprog_r;
+    std::vector<int> mlist_r;
+    std::vector<int4> dtabs, dtab_nodes;   // per table: {first entry, tip row A, tip row B}; {leaf A node, leaf B node, cherry node or -1}
+    int dstack_r = 0;
+    bool dense_reduced_built = false;
+    DevBuf<FusedOp2> d_dprog_r;
+    DevBuf<int> d_mlist_r;
+    DevBuf<int4> d_dtabs, d_dtab_nodes;
+    DevBuf<double> d_dtabV;
+    DevBuf<int> d_dtabK;
     DevBuf<double> d_Ppad, d_PTleaf, d_gstack;
     DevBuf<uint64_t> d_packed;
     DevBuf<int> d_bad;
@@ -229,7 +243,18 @@ struct pb_ctx {
     cudaEvent_t ev_start = nullptr;
     int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
     int host_lead_cats = 1;             // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
+    int host_chunk_align = 1;           // option "host_chunk_align": chunk bounds where a round of the persistent blocks ends
+    int fused4t_occ = 3;                // resident blocks per SM of the fused4t shape last launched
     int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)
+
+    // option "graph": one evaluation of the reduced 4-state program captured as a CUDA graph and replayed while nothing
+    // that shapes the launches changes (parameter VALUES live in device buffers whose addresses are stable)
+    int use_graph = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t config_epoch = 1, graph_epoch = 0, warm_epoch = 0;   // bumped by every setter that changes launches or kernel arguments
+    bool capturing = false;
+    int64_t graph_launches = 0;         // kernels inside the captured evaluation
+    int64_t graph_replays = 0;
 
     // optional per-phase device timing (pb_set_timing)
     bool timing = false;
@@ -243,7 +268,7 @@ namespace {
 
 int fail(pb_ctx* c, int code, const std::string& msg)
 {
-    if (c) c->err = msg; else g_create_error = msg;
+    if (c) { c->err = msg; c->err_status = code; } else { g_create_error = msg; g_create_status = code; }
     return code;
 }
 int cuda_fail(pb_ctx* c, cudaError_t e, const char* what)
@@ -597,6 +622,7 @@ int compile_tree(pb_ctx* c)
         }
         c->tab_leaves = -1;                     // the tabulated variant is built on demand (build_table_program)
         c->r_leaves = -1;                       // ... and so is the program over the reduced tree (build_reduced_program)
+        c->dense_reduced_built = false;         // ... and its dense-alphabet form (build_dense_reduced_program)
         // fused_dmma: compact matrix indices, tip rows, and the order the inner matrices are consumed in
         c->fprog_d.clear();
         c->mlist.clear();
@@ -1321,6 +1347,7 @@ int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     int occ = 0;
     PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
     if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4t: kernel does not fit on an SM");
+    c->fused4t_occ = occ;
     const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
     int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
@@ -1360,8 +1387,9 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     if (cat_hi < 0) cat_hi = c->ncat;
     std::lock_guard<std::mutex> lock(g_const_mutex);
     cudaEvent_t& bank_free = g_const_event[c->device & 63];
+    // (while an evaluation is being captured the bank's event is handled around the graph launch, pb_loglik_enqueue)
     if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
-    else PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
+    else if (!c->capturing) PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
     const int nmat = (int)c->rmat_nodes.size();
     int fb = 0, fq = 0;
     if (!fused4t_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4t: the tree does not fit shared memory");
@@ -1371,7 +1399,7 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         c->launches++;
     }
     const uint64_t want_version = (c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2) * 32 + (c->r_masked ? c->r_radix : 0);
-    if (g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
+    if (c->capturing || g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cProg, c->d_rprog.p, c->rprog.size() * sizeof(FusedOp2), 0,
                                            cudaMemcpyDeviceToDevice, c->stream));
         g_prog_owner[c->device & 63] = c;
@@ -1412,7 +1440,7 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
             if (rc != PB_OK) return rc;
         }
     }
-    PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
+    if (!c->capturing) PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
     return PB_OK;
 }
 
@@ -1514,6 +1542,98 @@ int launch_fused4(pb_ctx* c, int64_t site0, int64_t site1, bool reduced)
     return launch_fused4_shape<pbk::SCALE_PRODUCT>(c, fb, fq, site0, site1);
 }
 
+// ---- dense alphabets: the program over the tree whose cherries are tables (kernel fused_dmma3) -------------
+// Same emitter and stack rule as the 4-state reduced program; operands address matrices by the compact indices
+// of compile_tree (inner_nodes / leaf_nodes), tips by their tip-matrix rows, tables by descriptor index.
+int build_dense_reduced_program(pb_ctx* c)
+{
+    const int nn = c->nnodes;
+    auto is_leaf = [&](int v) { return c->child_ptr[v] == c->child_ptr[v + 1]; };
+    std::vector<int> order;
+    order.reserve(nn);
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({c->root, c->child_ptr[c->root]});
+        while (!st.empty()) {
+            auto& top = st.back();
+            if (top.second < c->child_ptr[top.first + 1]) {
+                const int ch = c->child_idx[top.second++];
+                st.push_back({ch, c->child_ptr[ch]});
+            } else {
+                order.push_back(top.first);
+                st.pop_back();
+            }
+        }
+    }
+    std::vector<char> kind(nn, 0);                            // 0 inner, 1 loose tip, 2 cherry (table), 3 a cherry's leaf
+    for (int v = 0; v < nn; v++) kind[v] = is_leaf(v) ? 1 : 0;
+    for (int v = 0; v < nn; v++) {
+        if (is_leaf(v) || c->child_ptr[v + 1] - c->child_ptr[v] != 2) continue;
+        const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
+        if (is_leaf(a) && is_leaf(b)) { kind[v] = 2; kind[a] = kind[b] = 3; }
+    }
+    std::vector<int> su;
+    stack_need(c, order, kind, su);
+    std::vector<RAbs> aops;
+    if (kind[c->root] == 2) aops.push_back({pbk::FOP_TAB, c->root, 0});
+    else emit_reduced(c, c->root, kind, su, aops);
+    aops.push_back({pbk::FOP_ROOT, 0, 0});
+
+    std::vector<int> compact(nn, -1);
+    for (size_t k = 0; k < c->inner_nodes.size(); k++) compact[c->inner_nodes[k]] = (int)k;
+    for (size_t k = 0; k < c->leaf_nodes.size(); k++) compact[c->leaf_nodes[k]] = (int)k;
+    c->dtabs.clear();
+    c->dtab_nodes.clear();
+    std::vector<int> tab_of(nn, -1);
+    const int n2 = c->n * c->n;
+    for (int v : order) {
+        if (kind[v] != 2) continue;
+        const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
+        tab_of[v] = (int)c->dtabs.size();
+        c->dtabs.push_back(make_int4((int)c->dtabs.size() * n2, c->tip_row[a], c->tip_row[b], 0));
+        c->dtab_nodes.push_back(make_int4(a, b, v == c->root ? -1 : v, 0));
+    }
+    c->dprog_r.clear();
+    c->mlist_r.clear();
+    c->dstack_r = 0;
+    int sp = 0;
+    for (const RAbs& a : aops) {
+        if (a.code == pbk::FOP_PUSH) {
+            c->dstack_r = std::max(c->dstack_r, ++sp);
+            if (!c->dprog_r.empty() && !(c->dprog_r.back().code & pbk::FOP_PUSH_AFTER)) { c->dprog_r.back().code |= pbk::FOP_PUSH_AFTER; continue; }
+            c->dprog_r.push_back({pbk::FOP_PUSH | pbk::FOP_PUSH_AFTER, 0, 0, 0});
+            continue;
+        }
+        FusedOp2 o{a.code, 0, 0, 0};
+        switch (a.code) {
+        case pbk::FOP_TIP_TIP: o.offA = compact[a.a]; o.offB = compact[a.b]; o.sh = c->tip_row[a.a] | (c->tip_row[a.b] << 16); break;
+        case pbk::FOP_TIP: case pbk::FOP_MUL_TIP: o.offA = compact[a.a]; o.sh = c->tip_row[a.a]; break;
+        case pbk::FOP_APPLY: o.offA = compact[a.a]; c->mlist_r.push_back(o.offA); break;
+        case pbk::FOP_APPLY_MUL_TIP: o.offA = compact[a.a]; o.offB = compact[a.b]; o.sh = c->tip_row[a.b] << 16; c->mlist_r.push_back(o.offA); break;
+        case pbk::FOP_ACC_POP: o.offA = compact[a.a]; o.offB = compact[a.b]; c->mlist_r.push_back(o.offA); c->mlist_r.push_back(o.offB); sp--; break;
+        case pbk::FOP_POP_MUL: sp--; break;
+        case pbk::FOP_TAB: case pbk::FOP_MUL_TAB: o.offA = tab_of[a.a]; break;
+        case pbk::FOP_TAB_TAB: o.offA = tab_of[a.a]; o.offB = tab_of[a.b]; break;
+        case pbk::FOP_TAB_TIP: o.offA = tab_of[a.a]; o.offB = compact[a.b]; o.sh = c->tip_row[a.b] << 16; break;
+        case pbk::FOP_APPLY_MUL_TAB: o.offA = compact[a.a]; o.offB = tab_of[a.b]; c->mlist_r.push_back(o.offA); break;
+        default: break;
+        }
+        c->dprog_r.push_back(o);
+    }
+    c->dense_reduced_built = true;
+    if (c->plan_only) return PB_OK;
+    PB_CUDA(c, c->d_dprog_r.ensure(c->dprog_r.size()));
+    PB_CUDA(c, c->d_mlist_r.ensure(std::max<size_t>(c->mlist_r.size(), 1)));
+    PB_CUDA(c, c->d_dtabs.ensure(std::max<size_t>(c->dtabs.size(), 1)));
+    PB_CUDA(c, c->d_dtab_nodes.ensure(std::max<size_t>(c->dtab_nodes.size(), 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_dprog_r.p, c->dprog_r.data(), c->dprog_r.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_mlist_r.p, c->mlist_r.data(), c->mlist_r.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_dtabs.p, c->dtabs.data(), c->dtabs.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_dtab_nodes.p, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));             // (the host vectors may be rebuilt by the next pb_set_tree)
+    return PB_OK;
+}
+
 // Site-resident tensor-core path (20 / 61 states): pad the branch matrices, then one persistent launch.
 int launch_fused_dmma_path(pb_ctx* c)
 {
@@ -1521,8 +1641,19 @@ int launch_fused_dmma_path(pb_ctx* c)
     const int ninner = (int)c->inner_nodes.size(), nleaf = (int)c->leaf_nodes.size();
     int ssm = 0, nslot = 0;
     size_t smem = 0;
+    // version 3, power-of-two rescaling: the program over the tree whose cherries are tables
+    const bool cherries = c->fused_dmma_version == 3 && c->fused_dmma_cherry && c->fused_pow2;
+    if (cherries && !c->dense_reduced_built) {
+        const int rc = build_dense_reduced_program(c);
+        if (rc != PB_OK) return rc;
+    }
+    const bool red = cherries && !c->dtabs.empty();
+    const int dstack = red ? c->dstack_r : c->dstack;
+    const int nops_d = red ? (int)c->dprog_r.size() : (int)c->fprog_d.size();
+    const int nmat_d = red ? (int)c->mlist_r.size() : (int)c->mlist.size();
+    const int ntab_d = red ? (int)c->dtabs.size() : 0;
     if (c->fused_dmma_version == 3 &&
-        pbk::fused_dmma3_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) {
+        pbk::fused_dmma3_plan(n, c->smem_optin, dstack, c->ntaxa, nops_d + ntab_d, nmat_d, &nslot, &ssm, &smem)) {
         if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
             smem -= (size_t)ssm * pbk::fused_dmma3_tilesz(n) * sizeof(double);
             ssm = 0;
@@ -1537,11 +1668,21 @@ int launch_fused_dmma_path(pb_ctx* c)
                                    c->d_Ppad.p, c->d_PTleaf.p, c->stream);
         c->launches++;
         const int grid = pbk::fused_dmma3_grid(n, c->sm_count, c->spad);
-        const int gdepth = c->dstack + 1 - ssm;
+        const int gdepth = dstack + 1 - ssm;
         PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * pbk::fused_dmma3_tilesz(n), 1)));
-        pbk::FusedDmmaArgs a{c->d_fprog_d.p, (int)c->fprog_d.size(), c->d_mlist.p, (int)c->mlist.size(), ssm, c->d_gstack.p, gdepth,
+        pbk::FusedDmmaArgs a{red ? c->d_dprog_r.p : c->d_fprog_d.p, nops_d, red ? c->d_mlist_r.p : c->d_mlist.p, nmat_d, ssm,
+                             c->d_gstack.p, gdepth,
                              c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
+        if (red) {
+            const size_t entries = (size_t)c->ncat * ntab_d * n * n;
+            PB_CUDA(c, c->d_dtabV.ensure(entries * ((n + 7) / 8 * 8)));
+            PB_CUDA(c, c->d_dtabK.ensure(entries));
+            pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->ncat, c->threshold,
+                                              c->d_dtabV.p, c->d_dtabK.p, c->stream);
+            c->launches++;
+            a.tabV = c->d_dtabV.p; a.tabK = c->d_dtabK.p; a.tabs = c->d_dtabs.p; a.ntab = ntab_d;
+        }
         if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
             return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
         c->launches++;
@@ -1806,6 +1947,16 @@ const char* pb_version(void) { return "phylo_b200 0.1 (sm_100a)"; }
 
 const char* pb_last_error(const pb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int pb_last_status(const pb_ctx* ctx) { return ctx ? ctx->err_status : g_create_status; }
+
+int pb_get_dims(const pb_ctx* c, int64_t* dims)
+{
+    if (!c || !dims) return PB_ERR_INVALID_ARG;
+    dims[0] = c->n; dims[1] = c->ncat; dims[2] = c->nsites; dims[3] = c->ntaxa;
+    dims[4] = c->have_tree ? c->nnodes : 0; dims[5] = c->flags;
+    return PB_OK;
+}
+
 pb_ctx* pb_create(int device, int nstates, int ncat, int64_t nsites, int ntaxa, unsigned flags)
 {
     if (nstates < 2 || nstates > 64) { fail(nullptr, PB_ERR_INVALID_ARG, "nstates must be in 2..64"); return nullptr; }
@@ -1874,6 +2025,7 @@ void pb_destroy(pb_ctx* c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
     if (c->h_total) cudaFreeHost(c->h_total);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (auto& set : c->ev_ring)
         for (int i = 0; i < 4; i++) if (set[i]) cudaEventDestroy(set[i]);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
@@ -1890,10 +2042,13 @@ void pb_destroy(pb_ctx* c)
 #define PB_ENTER(c)                                                          \
     if (!(c)) return PB_ERR_INVALID_ARG;                                     \
     { cudaError_t e_ = cudaSetDevice((c)->device); if (e_ != cudaSuccess) return cuda_fail((c), e_, "cudaSetDevice"); }
+// setters after which a captured evaluation (option "graph") no longer describes what would be launched
+#define PB_RESHAPES(c) ((c)->config_epoch++)
 
 int pb_set_stream(pb_ctx* c, void* s)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if ((cudaStream_t)s != c->stream) PB_CUDA(c, cudaStreamSynchronize(c->stream));   // finish what the old stream holds
     c->stream = (cudaStream_t)s;      // 0 is a valid handle: the CUDA default stream
     return PB_OK;
@@ -1902,6 +2057,7 @@ int pb_set_stream(pb_ctx* c, void* s)
 int pb_use_private_stream(pb_ctx* c)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (c->stream != c->own_stream) PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = c->own_stream;
     return PB_OK;
@@ -1910,6 +2066,7 @@ int pb_use_private_stream(pb_ctx* c)
 int pb_set_mode(pb_ctx* c, int mode)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (mode == PB_MODE_PHYLO_CTMC) { c->threshold = 1e-6; c->shift_at_root = 1; }
     else if (mode == PB_MODE_FELSENSTEIN) { c->threshold = 0.0000001; c->shift_at_root = 0; }
     else return fail(c, PB_ERR_INVALID_ARG, "unknown mode");
@@ -1921,6 +2078,7 @@ int pb_set_mode(pb_ctx* c, int mode)
 int pb_set_rescaling(pb_ctx* c, double threshold, int shift_at_root)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     c->threshold = threshold;
     c->shift_at_root = shift_at_root ? 1 : 0;
     c->all_dirty = true;
@@ -1963,6 +2121,7 @@ int pb_set_tree(pb_ctx* c, int nnodes, int root, const int32_t* child_ptr, const
     c->child_idx.assign(child_idx, child_idx + nedges);
     c->tip_row.assign(tip_row, tip_row + nnodes);
     c->parent = parent;
+    PB_RESHAPES(c);
     c->have_tree = true;
     c->have_blen = false;
     c->p_dirty = true;
@@ -2035,6 +2194,7 @@ static int alloc_tips2(pb_ctx* c)          // 2-bit upload buffer; padding colum
 int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
@@ -2056,6 +2216,7 @@ int pb_set_tips(pb_ctx* c, const uint8_t* states, int64_t ld)
 int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!d_states || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "tips: null pointer or ld < nsites");
     int rc = alloc_tips(c);
     if (rc != PB_OK) return rc;
@@ -2074,6 +2235,7 @@ int pb_set_tips_device(pb_ctx* c, const uint8_t* d_states, int64_t ld)
 int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     const int64_t nbytes = (c->nsites + 3) / 4;
     if (c->n != 4) return fail(c, PB_ERR_STATE, "2-bit packed tips are for 4-state alphabets");
     if (!packed || ld < nbytes) return fail(c, PB_ERR_INVALID_ARG, "packed tips: null pointer or ld < ceil(nsites / 4)");
@@ -2100,6 +2262,7 @@ int pb_set_tips_packed2(pb_ctx* c, const uint8_t* packed, int64_t ld)
 int pb_set_site_weights(pb_ctx* c, const double* w)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     c->fresh = false;
     if (!w) { c->have_site_weights = false; return PB_OK; }
     for (int64_t s = 0; s < c->nsites; s++)
@@ -2114,6 +2277,7 @@ int pb_set_site_weights(pb_ctx* c, const double* w)
 int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     const int width = alphabet == PB_ALPHABET_CODON ? 3 : 1;
     if (!text || ld < c->nsites * width) return fail(c, PB_ERR_INVALID_ARG, "text: null pointer or ld too small");
     const int expect = alphabet == PB_ALPHABET_DNA ? 4 : alphabet == PB_ALPHABET_AMINO_ACID ? 20 : alphabet == PB_ALPHABET_CODON ? 61 : -1;
@@ -2168,6 +2332,7 @@ int pb_set_tips_text(pb_ctx* c, const char* text, int64_t ld, int alphabet)
 int pb_set_tip_masks(pb_ctx* c, const uint64_t* masks, int64_t ld)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!masks || ld < c->nsites) return fail(c, PB_ERR_INVALID_ARG, "masks: null pointer or ld < nsites");
     const size_t count = (size_t)c->ntaxa * c->spad;
     const bool fresh = c->d_masks.count < count || !c->d_masks.p;
@@ -2239,6 +2404,7 @@ int pb_set_categories(pb_ctx* c, const double* rates, const double* weights)
 int pb_set_eigensystem(pb_ctx* c, const double* U, const double* lambda, const double* Uinv)
 {
     PB_ENTER(c);
+    if (c->psrc != PSRC_EIGEN) PB_RESHAPES(c);      // (new VALUES of an eigensystem keep the captured launches valid)
     if (!U || !lambda || !Uinv) return fail(c, PB_ERR_INVALID_ARG, "eigensystem: null pointer");
     const int n = c->n;
     std::vector<double> ur((size_t)n * n), uir((size_t)n * n);
@@ -2364,6 +2530,52 @@ int pb_debug_reduced_program(int nnodes, int root, const int32_t* child_ptr, con
     return PB_OK;
 }
 
+// Host-only view of the dense-alphabet program over the tree whose cherries are tables (kernel fused_dmma3;
+// build_dense_reduced_program), for tests of the planner.
+int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t* child_ptr, const int32_t* child_idx, const int32_t* tip_row,
+                                   int ntaxa, int nstates, int32_t* counts, int32_t* ops, int cap_ops, int32_t* mlist, int cap_mlist,
+                                   int32_t* tabs, int32_t* tab_nodes, int cap_tabs, int32_t* inner_nodes, int32_t* leaf_nodes)
+{
+    if (!child_ptr || !child_idx || !tip_row || !counts || !ops || !mlist || !tabs || !tab_nodes || !inner_nodes || !leaf_nodes ||
+        nnodes < 2 || root < 0 || root >= nnodes || ntaxa < 1 || child_ptr[0] != 0 || child_ptr[nnodes] != nnodes - 1)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_dense_reduced_program: bad arguments");
+    std::unique_ptr<pb_ctx> c(new pb_ctx());
+    c->plan_only = true;
+    c->n = nstates;
+    c->ncat = 1;
+    c->ntaxa = ntaxa;
+    c->nsites = 1;
+    c->spad = 1024;
+    c->nnodes = nnodes;
+    c->root = root;
+    c->child_ptr.assign(child_ptr, child_ptr + nnodes + 1);
+    c->child_idx.assign(child_idx, child_idx + nnodes - 1);
+    c->tip_row.assign(tip_row, tip_row + nnodes);
+    c->parent.assign(nnodes, -1);
+    for (int v = 0; v < nnodes; v++)
+        for (int k = child_ptr[v]; k < child_ptr[v + 1]; k++) {
+            const int ch = child_idx[k];
+            if (ch < 0 || ch >= nnodes || ch == root || c->parent[ch] != -1)
+                return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_dense_reduced_program: bad child index");
+            c->parent[ch] = v;
+        }
+    int rc = compile_tree(c.get());                           // (the compact matrix indices)
+    if (rc == PB_OK) rc = build_dense_reduced_program(c.get());
+    if (rc != PB_OK) return fail(nullptr, rc, c->err);
+    if ((int)c->dprog_r.size() > cap_ops || (int)c->mlist_r.size() > cap_mlist || (int)c->dtabs.size() > cap_tabs)
+        return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_dense_reduced_program: output buffers too small");
+    std::memcpy(ops, c->dprog_r.data(), c->dprog_r.size() * sizeof(FusedOp2));
+    std::copy(c->mlist_r.begin(), c->mlist_r.end(), mlist);
+    std::memcpy(tabs, c->dtabs.data(), c->dtabs.size() * sizeof(int4));
+    std::memcpy(tab_nodes, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(int4));
+    std::copy(c->inner_nodes.begin(), c->inner_nodes.end(), inner_nodes);
+    std::copy(c->leaf_nodes.begin(), c->leaf_nodes.end(), leaf_nodes);
+    const int32_t cnt[8] = {(int32_t)c->dprog_r.size(), (int32_t)c->mlist_r.size(), (int32_t)c->dtabs.size(), c->dstack_r,
+                            (int32_t)c->inner_nodes.size(), (int32_t)c->leaf_nodes.size(), c->dstack, (int32_t)c->mlist.size()};
+    std::copy(cnt, cnt + 8, counts);
+    return PB_OK;
+}
+
 // Page-lock a caller-owned host buffer (an OCaml Bigarray payload lives outside the OCaml heap and does not move)
 // so that the chunked copies of pb_loglik_host / pb_loglik_host_packed2 overlap with the pruning.
 int pb_pin_host_memory(void* p, size_t bytes)
@@ -2404,6 +2616,7 @@ int pb_set_rate_matrix(pb_ctx* c, const double* Q, const double* pi)
 int pb_set_rate_matrix_general(pb_ctx* c, const double* Q)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!Q) return fail(c, PB_ERR_INVALID_ARG, "rate matrix: null pointer");
     const int n = c->n;
     std::vector<double> qr((size_t)n * n);
@@ -2421,6 +2634,7 @@ int pb_set_rate_matrix_general(pb_ctx* c, const double* Q)
 int pb_set_pmatrices(pb_ctx* c, const double* P)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "set the tree first");
     if (!P) return fail(c, PB_ERR_INVALID_ARG, "P is null");
     const int n = c->n;
@@ -2437,12 +2651,73 @@ int pb_set_pmatrices(pb_ctx* c, const double* P)
     return PB_OK;
 }
 
+// Option "graph": replay (capturing it first when needed) one evaluation of the reduced 4-state program as a CUDA graph.
+// Only after a plain evaluation with the same configuration has allocated, planned and packed everything
+// (warm_epoch), and only while nothing has reshaped the launches since the capture (graph_epoch).
+static int enqueue_graph(pb_ctx* c, bool* done)
+{
+    *done = false;
+    bool reduced = false;
+    int rc = want_reduced(c, &reduced);
+    if (rc != PB_OK) return rc;
+    if (!reduced || path_of(c) != PATH_FUSED4 || c->have_masks || c->pack_dirty || c->psrc == PSRC_NONE ||
+        c->psrc == PSRC_DIRECT || !c->have_blen || c->warm_epoch != c->config_epoch)
+        return PB_OK;
+    cudaEvent_t& bank_free = g_const_event[c->device & 63];
+    if (c->graph_epoch != c->config_epoch || !c->graph_exec) {
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        const int64_t before = c->launches;
+        cudaGraph_t graph = nullptr;
+        PB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        c->capturing = true;
+        c->p_dirty = true;                                    // the captured evaluation always rebuilds P(t)
+        rc = build_pmatrices(c);
+        if (rc == PB_OK) rc = run_pruning(c);
+        if (rc == PB_OK) rc = run_root_reduction(c);
+        if (rc == PB_OK) {
+            cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        }
+        c->capturing = false;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != PB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(c, e, "cudaStreamEndCapture"); }
+        const cudaError_t e2 = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) { c->graph_exec = nullptr; return cuda_fail(c, e2, "cudaGraphInstantiate"); }
+        c->graph_launches = c->launches - before;
+        c->launches = before;
+        c->graph_epoch = c->config_epoch;
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_const_mutex);      // the constant bank is ours for the whole graph
+        if (bank_free) PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
+        PB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+        if (bank_free) PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
+        g_prog_owner[c->device & 63] = c;                     // (the graph uploads its program every time)
+        g_prog_version[c->device & 63] = (c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2) * 32;
+    }
+    c->launches += c->graph_launches;
+    c->graph_replays++;
+    c->p_dirty = false;
+    c->evaluated = true;
+    c->fresh = true;
+    *done = true;
+    return PB_OK;
+}
+
 int pb_loglik_enqueue(pb_ctx* c)
 {
     PB_ENTER(c);
     if (!c->have_tree) return fail(c, PB_ERR_STATE, "tree not set");
     if (!c->have_tips) return fail(c, PB_ERR_STATE, "tip states not set");
     if (!c->have_pi) return fail(c, PB_ERR_STATE, "root frequencies not set");
+    if (c->use_graph && !c->timing && !(c->flags & (PB_FLAG_KEEP_CLV | PB_FLAG_LEVEL_KERNELS))) {
+        bool done = false;
+        const int rc = enqueue_graph(c, &done);
+        if (rc != PB_OK) return rc;
+        if (done) return PB_OK;
+    }
     if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     int rc = build_pmatrices(c);
     if (rc != PB_OK) return rc;
@@ -2455,6 +2730,7 @@ int pb_loglik_enqueue(pb_ctx* c)
     PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->evaluated = true;
     c->fresh = true;
+    c->warm_epoch = c->config_epoch;         // everything is allocated, planned and packed for this configuration
     return PB_OK;
 }
 
@@ -2475,6 +2751,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
                             bool fetch = true)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (packed2 && c->n != 4) return fail(c, PB_ERR_STATE, "2-bit packed tips are for 4-state alphabets");
     if (!states || ld < (packed2 ? (c->nsites + 3) / 4 : c->nsites))
         return fail(c, PB_ERR_INVALID_ARG, packed2 ? "packed tips: null pointer or ld < ceil(nsites / 4)" : "tips: null pointer or ld < nsites");
@@ -2522,7 +2799,22 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
     PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
-    const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
+    int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
+    if (reduced && c->host_chunk_align) {
+        // A launch of the persistent kernel costs whole ROUNDS of its resident blocks: cut the columns where a round
+        // ends (sm_count x blocks per SM x sites per block), so that no chunk pays for a mostly empty round.
+        int fb = 0, fq = 0;
+        fused4t_shape(c, &fb, &fq);
+        const int64_t wave = (int64_t)c->sm_count * std::max(c->fused4t_occ, 1) * fb * fq;
+        const int64_t per = std::max<int64_t>(1, (c->spad / c->host_chunks + wave / 2) / wave);
+        chunk = round_up(per * wave, 1024);
+        while ((c->spad + chunk - 1) / chunk > 64) chunk *= 2;           // (the event pool holds 64 chunks)
+    }
+    while ((int64_t)c->chunk_events.size() < (c->spad + chunk - 1) / chunk) {
+        cudaEvent_t e;
+        PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
     // 2-bit packed: only the first `host_lead_cats` categories (default 1) are pruned chunk by chunk behind the
     // copy, the others run once over all the sites.  A launch costs one round of the persistent blocks (~0.09 ms)
     // however few tiles it has, so more chunked launches lose more than the overlap wins
@@ -2728,6 +3020,7 @@ int pb_get_pmatrices(pb_ctx* c, double* P)
 int pb_set_option(pb_ctx* c, const char* name, double value)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (!name) return fail(c, PB_ERR_INVALID_ARG, "option name is null");
     const std::string k(name);
     const int iv = (int)value;
@@ -2779,6 +3072,8 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->level4_minb = iv;
     } else if (k == "fused_dmma") {
         c->fused_dmma = value != 0.0;
+    } else if (k == "fused_dmma_cherry") {
+        c->fused_dmma_cherry = iv != 0;
     } else if (k == "fused_dmma_version") {
         if (iv < 1 || iv > 3) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1, 2 or 3");
         c->fused_dmma_version = iv;
@@ -2805,6 +3100,10 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "host_lead_cats") {
         if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "host_lead_cats must be in 1..64");
         c->host_lead_cats = iv;
+    } else if (k == "graph") {
+        c->use_graph = iv != 0;
+    } else if (k == "host_chunk_align") {
+        c->host_chunk_align = iv != 0;
     } else if (k == "host_chunks") {
         if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "host_chunks must be in 1..64");
         c->host_chunks = iv;
@@ -2823,6 +3122,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
 int pb_set_timing(pb_ctx* c, int on)
 {
     PB_ENTER(c);
+    PB_RESHAPES(c);
     if (on && !c->ev_ring[0][0])
         for (auto& set : c->ev_ring)
             for (int i = 0; i < 4; i++) PB_CUDA(c, cudaEventCreate(&set[i]));
@@ -2849,6 +3149,8 @@ int pb_get_timing_at(pb_ctx* c, int back, double* ms)
 int pb_get_timing(pb_ctx* c, double* ms) { return pb_get_timing_at(c, 0, ms); }
 
 int64_t pb_kernel_launches(const pb_ctx* c) { return c ? c->launches : 0; }
+
+int64_t pb_graph_replays(const pb_ctx* c) { return c ? c->graph_replays : 0; }
 
 const char* pb_path_name(const pb_ctx* c)
 {

@@ -738,6 +738,8 @@ struct FusedDmmaArgs {
     const double* Ppad; const double* PTleaf; int ninner, nleaf, ncat;
     const uint8_t* tips; int64_t tips_ld; int ntaxa; int64_t spad;
     const double* pi; double thr; int shift_at_root; double* site_cat;
+    // fused_dmma3 only: tabulated cherries (reduced program; see DenseTab)
+    const double* tabV = nullptr; const int* tabK = nullptr; const int4* tabs = nullptr; int ntab = 0;
 };
 
 template <int N>
@@ -903,13 +905,66 @@ __device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Sc
     }
 }
 
+// Tabulated cherries (dense alphabets).  A node whose two children are leaves can take only N^2 values per rate
+// category, whatever the site (400 at 20 states, 3 721 at 61): once per evaluation every such node gets a table of
+//     P[v] . shift(col_a(P[leaf A]) * col_b(P[leaf B]))        and the shift's exponent,
+// P[v] the matrix of the branch ABOVE the cherry, so that the kernel replaces two column gathers, a product, a
+// rescaling AND its parent's matrix-vector product (15 / 128 DMMAs, a layout conversion and a trip through the matrix
+// ring) by one gather of the same shape as a leaf-column gather: a third of the matrix-vector products of a
+// birth-death tree.  The program is compiled over the reduced tree (pb_api.cu: build_dense_reduced_program) with
+// the table as an operand of its parent's instruction, exactly as in the 4-state kernel fused4t.
+// A table descriptor: x = first entry, y / z = tip-matrix rows of the two leaves (entry index = state y * N + state z).
+template <int N>
+__global__ void __launch_bounds__(64)
+fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __restrict__ tabs, const int4* __restrict__ tab_nodes,
+                      int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+{
+    using F = Fd3Shape<N>;
+    __shared__ double sv[64];
+    const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const int4 nd = tab_nodes[t];                        // x = leaf A node, y = leaf B node, z = cherry node (-1: the root)
+    const double* Pc = P + (size_t)c * nnodes * N * N;
+    const double* PA = Pc + (size_t)nd.x * N * N;
+    const double* PB = Pc + (size_t)nd.y * N * N;
+    const double* PV = nd.z >= 0 ? Pc + (size_t)nd.z * N * N : nullptr;
+    const int thr_hi = __double2hiint(thr);
+    const size_t base = (size_t)c * ntab * N * N + (size_t)tabs[t].x;
+    for (int e = blockIdx.z; e < N * N; e += gridDim.z) {
+        const int a = e / N, b = e - a * N;
+        __syncthreads();
+        if (tid < N) sv[tid] = PA[tid * N + a] * PB[tid * N + b];       // column a of leaf A times column b of leaf B
+        __syncthreads();
+        int hmin = 0x7fffffff, hmax = (int)0x80000000;                  // SV.shift, power-of-two form (shift_tiles8)
+        for (int j = 0; j < N; j++) {
+            const int h = __double2hiint(sv[j]);
+            hmin = min(hmin, h);
+            hmax = max(hmax, h);
+        }
+        const int d = (hmin > thr_hi) ? 1023 : (hmax >> 20);
+        const double f = __hiloint2double((2046 - d) << 20, 0);
+        if (tid < F::MP8) {
+            double y = 0.0;
+            if (tid < N) {
+                if (PV) {
+                    for (int j = 0; j < N; j++) y = fma(PV[tid * N + j], sv[j] * f, y);
+                } else {
+                    y = sv[tid] * f;
+                }
+            }
+            tabV[(base + e) * F::MP8 + tid] = y;
+        }
+        if (tid == 0) tabK[base + e] = d - 1023;
+    }
+}
+
 template <int N, int SCALING>
 __global__ void __launch_bounds__((Fd3Shape<N>::NW + 1) * 32, 1)
 fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int nslot, int stack_smem,
             double* __restrict__ gstack, int gdepth,
             const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
             const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
-            const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat)
+            const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat,
+            const double* __restrict__ tabV, const int* __restrict__ tabK, const int4* __restrict__ tabs, int ntab)
 {
     using F = Fd3Shape<N>;
     constexpr int M8 = F::M8, K4 = F::K4, MP8 = F::MP8, NW = F::NW, KPP = F::KPP, NPAN = F::NPAN;
@@ -921,7 +976,8 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
     double* shS = shPi + MP8;                                             // [stack_smem][NW][XSZ]
     uint8_t* shT = reinterpret_cast<uint8_t*>(shS + (size_t)stack_smem * NW * F::XSZ);   // [NW][ntaxa][8]
     FusedOp2* shOps = reinterpret_cast<FusedOp2*>(shT + (((size_t)NW * ntaxa * 8 + 15) & ~(size_t)15));
-    int* shMl = reinterpret_cast<int*>(shOps + nops);
+    int4* shTabs = reinterpret_cast<int4*>(shOps + nops);               // [ntab] cherry descriptors (16 bytes each, like an op)
+    int* shMl = reinterpret_cast<int*>(shTabs + ntab);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tig = lane & 3;
     if (tid == 0) {
@@ -933,6 +989,7 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
         const int4* src = reinterpret_cast<const int4*>(prog);
         int4* dst = reinterpret_cast<int4*>(shOps);
         for (int idx = tid; idx < nops; idx += blockDim.x) dst[idx] = src[idx];
+        for (int idx = tid; idx < ntab; idx += blockDim.x) shTabs[idx] = tabs[idx];
         for (int idx = tid; idx < nmat; idx += blockDim.x) shMl[idx] = mlist[idx];
     }
     __syncthreads();                                         // the only CTA-wide barrier
@@ -1018,8 +1075,25 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
         cb = PTc + ((size_t)leaf * N + min((int)tb[1], N - 1)) * MP8 + g;
     };
 
+    // a tabulated cherry's value for the lane's two sites: a gather of the same shape as a leaf column, plus the exponents
+    const double* Tc = nullptr;
+    const int* Kc = nullptr;
+    auto tab_ptrs = [&](int t, const double*& ca, const double*& cb, Scale<SCALING> (&sc)[2]) {
+        const int4 d = shTabs[t];
+        const uint8_t* t0 = myT + d.y * 8 + tig * 2;
+        const uint8_t* t1 = myT + d.z * 8 + tig * 2;
+        const int ia = d.x + min((int)t0[0], N - 1) * N + min((int)t1[0], N - 1);
+        const int ib = d.x + min((int)t0[1], N - 1) * N + min((int)t1[1], N - 1);
+        ca = Tc + (size_t)ia * MP8 + g;
+        cb = Tc + (size_t)ib * MP8 + g;
+        sc[0].e += Kc[ia];
+        sc[1].e += Kc[ib];
+    };
+
     for (int c = 0; c < ncat; c++) {
         const double* PTc = PTleaf + (size_t)c * nleaf * N * MP8;
+        Tc = tabV + (size_t)c * ntab * N * N * MP8;
+        Kc = tabK + (size_t)c * ntab * N * N;
         for (int r = 0; r < rounds; r++) {
             const int64_t unit = lo + (int64_t)r * NW + warp;
             if (unit >= hi) {                                // no sites left for this warp: keep the ring moving
@@ -1062,6 +1136,41 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                     apply(level_tile(--sp), acc);
 #pragma unroll
                     for (int mt = 0; mt < M8; mt++) { acc[mt][0] *= y[mt][0]; acc[mt][1] *= y[mt][1]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (SCALING == 2 && code == FOP_APPLY_MUL_TAB) {     // (tables exist in the power-of-two mode only)
+                    double y[M8][2];
+                    const double *ca, *cb;
+                    tab_ptrs(opw.z, ca, cb, sc);
+                    double* X = level_tile(sp);
+                    to_tile(X, acc);
+                    apply(X, y);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = y[mt][0] * ca[mt * 8]; acc[mt][1] = y[mt][1] * cb[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (SCALING == 2 && code == FOP_TAB_TAB) {
+                    const double *ca, *cb, *da, *db;
+                    tab_ptrs(opw.y, ca, cb, sc);
+                    tab_ptrs(opw.z, da, db, sc);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = ca[mt * 8] * da[mt * 8]; acc[mt][1] = cb[mt * 8] * db[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (SCALING == 2 && code == FOP_TAB_TIP) {
+                    const double *ca, *cb, *da, *db;
+                    tab_ptrs(opw.y, ca, cb, sc);
+                    leaf_ptrs(PTc, opw.z, rowB, da, db);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = ca[mt * 8] * da[mt * 8]; acc[mt][1] = cb[mt * 8] * db[mt * 8]; }
+                    shift_tiles8<N>(acc, sc, lane, thr);
+                } else if (SCALING == 2 && code == FOP_TAB) {
+                    const double *ca, *cb;
+                    tab_ptrs(opw.y, ca, cb, sc);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] = ca[mt * 8]; acc[mt][1] = cb[mt * 8]; }
+                } else if (SCALING == 2 && code == FOP_MUL_TAB) {
+                    const double *ca, *cb;
+                    tab_ptrs(opw.y, ca, cb, sc);
+#pragma unroll
+                    for (int mt = 0; mt < M8; mt++) { acc[mt][0] *= ca[mt * 8]; acc[mt][1] *= cb[mt * 8]; }
                     shift_tiles8<N>(acc, sc, lane, thr);
                 } else if (code == FOP_TIP_TIP) {
                     const double *ca, *cb, *da, *db;
@@ -1229,8 +1338,17 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
     const int grid = fused_dmma3_grid(N, sm_count, a.spad);
     kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
                                                    a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
-                                                   a.pi, a.thr, a.shift_at_root, a.site_cat);
+                                                   a.pi, a.thr, a.shift_at_root, a.site_cat, a.tabV, a.tabK, a.tabs, a.ntab);
     return grid;
+}
+
+inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, const int4* tabs, const int4* tab_nodes, int ntab,
+                                         int ncat, double thr, double* tabV, int* tabK, cudaStream_t stream)
+{
+    if (ntab < 1) return;
+    const dim3 grid(ntab, ncat, n == 20 ? 50 : 128);
+    if (n == 20) fdmma3_build_cherries<20><<<grid, 64, 0, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+    else fdmma3_build_cherries<61><<<grid, 64, 0, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
 }
 
 inline int launch_fused_dmma3(int n, bool pow2, const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)

@@ -285,6 +285,11 @@ class LikelihoodContext:
         return int(lib.pb_kernel_launches(self._ctx))
 
     @property
+    def graph_replays(self):
+        """Evaluations that were replays of the captured CUDA graph (option "graph")."""
+        return int(lib.pb_graph_replays(self._ctx))
+
+    @property
     def path_name(self):
         return lib.pb_path_name(self._ctx).decode()
 

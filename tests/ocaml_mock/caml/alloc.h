@@ -5,4 +5,5 @@
 CAMLextern value caml_copy_double(double d);
 CAMLextern value caml_copy_int64(int64_t i);
 CAMLextern value caml_copy_string(const char *s);
+CAMLextern value caml_alloc_tuple(uintnat n);
 #endif

@@ -36,6 +36,9 @@ typedef uintptr_t uintnat;
 /* boxed float / int64: here a pointer to a malloc'd scalar */
 #define Double_val(v) (*(const double *)(v))
 #define Int64_val(v) (*(const int64_t *)(v))
+/* fields of a block (tuples): here a malloc'd array of values */
+#define Field(v, i) (((value *)(v))[i])
+#define Store_field(v, i, x) (((value *)(v))[i] = (x))
 /* OCaml string: here a NUL-terminated C string */
 #define String_val(v) ((const char *)(v))
 

@@ -74,6 +74,7 @@ uintnat caml_ba_byte_size(struct caml_ba_array *b)
     for (intnat i = 0; i < b->num_dims; i++) n *= (uintnat)b->dim[i];
     return n;
 }
+value caml_alloc_tuple(uintnat n) { return (value)calloc(n, sizeof(value)); }
 value caml_alloc_custom(struct custom_operations *ops, uintnat size, uintnat mem, uintnat max)
 {
     (void)mem; (void)max;
@@ -132,6 +133,23 @@ value pb_stub_loglik_host(value, value, value);
 value pb_stub_loglik_host_packed2(value, value, value);
 value pb_stub_pin(value);
 value pb_stub_unpin(value);
+value pb_stub_get_dims(value);
+value pb_stub_create_sharded(value, value, value, value, value, value);
+value pb_stub_create_sharded_bytecode(value *, int);
+value pb_stub_sharded_ndev(value);
+value pb_stub_sharded_set_reduce(value, value);
+value pb_stub_sharded_set_rescaling(value, value, value);
+value pb_stub_sharded_set_tree(value, value, value, value, value, value);
+value pb_stub_sharded_set_tree_bytecode(value *, int);
+value pb_stub_sharded_set_branch_lengths(value, value);
+value pb_stub_sharded_set_root_frequencies(value, value);
+value pb_stub_sharded_set_categories(value, value, value);
+value pb_stub_sharded_set_eigensystem(value, value, value, value);
+value pb_stub_sharded_set_rate_matrix(value, value, value);
+value pb_stub_sharded_set_pmatrices(value, value);
+value pb_stub_sharded_set_tips(value, value);
+value pb_stub_sharded_loglik(value, value);
+value pb_stub_sharded_loglik_host(value, value, value, value);
 
 /* ---- checks ----------------------------------------------------------------------------------------- */
 
@@ -315,7 +333,10 @@ int main(void)
 
     /* 5. error mapping (invalid_arg / failwith) */
     {
-        EXPECT_RAISES("create with 1 state -> Failure (pb_create returns NULL)", EXN_FAILURE, make_ctx(1, 1, 10, 4, 0));
+        EXPECT_RAISES("create with 1 state -> Invalid_argument (pb_create returns NULL, pb_last_status says why)", EXN_INVALID_ARGUMENT,
+                      make_ctx(1, 1, 10, 4, 0));
+        EXPECT_RAISES("create on a device that does not exist -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_create(Val_int(4096), Val_int(4), Val_int(1), Val_long(10), Val_int(4), Val_int(0)));
         value ctx = make_ctx(4, 1, 3, 4, 0);
         EXPECT_RAISES("set_mode 7 -> Invalid_argument", EXN_INVALID_ARGUMENT, pb_stub_set_mode(ctx, Val_int(7)));
         EXPECT_RAISES("loglik before set_tree -> Failure", EXN_FAILURE, pb_stub_loglik(ctx, ba1(&empty, 0, CAML_BA_FLOAT64)));
@@ -417,8 +438,135 @@ int main(void)
         finalise(keep);
     }
 
+    /* 7. every Bigarray is measured against the context before its pointer crosses the ABI: a short one is an
+     *    Invalid_argument, never an out-of-bounds access (the ABI carries no sizes) */
+    {
+        enum { S = 40 };
+        double bl[7] = {0.0, 0.4, 0.8, 1.2, 0.1, 0.6, 0.3};
+        static uint8_t tips[4][S];
+        static int64_t masks[4][S];
+        static double ps[S], big[7 * 16];
+        value ctx = make_ctx(4, 2, S, 4, PB_FLAG_KEEP_CLV);
+        value d = pb_stub_get_dims(ctx);
+        expect_true("get_dims before set_tree: (4, 2, 40, 4, 0, keep_clv)",
+                    Long_val(Field(d, 0)) == 4 && Long_val(Field(d, 1)) == 2 && Long_val(Field(d, 2)) == S &&
+                    Long_val(Field(d, 3)) == 4 && Long_val(Field(d, 4)) == 0 && Long_val(Field(d, 5)) == PB_FLAG_KEEP_CLV);
+        EXPECT_RAISES("set_pmatrices before set_tree -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_pmatrices(ctx, ba1(big, 7 * 16, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_tree with a short child_ptr -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tree(ctx, Val_int(0), ba1(child_ptr, 7, CAML_BA_INT32), ba1(child_idx, 6, CAML_BA_INT32),
+                                       ba1(tip_row, 7, CAML_BA_INT32), ba1(bl, 7, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_tree with a short child_idx -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tree(ctx, Val_int(0), ba1(child_ptr, 8, CAML_BA_INT32), ba1(child_idx, 5, CAML_BA_INT32),
+                                       ba1(tip_row, 7, CAML_BA_INT32), ba1(bl, 7, CAML_BA_FLOAT64)));
+        set_tree4(ctx, bl);
+        expect_true("get_dims after set_tree: 7 nodes", Long_val(Field(pb_stub_get_dims(ctx), 4)) == 7);
+        EXPECT_RAISES("set_branch_lengths with 6 of 7 entries -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_branch_lengths(ctx, ba1(bl, 6, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_tips with 3 of 4 rows -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tips(ctx, ba2(tips, 3, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT)));
+        EXPECT_RAISES("set_tips with too few columns -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tips(ctx, ba2(tips, 4, S - 1, CAML_BA_UINT8, CAML_BA_C_LAYOUT)));
+        EXPECT_RAISES("set_tips_packed2 with too few bytes per row -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tips_packed2(ctx, ba2(tips, 4, S / 4 - 1, CAML_BA_UINT8, CAML_BA_C_LAYOUT)));
+        EXPECT_RAISES("set_tip_masks with 3 of 4 rows -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_tip_masks(ctx, ba2(masks, 3, S, CAML_BA_INT64, CAML_BA_C_LAYOUT)));
+        EXPECT_RAISES("set_root_frequencies with 3 of 4 entries -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_root_frequencies(ctx, ba1(quarter, 3, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_categories with 1 of 2 rates -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_categories(ctx, ba1(quarter, 1, CAML_BA_FLOAT64), ba1(quarter, 2, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_rate_matrix with a 3 x 3 matrix -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_rate_matrix(ctx, ba2(big, 3, 3, CAML_BA_FLOAT64, CAML_BA_FORTRAN_LAYOUT), ba1(quarter, 4, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("set_pmatrices with one category of two -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_set_pmatrices(ctx, ba1(big, 7 * 16, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("loglik with a per_site array of nsites - 1 -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_loglik(ctx, ba1(ps, S - 1, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("conditional_likelihood with a short carry -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_get_clv(ctx, Val_int(1), Val_int(0), ba2(big, S, 4, CAML_BA_FLOAT64, CAML_BA_C_LAYOUT), ba1(ps, S - 1, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("conditional_simulation with 6 of 7 node rows -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_conditional_simulation(ctx, caml_copy_int64(1), ba2(tips, 6, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT)));
+        EXPECT_RAISES("loglik_host with too few columns -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_loglik_host(ctx, ba2(tips, 4, S - 1, CAML_BA_UINT8, CAML_BA_C_LAYOUT), ba1(&empty, 0, CAML_BA_FLOAT64)));
+        finalise(ctx);
+    }
+
+    /* 8. Felsenstein.Make(A)(Align)(E).felsenstein_single_shift ?threshold param ~site (lib/felsenstein.mli:19-35): E is a
+     *    plain Site_evolution_model.S, so the binding calls E.transition_probability_matrix once per branch on the host
+     *    and uploads the matrices (set_pmatrices), takes ONE column of the alignment, threshold as given, no shift after
+     *    x pi.  The K80 fixture again; then felsenstein_single (no shift at all: threshold -infinity). */
+    {
+        double bl[7] = {0.0, 0.1, 0.1, 0.1, 0.1, 3.0, 0.1}, zero[7] = {0};
+        static double p[7 * 16];
+        /* (the matrices play E.transition_probability_matrix param t; here they come from the device's eigen route,
+         * read back with get_pmatrices: the point is the call sequence of the binding) */
+        double q[16];
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                q[j * 4 + i] = i == j ? -1.0 : ((i ^ j) == 2 ? 0.5 : 0.25);
+        value src = make_ctx(4, 1, 1, 4, 0);
+        set_tree4(src, bl);
+        pb_stub_set_rate_matrix(src, ba2(q, 4, 4, CAML_BA_FLOAT64, CAML_BA_FORTRAN_LAYOUT), ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_get_pmatrices(src, ba1(p, 7 * 16, CAML_BA_FLOAT64));
+        finalise(src);
+        uint8_t column[4] = {0, 0, 0, 3};       /* the alignment's column `site` */
+        for (int pass = 0; pass < 2; pass++) {
+            value ctx = make_ctx(4, 1, 1, 4, 0);
+            set_tree4(ctx, zero);
+            pb_stub_set_pmatrices(ctx, ba1(p, 7 * 16, CAML_BA_FLOAT64));
+            pb_stub_set_tips(ctx, ba2(column, 4, 1, CAML_BA_UINT8, CAML_BA_C_LAYOUT));
+            pb_stub_set_rescaling(ctx, caml_copy_double(pass == 0 ? 0.0000001 : -INFINITY), Val_false);
+            pb_stub_set_root_frequencies(ctx, ba1(quarter, 4, CAML_BA_FLOAT64));
+            expect_close(pass == 0 ? "Felsenstein.Make(..).felsenstein_single_shift, K80 fixture (host matrices)"
+                                   : "Felsenstein.Make(..).felsenstein_single (no shift), K80 fixture",
+                         Double_val(pb_stub_loglik(ctx, ba1(&empty, 0, CAML_BA_FLOAT64))), -5.704499092002674, 1e-12);
+            finalise(ctx);
+        }
+    }
+
+    /* 9. multi-GPU through the binding (Phylo_b200.Sharded): one device here, so no communicator; the same device
+     *    twice is NCCL's error and must come back as Failure, an empty device list as Invalid_argument */
+    {
+        enum { S = 9000 };
+        double bl[7] = {0.0, 0.4, 0.8, 1.2, 0.1, 0.6, 0.3};
+        double q[16];
+        for (int k = 0; k < 16; k++) q[k] = (k % 5 == 0) ? -1.0 : 1.0 / 3.0;
+        static uint8_t bytes[4][S];
+        static double ps[S];
+        for (int r = 0; r < 4; r++)
+            for (int s = 0; s < S; s++) bytes[r][s] = (uint8_t)(s == 0 ? r : (r * 3 + s * 5 + (s >> 4)) & 3);
+        int32_t dev0[2] = {0, 0};
+        value sh = pb_stub_create_sharded(ba1(dev0, 1, CAML_BA_INT32), Val_int(4), Val_int(1), Val_long(S), Val_int(4), Val_int(0));
+        expect_true("Sharded.create on one device", Int_val(pb_stub_sharded_ndev(sh)) == 1);
+        value a[6] = {sh, Val_int(0), ba1(child_ptr, 8, CAML_BA_INT32), ba1(child_idx, 6, CAML_BA_INT32),
+                      ba1(tip_row, 7, CAML_BA_INT32), ba1(bl, 7, CAML_BA_FLOAT64)};
+        pb_stub_sharded_set_tree_bytecode(a, 6);
+        pb_stub_sharded_set_rate_matrix(sh, ba2(q, 4, 4, CAML_BA_FLOAT64, CAML_BA_FORTRAN_LAYOUT), ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_sharded_set_root_frequencies(sh, ba1(quarter, 4, CAML_BA_FLOAT64));
+        pb_stub_sharded_set_tips(sh, ba2(bytes, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT));
+        const double t1 = Double_val(pb_stub_sharded_loglik(sh, ba1(ps, S, CAML_BA_FLOAT64)));
+        expect_close("Sharded.loglik: site 0 (A,C,G,T under JC69)", ps[0], -6.157406549426741, 1e-13);
+        double sum = 0.0;
+        for (int s = 0; s < S; s++) sum += ps[s];
+        expect_close("  total = sum of the per-site values", t1, sum, 1e-13);
+        pb_stub_sharded_set_reduce(sh, Val_int(PB_REDUCE_ORDERED));
+        const double t2 = Double_val(pb_stub_sharded_loglik_host(sh, ba2(bytes, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT), Val_false,
+                                                                 ba1(&empty, 0, CAML_BA_FLOAT64)));
+        expect_true("  Sharded.loglik_host, ordered reduction: the same total", t2 == t1);
+        EXPECT_RAISES("Sharded.loglik with a short per_site -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_sharded_loglik(sh, ba1(ps, S - 1, CAML_BA_FLOAT64)));
+        EXPECT_RAISES("Sharded.set_tips with too few columns -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_sharded_set_tips(sh, ba2(bytes, 4, S - 8, CAML_BA_UINT8, CAML_BA_C_LAYOUT)));
+        Custom_ops_val(sh)->finalize(sh);
+        Custom_ops_val(sh)->finalize(sh);       /* harmless twice */
+        EXPECT_RAISES("Sharded.create with the same device twice -> Failure (PB_ERR_NCCL)", EXN_FAILURE,
+                      pb_stub_create_sharded(ba1(dev0, 2, CAML_BA_INT32), Val_int(4), Val_int(1), Val_long(S), Val_int(4), Val_int(0)));
+        expect_true("  and the message names NCCL", strstr(exn_msg, "NCCL") != NULL);
+        EXPECT_RAISES("Sharded.create without devices -> Invalid_argument", EXN_INVALID_ARGUMENT,
+                      pb_stub_create_sharded(ba1(dev0, 0, CAML_BA_INT32), Val_int(4), Val_int(1), Val_long(S), Val_int(4), Val_int(0)));
+    }
+
     expect_true("runtime lock: every release paired with an acquire, none across a raise", lock_errors == 0 && !lock_released);
-    expect_true("every context finalised", finalised == 8);
+    expect_true("every context finalised", finalised == 12);
     printf(failures ? "%d FAILED\n" : "all ok\n", failures);
     return failures ? 1 : 0;
 }

@@ -84,3 +84,19 @@ def test_cpp_mirror_matches_the_python_mirror_run_by_run():
     for name, (obj, _, its) in want.items():
         assert got[name][1] == its, (name, got[name], obj, its)
         assert got[name][0] == obj, (name, got[name], obj)
+
+
+def test_numpy_simplex_is_the_same_algorithm_to_the_bit():
+    """minimize_np (simplex in one array, for the 263-parameter problem of BASELINE config 5) against the list
+    mirror of lib/nelder_mead.ml:53-132: same value, same point, same iteration count."""
+    import numpy as np
+    from phylogenetics_b200 import nelder_mead as nm
+
+    def rosen(x):
+        x = np.asarray(x)
+        return float(np.sum(100 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+    for d in (2, 7, 23):
+        r1, r2 = np.random.default_rng(d), np.random.default_rng(d)
+        a = nm.minimize(rosen, lambda: list(r1.uniform(-2, 2, d)), tol=1e-10, maxit=2500)
+        b = nm.minimize_np(rosen, lambda: r2.uniform(-2, 2, d), tol=1e-10, maxit=2500)
+        assert a[0] == b[0] and a[2] == b[2] and np.array_equal(np.asarray(a[1]), b[1])

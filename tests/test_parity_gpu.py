@@ -259,6 +259,12 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
         check(per_site, total, expect)
         total2, per_site2 = ctx.loglik(per_site=True)            # bit-reproducible
         assert total2 == total and np.array_equal(per_site, per_site2)
+        if version == 3:                                        # default: nodes with two leaf children are tables
+            ctx.set_option("fused_dmma_cherry", 0)              # ... and without them (scalar table build vs DMMA order:
+            total5, per_site5 = ctx.loglik(per_site=True)       # equal to rounding, not to the bit)
+            check(per_site5, total5, expect)
+            np.testing.assert_allclose(per_site5, per_site, rtol=1e-12)
+            ctx.set_option("fused_dmma_cherry", 1)
         ctx.set_option("fused_pow2", 0)                         # the reference's scale factor 1/max instead of 2^-k
         total4, per_site4 = ctx.loglik(per_site=True)
         check(per_site4, total4, expect)
@@ -543,6 +549,53 @@ def test_fused_reduced_program_kary_tree_and_felsenstein_mode():
                 ctx.set_option("fused_reduced", 0)
                 t2, p2 = ctx.loglik(per_site=True)
                 assert t2 == total and np.array_equal(p2, per_site)
+
+
+def test_cuda_graph_replay_of_one_evaluation():
+    """Option "graph": the optimisation-loop pattern — same tree and tips, new branch lengths / model / categories /
+    frequencies every evaluation — replays one captured evaluation; results equal the plain launches to the bit, and a
+    call that reshapes the launches (a clade limit, new tips) drops the graph and captures again."""
+    from phylogenetics_b200 import models
+    case = cases.make_case("graph", "gtr", 64, 30000, ncat=4, seed=31)
+    rng = np.random.default_rng(1)
+    settings = []
+    for k in range(6):
+        Q, pi = __import__("phylogenetics_b200.synthetic", fromlist=["x"]).random_gtr(rng, 10.0)
+        rates, weights = models.gamma_category_rates(0.3 + 0.2 * k, 4)
+        settings.append((case.bl * (0.8 + 0.1 * k), Q, pi, rates, weights))
+
+    def run(graph):
+        out = []
+        with run_ctx(case, "eigen") as ctx:
+            ctx.set_option("graph", graph)
+            for i, (bl, Q, pi, rates, weights) in enumerate(settings):
+                ctx.set_rate_matrix(Q, pi)
+                ctx.set_root_frequencies(pi)
+                ctx.set_categories(rates, weights)
+                ctx.set_branch_lengths(bl)
+                out.append(ctx.loglik(per_site=True))
+                if i == 3:
+                    ctx.set_option("fused_clade_leaves", 4)     # reshapes the launches: plain evaluation, new capture
+            replays = ctx.graph_replays
+            bad = case.tips.copy()
+            bad[3, 17] = 9
+            ctx.set_tips(bad)                                   # the range check still works after graph mode
+            with pytest.raises(_lib.PhyloB200InvalidArgument):
+                ctx.loglik()
+        return out, replays
+    plain, r0 = run(0)
+    graphed, r1 = run(1)
+    assert r0 == 0 and r1 == 4                                 # evaluations 1, 2, 3 and 5 replay; 0 and 4 are plain
+    for (t0, p0), (t1, p1) in zip(plain, graphed):
+        assert t0 == t1 and np.array_equal(p0, p1)
+    P = None
+    with run_ctx(case, "eigen") as ctx:                         # and they are right
+        bl, Q, pi, rates, weights = settings[2]
+        ctx.set_rate_matrix(Q, pi); ctx.set_root_frequencies(pi); ctx.set_categories(rates, weights); ctx.set_branch_lengths(bl)
+        P = ctx.get_pmatrices()
+    f = case.flat
+    expect = C.pruning(4, f.root, f.child_ptr, f.child_idx, f.tip_row, P, settings[2][2], tips=case.tips, weights=settings[2][4])
+    check(graphed[2][1], graphed[2][0], expect)
 
 
 def test_fused_large_tree_falls_back_to_shared_memory_matrices():
