@@ -242,7 +242,8 @@ struct pb_ctx {
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
     int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
-    int host_lead_cats = 1;             // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
+    int host_lead_cats = 2;             // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
+                                        // (2: profiles/r02f_sweep_e2e_chunks_x_lead_cats.jsonl)
     int host_chunk_align = 1;           // option "host_chunk_align": chunk bounds where a round of the persistent blocks ends
     int fused4t_occ = 3;                // resident blocks per SM of the fused4t shape last launched
     int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)

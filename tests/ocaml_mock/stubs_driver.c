@@ -547,7 +547,7 @@ int main(void)
         expect_close("Sharded.loglik: site 0 (A,C,G,T under JC69)", ps[0], -6.157406549426741, 1e-13);
         double sum = 0.0;
         for (int s = 0; s < S; s++) sum += ps[s];
-        expect_close("  total = sum of the per-site values", t1, sum, 1e-13);
+        expect_close("  total = sum of the per-site values", t1, sum, 1e-12);     /* (a sequential sum here, a tree sum there) */
         pb_stub_sharded_set_reduce(sh, Val_int(PB_REDUCE_ORDERED));
         const double t2 = Double_val(pb_stub_sharded_loglik_host(sh, ba2(bytes, 4, S, CAML_BA_UINT8, CAML_BA_C_LAYOUT), Val_false,
                                                                  ba1(&empty, 0, CAML_BA_FLOAT64)));

@@ -500,32 +500,29 @@ def test_fused_constant_memory_variant(block, spt, ntaxa, ncat, pow2):
                                                         (1500, 1100, 1, "bd"), (200, 5000, 4, "random"), (2, 1300, 4, "bd"),
                                                         (3, 1300, 1, "bd"), (7, 70000, 2, "bd")])
 def test_fused_reduced_program_tree_sizes(ntaxa, nsites, ncat, tree_kind):
-    """fused4t on trees from 2 to 1 500 taxa (the constant bank holds the reduced tree's matrices up to about 1 000
-    taxa; beyond that the shared-memory kernel takes over), every clade limit, against the oracle and against the
-    untabulated kernels bit for bit."""
+    """fused4t on trees from 2 to 1 500 taxa (only the reduced tree's matrices go to the constant bank, so with
+    clades of up to 7 leaves even 1 500 taxa fit; smaller clade limits leave more matrices and may hand a large
+    tree to another kernel), every clade limit, against the oracle, and against the untabulated kernels bit for bit
+    whenever the site-resident path runs."""
     case = cases.make_case("fusedt", "gtr", ntaxa, nsites, ncat=ncat, seed=11, tree_kind=tree_kind)
     P = case.host_P()
     expect = oracle_per_site(case, P)
     with run_ctx(case, "direct", P=P) as ctx:
         ctx.set_option("fused_clade_force", 1)              # (with so few sites the library would stop at 3 leaves)
-        assert ctx.path_name == ("fused4" if ntaxa <= 1024 else "level4")
+        assert ctx.path_name == "fused4"
         total, per_site = ctx.loglik(per_site=True)
         check(per_site, total, expect)
-        if ntaxa > 1024:
-            return
-        for leaves in (8, 6, 4, 2):
-            ctx.set_option("fused_clade_leaves", leaves)
+        settings = [("fused_clade_leaves", 8), ("fused_clade_leaves", 6), ("fused_clade_leaves", 4), ("fused_clade_leaves", 2),
+                    ("fused_clade_leaves", 7), ("fused_cherry", 0), ("fused_reduced", 0), ("fused_const", 0)]
+        for name, value in settings:                        # cumulative: ends on the shared-memory kernel without tables
+            ctx.set_option(name, value)
+            path = ctx.path_name
             t2, p2 = ctx.loglik(per_site=True)
-            assert t2 == total and np.array_equal(p2, per_site), leaves
-        ctx.set_option("fused_clade_leaves", 7)
-        if ntaxa <= 300:                                    # (larger trees do not fit either kernel without tables)
-            ctx.set_option("fused_cherry", 0)               # nothing tabulated: the reduced tree is the tree
-            t2, p2 = ctx.loglik(per_site=True)
-            assert t2 == total and np.array_equal(p2, per_site)
-            ctx.set_option("fused_reduced", 0)
-            ctx.set_option("fused_const", 0)                # the shared-memory kernel, no tables at all
-            t2, p2 = ctx.loglik(per_site=True)
-            assert t2 == total and np.array_equal(p2, per_site)
+            check(p2, t2, expect)
+            if path == "fused4":                            # the site-resident kernels agree to the bit among themselves
+                assert t2 == total and np.array_equal(p2, per_site), (name, value)
+            else:
+                assert ntaxa >= 1024 and path == "level4", (name, value, path)
 
 
 def test_fused_reduced_program_kary_tree_and_felsenstein_mode():
