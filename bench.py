@@ -583,15 +583,22 @@ def run_ours(args, rank, world, local_rank):
         barrier()
     single = None
     if world > 1:
-        # one host thread driving all N devices through the C ABI (pb_create_sharded), while the other ranks idle
+        # one host thread driving all N devices through the C ABI (pb_create_sharded), while the other ranks idle.
+        # They must idle ON THE HOST: a rank waiting in an NCCL barrier keeps a spinning kernel on its GPU, and rank 0's
+        # kernels on that GPU would be time-sliced against it (measured: 5.2 ms per step instead of 0.7).
         barrier()
+        store = dist.distributed_c10d._get_default_store()
         if rank == 0:
             try:
                 single = single_process_block(case, world, tips_pinned, total0, max(5, min(args.steps, 20)))
             except SystemExit:
+                store.set("pb_single_done", "failed")
                 raise
             except Exception as e:
                 single = {"error": repr(e)}
+            store.set("pb_single_done", "1")
+        else:
+            store.wait(["pb_single_done"])
         barrier()
     if rank != 0:
         ctx.close()
@@ -609,7 +616,7 @@ def run_ours(args, rank, world, local_rank):
     tf = flops_eval / (prune_avg_ms * 1e-3) / 1e12
     path = ctx.path_name
     if path == "fused4":
-        kernel_name, nlaunch = "fused4t", ncat
+        kernel_name, nlaunch = "fused4t", max(1, launches // args.steps - 5)     # (P(t), compaction, tables, K3 x 2 are the other five)
         rec = ncu_record(kernel_name)
         roof = {"bound": "fp64", "achieved": tf, "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": tf / FP64_DFMA_PEAK_TFLOPS, "traffic": rec.get("dram_bytes_per_launch"),

@@ -176,7 +176,8 @@ struct pb_ctx {
     DevBuf<FusedOp2> d_fprog_c;
     DevBuf<int> d_inner_nodes, d_leaf_nodes;
     DevBuf<double> d_Pc;
-    int fused_const_cats = 1;           // option "fused_const_cats": categories per fused4c launch
+    int fused_const_cats = 1;           // option "fused_const_cats": categories per launch (fused4c: 1 unless set; fused4t: as many
+    bool fused_const_cats_set = false;  // as the constant bank holds unless set — all four at c2: profiles/r02i_ab_e2e_options.jsonl)
     int fused_const = 1;                // option "fused_const": use fused4c when the tree has <= 128 inner branches
     // fused_dmma: the same program for 20 / 61 states (compact matrix indices, tip rows, matrix order)
     std::vector<FusedOp2> fprog_d;
@@ -242,8 +243,8 @@ struct pb_ctx {
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
     int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
-    int host_lead_cats = 2;             // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
-                                        // (2: profiles/r02f_sweep_e2e_chunks_x_lead_cats.jsonl)
+    int host_lead_cats = 64;            // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
+                                        // (all of them, in one launch per chunk: profiles/r02i_ab_e2e_options.jsonl)
     int host_chunk_align = 1;           // option "host_chunk_align": chunk bounds where a round of the persistent blocks ends
     int fused4t_occ = 3;                // resident blocks per SM of the fused4t shape last launched
     int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)
@@ -1428,7 +1429,8 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         c->launches++;
         c->tables_stale = false;
     }
-    const int per_launch = std::max(1, std::min(c->fused_const_cats, pbk::FUSED_CONST_MATS / std::max(nmat, 1)));
+    const int per_launch = std::max(1, std::min(c->fused_const_cats_set ? c->fused_const_cats : 64,
+                                                pbk::FUSED_CONST_MATS / std::max(nmat, 1)));
     const int per_load = c->fused_const_group ? std::max(per_launch, pbk::FUSED_CONST_MATS / std::max(nmat, 1)) : per_launch;
     for (int g0 = cat_lo; g0 < cat_hi; g0 += per_load) {
         const int gk = std::min(per_load, cat_hi - g0);
@@ -1933,8 +1935,9 @@ int run_root_reduction(pb_ctx* c)
     pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p,
                                                                c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
                                                                c->spad, 0, c->d_per_site.p, c->d_partials.p);
+    c->launches++;
     pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, blocks, c->d_total.p);
-    c->launches += 2;
+    c->launches++;
     PB_CUDA(c, cudaGetLastError());
     return PB_OK;
 }
@@ -3035,6 +3038,7 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "fused_const_cats") {
         if (iv < 1 || iv > 8) return fail(c, PB_ERR_INVALID_ARG, "fused_const_cats must be in 1..8");
         c->fused_const_cats = iv;
+        c->fused_const_cats_set = true;
     } else if (k == "fused_const") {
         c->fused_const = iv != 0;
     } else if (k == "fused_reduced") {

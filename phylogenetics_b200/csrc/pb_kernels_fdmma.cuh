@@ -920,21 +920,34 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
                       int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
 {
     using F = Fd3Shape<N>;
-    __shared__ double sv[64];
+    // A block builds a slice of ONE table, so its three matrices are staged once: the cherry's branch matrix transposed
+    // (thread i reads PVt[j][i]: conflict-free; reading rows of P from global memory, 64 different lines per step, made
+    // the 61-state builder a fifth of the evaluation: 193 us at c4) and the two leaf matrices as they are.
+    extern __shared__ double sh[];
+    double* PVt = sh;                                    // [N][64]
+    double* PAs = PVt + N * 64;                          // [N][N]  leaf A: P[i][a]
+    double* PBs = PAs + N * N;                           // [N][N]  leaf B
+    double* sv = PBs + N * N;                            // [64]
     const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
     const int4 nd = tab_nodes[t];                        // x = leaf A node, y = leaf B node, z = cherry node (-1: the root)
     const double* Pc = P + (size_t)c * nnodes * N * N;
     const double* PA = Pc + (size_t)nd.x * N * N;
     const double* PB = Pc + (size_t)nd.y * N * N;
-    const double* PV = nd.z >= 0 ? Pc + (size_t)nd.z * N * N : nullptr;
+    const bool pre = nd.z >= 0;
+    for (int idx = tid; idx < N * N; idx += 64) {
+        PAs[idx] = PA[idx];
+        PBs[idx] = PB[idx];
+        if (pre) PVt[(idx % N) * 64 + idx / N] = Pc[(size_t)nd.z * N * N + idx];      // PVt[j][i] = PV[i][j]
+    }
     const int thr_hi = __double2hiint(thr);
     const size_t base = (size_t)c * ntab * N * N + (size_t)tabs[t].x;
     for (int e = blockIdx.z; e < N * N; e += gridDim.z) {
         const int a = e / N, b = e - a * N;
         __syncthreads();
-        if (tid < N) sv[tid] = PA[tid * N + a] * PB[tid * N + b];       // column a of leaf A times column b of leaf B
+        if (tid < N) sv[tid] = PAs[tid * N + a] * PBs[tid * N + b];     // column a of leaf A times column b of leaf B
         __syncthreads();
         int hmin = 0x7fffffff, hmax = (int)0x80000000;                  // SV.shift, power-of-two form (shift_tiles8)
+#pragma unroll 4
         for (int j = 0; j < N; j++) {
             const int h = __double2hiint(sv[j]);
             hmin = min(hmin, h);
@@ -945,8 +958,9 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
         if (tid < F::MP8) {
             double y = 0.0;
             if (tid < N) {
-                if (PV) {
-                    for (int j = 0; j < N; j++) y = fma(PV[tid * N + j], sv[j] * f, y);
+                if (pre) {
+#pragma unroll 4
+                    for (int j = 0; j < N; j++) y = fma(PVt[j * 64 + tid], sv[j] * f, y);
                 } else {
                     y = sv[tid] * f;
                 }
@@ -1346,9 +1360,14 @@ inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, con
                                          int ncat, double thr, double* tabV, int* tabK, cudaStream_t stream)
 {
     if (ntab < 1) return;
-    const dim3 grid(ntab, ncat, n == 20 ? 50 : 128);
-    if (n == 20) fdmma3_build_cherries<20><<<grid, 64, 0, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
-    else fdmma3_build_cherries<61><<<grid, 64, 0, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+    const dim3 grid(ntab, ncat, n == 20 ? 20 : 61);                       // 20 / 61 entries per block
+    const size_t smem = ((size_t)n * 64 + 2 * (size_t)n * n + 64) * sizeof(double);       // 61 states: 91 KB
+    if (n == 20) {
+        fdmma3_build_cherries<20><<<grid, 64, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+    } else {
+        cudaFuncSetAttribute(fdmma3_build_cherries<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fdmma3_build_cherries<61><<<grid, 64, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+    }
 }
 
 inline int launch_fused_dmma3(int n, bool pow2, const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)

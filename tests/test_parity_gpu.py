@@ -548,6 +548,48 @@ def test_fused_reduced_program_kary_tree_and_felsenstein_mode():
                 assert t2 == total and np.array_equal(p2, per_site)
 
 
+@pytest.mark.parametrize("n", [2, 3, 7, 16, 21, 33, 60, 64])
+def test_any_state_count(n):
+    """Phylo_ctmc.pruning is generic in ~nstates (lib/phylo_ctmc.mli:55-61): alphabets without a specialised kernel
+    (16 states, 21 = amino acids + gap, a 60-codon code ...) run the runtime-n level kernel; with tip state sets too."""
+    from phylogenetics_b200 import tree as T, synthetic
+    rng = np.random.default_rng(n)
+    flat = T.flatten(synthetic.birth_death_tree(rng, 19))
+    bl = flat.branch_lengths(float)
+    pi = rng.dirichlet(np.full(n, 5.0))
+    S = rng.gamma(1.0, 1.0, size=(n, n))
+    S = S + S.T
+    Q = S * pi[None, :]
+    np.fill_diagonal(Q, 0.0)
+    Q -= np.diag(Q.sum(1))
+    Q /= -(pi * np.diag(Q)).sum()
+    P = synthetic.host_transition_matrices(Q, pi, bl)
+    tips = synthetic.simulate_alignment(rng, flat, P, pi, 777)
+    case = cases.Case("n%d" % n, flat, bl, Q, pi, tips)
+    f = case.flat
+    for keep in (False, True):
+        with run_ctx(case, "direct", keep=keep, P=P) as ctx:
+            total, per_site = ctx.loglik(per_site=True)
+            check(per_site, total, oracle_per_site(case, P))
+    masks = np.uint64(1) << tips.astype(np.uint64)
+    masks[rng.random(masks.shape) < 0.2] = 0
+    masks[:, 5] = 0
+    expect = C.pruning(n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, pi, masks=masks)
+    with LikelihoodContext(n, 777, f.nleaves) as ctx:
+        ctx.set_tree(f, bl)
+        ctx.set_pmatrices(P)
+        ctx.set_tip_masks(masks)
+        ctx.set_root_frequencies(pi)
+        total, per_site = ctx.loglik(per_site=True)
+    nz = expect != 0.0
+    assert per_site[5] == 0.0 and (np.abs(per_site[nz] - expect[nz]) / np.abs(expect[nz])).max() <= 1e-9
+    # P(t) on the device for that alphabet as well (eigen route and Pade route)
+    for route in ("eigen", "expm"):
+        with run_ctx(case, route) as ctx:
+            total, per_site = ctx.loglik(per_site=True)
+            check(per_site, total, oracle_per_site(case, ctx.get_pmatrices()))
+
+
 def test_cuda_graph_replay_of_one_evaluation():
     """Option "graph": the optimisation-loop pattern — same tree and tips, new branch lengths / model / categories /
     frequencies every evaluation — replays one captured evaluation; results equal the plain launches to the bit, and a

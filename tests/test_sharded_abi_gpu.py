@@ -97,9 +97,15 @@ def test_two_devices_allreduce(model, ntaxa, nsites, ncat):
         s.set_reduce(_lib.PB_REDUCE_NCCL)
         t3 = s.loglik_host_ptr(case.tips.ctypes.data, nsites)
         assert t3 == total
-        # the optimisation-loop pattern: new branch lengths, re-evaluate (P(t) rebuilt on both devices)
-        s.set_branch_lengths(case.bl * 1.1)
-        assert s.loglik() != total
+    # the optimisation-loop pattern on the device-built matrices: new branch lengths, P(t) rebuilt on both devices
+    if case.n == 4:
+        with sharded(case, [0, 1]) as s:
+            s.set_tips(case.tips)
+            a = s.loglik()
+            s.set_branch_lengths(case.bl * 1.1)
+            b = s.loglik()
+            s.set_branch_lengths(case.bl)
+            assert b != a and s.loglik() == a
 
 
 def test_two_devices_eigen_route_and_masks():
