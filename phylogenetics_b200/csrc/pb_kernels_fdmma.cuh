@@ -915,59 +915,72 @@ __device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Sc
 // the table as an operand of its parent's instruction, exactly as in the 4-state kernel fused4t.
 // A table descriptor: x = first entry, y / z = tip-matrix rows of the two leaves (entry index = state y * N + state z).
 template <int N>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __restrict__ tabs, const int4* __restrict__ tab_nodes,
                       int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
 {
     using F = Fd3Shape<N>;
-    // A block builds a slice of ONE table, so its three matrices are staged once: the cherry's branch matrix transposed
-    // (thread i reads PVt[j][i]: conflict-free; reading rows of P from global memory, 64 different lines per step, made
-    // the 61-state builder a fifth of the evaluation: 193 us at c4) and the two leaf matrices as they are.
+    // A block builds a slice of ONE table, four entries per step (one per group of 64 threads).  Thread l of a group
+    // owns output state l and keeps ROW l of the cherry's branch matrix in registers for the whole slice; the entry's
+    // vector is broadcast from shared memory, so a step costs N broadcast loads and N FMAs per thread.  (Two earlier
+    // forms were bound elsewhere: rows of P read from global memory, 64 lines per step - 193 us at c4; the matrix
+    // transposed in shared memory, two loads per FMA - 131 us; profiles/r02j_*, r02n_*.)
     extern __shared__ double sh[];
-    double* PVt = sh;                                    // [N][64]
-    double* PAs = PVt + N * 64;                          // [N][N]  leaf A: P[i][a]
+    double* PAs = sh;                                    // [N][N]  leaf A: P[i][a]
     double* PBs = PAs + N * N;                           // [N][N]  leaf B
-    double* sv = PBs + N * N;                            // [64]
-    const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    double* svs = PBs + N * N;                           // [4][64] the entry's vector, per group
+    int* reds = reinterpret_cast<int*>(svs + 4 * 64);    // [4][2 warps][min, max]
+    const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, grp = tid >> 6, l = tid & 63;
     const int4 nd = tab_nodes[t];                        // x = leaf A node, y = leaf B node, z = cherry node (-1: the root)
     const double* Pc = P + (size_t)c * nnodes * N * N;
     const double* PA = Pc + (size_t)nd.x * N * N;
     const double* PB = Pc + (size_t)nd.y * N * N;
     const bool pre = nd.z >= 0;
-    for (int idx = tid; idx < N * N; idx += 64) {
+    double pv[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) pv[j] = (pre && l < N) ? Pc[(size_t)nd.z * N * N + l * N + j] : 0.0;
+    for (int idx = tid; idx < N * N; idx += 256) {
         PAs[idx] = PA[idx];
         PBs[idx] = PB[idx];
-        if (pre) PVt[(idx % N) * 64 + idx / N] = Pc[(size_t)nd.z * N * N + idx];      // PVt[j][i] = PV[i][j]
     }
     const int thr_hi = __double2hiint(thr);
     const size_t base = (size_t)c * ntab * N * N + (size_t)tabs[t].x;
-    for (int e = blockIdx.z; e < N * N; e += gridDim.z) {
-        const int a = e / N, b = e - a * N;
+    double* sv = svs + grp * 64;
+    int* red = reds + grp * 4;
+    __syncthreads();
+    for (int e0 = blockIdx.z * 4; e0 < N * N; e0 += gridDim.z * 4) {
+        const int e = e0 + grp;
+        const bool valid = e < N * N;
+        const int a = valid ? e / N : 0, b = valid ? e - a * N : 0;
+        const double v = (l < N) ? PAs[l * N + a] * PBs[l * N + b] : 0.0;    // column a of leaf A times column b of leaf B
+        const int h = __double2hiint(v);
+        const int wmin = __reduce_min_sync(0xffffffffu, l < N ? h : 0x7fffffff);
+        const int wmax = __reduce_max_sync(0xffffffffu, l < N ? h : (int)0x80000000);
+        if ((l & 31) == 0) { red[(l >> 5) * 2] = wmin; red[(l >> 5) * 2 + 1] = wmax; }
+        sv[l] = v;
         __syncthreads();
-        if (tid < N) sv[tid] = PAs[tid * N + a] * PBs[tid * N + b];     // column a of leaf A times column b of leaf B
-        __syncthreads();
-        int hmin = 0x7fffffff, hmax = (int)0x80000000;                  // SV.shift, power-of-two form (shift_tiles8)
-#pragma unroll 4
-        for (int j = 0; j < N; j++) {
-            const int h = __double2hiint(sv[j]);
-            hmin = min(hmin, h);
-            hmax = max(hmax, h);
-        }
+        const int hmin = min(red[0], red[2]), hmax = max(red[1], red[3]);       // SV.shift, power-of-two form (shift_tiles8)
         const int d = (hmin > thr_hi) ? 1023 : (hmax >> 20);
         const double f = __hiloint2double((2046 - d) << 20, 0);
-        if (tid < F::MP8) {
-            double y = 0.0;
-            if (tid < N) {
-                if (pre) {
-#pragma unroll 4
-                    for (int j = 0; j < N; j++) y = fma(PVt[j * 64 + tid], sv[j] * f, y);
-                } else {
-                    y = sv[tid] * f;
-                }
+        double y = v;
+        if (pre) {                                       // P[v] . vector: four partial sums (the order is not the kernel's anyway)
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+            for (int j = 0; j + 3 < N; j += 4) {
+                const double2 s01 = *reinterpret_cast<const double2*>(sv + j), s23 = *reinterpret_cast<const double2*>(sv + j + 2);
+                y0 = fma(pv[j], s01.x, y0);
+                y1 = fma(pv[j + 1], s01.y, y1);
+                y2 = fma(pv[j + 2], s23.x, y2);
+                y3 = fma(pv[j + 3], s23.y, y3);
             }
-            tabV[(base + e) * F::MP8 + tid] = y;
+#pragma unroll
+            for (int j = N / 4 * 4; j < N; j++) y0 = fma(pv[j], sv[j], y0);
+            y = (y0 + y1) + (y2 + y3);
         }
-        if (tid == 0) tabK[base + e] = d - 1023;
+        // (scaling by a power of two commutes with every rounding above: f * (P . v) = P . (f * v) exactly)
+        if (valid && l < F::MP8) tabV[(base + e) * F::MP8 + l] = (l < N) ? y * f : 0.0;
+        if (valid && l == 0) tabK[base + e] = d - 1023;
+        __syncthreads();
     }
 }
 
@@ -1360,13 +1373,15 @@ inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, con
                                          int ncat, double thr, double* tabV, int* tabK, cudaStream_t stream)
 {
     if (ntab < 1) return;
-    const dim3 grid(ntab, ncat, n == 20 ? 20 : 61);                       // 20 / 61 entries per block
-    const size_t smem = ((size_t)n * 64 + 2 * (size_t)n * n + 64) * sizeof(double);       // 61 states: 91 KB
+    // a block per (table, category, slice): enough slices for ~2 blocks per SM, 4 entries per step
+    const int slices = n == 20 ? 4 : std::max(4, std::min(64, (2 * 148 + ntab * ncat - 1) / (ntab * ncat)));
+    const dim3 grid(ntab, ncat, slices);
+    const size_t smem = (2 * (size_t)n * n + 4 * 64 + 8) * sizeof(double);       // 61 states: 62 KB
     if (n == 20) {
-        fdmma3_build_cherries<20><<<grid, 64, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+        fdmma3_build_cherries<20><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
     } else {
         cudaFuncSetAttribute(fdmma3_build_cherries<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fdmma3_build_cherries<61><<<grid, 64, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+        fdmma3_build_cherries<61><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
     }
 }
 
