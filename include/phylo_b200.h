@@ -221,7 +221,8 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
  *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_cherry" (1 (default): nodes with two leaf children are
- *   tables of N^2 entries carrying their branch matrix, version 3 with power-of-two rescaling), "fused_dmma_slots" (cap on the matrix ring),
+ *   tables of N^2 entries carrying their branch matrix, version 3 with power-of-two rescaling), "fused_dmma_triple" (1
+ *   (default): at 20 states a cherry joined by a leaf is a table of N^3 entries), "fused_dmma_slots" (cap on the matrix ring),
  *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
  *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
  * "graph": see pb_graph_replays.  "host_chunks": column chunks of pb_loglik_host (cut where a round of the persistent

@@ -195,12 +195,17 @@ struct pb_ctx {
     int fused_dmma_cherry = 1;          // option "fused_dmma_cherry"
     std::vector<FusedOp2> dprog_r;
     std::vector<int> mlist_r;
-    std::vector<int4> dtabs, dtab_nodes;   // per table: {first entry, tip row A, tip row B}; {leaf A node, leaf B node, cherry node or -1}
+    std::vector<int4> dtabs;               // per table: {first entry, tip row A, tip row B, tip row C or -1}
+    std::vector<pbk::DenseTabNodes> dtab_nodes;
+    int64_t dtab_entries = 0;              // entries of all tables of one category
+    bool dtab_three = false;               // some table is a three-leaf clade
+    int fused_dmma_triple = 1;             // option "fused_dmma_triple": clades of three leaves (cherry + leaf) as tables, 20 states
     int dstack_r = 0;
     bool dense_reduced_built = false;
     DevBuf<FusedOp2> d_dprog_r;
     DevBuf<int> d_mlist_r;
-    DevBuf<int4> d_dtabs, d_dtab_nodes;
+    DevBuf<int4> d_dtabs;
+    DevBuf<pbk::DenseTabNodes> d_dtab_nodes;
     DevBuf<double> d_dtabV;
     DevBuf<int> d_dtabK;
     DevBuf<double> d_Ppad, d_PTleaf, d_gstack;
@@ -1568,12 +1573,32 @@ int build_dense_reduced_program(pb_ctx* c)
             }
         }
     }
-    std::vector<char> kind(nn, 0);                            // 0 inner, 1 loose tip, 2 cherry (table), 3 a cherry's leaf
+    std::vector<char> kind(nn, 0);                            // 0 inner, 1 loose tip, 2 table (clade root), 3 inside a table's clade
+    std::vector<int> third(nn, -1), cherry_of(nn, -1);        // three-leaf clades: the extra leaf and the cherry under the table's node
     for (int v = 0; v < nn; v++) kind[v] = is_leaf(v) ? 1 : 0;
     for (int v = 0; v < nn; v++) {
         if (is_leaf(v) || c->child_ptr[v + 1] - c->child_ptr[v] != 2) continue;
         const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
         if (is_leaf(a) && is_leaf(b)) { kind[v] = 2; kind[a] = kind[b] = 3; }
+    }
+    // 20 states: a cherry joined by a leaf is a table of N^3 = 8 000 entries (one more matrix-vector product saved) -
+    // while all the tables of all categories stay well inside L2 (measured at c3, 13 such clades, 20 MB: 0.572 ms against
+    // 0.577 ms with cherries only - the products saved are paid back in gather latency; beyond L2 it would lose)
+    if (c->fused_dmma_triple && (int64_t)c->n * c->n * c->n <= 8000) {
+        std::vector<int> cand;
+        for (int v : order) {                                  // (children before parents: the cherries are marked)
+            if (is_leaf(v) || c->child_ptr[v + 1] - c->child_ptr[v] != 2) continue;
+            const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
+            if ((kind[a] == 2 && kind[b] == 1) || (kind[b] == 2 && kind[a] == 1)) cand.push_back(v);
+        }
+        const int64_t bytes = (int64_t)c->ncat * (int64_t)cand.size() * c->n * c->n * c->n * ((c->n + 7) / 8 * 8) * 8;
+        if (bytes <= ((int64_t)32 << 20))
+            for (int v : cand) {
+                const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
+                const int ch = kind[a] == 2 ? a : b;
+                kind[v] = 2; cherry_of[v] = ch; third[v] = ch == a ? b : a;
+                kind[ch] = 3; kind[third[v]] = 3;
+            }
     }
     std::vector<int> su;
     stack_need(c, order, kind, su);
@@ -1588,13 +1613,19 @@ int build_dense_reduced_program(pb_ctx* c)
     c->dtabs.clear();
     c->dtab_nodes.clear();
     std::vector<int> tab_of(nn, -1);
-    const int n2 = c->n * c->n;
+    const int64_t n2 = (int64_t)c->n * c->n;
+    c->dtab_entries = 0;
+    c->dtab_three = false;
     for (int v : order) {
         if (kind[v] != 2) continue;
-        const int a = c->child_idx[c->child_ptr[v]], b = c->child_idx[c->child_ptr[v] + 1];
+        const int ch = cherry_of[v] >= 0 ? cherry_of[v] : v;                 // the node whose two children are leaves
+        const int a = c->child_idx[c->child_ptr[ch]], b = c->child_idx[c->child_ptr[ch] + 1];
+        const int lc = third[v];
         tab_of[v] = (int)c->dtabs.size();
-        c->dtabs.push_back(make_int4((int)c->dtabs.size() * n2, c->tip_row[a], c->tip_row[b], 0));
-        c->dtab_nodes.push_back(make_int4(a, b, v == c->root ? -1 : v, 0));
+        c->dtabs.push_back(make_int4((int)c->dtab_entries, c->tip_row[a], c->tip_row[b], lc >= 0 ? c->tip_row[lc] : -1));
+        c->dtab_nodes.push_back(pbk::DenseTabNodes{a, b, ch, lc, v, v == c->root ? 1 : 0, 0, 0});
+        c->dtab_entries += lc >= 0 ? n2 * c->n : n2;
+        c->dtab_three = c->dtab_three || lc >= 0;
     }
     c->dprog_r.clear();
     c->mlist_r.clear();
@@ -1632,7 +1663,7 @@ int build_dense_reduced_program(pb_ctx* c)
     PB_CUDA(c, cudaMemcpyAsync(c->d_dprog_r.p, c->dprog_r.data(), c->dprog_r.size() * sizeof(FusedOp2), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_mlist_r.p, c->mlist_r.data(), c->mlist_r.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_dtabs.p, c->dtabs.data(), c->dtabs.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_dtab_nodes.p, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_dtab_nodes.p, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(pbk::DenseTabNodes), cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));             // (the host vectors may be rebuilt by the next pb_set_tree)
     return PB_OK;
 }
@@ -1678,13 +1709,14 @@ int launch_fused_dmma_path(pb_ctx* c)
                              c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
                              c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
         if (red) {
-            const size_t entries = (size_t)c->ncat * ntab_d * n * n;
+            const size_t entries = (size_t)c->ncat * c->dtab_entries;
             PB_CUDA(c, c->d_dtabV.ensure(entries * ((n + 7) / 8 * 8)));
             PB_CUDA(c, c->d_dtabK.ensure(entries));
-            pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->ncat, c->threshold,
-                                              c->d_dtabV.p, c->d_dtabK.p, c->stream);
+            pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->dtab_entries,
+                                              c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream);
             c->launches++;
             a.tabV = c->d_dtabV.p; a.tabK = c->d_dtabK.p; a.tabs = c->d_dtabs.p; a.ntab = ntab_d;
+            a.tab_entries = c->dtab_entries;
         }
         if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
             return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
@@ -2571,7 +2603,7 @@ int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t* child_pt
     std::memcpy(ops, c->dprog_r.data(), c->dprog_r.size() * sizeof(FusedOp2));
     std::copy(c->mlist_r.begin(), c->mlist_r.end(), mlist);
     std::memcpy(tabs, c->dtabs.data(), c->dtabs.size() * sizeof(int4));
-    std::memcpy(tab_nodes, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(int4));
+    std::memcpy(tab_nodes, c->dtab_nodes.data(), c->dtab_nodes.size() * sizeof(pbk::DenseTabNodes));
     std::copy(c->inner_nodes.begin(), c->inner_nodes.end(), inner_nodes);
     std::copy(c->leaf_nodes.begin(), c->leaf_nodes.end(), leaf_nodes);
     const int32_t cnt[8] = {(int32_t)c->dprog_r.size(), (int32_t)c->mlist_r.size(), (int32_t)c->dtabs.size(), c->dstack_r,
@@ -3079,6 +3111,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_dmma = value != 0.0;
     } else if (k == "fused_dmma_cherry") {
         c->fused_dmma_cherry = iv != 0;
+    } else if (k == "fused_dmma_triple") {
+        c->fused_dmma_triple = iv != 0;
+        c->dense_reduced_built = false;
     } else if (k == "fused_dmma_version") {
         if (iv < 1 || iv > 3) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_version must be 1, 2 or 3");
         c->fused_dmma_version = iv;

@@ -740,6 +740,7 @@ struct FusedDmmaArgs {
     const double* pi; double thr; int shift_at_root; double* site_cat;
     // fused_dmma3 only: tabulated cherries (reduced program; see DenseTab)
     const double* tabV = nullptr; const int* tabK = nullptr; const int4* tabs = nullptr; int ntab = 0;
+    int64_t tab_entries = 0;          // entries of all tables of one category (N^2 per cherry, N^3 per three-leaf clade)
 };
 
 template <int N>
@@ -914,56 +915,86 @@ __device__ __forceinline__ void shift_tiles8(double (&v)[Fd3Shape<N>::M8][2], Sc
 // birth-death tree.  The program is compiled over the reduced tree (pb_api.cu: build_dense_reduced_program) with
 // the table as an operand of its parent's instruction, exactly as in the 4-state kernel fused4t.
 // A table descriptor: x = first entry, y / z = tip-matrix rows of the two leaves (entry index = state y * N + state z).
+// What a table is made of: leaves A, B under node `cherry`; optionally (three-leaf clade) a third leaf C joining the
+// cherry under `top`.  The table holds P[top] . clv(top) (without the matrix when top is the root of the tree).
+struct DenseTabNodes { int leafA, leafB, cherry, leafC, top, is_root, pad0, pad1; };
+
 template <int N>
 __global__ void __launch_bounds__(256)
-fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __restrict__ tabs, const int4* __restrict__ tab_nodes,
-                      int ntab, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
+fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __restrict__ tabs, const DenseTabNodes* __restrict__ tab_nodes,
+                      int64_t tab_entries, double thr, double* __restrict__ tabV, int* __restrict__ tabK)
 {
     using F = Fd3Shape<N>;
     // A block builds a slice of ONE table, four entries per step (one per group of 64 threads).  Thread l of a group
-    // owns output state l and keeps ROW l of the cherry's branch matrix in registers for the whole slice; the entry's
+    // owns output state l and keeps ROW l of the matrix applied last in registers for the whole slice; the entry's
     // vector is broadcast from shared memory, so a step costs N broadcast loads and N FMAs per thread.  (Two earlier
     // forms were bound elsewhere: rows of P read from global memory, 64 lines per step - 193 us at c4; the matrix
     // transposed in shared memory, two loads per FMA - 131 us; profiles/r02j_*, r02n_*.)
+    // Three-leaf clades (20 states): the inner step shift(col_a * col_b) -> P[cherry] . -> * col_c -> shift runs from
+    // shared memory (P[cherry] transposed), then the same final product.
     extern __shared__ double sh[];
     double* PAs = sh;                                    // [N][N]  leaf A: P[i][a]
     double* PBs = PAs + N * N;                           // [N][N]  leaf B
     double* svs = PBs + N * N;                           // [4][64] the entry's vector, per group
     int* reds = reinterpret_cast<int*>(svs + 4 * 64);    // [4][2 warps][min, max]
+    double* PCs = svs + 4 * 64 + 8;                      // [N][N]  leaf C          (three-leaf clades only)
+    double* PMt = PCs + N * N;                           // [N][65] P[cherry] transposed
     const int t = blockIdx.x, c = blockIdx.y, tid = threadIdx.x, grp = tid >> 6, l = tid & 63;
-    const int4 nd = tab_nodes[t];                        // x = leaf A node, y = leaf B node, z = cherry node (-1: the root)
+    const DenseTabNodes nd = tab_nodes[t];
+    const bool three = nd.leafC >= 0;
+    const int nent = three ? N * N * N : N * N;
     const double* Pc = P + (size_t)c * nnodes * N * N;
-    const double* PA = Pc + (size_t)nd.x * N * N;
-    const double* PB = Pc + (size_t)nd.y * N * N;
-    const bool pre = nd.z >= 0;
+    const bool pre = !nd.is_root;
     double pv[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) pv[j] = (pre && l < N) ? Pc[(size_t)nd.z * N * N + l * N + j] : 0.0;
+    for (int j = 0; j < N; j++) pv[j] = (pre && l < N) ? Pc[(size_t)nd.top * N * N + l * N + j] : 0.0;
     for (int idx = tid; idx < N * N; idx += 256) {
-        PAs[idx] = PA[idx];
-        PBs[idx] = PB[idx];
+        PAs[idx] = Pc[(size_t)nd.leafA * N * N + idx];
+        PBs[idx] = Pc[(size_t)nd.leafB * N * N + idx];
+        if (three) {
+            PCs[idx] = Pc[(size_t)nd.leafC * N * N + idx];
+            PMt[(idx % N) * 65 + idx / N] = Pc[(size_t)nd.cherry * N * N + idx];
+        }
     }
     const int thr_hi = __double2hiint(thr);
-    const size_t base = (size_t)c * ntab * N * N + (size_t)tabs[t].x;
+    const size_t base = (size_t)c * tab_entries + (size_t)tabs[t].x;
     double* sv = svs + grp * 64;
     int* red = reds + grp * 4;
-    __syncthreads();
-    for (int e0 = blockIdx.z * 4; e0 < N * N; e0 += gridDim.z * 4) {
-        const int e = e0 + grp;
-        const bool valid = e < N * N;
-        const int a = valid ? e / N : 0, b = valid ? e - a * N : 0;
-        const double v = (l < N) ? PAs[l * N + a] * PBs[l * N + b] : 0.0;    // column a of leaf A times column b of leaf B
+    auto shift_group = [&](double v, int& d_out) {       // SV.shift over the group's N values, power-of-two form; barrier inside
         const int h = __double2hiint(v);
         const int wmin = __reduce_min_sync(0xffffffffu, l < N ? h : 0x7fffffff);
         const int wmax = __reduce_max_sync(0xffffffffu, l < N ? h : (int)0x80000000);
         if ((l & 31) == 0) { red[(l >> 5) * 2] = wmin; red[(l >> 5) * 2 + 1] = wmax; }
         sv[l] = v;
         __syncthreads();
-        const int hmin = min(red[0], red[2]), hmax = max(red[1], red[3]);       // SV.shift, power-of-two form (shift_tiles8)
-        const int d = (hmin > thr_hi) ? 1023 : (hmax >> 20);
-        const double f = __hiloint2double((2046 - d) << 20, 0);
+        const int hmin = min(red[0], red[2]), hmax = max(red[1], red[3]);
+        d_out = (hmin > thr_hi) ? 1023 : (hmax >> 20);
+        return __hiloint2double((2046 - d_out) << 20, 0);
+    };
+    __syncthreads();
+    for (int e0 = blockIdx.z * 4; e0 < nent; e0 += gridDim.z * 4) {
+        const int e = e0 + grp;
+        const bool valid = e < nent;
+        const int ev = valid ? e : 0;
+        const int cc = three ? ev % N : 0, ab = three ? ev / N : ev;
+        const int a = ab / N, b = ab - a * N;
+        double v = (l < N) ? PAs[l * N + a] * PBs[l * N + b] : 0.0;      // column a of leaf A times column b of leaf B
+        int d = 1023, d1 = 1023;
+        double f = shift_group(v, d);
+        if (three) {                                     // (uniform over the block: a block builds one table)
+            double w = 0.0;
+            if (l < N) {
+#pragma unroll 4
+                for (int j = 0; j < N; j++) w = fma(PMt[j * 65 + l], sv[j] * f, w);
+                w *= PCs[l * N + cc];
+            }
+            d1 = d;
+            __syncthreads();                             // everyone has read sv
+            v = w;
+            f = shift_group(v, d);
+        }
         double y = v;
-        if (pre) {                                       // P[v] . vector: four partial sums (the order is not the kernel's anyway)
+        if (pre) {                                       // P[top] . vector: four partial sums (the order is not the kernel's anyway)
             double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
             for (int j = 0; j + 3 < N; j += 4) {
@@ -979,7 +1010,7 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
         }
         // (scaling by a power of two commutes with every rounding above: f * (P . v) = P . (f * v) exactly)
         if (valid && l < F::MP8) tabV[(base + e) * F::MP8 + l] = (l < N) ? y * f : 0.0;
-        if (valid && l == 0) tabK[base + e] = d - 1023;
+        if (valid && l == 0) tabK[base + e] = (d - 1023) + (d1 - 1023);
         __syncthreads();
     }
 }
@@ -991,7 +1022,8 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
             const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
             const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
             const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat,
-            const double* __restrict__ tabV, const int* __restrict__ tabK, const int4* __restrict__ tabs, int ntab)
+            const double* __restrict__ tabV, const int* __restrict__ tabK, const int4* __restrict__ tabs, int ntab,
+            int64_t tab_entries)
 {
     using F = Fd3Shape<N>;
     constexpr int M8 = F::M8, K4 = F::K4, MP8 = F::MP8, NW = F::NW, KPP = F::KPP, NPAN = F::NPAN;
@@ -1106,11 +1138,18 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
     const double* Tc = nullptr;
     const int* Kc = nullptr;
     auto tab_ptrs = [&](int t, const double*& ca, const double*& cb, Scale<SCALING> (&sc)[2]) {
-        const int4 d = shTabs[t];
+        const int4 d = shTabs[t];                          // first entry, tip rows A, B and (clades of three leaves) C or -1
         const uint8_t* t0 = myT + d.y * 8 + tig * 2;
         const uint8_t* t1 = myT + d.z * 8 + tig * 2;
-        const int ia = d.x + min((int)t0[0], N - 1) * N + min((int)t1[0], N - 1);
-        const int ib = d.x + min((int)t0[1], N - 1) * N + min((int)t1[1], N - 1);
+        int ia = min((int)t0[0], N - 1) * N + min((int)t1[0], N - 1);
+        int ib = min((int)t0[1], N - 1) * N + min((int)t1[1], N - 1);
+        if (d.w >= 0) {
+            const uint8_t* t2 = myT + d.w * 8 + tig * 2;
+            ia = ia * N + min((int)t2[0], N - 1);
+            ib = ib * N + min((int)t2[1], N - 1);
+        }
+        ia += d.x;
+        ib += d.x;
         ca = Tc + (size_t)ia * MP8 + g;
         cb = Tc + (size_t)ib * MP8 + g;
         sc[0].e += Kc[ia];
@@ -1119,8 +1158,8 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
 
     for (int c = 0; c < ncat; c++) {
         const double* PTc = PTleaf + (size_t)c * nleaf * N * MP8;
-        Tc = tabV + (size_t)c * ntab * N * N * MP8;
-        Kc = tabK + (size_t)c * ntab * N * N;
+        Tc = tabV + (size_t)c * tab_entries * MP8;
+        Kc = tabK + (size_t)c * tab_entries;
         for (int r = 0; r < rounds; r++) {
             const int64_t unit = lo + (int64_t)r * NW + warp;
             if (unit >= hi) {                                // no sites left for this warp: keep the ring moving
@@ -1365,23 +1404,24 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
     const int grid = fused_dmma3_grid(N, sm_count, a.spad);
     kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
                                                    a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
-                                                   a.pi, a.thr, a.shift_at_root, a.site_cat, a.tabV, a.tabK, a.tabs, a.ntab);
+                                                   a.pi, a.thr, a.shift_at_root, a.site_cat, a.tabV, a.tabK, a.tabs, a.ntab, a.tab_entries);
     return grid;
 }
 
-inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, const int4* tabs, const int4* tab_nodes, int ntab,
-                                         int ncat, double thr, double* tabV, int* tabK, cudaStream_t stream)
+inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, const int4* tabs, const DenseTabNodes* tab_nodes, int ntab,
+                                         int64_t tab_entries, bool any_three, int ncat, double thr, double* tabV, int* tabK,
+                                         cudaStream_t stream)
 {
     if (ntab < 1) return;
     // a block per (table, category, slice): enough slices for ~2 blocks per SM, 4 entries per step
-    const int slices = n == 20 ? 4 : std::max(4, std::min(64, (2 * 148 + ntab * ncat - 1) / (ntab * ncat)));
+    const int slices = std::max(4, std::min(64, (2 * 148 + ntab * ncat - 1) / (ntab * ncat)));
     const dim3 grid(ntab, ncat, slices);
-    const size_t smem = (2 * (size_t)n * n + 4 * 64 + 8) * sizeof(double);       // 61 states: 62 KB
+    const size_t smem = ((any_three ? 3 : 2) * (size_t)n * n + (any_three ? (size_t)n * 65 : 0) + 4 * 64 + 8) * sizeof(double);
     if (n == 20) {
-        fdmma3_build_cherries<20><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+        fdmma3_build_cherries<20><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, tab_entries, thr, tabV, tabK);
     } else {
-        cudaFuncSetAttribute(fdmma3_build_cherries<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        fdmma3_build_cherries<61><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, ntab, thr, tabV, tabK);
+        cudaFuncSetAttribute(fdmma3_build_cherries<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // 62 KB
+        fdmma3_build_cherries<61><<<grid, 256, smem, stream>>>(P, nnodes, tabs, tab_nodes, tab_entries, thr, tabV, tabK);
     }
 }
 

@@ -28,7 +28,7 @@ def plan(flat, ntaxa, nstates):
     counts = np.zeros(8, np.int32)
     ops = np.zeros((cap, 4), np.int32)
     mlist = np.zeros(cap, np.int32)
-    tabs, tab_nodes = np.zeros((nn, 4), np.int32), np.zeros((nn, 4), np.int32)
+    tabs, tab_nodes = np.zeros((nn, 4), np.int32), np.zeros((nn, 8), np.int32)
     inner, leaf = np.zeros(nn, np.int32), np.zeros(nn, np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = _lib.lib.pb_debug_dense_reduced_program(nn, int(flat.root), p(child_ptr), p(child_idx), p(tip_row), ntaxa, nstates,
@@ -42,16 +42,27 @@ def plan(flat, ntaxa, nstates):
 def run(pl, P, pi, tips, n):
     """Interpret the plan for all sites; returns the per-site likelihood and the matrices applied, in order."""
     nsites = tips.shape[1]
-    tables = []
-    for (ent0, rowA, rowB, _), (la, lb, v, _) in zip(pl["tabs"], pl["tab_nodes"]):
-        t = np.empty((n * n, n))
-        for a in range(n):
-            for b in range(n):
-                val = P[la][:, a] * P[lb][:, b]
-                t[a * n + b] = val if v < 0 else P[v] @ val
-        assert ent0 == len(tables) * n * n
-        tables.append((t, rowA, rowB))
-    tab = lambda k: tables[k][0][tips[tables[k][1]].astype(int) * n + tips[tables[k][2]].astype(int)]      # [nsites][n]
+    tables, nent = [], 0
+    for (ent0, rowA, rowB, rowC), (la, lb, cherry, lc, top, is_root, _, _) in zip(pl["tabs"], pl["tab_nodes"]):
+        assert ent0 == nent
+        cols = P[la][:, :, None] * P[lb][:, None, :]                       # [state][a][b]: clv of the cherry
+        if lc >= 0:                                                       # a leaf joins the cherry: [state][a][b][c]
+            assert n ** 3 <= 8000 and rowC >= 0 and top != cherry
+            inner = np.einsum("ij,jab->iab", P[cherry], cols)
+            cols = inner[:, :, :, None] * P[lc][:, None, None, :]
+        else:
+            assert rowC < 0 and top == cherry
+        flat_cols = cols.reshape(n, -1)                                   # entry = (a * n + b) [* n + c]
+        t = (flat_cols if is_root else P[top] @ flat_cols).T.copy()       # [entry][state]
+        nent += t.shape[0]
+        tables.append((t, rowA, rowB, rowC))
+
+    def tab(k):
+        t, rowA, rowB, rowC = tables[k]
+        idx = tips[rowA].astype(int) * n + tips[rowB].astype(int)
+        if rowC >= 0:
+            idx = idx * n + tips[rowC].astype(int)
+        return t[idx]                                                     # [nsites][n]
     col = lambda leaf_idx, row: P[pl["leaf"][leaf_idx]][:, tips[row].astype(int)].T
     applied = []
 
@@ -107,8 +118,12 @@ def check(flat, P, pi, tips, n):
     ncherry = sum(1 for v in range(flat.nnodes)
                   if flat.child_ptr[v + 1] - flat.child_ptr[v] == 2 and
                   all(flat.child_ptr[c] == flat.child_ptr[c + 1] for c in flat.child_idx[flat.child_ptr[v]:flat.child_ptr[v + 1]]))
-    assert len(pl["tabs"]) == ncherry
-    assert len(pl["mlist"]) == pl["nmat_full"] - sum(1 for (_, _, v, _) in pl["tab_nodes"] if v >= 0)   # one product saved per cherry
+    assert len(pl["tabs"]) == ncherry                         # every cherry is in exactly one table (alone or with a third leaf)
+    triples = int((pl["tab_nodes"][:, 3] >= 0).sum())
+    assert triples == 0 or n ** 3 <= 8000                      # three-leaf clades only where N^3 entries are affordable (20 states)
+    # matrix-vector products saved: one per table that is not the root (its own branch), one more per three-leaf clade (the cherry's)
+    saved = sum(1 for row in pl["tab_nodes"] if not row[5]) + triples
+    assert len(pl["mlist"]) == pl["nmat_full"] - saved
     assert pl["stack"] <= pl["stack_full"]
     return pl
 

@@ -14,8 +14,9 @@ for name, model, ntaxa, nsites in (("c3", "wag", 64, 200_000), ("c4", "mg94", 32
         ctx.set_tree(f, case.bl); ctx.set_rate_matrix(case.Q, case.pi); ctx.set_root_frequencies(case.pi)
         ctx.set_tips(case.tips); ctx.set_timing(True)
         P = None
-        for cherry in (1, 0, 1):
+        for cherry, triple in ((1, 1), (1, 0), (0, 0), (1, 1)):
             ctx.set_option("fused_dmma_cherry", cherry)
+            ctx.set_option("fused_dmma_triple", triple)
             ms = []
             for _ in range(10):
                 ctx.set_branch_lengths(case.bl)
@@ -27,6 +28,6 @@ for name, model, ntaxa, nsites in (("c3", "wag", 64, 200_000), ("c4", "mg94", 32
                 expect = C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi,
                                    tips=np.ascontiguousarray(case.tips[:, :chk]), weights=case.weights)
             rel = float(np.max(np.abs(ps[:chk] - expect) / np.abs(expect)))
-            print(json.dumps({"config": name, "fused_dmma_cherry": cherry, "pruning_ms_min": min(ms[2:]),
+            print(json.dumps({"config": name, "fused_dmma_cherry": cherry, "fused_dmma_triple": triple, "pruning_ms_min": min(ms[2:]),
                               "pruning_ms_median": float(np.median(ms[2:])), "total": tot, "max_rel_vs_oracle_5000_sites": rel,
                               "launches": ctx.kernel_launches}), flush=True)
