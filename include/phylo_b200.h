@@ -366,6 +366,12 @@ int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t *child_pt
                                    int cap_ops, int32_t *mlist, int cap_mlist, int32_t *tabs, int32_t *tab_nodes,
                                    int cap_tabs, int32_t *inner_nodes, int32_t *leaf_nodes);
 
+/* Timeline of the last pipelined pb_loglik_host* call (option "host_trace" = 1): out[0] = number of column chunks K, then
+ * per chunk {first site, sites, ms at which its host-to-device copy ended, ms at which its pruning and root reduction
+ * ended}, then out[1 + 4K] = ms at which the total was on its way to the host; milliseconds since the call's first
+ * enqueue, from CUDA events.  cap >= 2 + 4K doubles. */
+int pb_debug_host_trace(pb_ctx *ctx, double *out, int cap);
+
 const char *pb_version(void);
 
 #ifdef __cplusplus

@@ -34,7 +34,7 @@ thread_local int g_create_status = 0;
 // The fused 4-state kernel stages matrices in the device's constant bank, which every context on
 // that device shares: users are serialised by a host mutex around the enqueue and, on the device,
 // by an event recorded after the last kernel that read the bank.
-std::mutex g_const_mutex;
+std::recursive_mutex g_const_mutex;      // (recursive: the pipelined host evaluation holds it around its launches)
 cudaEvent_t g_const_event[64] = {};
 
 enum PSource { PSRC_NONE = 0, PSRC_EIGEN = 1, PSRC_DIRECT = 2, PSRC_EXPM = 3 };
@@ -244,15 +244,28 @@ struct pb_ctx {
 
     // pipelined host evaluation (pb_loglik_host)
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t pack_stream = nullptr, root_stream = nullptr;   // side streams: a chunk is packed while the one before it is pruned
+    std::vector<cudaEvent_t> pack_events, prune_events;
+    cudaEvent_t ev_root_done = nullptr, ev_lane_done = nullptr;
+    bool bank_held = false;             // inside the lanes of a pipelined host evaluation (launch_fused4t)
+    int host_side_streams = 1;          // option "host_side_streams": 0 = pack, prune and reduce in one stream
     bool tip_bytes_stale = false;       // the alignment is resident 2-bit packed (d_tips2); d_tips is expanded on demand
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
+    uint64_t pc_epoch = 1;              // compactions of the inner matrices (d_Pc) so far: what the constant bank was loaded from
+    int fused_const_keep = 1;           // option "fused_const_keep": do not reload a constant bank that already holds these matrices
+    int fused_split = 1;                // option "fused_split" (measurement hook): the resident evaluation in this many launches
     int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
     int host_lead_cats = 64;            // option "host_lead_cats": rate categories pruned chunk by chunk behind a 2-bit packed copy
                                         // (all of them, in one launch per chunk: profiles/r02i_ab_e2e_options.jsonl)
     int host_chunk_align = 1;           // option "host_chunk_align": chunk bounds where a round of the persistent blocks ends
     int fused4t_occ = 3;                // resident blocks per SM of the fused4t shape last launched
-    int host_chunks = 4;                // option "host_chunks" (3-4 is best at 1M sites x 128 taxa: profiles/r01g_sweep_e2e_chunks.jsonl)
+    int64_t host_tail_sites = 0;        // option "host_tail_sites": the schedule ends on a chunk of about this many sites (0: one round
+                                        // of the persistent blocks, -1: no short last chunk)
+    int host_trace = 0;                 // option "host_trace": timing events per chunk (pb_debug_host_trace)
+    std::vector<cudaEvent_t> trace_events;      // [0] = start, then (copy done, compute done) per chunk, then the end
+    std::vector<int64_t> trace_sites;           // first site and width of every chunk
+    int host_chunks = 6;                // option "host_chunks" (6-8 is best at 1M sites x 128 taxa: profiles/r02u_e2e_trace.jsonl)
 
     // option "graph": one evaluation of the reduced 4-state program captured as a CUDA graph and replayed while nothing
     // that shapes the launches changes (parameter VALUES live in device buffers whose addresses are stable)
@@ -1382,21 +1395,33 @@ int launch_fused4t_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slo
     }
 }
 
+// Categories one launch of the reduced program covers when `ncats` are asked for (what the constant bank holds).
+int fused4t_cats_per_launch(const pb_ctx* c, int ncats)
+{
+    const int nmat = (int)c->rmat_nodes.size();
+    return std::max(1, std::min(ncats, std::min(c->fused_const_cats_set ? c->fused_const_cats : 64,
+                                                pbk::FUSED_CONST_MATS / std::max(nmat, 1))));
+}
+
 // Program and matrices of the constant bank belong to whoever loaded them last (every context of the device
 // shares the bank): owner and program version per device.
 const pb_ctx* g_prog_owner[64] = {};
 uint64_t g_prog_version[64] = {};
+const pb_ctx* g_pinner_owner[64] = {};      // ... and whose matrices (which compaction of them, which categories) cPinner holds
+uint64_t g_pinner_tag[64] = {};
 
 // The reduced program over the site columns [site0, site1), rate categories [cat_lo, cat_hi).  `regather`: the
 // matrices changed since the last call (new P(t)): compact them for the constant bank and refill the tables.
 int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
 {
     if (cat_hi < 0) cat_hi = c->ncat;
-    std::lock_guard<std::mutex> lock(g_const_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_const_mutex);
     cudaEvent_t& bank_free = g_const_event[c->device & 63];
-    // (while an evaluation is being captured the bank's event is handled around the graph launch, pb_loglik_enqueue)
-    if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
-    else if (!c->capturing) PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
+    // (while an evaluation is being captured the bank's event is handled around the graph launch, pb_loglik_enqueue;
+    // the lanes of a pipelined host evaluation only read the bank: loglik_host_impl holds it from its preparation on)
+    bool fresh_event = false;
+    if (!bank_free) { PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming)); fresh_event = true; }
+    if (!fresh_event && !c->capturing && !c->bank_held) PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
     const int nmat = (int)c->rmat_nodes.size();
     int fb = 0, fq = 0;
     if (!fused4t_shape(c, &fb, &fq)) return fail(c, PB_ERR_CUDA, "fused4t: the tree does not fit shared memory");
@@ -1404,6 +1429,7 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         PB_CUDA(c, c->d_Pc.ensure((size_t)c->ncat * nmat * 16));
         pbk::gather_inner_p<<<dim3(4, c->ncat), 256, 0, c->stream>>>(c->d_P.p, c->d_rmat_nodes.p, nmat, c->nnodes, c->d_Pc.p);
         c->launches++;
+        c->pc_epoch++;
     }
     const uint64_t want_version = (c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2) * 32 + (c->r_masked ? c->r_radix : 0);
     if (c->capturing || g_prog_owner[c->device & 63] != c || g_prog_version[c->device & 63] != want_version) {
@@ -1439,16 +1465,22 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     const int per_load = c->fused_const_group ? std::max(per_launch, pbk::FUSED_CONST_MATS / std::max(nmat, 1)) : per_launch;
     for (int g0 = cat_lo; g0 < cat_hi; g0 += per_load) {
         const int gk = std::min(per_load, cat_hi - g0);
-        if (nmat > 0)
+        // (a chunked evaluation launches the same categories once per column chunk: the bank is loaded for the first)
+        const uint64_t tag = (c->pc_epoch * 64 + (uint64_t)g0) * 64 + (uint64_t)gk;
+        if (nmat > 0 && (c->capturing || !c->fused_const_keep || g_pinner_owner[c->device & 63] != c || g_pinner_tag[c->device & 63] != tag)) {
             PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)g0 * nmat * 16,
                                                (size_t)gk * nmat * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice, c->stream));
+            g_pinner_owner[c->device & 63] = c;
+            g_pinner_tag[c->device & 63] = tag;
+        }
         for (int cat0 = g0; cat0 < g0 + gk; cat0 += per_launch) {
             const int k = std::min(per_launch, g0 + gk - cat0);
+            if (site1 <= site0) continue;                     // (prepare only: matrices, tables and the constant bank)
             const int rc = launch_fused4t_shape(c, fb, fq, cat0, k, cat0 - g0, site0, site1);
             if (rc != PB_OK) return rc;
         }
     }
-    if (!c->capturing) PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
+    if (!c->capturing && !c->bank_held) PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
     return PB_OK;
 }
 
@@ -1456,7 +1488,7 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
 int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int cat_lo = 0, int cat_hi = -1)
 {
     if (cat_hi < 0) cat_hi = c->ncat;
-    std::lock_guard<std::mutex> lock(g_const_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_const_mutex);
     cudaEvent_t& bank_free = g_const_event[c->device & 63];
     if (!bank_free) PB_CUDA(c, cudaEventCreateWithFlags(&bank_free, cudaEventDisableTiming));
     else PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));     // another stream may still be reading the bank
@@ -1511,6 +1543,7 @@ int launch_fused4c(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     const int per_load = c->fused_const_group ? std::max(per_launch, pbk::FUSED_CONST_MATS / std::max(ninner, 1)) : per_launch;
     for (int g0 = cat_lo; g0 < cat_hi; g0 += per_load) {
         const int gk = std::min(per_load, cat_hi - g0);
+        g_pinner_owner[c->device & 63] = nullptr;             // (fused4t's record of what the bank holds)
         PB_CUDA(c, cudaMemcpyToSymbolAsync(pbk::cPinner, c->d_Pc.p + (size_t)g0 * ninner * 16,
                                            (size_t)gk * ninner * 16 * sizeof(double), 0, cudaMemcpyDeviceToDevice,
                                            c->stream));
@@ -1820,7 +1853,12 @@ int run_pruning(pb_ctx* c)
             c->packed_for_reduced = reduced;
             c->tips_checked = true;
         }
-        rc = launch_fused4(c, 0, c->spad, reduced);
+        if (c->fused_split > 1 && reduced) {
+            const int64_t step = round_up((c->spad + c->fused_split - 1) / c->fused_split, 1024);
+            for (int64_t s0 = 0; s0 < c->spad; s0 += step)
+                if ((rc = launch_fused4(c, s0, std::min(s0 + step, c->spad), reduced)) != PB_OK) return rc;
+        } else
+            rc = launch_fused4(c, 0, c->spad, reduced);
         if (rc != PB_OK) return rc;
         PB_CUDA(c, cudaGetLastError());
         return PB_OK;
@@ -2057,6 +2095,11 @@ void pb_destroy(pb_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    {
+        std::lock_guard<std::recursive_mutex> lock(g_const_mutex);      // a later context may get this address
+        if (g_prog_owner[c->device & 63] == c) g_prog_owner[c->device & 63] = nullptr;
+        if (g_pinner_owner[c->device & 63] == c) g_pinner_owner[c->device & 63] = nullptr;
+    }
     if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);   // work may still use our buffers
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
@@ -2065,6 +2108,13 @@ void pb_destroy(pb_ctx* c)
     for (auto& set : c->ev_ring)
         for (int i = 0; i < 4; i++) if (set[i]) cudaEventDestroy(set[i]);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->pack_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prune_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->trace_events) cudaEventDestroy(e);
+    if (c->ev_root_done) cudaEventDestroy(c->ev_root_done);
+    if (c->ev_lane_done) cudaEventDestroy(c->ev_lane_done);
+    if (c->pack_stream) { cudaStreamSynchronize(c->pack_stream); cudaStreamDestroy(c->pack_stream); }
+    if (c->root_stream) { cudaStreamSynchronize(c->root_stream); cudaStreamDestroy(c->root_stream); }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
@@ -2726,11 +2776,12 @@ static int enqueue_graph(pb_ctx* c, bool* done)
         c->graph_epoch = c->config_epoch;
     }
     {
-        std::lock_guard<std::mutex> lock(g_const_mutex);      // the constant bank is ours for the whole graph
+        std::lock_guard<std::recursive_mutex> lock(g_const_mutex);      // the constant bank is ours for the whole graph
         if (bank_free) PB_CUDA(c, cudaStreamWaitEvent(c->stream, bank_free, 0));
         PB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
         if (bank_free) PB_CUDA(c, cudaEventRecord(bank_free, c->stream));
         g_prog_owner[c->device & 63] = c;                     // (the graph uploads its program every time)
+        g_pinner_owner[c->device & 63] = nullptr;             // (... and its matrices; what the bank holds afterwards is the last group's)
         g_prog_version[c->device & 63] = (c->fprog_version * 64 + (uint64_t)c->r_leaves * 4 + 2) * 32;
     }
     c->launches += c->graph_launches;
@@ -2835,32 +2886,93 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
     PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
     PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
-    int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
-    if (reduced && c->host_chunk_align) {
-        // A launch of the persistent kernel costs whole ROUNDS of its resident blocks: cut the columns where a round
-        // ends (sm_count x blocks per SM x sites per block), so that no chunk pays for a mostly empty round.
-        int fb = 0, fq = 0;
-        fused4t_shape(c, &fb, &fq);
-        const int64_t wave = (int64_t)c->sm_count * std::max(c->fused4t_occ, 1) * fb * fq;
-        const int64_t per = std::max<int64_t>(1, (c->spad / c->host_chunks + wave / 2) / wave);
-        chunk = round_up(per * wave, 1024);
-        while ((c->spad + chunk - 1) / chunk > 64) chunk *= 2;           // (the event pool holds 64 chunks)
-    }
-    while ((int64_t)c->chunk_events.size() < (c->spad + chunk - 1) / chunk) {
-        cudaEvent_t e;
-        PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->chunk_events.push_back(e);
-    }
-    // 2-bit packed: only the first `host_lead_cats` categories (default 1) are pruned chunk by chunk behind the
-    // copy, the others run once over all the sites.  A launch costs one round of the persistent blocks (~0.09 ms)
-    // however few tiles it has, so more chunked launches lose more than the overlap wins
-    // (profiles/r01m_sweep_e2e_chunks_x_lead_cats.jsonl).
+    size_t tr = 0;                                                // option "host_trace": next timing event
+    auto trace = [&](cudaStream_t st) -> cudaError_t {
+        if (!c->host_trace) return cudaSuccess;
+        if (tr == c->trace_events.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            c->trace_events.push_back(e);
+        }
+        return cudaEventRecord(c->trace_events[tr++], st);
+    };
+    c->trace_sites.clear();
+    PB_CUDA(c, trace(c->stream));
+    // 2-bit packed: the first `host_lead_cats` categories (default: all) are pruned chunk by chunk behind the copy in one
+    // launch per chunk, the others (if any) run once over all the sites.
     const bool first_cat_only = packed2 && c->ncat > 1 && (reduced || fused_const_ok(c));
     const int lead_cats = std::max(1, std::min(c->host_lead_cats, c->ncat));
-    int k = 0;
-    for (int64_t s0 = 0; s0 < c->spad; s0 += chunk, k++) {
-        const int64_t s1 = std::min(s0 + chunk, c->spad);
+    const bool root_per_chunk = !first_cat_only || lead_cats == c->ncat;
+    // Column bounds of the chunks.  A launch of the persistent kernel costs whole ROUNDS of its resident blocks (they
+    // are dealt over the categories of the launch: a round covers sm_count x blocks per SM / categories blocks of
+    // fb x fq sites), so chunks are whole rounds (cut to the 1024 sites = 256 packed bytes the copies are aligned to).
+    // What the pipeline cannot hide is the work behind the LAST copy: the schedule is laid from the end — a short
+    // last chunk (option "host_tail_sites"; default one round), regular chunks before it, what is left over first.
+    std::vector<int64_t> bounds;
+    if (reduced && c->host_chunk_align) {
+        int fb = 0, fq = 0;
+        fused4t_shape(c, &fb, &fq);
+        const int cats_per_launch = fused4t_cats_per_launch(c, first_cat_only ? lead_cats : c->ncat);
+        const int64_t blocks_x = std::max<int64_t>(1, ((int64_t)c->sm_count * std::max(c->fused4t_occ, 1) + cats_per_launch - 1) / cats_per_launch);
+        const int64_t round = blocks_x * fb * fq;                                  // sites of one round
+        auto rounds = [&](int64_t r) { return std::max<int64_t>(1024, r * round / 1024 * 1024); };
+        const int64_t per = std::max<int64_t>(1, (c->spad / c->host_chunks + round / 2) / round);
+        const int64_t tail = c->host_tail_sites < 0 ? 0 : rounds(std::max<int64_t>(1, c->host_tail_sites / round));
+        int64_t hi = c->spad;
+        bounds.push_back(hi);
+        if (tail > 0 && hi > tail + rounds(1) / 2) bounds.push_back(hi -= tail);
+        while (hi > rounds(per) + rounds(1) / 2 && bounds.size() < 63) bounds.push_back(hi -= rounds(per));
+        bounds.push_back(0);
+        std::reverse(bounds.begin(), bounds.end());
+    } else {
+        const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
+        for (int64_t s0 = 0; s0 < c->spad; s0 += chunk) bounds.push_back(s0);
+        bounds.push_back(c->spad);
+    }
+    const int nchunks = (int)bounds.size() - 1;
+    auto grow = [&](std::vector<cudaEvent_t>& v) -> cudaError_t {
+        while ((int)v.size() < nchunks) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (err != cudaSuccess) return err;
+            v.push_back(e);
+        }
+        return cudaSuccess;
+    };
+    PB_CUDA(c, grow(c->chunk_events));
+    // Two lanes: the chunks alternate between two streams, each packing, pruning and reducing its chunk in order.
+    // Nothing orders chunk k+1 after chunk k, so its blocks take over the SMs as the persistent blocks of chunk k
+    // retire — no ramp between launches — and the small pack / reduction kernels run in the gaps.
+    const bool side = c->host_side_streams != 0;
+    // The lanes' launches only READ the constant bank when one load holds every category they ask for: they neither wait
+    // for nor move the bank's event; the bank is ours (mutex) from its preparation until the event is recorded behind
+    // the joined lanes.
+    const int want_cats = first_cat_only ? lead_cats : c->ncat;
+    const bool hold_bank = side && reduced && c->fused_const_keep && fused4t_cats_per_launch(c, want_cats) == want_cats;
+    std::unique_lock<std::recursive_mutex> bank_lock(g_const_mutex, std::defer_lock);
+    if (hold_bank) bank_lock.lock();
+    // Nothing of this depends on the alignment: matrices for the constant bank and the clade tables are built while
+    // the first chunk is on its way.
+    if (reduced && (rc = launch_fused4t(c, 0, 0, true, 0, want_cats)) != PB_OK) return rc;
+    cudaStream_t lanes[2] = {c->stream, c->stream};
+    if (side) {
+        if (!c->pack_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+        if (!c->root_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->root_stream, cudaStreamNonBlocking));
+        if (!c->ev_root_done) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_root_done, cudaEventDisableTiming));
+        if (!c->ev_lane_done) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_lane_done, cudaEventDisableTiming));
+        lanes[0] = c->pack_stream;
+        lanes[1] = c->root_stream;
+        PB_CUDA(c, cudaEventRecord(c->ev_root_done, c->stream));       // (matrices, tables, the constant bank; earlier work)
+        PB_CUDA(c, cudaStreamWaitEvent(lanes[0], c->ev_root_done, 0));
+        PB_CUDA(c, cudaStreamWaitEvent(lanes[1], c->ev_root_done, 0));
+    }
+    cudaStream_t const main_stream = c->stream;
+    struct Restore { pb_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->bank_held = false; } } restore{c, main_stream};
+    for (int k = 0; k < nchunks; k++) {
+        const int64_t s0 = bounds[k], s1 = bounds[k + 1];
         const int64_t w = std::min(s1, c->nsites) - s0;
+        cudaStream_t lane = lanes[k & 1];
         if (w > 0 && !packed2)
             PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p + s0, c->spad, states + s0, ld, w, c->ntaxa,
                                          cudaMemcpyHostToDevice, c->copy_stream));
@@ -2868,36 +2980,53 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
             PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips2.p + s0 / 4, c->spad / 4, states + s0 / 4, ld, (w + 3) / 4, c->ntaxa,
                                          cudaMemcpyHostToDevice, c->copy_stream));
         PB_CUDA(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
-        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+        PB_CUDA(c, trace(c->copy_stream));
+        c->trace_sites.push_back(s0);
+        c->trace_sites.push_back(s1 - s0);
+        PB_CUDA(c, cudaStreamWaitEvent(lane, c->chunk_events[k], 0));
         if (packed2) {
             // The program-order words come straight from the 2-bit upload.  The byte-per-site matrix that other
             // consumers read (level kernels, pb_get_clv, a re-pack after pb_set_tree) is expanded when one of them
             // asks for it (ensure_tip_bytes): an evaluation loop over host alignments never pays for it.
-            pbk::pack_tips4_from2<<<(unsigned)(((s1 - s0) / 4 + 255) / 256), 256, 0, c->stream>>>(
+            pbk::pack_tips4_from2<<<dim3((unsigned)(((s1 - s0) / 16 + 127) / 128), (unsigned)std::min(nwords, 65535)), 128, 0, lane>>>(
                 c->d_tips2.p, c->spad / 4, d_order, d_xorder, nslots, nwords, c->d_packed.p, c->spad, s0 / 4, s1 / 4);
             c->launches++;
         } else {
-            pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, c->stream>>>(
+            pbk::pack_tips4<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, lane>>>(
                 c->d_tips.p, c->spad, d_order, d_xorder, nslots, nwords, c->d_packed.p, c->spad, s0, s1, c->d_bad.p);
             c->launches++;
         }
-        if (first_cat_only) {                                // the other categories follow once, over all the sites
-            if ((rc = reduced ? launch_fused4t(c, s0, s1, s0 == 0, 0, lead_cats)
-                              : launch_fused4c(c, s0, s1, s0 == 0, 0, lead_cats)) != PB_OK) return rc;
-            continue;
-        }
-        if ((rc = launch_fused4(c, s0, s1, reduced)) != PB_OK) return rc;
+        c->stream = lane;                                    // (the launchers enqueue on the context's stream)
+        c->bank_held = hold_bank;
+        if (first_cat_only) {                                // categories beyond lead_cats follow once, over all the sites
+            rc = reduced ? launch_fused4t(c, s0, s1, false, 0, lead_cats) : launch_fused4c(c, s0, s1, s0 == 0, 0, lead_cats);
+        } else
+            rc = reduced ? launch_fused4t(c, s0, s1, false) : launch_fused4(c, s0, s1, false);
+        c->stream = main_stream;
+        c->bank_held = false;
+        if (rc != PB_OK) return rc;
         const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
-        if (b1 > b0) {
-            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(
+        if (root_per_chunk && b1 > b0) {
+            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, lane>>>(
                 c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
                 c->spad, b0, c->d_per_site.p, c->d_partials.p);
             c->launches++;
         }
+        PB_CUDA(c, trace(lane));
     }
-    if (first_cat_only) {
-        if (c->ncat > lead_cats && (rc = reduced ? launch_fused4t(c, 0, c->spad, false, lead_cats, c->ncat)
-                                                 : launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
+    if (side) {
+        PB_CUDA(c, cudaEventRecord(c->ev_root_done, lanes[0]));
+        PB_CUDA(c, cudaEventRecord(c->ev_lane_done, lanes[1]));
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_root_done, 0));
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_lane_done, 0));
+        if (hold_bank) {
+            PB_CUDA(c, cudaEventRecord(g_const_event[c->device & 63], c->stream));
+            bank_lock.unlock();
+        }
+    }
+    if (!root_per_chunk) {
+        if ((rc = reduced ? launch_fused4t(c, 0, c->spad, false, lead_cats, c->ncat)
+                          : launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
         pbk::root_combine<<<(unsigned)nblocks, 256, 0, c->stream>>>(
             c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
             c->spad, 0, c->d_per_site.p, c->d_partials.p);
@@ -2910,6 +3039,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, trace(c->stream));
     c->have_tips = true;
     c->have_masks = false;
     c->pack_dirty = false;
@@ -2920,6 +3050,31 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     c->fresh = true;
     c->tip_bytes_stale = packed2;
     return fetch ? pb_loglik_fetch(c, total, per_site) : PB_OK;
+}
+
+int pb_debug_host_trace(pb_ctx* c, double* out, int cap)
+{
+    PB_ENTER(c);
+    const int nchunks = (int)c->trace_sites.size() / 2;
+    if (!c->host_trace || nchunks == 0 || (int)c->trace_events.size() < 2 * nchunks + 2)
+        return fail(c, PB_ERR_STATE, "option host_trace is off or no pipelined host evaluation has run");
+    if (!out || cap < 2 + 4 * nchunks) return fail(c, PB_ERR_INVALID_ARG, "trace: buffer too small");
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    auto ms = [&](int i, double* v) -> cudaError_t {
+        float f = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&f, c->trace_events[0], c->trace_events[i]);
+        *v = f;
+        return e;
+    };
+    out[0] = nchunks;
+    for (int k = 0; k < nchunks; k++) {
+        out[1 + 4 * k] = (double)c->trace_sites[2 * k];
+        out[2 + 4 * k] = (double)c->trace_sites[2 * k + 1];
+        PB_CUDA(c, ms(1 + 2 * k, &out[3 + 4 * k]));
+        PB_CUDA(c, ms(2 + 2 * k, &out[4 + 4 * k]));
+    }
+    PB_CUDA(c, ms(1 + 2 * nchunks, &out[1 + 4 * nchunks]));
+    return PB_OK;
 }
 
 int pb_loglik_host_enqueue(pb_ctx* c, const uint8_t* states, int64_t ld, int packed2)
@@ -3142,6 +3297,18 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->host_lead_cats = iv;
     } else if (k == "graph") {
         c->use_graph = iv != 0;
+    } else if (k == "fused_const_keep") {
+        c->fused_const_keep = iv != 0;
+    } else if (k == "fused_split") {
+        if (iv < 1 || iv > 64) return fail(c, PB_ERR_INVALID_ARG, "fused_split must be in 1..64");
+        c->fused_split = iv;
+    } else if (k == "host_tail_sites") {
+        if (iv < -1) return fail(c, PB_ERR_INVALID_ARG, "host_tail_sites must be >= -1");
+        c->host_tail_sites = iv;
+    } else if (k == "host_side_streams") {
+        c->host_side_streams = iv != 0;
+    } else if (k == "host_trace") {
+        c->host_trace = iv != 0;
     } else if (k == "host_chunk_align") {
         c->host_chunk_align = iv != 0;
     } else if (k == "host_chunks") {

@@ -593,7 +593,8 @@ __device__ __forceinline__ double block_sum_256(double x, double* red)
     return r;   // valid in thread 0
 }
 
-__global__ void __launch_bounds__(256)
+// (at most 40 registers: its blocks run beside the three resident blocks of the pruning kernel on a side stream)
+__global__ void __launch_bounds__(256, 6)
 root_combine(const double* __restrict__ site_cat, int ncat, const double* __restrict__ weights,
              const double* __restrict__ site_weights,   // nullable: multiplicity of every column (pattern compression)
              int64_t nsites, int64_t spad, int64_t block0, double* __restrict__ per_site,

@@ -108,50 +108,74 @@ expand_tips2(const uint8_t* __restrict__ in, int64_t ld_in, uint8_t* __restrict_
 
 // The two steps above in one, for the pipelined host evaluation (pb_loglik_host_packed2): 2-bit codes in the
 // HOST layout (in[row][byte], 4 sites per byte) -> 2-bit codes in PROGRAM order (packed[word][site], 32 tips per
-// word).  One thread per byte column = 4 sites: per 32 tips it gathers one byte per tip (32 consecutive bytes per
-// warp and row) and writes its sites' four words as two 16-byte stores.  Moves ntaxa/4 bytes in and
-// ntaxa/4 (rounded up to whole words) bytes out per site, against 1.25 + 1.4 bytes per tip for expand + pack.
-__global__ void __launch_bounds__(256)
+// word).  This is a transpose of 2-bit elements: a thread takes one 32-bit column of the upload (16 sites; a warp reads
+// 128 consecutive bytes of a row), gathers the rows of 16 slots, transposes the 16 x 16 matrix of 2-bit elements in
+// registers (four masked-swap stages, 0.75 instructions per element instead of 3 for shift-and-or) and, after both
+// halves of a word, writes its 16 sites' words as four 32-byte stores.  Moves ntaxa/4 bytes in and ntaxa/4 (rounded
+// up to whole words) bytes out per site.  grid (32-bit columns / 128, words): small blocks (128 threads, the 32 row
+// indices of their word in shared memory) that run beside the resident blocks of the pruning kernel on a side stream.
+template <int J>
+__device__ __forceinline__ void transpose_stage(uint32_t (&A)[16])
+{
+    constexpr uint32_t m = J == 8 ? 0x0000FFFFu : J == 4 ? 0x00FF00FFu : J == 2 ? 0x0F0F0F0Fu : 0x33333333u;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k & J) continue;
+        const uint32_t t = ((A[k] >> (2 * J)) ^ A[k + J]) & m;
+        A[k] ^= t << (2 * J);
+        A[k + J] ^= t;
+    }
+}
+
+__device__ __forceinline__ void transpose16x16x2(uint32_t (&A)[16])
+{
+    // A[k] bits 2i..2i+1 = element (k, i)  ->  A[i] bits 2k..2k+1 = element (k, i)
+    transpose_stage<8>(A);
+    transpose_stage<4>(A);
+    transpose_stage<2>(A);
+    transpose_stage<1>(A);
+}
+
+__global__ void __launch_bounds__(128)
 pack_tips4_from2(const uint8_t* __restrict__ in, int64_t ld_in, const int* __restrict__ order, const int* __restrict__ xorder,
                  int ntips, int nwords, uint64_t* __restrict__ packed, int64_t spad, int64_t byte0, int64_t byte1)
 {
-    __shared__ int s_order[PACK_ORDER_SMEM];
-    const bool staged = ntips <= PACK_ORDER_SMEM;
-    if (staged) {
-        for (int i = threadIdx.x; i < ntips; i += blockDim.x) s_order[i] = order[i];
+    // rows of the upload are 256-byte aligned and byte0, byte1, ld_in multiples of 256 (chunk bounds are multiples of
+    // 1024 sites): whole 32-bit columns
+    __shared__ int s_row[32], s_xrow[32];
+    const uint32_t* __restrict__ in32 = reinterpret_cast<const uint32_t*>(in);
+    const int64_t ld32 = ld_in >> 2;
+    const int64_t col = (byte0 >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = col < (byte1 >> 2);
+    for (int w = blockIdx.y; w < nwords; w += gridDim.y) {
         __syncthreads();
-    }
-    const int* ord = staged ? s_order : order;
-    const int64_t b = byte0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // byte columns [byte0, byte1)
-    if (b >= byte1) return;
-    for (int w = 0; w < nwords; w++) {
-        unsigned v[32];
-        int row[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) row[j] = ord[min(w * 32 + j, ntips - 1)];      // a negative row is a padding slot
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = in[(int64_t)max(row[j], 0) * ld_in + b];
-        if (xorder) {                                  // 2-bit fields XOR independently: whole bytes at once
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int xr = xorder[min(w * 32 + j, ntips - 1)];
-                if (xr >= 0) v[j] ^= in[(int64_t)xr * ld_in + b];
-            }
+        if (threadIdx.x < 32) {
+            const int slot = w * 32 + threadIdx.x;
+            s_row[threadIdx.x] = slot < ntips ? order[slot] : -1;                   // a negative row is a padding slot
+            s_xrow[threadIdx.x] = (xorder && slot < ntips) ? xorder[slot] : -1;     // difference coding: XOR with this row
         }
-        uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        __syncthreads();
+        if (!live) continue;
+        uint32_t A[16], B[16];                         // slots 0..15 and 16..31 of the word
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            if (w * 32 + j < ntips && row[j] >= 0) {
-                const uint64_t x = v[j];
-                w0 |= (x & 3u) << (2 * j);
-                w1 |= ((x >> 2) & 3u) << (2 * j);
-                w2 |= ((x >> 4) & 3u) << (2 * j);
-                w3 |= (x >> 6) << (2 * j);
-            }
+        for (int k = 0; k < 32; k++) {
+            // branch-free: padding slots and tips without a difference row read row 0 and drop it (2-bit fields XOR
+            // independently: 16 sites at once; the tips of a clade share their first tip's row, an L1 hit)
+            const int r = s_row[k], xr = s_xrow[k];
+            const uint32_t x = in32[(int64_t)max(r, 0) * ld32 + col];
+            const uint32_t base = in32[(int64_t)max(xr, 0) * ld32 + col];
+            const uint32_t v = r >= 0 ? (x ^ (xr >= 0 ? base : 0u)) : 0u;
+            if (k < 16) A[k] = v; else B[k - 16] = v;
         }
-        ulonglong2* out = reinterpret_cast<ulonglong2*>(packed + (int64_t)w * spad + 4 * b);   // 32-byte aligned
-        out[0] = make_ulonglong2(w0, w1);
-        out[1] = make_ulonglong2(w2, w3);
+        transpose16x16x2(A);
+        transpose16x16x2(B);
+        uint64_t* out = packed + (int64_t)w * spad + 16 * col;               // 128-byte aligned
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(out + i),
+                         "l"((uint64_t)A[i] | (uint64_t)B[i] << 32), "l"((uint64_t)A[i + 1] | (uint64_t)B[i + 1] << 32),
+                         "l"((uint64_t)A[i + 2] | (uint64_t)B[i + 2] << 32), "l"((uint64_t)A[i + 3] | (uint64_t)B[i + 3] << 32)
+                         : "memory");
     }
 }
 

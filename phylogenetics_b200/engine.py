@@ -284,6 +284,14 @@ class LikelihoodContext:
     def kernel_launches(self):
         return int(lib.pb_kernel_launches(self._ctx))
 
+    def host_trace(self):
+        """pb_debug_host_trace: timeline of the last pipelined host evaluation (option "host_trace"): a list of
+        (first site, sites, copy-done ms, compute-done ms) per column chunk and the ms at which the call's device work ended."""
+        out = np.zeros(2 + 4 * 64)
+        self._ck(lib.pb_debug_host_trace(self._ctx, out.ctypes.data, len(out)))
+        k = int(out[0])
+        return [tuple(float(x) for x in out[1 + 4 * i:5 + 4 * i]) for i in range(k)], float(out[1 + 4 * k])
+
     @property
     def graph_replays(self):
         """Evaluations that were replays of the captured CUDA graph (option "graph")."""

@@ -105,3 +105,43 @@ def test_two_bit_packed_host_alignment(nsites, chunks):
     with LikelihoodContext(20, 10, 5) as ctx:            # 4 states only
         with pytest.raises(_lib.PhyloB200Error):
             ctx.set_tips_packed2(np.zeros((5, 3), np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [{}, {"host_side_streams": 0}, {"host_chunks": 12}, {"host_tail_sites": -1},
+                                  {"host_tail_sites": 200000, "host_chunks": 3}, {"host_chunk_align": 0, "host_chunks": 5},
+                                  {"host_lead_cats": 1}, {"fused_const_keep": 0}, {"fused_const_cats": 1}])
+def test_pipelined_schedule_variants(opts):
+    """The column-chunk schedule of the pipelined host evaluation (whole rounds of the persistent blocks, laid from the
+    end with a short last chunk; chunks alternating between two lanes; the 2-bit transpose kernel): every schedule gives
+    the per-site values of the resident evaluation to the bit, on enough sites for several chunks, and the timeline
+    (pb_debug_host_trace) covers the columns exactly once."""
+    import cases
+    from phylogenetics_b200.engine import pack_tips2
+    nsites = 700_001
+    case = cases.make_case("sched", "gtr", 24, nsites, ncat=2, seed=11)
+    packed = pack_tips2(case.tips)
+    with LikelihoodContext(4, nsites, 24, ncat=2) as ctx:
+        ctx.set_tree(case.flat, case.bl)
+        ctx.set_categories(case.rates, case.weights)
+        ctx.set_rate_matrix(case.Q, case.pi)
+        ctx.set_root_frequencies(case.pi)
+        ctx.set_tips(case.tips)
+        total, per_site = ctx.loglik(per_site=True)
+        for name, value in opts.items():
+            ctx.set_option(name, value)
+        ctx.set_option("host_trace", 1)
+        for _ in range(2):                                   # (the second call reuses streams, events and the constant bank)
+            total2, per_site2 = ctx.loglik_host_packed2(packed, per_site=True)
+            assert np.array_equal(per_site2, per_site) and abs(total2 - total) <= 1e-13 * abs(total)
+        chunks, end_ms = ctx.host_trace()
+        assert len(chunks) > 1 or opts.get("host_chunks") == 1
+        pos = 0
+        for first, width, copy_ms, done_ms in chunks:
+            assert first == pos and width > 0 and first % 1024 == 0 and 0 < copy_ms < done_ms <= end_ms
+            pos += width
+        assert pos == (nsites + 1023) // 1024 * 1024
+        total3, per_site3 = ctx.loglik_host(case.tips, per_site=True)      # byte per site through the same lanes
+        assert np.array_equal(per_site3, per_site) and abs(total3 - total) <= 1e-13 * abs(total)
+        total4 = ctx.loglik()
+        assert abs(total4 - total) <= 1e-13 * abs(total)
