@@ -234,6 +234,7 @@ struct pb_ctx {
 
     // work + outputs
     DevBuf<double> d_pool, d_site_cat, d_per_site, d_partials, d_total, d_site_weights;
+    DevBuf<int> d_site_exp;             // binary exponents beside d_site_cat (site_cat_raw)
     DevBuf<unsigned char> d_text, d_lut;
     bool have_site_weights = false;
     int64_t slot_stride = 0;
@@ -800,7 +801,7 @@ int launch_fused4_variant(pb_ctx* c, int64_t site0, int64_t site1)
     dim3 grid((unsigned)gx, c->ncat);
     kern<<<grid, BLOCK, smem, c->stream>>>(c->d_fprog.p, (int)c->fprog.size(), std::max(c->fstack, 1), c->d_P.p,
                                            c->d_is_leaf.p, c->nnodes, c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
-                                           c->shift_at_root, c->d_site_cat.p);
+                                           c->shift_at_root, c->d_site_cat.p, c->d_site_exp.p);
     c->launches++;
     return PB_OK;
 }
@@ -849,7 +850,7 @@ int launch_fused4c_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
         c->d_fprog_c.p, c->fprog_bank_nops, std::max(c->fstack, 1), c->d_P.p, c->d_leaf_nodes.p,
         (int)c->leaf_nodes.size(), c->nnodes, cat0, slot0, (int)c->inner_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles,
         c->d_pi.p, c->threshold, c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->ntab,
-        c->d_site_cat.p);
+        c->d_site_cat.p, c->d_site_exp.p);
     c->launches++;
     return PB_OK;
 }
@@ -1374,7 +1375,7 @@ int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
         cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
-        c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p,
+        c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p, c->d_site_exp.p,
         c->r_radix, (1u << c->r_tipbits) - 1u, c->d_mask_set.p);
     c->launches++;
     return PB_OK;
@@ -1826,6 +1827,7 @@ int run_pruning(pb_ctx* c)
     }
     const int path = path_of(c);
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    PB_CUDA(c, c->d_site_exp.ensure((size_t)c->ncat * c->spad));
     if ((path != PATH_FUSED4 || c->pack_dirty) && !c->have_masks) {
         const int rc = ensure_tip_bytes(c);
         if (rc != PB_OK) return rc;
@@ -1996,13 +1998,19 @@ int run_pruning(pb_ctx* c)
     return PB_OK;
 }
 
+// The 4-state site-resident kernels in power-of-two mode leave likelihoods as (value, binary exponent) pairs.
+const int* site_exp_of(const pb_ctx* c)
+{
+    return path_of(c) == PATH_FUSED4 && c->fused_pow2 && !c->fused_exact_log ? c->d_site_exp.p : nullptr;
+}
+
 int run_root_reduction(pb_ctx* c)
 {
     const int64_t blocks = (c->nsites + 255) / 256;
     PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
     PB_CUDA(c, c->d_partials.ensure((size_t)blocks));
     PB_CUDA(c, c->d_total.ensure(1));
-    pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, c->ncat, c->d_weights.p,
+    pbk::root_combine<<<(unsigned)blocks, 256, 0, c->stream>>>(c->d_site_cat.p, site_exp_of(c), c->ncat, c->d_weights.p,
                                                                c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
                                                                c->spad, 0, c->d_per_site.p, c->d_partials.p);
     c->launches++;
@@ -2120,7 +2128,7 @@ void pb_destroy(pb_ctx* c)
     c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
     c->d_tips.release(); c->d_masks.release(); c->d_pi.release(); c->d_rates.release(); c->d_weights.release();
     c->d_blen.release(); c->d_U.release(); c->d_lambda.release(); c->d_Uinv.release(); c->d_Q.release();
-    c->d_P.release(); c->d_pool.release(); c->d_site_cat.release(); c->d_per_site.release();
+    c->d_P.release(); c->d_pool.release(); c->d_site_cat.release(); c->d_site_exp.release(); c->d_per_site.release();
     c->d_partials.release(); c->d_total.release();
     delete c;
 }
@@ -2879,6 +2887,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     const int* d_xorder = reduced ? c->d_rxorder.p : nullptr;
     const int nslots = reduced ? (int)c->rorder.size() : (int)c->tip_order.size();
     PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    PB_CUDA(c, c->d_site_exp.ensure((size_t)c->ncat * c->spad));
     PB_CUDA(c, c->d_packed.ensure((size_t)(nwords + 2) * c->spad));
     PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
     PB_CUDA(c, c->d_partials.ensure((size_t)nblocks));
@@ -3008,7 +3017,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
         if (root_per_chunk && b1 > b0) {
             pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, lane>>>(
-                c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
+                c->d_site_cat.p, site_exp_of(c), c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
                 c->spad, b0, c->d_per_site.p, c->d_partials.p);
             c->launches++;
         }
@@ -3028,7 +3037,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         if ((rc = reduced ? launch_fused4t(c, 0, c->spad, false, lead_cats, c->ncat)
                           : launch_fused4c(c, 0, c->spad, false, lead_cats, c->ncat)) != PB_OK) return rc;
         pbk::root_combine<<<(unsigned)nblocks, 256, 0, c->stream>>>(
-            c->d_site_cat.p, c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
+            c->d_site_cat.p, site_exp_of(c), c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr, c->nsites,
             c->spad, 0, c->d_per_site.p, c->d_partials.p);
         c->launches++;
     }

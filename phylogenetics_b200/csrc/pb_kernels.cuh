@@ -13,6 +13,7 @@
 //   CLV    f64    slot -> [ncat][n+1][spad]   plane-per-state, site contiguous; plane n = carry
 //   site_cat f64  [ncat][spad]                log-likelihood of every (category, site)
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -595,7 +596,10 @@ __device__ __forceinline__ double block_sum_256(double x, double* red)
 
 // (at most 40 registers: its blocks run beside the three resident blocks of the pruning kernel on a side stream)
 __global__ void __launch_bounds__(256, 6)
-root_combine(const double* __restrict__ site_cat, int ncat, const double* __restrict__ weights,
+root_combine(const double* __restrict__ site_cat,
+             const int* __restrict__ site_exp,          // nullable: site_cat holds likelihoods as value x 2^site_exp (the
+                                                        // site-resident 4-state kernels in power-of-two mode), else logarithms
+             int ncat, const double* __restrict__ weights,
              const double* __restrict__ site_weights,   // nullable: multiplicity of every column (pattern compression)
              int64_t nsites, int64_t spad, int64_t block0, double* __restrict__ per_site,
              double* __restrict__ partials)
@@ -607,6 +611,28 @@ root_combine(const double* __restrict__ site_cat, int ncat, const double* __rest
     if (s < nsites) {
         if (site_cat[s] == INFINITY) {          // no observation at all in this column: 0. like the reference
             out = 0.0;
+        } else if (site_exp) {
+            // log(sum_c w_c v_c 2^e_c) with ONE logarithm: the terms are aligned to the largest exponent by exact
+            // multiplications by powers of two (a term more than 2^1022 below the largest contributes nothing)
+            constexpr double LN2 = 0.693147180559945309417232121458;
+            if (ncat == 1) {
+                out = (log(site_cat[s]) + (double)site_exp[s] * LN2) + log(weights[0]);
+            } else {
+                int emax = INT_MIN;
+                for (int c = 0; c < ncat; c++)
+                    if (site_cat[(int64_t)c * spad + s] > 0.0) emax = max(emax, site_exp[(int64_t)c * spad + s]);
+                if (emax == INT_MIN) {
+                    out = -INFINITY;
+                } else {
+                    double acc = 0.0;
+                    for (int c = 0; c < ncat; c++) {
+                        const int d = site_exp[(int64_t)c * spad + s] - emax;          // <= 0 for every positive term
+                        const double p2 = d >= -1022 ? __hiloint2double((1023 + min(d, 0)) << 20, 0) : 0.0;
+                        acc += weights[c] * (site_cat[(int64_t)c * spad + s] * p2);
+                    }
+                    out = log(acc) + (double)emax * LN2;
+                }
+            }
         } else if (ncat == 1) {
             // one category: log(w_0 L) (a single weight other than 1 is the same model as a 2-category mixture
             // whose other weight is 0; log(1.0) is exactly 0, so the reference's ncat = 1 case is untouched)

@@ -368,7 +368,7 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
        const double* __restrict__ P, const uint8_t* __restrict__ is_leaf, int nnodes,
        const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
        const double* __restrict__ pi, double thr, int shift_at_root,
-       double* __restrict__ site_cat)
+       double* __restrict__ site_cat, int* __restrict__ site_exp)
 {
     extern __shared__ double sh[];
     double* shP = sh;                                       // [nnodes][16] of this category
@@ -498,7 +498,13 @@ fused4(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
                     if (shift_at_root) shift4s(v[q], sc[q], thr);
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
-                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                    // power-of-two mode: the likelihood leaves as (value, binary exponent); the logarithm is taken once
+                    // per site, of the category mixture, by root_combine (no log here, no exp there)
+                    if (EXACT_LOG == SCALE_POW2) {
+                        site_cat[(int64_t)c * spad + s0 + q * BLOCK] = sum;
+                        site_exp[(int64_t)c * spad + s0 + q * BLOCK] = sc[q].e;
+                    } else
+                        site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
                 }
             }
             if (opw.x & FOP_PUSH_AFTER) {                     // also the stand-alone FOP_PUSH
@@ -674,7 +680,7 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
         const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
         const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab,
-        double* __restrict__ site_cat)
+        double* __restrict__ site_cat, int* __restrict__ site_exp)
 {
     extern __shared__ double sh[];
     double* shP = sh;                                       // [nleaf][16], transposed, of this category
@@ -826,7 +832,13 @@ fused4c(const FusedOp2* __restrict__ prog, int nops, int stack_depth,
                     for (int i = 0; i < 4; i++) v[q][i] = v[q][i] * pir[i];
                     if (shift_at_root) shift4s(v[q], sc[q], thr);
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
-                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
+                    // power-of-two mode: the likelihood leaves as (value, binary exponent); the logarithm is taken once
+                    // per site, of the category mixture, by root_combine (no log here, no exp there)
+                    if (EXACT_LOG == SCALE_POW2) {
+                        site_cat[(int64_t)c * spad + s0 + q * BLOCK] = sum;
+                        site_exp[(int64_t)c * spad + s0 + q * BLOCK] = sc[q].e;
+                    } else
+                        site_cat[(int64_t)c * spad + s0 + q * BLOCK] = log(sum) + sc[q].value();
                 }
             }
             if (opw.x & FOP_PUSH_AFTER) {
@@ -1057,7 +1069,7 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
         int cat0, int slot0, int nmat, const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
         const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat,
-        int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code)
+        int* __restrict__ site_exp, int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code)
 {
     extern __shared__ double sh[];
     double* shP = sh;                                       // loose tips' columns: [nleaf][16] transposed, or [nleaf][radix][4]
@@ -1269,7 +1281,9 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                     shift_pow2(v[q], sc[q], thr_hi, shift_at_root != 0);
                     const double sum = ((v[q][0] + v[q][1]) + v[q][2]) + v[q][3];
                     // a column without any observation: +inf here, 0 after root_combine (lib/phylo_ctmc.ml:172, :302)
-                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = (MASKS && nv[q]) ? INFINITY : log(sum) + sc[q].value();
+                    // (value, binary exponent): root_combine takes the one logarithm of the site, of the category mixture
+                    site_cat[(int64_t)c * spad + s0 + q * BLOCK] = (MASKS && nv[q]) ? INFINITY : sum;
+                    site_exp[(int64_t)c * spad + s0 + q * BLOCK] = sc[q].e;
                 }
             } break;
             default: break;
