@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <map>
 #include <vector>
 
 #include <cstdio>
@@ -254,6 +255,9 @@ struct pb_ctx {
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_start = nullptr;
     uint64_t pc_epoch = 1;              // compactions of the inner matrices (d_Pc) so far: what the constant bank was loaded from
+    std::map<const void*, size_t> smem_allowed;                // dynamic shared memory the kernels launched so far may use
+    std::map<std::pair<const void*, size_t>, int> occ_cache;   // resident blocks per SM of the kernels launched so far
+    int fused_fold = 1;                 // option "fused_fold": table exponents folded into the vectors (one gather per look-up)
     int fused_const_keep = 1;           // option "fused_const_keep": do not reload a constant bank that already holds these matrices
     int fused_split = 1;                // option "fused_split" (measurement hook): the resident evaluation in this many launches
     int fused_const_group = 1;          // option "fused_const_group": load the constant bank for several categories at once
@@ -1359,15 +1363,21 @@ int want_reduced(pb_ctx* c, bool* yes)
     return PB_OK;
 }
 
-template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
-int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
+template <int BLOCK, int SPT, int MINB, bool MASKS, bool FOLD>
+int launch_fused4t_build(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
 {
-    auto kern = pbk::fused4t<BLOCK, SPT, MINB, MASKS>;
+    auto kern = pbk::fused4t<BLOCK, SPT, MINB, MASKS, FOLD>;
     const size_t smem = fused4t_smem_for(c, BLOCK, SPT);
-    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
-    if (occ < 1) return fail(c, PB_ERR_CUDA, "fused4t: kernel does not fit on an SM");
+    size_t& allowed = c->smem_allowed[(const void*)kern];                      // (the attribute only ever grows)
+    if (smem > allowed) {
+        PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allowed = smem;
+    }
+    int& occ = c->occ_cache[std::make_pair((const void*)kern, smem)];          // (occupancy once per kernel and size)
+    if (occ == 0) {
+        PB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+        if (occ < 1) { occ = 0; return fail(c, PB_ERR_CUDA, "fused4t: kernel does not fit on an SM"); }
+    }
     c->fused4t_occ = occ;
     const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
     int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
@@ -1376,9 +1386,23 @@ int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
         (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
         cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
         c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p, c->d_site_exp.p,
-        c->r_radix, (1u << c->r_tipbits) - 1u, c->d_mask_set.p);
+        c->r_radix, (1u << c->r_tipbits) - 1u, c->d_mask_set.p,
+        c->rclades.empty() ? nullptr : c->d_cherry_k.p + (size_t)c->ncat * c->rntab);
     c->launches++;
     return PB_OK;
+}
+
+// With tables whose exponents may be folded into their vectors (option "fused_fold") the build without exponent
+// code is launched first and the general one behind it: the device-side flag of the table builder decides which of
+// the two does the work, the other returns at once.
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
+int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
+{
+    if (c->fused_fold && !c->rclades.empty()) {
+        const int rc = launch_fused4t_build<BLOCK, SPT, MINB, MASKS, true>(c, cat0, ncats, slot0, site0, site1);
+        if (rc != PB_OK) return rc;
+    }
+    return launch_fused4t_build<BLOCK, SPT, MINB, MASKS, false>(c, cat0, ncats, slot0, site0, site1);
 }
 
 int launch_fused4t_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slot0, int64_t site0, int64_t site1)
@@ -1442,7 +1466,9 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
     if (!c->rclades.empty() && (regather || c->tables_stale || c->tab_variant != 2)) {
         c->tab_variant = 2;
         PB_CUDA(c, c->d_cherry_v.ensure((size_t)c->ncat * c->rntab * 4));
-        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->rntab));
+        PB_CUDA(c, c->d_cherry_k.ensure((size_t)c->ncat * c->rntab + 1));      // (+ the flag of exponents that were not folded)
+        int* fold_flag = c->d_cherry_k.p + (size_t)c->ncat * c->rntab;
+        PB_CUDA(c, cudaMemsetAsync(fold_flag, c->fused_fold ? 0 : 0xff, sizeof(int), c->stream));
         int64_t emax = 1;
         for (const pbk::CladeTab& t : c->rclades) {
             int64_t e = 1;
@@ -1453,11 +1479,11 @@ int launch_fused4t(pb_ctx* c, int64_t site0, int64_t site1, bool regather, int c
         if (c->r_masked)
             pbk::build_clade_tables_masks<<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
                 c->d_cprog.p, c->d_rclades.p, c->d_P.p, c->nnodes, c->rntab, c->threshold, c->r_radix, c->d_mask_set.p,
-                c->d_cherry_v.p, c->d_cherry_k.p);
+                c->d_cherry_v.p, c->d_cherry_k.p, c->fused_fold ? fold_flag : nullptr);
         else
             pbk::build_clade_tables<true><<<dim3((unsigned)c->rclades.size(), c->ncat, gz), 256, 0, c->stream>>>(
                 c->d_cprog.p, c->d_rclades.p, c->d_P.p, nullptr, nullptr, c->nnodes, c->rntab, c->threshold,
-                c->d_cherry_v.p, c->d_cherry_k.p);
+                c->d_cherry_v.p, c->d_cherry_k.p, c->fused_fold ? fold_flag : nullptr);
         c->launches++;
         c->tables_stale = false;
     }
@@ -2930,7 +2956,15 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         const int64_t tail = c->host_tail_sites < 0 ? 0 : rounds(std::max<int64_t>(1, c->host_tail_sites / round));
         int64_t hi = c->spad;
         bounds.push_back(hi);
-        if (tail > 0 && hi > tail + rounds(1) / 2) bounds.push_back(hi -= tail);
+        // (the ramp down to the short last chunk: t, t, 2t, 4t, ... rounds while shorter than a regular chunk, so that
+        // every chunk is done by the time the one after it has arrived)
+        if (tail > 0) {
+            int64_t t = std::max<int64_t>(1, c->host_tail_sites / round);
+            for (int step = 0; t < per && hi > rounds(t) + rounds(1) / 2 && bounds.size() < 60; step++) {
+                bounds.push_back(hi -= rounds(t));
+                if (step >= 1) t *= 2;
+            }
+        }
         while (hi > rounds(per) + rounds(1) / 2 && bounds.size() < 63) bounds.push_back(hi -= rounds(per));
         bounds.push_back(0);
         std::reverse(bounds.begin(), bounds.end());
@@ -3306,6 +3340,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->host_lead_cats = iv;
     } else if (k == "graph") {
         c->use_graph = iv != 0;
+    } else if (k == "fused_fold") {
+        c->fused_fold = iv != 0;
+        c->tables_stale = true;
     } else if (k == "fused_const_keep") {
         c->fused_const_keep = iv != 0;
     } else if (k == "fused_split") {

@@ -615,20 +615,36 @@ root_combine(const double* __restrict__ site_cat,
             // log(sum_c w_c v_c 2^e_c) with ONE logarithm: the terms are aligned to the largest exponent by exact
             // multiplications by powers of two (a term more than 2^1022 below the largest contributes nothing)
             constexpr double LN2 = 0.693147180559945309417232121458;
+            // a likelihood is normalised first to mantissa in [1, 2) x 2^E — however the kernel split it into value
+            // and exponent (tables with folded exponents, rescaling at other nodes) the result is the same to the bit
+            auto norm = [&](int c, double& mant, int& E) {
+                const double x = site_cat[(int64_t)c * spad + s];
+                const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+                mant = x * __hiloint2double((1023 - max(ex, -1022)) << 20, 0);
+                E = site_exp[(int64_t)c * spad + s] + max(ex, -1022);
+                return x > 0.0;
+            };
             if (ncat == 1) {
-                out = (log(site_cat[s]) + (double)site_exp[s] * LN2) + log(weights[0]);
+                double mant;
+                int E;
+                out = norm(0, mant, E) ? (log(mant) + (double)E * LN2) + log(weights[0]) : -INFINITY;
             } else {
                 int emax = INT_MIN;
-                for (int c = 0; c < ncat; c++)
-                    if (site_cat[(int64_t)c * spad + s] > 0.0) emax = max(emax, site_exp[(int64_t)c * spad + s]);
+                for (int c = 0; c < ncat; c++) {
+                    double mant;
+                    int E;
+                    if (norm(c, mant, E)) emax = max(emax, E);
+                }
                 if (emax == INT_MIN) {
                     out = -INFINITY;
                 } else {
                     double acc = 0.0;
                     for (int c = 0; c < ncat; c++) {
-                        const int d = site_exp[(int64_t)c * spad + s] - emax;          // <= 0 for every positive term
-                        const double p2 = d >= -1022 ? __hiloint2double((1023 + min(d, 0)) << 20, 0) : 0.0;
-                        acc += weights[c] * (site_cat[(int64_t)c * spad + s] * p2);
+                        double mant;
+                        int E;
+                        if (!norm(c, mant, E)) continue;
+                        const int d = E - emax;                                            // <= 0
+                        acc += weights[c] * (mant * (d >= -1022 ? __hiloint2double((1023 + d) << 20, 0) : 0.0));
                     }
                     out = log(acc) + (double)emax * LN2;
                 }

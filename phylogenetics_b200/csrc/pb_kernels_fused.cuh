@@ -575,6 +575,23 @@ __device__ __forceinline__ void matvec4c(int off, const double (&x)[4], double (
 // rescalings, stack traffic) by ONE 32-byte look-up and an integer add (FOP_CHERRY).  The leaves of a clade are
 // consumed back to back, so the table index is one shift and mask of the packed-tip window.
 // One table per category, `ntab` entries of (4 doubles, 1 exponent); clade t owns entries [ent0, ent0 + 4^k).
+// fold_flag != nullptr (the reduced program's tables): an entry's scale exponent is folded into its vector — v 2^k, an
+// exact multiplication — whenever |k| <= 480, so that a look-up is ONE 32-byte gather instead of a gather of the vector
+// and a gather of the exponent from another cache line (the exponent gather costs the L1 as many wavefronts as the
+// vector's).  The consumer's rescaling rule restores the range; every factor is a power of two, so the likelihood is
+// the same number whichever way it is split into value and exponent (root_combine normalises the split).  An entry
+// that does not fit keeps (v, k) and raises *fold_flag: the kernel then gathers the exponents too.
+__device__ __forceinline__ void fold_exponent(double (&v)[4], int& k, int* fold_flag)
+{
+    if (!fold_flag || k == 0) return;
+    if (k >= -480 && k <= 480) {
+        const double f = __hiloint2double((1023 + k) << 20, 0);
+        v[0] *= f; v[1] *= f; v[2] *= f; v[3] *= f;
+        k = 0;
+    } else
+        atomicOr(fold_flag, 1);
+}
+
 struct CladeTab {
     int op0, op1;      // the clade's instructions in the untabulated program (inclusive)
     int sh0, k;        // bit offset of its first tip in the window, number of leaves
@@ -588,7 +605,7 @@ template <bool DIRECT>
 __global__ void __launch_bounds__(256)
 build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict__ tabs, const double* __restrict__ P,
                    const int* __restrict__ inner_nodes, const int* __restrict__ leaf_nodes, int nnodes, int ntab, double thr,
-                   double* __restrict__ tabV, int* __restrict__ tabK)
+                   double* __restrict__ tabV, int* __restrict__ tabK, int* __restrict__ fold_flag = nullptr)
 {
     const CladeTab tb = tabs[blockIdx.x];
     const int c = blockIdx.y;
@@ -665,6 +682,7 @@ build_clade_tables(const FusedOp2* __restrict__ prog, const CladeTab* __restrict
             for (int i = 0; i < 4; i++) v[i] = y[i];
         }
         const size_t e = (size_t)c * ntab + tb.ent0 + idx;
+        fold_exponent(v, sc.e, fold_flag);
 #pragma unroll
         for (int i = 0; i < 4; i++) tabV[e * 4 + i] = v[i];
         tabK[e] = sc.e;
@@ -879,13 +897,15 @@ constexpr int FOP_MUL_TAB = 15;        // ACC = shiftmul(ACC, T[offA][field A]) 
 // sh word of these instructions: shA | shB << 8 | bitsA << 16 | bitsB << 24  (a field is `bits` wide at bit `sh`
 // of the current window word; a tip is a 2-bit field)
 
+// (FOLD: every exponent of this evaluation's tables is folded into its vector, see fold_exponent)
+template <bool FOLD>
 __device__ __forceinline__ void tab_gather(const double* __restrict__ tv, const int* __restrict__ tk, int ent0,
                                            uint64_t cur, int sh, unsigned mask, double (&v)[4], int& e)
 {
     const unsigned idx = (unsigned)(cur >> sh) & mask;
     const double* p = tv + (size_t)(ent0 + idx) * 4;
     asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-    e = __ldg(tk + ent0 + idx);
+    e = FOLD ? 0 : __ldg(tk + ent0 + idx);
 }
 
 // ---- tip state SETS in the site-resident kernel (Missing_values / Ambiguous, lib/phylo_ctmc.ml:145-172, :232-302) ----
@@ -976,7 +996,7 @@ mask_alphabet(const uint64_t* __restrict__ masks, int64_t ld, int64_t nsites, in
 __global__ void __launch_bounds__(256)
 build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __restrict__ tabs, const double* __restrict__ P,
                          int nnodes, int ntab, double thr, int radix, const unsigned char* __restrict__ mask_of_code,
-                         double* __restrict__ tabV, int* __restrict__ tabK)
+                         double* __restrict__ tabV, int* __restrict__ tabK, int* __restrict__ fold_flag = nullptr)
 {
     const CladeTab tb = tabs[blockIdx.x];
     const int c = blockIdx.y;
@@ -1056,6 +1076,7 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
             v[0] = y[0]; v[1] = y[1]; v[2] = y[2]; v[3] = y[3];
         }
         const size_t e = (size_t)c * ntab + tb.ent0 + idx;
+        if (!nv) fold_exponent(v, sc.e, fold_flag);
         tabV[e * 4 + 0] = nv ? NONE_MARK : v[0];
         tabV[e * 4 + 1] = v[1]; tabV[e * 4 + 2] = v[2]; tabV[e * 4 + 3] = v[3];
         tabK[e] = nv ? 0 : sc.e;
@@ -1063,14 +1084,19 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
 }
 
 // tip_stride: doubles per loose tip in shared memory (16, or 4 * radix with MASKS); tip_mask: (1 << bits of a tip field) - 1
-template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
+// FOLD: the build for tables whose exponents are all folded into their vectors (no exponent gather, no exponent
+// arithmetic).  Whether they are is known on the device only (*fold_flag, written by the table builder just before), so
+// the host launches both builds and the one that does not apply returns at once.
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false, bool FOLD = false>
 __global__ void __launch_bounds__(BLOCK, MINB ? MINB : (BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1)))
 fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
         int cat0, int slot0, int nmat, const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
         const double* __restrict__ pi, double thr, int shift_at_root,
         const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat,
-        int* __restrict__ site_exp, int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code)
+        int* __restrict__ site_exp, int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code,
+        const int* __restrict__ fold_flag)
 {
+    if (fold_flag && (*fold_flag == 0) != FOLD) return;     // (uniform over the grid: the other build runs)
     extern __shared__ double sh[];
     double* shP = sh;                                       // loose tips' columns: [nleaf][16] transposed, or [nleaf][radix][4]
     const int tip_stride = MASKS ? 4 * radix : 16;
@@ -1135,7 +1161,7 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 double b[SPT][4];
                 int eb[SPT];
 #pragma unroll
-                for (int q = 0; q < SPT; q++) tab_gather(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
+                for (int q = 0; q < SPT; q++) tab_gather<FOLD>(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
@@ -1160,8 +1186,8 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 int ea[SPT], eb[SPT];
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
-                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);      // (operand A straight into the accumulator)
-                    tab_gather(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
+                    tab_gather<FOLD>(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);      // (operand A straight into the accumulator)
+                    tab_gather<FOLD>(tv, tk, offB, cur[q], shB, mB, b[q], eb[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
@@ -1187,7 +1213,7 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
             case FOP_TAB_TIP: {
                 int ea[SPT];
 #pragma unroll
-                for (int q = 0; q < SPT; q++) tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);
+                for (int q = 0; q < SPT; q++) tab_gather<FOLD>(tv, tk, offA, cur[q], shA, mA, v[q], ea[q]);
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     double t[4];
@@ -1209,7 +1235,7 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
 #pragma unroll
                 for (int q = 0; q < SPT; q++) {
                     int ea;
-                    tab_gather(tv, tk, offA, cur[q], shA, mA, v[q], ea);
+                    tab_gather<FOLD>(tv, tk, offA, cur[q], shA, mA, v[q], ea);
                     nv[q] = is_none<MASKS>(v[q]);
                     sc[q].e += ea;
                 }
@@ -1219,7 +1245,7 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
                 for (int q = 0; q < SPT; q++) {
                     double a[4], w[4] = {v[q][0], v[q][1], v[q][2], v[q][3]};
                     int ea;
-                    tab_gather(tv, tk, offA, cur[q], shA, mA, a, ea);
+                    tab_gather<FOLD>(tv, tk, offA, cur[q], shA, mA, a, ea);
                     const bool on = combine4<MASKS>(v[q], nv[q], w, nv[q], a, is_none<MASKS>(a));
                     sc[q].e += ea;
                     shift_pow2(v[q], sc[q], thr_hi, on);

@@ -7,13 +7,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import cases
 from oracle import c_oracle as C
-from phylogenetics_b200.engine import LikelihoodContext, pack_tips2
+from phylogenetics_b200.engine import LikelihoodContext, pack_tips2, pinned_near_device
 
 nsites = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
-tips = torch.from_numpy(case.tips).pin_memory()
-packed = torch.from_numpy(pack_tips2(case.tips)).pin_memory()
+tips = pinned_near_device(case.tips, 0)
+packed = pinned_near_device(pack_tips2(case.tips), 0)
 rec = {"lib": os.environ.get("PHYLO_B200_LIB", "default"), "nsites": nsites}
 with LikelihoodContext(4, nsites, f.nleaves, ncat=4) as ctx:
     ctx.set_tree(f, case.bl); ctx.set_categories(case.rates, case.weights)

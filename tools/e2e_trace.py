@@ -6,12 +6,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import cases
-from phylogenetics_b200.engine import LikelihoodContext, pack_tips2
+from phylogenetics_b200.engine import LikelihoodContext, pack_tips2, pinned_near_device
 
 nsites = int(os.environ.get("NSITES", 1_000_000))
 case = cases.make_case("c2", "gtr", 128, nsites, ncat=4, seed=100)
 f = case.flat
-packed = torch.from_numpy(pack_tips2(case.tips)).pin_memory()
+packed = pinned_near_device(pack_tips2(case.tips), 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 optsets = sys.argv[1:] or [""]
 # a plain copy of the same bytes for reference: one flat cudaMemcpyAsync and the library's 2-D form
