@@ -216,7 +216,10 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   with two leaf children), "fused_clade_leaves" (2..8, default 7: the largest clade whose 4^k
  *   possible values are tabulated the same way; fewer when the alignment has fewer than 8 * 4^k sites unless
  *   "fused_clade_force"), "fused_triple" (0: cherries only), "fused_reduced" (1 (default): the program over the reduced tree, kernel fused4t;
- *   0: look-ups inside the full program, kernel fused4c).
+ *   0: look-ups inside the full program, kernel fused4c), "fused_fold" (1 (default): the reduced program's table entries
+ *   carry their scale exponent inside the vector, one gather per look-up), "fused_const_keep" (1 (default): a constant
+ *   bank that already holds these matrices is not reloaded), "fused_split" (measurement hook: the resident evaluation
+ *   in this many launches).
  * 4 states, level-scheduled: "level4_async" (cp.async-pipelined kernel), "level4_waves",
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
@@ -225,10 +228,13 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   (default): at 20 states a cherry joined by a leaf is a table of N^3 entries), "fused_dmma_slots" (cap on the matrix ring),
  *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
  *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
- * "graph": see pb_graph_replays.  "host_chunks": column chunks of pb_loglik_host (cut where a round of the persistent
- *   blocks ends unless "host_chunk_align" is 0); "host_lead_cats": rate categories pruned chunk by chunk
- *   behind a 2-bit packed copy (the others run once over all the sites); "fused_const_group" (1 (default): the
- *   constant bank is loaded for as many categories as it holds).  Unknown names are PB_ERR_INVALID_ARG. */
+ * "graph": see pb_graph_replays.  "host_chunks" (default 6): column chunks of pb_loglik_host*, whole rounds of the
+ *   persistent blocks laid from the end of the alignment unless "host_chunk_align" is 0; "host_tail_sites": sites of
+ *   the short last chunk the schedule ramps down to (0 (default): one round; -1: none); "host_side_streams" (1
+ *   (default): chunks alternate between two streams; 0: everything on the context's stream); "host_lead_cats": rate
+ *   categories pruned chunk by chunk behind a 2-bit packed copy (default: all; the others run once over all the
+ *   sites); "host_trace": see pb_debug_host_trace; "fused_const_group" (1 (default): the constant bank is loaded for
+ *   as many categories as it holds).  Unknown names are PB_ERR_INVALID_ARG. */
 int pb_set_option(pb_ctx *ctx, const char *name, double value);
 
 /* Device timing of the phases of an evaluation, measured with CUDA events on the
@@ -359,8 +365,10 @@ int pb_debug_reduced_program(int nnodes, int root, const int32_t *child_ptr, con
  * delivers them), tables, stack depth, inner branches, leaf branches, stack depth and matrices of the untabulated
  * program}; an instruction is 4 ints {code, A, B, rowA | rowB << 16}: A / B are compact indices into inner_nodes
  * (matrices), leaf_nodes (tip columns) or table numbers, by operand kind; tabs[t] = {first entry, tip row A, tip row
- * B, 0} (entry = state A * nstates + state B); tab_nodes[t] = {leaf A node, leaf B node, cherry node or -1 at the
- * root, 0}: the table holds P[cherry] . (column of P[leaf A] * column of P[leaf B]), rescaled. */
+ * B, tip row C or -1} (entry = (state A * nstates + state B) [* nstates + state C]); tab_nodes[t] (8 ints) = {leaf A
+ * node, leaf B node, cherry node, leaf C node or -1, top node (the cherry, or its parent when leaf C joins it), 1 if
+ * top is the root, 0, 0}: the table holds P[top] . v (v alone at the root), v = column of P[leaf A] * column of
+ * P[leaf B], or (P[cherry] . that) * column of P[leaf C] for a three-leaf clade (20 states), rescaled. */
 int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t *child_ptr, const int32_t *child_idx,
                                    const int32_t *tip_row, int ntaxa, int nstates, int32_t *counts, int32_t *ops,
                                    int cap_ops, int32_t *mlist, int cap_mlist, int32_t *tabs, int32_t *tab_nodes,
