@@ -1363,10 +1363,10 @@ int want_reduced(pb_ctx* c, bool* yes)
     return PB_OK;
 }
 
-template <int BLOCK, int SPT, int MINB, bool MASKS, bool FOLD>
-int launch_fused4t_build(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
+int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
 {
-    auto kern = pbk::fused4t<BLOCK, SPT, MINB, MASKS, FOLD>;
+    auto kern = pbk::fused4t<BLOCK, SPT, MINB, MASKS>;
     const size_t smem = fused4t_smem_for(c, BLOCK, SPT);
     size_t& allowed = c->smem_allowed[(const void*)kern];                      // (the attribute only ever grows)
     if (smem > allowed) {
@@ -1382,6 +1382,8 @@ int launch_fused4t_build(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site
     const int64_t tile0 = site0 / (BLOCK * SPT), ntiles = (site1 - site0) / (BLOCK * SPT);
     int64_t gx = ((int64_t)c->sm_count * occ + ncats - 1) / ncats;
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
+    // (the device-side flag of the table builder decides between the kernel's two bodies: exponents folded into the
+    // table vectors, or gathered beside them; no tables or option "fused_fold" off: the general body)
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
         cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
@@ -1390,19 +1392,6 @@ int launch_fused4t_build(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site
         c->rclades.empty() ? nullptr : c->d_cherry_k.p + (size_t)c->ncat * c->rntab);
     c->launches++;
     return PB_OK;
-}
-
-// With tables whose exponents may be folded into their vectors (option "fused_fold") the build without exponent
-// code is launched first and the general one behind it: the device-side flag of the table builder decides which of
-// the two does the work, the other returns at once.
-template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
-int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
-{
-    if (c->fused_fold && !c->rclades.empty()) {
-        const int rc = launch_fused4t_build<BLOCK, SPT, MINB, MASKS, true>(c, cat0, ncats, slot0, site0, site1);
-        if (rc != PB_OK) return rc;
-    }
-    return launch_fused4t_build<BLOCK, SPT, MINB, MASKS, false>(c, cat0, ncats, slot0, site0, site1);
 }
 
 int launch_fused4t_shape(pb_ctx* c, int block, int spt, int cat0, int k, int slot0, int64_t site0, int64_t site1)

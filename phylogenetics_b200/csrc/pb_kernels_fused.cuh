@@ -1084,19 +1084,23 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
 }
 
 // tip_stride: doubles per loose tip in shared memory (16, or 4 * radix with MASKS); tip_mask: (1 << bits of a tip field) - 1
-// FOLD: the build for tables whose exponents are all folded into their vectors (no exponent gather, no exponent
-// arithmetic).  Whether they are is known on the device only (*fold_flag, written by the table builder just before), so
-// the host launches both builds and the one that does not apply returns at once.
-template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false, bool FOLD = false>
-__global__ void __launch_bounds__(BLOCK, MINB ? MINB : (BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1)))
-fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __restrict__ leaf_nodes, int nleaf, int nnodes,
-        int cat0, int slot0, int nmat, const uint64_t* __restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,
-        const double* __restrict__ pi, double thr, int shift_at_root,
-        const double* __restrict__ tabV, const int* __restrict__ tabK, int ntab, double* __restrict__ site_cat,
-        int* __restrict__ site_exp, int radix, unsigned tip_mask, const unsigned char* __restrict__ mask_of_code,
-        const int* __restrict__ fold_flag)
+// FOLD: the body for tables whose exponents are all folded into their vectors (no exponent gather, no exponent
+// arithmetic).  Whether they are is known on the device only (*fold_flag, written by the table builder just before):
+// the kernel reads the flag and runs the FOLD body inline, or calls the general body (a separate function, so that
+// the common path keeps its own register allocation).
+#define FUSED4T_PARAMS                                                                                                      \
+    int nops, int stack_depth, const double *__restrict__ P, const int *__restrict__ leaf_nodes, int nleaf, int nnodes,    \
+        int cat0, int slot0, int nmat, const uint64_t *__restrict__ packed, int64_t spad, int64_t tile0, int64_t ntiles,    \
+        const double *__restrict__ pi, double thr, int shift_at_root, const double *__restrict__ tabV,                     \
+        const int *__restrict__ tabK, int ntab, double *__restrict__ site_cat, int *__restrict__ site_exp, int radix,      \
+        unsigned tip_mask, const unsigned char *__restrict__ mask_of_code
+#define FUSED4T_ARGS                                                                                                        \
+    nops, stack_depth, P, leaf_nodes, nleaf, nnodes, cat0, slot0, nmat, packed, spad, tile0, ntiles, pi, thr, shift_at_root, \
+        tabV, tabK, ntab, site_cat, site_exp, radix, tip_mask, mask_of_code
+
+template <int BLOCK, int SPT, bool MASKS, bool FOLD>
+__device__ __forceinline__ void fused4t_body(FUSED4T_PARAMS)
 {
-    if (fold_flag && (*fold_flag == 0) != FOLD) return;     // (uniform over the grid: the other build runs)
     extern __shared__ double sh[];
     double* shP = sh;                                       // loose tips' columns: [nleaf][16] transposed, or [nleaf][radix][4]
     const int tip_stride = MASKS ? 4 * radix : 16;
@@ -1325,6 +1329,22 @@ fused4t(int nops, int stack_depth, const double* __restrict__ P, const int* __re
             }
         }
     }
+}
+
+template <int BLOCK, int SPT, bool MASKS>
+__device__ __noinline__ void fused4t_general(FUSED4T_PARAMS)
+{
+    fused4t_body<BLOCK, SPT, MASKS, false>(FUSED4T_ARGS);
+}
+
+template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
+__global__ void __launch_bounds__(BLOCK, MINB ? MINB : (BLOCK == 256 ? (SPT <= 2 ? 3 : 2) : (BLOCK == 128 ? (SPT <= 2 ? 6 : 4) : 1)))
+fused4t(FUSED4T_PARAMS, const int* __restrict__ fold_flag)
+{
+    if (fold_flag && *fold_flag == 0)       // (uniform over the grid)
+        fused4t_body<BLOCK, SPT, MASKS, true>(FUSED4T_ARGS);
+    else
+        fused4t_general<BLOCK, SPT, MASKS>(FUSED4T_ARGS);
 }
 
 }  // namespace pbk

@@ -704,3 +704,42 @@ def test_timing_ring_keeps_queued_evaluations():
         with pytest.raises(_lib.PhyloB200InvalidArgument):
             ctx.get_timing(64)
         assert ctx.get_timing() == times[0]
+
+
+@pytest.mark.parametrize("masked,every_category", [(False, False), (False, True), (True, True)])
+def test_table_exponents_that_do_not_fold(masked, every_category):
+    """Table entries whose scale exponent cannot be folded into the vector (|k| > 480: here leaf branches whose
+    off-diagonal transition probabilities are 1e-70, so a clade of mismatching leaves is rescaled by 2^-232 several
+    times): the table builder raises its device-side flag and the general build of fused4t (vector AND exponent
+    gathers) does the work instead of the FOLD build.  Against the oracle, and bit for bit against the evaluation with
+    folding switched off and against the untabulated kernels; also through the (value, exponent) root reduction with
+    categories whose exponents are thousands apart."""
+    case = cases.make_case("nofold", "gtr", 48, 6000, ncat=3, seed=21)
+    P = case.host_P()
+    f = case.flat
+    eps = np.full((4, 4), 1e-70)
+    np.fill_diagonal(eps, 1.0)
+    for v in range(f.nnodes):
+        if f.child_ptr[v] == f.child_ptr[v + 1]:            # every leaf branch (of every category but the last: that one
+            P[:None if every_category else -1, v] = eps      # then carries the mixture, thousands of binary orders above)
+    masks = None
+    if masked:
+        rng = np.random.default_rng(5)
+        masks = np.uint64(1) << case.tips.astype(np.uint64)
+        masks[rng.random(masks.shape) < 0.1] = 0
+    expect = C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi,
+                       tips=None if masked else case.tips, masks=masks, weights=case.weights, threshold=1e-6, root_mode=1)
+    assert not every_category or expect.min() < -400.0      # (the point of the case: likelihoods far below 2^-480)
+    with run_ctx(case, "direct", P=P) as ctx:
+        if masked:
+            ctx.set_tip_masks(masks)
+        ctx.set_option("fused_clade_force", 1)
+        assert ctx.path_name == "fused4"
+        total, per_site = ctx.loglik(per_site=True)
+        check(per_site, total, expect)
+        for name, value in (("fused_fold", 0), ("fused_clade_leaves", 3), ("fused_fold", 1)) + \
+                           ((() if masked else (("fused_reduced", 0), ("fused_const", 0)))):
+            ctx.set_option(name, value)
+            t2, p2 = ctx.loglik(per_site=True)
+            assert ctx.path_name == "fused4"
+            assert t2 == total and np.array_equal(p2, per_site), (name, value)
