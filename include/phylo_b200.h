@@ -380,6 +380,13 @@ int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t *child_pt
  * enqueue, from CUDA events.  cap >= 2 + 4K doubles. */
 int pb_debug_host_trace(pb_ctx *ctx, double *out, int cap);
 
+/* Host-only: the column-chunk schedule of a pipelined host evaluation over `spad` site columns (a multiple of 1024) —
+ * options "host_chunks", "host_tail_sites", and the sites one round of the persistent pruning blocks covers (0: the
+ * unaligned schedule of option "host_chunk_align" = 0).  bounds[0] = 0 < ... < bounds[*nbounds - 1] = spad, every bound
+ * a multiple of 1024, at most 65 of them.  tests/test_abi_cpu.py checks the invariants. */
+int pb_debug_host_schedule(int64_t spad, int host_chunks, int64_t host_tail_sites, int64_t round_sites, int64_t *bounds,
+                           int cap, int *nbounds);
+
 const char *pb_version(void);
 
 #ifdef __cplusplus

@@ -1760,7 +1760,8 @@ int launch_fused_dmma_path(pb_ctx* c)
         if (red) {
             const size_t entries = (size_t)c->ncat * c->dtab_entries;
             PB_CUDA(c, c->d_dtabV.ensure(entries * ((n + 7) / 8 * 8)));
-            PB_CUDA(c, c->d_dtabK.ensure(entries));
+            PB_CUDA(c, c->d_dtabK.ensure(entries + 1));                 // (+ the flag "an exponent was not folded")
+            PB_CUDA(c, cudaMemsetAsync(c->d_dtabK.p + entries, (c->fused_fold && c->fused_pow2) ? 0 : 0xff, sizeof(int), c->stream));
             pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->dtab_entries,
                                               c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream);
             c->launches++;
@@ -2857,6 +2858,51 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
     return PB_OK;
 }
 
+// Column bounds of the chunks of a pipelined host evaluation over `spad` (a multiple of 1024) site columns.
+// round > 0: the sites one ROUND of the persistent pruning blocks covers.  A launch costs whole rounds, so chunks are
+// whole rounds (cut down to the 1024 sites = 256 packed bytes the copies are aligned to), and what the pipeline cannot
+// hide is the work behind the LAST copy, so the schedule is laid from the end: a ramp of short last chunks (t, t, 2t,
+// 4t, ... rounds, t = tail_sites in rounds, at least one; tail_sites < 0: no ramp) while shorter than a regular chunk,
+// regular chunks of about spad / chunks before it, what is left over first.  round == 0: `chunks` equal chunks.
+// At most 64 chunks either way.
+static std::vector<int64_t> host_chunk_bounds(int64_t spad, int chunks, int64_t tail_sites, int64_t round)
+{
+    std::vector<int64_t> bounds;
+    chunks = std::max(1, std::min(chunks, 64));
+    if (round > 0) {
+        auto rounds = [&](int64_t r) { return std::max<int64_t>(1024, r * round / 1024 * 1024); };
+        const int64_t per = std::max<int64_t>(1, (spad / chunks + round / 2) / round);
+        int64_t hi = spad;
+        bounds.push_back(hi);
+        if (tail_sites >= 0) {
+            int64_t t = std::max<int64_t>(1, tail_sites / round);
+            for (int step = 0; t < per && hi > rounds(t) + rounds(1) / 2 && bounds.size() < 60; step++) {
+                bounds.push_back(hi -= rounds(t));
+                if (step >= 1) t *= 2;
+            }
+        }
+        while (hi > rounds(per) + rounds(1) / 2 && bounds.size() < 64) bounds.push_back(hi -= rounds(per));
+        bounds.push_back(0);
+        std::reverse(bounds.begin(), bounds.end());
+    } else {
+        const int64_t chunk = round_up((spad + chunks - 1) / chunks, 1024);
+        for (int64_t s0 = 0; s0 < spad; s0 += chunk) bounds.push_back(s0);
+        bounds.push_back(spad);
+    }
+    return bounds;
+}
+
+int pb_debug_host_schedule(int64_t spad, int host_chunks, int64_t host_tail_sites, int64_t round_sites, int64_t* bounds,
+                           int cap, int* nbounds)
+{
+    if (spad < 1024 || spad % 1024 || host_chunks < 1 || round_sites < 0 || !bounds || !nbounds) return PB_ERR_INVALID_ARG;
+    const std::vector<int64_t> b = host_chunk_bounds(spad, host_chunks, host_tail_sites, round_sites);
+    if ((int)b.size() > cap) return PB_ERR_INVALID_ARG;
+    std::copy(b.begin(), b.end(), bounds);
+    *nbounds = (int)b.size();
+    return PB_OK;
+}
+
 static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool packed2, double* total, double* per_site,
                             bool fetch = true)
 {
@@ -2933,35 +2979,15 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     // fb x fq sites), so chunks are whole rounds (cut to the 1024 sites = 256 packed bytes the copies are aligned to).
     // What the pipeline cannot hide is the work behind the LAST copy: the schedule is laid from the end — a short
     // last chunk (option "host_tail_sites"; default one round), regular chunks before it, what is left over first.
-    std::vector<int64_t> bounds;
+    int64_t round_sites = 0;
     if (reduced && c->host_chunk_align) {
         int fb = 0, fq = 0;
         fused4t_shape(c, &fb, &fq);
         const int cats_per_launch = fused4t_cats_per_launch(c, first_cat_only ? lead_cats : c->ncat);
         const int64_t blocks_x = std::max<int64_t>(1, ((int64_t)c->sm_count * std::max(c->fused4t_occ, 1) + cats_per_launch - 1) / cats_per_launch);
-        const int64_t round = blocks_x * fb * fq;                                  // sites of one round
-        auto rounds = [&](int64_t r) { return std::max<int64_t>(1024, r * round / 1024 * 1024); };
-        const int64_t per = std::max<int64_t>(1, (c->spad / c->host_chunks + round / 2) / round);
-        const int64_t tail = c->host_tail_sites < 0 ? 0 : rounds(std::max<int64_t>(1, c->host_tail_sites / round));
-        int64_t hi = c->spad;
-        bounds.push_back(hi);
-        // (the ramp down to the short last chunk: t, t, 2t, 4t, ... rounds while shorter than a regular chunk, so that
-        // every chunk is done by the time the one after it has arrived)
-        if (tail > 0) {
-            int64_t t = std::max<int64_t>(1, c->host_tail_sites / round);
-            for (int step = 0; t < per && hi > rounds(t) + rounds(1) / 2 && bounds.size() < 60; step++) {
-                bounds.push_back(hi -= rounds(t));
-                if (step >= 1) t *= 2;
-            }
-        }
-        while (hi > rounds(per) + rounds(1) / 2 && bounds.size() < 63) bounds.push_back(hi -= rounds(per));
-        bounds.push_back(0);
-        std::reverse(bounds.begin(), bounds.end());
-    } else {
-        const int64_t chunk = round_up((c->spad + c->host_chunks - 1) / c->host_chunks, 1024);
-        for (int64_t s0 = 0; s0 < c->spad; s0 += chunk) bounds.push_back(s0);
-        bounds.push_back(c->spad);
+        round_sites = blocks_x * fb * fq;
     }
+    const std::vector<int64_t> bounds = host_chunk_bounds(c->spad, c->host_chunks, c->host_tail_sites, round_sites);
     const int nchunks = (int)bounds.size() - 1;
     auto grow = [&](std::vector<cudaEvent_t>& v) -> cudaError_t {
         while ((int)v.size() < nchunks) {

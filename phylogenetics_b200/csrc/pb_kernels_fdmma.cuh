@@ -781,9 +781,12 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+#ifndef FD3_NW20
+#define FD3_NW20 23   // compute warps per CTA at 20 states (see Fd3Shape::NW)
+#endif
 template <int N>
 struct Fd3Shape {
-    static constexpr int NW = (N <= 32) ? 23 : 15;              // compute warps per CTA (+1 producer warp): 768 threads x 80 registers at 20 states (measured: 15 warps 1.02 ms, 23 0.915, 31 0.908 at c3), 512 x 128 at 61
+    static constexpr int NW = (N <= 32) ? FD3_NW20 : 15;              // compute warps per CTA (+1 producer warp): 768 threads x 80 registers at 20 states (measured: 15 warps 1.02 ms, 23 0.915, 31 0.908 at c3 in round 1; with cherry tables 23 warps 0.575 ms, 27 warps x 72 registers 0.576: -DFD3_NW20=27, profiles/r03a_sweep_dense_nw27_fold.jsonl), 512 x 128 at 61
     static constexpr int M8 = (N + 7) / 8;                      // 8-row tiles of parent states (20: 3, 61: 8)
     static constexpr int K4 = (N + 3) / 4;                      // k-steps of 4 child states (20: 5, 61: 16)
     static constexpr int KP2 = (K4 + 1) / 2;                    // pairs of k-steps (20: 3, 61: 8)
@@ -958,6 +961,8 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
     }
     const int thr_hi = __double2hiint(thr);
     const size_t base = (size_t)c * tab_entries + (size_t)tabs[t].x;
+    int* fold_flag = tabK + (size_t)gridDim.y * tab_entries;
+    const bool fold = *reinterpret_cast<volatile int*>(fold_flag) == 0;    // (a mix of folded and unfolded entries is valid)
     double* sv = svs + grp * 64;
     int* red = reds + grp * 4;
     auto shift_group = [&](double v, int& d_out) {       // SV.shift over the group's N values, power-of-two form; barrier inside
@@ -1009,8 +1014,17 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
             y = (y0 + y1) + (y2 + y3);
         }
         // (scaling by a power of two commutes with every rounding above: f * (P . v) = P . (f * v) exactly)
+        // The entry's exponent k is folded into its vector when it is small (see fold_exponent, pb_kernels_fused.cuh):
+        // y f 2^k = y 2^(d1 - 1023), and the kernel then skips the exponent gathers.  tabK[ncat * tab_entries] is the
+        // flag "some exponent was not folded" (preset to non-zero when folding is switched off).
+        int k = (d - 1023) + (d1 - 1023);
+        if (fold && k >= -480) {
+            f = __hiloint2double(d1 << 20, 0);
+            k = 0;
+        } else if (fold && valid && l == 0)
+            atomicOr(fold_flag, 1);
         if (valid && l < F::MP8) tabV[(base + e) * F::MP8 + l] = (l < N) ? y * f : 0.0;
-        if (valid && l == 0) tabK[base + e] = (d - 1023) + (d1 - 1023);
+        if (valid && l == 0) tabK[base + e] = k;
         __syncthreads();
     }
 }
@@ -1152,14 +1166,16 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
         ib += d.x;
         ca = Tc + (size_t)ia * MP8 + g;
         cb = Tc + (size_t)ib * MP8 + g;
-        sc[0].e += Kc[ia];
-        sc[1].e += Kc[ib];
+        if (Kc) {                                          // (null: every exponent is folded into its vector)
+            sc[0].e += Kc[ia];
+            sc[1].e += Kc[ib];
+        }
     };
 
     for (int c = 0; c < ncat; c++) {
         const double* PTc = PTleaf + (size_t)c * nleaf * N * MP8;
         Tc = tabV + (size_t)c * tab_entries * MP8;
-        Kc = tabK + (size_t)c * tab_entries;
+        Kc = (tabK && tabK[(size_t)ncat * tab_entries] != 0) ? tabK + (size_t)c * tab_entries : nullptr;
         for (int r = 0; r < rounds; r++) {
             const int64_t unit = lo + (int64_t)r * NW + warp;
             if (unit >= hi) {                                // no sites left for this warp: keep the ring moving

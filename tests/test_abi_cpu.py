@@ -94,3 +94,42 @@ def test_host_eigensystem_helper_reconstructs_q():
     Qn = np.array([[-1., 1., 0., 0.], [0., -1., 1., 0.], [0., 0., -1., 1.], [1., 0., 0., -1.]])
     with pytest.raises(_lib.PhyloB200Error):
         host_reversible_eigensystem(Qn, np.full(4, 0.25))
+
+
+def test_host_chunk_schedule_invariants():
+    """pb_debug_host_schedule (host only): the column chunks of the pipelined host evaluation cover [0, spad) exactly
+    once in order, on 1024-site bounds, never more than 64 of them; with a round size they are whole rounds of the
+    persistent blocks laid from the end (a ramp of short last chunks), without one they are equal."""
+    import ctypes
+    import numpy as np
+
+    def schedule(spad, chunks, tail, rnd):
+        b = np.zeros(80, np.int64)
+        n = ctypes.c_int(0)
+        rc = _lib.lib.pb_debug_host_schedule(spad, chunks, tail, rnd, b.ctypes.data, len(b), ctypes.byref(n))
+        assert rc == 0, (spad, chunks, tail, rnd)
+        return b[:n.value]
+
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        spad = int(rng.integers(1, 4000)) * 1024
+        chunks = int(rng.integers(1, 65))
+        rnd = int(rng.choice([0, 512, 3 * 512, 111 * 512, 444 * 512, 148 * 1024, 7 * 4096]))
+        tail = int(rng.choice([-1, 0, 1000, 60000, 250000, 10**7]))
+        b = schedule(spad, chunks, tail, rnd)
+        assert b[0] == 0 and b[-1] == spad and np.all(np.diff(b) > 0) and np.all(b % 1024 == 0)
+        assert 2 <= len(b) <= 65
+        if rnd == 0:
+            w = np.diff(b)
+            assert len(w) <= chunks and np.all(w[:-1] == w[0]) and w[-1] <= w[0]
+    # the bench shape: 1M sites, 111 blocks of 512 sites per round (4 categories per launch), 6 chunks
+    b = schedule(1000448, 6, 0, 111 * 512)
+    w = np.diff(b)
+    per_round = 111 * 512
+    assert list(w[-3:] // 1024 * 1024) == [2 * per_round // 1024 * 1024, per_round // 1024 * 1024, per_round // 1024 * 1024]
+    assert np.all(w[1:-3] == 3 * per_round // 1024 * 1024) and w[0] <= 3 * per_round + per_round // 2
+    assert list(np.diff(schedule(1000448, 6, -1, 111 * 512))[1:]) == [3 * per_round // 1024 * 1024] * 5
+    for bad in ((1000, 4, 0, 0), (2048, 0, 0, 0), (2048, 4, 0, -5)):
+        n = ctypes.c_int(0)
+        out = np.zeros(80, np.int64)
+        assert _lib.lib.pb_debug_host_schedule(*bad, out.ctypes.data, 80, ctypes.byref(n)) != 0
