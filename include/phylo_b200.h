@@ -224,8 +224,8 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  *   "level4_min_blocks".
  * 20 / 61 states: "fused_dmma" (0: level-scheduled kernels), "fused_dmma_version" (3 = m8n8k4 tiles,
  *   2 = m16n8k8 tiles, 1 = CTA-synchronous), "fused_dmma_cherry" (1 (default): nodes with two leaf children are
- *   tables of N^2 entries carrying their branch matrix, version 3 with power-of-two rescaling), "fused_dmma_triple" (1
- *   (default): at 20 states a cherry joined by a leaf is a table of N^3 entries), "fused_dmma_slots" (cap on the matrix ring),
+ *   tables of N^2 entries carrying their branch matrix, version 3 with power-of-two rescaling), "fused_dmma_triple" (1:
+ *   at 20 states a cherry joined by a leaf is a table of N^3 entries; default 0), "fused_dmma_slots" (cap on the matrix ring),
  *   "fused_dmma_spill" (test hook: stack in L2), "dmma_version", "dmma_per_level",
  *   "dmma_group_tiles", "dense_scalar" (DFMA level kernel).
  * "graph": see pb_graph_replays.  "host_chunks" (default 6): column chunks of pb_loglik_host*, whole rounds of the
@@ -361,7 +361,8 @@ int pb_debug_reduced_program(int nnodes, int root, const int32_t *child_ptr, con
                              int32_t *clades, int cap_clades);
 
 /* The dense-alphabet (20 / 61 states) program over the tree whose cherries — nodes with two leaf children — are
- * tables (kernel fused_dmma3).  counts[8] = {instructions, matrices applied (in the order the kernel's matrix ring
+ * tables (kernel fused_dmma3); nstates | 0x100 also plans three-leaf clades (a cherry joined by a leaf, option
+ * "fused_dmma_triple", 20 states).  counts[8] = {instructions, matrices applied (in the order the kernel's matrix ring
  * delivers them), tables, stack depth, inner branches, leaf branches, stack depth and matrices of the untabulated
  * program}; an instruction is 4 ints {code, A, B, rowA | rowB << 16}: A / B are compact indices into inner_nodes
  * (matrices), leaf_nodes (tip columns) or table numbers, by operand kind; tabs[t] = {first entry, tip row A, tip row

@@ -200,7 +200,9 @@ struct pb_ctx {
     std::vector<pbk::DenseTabNodes> dtab_nodes;
     int64_t dtab_entries = 0;              // entries of all tables of one category
     bool dtab_three = false;               // some table is a three-leaf clade
-    int fused_dmma_triple = 1;             // option "fused_dmma_triple": clades of three leaves (cherry + leaf) as tables, 20 states
+    int fused_dmma_triple = 0;             // option "fused_dmma_triple": clades of three leaves (cherry + leaf) as tables, 20 states
+                                           // (off by default: with two CTAs per SM cherries alone are faster, 0.560 against 0.568 ms
+                                           // at c3, profiles/r03c_sweep_dense_2ctas.jsonl)
     int dstack_r = 0;
     bool dense_reduced_built = false;
     DevBuf<FusedOp2> d_dprog_r;
@@ -2651,7 +2653,8 @@ int pb_debug_dense_reduced_program(int nnodes, int root, const int32_t* child_pt
         return fail(nullptr, PB_ERR_INVALID_ARG, "pb_debug_dense_reduced_program: bad arguments");
     std::unique_ptr<pb_ctx> c(new pb_ctx());
     c->plan_only = true;
-    c->n = nstates;
+    c->n = nstates & 0xff;
+    c->fused_dmma_triple = (nstates & 0x100) != 0;          // (option "fused_dmma_triple")
     c->ncat = 1;
     c->ntaxa = ntaxa;
     c->nsites = 1;

@@ -782,11 +782,15 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
 }
 
 #ifndef FD3_NW20
-#define FD3_NW20 23   // compute warps per CTA at 20 states (see Fd3Shape::NW)
+#define FD3_NW20 11   // compute warps per CTA at 20 states (see Fd3Shape::NW)
+#endif
+#ifndef FD3_CTAS20
+#define FD3_CTAS20 2  // CTAs per SM at 20 states (see Fd3Shape::CTAS)
 #endif
 template <int N>
 struct Fd3Shape {
     static constexpr int NW = (N <= 32) ? FD3_NW20 : 15;              // compute warps per CTA (+1 producer warp): 768 threads x 80 registers at 20 states (measured: 15 warps 1.02 ms, 23 0.915, 31 0.908 at c3 in round 1; with cherry tables 23 warps 0.575 ms, 27 warps x 72 registers 0.576: -DFD3_NW20=27, profiles/r03a_sweep_dense_nw27_fold.jsonl), 512 x 128 at 61
+    static constexpr int CTAS = (N <= 32) ? FD3_CTAS20 : 1;     // CTAs per SM: two independent CTAs of 11 + 1 warps at 20 states (their rounds interleave)
     static constexpr int M8 = (N + 7) / 8;                      // 8-row tiles of parent states (20: 3, 61: 8)
     static constexpr int K4 = (N + 3) / 4;                      // k-steps of 4 child states (20: 5, 61: 16)
     static constexpr int KP2 = (K4 + 1) / 2;                    // pairs of k-steps (20: 3, 61: 8)
@@ -1030,7 +1034,7 @@ fdmma3_build_cherries(const double* __restrict__ P, int nnodes, const int4* __re
 }
 
 template <int N, int SCALING>
-__global__ void __launch_bounds__((Fd3Shape<N>::NW + 1) * 32, 1)
+__global__ void __launch_bounds__((Fd3Shape<N>::NW + 1) * 32, Fd3Shape<N>::CTAS)
 fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__ mlist, int nmat, int nslot, int stack_smem,
             double* __restrict__ gstack, int gdepth,
             const double* __restrict__ Apanel, const double* __restrict__ PTleaf, int ninner, int nleaf, int ncat,
@@ -1383,6 +1387,7 @@ bool fused_dmma3_plan_n(size_t smem_optin, int stack_depth, int ntaxa, int nops,
 {
     using F = Fd3Shape<N>;
     const int levels = stack_depth + 1;
+    smem_optin = smem_optin / F::CTAS - (F::CTAS > 1 ? 1024 : 0);        // (per CTA; 1 KB per resident CTA is the system's)
     if (F::fixed_bytes(F::NSLOT_MIN, ntaxa, nops, nmat) > smem_optin) return false;
     int ns = F::NSLOT_MAX;
     while (ns > F::NSLOT_MIN && F::fixed_bytes(ns, ntaxa, nops, nmat) + (size_t)levels * F::level_bytes > smem_optin) ns--;
@@ -1408,7 +1413,8 @@ inline size_t fused_dmma3_tilesz(int n) { return n == 20 ? Fd3Shape<20>::XSZ * F
 inline int fused_dmma3_grid(int n, int sm_count, int64_t spad)
 {
     const int nw = n == 20 ? Fd3Shape<20>::NW : Fd3Shape<61>::NW;
-    return (int)std::max<int64_t>(1, std::min<int64_t>((spad / 8 + nw - 1) / nw, sm_count));
+    const int ctas = n == 20 ? Fd3Shape<20>::CTAS : Fd3Shape<61>::CTAS;
+    return (int)std::max<int64_t>(1, std::min<int64_t>((spad / 8 + nw - 1) / nw, (int64_t)sm_count * ctas));
 }
 
 template <int N, int SCALING>

@@ -20,7 +20,7 @@ from test_fused_program_cpu import random_kary_tree
 PUSH_AFTER = 0x100
 
 
-def plan(flat, ntaxa, nstates):
+def plan(flat, ntaxa, nstates, triple=False):
     nn = flat.nnodes
     cap = 4 * nn + 16
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -31,7 +31,7 @@ def plan(flat, ntaxa, nstates):
     tabs, tab_nodes = np.zeros((nn, 4), np.int32), np.zeros((nn, 8), np.int32)
     inner, leaf = np.zeros(nn, np.int32), np.zeros(nn, np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = _lib.lib.pb_debug_dense_reduced_program(nn, int(flat.root), p(child_ptr), p(child_idx), p(tip_row), ntaxa, nstates,
+    rc = _lib.lib.pb_debug_dense_reduced_program(nn, int(flat.root), p(child_ptr), p(child_idx), p(tip_row), ntaxa, nstates | (0x100 if triple else 0),
                                                  p(counts), p(ops), cap, p(mlist), cap, p(tabs), p(tab_nodes), nn, p(inner), p(leaf))
     assert rc == 0, _lib.lib.pb_last_error(None)
     nops, nmat, ntab, stack, ninner, nleaf, stack_full, nmat_full = (int(x) for x in counts)
@@ -110,7 +110,16 @@ def run(pl, P, pi, tips, n):
 
 
 def check(flat, P, pi, tips, n):
-    pl = plan(flat, tips.shape[0], n)
+    """Both plans: cherries only (the default) and with three-leaf clades (option fused_dmma_triple, 20 states)."""
+    pl = check_plan(flat, P, pi, tips, n, False)
+    assert int((pl["tab_nodes"][:, 3] >= 0).sum()) == 0
+    pl3 = check_plan(flat, P, pi, tips, n, True)
+    assert n ** 3 <= 8000 or int((pl3["tab_nodes"][:, 3] >= 0).sum()) == 0
+    return pl
+
+
+def check_plan(flat, P, pi, tips, n, triple):
+    pl = plan(flat, tips.shape[0], n, triple)
     lik, applied = run(pl, P, pi, tips, n)
     assert applied == [int(m) for m in pl["mlist"]]          # the ring delivers exactly these matrices, in this order
     expect = C.pruning(n, flat.root, flat.child_ptr, flat.child_idx, flat.tip_row, P[None], pi, tips=tips)

@@ -265,11 +265,11 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
             check(per_site5, total5, expect)
             np.testing.assert_allclose(per_site5, per_site, rtol=1e-12)
             ctx.set_option("fused_dmma_cherry", 1)
-            ctx.set_option("fused_dmma_triple", 0)              # cherries only (no three-leaf clades at 20 states)
+            ctx.set_option("fused_dmma_triple", 1)              # three-leaf clades as tables too (20 states; off by default)
             total6, per_site6 = ctx.loglik(per_site=True)
             check(per_site6, total6, expect)
             np.testing.assert_allclose(per_site6, per_site, rtol=1e-12)
-            ctx.set_option("fused_dmma_triple", 1)
+            ctx.set_option("fused_dmma_triple", 0)
         ctx.set_option("fused_pow2", 0)                         # the reference's scale factor 1/max instead of 2^-k
         total4, per_site4 = ctx.loglik(per_site=True)
         check(per_site4, total4, expect)
