@@ -383,7 +383,8 @@ int pb_debug_host_trace(pb_ctx *ctx, double *out, int cap);
 
 /* Host-only: the column-chunk schedule of a pipelined host evaluation over `spad` site columns (a multiple of 1024) —
  * options "host_chunks", "host_tail_sites", and the sites one round of the persistent pruning blocks covers (0: the
- * unaligned schedule of option "host_chunk_align" = 0).  bounds[0] = 0 < ... < bounds[*nbounds - 1] = spad, every bound
+ * unaligned schedule of option "host_chunk_align" = 0); host_tail_sites = -2: the schedule of the dense alphabets'
+ * compute-bound pipeline, chunks of 1, 2, 4, ... rounds from the start.  bounds[0] = 0 < ... < bounds[*nbounds - 1] = spad, every bound
  * a multiple of 1024, at most 65 of them.  tests/test_abi_cpu.py checks the invariants. */
 int pb_debug_host_schedule(int64_t spad, int host_chunks, int64_t host_tail_sites, int64_t round_sites, int64_t *bounds,
                            int cap, int *nbounds);

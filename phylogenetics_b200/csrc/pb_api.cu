@@ -1720,8 +1720,12 @@ int build_dense_reduced_program(pb_ctx* c)
 }
 
 // Site-resident tensor-core path (20 / 61 states): pad the branch matrices, then one persistent launch.
-int launch_fused_dmma_path(pb_ctx* c)
+// site0 < site1: version 3 over that column range only (a chunk of a pipelined host evaluation); `prepare`: the
+// per-evaluation matrix panels and tables are (re)built first; prepare with an empty range builds them only.
+int launch_fused_dmma_path(pb_ctx* c, int64_t site0 = 0, int64_t site1 = -1, bool prepare = true)
 {
+    const bool whole = site1 < 0;
+    if (whole) { site0 = 0; site1 = c->spad; }
     const int n = c->n;
     const int ninner = (int)c->inner_nodes.size(), nleaf = (int)c->leaf_nodes.size();
     int ssm = 0, nslot = 0;
@@ -1747,34 +1751,42 @@ int launch_fused_dmma_path(pb_ctx* c)
             smem -= (size_t)(nslot - c->fused_dmma_slots) * pbk::fused_dmma3_panelsz(n) * sizeof(double);
             nslot = c->fused_dmma_slots;
         }
-        PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma3_matsz(n), 1)));
-        PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma3_leafsz(n), 1)));
-        pbk::launch_fdmma3_prepare(n, c->d_P.p, c->d_inner_nodes.p, ninner, c->d_leaf_nodes.p, nleaf, c->nnodes, c->ncat,
-                                   c->d_Ppad.p, c->d_PTleaf.p, c->stream);
-        c->launches++;
+        if (prepare) {
+            PB_CUDA(c, c->d_Ppad.ensure(std::max<size_t>((size_t)c->ncat * ninner * pbk::fused_dmma3_matsz(n), 1)));
+            PB_CUDA(c, c->d_PTleaf.ensure(std::max<size_t>((size_t)c->ncat * nleaf * pbk::fused_dmma3_leafsz(n), 1)));
+            pbk::launch_fdmma3_prepare(n, c->d_P.p, c->d_inner_nodes.p, ninner, c->d_leaf_nodes.p, nleaf, c->nnodes, c->ncat,
+                                       c->d_Ppad.p, c->d_PTleaf.p, c->stream);
+            c->launches++;
+        }
         const int grid = pbk::fused_dmma3_grid(n, c->sm_count, c->spad);
         const int gdepth = dstack + 1 - ssm;
         PB_CUDA(c, c->d_gstack.ensure(std::max<size_t>((size_t)grid * gdepth * pbk::fused_dmma3_tilesz(n), 1)));
         pbk::FusedDmmaArgs a{red ? c->d_dprog_r.p : c->d_fprog_d.p, nops_d, red ? c->d_mlist_r.p : c->d_mlist.p, nmat_d, ssm,
                              c->d_gstack.p, gdepth,
-                             c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p, c->spad, c->ntaxa, c->spad,
-                             c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p};
+                             c->d_Ppad.p, c->d_PTleaf.p, ninner, nleaf, c->ncat, c->d_tips.p + site0, c->spad, c->ntaxa,
+                             site1 - site0, c->d_pi.p, c->threshold, c->shift_at_root, c->d_site_cat.p + site0};
+        a.cat_stride = c->spad;
         if (red) {
             const size_t entries = (size_t)c->ncat * c->dtab_entries;
-            PB_CUDA(c, c->d_dtabV.ensure(entries * ((n + 7) / 8 * 8)));
-            PB_CUDA(c, c->d_dtabK.ensure(entries + 1));                 // (+ the flag "an exponent was not folded")
-            PB_CUDA(c, cudaMemsetAsync(c->d_dtabK.p + entries, (c->fused_fold && c->fused_pow2) ? 0 : 0xff, sizeof(int), c->stream));
-            pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->dtab_entries,
-                                              c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream);
-            c->launches++;
+            if (prepare) {
+                PB_CUDA(c, c->d_dtabV.ensure(entries * ((n + 7) / 8 * 8)));
+                PB_CUDA(c, c->d_dtabK.ensure(entries + 1));                 // (+ the flag "an exponent was not folded")
+                PB_CUDA(c, cudaMemsetAsync(c->d_dtabK.p + entries, (c->fused_fold && c->fused_pow2) ? 0 : 0xff, sizeof(int), c->stream));
+                pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->dtab_entries,
+                                                  c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream);
+                c->launches++;
+            }
             a.tabV = c->d_dtabV.p; a.tabK = c->d_dtabK.p; a.tabs = c->d_dtabs.p; a.ntab = ntab_d;
             a.tab_entries = c->dtab_entries;
         }
-        if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
-            return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
-        c->launches++;
+        if (site1 > site0) {
+            if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
+                return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
+            c->launches++;
+        }
         return PB_OK;
     }
+    if (!whole) return fail(c, PB_ERR_STATE, "column chunks need version 3 of the fused tensor-core kernel");
     if (c->fused_dmma_version == 2 &&
         pbk::fused_dmma2_plan(n, c->smem_optin, c->dstack, c->ntaxa, (int)c->fprog_d.size(), (int)c->mlist.size(), &nslot, &ssm, &smem)) {
         if (c->fused_dmma_spill) {                            // test hook: keep every stack level in the L2 scratch
@@ -2867,11 +2879,22 @@ int pb_loglik_fetch(pb_ctx* c, double* total, double* per_site)
 // hide is the work behind the LAST copy, so the schedule is laid from the end: a ramp of short last chunks (t, t, 2t,
 // 4t, ... rounds, t = tail_sites in rounds, at least one; tail_sites < 0: no ramp) while shorter than a regular chunk,
 // regular chunks of about spad / chunks before it, what is left over first.  round == 0: `chunks` equal chunks.
-// At most 64 chunks either way.
+// tail_sites == -2: the ramp-up schedule of a compute-bound pipeline (below).  At most 64 chunks in every case.
 static std::vector<int64_t> host_chunk_bounds(int64_t spad, int chunks, int64_t tail_sites, int64_t round)
 {
     std::vector<int64_t> bounds;
     chunks = std::max(1, std::min(chunks, 64));
+    if (round > 0 && tail_sites == -2) {
+        // The schedule of a COMPUTE-bound pipeline (the dense alphabets: the copy takes a fraction of the pruning time):
+        // what cannot be hidden is the FIRST copy, so the chunks grow from one round — 1, 2, 4, ... rounds; every copy
+        // is done long before the chunks ahead of it are pruned.
+        auto rounds = [&](int64_t r) { return std::max<int64_t>(1024, r * round / 1024 * 1024); };
+        int64_t lo = 0;
+        bounds.push_back(0);
+        for (int64_t t = 1; spad - lo > rounds(t) + rounds(t) / 2 && bounds.size() < 64; t *= 2) bounds.push_back(lo += rounds(t));
+        bounds.push_back(spad);
+        return bounds;
+    }
     if (round > 0) {
         auto rounds = [&](int64_t r) { return std::max<int64_t>(1024, r * round / 1024 * 1024); };
         const int64_t per = std::max<int64_t>(1, (spad / chunks + round / 2) / round);
@@ -2906,6 +2929,93 @@ int pb_debug_host_schedule(int64_t spad, int host_chunks, int64_t host_tail_site
     return PB_OK;
 }
 
+// The pipelined host evaluation of the dense alphabets (20 / 61 states, kernel fused_dmma3): the byte-per-site
+// alignment crosses PCIe in column chunks (whole rounds of the persistent CTAs, host_chunk_bounds) on the copy stream
+// while the chunks before it are pruned and reduced; matrix panels and cherry tables are built behind the first copy.
+// One compute stream: the kernel's spill area (d_gstack) belongs to one launch at a time.
+static int loglik_host_dense(pb_ctx* c, const uint8_t* states, int64_t ld, double* total, double* per_site, bool fetch)
+{
+    int rc = alloc_tips(c);
+    if (rc != PB_OK) return rc;
+    if (!c->copy_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_start) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    if ((rc = build_pmatrices(c)) != PB_OK) return rc;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    const int64_t nblocks = (c->nsites + 255) / 256;
+    PB_CUDA(c, c->d_site_cat.ensure((size_t)c->ncat * c->spad));
+    PB_CUDA(c, c->d_site_exp.ensure((size_t)c->ncat * c->spad));
+    PB_CUDA(c, c->d_per_site.ensure((size_t)c->spad));
+    PB_CUDA(c, c->d_partials.ensure((size_t)nblocks));
+    PB_CUDA(c, c->d_total.ensure(1));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->stream));
+    PB_CUDA(c, cudaEventRecord(c->ev_start, c->stream));          // earlier work may still read d_tips
+    PB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+    size_t tr = 0;                                                // option "host_trace": next timing event
+    auto trace = [&](cudaStream_t st) -> cudaError_t {
+        if (!c->host_trace) return cudaSuccess;
+        if (tr == c->trace_events.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            c->trace_events.push_back(e);
+        }
+        return cudaEventRecord(c->trace_events[tr++], st);
+    };
+    c->trace_sites.clear();
+    PB_CUDA(c, trace(c->stream));
+    const std::vector<int64_t> bounds = host_chunk_bounds(c->spad, c->host_chunks, c->host_chunk_align ? -2 : c->host_tail_sites,
+                                                          c->host_chunk_align ? pbk::fused_dmma3_round_sites(c->n, c->sm_count) : 0);
+    const int nchunks = (int)bounds.size() - 1;
+    while ((int)c->chunk_events.size() < nchunks) {
+        cudaEvent_t e;
+        PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    if ((rc = launch_fused_dmma_path(c, 0, 0, true)) != PB_OK) return rc;      // panels and tables, behind the first copy
+    for (int k = 0; k < nchunks; k++) {
+        const int64_t s0 = bounds[k], s1 = bounds[k + 1];
+        const int64_t w = std::min(s1, c->nsites) - s0;
+        if (w > 0)
+            PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p + s0, c->spad, states + s0, ld, w, c->ntaxa, cudaMemcpyHostToDevice,
+                                         c->copy_stream));
+        PB_CUDA(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
+        PB_CUDA(c, trace(c->copy_stream));
+        c->trace_sites.push_back(s0);
+        c->trace_sites.push_back(s1 - s0);
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+        if ((rc = launch_fused_dmma_path(c, s0, s1, false)) != PB_OK) return rc;
+        const int64_t b0 = s0 / 256, b1 = std::min<int64_t>(s1 / 256, nblocks);
+        if (b1 > b0) {
+            pbk::root_combine<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(
+                c->d_site_cat.p, site_exp_of(c), c->ncat, c->d_weights.p, c->have_site_weights ? c->d_site_weights.p : nullptr,
+                c->nsites, c->spad, b0, c->d_per_site.p, c->d_partials.p);
+            c->launches++;
+        }
+        PB_CUDA(c, trace(c->stream));
+    }
+    // (the kernel clamps a state outside the alphabet; the flag makes the call fail instead of returning that value)
+    pbk::validate_tips<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_tips.p, (int64_t)c->ntaxa * c->spad, c->n, c->d_bad.p);
+    c->launches++;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    pbk::final_sum<<<1, 256, 0, c->stream>>>(c->d_partials.p, nblocks, c->d_total.p);
+    c->launches++;
+    if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total, c->d_total.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->h_total + 1, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PB_CUDA(c, trace(c->stream));
+    c->have_tips = true;
+    c->have_masks = false;
+    c->pack_dirty = true;
+    c->tips_checked = true;
+    c->all_dirty = true;
+    c->evaluated = true;
+    c->fresh = true;
+    c->tip_bytes_stale = false;
+    return fetch ? pb_loglik_fetch(c, total, per_site) : PB_OK;
+}
+
 static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool packed2, double* total, double* per_site,
                             bool fetch = true)
 {
@@ -2923,6 +3033,14 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         const int rc0 = want_reduced(c, &reduced);
         c->have_masks = had_masks;
         if (rc0 != PB_OK) return rc0;
+    }
+    {
+        const bool had_masks = c->have_masks;
+        c->have_masks = false;                                    // (the path of plain tips: this call replaces the masks)
+        const bool dense = path_of(c) == PATH_FUSED_DMMA && !packed2 && c->fused_dmma_version == 3 && c->host_chunks > 1 &&
+                           c->spad >= 8192;
+        if (dense) return loglik_host_dense(c, states, ld, total, per_site, fetch);
+        c->have_masks = had_masks;
     }
     if (path_of(c) != PATH_FUSED4 || c->host_chunks == 1 || c->spad < 8192) {
         int rc = packed2 ? pb_set_tips_packed2(c, states, ld) : pb_set_tips(c, states, ld);

@@ -741,6 +741,8 @@ struct FusedDmmaArgs {
     // fused_dmma3 only: tabulated cherries (reduced program; see DenseTab)
     const double* tabV = nullptr; const int* tabK = nullptr; const int4* tabs = nullptr; int ntab = 0;
     int64_t tab_entries = 0;          // entries of all tables of one category (N^2 per cherry, N^3 per three-leaf clade)
+    int64_t cat_stride = 0;           // fused_dmma3: stride of site_cat between categories (0: spad); a launch over a column
+                                      // chunk passes tips / site_cat at its first column and spad = its width
 };
 
 template <int N>
@@ -1041,8 +1043,10 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
             const uint8_t* __restrict__ tips, int64_t tips_ld, int ntaxa, int64_t spad,
             const double* __restrict__ pi, double thr, int shift_at_root, double* __restrict__ site_cat,
             const double* __restrict__ tabV, const int* __restrict__ tabK, const int4* __restrict__ tabs, int ntab,
-            int64_t tab_entries)
+            int64_t tab_entries, int64_t cat_stride)
 {
+    // (spad: the site columns of THIS launch — tips and site_cat point at its first column; tips_ld and cat_stride are the
+    // strides of the whole arrays: a pipelined host evaluation launches the kernel per column chunk)
     using F = Fd3Shape<N>;
     constexpr int M8 = F::M8, K4 = F::K4, MP8 = F::MP8, NW = F::NW, KPP = F::KPP, NPAN = F::NPAN;
     extern __shared__ __align__(128) unsigned char shbytes[];
@@ -1307,7 +1311,7 @@ fused_dmma3(const FusedOp2* __restrict__ prog, int nops, const int* __restrict__
                         sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
                     }
                     if (g == 0)
-                        *reinterpret_cast<double2*>(site_cat + (int64_t)c * spad + s0 + tig * 2) =
+                        *reinterpret_cast<double2*>(site_cat + (int64_t)c * cat_stride + s0 + tig * 2) =
                             make_double2(log(sum[0]) + sc[0].value(), log(sum[1]) + sc[1].value());
                 }
                 if (opw.x & FOP_PUSH_AFTER) to_tile(level_tile(sp++), acc);
@@ -1417,6 +1421,14 @@ inline int fused_dmma3_grid(int n, int sm_count, int64_t spad)
     return (int)std::max<int64_t>(1, std::min<int64_t>((spad / 8 + nw - 1) / nw, (int64_t)sm_count * ctas));
 }
 
+// Site columns one ROUND of the kernel covers when every CTA is resident (each compute warp one 8-site unit).
+inline int64_t fused_dmma3_round_sites(int n, int sm_count)
+{
+    const int nw = n == 20 ? Fd3Shape<20>::NW : Fd3Shape<61>::NW;
+    const int ctas = n == 20 ? Fd3Shape<20>::CTAS : Fd3Shape<61>::CTAS;
+    return (int64_t)sm_count * ctas * nw * 8;
+}
+
 template <int N, int SCALING>
 int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t smem, cudaStream_t stream)
 {
@@ -1426,7 +1438,8 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
     const int grid = fused_dmma3_grid(N, sm_count, a.spad);
     kern<<<grid, (F::NW + 1) * 32, smem, stream>>>(a.prog, a.nops, a.mlist, a.nmat, nslot, a.stack_smem, a.gstack, a.gdepth, a.Ppad,
                                                    a.PTleaf, a.ninner, a.nleaf, a.ncat, a.tips, a.tips_ld, a.ntaxa, a.spad,
-                                                   a.pi, a.thr, a.shift_at_root, a.site_cat, a.tabV, a.tabK, a.tabs, a.ntab, a.tab_entries);
+                                                   a.pi, a.thr, a.shift_at_root, a.site_cat, a.tabV, a.tabK, a.tabs, a.ntab, a.tab_entries,
+                                                   a.cat_stride ? a.cat_stride : a.spad);
     return grid;
 }
 

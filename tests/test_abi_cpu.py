@@ -115,7 +115,7 @@ def test_host_chunk_schedule_invariants():
         spad = int(rng.integers(1, 4000)) * 1024
         chunks = int(rng.integers(1, 65))
         rnd = int(rng.choice([0, 512, 3 * 512, 111 * 512, 444 * 512, 148 * 1024, 7 * 4096]))
-        tail = int(rng.choice([-1, 0, 1000, 60000, 250000, 10**7]))
+        tail = int(rng.choice([-2, -1, 0, 1000, 60000, 250000, 10**7]))
         b = schedule(spad, chunks, tail, rnd)
         assert b[0] == 0 and b[-1] == spad and np.all(np.diff(b) > 0) and np.all(b % 1024 == 0)
         assert 2 <= len(b) <= 65
@@ -129,6 +129,9 @@ def test_host_chunk_schedule_invariants():
     assert list(w[-3:] // 1024 * 1024) == [2 * per_round // 1024 * 1024, per_round // 1024 * 1024, per_round // 1024 * 1024]
     assert np.all(w[1:-3] == 3 * per_round // 1024 * 1024) and w[0] <= 3 * per_round + per_round // 2
     assert list(np.diff(schedule(1000448, 6, -1, 111 * 512))[1:]) == [3 * per_round // 1024 * 1024] * 5
+    # the dense alphabets' ramp-up: 1, 2, 4, ... rounds from the start (c3: 296 CTAs x 11 warps x 8 sites per round)
+    w = np.diff(schedule(200704, 6, -2, 296 * 11 * 8))
+    assert list(w[:2]) == [25600, 51200] and w.sum() == 200704 and len(w) == 3
     for bad in ((1000, 4, 0, 0), (2048, 0, 0, 0), (2048, 4, 0, -5)):
         n = ctypes.c_int(0)
         out = np.zeros(80, np.int64)

@@ -145,3 +145,46 @@ def test_pipelined_schedule_variants(opts):
         assert np.array_equal(per_site3, per_site) and abs(total3 - total) <= 1e-13 * abs(total)
         total4 = ctx.loglik()
         assert abs(total4 - total) <= 1e-13 * abs(total)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,ntaxa,nsites,opts", [("wag", 14, 120_001, {}), ("wag", 14, 120_001, {"host_chunks": 3, "host_tail_sites": -1}),
+                                                      ("wag", 9, 30_000, {"host_chunk_align": 0, "host_chunks": 4}),
+                                                      ("mg94", 10, 60_001, {}), ("wag", 6, 5000, {})])
+def test_pipelined_host_evaluation_dense(model, ntaxa, nsites, opts):
+    """pb_loglik_host on the tensor-core path (20 / 61 states): the alignment crosses in column chunks that are pruned
+    (fused_dmma3 launched per chunk) and reduced behind the copy — the per-site values of the two-step pb_set_tips +
+    pb_loglik to the bit, tips resident afterwards, a state outside the alphabet still an error."""
+    import cases
+    case = cases.make_case("hostd", model, ntaxa, nsites, seed=13)
+    f = case.flat
+    with LikelihoodContext(case.n, nsites, ntaxa) as ctx:
+        ctx.set_tree(f, case.bl)
+        ctx.set_rate_matrix(case.Q, case.pi)
+        ctx.set_root_frequencies(case.pi)
+        ctx.set_tips(case.tips)
+        assert ctx.path_name == "fused_dmma"
+        total, per_site = ctx.loglik(per_site=True)
+        P = ctx.get_pmatrices()
+        chk = 3000
+        expect = C.pruning(case.n, f.root, f.child_ptr, f.child_idx, f.tip_row, P, case.pi,
+                           tips=np.ascontiguousarray(case.tips[:, :chk]))
+        assert np.max(np.abs(per_site[:chk] - expect) / np.abs(expect)) < 1e-9
+        for name, value in opts.items():
+            ctx.set_option(name, value)
+        ctx.set_option("host_trace", 1)
+        for _ in range(2):
+            total2, per_site2 = ctx.loglik_host(case.tips, per_site=True)
+            assert np.array_equal(per_site2, per_site) and abs(total2 - total) <= 1e-13 * abs(total)
+        if nsites >= 8192:
+            chunks, end_ms = ctx.host_trace()
+            assert sum(w for _, w, _, _ in chunks) == (nsites + 1023) // 1024 * 1024
+            assert len(chunks) > 1
+        total3, per_site3 = ctx.loglik(per_site=True)                 # the tips stay resident
+        assert np.array_equal(per_site3, per_site)
+        bad = case.tips.copy()
+        bad[2, nsites - 1] = case.n
+        with pytest.raises(_lib.PhyloB200InvalidArgument):
+            ctx.loglik_host(bad)
+        total4, per_site4 = ctx.loglik_host(case.tips, per_site=True)
+        assert np.array_equal(per_site4, per_site)
