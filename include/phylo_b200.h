@@ -246,6 +246,11 @@ int pb_get_timing(pb_ctx *ctx, double *ms /* [3] */);
  * events of the 64 most recent timed evaluations are kept, so a caller can queue many
  * evaluations without synchronising and read their phase times afterwards. */
 int pb_get_timing_at(pb_ctx *ctx, int back, double *ms /* [3] */);
+/* pb_set_timing(ctx, 2): the time of the DOMINANT kernel alone in the last evaluation — the site-resident pruning kernel of the
+ * 4-state (fused4t) and 20 / 61-state (fused_dmma3) default paths, summed over its launches (*launches, may be null),
+ * from CUDA events around each launch; 0 launches on other paths.  pb_get_timing's pruning phase also holds the
+ * per-evaluation table builders and matrix staging. */
+int pb_get_kernel_timing(pb_ctx *ctx, double *ms, int *launches);
 
 /* How many kernels of this library the context has launched so far. */
 int64_t pb_kernel_launches(const pb_ctx *ctx);

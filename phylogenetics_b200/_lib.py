@@ -33,7 +33,7 @@ EXPORTS = [
     "pb_set_root_frequencies", "pb_set_categories", "pb_set_eigensystem", "pb_set_rate_matrix",
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
-    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_kernel_launches", "pb_graph_replays", "pb_path_name", "pb_transition_matrices_eigen",
+    "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_get_kernel_timing", "pb_kernel_launches", "pb_graph_replays", "pb_path_name", "pb_transition_matrices_eigen",
     "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_debug_dense_reduced_program", "pb_debug_host_trace", "pb_debug_host_schedule", "pb_version",
     "pb_create_sharded", "pb_sharded_destroy", "pb_sharded_last_error", "pb_sharded_ndev", "pb_sharded_ctx",
     "pb_sharded_shard_bounds", "pb_sharded_set_reduce", "pb_sharded_set_mode", "pb_sharded_set_option", "pb_sharded_set_tree",
@@ -105,6 +105,7 @@ def _load():
         "pb_set_timing": (ci, [vp, ci]),
         "pb_get_timing": (ci, [vp, vp]),
         "pb_get_timing_at": (ci, [vp, ci, vp]),
+        "pb_get_kernel_timing": (ci, [vp, vp, vp]),
         "pb_kernel_launches": (i64, [vp]),
         "pb_graph_replays": (i64, [vp]),
         "pb_path_name": (ctypes.c_char_p, [vp]),

@@ -200,6 +200,7 @@ struct pb_ctx {
     std::vector<pbk::DenseTabNodes> dtab_nodes;
     int64_t dtab_entries = 0;              // entries of all tables of one category
     bool dtab_three = false;               // some table is a three-leaf clade
+    int dense_builder_waves = 0;           // option "fused_dmma_builder_waves": waves of blocks of the cherry-table builder (0: default)
     int fused_dmma_triple = 0;             // option "fused_dmma_triple": clades of three leaves (cherry + leaf) as tables, 20 states
                                            // (off by default: with two CTAs per SM cherries alone are faster, 0.560 against 0.568 ms
                                            // at c3, profiles/r03c_sweep_dense_2ctas.jsonl)
@@ -289,6 +290,10 @@ struct pb_ctx {
     cudaEvent_t ev_ring[TIMING_RING][4] = {};
     cudaEvent_t* ev = ev_ring[0];                 // event set of the evaluation being enqueued
     int64_t timed_evals = 0;
+    // ... and of the dominant kernel alone (fused4t / fused_dmma3): one event pair per launch of the last timed evaluation
+    std::vector<cudaEvent_t> kev;
+    size_t kev_n = 0;
+    bool kernel_timing = false;                   // pb_set_timing(ctx, 2)
 };
 
 namespace {
@@ -1365,6 +1370,19 @@ int want_reduced(pb_ctx* c, bool* yes)
     return PB_OK;
 }
 
+// Timing on: an event on the context's stream before / after a launch of the dominant kernel (pb_get_kernel_timing).
+cudaError_t kernel_mark(pb_ctx* c)
+{
+    if (!c->timing || !c->kernel_timing || c->capturing) return cudaSuccess;
+    if (c->kev_n == c->kev.size()) {
+        cudaEvent_t e;
+        cudaError_t err = cudaEventCreate(&e);
+        if (err != cudaSuccess) return err;
+        c->kev.push_back(e);
+    }
+    return cudaEventRecord(c->kev[c->kev_n++], c->stream);
+}
+
 template <int BLOCK, int SPT, int MINB = 0, bool MASKS = false>
 int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t site0, int64_t site1)
 {
@@ -1386,12 +1404,14 @@ int launch_fused4t_variant(pb_ctx* c, int cat0, int ncats, int slot0, int64_t si
     gx = std::max<int64_t>(1, std::min<int64_t>(gx, ntiles));
     // (the device-side flag of the table builder decides between the kernel's two bodies: exponents folded into the
     // table vectors, or gathered beside them; no tables or option "fused_fold" off: the general body)
+    PB_CUDA(c, kernel_mark(c));
     kern<<<dim3((unsigned)gx, ncats), BLOCK, smem, c->stream>>>(
         (int)c->rprog.size(), std::max(c->rstack, 1), c->d_P.p, c->d_rleaf_nodes.p, (int)c->rleaf_nodes.size(), c->nnodes,
         cat0, slot0, (int)c->rmat_nodes.size(), c->d_packed.p, c->spad, tile0, ntiles, c->d_pi.p, c->threshold,
         c->shift_at_root, c->d_cherry_v.p, c->d_cherry_k.p, c->rntab, c->d_site_cat.p, c->d_site_exp.p,
         c->r_radix, (1u << c->r_tipbits) - 1u, c->d_mask_set.p,
         c->rclades.empty() ? nullptr : c->d_cherry_k.p + (size_t)c->ncat * c->rntab);
+    PB_CUDA(c, kernel_mark(c));
     c->launches++;
     return PB_OK;
 }
@@ -1773,15 +1793,18 @@ int launch_fused_dmma_path(pb_ctx* c, int64_t site0 = 0, int64_t site1 = -1, boo
                 PB_CUDA(c, c->d_dtabK.ensure(entries + 1));                 // (+ the flag "an exponent was not folded")
                 PB_CUDA(c, cudaMemsetAsync(c->d_dtabK.p + entries, (c->fused_fold && c->fused_pow2) ? 0 : 0xff, sizeof(int), c->stream));
                 pbk::launch_fdmma3_build_cherries(n, c->d_P.p, c->nnodes, c->d_dtabs.p, c->d_dtab_nodes.p, ntab_d, c->dtab_entries,
-                                                  c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream);
+                                                  c->dtab_three, c->ncat, c->threshold, c->d_dtabV.p, c->d_dtabK.p, c->stream,
+                                                  c->sm_count, c->dense_builder_waves);
                 c->launches++;
             }
             a.tabV = c->d_dtabV.p; a.tabK = c->d_dtabK.p; a.tabs = c->d_dtabs.p; a.ntab = ntab_d;
             a.tab_entries = c->dtab_entries;
         }
         if (site1 > site0) {
+            PB_CUDA(c, kernel_mark(c));
             if (pbk::launch_fused_dmma3(n, c->fused_pow2 != 0, a, nslot, c->sm_count, smem, c->stream) < 1)
                 return fail(c, PB_ERR_CUDA, "fused_dmma3 launch configuration failed");
+            PB_CUDA(c, kernel_mark(c));
             c->launches++;
         }
         return PB_OK;
@@ -2149,6 +2172,7 @@ void pb_destroy(pb_ctx* c)
     for (cudaEvent_t e : c->pack_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prune_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->trace_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     if (c->ev_root_done) cudaEventDestroy(c->ev_root_done);
     if (c->ev_lane_done) cudaEventDestroy(c->ev_lane_done);
     if (c->pack_stream) { cudaStreamSynchronize(c->pack_stream); cudaStreamDestroy(c->pack_stream); }
@@ -2844,7 +2868,7 @@ int pb_loglik_enqueue(pb_ctx* c)
         if (rc != PB_OK) return rc;
         if (done) return PB_OK;
     }
-    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; c->kev_n = 0; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     int rc = build_pmatrices(c);
     if (rc != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -2939,7 +2963,7 @@ static int loglik_host_dense(pb_ctx* c, const uint8_t* states, int64_t ld, doubl
     if (rc != PB_OK) return rc;
     if (!c->copy_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if (!c->ev_start) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; c->kev_n = 0; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     if ((rc = build_pmatrices(c)) != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     const int64_t nblocks = (c->nsites + 255) / 256;
@@ -3060,7 +3084,7 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         PB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->chunk_events.push_back(e);
     }
-    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
+    if (c->timing) { c->ev = c->ev_ring[c->timed_evals++ % pb_ctx::TIMING_RING]; c->kev_n = 0; PB_CUDA(c, cudaEventRecord(c->ev[0], c->stream)); }
     if ((rc = build_pmatrices(c)) != PB_OK) return rc;
     if (c->timing) PB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     const int64_t nblocks = (c->nsites + 255) / 256;
@@ -3445,6 +3469,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
         c->fused_dmma = value != 0.0;
     } else if (k == "fused_dmma_cherry") {
         c->fused_dmma_cherry = iv != 0;
+    } else if (k == "fused_dmma_builder_waves") {
+        if (iv < 0 || iv > 8) return fail(c, PB_ERR_INVALID_ARG, "fused_dmma_builder_waves must be in 0..8");
+        c->dense_builder_waves = iv;
     } else if (k == "fused_dmma_triple") {
         c->fused_dmma_triple = iv != 0;
         c->dense_reduced_built = false;
@@ -3516,6 +3543,7 @@ int pb_set_timing(pb_ctx* c, int on)
         for (auto& set : c->ev_ring)
             for (int i = 0; i < 4; i++) PB_CUDA(c, cudaEventCreate(&set[i]));
     c->timing = on != 0;
+    c->kernel_timing = on == 2;          // (2: also an event pair around every launch of the dominant kernel)
     return PB_OK;
 }
 
@@ -3536,6 +3564,23 @@ int pb_get_timing_at(pb_ctx* c, int back, double* ms)
 }
 
 int pb_get_timing(pb_ctx* c, double* ms) { return pb_get_timing_at(c, 0, ms); }
+
+int pb_get_kernel_timing(pb_ctx* c, double* ms, int* launches)
+{
+    PB_ENTER(c);
+    if (!c->timing || !c->kernel_timing || c->timed_evals == 0 || !ms)
+        return fail(c, PB_ERR_STATE, "kernel timing is off (pb_set_timing(ctx, 2)) or nothing was evaluated");
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < c->kev_n; i += 2) {
+        float t = 0.f;
+        PB_CUDA(c, cudaEventSynchronize(c->kev[i + 1]));
+        PB_CUDA(c, cudaEventElapsedTime(&t, c->kev[i], c->kev[i + 1]));
+        sum += t;
+    }
+    *ms = sum;
+    if (launches) *launches = (int)(c->kev_n / 2);
+    return PB_OK;
+}
 
 int64_t pb_kernel_launches(const pb_ctx* c) { return c ? c->launches : 0; }
 

@@ -1445,11 +1445,15 @@ int launch_fused_dmma3_n(const FusedDmmaArgs& a, int nslot, int sm_count, size_t
 
 inline void launch_fdmma3_build_cherries(int n, const double* P, int nnodes, const int4* tabs, const DenseTabNodes* tab_nodes, int ntab,
                                          int64_t tab_entries, bool any_three, int ncat, double thr, double* tabV, int* tabK,
-                                         cudaStream_t stream)
+                                         cudaStream_t stream, int sm_count = 148, int waves = 0)
 {
     if (ntab < 1) return;
-    // a block per (table, category, slice): enough slices for ~2 blocks per SM, 4 entries per step
-    const int slices = std::max(4, std::min(64, (2 * 148 + ntab * ncat - 1) / (ntab * ncat)));
+    // A block per (table, category, slice), 4 entries per step.  The slices fill WHOLE waves of the resident blocks and
+    // never spill into another one: at 61 states a block holds a matrix row per thread (164 registers, one block per
+    // SM), and 300 blocks on 148 SMs ran as three waves of which the last held four blocks (profiles/r02o_*).
+    const int per_sm = n == 20 ? 3 : 1;
+    if (waves < 1) waves = 1;                                   // (c4: one wave 0.737 ms, two 0.744, three 0.750: profiles/r03l_*)
+    const int slices = std::max(1, std::min(64, waves * per_sm * sm_count / (ntab * ncat)));
     const dim3 grid(ntab, ncat, slices);
     const size_t smem = ((any_three ? 3 : 2) * (size_t)n * n + (any_three ? (size_t)n * 65 : 0) + 4 * 64 + 8) * sizeof(double);
     if (n == 20) {

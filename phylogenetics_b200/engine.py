@@ -262,7 +262,8 @@ class LikelihoodContext:
         self._ck(lib.pb_set_option(self._ctx, name.encode(), float(value)))
 
     def set_timing(self, on=True):
-        self._ck(lib.pb_set_timing(self._ctx, int(bool(on))))
+        """on = 2: also time the dominant kernel alone (get_kernel_timing)."""
+        self._ck(lib.pb_set_timing(self._ctx, 2 if on == 2 else int(bool(on))))
 
     def get_timing(self, back=0):
         """(pmat_ms, pruning_ms, root_ms) of the last evaluation (or the one `back` evaluations before
@@ -270,6 +271,12 @@ class LikelihoodContext:
         ms = np.empty(3)
         self._ck(lib.pb_get_timing_at(self._ctx, int(back), ms.ctypes.data))
         return tuple(float(x) for x in ms)
+
+    def get_kernel_timing(self):
+        """pb_get_kernel_timing: (ms, launches) of the dominant pruning kernel alone in the last evaluation."""
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        self._ck(lib.pb_get_kernel_timing(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def total_as_cuda_array(self):
         """The device-resident total (1 double) as an object torch.as_tensor can wrap without a

@@ -743,3 +743,21 @@ def test_table_exponents_that_do_not_fold(masked, every_category):
             t2, p2 = ctx.loglik(per_site=True)
             assert ctx.path_name == "fused4"
             assert t2 == total and np.array_equal(p2, per_site), (name, value)
+
+
+def test_kernel_only_timing():
+    """pb_set_timing(ctx, 2) + pb_get_kernel_timing: the dominant kernel alone, per launch, inside the pruning phase."""
+    for model, ntaxa, nsites, ncat in (("gtr", 40, 60000, 4), ("wag", 12, 20000, 1)):
+        case = cases.make_case("ktime", model, ntaxa, nsites, ncat=ncat, seed=3)
+        with run_ctx(case, "eigen" if model == "gtr" else "expm") as ctx:
+            ctx.set_timing(True)
+            total = ctx.loglik()
+            with pytest.raises(_lib.PhyloB200Error):
+                ctx.get_kernel_timing()                     # kernel timing is off
+            ctx.set_timing(2)
+            for _ in range(3):
+                assert ctx.loglik() == total
+            k_ms, launches = ctx.get_kernel_timing()
+            phases = ctx.get_timing()
+            assert launches >= 1 and 0.0 < k_ms <= phases[1] * 1.001
+            ctx.set_timing(True)
