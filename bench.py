@@ -646,6 +646,15 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peaks, peak_kind = measured_peaks()
+    try:        # the FP64 peaks of THIS device, measured now (pb_measure_fp64_peak), beside the constants the fractions use
+        from phylogenetics_b200.engine import measure_fp64_peak
+        dfma_live, dmma_live = measure_fp64_peak(local_rank)
+        fp64_live = {"dfma_tflops": dfma_live, "dmma_tflops": dmma_live,
+                     "constants_used": {"dfma_tflops": FP64_DFMA_PEAK_TFLOPS, "dmma_tflops": FP64_DMMA_PEAK_TFLOPS},
+                     "note": "register-resident dependent chains on every SM (8 per thread, 4 blocks of 256 threads per SM), best of "
+                             "three repetitions; the roofline fractions use the constants (measured the same way in round 1)"}
+    except Exception as e:
+        fp64_live = {"error": repr(e)}
     units = world * nsites * ninternal * args.steps
     value = units / t_max
     prune_avg_ms = float(phases[:, 1].mean())
@@ -705,6 +714,7 @@ def run_ours(args, rank, world, local_rank):
                    "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
                    "parity_gate": gate},
         "roofline": roof,
+        "fp64_peaks_live": fp64_live,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "reps_ms_per_step": e2e_reps[-1], "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": 8, "steps": e2e_steps, "call": e2e_call,
                 "byte_per_site": {"value": e2e_bytes_val, "ms_per_step": e2e_bytes_ms,

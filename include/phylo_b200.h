@@ -394,6 +394,11 @@ int pb_debug_host_trace(pb_ctx *ctx, double *out, int cap);
 int pb_debug_host_schedule(int64_t spad, int host_chunks, int64_t host_tail_sites, int64_t round_sites, int64_t *bounds,
                            int cap, int *nbounds);
 
+/* The device's FP64 peak, measured: kind 0 = DFMA (register-resident dependent chains, 2 flops per FMA), kind 1 = the
+ * FP64 tensor-core shape mma.sync.m8n8k4 (DMMA.8x8x4, 512 flops per warp instruction); ~10 ms.  bench.py reports them
+ * beside the constants its roofline fractions use. */
+int pb_measure_fp64_peak(int device, int kind, double *tflops);
+
 const char *pb_version(void);
 
 #ifdef __cplusplus

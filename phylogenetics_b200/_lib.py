@@ -34,7 +34,7 @@ EXPORTS = [
     "pb_set_rate_matrix_general", "pb_set_pmatrices", "pb_loglik", "pb_loglik_host", "pb_loglik_enqueue",
     "pb_loglik_fetch", "pb_result_device_ptrs", "pb_get_clv", "pb_conditional_simulation", "pb_get_pmatrices",
     "pb_set_option", "pb_set_timing", "pb_get_timing", "pb_get_timing_at", "pb_get_kernel_timing", "pb_kernel_launches", "pb_graph_replays", "pb_path_name", "pb_transition_matrices_eigen",
-    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_debug_dense_reduced_program", "pb_debug_host_trace", "pb_debug_host_schedule", "pb_version",
+    "pb_transition_matrices_expm", "pb_host_reversible_eigensystem", "pb_debug_fused_program", "pb_debug_reduced_program", "pb_debug_dense_reduced_program", "pb_debug_host_trace", "pb_debug_host_schedule", "pb_measure_fp64_peak", "pb_version",
     "pb_create_sharded", "pb_sharded_destroy", "pb_sharded_last_error", "pb_sharded_ndev", "pb_sharded_ctx",
     "pb_sharded_shard_bounds", "pb_sharded_set_reduce", "pb_sharded_set_mode", "pb_sharded_set_option", "pb_sharded_set_tree",
     "pb_sharded_set_branch_lengths", "pb_sharded_update_branch_length", "pb_sharded_set_root_frequencies",
@@ -139,6 +139,7 @@ def _load():
         "pb_debug_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, vp, ci]),
         "pb_debug_dense_reduced_program": (ci, [ci, ci, vp, vp, vp, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp]),
         "pb_debug_host_trace": (ci, [vp, vp, ci]),
+        "pb_measure_fp64_peak": (ci, [ci, ci, vp]),
         "pb_debug_host_schedule": (ci, [i64, ci, i64, i64, vp, ci, vp]),
         "pb_version": (ctypes.c_char_p, []),
     }

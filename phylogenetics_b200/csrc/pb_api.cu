@@ -2076,6 +2076,45 @@ int run_root_reduction(pb_ctx* c)
 }  // namespace
 
 // ===========================================================================
+
+// ---- FP64 peak probes (pb_measure_fp64_peak): the denominators of the roofline fractions, measured on the device the
+// benchmark runs on.  Register-resident dependent chains, 8 per thread: DFMA, or the native FP64 tensor-core shape.
+namespace pbk {
+__global__ void __launch_bounds__(256) fp64_peak_dfma(double* out, int iters)
+{
+    double c[8];
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) fp64_peak_dmma(double* out, int iters)
+{
+    double c[8][2];
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace pbk
+
 extern "C" {
 
 const char* pb_version(void) { return "phylo_b200 0.1 (sm_100a)"; }
@@ -3579,6 +3618,39 @@ int pb_get_kernel_timing(pb_ctx* c, double* ms, int* launches)
     }
     *ms = sum;
     if (launches) *launches = (int)(c->kev_n / 2);
+    return PB_OK;
+}
+
+int pb_measure_fp64_peak(int device, int kind, double* tflops)
+{
+    if (!tflops || (kind != 0 && kind != 1)) return PB_ERR_INVALID_ARG;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PB_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 20000;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return PB_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {                  // (the first repetition warms the clocks up)
+        cudaEventRecord(e0);
+        if (kind == 0) pbk::fp64_peak_dfma<<<blocks, threads>>>(out, iters);
+        else pbk::fp64_peak_dmma<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (err != cudaSuccess || !(best > 0.f)) return PB_ERR_CUDA;
+    // flops per thread and iteration: 8 chains x 2 (one FMA), or 8 chains x 512 / 32 (an 8 x 8 x 4 MMA is 512 flops per warp)
+    const double per_thread_iter = kind == 0 ? 16.0 : 8.0 * 512.0 / 32.0;
+    *tflops = per_thread_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     return PB_OK;
 }
 

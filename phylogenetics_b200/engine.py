@@ -497,6 +497,18 @@ def pack_tips2(tips):
     return (t[:, :, 0] | (t[:, :, 1] << 2) | (t[:, :, 2] << 4) | (t[:, :, 3] << 6)).astype(np.uint8)
 
 
+def measure_fp64_peak(device=0):
+    """pb_measure_fp64_peak: (DFMA TFLOP/s, DMMA TFLOP/s) of the device, measured now."""
+    out = []
+    for kind in (0, 1):
+        v = ctypes.c_double()
+        rc = lib.pb_measure_fp64_peak(int(device), kind, ctypes.byref(v))
+        if rc != 0:
+            raise _lib.PhyloB200Error(rc, "pb_measure_fp64_peak failed")
+        out.append(v.value)
+    return tuple(out)
+
+
 def device_local_cpus(device=0):
     """CPUs of the NUMA node the GPU `device` hangs off (sysfs local_cpulist of its PCI function), or None when the
     topology cannot be read.  Host buffers the copy engine reads should live on that node: on a two-socket box a pinned

@@ -93,3 +93,12 @@ def test_not_reversible_is_refused_by_the_eigen_path():
         with pytest.raises(_lib.PhyloB200Error) as e:
             ctx.set_rate_matrix(Qn, np.full(4, 0.25))
         assert e.value.code == _lib.PB_ERR_NUMERIC
+
+
+@pytest.mark.gpu
+def test_fp64_peak_probe():
+    """pb_measure_fp64_peak: the DFMA and FP64 tensor-core peaks of the device are measured in the same range as the
+    constants bench.py's roofline fractions use (34.8 / 36.8 TFLOP/s on a B200 at 1.965 GHz)."""
+    from phylogenetics_b200.engine import measure_fp64_peak
+    dfma, dmma = measure_fp64_peak(0)
+    assert 25.0 < dfma < 40.0 and 25.0 < dmma < 40.0, (dfma, dmma)
