@@ -912,25 +912,44 @@ __device__ __forceinline__ void tab_gather(const double* __restrict__ tv, const 
 // MASKS = true: a tip is one of the `radix` distinct state sets the alignment contains (code 0..radix-1; pb_set_tip_masks
 // scans them), a tabulated clade of k tips has radix^k entries indexed in mixed radix, and a loose tip's column is the sum
 // of the set's columns of P (dgemv against the 0/1 indicator, ascending j).  The empty set is a missing observation:
-// "None".  None is carried in memory (table entries, leaf columns, the stack) as v[0] == -1 and in registers as one flag
-// per site; the reference's rule (Missing_values.maybe_sv_mul :146-150, Ambiguous.pruning :289-296) is
+// "None".  None is carried in memory (table entries, leaf columns, the stack) by a marker, v[0] == -1, and in registers
+// as one flag per site (below); the reference's rule (Missing_values.maybe_sv_mul :146-150, Ambiguous.pruning :289-296) is
 //     None x None = None,  None x v = v (NO shift),  v x w = SV.mul v w (shift),
 // and the branch matrix of a None subtree is never applied; a site with no observation at all has log-likelihood 0.
 constexpr double NONE_MARK = -1.0;
+// In MEMORY a None vector is (-1, 1, 1, 1): the marker in component 0 and ones elsewhere.  In REGISTERS a None operand is
+// the vector of ones plus its flag — x * 1.0 is x exactly, so the rule above is a plain product and a flag AND, without a
+// select per component: is_none reads the marker (an integer compare on the high word) and turns it into the 1.0 it
+// stands for (one select; the low words of -1.0 and 1.0 are both zero); a matrix-vector product of a None accumulator
+// (P . ones is only approximately ones) is put back by keep_none.
+template <bool MASKS>
+__device__ __forceinline__ bool is_none(double (&x)[4])
+{
+    if constexpr (MASKS) {
+        const int hi = __double2hiint(x[0]);
+        const bool none = hi == (int)0xBFF00000;
+        x[0] = __hiloint2double(none ? 0x3FF00000 : hi, __double2loint(x[0]));
+        return none;
+    } else
+        return false;
+}
 
 template <bool MASKS>
-__device__ __forceinline__ bool is_none(const double (&x)[4]) { return MASKS && x[0] == NONE_MARK; }
+__device__ __forceinline__ void keep_none(double (&y)[4], bool none)
+{
+    if constexpr (MASKS) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = none ? 1.0 : y[i];
+    }
+}
 
-// v = a (x) b under the rule above; returns whether the product was formed (only then SV.mul shifts)
+// v = a (x) b under the rule above (operands normalised as described); returns whether the product was formed (only
+// then SV.mul shifts)
 template <bool MASKS>
 __device__ __forceinline__ bool combine4(double (&v)[4], bool& nv, const double (&a)[4], bool na, const double (&b)[4], bool nb)
 {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        double r = a[i] * b[i];
-        if (MASKS) { r = nb ? a[i] : r; r = na ? b[i] : r; }
-        v[i] = r;
-    }
+    for (int i = 0; i < 4; i++) v[i] = a[i] * b[i];
     nv = MASKS && na && nb;
     return !MASKS || !(na || nb);
 }
@@ -1013,7 +1032,7 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
         auto column = [&](int off, int tip, double (&t)[4]) {   // P[leaf] . indicator(set): set columns added, ascending
             const double* lf = Pc + off;
             const unsigned m = sets[tip];
-            if (m == 0) { t[0] = NONE_MARK; t[1] = t[2] = t[3] = 0.0; return; }
+            if (m == 0) { t[0] = NONE_MARK; t[1] = t[2] = t[3] = 1.0; return; }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 double a = 0.0;
@@ -1034,6 +1053,7 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
             if (code == FOP_APPLY_MUL_TIP) {
                 double y[4], t[4];
                 matvec4(Pc + o.offA, v, y);
+                keep_none<true>(y, nv);
                 column(o.offB, tB, t);
                 if (combine4<true>(v, nv, y, nv, t, is_none<true>(t))) shift_pow2(v, sc, thr_hi, true);
             } else if (code == FOP_ACC_POP) {
@@ -1042,6 +1062,8 @@ build_clade_tables_masks(const FusedOp2* __restrict__ prog, const CladeTab* __re
                 const bool nb = is_none<true>(stk[sp]);
                 matvec4(Pc + o.offA, v, y);
                 matvec4(Pc + o.offB, stk[sp], z);
+                keep_none<true>(y, nv);
+                keep_none<true>(z, nb);
                 if (combine4<true>(v, nv, y, nv, z, nb)) shift_pow2(v, sc, thr_hi, true);
             } else if (code == FOP_TIP_TIP) {
                 double a[4], b[4];
@@ -1123,7 +1145,7 @@ __device__ __forceinline__ void fused4t_body(FUSED4T_PARAMS)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     if ((m >> j) & 1u) a += lf[j];
-                shP[idx] = m ? a : (i == 0 ? NONE_MARK : 0.0);
+                shP[idx] = m ? a : (i == 0 ? NONE_MARK : 1.0);
             }
         }
     }
@@ -1170,6 +1192,7 @@ __device__ __forceinline__ void fused4t_body(FUSED4T_PARAMS)
                 for (int q = 0; q < SPT; q++) {
                     double y[4];
                     matvec4c(cbase + offA, v[q], y);
+                    keep_none<MASKS>(y, nv[q]);
                     const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], b[q], is_none<MASKS>(b[q]));
                     sc[q].e += eb[q];
                     shift_pow2(v[q], sc[q], thr_hi, on);
@@ -1181,6 +1204,7 @@ __device__ __forceinline__ void fused4t_body(FUSED4T_PARAMS)
                     double y[4], t[4];
                     lds_col4(pbase + 8u * (unsigned)offB, (int)((unsigned)(cur[q] >> shB) & tip_mask), t);
                     matvec4c(cbase + offA, v[q], y);
+                    keep_none<MASKS>(y, nv[q]);
                     const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], t, is_none<MASKS>(t));
                     shift_pow2(v[q], sc[q], thr_hi, on);
                 }
@@ -1210,6 +1234,8 @@ __device__ __forceinline__ void fused4t_body(FUSED4T_PARAMS)
                     const bool nb = is_none<MASKS>(x);
                     matvec4c(cbase + offA, v[q], y);
                     matvec4c(cbase + offB, x, z);
+                    keep_none<MASKS>(y, nv[q]);
+                    keep_none<MASKS>(z, nb);
                     const bool on = combine4<MASKS>(v[q], nv[q], y, nv[q], z, nb);
                     shift_pow2(v[q], sc[q], thr_hi, on);
                 }
