@@ -231,7 +231,8 @@ int pb_get_pmatrices(pb_ctx *ctx, double *P);
  * "graph": see pb_graph_replays.  "host_chunks" (default 6): column chunks of pb_loglik_host*, whole rounds of the
  *   persistent blocks laid from the end of the alignment unless "host_chunk_align" is 0; "host_tail_sites": sites of
  *   the short last chunk the schedule ramps down to (0 (default): one round; -1: none); "host_side_streams" (1
- *   (default): chunks alternate between two streams; 0: everything on the context's stream); "host_lead_cats": rate
+ *   (default): chunks alternate between "host_lanes" streams (2..4, default 2: three and four measured equal); 0:
+ *   everything on the context's stream); "host_lead_cats": rate
  *   categories pruned chunk by chunk behind a 2-bit packed copy (default: all; the others run once over all the
  *   sites); "host_trace": see pb_debug_host_trace; "fused_const_group" (1 (default): the constant bank is loaded for
  *   as many categories as it holds).  Unknown names are PB_ERR_INVALID_ARG. */

@@ -249,9 +249,10 @@ struct pb_ctx {
 
     // pipelined host evaluation (pb_loglik_host)
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t pack_stream = nullptr, root_stream = nullptr;   // side streams: a chunk is packed while the one before it is pruned
-    std::vector<cudaEvent_t> pack_events, prune_events;
-    cudaEvent_t ev_root_done = nullptr, ev_lane_done = nullptr;
+    cudaStream_t lane_streams[4] = {};  // the lanes of the pipelined host evaluation (option "host_lanes" of them)
+    cudaEvent_t lane_events[4] = {};
+    int host_lanes = 2;
+    cudaEvent_t ev_root_done = nullptr;
     bool bank_held = false;             // inside the lanes of a pipelined host evaluation (launch_fused4t)
     int host_side_streams = 1;          // option "host_side_streams": 0 = pack, prune and reduce in one stream
     bool tip_bytes_stale = false;       // the alignment is resident 2-bit packed (d_tips2); d_tips is expanded on demand
@@ -2208,14 +2209,13 @@ void pb_destroy(pb_ctx* c)
     for (auto& set : c->ev_ring)
         for (int i = 0; i < 4; i++) if (set[i]) cudaEventDestroy(set[i]);
     for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
-    for (cudaEvent_t e : c->pack_events) cudaEventDestroy(e);
-    for (cudaEvent_t e : c->prune_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->trace_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
     if (c->ev_root_done) cudaEventDestroy(c->ev_root_done);
-    if (c->ev_lane_done) cudaEventDestroy(c->ev_lane_done);
-    if (c->pack_stream) { cudaStreamSynchronize(c->pack_stream); cudaStreamDestroy(c->pack_stream); }
-    if (c->root_stream) { cudaStreamSynchronize(c->root_stream); cudaStreamDestroy(c->root_stream); }
+    for (int l = 0; l < 4; l++) {
+        if (c->lane_events[l]) cudaEventDestroy(c->lane_events[l]);
+        if (c->lane_streams[l]) { cudaStreamSynchronize(c->lane_streams[l]); cudaStreamDestroy(c->lane_streams[l]); }
+    }
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     c->d_lv_nodes.release(); c->d_lv_children.release(); c->d_fprog.release();
@@ -3197,24 +3197,24 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
     // Nothing of this depends on the alignment: matrices for the constant bank and the clade tables are built while
     // the first chunk is on its way.
     if (reduced && (rc = launch_fused4t(c, 0, 0, true, 0, want_cats)) != PB_OK) return rc;
-    cudaStream_t lanes[2] = {c->stream, c->stream};
+    const int nlanes = side ? std::max(2, std::min(c->host_lanes, 4)) : 1;
+    cudaStream_t lanes[4] = {c->stream, c->stream, c->stream, c->stream};
     if (side) {
-        if (!c->pack_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
-        if (!c->root_stream) PB_CUDA(c, cudaStreamCreateWithFlags(&c->root_stream, cudaStreamNonBlocking));
         if (!c->ev_root_done) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_root_done, cudaEventDisableTiming));
-        if (!c->ev_lane_done) PB_CUDA(c, cudaEventCreateWithFlags(&c->ev_lane_done, cudaEventDisableTiming));
-        lanes[0] = c->pack_stream;
-        lanes[1] = c->root_stream;
+        for (int l = 0; l < nlanes; l++) {
+            if (!c->lane_streams[l]) PB_CUDA(c, cudaStreamCreateWithFlags(&c->lane_streams[l], cudaStreamNonBlocking));
+            if (!c->lane_events[l]) PB_CUDA(c, cudaEventCreateWithFlags(&c->lane_events[l], cudaEventDisableTiming));
+            lanes[l] = c->lane_streams[l];
+        }
         PB_CUDA(c, cudaEventRecord(c->ev_root_done, c->stream));       // (matrices, tables, the constant bank; earlier work)
-        PB_CUDA(c, cudaStreamWaitEvent(lanes[0], c->ev_root_done, 0));
-        PB_CUDA(c, cudaStreamWaitEvent(lanes[1], c->ev_root_done, 0));
+        for (int l = 0; l < nlanes; l++) PB_CUDA(c, cudaStreamWaitEvent(lanes[l], c->ev_root_done, 0));
     }
     cudaStream_t const main_stream = c->stream;
     struct Restore { pb_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->bank_held = false; } } restore{c, main_stream};
     for (int k = 0; k < nchunks; k++) {
         const int64_t s0 = bounds[k], s1 = bounds[k + 1];
         const int64_t w = std::min(s1, c->nsites) - s0;
-        cudaStream_t lane = lanes[k & 1];
+        cudaStream_t lane = lanes[k % nlanes];
         if (w > 0 && !packed2)
             PB_CUDA(c, cudaMemcpy2DAsync(c->d_tips.p + s0, c->spad, states + s0, ld, w, c->ntaxa,
                                          cudaMemcpyHostToDevice, c->copy_stream));
@@ -3257,10 +3257,10 @@ static int loglik_host_impl(pb_ctx* c, const uint8_t* states, int64_t ld, bool p
         PB_CUDA(c, trace(lane));
     }
     if (side) {
-        PB_CUDA(c, cudaEventRecord(c->ev_root_done, lanes[0]));
-        PB_CUDA(c, cudaEventRecord(c->ev_lane_done, lanes[1]));
-        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_root_done, 0));
-        PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_lane_done, 0));
+        for (int l = 0; l < nlanes; l++) {
+            PB_CUDA(c, cudaEventRecord(c->lane_events[l], lanes[l]));
+            PB_CUDA(c, cudaStreamWaitEvent(c->stream, c->lane_events[l], 0));
+        }
         if (hold_bank) {
             PB_CUDA(c, cudaEventRecord(g_const_event[c->device & 63], c->stream));
             bank_lock.unlock();
@@ -3553,6 +3553,9 @@ int pb_set_option(pb_ctx* c, const char* name, double value)
     } else if (k == "host_tail_sites") {
         if (iv < -1) return fail(c, PB_ERR_INVALID_ARG, "host_tail_sites must be >= -1");
         c->host_tail_sites = iv;
+    } else if (k == "host_lanes") {
+        if (iv < 2 || iv > 4) return fail(c, PB_ERR_INVALID_ARG, "host_lanes must be in 2..4");
+        c->host_lanes = iv;
     } else if (k == "host_side_streams") {
         c->host_side_streams = iv != 0;
     } else if (k == "host_trace") {
