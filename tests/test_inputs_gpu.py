@@ -110,7 +110,8 @@ def test_two_bit_packed_host_alignment(nsites, chunks):
 @pytest.mark.gpu
 @pytest.mark.parametrize("opts", [{}, {"host_side_streams": 0}, {"host_chunks": 12}, {"host_tail_sites": -1},
                                   {"host_tail_sites": 200000, "host_chunks": 3}, {"host_chunk_align": 0, "host_chunks": 5},
-                                  {"host_lead_cats": 1}, {"fused_const_keep": 0}, {"fused_const_cats": 1}])
+                                  {"host_lead_cats": 1}, {"fused_const_keep": 0}, {"fused_const_cats": 1},
+                                  {"host_lanes": 3}, {"host_lanes": 4, "host_chunks": 10}])
 def test_pipelined_schedule_variants(opts):
     """The column-chunk schedule of the pipelined host evaluation (whole rounds of the persistent blocks, laid from the
     end with a short last chunk; chunks alternating between two lanes; the 2-bit transpose kernel): every schedule gives

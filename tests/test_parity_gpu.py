@@ -265,6 +265,10 @@ def test_fused_dmma(model, ntaxa, nsites, ncat, tree_kind, version):
             check(per_site5, total5, expect)
             np.testing.assert_allclose(per_site5, per_site, rtol=1e-12)
             ctx.set_option("fused_dmma_cherry", 1)
+            ctx.set_option("fused_dmma_builder_waves", 3)       # the table builder cut into more, shorter blocks: same tables
+            total7, per_site7 = ctx.loglik(per_site=True)
+            assert total7 == total and np.array_equal(per_site7, per_site)
+            ctx.set_option("fused_dmma_builder_waves", 0)
             ctx.set_option("fused_dmma_triple", 1)              # three-leaf clades as tables too (20 states; off by default)
             total6, per_site6 = ctx.loglik(per_site=True)
             check(per_site6, total6, expect)
